@@ -1,0 +1,195 @@
+// Internal definitions shared by the engine's translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "aefft.h"
+
+namespace aefft {
+
+void set_error(const char* fmt, ...);
+
+#define AE_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      aefft::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return AEFFT_ERR_CUDA;                                                                  \
+    }                                                                                         \
+  } while (0)
+
+#define AE_TRY(call)            \
+  do {                          \
+    int r__ = (call);           \
+    if (r__ != AEFFT_OK) return r__; \
+  } while (0)
+
+#define AE_ARG(cond)                                                        \
+  do {                                                                      \
+    if (!(cond)) {                                                          \
+      aefft::set_error("%s:%d bad argument: %s", __FILE__, __LINE__, #cond); \
+      return AEFFT_ERR_ARG;                                                 \
+    }                                                                       \
+  } while (0)
+
+// Grow-only device scratch slots keyed by name: the reference cudaMallocs/frees inside every call
+// (backproplib.cu:150-151, fft_backproplib.cu:1394-1427); here workspaces persist in the ctx.
+struct Scratch {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+// One record per kernel launch while profiling is on (aefft_profile_enable): CUDA events on the launching stream
+// plus the ALGORITHMIC work of that launch (flops, bytes), which bench.py turns into the roofline numbers.
+struct ProfRec {
+  const char* name;
+  cudaEvent_t e0, e1;
+  double flops, bytes;
+};
+
+}  // namespace aefft
+
+struct aefft_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int64_t launches = 0;
+  bool profiling = false;
+  std::vector<aefft::ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t get_event();
+  std::map<std::string, aefft::Scratch> scratch;
+  std::map<std::string, aefft::Scratch> pinned;
+
+  int get(const char* name, size_t bytes, void** out);         // device scratch
+  int get_pinned(const char* name, size_t bytes, void** out);  // pinned host staging
+  template <class T>
+  int getT(const char* name, size_t n, T** out) {
+    return get(name, n * sizeof(T), (void**)out);
+  }
+};
+
+namespace aefft {
+
+// RAII event pair around one kernel launch (no-op unless ctx->profiling).
+struct ProfScope {
+  aefft_ctx* ctx;
+  int idx = -1;
+  ProfScope(aefft_ctx* c, const char* name, double flops, double bytes) : ctx(c) {
+    if (!c->profiling) return;
+    ProfRec r{name, c->get_event(), c->get_event(), flops, bytes};
+    cudaEventRecord(r.e0, c->stream);
+    idx = (int)c->prof.size();
+    c->prof.push_back(r);
+  }
+  ~ProfScope() {
+    if (idx >= 0) cudaEventRecord(ctx->prof[idx].e1, ctx->stream);
+  }
+};
+
+// ---- conv geometry -------------------------------------------------------------------------------
+// Every coordinate-space contraction is expressed in "window" coordinates: output pixel (i,j) reads source
+// pixels (i + ai0 + tk, j + aj0 + tl), tk in [0,Nk), tl in [0,Nl); the weight tap multiplying window position
+// (tk,tl) is (k,l) = flip ? (Nk-1-tk, Nl-1-tl) : (tk,tl).  Source pixels outside [lo, N) contribute zero.
+struct Window {
+  int Nk, Nl;
+  int ai0, aj0;  // window origin relative to the output pixel
+  int flip;      // 1: forward conv (in[i - ik(k)]), 0: transposed (e[u + ik(k)])
+  int lo;        // lowest valid source index (0: CUDA `>=0`, 1: CPU strict `>0`)
+};
+
+// reference tap offset ik(k) = base + k  
+inline int tap_base(int N, int convention) {
+  int a = (N - 1) / 2 - 1;
+  if (convention == AEFFT_CONV_CUDA) a = a / 2;
+  return -2 * a - 1;
+}
+// forward conv window: source index i - (base+k), k=0..N-1  ->  origin i - base - (N-1), flipped
+inline Window fwd_window(int Nk, int Nl, int convention) {
+  Window w;
+  w.Nk = Nk; w.Nl = Nl;
+  w.ai0 = -tap_base(Nk, convention) - (Nk - 1);
+  w.aj0 = -tap_base(Nl, convention) - (Nl - 1);
+  w.flip = 1;
+  w.lo = (convention == AEFFT_CONV_CPU) ? 1 : 0;
+  return w;
+}
+// transposed window: source index u + (base+k)
+inline Window tr_window(int Nk, int Nl, int convention) {
+  Window w;
+  w.Nk = Nk; w.Nl = Nl;
+  w.ai0 = tap_base(Nk, convention);
+  w.aj0 = tap_base(Nl, convention);
+  w.flip = 0;
+  w.lo = 0;
+  return w;
+}
+
+// ---- kernel launchers (conv_kernels.cu / wgrad_kernels.cu / misc_kernels.cu) ------------------------
+
+// out[b][o][i][j] = bias[o] + sum_{c,tk,tl} W(o,c,k,l) * S[b][c](i+ai0+tk, j+aj0+tl)
+//   S = src0 * (pre_div ? 1/pre_div : 1)           when src1 == nullptr
+//   S = src0 - src1                                 otherwise (fused e = out - in)
+//   W(o,c,k,l) = w[o*w_so + c*w_sc + k*Nl + l]
+int launch_conv(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, int Nx, int Ny, const float* src0,
+                const float* src1, float pre_div, const float* w, int64_t w_so, int64_t w_sc, const float* bias,
+                float* out);
+
+// Correlation (weight-gradient) contraction, summed over all frames and pixels:
+//   G[a][x][k][l] = sum_{b,i,j} A[b][a](i,j) * X[b][x](i+ai0+tk, j+aj0+tl)          (k,l) <-> (tk,tl) per win.flip
+//   sumA[a] = sum A[b][a](i,j);  sumsq = sum A^2
+// A operand modes:
+//   A_PLAIN : A = a0                       (nA channels)
+//   A_DIFF  : A = a0 - a1                  (e = out - in)
+//   A_SHIFT : virtual channels a=(d1,tk1,tl1): A = Vlo(i,j) * (a0-a1)[d1](i+ei0+tk1, j+ej0+tl1)   (CPU_REF R tensor)
+enum { A_PLAIN = 0, A_DIFF = 1, A_SHIFT = 2 };
+struct AOperand {
+  int mode = A_PLAIN;
+  const float* a0 = nullptr;
+  const float* a1 = nullptr;
+  int nA = 0;       // logical channel count (for A_SHIFT: d1 count * Nk * Nl)
+  int src_ch = 0;   // physical channels of a0/a1 per frame
+  int ei0 = 0, ej0 = 0, eNk = 0, eNl = 0, out_lo = 0;  // A_SHIFT only
+};
+// Results land in ctx scratch and are finished by reduce_wgrad: G (nA*nX*Nk*Nl floats), sumA (nA), sumsq (1).
+int launch_wgrad(aefft_ctx* ctx, const Window& win, int64_t B, int Nx, int Ny, const AOperand& A, const float* X,
+                 int nX, float* G, float* sumA, float* sumsq);
+
+int launch_pool(aefft_ctx* ctx, int64_t B, int D, int Nx, int Ny, int oNx, int oNy, int scale, const float* in,
+                float* out);
+int launch_portion(aefft_ctx* ctx, int64_t B, int D, int Nx, int Ny, int q, const float* in, float* out);
+int launch_synth(aefft_ctx* ctx, uint64_t seed, int64_t b0, int64_t B, int D, int Nx, int Ny, float* out);
+
+// T[d][k1][l1] = sum_{b,i,j} (out-in)[b][d](i,j) * V_lo(i - (bi+k1), j - (bj+l1))   (border-aware sums of e)
+int launch_border_sums(aefft_ctx* ctx, int64_t B, int D, int Nx, int Ny, int Nk, int Nl, int bi, int bj, int lo,
+                       const float* out, const float* in, float* T);
+
+// CUDA_REF quirks C3+C4: bug-compatible dF (see misc_kernels.cu)
+int launch_quirk_dF(aefft_ctx* ctx, int quirks, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl,
+                    const float* out, const float* in, const float* hin, float* gF /*[dD][dM][Nk][Nl], summed*/);
+
+struct UpdateArgs {
+  int mode, dD, dM, Nk, Nl;
+  float inv_norm;  // 1/(Norm * B_global)
+  float delmax, alpha;
+  const float* g;  // gradient block (layout per mode, see capi.cu)
+  float *c, *b, *f, *p, *dc, *db, *df, *dp, *ddc, *ddb, *ddf, *ddp;
+  float* mse_out;  // device scalar or nullptr
+  float mse_scale;
+};
+int launch_update(aefft_ctx* ctx, const UpdateArgs& a);
+
+// ---- host orchestration shared by capi.cu and net.cu ------------------------------------------------
+int64_t gbuf_len(int mode, int dD, int dM, int Nk, int Nl);
+int coord_gradients_dev(aefft_ctx* ctx, int mode, int quirks, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl,
+                        const float* in, const float* out, const float* hin, const float* f, float* gbuf);
+int coord_update_dev(aefft_ctx* ctx, int mode, int64_t B_global, int dD, int dM, int Nx, int Ny, int Nk, int Nl,
+                     const float* gbuf, float* c, float* b, float* f, float* p, float* dc, float* db, float* df,
+                     float* dp, float* ddc, float* ddb, float* ddf, float* ddp, float delmax, float alpha,
+                     float* mse_dev);
+
+}  // namespace aefft

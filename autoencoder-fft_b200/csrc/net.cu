@@ -1,0 +1,359 @@
+// Device-resident replay of autoencoder.cpp's state model (:69-120 state, :135-150 forward, :158-201 training
+// dispatch, :384-457 add/delete layer, :343-356 symmetric copy).  The reference keeps layers[], net_c[], net_b[],
+// scale[] as nested host vectors and crosses the PCIe bus twice per conv; here they live in HBM for B frames at once.
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace aefft;
+
+namespace {
+
+struct ConvL {
+  int dM, dD, Nk, Nl, scale;
+  float *c = nullptr, *b = nullptr;  // device
+};
+struct LayerL {
+  int D, Nx, Ny;
+  float* p = nullptr;  // [B][D][Nx][Ny]
+};
+// per-pair momentum / last-gradient state.  The reference shares ONE set (dc,db,df,dp,ddc,..) between all pairs and
+// zeroes it whenever the active pair changes (autoencoder.cpp:288-292, 412-417, 447-452); here each pair owns its set
+// (aefft_net_reset_momentum reproduces the zeroing).
+struct PairState {
+  float *dc = nullptr, *db = nullptr, *df = nullptr, *dp = nullptr;
+  float *ddc = nullptr, *ddb = nullptr, *ddf = nullptr, *ddp = nullptr;
+  float* gbuf = nullptr;
+  int64_t gbuf_len = 0;
+  int gbuf_mode = -1;
+};
+
+}  // namespace
+
+struct aefft_net {
+  aefft_ctx* ctx;
+  int64_t B;
+  std::vector<LayerL> layers;   // 2*convs+1
+  std::vector<ConvL> convs;     // encoder convs 0..P-1, decoder convs P..2P-1 (pair n: convs n and N-1-n)
+  std::vector<PairState> pairs; // index = pair
+  float* mse_dev = nullptr;     // [64]
+};
+
+namespace {
+
+int dev_alloc(float** p, size_t n) {
+  AE_CUDA(cudaMalloc((void**)p, (n ? n : 1) * sizeof(float)));
+  return AEFFT_OK;
+}
+int dev_zero(aefft_ctx* ctx, float* p, size_t n) {
+  AE_CUDA(cudaMemsetAsync(p, 0, n * sizeof(float), ctx->stream));
+  return AEFFT_OK;
+}
+void dev_free(float*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+int alloc_layer(aefft_net* net, LayerL& L) {
+  AE_TRY(dev_alloc(&L.p, (size_t)net->B * L.D * L.Nx * L.Ny));
+  return dev_zero(net->ctx, L.p, (size_t)net->B * L.D * L.Nx * L.Ny);
+}
+
+int alloc_pair_state(aefft_net* net, PairState& s, int dM, int dD, int Nk, int Nl) {
+  const size_t nC = (size_t)dM * dD * Nk * Nl;
+  float** w4[4] = {&s.dc, &s.df, &s.ddc, &s.ddf};
+  for (auto p : w4) { AE_TRY(dev_alloc(p, nC)); AE_TRY(dev_zero(net->ctx, *p, nC)); }
+  float** bm[2] = {&s.db, &s.ddb};
+  for (auto p : bm) { AE_TRY(dev_alloc(p, dM)); AE_TRY(dev_zero(net->ctx, *p, dM)); }
+  float** bd[2] = {&s.dp, &s.ddp};
+  for (auto p : bd) { AE_TRY(dev_alloc(p, dD)); AE_TRY(dev_zero(net->ctx, *p, dD)); }
+  return AEFFT_OK;
+}
+void free_pair_state(PairState& s) {
+  dev_free(s.dc); dev_free(s.db); dev_free(s.df); dev_free(s.dp);
+  dev_free(s.ddc); dev_free(s.ddb); dev_free(s.ddf); dev_free(s.ddp);
+  dev_free(s.gbuf);
+  s.gbuf_len = 0; s.gbuf_mode = -1;
+}
+
+int upload(aefft_ctx* ctx, float* dst, const float* src, size_t n) {
+  AE_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  AE_CUDA(cudaStreamSynchronize(ctx->stream));
+  return AEFFT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int aefft_net_create(aefft_ctx* ctx, aefft_net** out, int D, int Nx, int Ny, int64_t B) {
+  AE_ARG(ctx && out && D > 0 && Nx > 0 && Ny > 0 && B > 0);
+  AE_CUDA(cudaSetDevice(ctx->device));
+  aefft_net* net = new aefft_net();
+  net->ctx = ctx;
+  net->B = B;
+  LayerL in{D, Nx, Ny, nullptr};
+  int r = alloc_layer(net, in);
+  if (r == AEFFT_OK) r = dev_alloc(&net->mse_dev, 64);
+  if (r != AEFFT_OK) { delete net; return r; }
+  net->layers.push_back(in);
+  *out = net;
+  return AEFFT_OK;
+}
+
+int aefft_net_destroy(aefft_net* net) {
+  if (!net) return AEFFT_OK;
+  cudaSetDevice(net->ctx->device);
+  cudaStreamSynchronize(net->ctx->stream);
+  for (auto& L : net->layers) dev_free(L.p);
+  for (auto& c : net->convs) { dev_free(c.c); dev_free(c.b); }
+  for (auto& s : net->pairs) free_pair_state(s);
+  dev_free(net->mse_dev);
+  delete net;
+  return AEFFT_OK;
+}
+
+// 'n' key (autoencoder.cpp:384-431).  The very first pair is what main() builds at start-up (:69-120) from the same
+// five parameters.  New pair = innermost: input = current innermost hidden layer (or the frame), channels dD -> dM,
+// resolution /scal.  Weights: Init_conv(c,b,dM,dD) then Init_conv(f,p,dD,dM) from libc rand() (:100-101, :412-413).
+int aefft_net_add_layer(aefft_net* net, int dM, int Lk, int Ll, int scal, float rmax) {
+  AE_ARG(net && dM > 0 && Lk >= 0 && Ll >= 0 && scal >= 1);
+  aefft_ctx* ctx = net->ctx;
+  AE_CUDA(cudaSetDevice(ctx->device));
+  const int Nk = 2 * (Lk + 1) + 1, Nl = 2 * (Ll + 1) + 1;
+  const int n = ((int)net->layers.size() - 1) / 2;  // centre layer (:392)
+  const LayerL centre = net->layers[n];
+  const int dD = centre.D, dNx = centre.Nx, dNy = centre.Ny;
+  AE_ARG(dNx / scal > 0 && dNy / scal > 0);
+  LayerL Pin{dD, dNx / scal, dNy / scal, nullptr}, hC{dM, dNx / scal, dNy / scal, nullptr},
+      PhC{dD, dNx / scal, dNy / scal, nullptr}, outn{dD, dNx, dNy, nullptr};
+  AE_TRY(alloc_layer(net, Pin)); AE_TRY(alloc_layer(net, hC)); AE_TRY(alloc_layer(net, PhC)); AE_TRY(alloc_layer(net, outn));
+  if (net->layers.size() == 1) {
+    // first pair: layers = in, Pin, hC, PhC, out (:108-112)
+    net->layers.push_back(Pin); net->layers.push_back(hC); net->layers.push_back(PhC); net->layers.push_back(outn);
+  } else {
+    net->layers.insert(net->layers.begin() + n + 1, {Pin, hC, PhC, outn});
+  }
+  const size_t nC = (size_t)dM * dD * Nk * Nl;
+  std::vector<float> c(nC), b(dM), f(nC), p(dD);
+  AE_TRY(aefft_init_conv(c.data(), b.data(), dM, dD, Nk, Nl, rmax));
+  AE_TRY(aefft_init_conv(f.data(), p.data(), dD, dM, Nk, Nl, rmax));
+  ConvL enc{dM, dD, Nk, Nl, scal}, dec{dD, dM, Nk, Nl, -scal};
+  AE_TRY(dev_alloc(&enc.c, nC)); AE_TRY(dev_alloc(&enc.b, dM));
+  AE_TRY(dev_alloc(&dec.c, nC)); AE_TRY(dev_alloc(&dec.b, dD));
+  AE_TRY(upload(ctx, enc.c, c.data(), nC)); AE_TRY(upload(ctx, enc.b, b.data(), dM));
+  AE_TRY(upload(ctx, dec.c, f.data(), nC)); AE_TRY(upload(ctx, dec.b, p.data(), dD));
+  const int mid = (int)net->convs.size() / 2;
+  net->convs.insert(net->convs.begin() + mid, {enc, dec});
+  PairState st;
+  AE_TRY(alloc_pair_state(net, st, dM, dD, Nk, Nl));
+  net->pairs.push_back(st);  // innermost pair has the highest index
+  AE_CUDA(cudaStreamSynchronize(ctx->stream));
+  return AEFFT_OK;
+}
+
+// 'd' key (:432-457): remove the innermost pair, never the last remaining one.
+int aefft_net_delete_layer(aefft_net* net) {
+  AE_ARG(net);
+  if (net->convs.size() <= 2) { set_error("aefft_net_delete_layer: only one pair left"); return AEFFT_ERR_ARG; }
+  AE_CUDA(cudaSetDevice(net->ctx->device));
+  AE_CUDA(cudaStreamSynchronize(net->ctx->stream));
+  int n = (int)net->convs.size() / 2;
+  for (int i = n - 1; i <= n; i++) { dev_free(net->convs[i].c); dev_free(net->convs[i].b); }
+  net->convs.erase(net->convs.begin() + n - 1, net->convs.begin() + n + 1);
+  n = ((int)net->layers.size() - 1) / 2;
+  for (int i = n - 1; i < n + 3; i++) dev_free(net->layers[i].p);
+  net->layers.erase(net->layers.begin() + n - 1, net->layers.begin() + n + 3);
+  free_pair_state(net->pairs.back());
+  net->pairs.pop_back();
+  return AEFFT_OK;
+}
+
+int aefft_net_num_pairs(const aefft_net* net) { return net ? (int)net->pairs.size() : -1; }
+
+int aefft_net_conv_dims(const aefft_net* net, int n, int* dM, int* dD, int* Nk, int* Nl, int* scale) {
+  AE_ARG(net && n >= 0 && n < (int)net->convs.size());
+  const ConvL& c = net->convs[n];
+  if (dM) *dM = c.dM;
+  if (dD) *dD = c.dD;
+  if (Nk) *Nk = c.Nk;
+  if (Nl) *Nl = c.Nl;
+  if (scale) *scale = c.scale;
+  return AEFFT_OK;
+}
+
+int aefft_net_get_conv(aefft_net* net, int n, float* c, float* b) {
+  AE_ARG(net && n >= 0 && n < (int)net->convs.size());
+  const ConvL& L = net->convs[n];
+  cudaStream_t s = net->ctx->stream;
+  AE_CUDA(cudaSetDevice(net->ctx->device));
+  if (c) AE_CUDA(cudaMemcpyAsync(c, L.c, (size_t)L.dM * L.dD * L.Nk * L.Nl * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (b) AE_CUDA(cudaMemcpyAsync(b, L.b, (size_t)L.dM * sizeof(float), cudaMemcpyDeviceToHost, s));
+  AE_CUDA(cudaStreamSynchronize(s));
+  return AEFFT_OK;
+}
+
+int aefft_net_set_conv(aefft_net* net, int n, const float* c, const float* b) {
+  AE_ARG(net && n >= 0 && n < (int)net->convs.size());
+  const ConvL& L = net->convs[n];
+  AE_CUDA(cudaSetDevice(net->ctx->device));
+  if (c) AE_TRY(upload(net->ctx, L.c, c, (size_t)L.dM * L.dD * L.Nk * L.Nl));
+  if (b) AE_TRY(upload(net->ctx, L.b, b, (size_t)L.dM));
+  return AEFFT_OK;
+}
+
+__global__ void sym_copy_kernel(const float* __restrict__ c, float* __restrict__ f, int dM, int dD, int T) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= dM * dD * T) return;
+  int t = n % T, d = (n / T) % dD, m = n / (T * dD);
+  f[(d * dM + m) * T + t] = c[n];
+}
+
+// 'p' key (:343-356): net_c[N-n_l][d][m][k][l] = net_c[n_l][m][d][k][l]
+int aefft_net_set_symmetric(aefft_net* net, int n_l) {
+  AE_ARG(net && n_l >= 0 && n_l < (int)net->pairs.size());
+  const int N = (int)net->convs.size() - 1;
+  const ConvL& e = net->convs[n_l];
+  const ConvL& d = net->convs[N - n_l];
+  AE_CUDA(cudaSetDevice(net->ctx->device));
+  const int total = e.dM * e.dD * e.Nk * e.Nl;
+  sym_copy_kernel<<<(total + 255) / 256, 256, 0, net->ctx->stream>>>(e.c, d.c, e.dM, e.dD, e.Nk * e.Nl);
+  net->ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// 'z'/'x' keys (:281-292): the shared momentum / last-gradient buffers are re-initialised to zero.
+int aefft_net_reset_momentum(aefft_net* net, int n_l) {
+  AE_ARG(net && n_l >= 0 && n_l < (int)net->pairs.size());
+  const ConvL& e = net->convs[n_l];
+  PairState& s = net->pairs[n_l];
+  const size_t nC = (size_t)e.dM * e.dD * e.Nk * e.Nl;
+  AE_CUDA(cudaSetDevice(net->ctx->device));
+  AE_TRY(dev_zero(net->ctx, s.dc, nC)); AE_TRY(dev_zero(net->ctx, s.df, nC));
+  AE_TRY(dev_zero(net->ctx, s.ddc, nC)); AE_TRY(dev_zero(net->ctx, s.ddf, nC));
+  AE_TRY(dev_zero(net->ctx, s.db, e.dM)); AE_TRY(dev_zero(net->ctx, s.ddb, e.dM));
+  AE_TRY(dev_zero(net->ctx, s.dp, e.dD)); AE_TRY(dev_zero(net->ctx, s.ddp, e.dD));
+  return AEFFT_OK;
+}
+
+int aefft_net_layer(aefft_net* net, int l, int* D, int* Nx, int* Ny, float** dev_ptr) {
+  AE_ARG(net && l >= 0 && l < (int)net->layers.size());
+  const LayerL& L = net->layers[l];
+  if (D) *D = L.D;
+  if (Nx) *Nx = L.Nx;
+  if (Ny) *Ny = L.Ny;
+  if (dev_ptr) *dev_ptr = L.p;
+  return AEFFT_OK;
+}
+
+int aefft_net_num_layers(const aefft_net* net) { return net ? (int)net->layers.size() : -1; }
+
+// forward, coordinate space (autoencoder.cpp:135-150)
+int aefft_net_forward(aefft_net* net, int loc, const float* frames) {
+  AE_ARG(net && net->convs.size() >= 2);
+  aefft_ctx* ctx = net->ctx;
+  AE_CUDA(cudaSetDevice(ctx->device));
+  LayerL& L0 = net->layers[0];
+  const size_t n0 = (size_t)net->B * L0.D * L0.Nx * L0.Ny;
+  if (frames && frames != L0.p)
+    AE_CUDA(cudaMemcpyAsync(L0.p, frames, n0 * sizeof(float),
+                            loc == AEFFT_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+  const int N = (int)net->convs.size();
+  for (int n = 0; n < N; n++) {
+    const ConvL& c = net->convs[n];
+    const int nl = 2 * n;
+    LayerL &a = net->layers[nl], &m = net->layers[nl + 1], &z = net->layers[nl + 2];
+    if (n < N / 2) {
+      AE_TRY(launch_pool(ctx, net->B, a.D, a.Nx, a.Ny, m.Nx, m.Ny, c.scale, a.p, m.p));
+      AE_TRY(launch_conv(ctx, fwd_window(c.Nk, c.Nl, AEFFT_CONV_CUDA), net->B, c.dD, c.dM, m.Nx, m.Ny, m.p, nullptr,
+                         (float)c.dM, c.c, (int64_t)c.dD * c.Nk * c.Nl, (int64_t)c.Nk * c.Nl, c.b, z.p));
+    } else {
+      AE_TRY(launch_conv(ctx, fwd_window(c.Nk, c.Nl, AEFFT_CONV_CUDA), net->B, c.dD, c.dM, a.Nx, a.Ny, a.p, nullptr,
+                         (float)c.dM, c.c, (int64_t)c.dD * c.Nk * c.Nl, (int64_t)c.Nk * c.Nl, c.b, m.p));
+      AE_TRY(launch_pool(ctx, net->B, m.D, m.Nx, m.Ny, z.Nx, z.Ny, c.scale, m.p, z.p));
+    }
+  }
+  return AEFFT_OK;
+}
+
+static int pair_views(aefft_net* net, int n_l, const ConvL** enc, const ConvL** dec, const LayerL** in,
+                      const LayerL** hin, const LayerL** out) {
+  AE_ARG(net && n_l >= 0 && n_l < (int)net->pairs.size());
+  const int N = (int)net->convs.size();
+  *enc = &net->convs[n_l];
+  *dec = &net->convs[N - 1 - n_l];
+  // in = layers[2n+1], hin = layers[2n+2], out = layers[size-2-2n] (autoencoder.cpp:161-169)
+  *in = &net->layers[2 * n_l + 1];
+  *hin = &net->layers[2 * n_l + 2];
+  *out = &net->layers[net->layers.size() - 2 - 2 * n_l];
+  return AEFFT_OK;
+}
+
+int aefft_net_pair_gradients(aefft_net* net, int n_l, int mode, int quirks, float** gbuf_dev, int64_t* gbuf_n) {
+  const ConvL *enc, *dec;
+  const LayerL *in, *hin, *out;
+  AE_TRY(pair_views(net, n_l, &enc, &dec, &in, &hin, &out));
+  aefft_ctx* ctx = net->ctx;
+  AE_CUDA(cudaSetDevice(ctx->device));
+  PairState& s = net->pairs[n_l];
+  const int64_t len = gbuf_len(mode, enc->dD, enc->dM, enc->Nk, enc->Nl);
+  if (s.gbuf_len < len) {
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
+    dev_free(s.gbuf);
+    AE_TRY(dev_alloc(&s.gbuf, (size_t)len));
+    s.gbuf_len = len;
+  }
+  s.gbuf_mode = mode;
+  AE_TRY(coord_gradients_dev(ctx, mode, quirks, net->B, enc->dD, enc->dM, in->Nx, in->Ny, enc->Nk, enc->Nl, in->p, out->p,
+                             hin->p, dec->c, s.gbuf));
+  if (gbuf_dev) *gbuf_dev = s.gbuf;
+  if (gbuf_n) *gbuf_n = len;
+  return AEFFT_OK;
+}
+
+int aefft_net_pair_update(aefft_net* net, int n_l, int mode, int64_t B_global, float delmax, float alpha, float* mse) {
+  const ConvL *enc, *dec;
+  const LayerL *in, *hin, *out;
+  AE_TRY(pair_views(net, n_l, &enc, &dec, &in, &hin, &out));
+  aefft_ctx* ctx = net->ctx;
+  AE_CUDA(cudaSetDevice(ctx->device));
+  PairState& s = net->pairs[n_l];
+  AE_ARG(s.gbuf && s.gbuf_mode == mode);
+  float* mse_dev = net->mse_dev + (n_l % 64);
+  AE_TRY(coord_update_dev(ctx, mode, B_global, enc->dD, enc->dM, in->Nx, in->Ny, enc->Nk, enc->Nl, s.gbuf, enc->c, enc->b,
+                          dec->c, dec->b, s.dc, s.db, s.df, s.dp, s.ddc, s.ddb, s.ddf, s.ddp, delmax, alpha, mse_dev));
+  if (mse) {
+    AE_CUDA(cudaMemcpyAsync(mse, mse_dev, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return AEFFT_OK;
+}
+
+int aefft_net_train_pair(aefft_net* net, int n_l, int mode, int quirks, float delmax, float alpha, float* mse) {
+  AE_TRY(aefft_net_pair_gradients(net, n_l, mode, quirks, nullptr, nullptr));
+  return aefft_net_pair_update(net, n_l, mode, net->B, delmax, alpha, mse);
+}
+
+// One whole training step: forward + train every pair once on that forward's activations (order 0..pairs-1).
+// The reference trains one pair per frame (greedy, N4); a sweep over all pairs on the same forward is this repo's
+// definition of a multi-pair "step" (DESIGN.md).  Pairs are independent given the activations.
+int aefft_net_step(aefft_net* net, int loc, const float* frames, int mode, int quirks, float delmax, float alpha,
+                   float* mse) {
+  AE_ARG(net);
+  AE_TRY(aefft_net_forward(net, loc, frames));
+  const int P = (int)net->pairs.size();
+  for (int n = 0; n < P; n++) {
+    AE_TRY(aefft_net_pair_gradients(net, n, mode, quirks, nullptr, nullptr));
+    AE_TRY(aefft_net_pair_update(net, n, mode, net->B, delmax, alpha, nullptr));
+  }
+  if (mse) {
+    AE_CUDA(cudaMemcpyAsync(mse, net->mse_dev, sizeof(float) * (P < 64 ? P : 64), cudaMemcpyDeviceToHost,
+                            net->ctx->stream));
+    AE_CUDA(cudaStreamSynchronize(net->ctx->stream));
+  }
+  return AEFFT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- training frames/sec (forward + backprop + update) of the autoencoder hot path on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c3]
+
+Workloads (BASELINE.json configs; DESIGN.md "Measurement"):
+  c2 (default, configs[1]): 3-pair coordinate-space autoencoder 3->16->32->64, 5x5 taps, pool 2 per pair, symmetric
+      weights (backprop_gpu_cc semantics), 640x480 RGB frames, batch 64 per GPU.  One step = forward of the whole stack
+      + one clipped-momentum update of every pair on the mean gradient of the batch.
+  c3 (configs[2]): the same widths in momentum (FFT) space on 1024x1024 frames, batch 128 per GPU.
+N>1: data-parallel frames (weak scaling: every rank owns its own batch), one NCCL all-reduce of the raw
+kernel-space gradient block per pair, identical update on every rank.
+
+Prints ONE JSON line (rank 0).  `value` = frames/s with frames resident in HBM; `e2e` = the same step through the
+host-buffer C-ABI call (pinned host frames -> device every step, mse read back every step).
+`--impl reference` times the reference's own CPU implementation (oracle/_ref/libref.so = unmodified netlib.cpp, else the
+numpy port) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "autoencoder-fft_b200"), os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+SEED = 1234
+WORKLOADS = {
+    # name: (D, Nx, Ny, widths, Lk, Ll, pool, rmax, batch per GPU, space)
+    "c2": dict(D=3, Nx=640, Ny=480, widths=[16, 32, 64], Lk=1, Ll=1, pool=2, rmax=3.0, batch=64, space="coordinate"),
+    "c3": dict(D=3, Nx=1024, Ny=1024, widths=[16, 32, 64], Lk=1, Ll=1, pool=2, rmax=3.0, batch=128, space="fft"),
+}
+DELMAX, ALPHA = 0.2, 0.9  # autoencoder.cpp:87-89
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def pair_geometry(w):
+    """[(dD, dM, Nx, Ny)] per pair (resolution at which the pair's convs run)."""
+    out, d, nx, ny = [], w["D"], w["Nx"], w["Ny"]
+    for m in w["widths"]:
+        nx, ny = nx // w["pool"], ny // w["pool"]
+        out.append((d, m, nx, ny))
+        d = m
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ reference CPU arm
+def cpu_cost_units(dD, dM, T, P):
+    """netlib.cpp:361-451 backprop: 9-deep loop nest, O(dM * dD^2 * (Nk*Nl)^2 * P)."""
+    return float(dM) * dD * dD * T * T * P
+
+
+def cpu_reference_sample(w, budget_s, repeats=1):
+    """Times the reference's CPU path (Pool + Conv + Conv + backprop, netlib.cpp) on pair 0 of ONE frame, centre-cropped
+    by Portion(q) so that one sample costs about budget_s, and extrapolates to the full step with the loop-nest cost
+    model.  Returns dict(value frames/s, seconds per sample, sample description, kind, cores)."""
+    import oracle_np as O
+    import ref_lib
+
+    kind = "reference" if ref_lib.available() else "port"
+    geo = pair_geometry(w)
+    Nk, Nl = 2 * (w["Lk"] + 1) + 1, 2 * (w["Ll"] + 1) + 1
+    T = Nk * Nl
+    dD, dM, nx, ny = geo[0]
+    full_units = sum(cpu_cost_units(d, m, T, x * y) for d, m, x, y in geo)
+    # measured on this image's Xeon: ~6.3e-6 s per cost unit (15.4 s for 8*1*625*307200 units)
+    sec_per_unit = 6.3e-6 / 625.0
+    q = 1
+    while cpu_cost_units(dD, dM, T, (nx // q) * (ny // q)) * sec_per_unit > budget_s and min(nx, ny) // (2 * q) >= 16:
+        q *= 2
+    frame = O.synth_frames(SEED, 1, w["D"], w["Nx"], w["Ny"])[0]
+    rng = O.GlibcRand(SEED)
+    c, b = O.init_conv(rng, dM, dD, Nk, Nl, w["rmax"])
+    f = np.ascontiguousarray(np.swapaxes(c, 0, 1))
+    p = np.zeros(dD, np.float32)
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        if kind == "reference":
+            devnull = os.open(os.devnull, os.O_WRONLY)
+            saved = os.dup(1)
+            os.dup2(devnull, 1)  # the reference prints "mse: ..." from inside backprop()
+            try:
+                pin = ref_lib.pool(frame, w["pool"], (nx, ny))
+                pin, _, _ = ref_lib.portion(pin, pin, pin, q)
+                hin = ref_lib.conv_cpu(pin, c, b)
+                out = ref_lib.conv_cpu(hin, f, p)
+                ref_lib.backprop_cpu(pin, out, hin, c, b, f, p, DELMAX)
+            finally:
+                os.dup2(saved, 1)
+                os.close(devnull)
+                os.close(saved)
+        else:
+            pin = O.pool(frame, w["pool"], (nx, ny))
+            pin, _, _ = O.portion(pin, pin, pin, q)
+            hin = O.conv_cpu(pin, c, b).astype(np.float32)
+            out = O.conv_cpu(hin, f, p).astype(np.float32)
+            O.backprop_cpu(pin, out, hin, c, b, f, p, DELMAX)
+        times.append(time.perf_counter() - t0)
+    t = min(times)
+    sample_units = cpu_cost_units(dD, dM, T, (nx // q) * (ny // q))
+    per_frame = t * full_units / sample_units
+    desc = (f"1 frame, pair 0 only ({dD}->{dM}, {Nk}x{Nl}) on the centre {nx // q}x{ny // q} crop (Portion q={q}): Pool+Conv+Conv+"
+            f"backprop of netlib.cpp, {t:.2f} s; extrapolated to all {len(geo)} pairs at full resolution with the loop-nest "
+            f"cost dM*dD^2*(Nk*Nl)^2*P (x{full_units / sample_units:.0f})")
+    return dict(value=1.0 / per_frame, seconds=t, sample=desc, kind=kind, cores=1, q=q)
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return
+    total_budget = 150.0
+    per = max(0.5, total_budget / max(1, args.steps + args.warmup))
+    for _ in range(args.warmup):
+        cpu_reference_sample(w, per)
+    res = [cpu_reference_sample(w, per) for _ in range(args.steps)]
+    v = float(np.mean([r["value"] for r in res]))
+    line = {
+        "impl": "reference", "metric": "training frames/sec (fwd+backprop)", "value": v, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean([r["seconds"] for r in res]) * 1e3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(w, args, world),
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": 1, "kind": res[0]["kind"], "sample": res[0]["sample"]},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def config_dict(w, args, world):
+    geo = pair_geometry(w)
+    return {
+        "workload": f"{args.workload}: {len(w['widths'])}-pair {w['space']}-space autoencoder {w['D']}->" +
+                    "->".join(map(str, w["widths"])) + f", {2 * (w['Lk'] + 1) + 1}x{2 * (w['Ll'] + 1) + 1} taps, pool {w['pool']}, "
+                    f"symmetric weights, {w['Nx']}x{w['Ny']} frames, batch {args.batch} per GPU",
+        "global_batch": args.batch * world,
+        "pairs": [{"dD": d, "dM": m, "Nx": x, "Ny": y} for d, m, x, y in geo],
+        "parallelism": f"dp{world}",
+        "cache": "inputs larger than L2 (frames + activations per step >> 126 MB); no explicit flush",
+        "step": "forward of the full stack + gradients + clipped-momentum update of every pair",
+    }
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class CudaArray:
+    """Wraps a raw device pointer so torch can view it (for torch.distributed.all_reduce on the gradient block)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def run_ours(args, w, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import aefft_ctypes as A
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = A.Ctx(local_rank)
+    stream = torch.cuda.current_stream()
+    A._chk(A.lib().aefft_set_stream(ctx.h, ctypes.c_void_p(stream.cuda_stream)))
+    B = args.batch
+    if w["space"] != "coordinate":
+        raise SystemExit("workload c3 (FFT space) is benchmarked by bench_fft in a later round-1 milestone")
+    ctypes.CDLL("libc.so.6").srand(SEED)
+    net = A.Net(ctx, w["D"], w["Nx"], w["Ny"], B)
+    for m in w["widths"]:
+        net.add_layer(m, w["Lk"], w["Ll"], w["pool"], w["rmax"])
+    P = net.num_pairs
+    for n in range(P):
+        net.set_symmetric(n)  # 'p' key: decoder = transposed encoder before symmetric training
+    mode = A.MODE_CUDA_REF_SYM
+    _, _, _, l0 = net.layer_info(0)
+    n0 = B * w["D"] * w["Nx"] * w["Ny"]
+    ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=rank * B, out=l0, loc=A.DEVICE)
+    gviews = []
+
+    def step_resident():
+        if world == 1:
+            net.step(None, mode, DELMAX, ALPHA, loc=A.DEVICE)
+            return
+        net.forward(None, loc=A.DEVICE)
+        for n in range(P):
+            ptr, glen = net.pair_gradients(n, mode)
+            if len(gviews) <= n:
+                gviews.append(torch.as_tensor(CudaArray(ptr, glen), device=dev))
+            dist.all_reduce(gviews[n])
+            net.pair_update(n, mode, B * world, DELMAX, ALPHA)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    A._chk(A.lib().aefft_profile_enable(ctx.h, 1))
+    l_before = ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    A._chk(A.lib().aefft_profile_enable(ctx.h, 0))
+    launches = ctx.launches - l_before
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    # per-kernel timing (CUDA events on the launching stream, inside the timed region)
+    maxr = 64
+    names = ctypes.create_string_buffer(64 * maxr)
+    kms = (ctypes.c_float * maxr)()
+    cnt = (ctypes.c_int64 * maxr)()
+    fl = (ctypes.c_double * maxr)()
+    by = (ctypes.c_double * maxr)()
+    nrows = ctypes.c_int()
+    A._chk(A.lib().aefft_profile_read(ctx.h, maxr, names, kms, cnt, fl, by, ctypes.byref(nrows)))
+    kernels = []
+    for k in range(nrows.value):
+        nm = names.raw[64 * k: 64 * k + 64].split(b"\0")[0].decode()
+        kernels.append(dict(name=nm, ms=float(kms[k]), launches=int(cnt[k]), flops=float(fl[k]), bytes=float(by[k])))
+    kernels.sort(key=lambda r: -r["ms"])
+
+    # ---- end to end: pinned host frames -> device every step, mse read back every step
+    host = torch.empty(n0, dtype=torch.float32).pin_memory()
+    A.lib().aefft_memcpy(ctx.h, ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(l0), ctypes.c_int64(n0 * 4), 1)
+    mse_host = torch.zeros(64, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        if world == 1:
+            net.step(host, mode, DELMAX, ALPHA, loc=A.HOST, mse=mse_host)
+            return
+        net.forward(host, loc=A.HOST)
+        for n in range(P):
+            net.pair_gradients(n, mode)
+            dist.all_reduce(gviews[n])
+            net.pair_update(n, mode, B * world, DELMAX, ALPHA, want_mse=(n == P - 1))
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2.item())
+
+    if rank == 0:
+        pk = peaks()
+        frames = B * world * args.steps
+        value = frames / (ms_total * 1e-3)
+        top = kernels[0] if kernels else None
+        roof = None
+        if top and top["ms"] > 0:
+            per_ms = top["ms"] / top["launches"]
+            fl_l, by_l = top["flops"] / top["launches"], top["bytes"] / top["launches"]
+            t_tensor = fl_l / (pk["tf_sust"] * 1e12)
+            t_hbm = by_l / (pk["hbm"] * 1e9)
+            if t_tensor >= t_hbm:
+                ach = fl_l / (per_ms * 1e-3) / 1e12
+                roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"]}
+            else:
+                ach = by_l / (per_ms * 1e-3) / 1e9
+                roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
+            roof.update({"traffic": None, "kernel": top["name"], "avg_launch_ms": per_ms, "share_of_step": top["ms"] / ms_total,
+                         "peak_source": pk["source"] + (", sustained bf16" if roof["bound"] == "tensor" else ""),
+                         "algorithmic_flops_per_launch": fl_l, "algorithmic_bytes_per_launch": by_l})
+        line = {
+            "metric": "training frames/sec (fwd+backprop)", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(w, args, world),
+            "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": n0 * 4,
+                    "d2h_bytes_per_step": 4 * P, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches) * world,
+            "clocks": clocks,
+            "roofline": roof,
+            "kernels": [{"name": k["name"], "ms_per_step": k["ms"] / args.steps, "launches_per_step": k["launches"] / args.steps,
+                         "tflops": (k["flops"] / (k["ms"] * 1e-3) / 1e12) if k["ms"] > 0 else None,
+                         "gbs": (k["bytes"] / (k["ms"] * 1e-3) / 1e9) if k["ms"] > 0 else None} for k in kernels],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_sample(w, 15.0)
+            line["cpu_baseline"] = {"value": cb["value"], "unit": "frames/s", "cores": cb["cores"], "kind": cb["kind"],
+                                    "sample": cb["sample"]}
+        print(json.dumps(line))
+    net.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.batch is None:
+        args.batch = w["batch"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    run_ours(args, w, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

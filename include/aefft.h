@@ -1,0 +1,218 @@
+/* aefft.h -- C ABI of the B200-native autoencoder engine (libaefft.so).
+ *
+ * Drop-in boundary for ONE hot path of fabrii4/AutoEncoder-FFT: the convolutional autoencoder's
+ * forward + backprop training step in coordinate space and in momentum (FFT) space.
+ * The reference has no FFI layer; its boundary is the set of C++ free functions in
+ *   source/netlib.h:4-24, source/backproplib.h:5-16, source/fft_backproplib.h:5-11
+ * called from source/autoencoder.cpp (sites: :132 :140-148 :169-200 :42 :100-107 :361-374).
+ * Every entry point below names the reference function it replaces.  The C++ mirror with the exact
+ * reference signatures lives in autoencoder-fft_b200/shim/ and calls only this ABI.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no C++/torch types; all functions return 0 on success, !=0 on error
+ *     (message via aefft_last_error()).  The reference returns void and checks nothing.
+ *   - float32 data.  Feature maps are [B][ch][Nx][Ny] (j fastest; B=1 is the reference's only case),
+ *     kernels c[dM][dD][Nk][Nl], f[dD][dM][Nk][Nl], flat in nesting order.
+ *   - `loc` says where the DATA pointers of a call live: AEFFT_HOST (copies are made inside the call,
+ *     like the reference's per-call H2D/D2H) or AEFFT_DEVICE (device pointers, no copies, async on the
+ *     ctx stream).  Scalar outputs (mse) are always host pointers (may be NULL).
+ *   - B>1 is this engine's batch extension: raw gradients are averaged over the B frames and ONE
+ *     clipped update is applied; B=1 reproduces the reference exactly (DESIGN.md "batch semantics").
+ *   - There is NO CPU fallback: every compute entry point fails with AEFFT_ERR_CUDA when no GPU is usable.
+ */
+#ifndef AEFFT_H
+#define AEFFT_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AEFFT_ABI_VERSION 1
+
+enum { AEFFT_OK = 0, AEFFT_ERR_ARG = 1, AEFFT_ERR_CUDA = 2, AEFFT_ERR_IO = 3, AEFFT_ERR_UNSUPPORTED = 4 };
+enum { AEFFT_HOST = 0, AEFFT_DEVICE = 1 };
+
+/* Tap-offset / bounds convention of a coordinate-space conv. */
+enum {
+  AEFFT_CONV_CUDA = 0, /* backproplib.cu:123,89: ak=((Nk-1)/2-1)/2, >=0 bounds, input pre-scaled by 1/dM */
+  AEFFT_CONV_CPU = 1   /* netlib.cpp:325,338:    ak=(Nk-1)/2-1, strict >0 bounds, no pre-scale            */
+};
+
+/* Training back-end being replaced (autoencoder.cpp:171-201). */
+enum {
+  AEFFT_MODE_CPU_REF = 0,      /* netlib.cpp:361 backprop: sequential-f, no momentum                     */
+  AEFFT_MODE_CUDA_REF = 1,     /* backproplib.cu:291 backprop_gpu                                        */
+  AEFFT_MODE_CUDA_REF_SYM = 2  /* backproplib.cu:521 backprop_gpu_cc (tied weights)                      */
+};
+
+/* Bug-compat switches for AEFFT_MODE_CUDA_REF.  Default for parity runs: all on. */
+enum {
+  AEFFT_QUIRK_C1 = 1, /* backproplib.cu:220  bias gradient keeps only d1=dD-1                            */
+  AEFFT_QUIRK_C3 = 2, /* backproplib.cu:283  (j-ik) instead of (j-il) in the dF term, taps != (0,0)      */
+  AEFFT_QUIRK_C4 = 4, /* backproplib.cu:225,282,335  dDdF buffer keeps stale border values               */
+  AEFFT_QUIRKS_ALL = 7
+};
+
+typedef struct aefft_ctx aefft_ctx; /* one per process/GPU: device, stream, workspace arena, FFT plans */
+
+const char* aefft_last_error(void);
+int aefft_abi_version(void);
+/* Number of CUDA kernels this library has launched on this ctx since creation (bench.py "gpu_launches"). */
+int64_t aefft_launch_count(const aefft_ctx* ctx);
+
+int aefft_create(aefft_ctx** ctx, int device);
+int aefft_destroy(aefft_ctx* ctx);
+int aefft_sync(aefft_ctx* ctx);
+/* The CUDA stream all work of this ctx is launched on (as an opaque cudaStream_t). */
+void* aefft_stream(aefft_ctx* ctx);
+
+/* Launch all work of this ctx on a caller-owned stream (e.g. torch's current stream, so torch.distributed
+ * collectives and torch.cuda.Event timing order with it); NULL restores the ctx's own stream. */
+int aefft_set_stream(aefft_ctx* ctx, void* cuda_stream);
+/* Per-kernel timing: while enabled, every kernel launch is bracketed by a CUDA event pair on the launching stream.
+ * aefft_profile_read synchronises, aggregates by kernel name (names: max_rows x 64 chars; ms/counts/flops/bytes summed
+ * over launches, flops/bytes being the ALGORITHMIC work of those launches) and clears the records. */
+int aefft_profile_enable(aefft_ctx* ctx, int on);
+int aefft_profile_read(aefft_ctx* ctx, int max_rows, char* names, float* ms, int64_t* counts, double* flops,
+                       double* bytes, int* n_rows);
+
+/* Device memory helpers for callers that keep data resident (loc == AEFFT_DEVICE) without linking cudart. */
+int aefft_malloc(aefft_ctx* ctx, void** dev_ptr, int64_t bytes);
+int aefft_free(aefft_ctx* ctx, void* dev_ptr);
+/* kind: 0 host->device, 1 device->host, 2 device->device; ordered on the ctx stream, synchronous on return. */
+int aefft_memcpy(aefft_ctx* ctx, void* dst, const void* src, int64_t bytes, int kind);
+
+/* ------------------------------------------------------------------ forward, coordinate space */
+
+/* Conv_gpu (backproplib.cu:114-182) / Conv (netlib.cpp:318-358), per `convention`.
+ * in [B][dD][Nx][Ny], c [dM][dD][Nk][Nl], b [dM] -> out [B][dM][Nx][Ny]. */
+int aefft_conv_fwd(aefft_ctx* ctx, int loc, int convention, int64_t B, int dD, int dM, int Nx, int Ny, int Nk,
+                   int Nl, const float* in, const float* c, const float* b, float* out);
+
+/* Pool (netlib.cpp:114-164).  scale>0: max through an int accumulator floored at 0; scale<0: replicate.
+ * in [B][D][Nx][Ny] -> out [B][D][oNx][oNy] (caller-sized, as in autoencoder.cpp:70-74). */
+int aefft_pool(aefft_ctx* ctx, int loc, int64_t B, int D, int Nx, int Ny, int oNx, int oNy, int scale,
+               const float* in, float* out);
+
+/* Portion (netlib.cpp:292-315): centre crop by q of one [B][D][Nx][Ny] tensor -> [B][D][Nx/q][Ny/q]. */
+int aefft_portion(aefft_ctx* ctx, int loc, int64_t B, int D, int Nx, int Ny, int q, const float* in, float* out);
+
+/* ------------------------------------------------------------------ training, coordinate space */
+
+/* One layer pair, one step: backprop (netlib.cpp:361), backprop_gpu (backproplib.cu:291) or
+ * backprop_gpu_cc (:521) per `mode`.  in,out [B][dD][Nx][Ny], hin [B][dM][Nx][Ny].
+ * c,b,f,p and the caller-owned momentum (dc,db,df,dp) / last-gradient (ddc,ddb,ddf,ddp) buffers are
+ * updated in place (the d* / dd* pointers are ignored for CPU_REF and may be NULL).
+ * *mse receives the value the reference prints (CUDA: sum e^2/Norm; CPU: raw sum e^2), averaged over B. */
+int aefft_backprop_coord(aefft_ctx* ctx, int loc, int mode, int quirks, int64_t B, int dD, int dM, int Nx,
+                         int Ny, int Nk, int Nl, const float* in, const float* out, const float* hin, float* c,
+                         float* b, float* f, float* p, float* dc, float* db, float* df, float* dp, float* ddc,
+                         float* ddb, float* ddf, float* ddp, float delmax, float alpha, int active, float* mse);
+
+/* Data-parallel split of the same step (device pointers only):
+ *   aefft_coord_gradients  -> raw, un-clipped, SUMMED-over-local-frames gradient block in gbuf (device)
+ *   [all-reduce(sum) of gbuf across ranks -- torch.distributed / NCCL, outside this library]
+ *   aefft_coord_update     -> divide by B_global, clip, momentum, update weights (replicated on every rank)
+ * gbuf length = aefft_coord_gbuf_len(mode,dD,dM,Nk,Nl) floats. */
+int64_t aefft_coord_gbuf_len(int mode, int dD, int dM, int Nk, int Nl);
+int aefft_coord_gradients(aefft_ctx* ctx, int mode, int quirks, int64_t B, int dD, int dM, int Nx, int Ny, int Nk,
+                          int Nl, const float* in, const float* out, const float* hin, const float* c,
+                          const float* f, float* gbuf);
+int aefft_coord_update(aefft_ctx* ctx, int mode, int64_t B_global, int dD, int dM, int Nx, int Ny, int Nk, int Nl,
+                       const float* gbuf, float* c, float* b, float* f, float* p, float* dc, float* db, float* df,
+                       float* dp, float* ddc, float* ddb, float* ddf, float* ddp, float delmax, float alpha,
+                       float* mse_dev);
+
+/* ------------------------------------------------------------------ momentum (FFT) space */
+
+/* Batched 2-D real-to-complex / complex-to-real transforms, unnormalised both ways, n={Nx,Ny}; replaces the
+ * cufftPlanMany+cufftExecR2C/C2R call sites fft_backproplib.cu:779/796, 821/829, 885/910, 937/946, 1208-1282.
+ * spec is interleaved (re,im) [batch][Nx][Ny/2+1][2].  Nx, Ny powers of two (8..8192). */
+int aefft_fft_r2c(aefft_ctx* ctx, int loc, int64_t batch, int Nx, int Ny, const float* in, float* spec);
+int aefft_fft_c2r(aefft_ctx* ctx, int loc, int64_t batch, int Nx, int Ny, const float* spec, float* out);
+
+/* kernel_pad (fft_backproplib.cu:1018-1064): c [dM][dD][Nk][Nl] -> c_pad [dM][dD][Nx][Ny] (wrapped). */
+int aefft_kernel_pad(aefft_ctx* ctx, int loc, int dM, int dD, int Nk, int Nl, int Nx, int Ny, const float* c,
+                     float* c_pad);
+
+/* Kernel spectra in the reference's net_cfreq wire format (store_cfreq, fft_backproplib.cu:1117-1127):
+ * interleaved (re,im) float32 [dM][dD][Nx][Ny/2+1][2] = R2C(kernel_pad(c)). */
+int aefft_kernel_spectrum(aefft_ctx* ctx, int loc, int dM, int dD, int Nk, int Nl, int Nx, int Ny, const float* c,
+                          float* cfreq);
+
+/* autoenc_fft (fft_backproplib.cu:1331-1376): full-stack forward in frequency space.
+ *   n_conv convs; conv n has dims[4n..4n+3]=(dM,dD,Nk,Nl), weights c_all+coff[n], bias b_all+boff[n],
+ *   spectral pooling scale[n].  layer l has ldims[3l..3l+2]=(D,Nx,Ny) at layers_all+loff[l] (per frame; frame
+ *   stride lstride floats), n_layers = 2*n_conv+1; layer 0 is the input.  fft_l!=0 writes every layer, else only
+ *   the last.  cfreq_all (+cfoff[n]) is the net_cfreq cache: cfreq_valid!=0 -> used as the kernel spectra;
+ *   ==0 -> rebuilt from c_all and written back (StoreLoad_cfreq :1146-1161).  May be NULL (always rebuild). */
+int aefft_autoenc_fft(aefft_ctx* ctx, int loc, int64_t B, int n_conv, const int* dims, const float* c_all,
+                      const int64_t* coff, const float* b_all, const int64_t* boff, const int* scale, int n_layers,
+                      const int* ldims, float* layers_all, const int64_t* loff, int64_t lstride, int cfreq_valid,
+                      float* cfreq_all, const int64_t* cfoff, int fft_l);
+
+/* backprop_fft (fft_backproplib.cu:1381-1511): n_iter (reference: 100) iterations of spectral gradients ->
+ * kernel-space clipped-momentum update (lr 0.1*del0, alpha 0.9, momentum zeroed per call) -> re-forward.
+ * in, expout, out [B][dD][Nx][Ny]; cfreq/ffreq wire-format spectra (in: cache, out: trained; may be NULL ->
+ * derived from c,f); c,f,b,p updated in place.  mse_trace (host, n_iter+1 floats, may be NULL) receives the
+ * "mse fft:" / "n: .. mse:" values the reference prints (:1441,:1464). */
+int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl,
+                       const float* in, const float* expout, const float* out, float* cfreq, float* c, float* ffreq,
+                       float* f, float* b, float* p, float del0, int maxdiff, int n_iter, float* mse_trace);
+
+/* ------------------------------------------------------------------ glue (netlib.cpp:167-289) */
+
+/* Init_conv (netlib.cpp:167-197): consumes libc rand() in the reference's order; call srand() first. */
+int aefft_init_conv(float* c, float* b, int mS, int dD, int kS, int lS, float rmax);
+/* SaveLoad_conv (netlib.cpp:220-272): byte-exact ./weights/C_weights_{L}{_in,_out}_D=.._M=.._Lk=.._Ll=.._S=...conv
+ * under `dir` (reference: "./weights").  Unlike the reference a missing file is an error (AEFFT_ERR_IO). */
+int aefft_saveload_conv(const char* dir, float* c, float* b, int dM, int dD, int Nk, int Nl, int scale, int L,
+                        int io, int write);
+/* LoadParam (netlib.cpp:274-289): positional name/value pairs dM, Lk, Ll, scale, rmax from `path`
+ * (reference: "New_Layer_Param.txt"). */
+int aefft_load_param(const char* path, int* dM, int* Lk, int* Ll, int* scal, float* rmax);
+
+/* Synthetic frames: pixel = float(splitmix64(seed, linear index of (b0+b,d,i,j)) & 255). */
+int aefft_synth_frames(aefft_ctx* ctx, int loc, uint64_t seed, int64_t b0, int64_t B, int D, int Nx, int Ny,
+                       float* out);
+
+/* ------------------------------------------------------------------ device-resident network
+ * Replays autoencoder.cpp's state model (:69-120, :384-457) with all state in HBM: layers[], net_c[], net_b[],
+ * scale[], momentum, cached spectra.  Pair n: encoder conv n, decoder conv N-1-n (N = 2*pairs). */
+typedef struct aefft_net aefft_net;
+int aefft_net_create(aefft_ctx* ctx, aefft_net** net, int D, int Nx, int Ny, int64_t B);
+int aefft_net_destroy(aefft_net* net);
+/* 'n' key (autoencoder.cpp:384-431): insert a new innermost pair; weights drawn with Init_conv from libc rand(). */
+int aefft_net_add_layer(aefft_net* net, int dM, int Lk, int Ll, int scal, float rmax);
+/* 'd' key (:432-457): remove the innermost pair (never the last one). */
+int aefft_net_delete_layer(aefft_net* net);
+int aefft_net_num_pairs(const aefft_net* net);
+/* copy weights of conv n (0..2*pairs-1) to/from host: c [dM][dD][Nk][Nl], b [dM] */
+int aefft_net_get_conv(aefft_net* net, int n, float* c, float* b);
+int aefft_net_set_conv(aefft_net* net, int n, const float* c, const float* b);
+int aefft_net_conv_dims(const aefft_net* net, int n, int* dM, int* dD, int* Nk, int* Nl, int* scale);
+/* 'p' key (:343-356): copy encoder weights of pair n_l into its decoder (f[d][m]=c[m][d]). */
+int aefft_net_set_symmetric(aefft_net* net, int n_l);
+/* 'z'/'x' keys (:281-292): zero the momentum / last-gradient buffers of pair n_l (the reference shares one set
+ * between all pairs and re-initialises it whenever the active pair changes). */
+int aefft_net_reset_momentum(aefft_net* net, int n_l);
+int aefft_net_num_layers(const aefft_net* net);
+/* layer l (0..2*convs) dims and device pointer ([B][D][Nx][Ny]) */
+int aefft_net_layer(aefft_net* net, int l, int* D, int* Nx, int* Ny, float** dev_ptr);
+/* forward, coordinate space (autoencoder.cpp:135-150): frames = layer 0 ([B][D][Nx][Ny], per `loc`) */
+int aefft_net_forward(aefft_net* net, int loc, const float* frames);
+/* train pair n_l on the activations of the last forward (autoencoder.cpp:158-201, q=1).  *mse host or NULL. */
+int aefft_net_train_pair(aefft_net* net, int n_l, int mode, int quirks, float delmax, float alpha, float* mse);
+/* raw gradient block of pair n_l into the net's gradient buffer (device ptr returned), then update: the
+ * data-parallel split (all-reduce the buffer in between). */
+int aefft_net_pair_gradients(aefft_net* net, int n_l, int mode, int quirks, float** gbuf_dev, int64_t* gbuf_len);
+int aefft_net_pair_update(aefft_net* net, int n_l, int mode, int64_t B_global, float delmax, float alpha, float* mse);
+/* one whole training step: forward + train every pair once (order 0..pairs-1). mse[pairs] host or NULL. */
+int aefft_net_step(aefft_net* net, int loc, const float* frames, int mode, int quirks, float delmax, float alpha,
+                   float* mse);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AEFFT_H */

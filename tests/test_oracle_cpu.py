@@ -1,0 +1,165 @@
+"""CPU tests (no GPU): the numpy oracle (oracle/oracle_np.py) against golden vectors produced by the UNMODIFIED
+reference (tests/golden/make_golden.py -> cpu_golden.npz), live against oracle/_ref/libref.so when it is present,
+plus the host-only glue of libaefft.so (Init_conv, SaveLoad_conv byte format, LoadParam)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_np as O
+from conftest import GOLDEN
+
+G = np.load(os.path.join(GOLDEN, "cpu_golden.npz"))
+
+
+def test_glibc_rand_init_conv_matches_reference_golden():
+    rng = O.GlibcRand(1234)
+    c, b = O.init_conv(rng, 4, 3, 5, 5, 3.0)
+    f, p = O.init_conv(rng, 3, 4, 5, 5, 3.0)
+    for got, key in ((c, "init_c"), (b, "init_b"), (f, "init_f"), (p, "init_p")):
+        assert np.array_equal(got, G[key]), key  # bit-exact: same float32 expression, same draw order
+
+
+def test_pool_golden():
+    x = G["pool_x"]
+    assert np.array_equal(O.pool(x, 2, (6, 5)), G["pool_down2"])
+    assert np.array_equal(O.pool(x, 1, (12, 10)), G["pool_down1"])  # scale 1 still truncates and floors at 0
+    assert np.array_equal(O.pool(G["pool_down2"], -2, (12, 10)), G["pool_up2"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_conv_cpu_golden(tag):
+    out = O.conv_cpu(G[f"conv_{tag}_x"], G[f"conv_{tag}_c"], G[f"conv_{tag}_b"])
+    assert O.rel_l2(out, G[f"conv_{tag}_out"]) < 2e-6
+
+
+@pytest.mark.parametrize("tag", ["c1", "d3", "k3"])
+def test_backprop_cpu_golden(tag):
+    a = {k: G[f"bp_{tag}_{k}"] for k in "inp out hin c b f p".split()}
+    delta = float(G[f"bp_{tag}_delta"])
+    res = O.backprop_cpu(a["inp"], a["out"], a["hin"], a["c"], a["b"], a["f"], a["p"], delta)
+    for k in "cbfp":
+        new = G[f"bp_{tag}_new_{k}"]
+        assert O.rel_l2(res[k], new) < 1e-5, k
+        # the update itself (delta w), not just the weights
+        assert O.rel_l2(res[k] - a[k], new - a[k]) < 1e-3, k
+
+
+def test_backprop_cpu_literal_equals_parallel_formulation():
+    a = {k: G[f"bp_k3_{k}"] for k in "inp out hin c b f p".split()}
+    lit = O.backprop_cpu_literal(a["inp"], a["out"], a["hin"], a["c"], a["b"], a["f"], a["p"], 0.5)
+    par = O.backprop_cpu(a["inp"], a["out"], a["hin"], a["c"], a["b"], a["f"], a["p"], 0.5)
+    for k in "cbfp":
+        assert O.rel_l2(par[k], lit[k]) < 1e-12, k
+
+
+def test_portion_and_kernel_pad_golden():
+    a, h, o = O.portion(G["bp_d3_inp"], G["bp_d3_hin"], G["bp_d3_out"], 2)
+    assert np.array_equal(a, G["portion_in"]) and np.array_equal(h, G["portion_hin"]) and np.array_equal(o, G["portion_out"])
+    assert np.array_equal(O.kernel_pad(G["kpad_c"], 16, 8), G["kpad_out"])
+    assert np.array_equal(O.kernel_shrink(G["kpad_out"], 5, 5), G["kpad_c"])
+
+
+def test_synth_frames_properties():
+    x = O.synth_frames(1234, 2, 3, 8, 6)
+    assert x.shape == (2, 3, 8, 6) and x.dtype == np.float32
+    assert x.min() >= 0 and x.max() <= 255 and np.all(x == np.round(x))
+    # counter based: frame b of a longer batch equals the same frame generated alone
+    assert np.array_equal(O.synth_frames(1234, 1, 3, 8, 6, b0=1)[0], x[1])
+
+
+def test_fft_path_restatement_is_a_gradient_step():
+    """dck = dL/dc / (2 Nx Ny) for L = 1/2 sum e^2 of the circular-conv autoencoder (numerical check)."""
+    rng = np.random.default_rng(0)
+    dD, dM, Nk, Nl, Nx, Ny = 2, 3, 3, 3, 8, 8
+    x = rng.random((dD, Nx, Ny)) * 10
+    c = rng.random((dM, dD, Nk, Nl)) - 0.5
+    f = rng.random((dD, dM, Nk, Nl)) - 0.5
+    b = rng.random(dM) - 0.5
+    p = rng.random(dD) - 0.5
+
+    def fwd(c_):
+        X = O.r2c(x)
+        H = O.conv_k(X, O.kernel_spectrum(c_, Nx, Ny), b, Nx, Ny)
+        Oq = O.conv_k(H, O.kernel_spectrum(f, Nx, Ny), p, Nx, Ny)
+        return X, Oq
+
+    X, Oq = fwd(c)
+    dC, dF, db, dp = O.gradient_k_io(X, X, Oq, O.kernel_spectrum(c, Nx, Ny), O.kernel_spectrum(f, Nx, Ny), b, Nx, Ny)
+    dck = O.kernel_shrink(O.c2r(dC, Ny), Nk, Nl)
+
+    def loss(c_):
+        X_, O_ = fwd(c_)
+        e = O.c2r(O_ - X_, Ny) / (Nx * Ny)
+        return 0.5 * (e**2).sum()
+
+    eps = 1e-5
+    for idx in [(0, 0, 0, 0), (2, 1, 1, 2), (1, 0, 2, 1)]:
+        cp, cm = c.copy(), c.copy()
+        cp[idx] += eps
+        cm[idx] -= eps
+        num = (loss(cp) - loss(cm)) / (2 * eps)
+        assert abs(num / (2 * Nx * Ny) - dck[idx]) < 1e-6 * max(1, abs(dck[idx]))
+
+
+# ---------------------------------------------------------------- live against the compiled reference (when built)
+def test_oracle_live_against_libref(ref):
+    if ref is None:
+        pytest.skip("oracle/_ref/libref.so not built in this checkout")
+    rng = np.random.default_rng(3)
+    dM, dD, Nk, Nl, Nx, Ny = 5, 2, 5, 5, 18, 15
+    inp = (rng.random((dD, Nx, Ny)) * 255).astype(np.float32)
+    c = ((rng.random((dM, dD, Nk, Nl)) * 2 - 1) * 0.2).astype(np.float32)
+    f = ((rng.random((dD, dM, Nk, Nl)) * 2 - 1) * 0.2).astype(np.float32)
+    b = (rng.random(dM) * 2 - 1).astype(np.float32)
+    p = (rng.random(dD) * 2 - 1).astype(np.float32)
+    hin = ref.conv_cpu(inp, c, b)
+    assert O.rel_l2(O.conv_cpu(inp, c, b), hin) < 2e-6
+    out = ref.conv_cpu(hin, f, p)
+    want = ref.backprop_cpu(inp, out, hin, c, b, f, p, 0.2)
+    got = O.backprop_cpu(inp, out, hin, c, b, f, p, 0.2)
+    for k in "cbfp":
+        assert O.rel_l2(got[k], want[k]) < 1e-5, k
+    ref.srand(99)
+    rc, rb = ref.init_conv(3, 2, 3, 3, 1.5)
+    oc, ob = O.init_conv(O.GlibcRand(99), 3, 2, 3, 3, 1.5)
+    assert np.array_equal(rc, oc) and np.array_equal(rb, ob)
+
+
+# ---------------------------------------------------------------- host-only glue of the product library
+def test_product_init_conv_matches_reference_draw_order():
+    import ctypes
+
+    import aefft_ctypes as A
+
+    ctypes.CDLL("libc.so.6").srand(1234)
+    c, b = A.init_conv(4, 3, 5, 5, 3.0)
+    f, p = A.init_conv(3, 4, 5, 5, 3.0)
+    for got, key in ((c, "init_c"), (b, "init_b"), (f, "init_f"), (p, "init_p")):
+        assert np.array_equal(got, G[key]), key
+
+
+def test_product_saveload_conv_is_byte_exact(tmp_path):
+    import aefft_ctypes as A
+
+    c, b = np.ascontiguousarray(G["conv_a_c"]), np.ascontiguousarray(G["conv_a_b"])
+    A.saveload_conv(tmp_path, c, b, 2, 0, 0, 1)
+    name = str(G["save_name"])
+    path = tmp_path / name
+    assert path.exists(), f"expected the reference's file name {name}, have {os.listdir(tmp_path)}"
+    assert np.array_equal(np.frombuffer(path.read_bytes(), np.uint8), G["save_bytes"])
+    c2, b2 = np.zeros_like(c), np.zeros_like(b)
+    A.saveload_conv(tmp_path, c2, b2, 2, 0, 0, 0)
+    assert np.array_equal(c2, c) and np.array_equal(b2, b)
+    with pytest.raises(A.AefftError):  # unlike the reference (silent zeros, N5) a missing file is an error
+        A.saveload_conv(tmp_path, c2, b2, 2, 7, 1, 0)
+
+
+def test_product_load_param(tmp_path):
+    import aefft_ctypes as A
+
+    pth = tmp_path / "New_Layer_Param.txt"
+    pth.write_text("Layer_depth 10\nKernel_L_x 1\nKernel_L_y 1\nPooling_scale 2\nMax_Rand_Init 3\n")
+    assert A.load_param(pth) == (10, 1, 1, 2, 3.0)
+    with pytest.raises(A.AefftError):
+        A.load_param(tmp_path / "missing.txt")
