@@ -183,6 +183,26 @@ struct UpdateArgs {
 };
 int launch_update(aefft_ctx* ctx, const UpdateArgs& a);
 
+// ---- momentum-space launchers (fft_kernels.cu / spectral_kernels.cu) ---------------------------------
+// batched 2-D R2C / C2R, unnormalised, n = {Nx, Ny} powers of two; spectra [batch][Nx][Ny/2+1] complex64
+int launch_fft_r2c(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float* in, float2* spec);
+int launch_fft_c2r(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float2* spec, float2* work, float* out,
+                   float scale);
+int launch_spec_resize(aefft_ctx* ctx, int64_t planes, int Nx, int Ny, int Nxs, int Nys, const float2* in, float2* out);
+int launch_spec_contract(aefft_ctx* ctx, int64_t B, int C, int O, int64_t S, const float2* in0, const float2* in1,
+                         const float2* W, int64_t w_so, int64_t w_sc, int conjW, float in_scale, const float* bias,
+                         float bias_scale, float2* out);
+int launch_spec_outer(aefft_ctx* ctx, int64_t B, int nA, int nC, int64_t S, const float2* A0, const float2* A1,
+                      const float2* Bm, float bm_alpha, const float* bm_bias, float bm_bias_scale, float scale, float2* out);
+int launch_spec_dc_sums(aefft_ctx* ctx, int64_t B, int dM, int dD, int64_t S, const float2* G, const float2* O,
+                        const float2* Xt, float* db, float* dp, float gscale);
+int launch_pad(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* taps, float* img);
+int launch_shrink(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* img, float* taps);
+int launch_fft_update(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, float* c, float* f, float* b, float* p,
+                      const float* dck, const float* dfk, const float* db, const float* dp, float* Dc, float* Df, float* Db,
+                      float* Dp, float del, int maxdiff, float* div_scratch);
+int launch_spec_mse(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx, int Ny, const float2* Xt, const float2* O, float* out);
+
 // ---- host orchestration shared by capi.cu and net.cu ------------------------------------------------
 int64_t gbuf_len(int mode, int dD, int dM, int Nk, int Nl);
 int coord_gradients_dev(aefft_ctx* ctx, int mode, int quirks, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl,

@@ -1,0 +1,351 @@
+// C ABI, momentum (FFT) space: batched transforms, kernel spectra, autoenc_fft and backprop_fft.
+// Host orchestration only; the kernels live in fft_kernels.cu and spectral_kernels.cu.
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace aefft;
+
+namespace aefft {
+
+static bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+// C = R2C(pad(c)) for n_img kernels (StoreLoad_cfreq first-time branch, fft_backproplib.cu:1148-1157; backprop :1274-1282)
+static int kernel_spectrum_dev(aefft_ctx* ctx, int64_t n_img, int Nk, int Nl, int Nx, int Ny, const float* taps, float* img,
+                               float2* spec) {
+  AE_TRY(launch_pad(ctx, n_img, Nx, Ny, Nk, Nl, taps, img));
+  return launch_fft_r2c(ctx, n_img, Nx, Ny, img, spec);
+}
+
+struct FftPairBufs {
+  float2 *X, *Xt, *O, *H, *G, *C, *F, *dCF, *work;
+  float *img, *taps, *db, *dp, *Dc, *Df, *Db, *Dp, *div, *mse;
+};
+
+}  // namespace aefft
+
+extern "C" {
+
+int aefft_fft_r2c(aefft_ctx* ctx, int loc, int64_t batch, int Nx, int Ny, const float* in, float* spec) {
+  AE_ARG(ctx && in && spec && batch > 0 && pow2(Nx) && pow2(Ny));
+  AE_CUDA(cudaSetDevice(ctx->device));
+  const size_t nin = (size_t)batch * Nx * Ny, nsp = (size_t)batch * Nx * (Ny / 2 + 1) * 2;
+  const float* din = in;
+  float* dsp = spec;
+  if (loc == AEFFT_HOST) {
+    float* t;
+    AE_TRY(ctx->getT("fft_in", nin, &t));
+    AE_CUDA(cudaMemcpyAsync(t, in, nin * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    din = t;
+    AE_TRY(ctx->getT("fft_spec", nsp, &dsp));
+  }
+  AE_TRY(launch_fft_r2c(ctx, batch, Nx, Ny, din, (float2*)dsp));
+  if (loc == AEFFT_HOST) {
+    AE_CUDA(cudaMemcpyAsync(spec, dsp, nsp * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return AEFFT_OK;
+}
+
+int aefft_fft_c2r(aefft_ctx* ctx, int loc, int64_t batch, int Nx, int Ny, const float* spec, float* out) {
+  AE_ARG(ctx && spec && out && batch > 0 && pow2(Nx) && pow2(Ny));
+  AE_CUDA(cudaSetDevice(ctx->device));
+  const size_t nout = (size_t)batch * Nx * Ny, nsp = (size_t)batch * Nx * (Ny / 2 + 1) * 2;
+  const float* dsp = spec;
+  float* dout = out;
+  float* work;
+  AE_TRY(ctx->getT("fft_work", nsp, &work));
+  if (loc == AEFFT_HOST) {
+    float* t;
+    AE_TRY(ctx->getT("fft_spec", nsp, &t));
+    AE_CUDA(cudaMemcpyAsync(t, spec, nsp * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    dsp = t;
+    AE_TRY(ctx->getT("fft_in", nout, &dout));
+  }
+  AE_TRY(launch_fft_c2r(ctx, batch, Nx, Ny, (const float2*)dsp, (float2*)work, dout, 1.f));
+  if (loc == AEFFT_HOST) {
+    AE_CUDA(cudaMemcpyAsync(out, dout, nout * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return AEFFT_OK;
+}
+
+int aefft_kernel_pad(aefft_ctx* ctx, int loc, int dM, int dD, int Nk, int Nl, int Nx, int Ny, const float* c,
+                     float* c_pad) {
+  AE_ARG(ctx && c && c_pad && dM > 0 && dD > 0 && Nk > 0 && Nl > 0 && Nk <= Nx && Nl <= Ny);
+  AE_CUDA(cudaSetDevice(ctx->device));
+  const size_t nC = (size_t)dM * dD * Nk * Nl, nI = (size_t)dM * dD * Nx * Ny;
+  const float* dc = c;
+  float* di = c_pad;
+  if (loc == AEFFT_HOST) {
+    float* t;
+    AE_TRY(ctx->getT("kp_c", nC, &t));
+    AE_CUDA(cudaMemcpyAsync(t, c, nC * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    dc = t;
+    AE_TRY(ctx->getT("kp_img", nI, &di));
+  }
+  AE_TRY(launch_pad(ctx, (int64_t)dM * dD, Nx, Ny, Nk, Nl, dc, di));
+  if (loc == AEFFT_HOST) {
+    AE_CUDA(cudaMemcpyAsync(c_pad, di, nI * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return AEFFT_OK;
+}
+
+int aefft_kernel_spectrum(aefft_ctx* ctx, int loc, int dM, int dD, int Nk, int Nl, int Nx, int Ny, const float* c,
+                          float* cfreq) {
+  AE_ARG(ctx && c && cfreq && dM > 0 && dD > 0 && Nk > 0 && Nl > 0 && Nk <= Nx && Nl <= Ny && pow2(Nx) && pow2(Ny));
+  AE_CUDA(cudaSetDevice(ctx->device));
+  const size_t nC = (size_t)dM * dD * Nk * Nl, nI = (size_t)dM * dD * Nx * Ny, nS = (size_t)dM * dD * Nx * (Ny / 2 + 1) * 2;
+  const float* dc = c;
+  float *img, *ds = cfreq;
+  AE_TRY(ctx->getT("kp_img", nI, &img));
+  if (loc == AEFFT_HOST) {
+    float* t;
+    AE_TRY(ctx->getT("kp_c", nC, &t));
+    AE_CUDA(cudaMemcpyAsync(t, c, nC * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    dc = t;
+    AE_TRY(ctx->getT("kp_spec", nS, &ds));
+  }
+  AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc, img, (float2*)ds));
+  if (loc == AEFFT_HOST) {
+    AE_CUDA(cudaMemcpyAsync(cfreq, ds, nS * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return AEFFT_OK;
+}
+
+// autoenc_fft (fft_backproplib.cu:1331-1376).  Activations stay in frequency space across the whole stack; layers are
+// inverse-transformed only where the caller asks (fft_l) -- and, unlike the reference, the inverse transform never
+// clobbers the spectrum it reads (cuFFT's multi-dimensional C2R overwrites its input, so with fft_l=1 the reference
+// continues from garbage; see DESIGN.md "reference defects").
+int aefft_autoenc_fft(aefft_ctx* ctx, int loc, int64_t B, int n_conv, const int* dims, const float* c_all,
+                      const int64_t* coff, const float* b_all, const int64_t* boff, const int* scale, int n_layers,
+                      const int* ldims, float* layers_all, const int64_t* loff, int64_t lstride, int cfreq_valid,
+                      float* cfreq_all, const int64_t* cfoff, int fft_l) {
+  AE_ARG(ctx && dims && c_all && coff && b_all && boff && scale && ldims && layers_all && loff);
+  AE_ARG(B > 0 && n_conv >= 2 && n_conv % 2 == 0 && n_layers == 2 * n_conv + 1);
+  AE_ARG(!cfreq_valid || (cfreq_all && cfoff));
+  AE_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  // ---- plan: resolutions per conv, buffer sizes
+  int D = ldims[0], Nx = ldims[1], Ny = ldims[2];
+  AE_ARG(pow2(Nx) && pow2(Ny));
+  size_t max_spec = (size_t)B * D * Nx * (Ny / 2 + 1), max_real = (size_t)B * D * Nx * Ny, max_kimg = 0, max_kspec = 0;
+  size_t tot_c = 0, tot_b = 0;
+  {
+    int d = D, nx = Nx, ny = Ny;
+    for (int n = 0; n < n_conv; n++) {
+      const int dM = dims[4 * n], dD = dims[4 * n + 1], Nk = dims[4 * n + 2], Nl = dims[4 * n + 3];
+      AE_ARG(dD == d && scale[n] != 0);
+      auto rs = [&](int s) {
+        if (s == 1) return;
+        float l = s > 0 ? (float)s : -1.f / (float)s;
+        nx = (int)(nx / l);
+        ny = (int)(ny / l);
+      };
+      if (n < n_conv / 2) rs(scale[n]);
+      AE_ARG(pow2(nx) && pow2(ny) && Nk <= nx && Nl <= ny);
+      size_t s1 = (size_t)B * (dM > dD ? dM : dD) * nx * (ny / 2 + 1), r1 = (size_t)B * (dM > dD ? dM : dD) * nx * ny;
+      if (s1 > max_spec) max_spec = s1;
+      if (r1 > max_real) max_real = r1;
+      size_t ki = (size_t)dM * dD * nx * ny, ks = (size_t)dM * dD * nx * (ny / 2 + 1);
+      if (ki > max_kimg) max_kimg = ki;
+      if (ks > max_kspec) max_kspec = ks;
+      if (n >= n_conv / 2) {
+        rs(scale[n]);
+        size_t s2 = (size_t)B * dM * nx * (ny / 2 + 1), r2 = (size_t)B * dM * nx * ny;
+        if (s2 > max_spec) max_spec = s2;
+        if (r2 > max_real) max_real = r2;
+      }
+      d = dM;
+      tot_c = (size_t)coff[n] + (size_t)dM * dD * Nk * Nl > tot_c ? (size_t)coff[n] + (size_t)dM * dD * Nk * Nl : tot_c;
+      tot_b = (size_t)boff[n] + dM > tot_b ? (size_t)boff[n] + dM : tot_b;
+    }
+  }
+  float2 *fa, *fb, *work, *kspec;
+  float *real, *kimg, *dc_all, *db_all;
+  AE_TRY(ctx->getT("aef_fa", max_spec, &fa));
+  AE_TRY(ctx->getT("aef_fb", max_spec, &fb));
+  AE_TRY(ctx->getT("aef_work", max_spec, &work));
+  AE_TRY(ctx->getT("aef_real", max_real, &real));
+  AE_TRY(ctx->getT("aef_kimg", max_kimg, &kimg));
+  AE_TRY(ctx->getT("aef_kspec", max_kspec, &kspec));
+  const float* cw = c_all;
+  const float* bw = b_all;
+  if (loc == AEFFT_HOST) {
+    AE_TRY(ctx->getT("aef_c", tot_c, &dc_all));
+    AE_TRY(ctx->getT("aef_b", tot_b, &db_all));
+    AE_CUDA(cudaMemcpyAsync(dc_all, c_all, tot_c * sizeof(float), cudaMemcpyHostToDevice, st));
+    AE_CUDA(cudaMemcpyAsync(db_all, b_all, tot_b * sizeof(float), cudaMemcpyHostToDevice, st));
+    cw = dc_all;
+    bw = db_all;
+  }
+  const cudaMemcpyKind k_in = loc == AEFFT_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  const cudaMemcpyKind k_out = loc == AEFFT_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  // gather layer 0 of every frame into a contiguous [B][D][Nx][Ny] block
+  {
+    const size_t w = (size_t)D * Nx * Ny * sizeof(float);
+    AE_CUDA(cudaMemcpy2DAsync(real, w, layers_all + loff[0], (size_t)lstride * sizeof(float), w, (size_t)B, k_in, st));
+  }
+  AE_TRY(launch_fft_r2c(ctx, B * D, Nx, Ny, real, fa));
+  float2 *freq = fa, *other = fb;
+  int l = 1;
+  auto emit_layer = [&](const float2* spec, int ch, int nx, int ny) -> int {
+    AE_ARG(l < n_layers && ldims[3 * l] == ch && ldims[3 * l + 1] == nx && ldims[3 * l + 2] == ny);
+    AE_TRY(launch_fft_c2r(ctx, B * ch, nx, ny, spec, work, real, 1.f / ((float)nx * (float)ny)));  // fft_inv :831
+    const size_t w = (size_t)ch * nx * ny * sizeof(float);
+    AE_CUDA(cudaMemcpy2DAsync(layers_all + loff[l], (size_t)lstride * sizeof(float), real, w, w, (size_t)B, k_out, st));
+    return AEFFT_OK;
+  };
+  auto do_resize = [&](int ch, int s) -> int {
+    if (s == 1) return AEFFT_OK;
+    float lf = s > 0 ? (float)s : -1.f / (float)s;
+    const int nxs = (int)(Nx / lf), nys = (int)(Ny / lf);
+    AE_TRY(launch_spec_resize(ctx, B * ch, Nx, Ny, nxs, nys, freq, other));
+    std::swap(freq, other);
+    Nx = nxs;
+    Ny = nys;
+    return AEFFT_OK;
+  };
+  for (int n = 0; n < n_conv; n++) {
+    const int dM = dims[4 * n], dD = dims[4 * n + 1], Nk = dims[4 * n + 2], Nl = dims[4 * n + 3];
+    if (n < n_conv / 2) {
+      AE_TRY(do_resize(dD, scale[n]));
+      if (fft_l) { AE_TRY(emit_layer(freq, dD, Nx, Ny)); l++; }
+    }
+    const int64_t S = (int64_t)Nx * (Ny / 2 + 1);
+    const size_t nks = (size_t)dM * dD * S;
+    if (cfreq_valid) {
+      AE_CUDA(cudaMemcpyAsync(kspec, cfreq_all + cfoff[n], nks * sizeof(float2), k_in, st));  // load_cfreq :1131-1141
+    } else {
+      AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, cw + coff[n], kimg, kspec));
+      if (cfreq_all && cfoff)
+        AE_CUDA(cudaMemcpyAsync(cfreq_all + cfoff[n], kspec, nks * sizeof(float2), k_out, st));  // store_cfreq :1117-1127
+    }
+    // conv_k (:162-189): out[m] = sum_d (in[d]/dM) c[m][d] + b[m] Nx Ny at DC
+    AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, freq, nullptr, kspec, (int64_t)dD * S, S, 0, 1.f / (float)dM, bw + boff[n],
+                                (float)Nx * (float)Ny, other));
+    std::swap(freq, other);
+    if (fft_l) { AE_TRY(emit_layer(freq, dM, Nx, Ny)); l++; }
+    if (n >= n_conv / 2) {
+      AE_TRY(do_resize(dM, scale[n]));
+      if (fft_l) { AE_TRY(emit_layer(freq, dM, Nx, Ny)); l++; }
+    }
+    D = dM;
+  }
+  if (!fft_l) {
+    l = n_layers - 1;
+    AE_TRY(emit_layer(freq, D, Nx, Ny));
+  }
+  AE_CUDA(cudaStreamSynchronize(st));
+  return AEFFT_OK;
+}
+
+// backprop_fft (fft_backproplib.cu:1381-1511).
+int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl,
+                       const float* in, const float* expout, const float* out, float* cfreq, float* c, float* ffreq,
+                       float* f, float* b, float* p, float del0, int maxdiff, int n_iter, float* mse_trace) {
+  AE_ARG(ctx && in && expout && out && c && f && b && p);
+  AE_ARG(B > 0 && dD > 0 && dM > 0 && pow2(Nx) && pow2(Ny) && Nk <= Nx && Nl <= Ny && n_iter >= 0);
+  AE_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int64_t S = (int64_t)Nx * (Ny / 2 + 1);
+  const size_t P = (size_t)Nx * Ny, nC = (size_t)dM * dD * Nk * Nl, nKS = (size_t)dM * dD * S;
+  const size_t nXs = (size_t)B * dD * S, nHs = (size_t)B * dM * S;
+  const cudaMemcpyKind k_in = loc == AEFFT_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  const cudaMemcpyKind k_out = loc == AEFFT_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  FftPairBufs q;
+  float *real, *wts;  // wts = [c | f | b | p]
+  AE_TRY(ctx->getT("bpf_X", nXs, &q.X));
+  AE_TRY(ctx->getT("bpf_Xt", nXs, &q.Xt));
+  AE_TRY(ctx->getT("bpf_O", nXs, &q.O));
+  AE_TRY(ctx->getT("bpf_H", nHs, &q.H));
+  AE_TRY(ctx->getT("bpf_G", nHs, &q.G));
+  AE_TRY(ctx->getT("bpf_C", nKS, &q.C));
+  AE_TRY(ctx->getT("bpf_F", nKS, &q.F));
+  AE_TRY(ctx->getT("bpf_dCF", 2 * nKS, &q.dCF));
+  AE_TRY(ctx->getT("bpf_work", 2 * nKS > nXs ? 2 * nKS : nXs, &q.work));
+  AE_TRY(ctx->getT("bpf_img", 2 * (size_t)dM * dD * P, &q.img));
+  AE_TRY(ctx->getT("bpf_real", (size_t)B * dD * P, &real));
+  AE_TRY(ctx->getT("bpf_taps", 2 * nC, &q.taps));
+  AE_TRY(ctx->getT("bpf_wts", 2 * nC + dM + dD, &wts));
+  float* small;
+  AE_TRY(ctx->getT("bpf_small", 2 * (size_t)(dM + dD) + 2 * nC + 2 * nC + dM + dD + (size_t)n_iter + 1, &small));
+  q.db = small; q.dp = q.db + dM; q.Db = q.dp + dD; q.Dp = q.Db + dM;
+  q.Dc = q.Dp + dD; q.Df = q.Dc + nC; q.div = q.Df + nC; q.mse = q.div + 2 * nC + dM + dD;
+  float *dc_w = wts, *df_w = wts + nC, *db_w = wts + 2 * nC, *dp_w = db_w + dM;
+  // momentum buffers are zeroed at the start of every call (:1420-1423)
+  AE_CUDA(cudaMemsetAsync(q.Db, 0, (2 * (size_t)(dM + dD) - dM - dD + 2 * nC) * sizeof(float), st));
+  AE_CUDA(cudaMemcpyAsync(dc_w, c, nC * sizeof(float), k_in, st));  // flatten_kernel :1436-1437
+  AE_CUDA(cudaMemcpyAsync(df_w, f, nC * sizeof(float), k_in, st));
+  AE_CUDA(cudaMemcpyAsync(db_w, b, dM * sizeof(float), k_in, st));
+  AE_CUDA(cudaMemcpyAsync(dp_w, p, dD * sizeof(float), k_in, st));
+  // fft(in), fft(expout), fft(out) (:1430-1432)
+  auto load_fft = [&](const float* src, float2* dst) -> int {
+    const float* d = src;
+    if (loc == AEFFT_HOST) {
+      AE_CUDA(cudaMemcpyAsync(real, src, (size_t)B * dD * P * sizeof(float), cudaMemcpyHostToDevice, st));
+      d = real;
+    }
+    return launch_fft_r2c(ctx, B * dD, Nx, Ny, d, dst);
+  };
+  AE_TRY(load_fft(in, q.X));
+  const float2* Xt = q.X;
+  if (expout != in) {
+    AE_TRY(load_fft(expout, q.Xt));
+    Xt = q.Xt;
+  }
+  AE_TRY(load_fft(out, q.O));
+  // kernel spectra: the caller's cache (load_cfreq :1434-1435) or derived from c,f
+  if (cfreq) AE_CUDA(cudaMemcpyAsync(q.C, cfreq, nKS * sizeof(float2), k_in, st));
+  else AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C));
+  if (ffreq) AE_CUDA(cudaMemcpyAsync(q.F, ffreq, nKS * sizeof(float2), k_in, st));
+  else AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F));
+  const float norm = (float)Nx * (float)Ny;
+  AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse));  // "mse fft:" (:1440)
+  // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1)
+  AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, db_w, norm, q.H));
+  const float del = 0.1f * del0;                                        // :1445
+  const double Norm = (double)norm * 2.0 * dM * dD * (double)Nx * Ny;   // :399
+  const float gscale = (float)(1.0 / (Norm * (double)B));
+  for (int n = 0; n < n_iter; n++) {
+    // G[m] = sum_d1 (O - Xt)[d1] conj(F[d1][m])
+    AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.O, Xt, q.F, S, (int64_t)dM * S, 1, 1.f, nullptr, 0.f, q.G));
+    // dC[m][d] = G[m] conj(X[d]) / Norm ; dF[d][m] = E[d] conj(H-hat[m]) / Norm, averaged over frames
+    AE_TRY(launch_spec_outer(ctx, B, dM, dD, S, q.G, nullptr, q.X, 1.f, nullptr, 0.f, gscale, q.dCF));
+    AE_TRY(launch_spec_outer(ctx, B, dD, dM, S, q.O, Xt, q.H, (float)dM, db_w, -(float)(dM - 1) * norm, gscale, q.dCF + nKS));
+    AE_TRY(launch_spec_dc_sums(ctx, B, dM, dD, S, q.G, q.O, Xt, q.db, q.dp, (float)((double)norm / (Norm * (double)B))));
+    // kernel-space gradients: C2R (unnormalised) + shrink_k (:1219-1226)
+    AE_TRY(launch_fft_c2r(ctx, 2 * (int64_t)dM * dD, Nx, Ny, q.dCF, q.work, q.img, 1.f));
+    AE_TRY(launch_shrink(ctx, 2 * (int64_t)dM * dD, Nx, Ny, Nk, Nl, q.img, q.taps));
+    // clipped-momentum update in kernel space (+ multiobjective term)
+    AE_TRY(launch_fft_update(ctx, dM, dD, Nk, Nl, dc_w, df_w, db_w, dp_w, q.taps, q.taps + nC, q.db, q.dp, q.Dc, q.Df, q.Db,
+                             q.Dp, del, maxdiff, q.div));
+    // new kernel spectra: pad_k + R2C (:1274-1282); c and f are adjacent in wts -> one batched transform
+    AE_TRY(launch_pad(ctx, 2 * (int64_t)dM * dD, Nx, Ny, Nk, Nl, wts, q.img));
+    AE_TRY(launch_fft_r2c(ctx, (int64_t)dM * dD, Nx, Ny, q.img, q.C));
+    AE_TRY(launch_fft_r2c(ctx, (int64_t)dM * dD, Nx, Ny, q.img + (size_t)dM * dD * P, q.F));
+    // re-forward (:1460-1461) and mse (:1463)
+    AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, db_w, norm, q.H));
+    AE_TRY(launch_spec_contract(ctx, B, dM, dD, S, q.H, nullptr, q.F, (int64_t)dM * S, S, 0, 1.f / (float)dD, dp_w, norm, q.O));
+    AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse + n + 1));
+  }
+  // store_cfreq (:1484-1485) and export_cfreq (:1487-1488: c,f re-derived from the spectra: C2R/(NxNy) + kernel_invpad)
+  if (cfreq) AE_CUDA(cudaMemcpyAsync(cfreq, q.C, nKS * sizeof(float2), k_out, st));
+  if (ffreq) AE_CUDA(cudaMemcpyAsync(ffreq, q.F, nKS * sizeof(float2), k_out, st));
+  AE_TRY(launch_fft_c2r(ctx, (int64_t)dM * dD, Nx, Ny, q.C, q.work, q.img, 1.f / norm));
+  AE_TRY(launch_fft_c2r(ctx, (int64_t)dM * dD, Nx, Ny, q.F, q.work, q.img + (size_t)dM * dD * P, 1.f / norm));
+  AE_TRY(launch_shrink(ctx, 2 * (int64_t)dM * dD, Nx, Ny, Nk, Nl, q.img, q.taps));
+  AE_CUDA(cudaMemcpyAsync(c, q.taps, nC * sizeof(float), k_out, st));
+  AE_CUDA(cudaMemcpyAsync(f, q.taps + nC, nC * sizeof(float), k_out, st));
+  AE_CUDA(cudaMemcpyAsync(b, db_w, dM * sizeof(float), k_out, st));
+  AE_CUDA(cudaMemcpyAsync(p, dp_w, dD * sizeof(float), k_out, st));
+  if (mse_trace)
+    AE_CUDA(cudaMemcpyAsync(mse_trace, q.mse, ((size_t)n_iter + 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
+  AE_CUDA(cudaStreamSynchronize(st));
+  return AEFFT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,465 @@
+// Momentum-space (per-frequency-bin) kernels: spectral pooling, the per-bin channel contractions of the forward and of
+// the gradients, kernel pad/shrink, the kernel-space clipped-momentum update with the multiobjective term, and the
+// Hermitian-weighted MSE.  Half spectra are [frame][channel][Nx][Ny/2+1] complex64, bins (w) fastest, so every kernel
+// below maps threads to consecutive bins (coalesced 8-byte accesses) and keeps a small channel x frame register tile.
+//
+// Reference kernels replaced (fft_backproplib.cu): resize :87-157, conv_k :162-189, gradient_k_io :395-475,
+// calc_mse + thrust::reduce :480-498/1178-1192, shrink_k :535-565, pad_k :570-600, backprop_d :605-652,
+// backprop_double :657-704, gradient_diff :709-753.
+#include "common.cuh"
+
+namespace aefft {
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ void cfma(float2& acc, float2 a, float2 b) {  // acc += a*b
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cfma_conj(float2& acc, float2 a, float2 b) {  // acc += a*conj(b)
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(a.y, b.y, acc.x);
+  acc.y = fmaf(a.y, b.x, acc.y); acc.y = fmaf(-a.x, b.y, acc.y);
+}
+
+// ------------------------------------------------------------------------------------------------ spectral pooling
+// resize (:87-157): scale>1 crops the half spectrum around zero frequency, scale<0 embeds it into a zeroed larger
+// one; the Nyquist column/row of the source lands on the Nyquist of the target; no amplitude rescale.
+__global__ void spec_resize_kernel(const float2* __restrict__ in, float2* __restrict__ out, long long planes, int Nx,
+                                   int Ny, int Nxs, int Nys) {
+  const int Nyr = Ny / 2 + 1, Nyrs = Nys / 2 + 1;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= planes * Nxs * Nyrs) return;
+  const int j = idx % Nyrs;
+  const int i = (idx / Nyrs) % Nxs;
+  const long long d = idx / ((long long)Nyrs * Nxs);
+  const float2* src = in + d * (long long)Nx * Nyr;
+  float2 v = make_float2(0.f, 0.f);
+  if (Nxs <= Nx) {
+    const int si = i < Nxs / 2 ? i : (i == Nxs / 2 ? Nx / 2 : i + Nx - Nxs);
+    const int sj = j < Nyrs - 1 ? j : Nyr - 1;
+    v = src[(long long)si * Nyr + sj];
+  } else {
+    int si = -1;
+    if (i < Nx / 2) si = i;
+    else if (i > Nxs - Nx / 2) si = i - Nxs + Nx;
+    else if (i == Nxs / 2) si = Nx / 2;
+    int sj = -1;
+    if (j == Nyrs - 1) sj = Nyr - 1;      // (the reference tests j<Nyr-1 first; j==Nyrs-1 never satisfies it when upsampling)
+    else if (j < Nyr - 1) sj = j;
+    if (si >= 0 && sj >= 0) v = src[(long long)si * Nyr + sj];
+  }
+  out[idx] = v;
+}
+
+int launch_spec_resize(aefft_ctx* ctx, int64_t planes, int Nx, int Ny, int Nxs, int Nys, const float2* in, float2* out) {
+  const long long total = (long long)planes * Nxs * (Nys / 2 + 1);
+  ProfScope prof(ctx, "spec_resize", 0.0, 8.0 * (total + (double)planes * (Nxs <= Nx ? Nxs : Nx) * (Nys / 2 + 1)));
+  spec_resize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(in, out, planes, Nx, Ny, Nxs, Nys);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ per-bin contraction
+// out[b][o][w] = sum_c Wt(o,c)[w] * (in_scale * (in0[b][c][w] - in1[b][c][w])) + [w==0] bias[o]*bias_scale
+//   Wt(o,c) = W[o*w_so + c*w_sc + w], conjugated when conjW.
+// conv_k (:162-189):           in_scale = 1/dM, W = C[m][d], bias b*Nx*Ny
+// G of gradient_k_io (:410-419): in = O - Xt, W = conj(F[d1][m])
+constexpr int SC_OT = 4, SC_FT = 4, SC_THREADS = 128;
+
+struct ContractParams {
+  const float2* in0;
+  const float2* in1;
+  const float2* W;
+  const float* bias;
+  float2* out;
+  long long w_so, w_sc, S;
+  int B, C, O, conjW;
+  float in_scale, bias_scale;
+};
+
+__global__ void __launch_bounds__(SC_THREADS) spec_contract_kernel(ContractParams p) {
+  const long long w = (long long)blockIdx.x * SC_THREADS + threadIdx.x;
+  if (w >= p.S) return;
+  const int o0 = blockIdx.y * SC_OT, b0 = blockIdx.z * SC_FT;
+  float2 acc[SC_OT][SC_FT];
+#pragma unroll
+  for (int o = 0; o < SC_OT; o++)
+#pragma unroll
+    for (int f = 0; f < SC_FT; f++) acc[o][f] = make_float2(0.f, 0.f);
+  for (int c = 0; c < p.C; c++) {
+    float2 x[SC_FT], wv[SC_OT];
+#pragma unroll
+    for (int f = 0; f < SC_FT; f++) {
+      x[f] = make_float2(0.f, 0.f);
+      if (b0 + f < p.B) {
+        const long long off = ((long long)(b0 + f) * p.C + c) * p.S + w;
+        float2 v = p.in0[off];
+        if (p.in1) { float2 u = p.in1[off]; v.x -= u.x; v.y -= u.y; }
+        x[f] = make_float2(v.x * p.in_scale, v.y * p.in_scale);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < SC_OT; o++) {
+      wv[o] = make_float2(0.f, 0.f);
+      if (o0 + o < p.O) {
+        wv[o] = __ldg(p.W + (o0 + o) * p.w_so + c * p.w_sc + w);
+        if (p.conjW) wv[o].y = -wv[o].y;
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < SC_OT; o++)
+#pragma unroll
+      for (int f = 0; f < SC_FT; f++) cfma(acc[o][f], x[f], wv[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < SC_OT; o++) {
+    if (o0 + o >= p.O) continue;
+    const float bv = (w == 0 && p.bias) ? p.bias[o0 + o] * p.bias_scale : 0.f;
+#pragma unroll
+    for (int f = 0; f < SC_FT; f++) {
+      if (b0 + f >= p.B) continue;
+      float2 v = acc[o][f];
+      v.x += bv;
+      p.out[((long long)(b0 + f) * p.O + o0 + o) * p.S + w] = v;
+    }
+  }
+}
+
+int launch_spec_contract(aefft_ctx* ctx, int64_t B, int C, int O, int64_t S, const float2* in0, const float2* in1,
+                         const float2* W, int64_t w_so, int64_t w_sc, int conjW, float in_scale, const float* bias,
+                         float bias_scale, float2* out) {
+  AE_ARG(B > 0 && C > 0 && O > 0 && S > 0);
+  ContractParams p{in0, in1, W, bias, out, w_so, w_sc, S, (int)B, C, O, conjW, in_scale, bias_scale};
+  dim3 grid((unsigned)((S + SC_THREADS - 1) / SC_THREADS), (O + SC_OT - 1) / SC_OT, (unsigned)((B + SC_FT - 1) / SC_FT));
+  AE_ARG(grid.z <= 65535 && grid.y <= 65535);
+  ProfScope prof(ctx, "spec_contract", 8.0 * B * C * O * S, 8.0 * S * ((double)B * C * (in1 ? 2 : 1) + (double)B * O + (double)C * O));
+  spec_contract_kernel<<<grid, SC_THREADS, 0, ctx->stream>>>(p);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ per-bin outer product
+// out[a][c][w] = scale * sum_b (A0[b][a][w] - A1[b][a][w]) * conj( bm_alpha * Bm[b][c][w] + [w==0] bm_bias[c]*bm_bias_scale )
+//   dC = G . conj(X)           (gradient_k_io :437-445)
+//   dF = E . conj(H-hat)       (:447-459; H-hat = dM*H - (dM-1)*b*Nx*Ny at DC: quirk F1, no /dM)
+// The frame index is the reduction dimension (this repo's batch extension; B=1 is the reference).
+constexpr int SO_AT = 4, SO_CT = 4;
+
+struct OuterParams {
+  const float2* A0;
+  const float2* A1;
+  const float2* Bm;
+  const float* bm_bias;
+  float2* out;
+  long long S;
+  int B, nA, nC;
+  float bm_alpha, bm_bias_scale, scale;
+};
+
+__global__ void __launch_bounds__(SC_THREADS) spec_outer_kernel(OuterParams p) {
+  const long long w = (long long)blockIdx.x * SC_THREADS + threadIdx.x;
+  if (w >= p.S) return;
+  const int a0 = blockIdx.y * SO_AT, c0 = blockIdx.z * SO_CT;
+  float2 acc[SO_AT][SO_CT];
+#pragma unroll
+  for (int a = 0; a < SO_AT; a++)
+#pragma unroll
+    for (int c = 0; c < SO_CT; c++) acc[a][c] = make_float2(0.f, 0.f);
+  float cb[SO_CT];
+#pragma unroll
+  for (int c = 0; c < SO_CT; c++) cb[c] = (w == 0 && p.bm_bias && c0 + c < p.nC) ? p.bm_bias[c0 + c] * p.bm_bias_scale : 0.f;
+  for (int b = 0; b < p.B; b++) {
+    float2 av[SO_AT], bv[SO_CT];
+#pragma unroll
+    for (int a = 0; a < SO_AT; a++) {
+      av[a] = make_float2(0.f, 0.f);
+      if (a0 + a < p.nA) {
+        const long long off = ((long long)b * p.nA + a0 + a) * p.S + w;
+        av[a] = p.A0[off];
+        if (p.A1) { float2 u = p.A1[off]; av[a].x -= u.x; av[a].y -= u.y; }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < SO_CT; c++) {
+      bv[c] = make_float2(0.f, 0.f);
+      if (c0 + c < p.nC) {
+        float2 v = p.Bm[((long long)b * p.nC + c0 + c) * p.S + w];
+        bv[c] = make_float2(fmaf(v.x, p.bm_alpha, cb[c]), v.y * p.bm_alpha);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < SO_AT; a++)
+#pragma unroll
+      for (int c = 0; c < SO_CT; c++) cfma_conj(acc[a][c], av[a], bv[c]);
+  }
+#pragma unroll
+  for (int a = 0; a < SO_AT; a++)
+#pragma unroll
+    for (int c = 0; c < SO_CT; c++)
+      if (a0 + a < p.nA && c0 + c < p.nC)
+        p.out[((long long)(a0 + a) * p.nC + c0 + c) * p.S + w] = make_float2(acc[a][c].x * p.scale, acc[a][c].y * p.scale);
+}
+
+int launch_spec_outer(aefft_ctx* ctx, int64_t B, int nA, int nC, int64_t S, const float2* A0, const float2* A1,
+                      const float2* Bm, float bm_alpha, const float* bm_bias, float bm_bias_scale, float scale, float2* out) {
+  AE_ARG(B > 0 && nA > 0 && nC > 0 && S > 0);
+  OuterParams p{A0, A1, Bm, bm_bias, out, S, (int)B, nA, nC, bm_alpha, bm_bias_scale, scale};
+  dim3 grid((unsigned)((S + SC_THREADS - 1) / SC_THREADS), (nA + SO_AT - 1) / SO_AT, (nC + SO_CT - 1) / SO_CT);
+  AE_ARG(grid.z <= 65535 && grid.y <= 65535);
+  ProfScope prof(ctx, "spec_outer", 8.0 * B * nA * nC * S, 8.0 * S * ((double)B * nA * (A1 ? 2 : 1) + (double)B * nC + (double)nA * nC));
+  spec_outer_kernel<<<grid, SC_THREADS, 0, ctx->stream>>>(p);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// db[m] = gscale * sum_b Re G[b][m](0) ; dp[d] = gscale * sum_b Re (O - Xt)[b][d](0)     (:462-473)
+__global__ void spec_dc_sums_kernel(const float2* __restrict__ G, const float2* __restrict__ O, const float2* __restrict__ Xt,
+                                    float* __restrict__ db, float* __restrict__ dp, int B, int dM, int dD, long long S,
+                                    float gscale) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < dM) {
+    double s = 0.0;
+    for (int b = 0; b < B; b++) s += (double)G[((long long)b * dM + n) * S].x;
+    db[n] = (float)(s * (double)gscale);
+  } else if (n < dM + dD) {
+    const int d = n - dM;
+    double s = 0.0;
+    for (int b = 0; b < B; b++) s += (double)O[((long long)b * dD + d) * S].x - (double)Xt[((long long)b * dD + d) * S].x;
+    dp[d] = (float)(s * (double)gscale);
+  }
+}
+
+int launch_spec_dc_sums(aefft_ctx* ctx, int64_t B, int dM, int dD, int64_t S, const float2* G, const float2* O,
+                        const float2* Xt, float* db, float* dp, float gscale) {
+  spec_dc_sums_kernel<<<(dM + dD + 127) / 128, 128, 0, ctx->stream>>>(G, O, Xt, db, dp, (int)B, dM, dD, S, gscale);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ pad / shrink
+// pad_k (:570-600) / kernel_pad (:1018-1064): img[(k-Nk/2) mod Nx][(l-Nl/2) mod Ny] = w[k][l], everything else 0.
+// One thread per image pixel: writes the whole (zero-filled) image in one pass (the reference memsets first).
+__global__ void pad_kernel(const float* __restrict__ taps, float* __restrict__ img, long long n_img, int Nx, int Ny,
+                           int Nk, int Nl) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_img * Nx * Ny) return;
+  const int j = idx % Ny;
+  const int i = (idx / Ny) % Nx;
+  const long long n = idx / ((long long)Nx * Ny);
+  // inverse of the wrap: k = i + Nk/2 (i small) or i - Nx + Nk/2 (i near Nx)
+  int k = i + Nk / 2;
+  if (k >= Nk) k = i - Nx + Nk / 2;
+  int l = j + Nl / 2;
+  if (l >= Nl) l = j - Ny + Nl / 2;
+  float v = 0.f;
+  if (k >= 0 && k < Nk && l >= 0 && l < Nl) v = __ldg(taps + (n * Nk + k) * Nl + l);
+  img[idx] = v;
+}
+
+int launch_pad(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* taps, float* img) {
+  AE_ARG(Nk <= Nx && Nl <= Ny);
+  const long long total = (long long)n_img * Nx * Ny;
+  ProfScope prof(ctx, "pad_k", 0.0, 4.0 * total);
+  pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(taps, img, n_img, Nx, Ny, Nk, Nl);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// shrink_k (:535-565) / kernel_invpad (:1069-1112): w[k][l] = img[(k-Nk/2) mod Nx][(l-Nl/2) mod Ny]
+__global__ void shrink_kernel(const float* __restrict__ img, float* __restrict__ taps, long long n_img, int Nx, int Ny,
+                              int Nk, int Nl) {
+  long long idk = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idk >= n_img * Nk * Nl) return;
+  const int l = idk % Nl;
+  const int k = (idk / Nl) % Nk;
+  const long long n = idk / ((long long)Nk * Nl);
+  const int i = k >= Nk / 2 ? k - Nk / 2 : k + Nx - Nk / 2;
+  const int j = l >= Nl / 2 ? l - Nl / 2 : l + Ny - Nl / 2;
+  taps[idk] = img[(n * Nx + i) * Ny + j];
+}
+
+int launch_shrink(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* img, float* taps) {
+  const long long total = (long long)n_img * Nk * Nl;
+  shrink_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(img, taps, n_img, Nx, Ny, Nk, Nl);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ update
+// gradient_diff (:709-753): cd[m][d][k][l] = sum_{m1!=m, d1!=d} (c[m][d][k][l]-c[m1][d1][k][l]) / |c[m][d]-c[m1][d1]|^2,
+// fd likewise on f[d][m]; bd[m] = sum_{m1!=m} 1/(b[m]-b[m1]); pd[d] = sum_{d1!=d} 1/(p[d]-p[d1]).
+// One CTA per kernel (m,d): squared distances to every other kernel first (shared memory), then the tap sums.
+__global__ void gradient_diff_kernel(const float* __restrict__ c, const float* __restrict__ f, const float* __restrict__ b,
+                                     const float* __restrict__ p, float* __restrict__ cd, float* __restrict__ fd,
+                                     float* __restrict__ bd, float* __restrict__ pd, int dM, int dD, int T) {
+  extern __shared__ float sh[];  // [2][dM*dD] inverse squared distances
+  const int m = blockIdx.x / dD, d = blockIdx.x % dD;
+  float* inv_c = sh;
+  float* inv_f = sh + dM * dD;
+  const float* cm = c + (m * dD + d) * T;
+  const float* fm = f + (d * dM + m) * T;
+  for (int o = threadIdx.x; o < dM * dD; o += blockDim.x) {
+    const int m1 = o / dD, d1 = o % dD;
+    float dc = 0.f, df = 0.f;
+    if (m1 != m && d1 != d) {
+      const float* c1 = c + (m1 * dD + d1) * T;
+      const float* f1 = f + (d1 * dM + m1) * T;
+      for (int t = 0; t < T; t++) {
+        float x = cm[t] - c1[t], y = fm[t] - f1[t];
+        dc = fmaf(x, x, dc);
+        df = fmaf(y, y, df);
+      }
+      dc = 1.f / dc;
+      df = 1.f / df;
+    }
+    inv_c[o] = dc;
+    inv_f[o] = df;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float sc = 0.f, sf = 0.f;
+    for (int m1 = 0; m1 < dM; m1++)
+      for (int d1 = 0; d1 < dD; d1++) {
+        if (m1 == m || d1 == d) continue;
+        sc += (cm[t] - c[(m1 * dD + d1) * T + t]) * inv_c[m1 * dD + d1];
+        sf += (fm[t] - f[(d1 * dM + m1) * T + t]) * inv_f[m1 * dD + d1];
+      }
+    cd[(m * dD + d) * T + t] = sc;
+    fd[(d * dM + m) * T + t] = sf;
+  }
+  if (threadIdx.x == 0) {
+    if (d == 0) {
+      float s = 0.f;
+      for (int m1 = 0; m1 < dM; m1++)
+        if (m1 != m) s += 1.f / (b[m] - b[m1]);
+      bd[m] = s;
+    }
+    if (m == 0) {
+      float s = 0.f;
+      for (int d1 = 0; d1 < dD; d1++)
+        if (d1 != d) s += 1.f / (p[d] - p[d1]);
+      pd[d] = s;
+    }
+  }
+}
+
+__device__ __forceinline__ float clip10f(float g) { return g / fmaxf(10.f, fabsf(g)); }
+
+// backprop_d (:605-652) / backprop_double (:657-704): v = (1-0.9)*del*clip(g) + 0.9*v ; w -= v, elementwise on the flat
+// arrays (c and f share the flat index), g = w0*g_mse - w1*g_div when the multiobjective term is on.
+__global__ void fft_update_kernel(float* __restrict__ c, float* __restrict__ f, float* __restrict__ b, float* __restrict__ p,
+                                  const float* __restrict__ dck, const float* __restrict__ dfk, const float* __restrict__ db,
+                                  const float* __restrict__ dp, float* __restrict__ Dc, float* __restrict__ Df,
+                                  float* __restrict__ Db, float* __restrict__ Dp, const float* __restrict__ cd,
+                                  const float* __restrict__ fd, const float* __restrict__ bd, const float* __restrict__ pd,
+                                  int nC, int dM, int dD, float del, float w0, float w1) {
+  const float alpha = 0.9f;
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nC) return;
+  {
+    float g = cd ? w0 * dck[n] - w1 * cd[n] : dck[n];
+    float v = (1.f - alpha) * del * clip10f(g) + alpha * Dc[n];
+    c[n] -= v;
+    Dc[n] = v;
+  }
+  {
+    float g = fd ? w0 * dfk[n] - w1 * fd[n] : dfk[n];
+    float v = (1.f - alpha) * del * clip10f(g) + alpha * Df[n];
+    f[n] -= v;
+    Df[n] = v;
+  }
+  if (n < dM) {
+    float g = bd ? w0 * db[n] - w1 * bd[n] : db[n];
+    float v = (1.f - alpha) * del * clip10f(g) + alpha * Db[n];
+    b[n] -= v;
+    Db[n] = v;
+  }
+  if (n < dD) {
+    float g = pd ? w0 * dp[n] - w1 * pd[n] : dp[n];
+    float v = (1.f - alpha) * del * clip10f(g) + alpha * Dp[n];
+    p[n] -= v;
+    Dp[n] = v;
+  }
+}
+
+int launch_fft_update(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, float* c, float* f, float* b, float* p,
+                      const float* dck, const float* dfk, const float* db, const float* dp, float* Dc, float* Df, float* Db,
+                      float* Dp, float del, int maxdiff, float* div_scratch /* 2*nC + dM + dD floats */) {
+  const int T = Nk * Nl, nC = dM * dD * T;
+  float *cd = nullptr, *fd = nullptr, *bd = nullptr, *pd = nullptr;
+  if (maxdiff) {
+    cd = div_scratch; fd = cd + nC; bd = fd + nC; pd = bd + dM;
+    const size_t smem = (size_t)2 * dM * dD * sizeof(float);
+    AE_ARG(smem <= 48 * 1024);
+    gradient_diff_kernel<<<dM * dD, 64, smem, ctx->stream>>>(c, f, b, p, cd, fd, bd, pd, dM, dD, T);
+    ctx->launches++;
+    AE_CUDA(cudaGetLastError());
+  }
+  fft_update_kernel<<<(nC + 127) / 128, 128, 0, ctx->stream>>>(c, f, b, p, dck, dfk, db, dp, Dc, Df, Db, Dp, cd, fd, bd, pd, nC,
+                                                                dM, dD, del, 1.f, 10.f);  // w0=1, w1=10 (:1252)
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ mse
+// calc_mse + thrust::reduce (:480-498, 1178-1192): sum_w |Xt-O|^2 / n_w, n_w = dD*Nx*Ny halved for 0<j<Nyr-1.
+// Deterministic two-stage reduction in double; *out = scale * total.
+__global__ void spec_mse_kernel(const float2* __restrict__ Xt, const float2* __restrict__ O, long long total, int Nyr,
+                                double* __restrict__ part) {
+  double s = 0.0;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = idx % Nyr;
+    float2 a = Xt[idx], b = O[idx];
+    float dx = a.x - b.x, dy = a.y - b.y;
+    float v = dx * dx + dy * dy;
+    s += (double)((j > 0 && j < Nyr - 1) ? 2.f * v : v);
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void spec_mse_final_kernel(const double* __restrict__ part, int n, double scale, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)(red[0] * scale);
+}
+
+int launch_spec_mse(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx, int Ny, const float2* Xt, const float2* O, float* out) {
+  const int Nyr = Ny / 2 + 1;
+  const long long total = (long long)B * dD * Nx * Nyr;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4 * ctx->sm_count) blocks = 4 * ctx->sm_count;
+  double* part;
+  AE_TRY(ctx->getT("mse_part", (size_t)blocks, &part));
+  ProfScope prof(ctx, "spec_mse", 0.0, 16.0 * total);
+  spec_mse_kernel<<<blocks, 256, 0, ctx->stream>>>(Xt, O, total, Nyr, part);
+  // per frame: [sum |.|^2 / (dD Nx Ny)] / (2 dM Nx Ny); mean over frames
+  const double scale = 1.0 / ((double)dD * Nx * Ny) / (2.0 * dM * Nx * Ny) / (double)B;
+  spec_mse_final_kernel<<<1, 256, 0, ctx->stream>>>(part, blocks, scale, out);
+  ctx->launches += 2;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// interleaved-float wire format of net_cfreq (copy_out / copy_in, :246-282) is bit-identical to complex64: the
+// "conversion" is a plain copy, done with cudaMemcpyAsync by the callers.
+
+}  // namespace aefft

@@ -220,7 +220,10 @@ def run_ours(args, w, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = A.Ctx(local_rank)
-    stream = torch.cuda.current_stream()
+    # all engine work, the NCCL collectives and the timing events share ONE non-default torch stream
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     A._chk(A.lib().aefft_set_stream(ctx.h, ctypes.c_void_p(stream.cuda_stream)))
     B = args.batch
     if w["space"] != "coordinate":

@@ -8,11 +8,30 @@ and the result is copied to tests/golden/gpu_golden.npz and committed.  Square f
 import os
 import sys
 
+import re
+import tempfile
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import ref_lib as R  # noqa: E402
+
+
+def capture_stdout(fn):
+    """Run fn() with fd 1 redirected to a file; returns (result, text).  The reference prints its per-iteration
+    "mse fft:" / "n: .. mse: .." values with cout (fft_backproplib.cu:1441,1464)."""
+    sys.stdout.flush()
+    with tempfile.TemporaryFile(mode="w+b") as tf:
+        saved = os.dup(1)
+        os.dup2(tf.fileno(), 1)
+        try:
+            res = fn()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        tf.seek(0)
+        return res, tf.read().decode()
 
 
 def case(rng, dM, dD, Nk, Nl, Nx, Ny, wscale=0.2):
@@ -78,6 +97,12 @@ def main(out_path):
         net_b = [e[1] for e in encs] + [e[3] for e in reversed(encs)]
         scale = [e[4] for e in encs] + [-e[4] for e in reversed(encs)]
         layers, cfs = R.autoenc_fft(x, net_c, net_b, scale, layer_shapes, None, 1)
+        # fft_l = 0: only the last layer is inverse-transformed.  (With fft_l = 1 cuFFT's multi-dimensional C2R
+        # overwrites its INPUT spectrum, so every layer after the first inverse is computed from clobbered data.)
+        layers0, _ = R.autoenc_fft(x, net_c, net_b, scale, layer_shapes, None, 0)
+        g[f"aef_{tag}_last_fftl0"] = layers0[-1]
+        layers0c, _ = R.autoenc_fft(x, net_c, net_b, scale, layer_shapes, cfs, 0)  # cached-spectra branch
+        g[f"aef_{tag}_last_fftl0_cached"] = layers0c[-1]
         g[f"aef_{tag}_x"] = x
         g[f"aef_{tag}_scale"] = np.array(scale, np.int32)
         g[f"aef_{tag}_shapes"] = np.array(layer_shapes, np.int32)
@@ -87,19 +112,26 @@ def main(out_path):
         for l, a in enumerate(layers):
             g[f"aef_{tag}_L{l}"] = a
     # ---- backprop_fft: 100 iterations, with and without the multiobjective term
-    for tag, (dims, maxdiff) in {"f5": ((4, 3, 5, 5, 16, 16), 0), "f3": ((3, 2, 3, 3, 32, 16), 0),
-                                 "m5": ((4, 3, 5, 5, 16, 16), 1)}.items():
+    # del0 = 0.2 is the app default (autoencoder.cpp:87); the small-del0 twins stay in the smooth regime, where 100
+    # iterations of fp32 (reference) and fp64 (oracle) arithmetic do not drift apart.
+    for tag, (dims, maxdiff, del0) in {"f5": ((4, 3, 5, 5, 16, 16), 0, 0.2), "f3": ((3, 2, 3, 3, 32, 16), 0, 0.2),
+                                       "m5": ((4, 3, 5, 5, 16, 16), 1, 0.2), "g5": ((4, 3, 5, 5, 16, 16), 0, 0.005),
+                                       "g3": ((3, 2, 3, 3, 32, 16), 0, 0.005), "n5": ((4, 3, 5, 5, 16, 16), 1, 0.005)}.items():
         inp, c, b, f, p = case(rng, *dims, wscale=0.5)
         dM, dD, Nk, Nl, Nx, Ny = dims
         shapes = [(dD, Nx, Ny), (dD, Nx, Ny), (dM, Nx, Ny), (dD, Nx, Ny), (dD, Nx, Ny)]
         layers, cfs = R.autoenc_fft(inp, [c, f], [b, p], [1, -1], shapes, None, 1)
         out = layers[3]
-        res = R.backprop_fft(layers[1], layers[1], out, cfs[0], c, cfs[1], f, b, p, 0.2, maxdiff)
+        res, text = capture_stdout(lambda: R.backprop_fft(layers[1], layers[1], out, cfs[0], c, cfs[1], f, b, p, del0, maxdiff))
+        trace = [float(m) for m in re.findall(r"mse(?: fft)?: *([-+0-9.eEinfa]+)", text)]
+        assert len(trace) == 101, (len(trace), text[:200])
+        g[f"bpf_{tag}_trace"] = np.array(trace, np.float64)
         for k, v in dict(inp=layers[1], out=out, c=c, b=b, f=f, p=p, cfreq=cfs[0], ffreq=cfs[1]).items():
             g[f"bpf_{tag}_{k}"] = v
         for k, v in res.items():
             g[f"bpf_{tag}_new_{k}"] = v
         g[f"bpf_{tag}_maxdiff"] = np.int32(maxdiff)
+        g[f"bpf_{tag}_del0"] = np.float32(del0)
     np.savez_compressed(out_path, **g)
     print("wrote", out_path, os.path.getsize(out_path), "bytes")
 

@@ -163,3 +163,34 @@ def test_product_load_param(tmp_path):
     assert A.load_param(pth) == (10, 1, 1, 2, 3.0)
     with pytest.raises(A.AefftError):
         A.load_param(tmp_path / "missing.txt")
+
+
+# ---------------------------------------------------------------- oracle vs the reference's CUDA path (golden, from a B200)
+GPU_GOLDEN = os.path.join(GOLDEN, "gpu_golden.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(GPU_GOLDEN), reason="gpu_golden.npz not generated yet")
+def test_oracle_vs_reference_cuda_golden_coordinate():
+    """Conv_gpu / backprop_gpu / backprop_gpu_cc of the unmodified reference, run on a B200 by
+    tests/golden/make_golden_gpu.py.  backprop_gpu's dF (quirk C3) reads outside hin for channels m=0 and m=dM-1
+    (undefined behaviour in the reference); those two channels of f are excluded, the rest is pinned."""
+    Gg = np.load(GPU_GOLDEN)
+    for tag in "abc":
+        out = O.conv_gpu(Gg[f"convg_{tag}_x"], Gg[f"convg_{tag}_c"], Gg[f"convg_{tag}_b"])
+        assert O.rel_l2(out, Gg[f"convg_{tag}_out"]) < 2e-6
+    names = "c b f p dc db df dp ddc ddb ddf ddp".split()
+    for tag in ("s5", "s3"):
+        for sym in (0, 1):
+            key = f"bpg_{tag}_{sym}"
+            cs = {k: Gg[f"{key}_{k}"] for k in ["inp", "hin", "out"] + names}
+            st = {k: cs[k] for k in names[4:]}
+            fn = O.backprop_gpu_cc if sym else O.backprop_gpu
+            w = fn(cs["inp"], cs["out"], cs["hin"], cs["c"], cs["b"], cs["f"], cs["p"], **st, delmax=0.2, alpha=0.9)
+            dM = cs["c"].shape[0]
+            for k in ("c", "b", "p", "ddc", "ddb", "ddp", "dc", "db", "dp"):
+                assert O.rel_l2(w[k], Gg[f"{key}_step1_{k}"]) < 1e-5, (key, k)
+            sl = (slice(None), slice(None)) if sym else (slice(None), slice(1, dM - 1))
+            for k in ("f", "ddf"):
+                if sym and k == "ddf":
+                    continue
+                assert O.rel_l2(np.asarray(w[k])[sl], Gg[f"{key}_step1_{k}"][sl]) < 1e-5, (key, k)
