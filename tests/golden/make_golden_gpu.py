@@ -77,7 +77,7 @@ def main(out_path):
                 for k, v in st.items():
                     g[f"{key}_step{step}_{k}"] = v
     # ---- autoenc_fft: 1 pair and 2 pairs, fft_l = 1 (all layers) ; spectra cache returned
-    for tag, (D, Nx, Ny, widths, sc) in {"p1": (3, 16, 16, [4], [2]), "p2": (2, 32, 16, [3, 5], [2, 2]),
+    for tag, (D, Nx, Ny, widths, sc) in {"p1": (3, 16, 16, [4], [2]), "p2": (2, 32, 32, [3, 5], [2, 2]),
                                          "s1": (3, 16, 16, [4], [1])}.items():
         x = np.floor(rng.random((D, Nx, Ny)) * 256).astype(np.float32)
         enc, dec, shapes_e, shapes_d = [], [], [], []

@@ -78,7 +78,7 @@ def build_net(rng, D, Nx, Ny, widths, scales, Nk=5, Nl=5, wscale=0.2):
     return net_c, net_b, scale, shapes
 
 
-@pytest.mark.parametrize("cfg", [(3, 16, 16, [4], [2]), (2, 32, 16, [3, 5], [2, 2]), (3, 16, 16, [4], [1]), (3, 64, 64, [6, 4, 5], [2, 1, 2])])
+@pytest.mark.parametrize("cfg", [(3, 16, 16, [4], [2]), (2, 32, 32, [3, 5], [2, 2]), (3, 16, 16, [4], [1]), (3, 64, 64, [6, 4, 5], [2, 1, 2])])
 def test_autoenc_fft_vs_oracle(ctx, cfg):
     D, Nx, Ny, widths, scales = cfg
     rng = np.random.default_rng(2)
