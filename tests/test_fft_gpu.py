@@ -156,7 +156,8 @@ def test_fft_path_vs_reference_golden(ctx):
         assert O.rel_l2(layers[-1], G[f"aef_{tag}_last_fftl0"]) < 1e-4, tag
         for n in range(len(scale)):
             assert O.rel_l2(spectra[n], G[f"aef_{tag}_cf{n}"]) < 1e-5
-        assert O.rel_l2(layers[1], G[f"aef_{tag}_L1"]) < 1e-5  # first pooled layer (before cuFFT clobbers anything)
+        all_layers, _ = ctx.autoenc_fft(x, net_c, net_b, scale, shapes, None, 1)
+        assert O.rel_l2(all_layers[1], G[f"aef_{tag}_L1"]) < 1e-5  # first pooled layer (before cuFFT clobbers anything)
     for tag in ("f5", "f3", "m5", "g5", "g3", "n5"):
         k = {x: np.ascontiguousarray(G[f"bpf_{tag}_{x}"]) for x in "inp out c b f p cfreq ffreq".split()}
         md, del0 = int(G[f"bpf_{tag}_maxdiff"]), float(G[f"bpf_{tag}_del0"])
