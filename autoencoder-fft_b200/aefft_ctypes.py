@@ -19,6 +19,7 @@ HOST, DEVICE = 0, 1
 CONV_CUDA, CONV_CPU = 0, 1
 MODE_CPU_REF, MODE_CUDA_REF, MODE_CUDA_REF_SYM = 0, 1, 2
 QUIRK_C1, QUIRK_C3, QUIRK_C4, QUIRKS_ALL = 1, 2, 4, 7
+PRECISION_FP32, PRECISION_BF16X3, PRECISION_BF16 = 0, 1, 2
 
 FP = C.POINTER(C.c_float)
 _lib = None
@@ -112,6 +113,13 @@ class Ctx:
 
     def sync(self):
         _chk(lib().aefft_sync(self.h))
+
+    def set_precision(self, precision: int):
+        _chk(lib().aefft_set_precision(self.h, int(precision)))
+
+    @property
+    def precision(self) -> int:
+        return int(lib().aefft_get_precision(self.h))
 
     def malloc(self, nbytes: int) -> int:
         p = C.c_void_p()

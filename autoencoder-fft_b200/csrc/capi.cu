@@ -276,6 +276,13 @@ int aefft_set_stream(aefft_ctx* ctx, void* cuda_stream) {
   return AEFFT_OK;
 }
 
+int aefft_set_precision(aefft_ctx* ctx, int precision) {
+  AE_ARG(ctx && precision >= AEFFT_PRECISION_FP32 && precision <= AEFFT_PRECISION_BF16);
+  ctx->precision = precision;
+  return AEFFT_OK;
+}
+int aefft_get_precision(const aefft_ctx* ctx) { return ctx ? ctx->precision : -1; }
+
 int aefft_profile_enable(aefft_ctx* ctx, int on) {
   AE_ARG(ctx);
   ctx->profiling = on != 0;

@@ -58,6 +58,7 @@ struct aefft_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
   int64_t launches = 0;
+  int precision = AEFFT_PRECISION_FP32;  // arithmetic of the coordinate-space contractions (aefft_set_precision)
   bool profiling = false;
   std::vector<aefft::ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;
@@ -138,6 +139,12 @@ inline Window tr_window(int Nk, int Nl, int convention) {
 int launch_conv(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, int Nx, int Ny, const float* src0,
                 const float* src1, float pre_div, const float* w, int64_t w_so, int64_t w_sc, const float* bias,
                 float* out);
+
+// Tensor-core (tcgen05) implementation of the same contract (conv_tc.cu); passes = 3 (BF16X3) or 1 (BF16).
+// Returns AEFFT_ERR_UNSUPPORTED for shapes outside its envelope (the caller then uses the fp32 kernel).
+int launch_conv_tc(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, int Nx, int Ny, const float* src0,
+                   const float* src1, float pre_div, const float* w, int64_t w_so, int64_t w_sc, const float* bias,
+                   float* out, int passes);
 
 // Correlation (weight-gradient) contraction, summed over all frames and pixels:
 //   G[a][x][k][l] = sum_{b,i,j} A[b][a](i,j) * X[b][x](i+ai0+tk, j+aj0+tl)          (k,l) <-> (tk,tl) per win.flip

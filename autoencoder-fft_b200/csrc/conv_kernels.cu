@@ -179,6 +179,11 @@ int launch_conv(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, int 
                 const float* src1, float pre_div, const float* w, int64_t w_so, int64_t w_sc, const float* bias,
                 float* out) {
   AE_ARG(B > 0 && C > 0 && O > 0 && Nx > 0 && Ny > 0);
+  if (ctx->precision != AEFFT_PRECISION_FP32) {
+    const int rc = launch_conv_tc(ctx, win, B, C, O, Nx, Ny, src0, src1, pre_div, w, w_so, w_sc, bias, out,
+                                  ctx->precision == AEFFT_PRECISION_BF16X3 ? 3 : 1);
+    if (rc != AEFFT_ERR_UNSUPPORTED) return rc;
+  }
   ConvParams p;
   p.src0 = src0; p.src1 = src1; p.w = w; p.bias = bias; p.out = out;
   p.w_so = w_so; p.w_sc = w_sc; p.pre_div = pre_div;

@@ -54,6 +54,13 @@ enum {
   AEFFT_QUIRKS_ALL = 7
 };
 
+/* Arithmetic of the coordinate-space contractions (conv forward / data gradient / weight gradients).
+ *   FP32   : fp32 FMA on CUDA cores.
+ *   BF16X3 : tcgen05 tensor cores, every fp32 operand split into bf16 hi+lo, three products accumulated in fp32
+ *            (fp32-grade: ~1e-5 relative L2 against the fp32 oracle; meets the 1e-4 parity bar).
+ *   BF16   : tcgen05 tensor cores, single bf16 product (looser tolerance: ~5e-3 relative L2). */
+enum { AEFFT_PRECISION_FP32 = 0, AEFFT_PRECISION_BF16X3 = 1, AEFFT_PRECISION_BF16 = 2 };
+
 typedef struct aefft_ctx aefft_ctx; /* one per process/GPU: device, stream, workspace arena, FFT plans */
 
 const char* aefft_last_error(void);
@@ -67,6 +74,8 @@ int aefft_sync(aefft_ctx* ctx);
 /* The CUDA stream all work of this ctx is launched on (as an opaque cudaStream_t). */
 void* aefft_stream(aefft_ctx* ctx);
 
+int aefft_set_precision(aefft_ctx* ctx, int precision);
+int aefft_get_precision(const aefft_ctx* ctx);
 /* Launch all work of this ctx on a caller-owned stream (e.g. torch's current stream, so torch.distributed
  * collectives and torch.cuda.Event timing order with it); NULL restores the ctx's own stream. */
 int aefft_set_stream(aefft_ctx* ctx, void* cuda_stream);
