@@ -161,12 +161,27 @@ int coord_gradients_dev(aefft_ctx* ctx, int mode, int quirks, int64_t B, int dD,
   AE_TRY(launch_conv(ctx, tr_window(Nk, Nl, AEFFT_CONV_CUDA), B, dD, dM, Nx, Ny, out, in, 0.f, f, T, (int64_t)dM * T,
                      nullptr, dh));
   Window wg = fwd_window(Nk, Nl, AEFFT_CONV_CUDA);
-  AOperand A;
-  A.mode = A_PLAIN; A.a0 = dh; A.nA = dM; A.src_ch = dM;
-  AE_TRY(launch_wgrad(ctx, wg, B, Nx, Ny, A, in, dD, GC, GB, nullptr));
-  AOperand E;
-  E.mode = A_DIFF; E.a0 = out; E.a1 = in; E.nA = dD; E.src_ch = dD;
-  AE_TRY(launch_wgrad(ctx, wg, B, Nx, Ny, E, hin, dM, GF, GP, SQ));
+  bool done = false;
+  if (ctx->precision != AEFFT_PRECISION_FP32) {
+    // tensor-core path: GC and GF in one launch (adjacent in gbuf), bias sums / sum e^2 by a streaming reduction
+    const int rc = launch_wgrad_tc(ctx, wg, B, dD, dM, Nx, Ny, in, out, hin, dh, GC,
+                                   ctx->precision == AEFFT_PRECISION_BF16X3 ? 3 : 1);
+    if (rc == AEFFT_OK) {
+      AE_TRY(launch_channel_sums(ctx, B, dM, Nx, Ny, dh, nullptr, GB, nullptr));
+      AE_TRY(launch_channel_sums(ctx, B, dD, Nx, Ny, out, in, GP, SQ));
+      done = true;
+    } else if (rc != AEFFT_ERR_UNSUPPORTED) {
+      return rc;
+    }
+  }
+  if (!done) {
+    AOperand A;
+    A.mode = A_PLAIN; A.a0 = dh; A.nA = dM; A.src_ch = dM;
+    AE_TRY(launch_wgrad(ctx, wg, B, Nx, Ny, A, in, dD, GC, GB, nullptr));
+    AOperand E;
+    E.mode = A_DIFF; E.a0 = out; E.a1 = in; E.nA = dD; E.src_ch = dD;
+    AE_TRY(launch_wgrad(ctx, wg, B, Nx, Ny, E, hin, dM, GF, GP, SQ));
+  }
   if (mode == AEFFT_MODE_CUDA_REF) {
     if (quirks & (AEFFT_QUIRK_C3 | AEFFT_QUIRK_C4)) {
       AE_ARG(Nx == Ny);  // the compiled reference is only defined on square frames (stride quirk C2)

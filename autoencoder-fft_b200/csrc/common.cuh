@@ -166,6 +166,14 @@ struct AOperand {
 int launch_wgrad(aefft_ctx* ctx, const Window& win, int64_t B, int Nx, int Ny, const AOperand& A, const float* X,
                  int nX, float* G, float* sumA, float* sumsq);
 
+// Tensor-core weight gradients of one pair (wgrad_tc.cu): G = [GC dM*dD*T | GF dD*dM*T] raw sums over the frames,
+// GC = corr(dh, in), GF = corr(out-in, hin) with the forward window `win`.  AEFFT_ERR_UNSUPPORTED outside its envelope.
+int launch_wgrad_tc(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM, int Nx, int Ny, const float* in,
+                    const float* out, const float* hin, const float* dh, float* G, int passes);
+// sum[c] = sum_{b,pix} (a0-a1)[b][c], *sumsq = sum (a0-a1)^2 (double accumulation, deterministic); a1/sum/sumsq optional
+int launch_channel_sums(aefft_ctx* ctx, int64_t B, int ch, int Nx, int Ny, const float* a0, const float* a1, float* sum,
+                        float* sumsq);
+
 int launch_pool(aefft_ctx* ctx, int64_t B, int D, int Nx, int Ny, int oNx, int oNy, int scale, const float* in,
                 float* out);
 int launch_portion(aefft_ctx* ctx, int64_t B, int D, int Nx, int Ny, int q, const float* in, float* out);

@@ -39,14 +39,18 @@ struct ConvTcParams {
   int tiles_per_frame;
   long long n_tiles;
   int passes;  // 3 = BF16X3, 1 = BF16
+  int kpack;   // C <= 8: one channel plane, the two 16-byte K chunks of an MMA are taps (tl, tl+1) (LBO = one pixel)
+  int TE;      // MMAs per (M-block, pass): NK*NL, or NK*ceil(NL/2) when kpack
   uint32_t tmem_cols;
 };
 
 // w(o,c,k,l) fp32 -> bf16 hi/lo in the shared-memory image of each K stage:
 //   wprep[ks][pass][t][kchunk][n][e]   c = ks*16 + kchunk*8 + e,  t = tk*NL + tl (window position),  zero padded
+// kpack (C <= 8): t = tk*ceil(NL/2) + pair, kchunk = tap within the pair (tl = 2*pair + kchunk), c = e.
 __global__ void weight_prep_kernel(const float* __restrict__ w, long long w_so, long long w_sc, int C, int O, int N, int NK,
-                                   int NL, int flip, int KS, __nv_bfloat16* __restrict__ wprep) {
-  const int T = NK * NL;
+                                   int NL, int flip, int KS, int kpack, __nv_bfloat16* __restrict__ wprep) {
+  const int NLP = kpack ? (NL + 1) / 2 : NL;
+  const int T = NK * NLP;
   const long long per_pass = (long long)T * 2 * N * 8;
   const long long total = (long long)KS * per_pass;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -55,11 +59,11 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, long long w_so, 
     const int kchunk = (idx / (8 * N)) % 2;
     const int t = (idx / (16 * N)) % T;
     const int ks = idx / per_pass;
-    const int c = ks * KC + kchunk * 8 + e;
-    const int tk = t / NL, tl = t % NL;
+    const int c = kpack ? e : ks * KC + kchunk * 8 + e;
+    const int tk = t / NLP, tl = kpack ? 2 * (t % NLP) + kchunk : t % NLP;
     const int k = flip ? NK - 1 - tk : tk, l = flip ? NL - 1 - tl : tl;
     float v = 0.f;
-    if (c < C && n < O) v = w[n * w_so + c * w_sc + k * NL + l];
+    if (c < C && n < O && tl < NL) v = w[n * w_so + c * w_sc + k * NL + l];
     __nv_bfloat16 hi, lo;
     split_bf16(v, hi, lo);
     const long long base = (long long)ks * 2 * per_pass + (idx % per_pass);
@@ -70,11 +74,12 @@ __global__ void weight_prep_kernel(const float* __restrict__ w, long long w_so, 
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(ConvTcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int w_bytes = 64 * p.T * p.N;  // both passes of one K stage
-  const int a_plane = p.HP * 16;       // one kchunk plane
+  const int w_bytes = 64 * p.TE * p.N;  // both passes of one K stage
+  const int a_plane = p.HP * 16;        // one 8-channel plane
+  const int nkc = p.kpack ? 1 : 2;      // planes per pass
   unsigned char* Wsm = smem;
-  unsigned char* Asm = smem + w_bytes;  // [pass][kchunk][HP][16]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + w_bytes + 4 * a_plane);
+  unsigned char* Asm = smem + w_bytes;  // [pass][plane][HP][16]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + w_bytes + 2 * nkc * a_plane);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -107,32 +112,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(ConvTcParams p) 
         for (int i = tid; i < w_bytes / 16; i += TC_THREADS) dst[i] = __ldg(src + i);
         w_resident = true;
       }
-      // ---- stage the input halo tile: one thread = one halo pixel x 8 channels -> one 16-byte store per pass ----
-      for (int idx = tid; idx < 2 * p.HP; idx += TC_THREADS) {
+      // ---- stage the input halo tile: one thread = one halo pixel x 8 channels -> one 16-byte store per pass.
+      //      All global loads of an item are issued before any is used (addresses clamped, values masked afterwards).
+      for (int idx = tid; idx < nkc * p.HP; idx += TC_THREADS) {
         const int kchunk = idx / p.HP, h = idx - kchunk * p.HP;
         const int r = h / p.PJ, col = h - r * p.PJ;
         const int si = i0 + p.ai0 + r, sj = p.aj0 + col;
         const bool inb = r < HI && si >= p.lo && si < p.Nx && sj >= p.lo && sj < p.Ny;
         const int c0 = ks * KC + kchunk * 8;
-        float v[8];
+        const long long pix = inb ? (long long)si * p.Ny + sj : 0;
+        float v[8], u[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-          v[e] = 0.f;
-          if (inb && c0 + e < p.C) {
-            const long long off = (long long)(c0 + e) * plane + (long long)si * p.Ny + sj;
-            float x = __ldg(s0 + off);
-            if (s1) x -= __ldg(s1 + off);
-            else if (p.pre_div != 0.f) x = __fdiv_rn(x, p.pre_div);
-            v[e] = x;
+          const int c = min(c0 + e, p.C - 1);
+          v[e] = __ldg(s0 + (long long)c * plane + pix);
+        }
+        if (s1) {
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            const int c = min(c0 + e, p.C - 1);
+            u[e] = __ldg(s1 + (long long)c * plane + pix);
           }
+#pragma unroll
+          for (int e = 0; e < 8; e++) v[e] -= u[e];
+        } else if (p.pre_div != 0.f) {
+#pragma unroll
+          for (int e = 0; e < 8; e++) v[e] = __fdiv_rn(v[e], p.pre_div);
         }
         __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) split_bf16(v[e], hi[e], lo[e]);
+        for (int e = 0; e < 8; e++) {
+          if (!inb || c0 + e >= p.C) v[e] = 0.f;
+          split_bf16(v[e], hi[e], lo[e]);
+        }
         uint4 qh = make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
         uint4 ql = make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
         *reinterpret_cast<uint4*>(Asm + (size_t)kchunk * a_plane + (size_t)h * 16) = qh;
-        *reinterpret_cast<uint4*>(Asm + (size_t)(2 + kchunk) * a_plane + (size_t)h * 16) = ql;
+        *reinterpret_cast<uint4*>(Asm + (size_t)(nkc + kchunk) * a_plane + (size_t)h * 16) = ql;
       }
       fence_proxy_async();
       __syncthreads();
@@ -140,19 +156,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(ConvTcParams p) 
       if (tid == 0) {
         fence_after_sync();
         const uint32_t w_pass = (uint32_t)w_bytes / 2, w_tap = 32u * p.N;
+        const uint32_t a_lbo = p.kpack ? 16u : (uint32_t)a_plane;
+        const int NLP = p.kpack ? (p.NL + 1) / 2 : p.NL, tstep = p.kpack ? 2 : 1;
+        // descriptors differ only in their 14-bit start-address field: build once, then add (bytes >> 4)
+        const uint64_t a_hi0 = make_desc(Asm_addr, a_lbo, 128), a_lo0 = make_desc(Asm_addr + nkc * a_plane, a_lbo, 128);
+        const uint64_t b_hi0 = make_desc(Wsm_addr, 16u * p.N, 128), b_lo0 = make_desc(Wsm_addr + w_pass, 16u * p.N, 128);
         for (int mb = 0; mb < p.MB; mb++) {
           const uint32_t d = tmem_base + (uint32_t)(mb * p.N);
-          for (int t = 0; t < p.T; t++) {
-            const int tk = t / p.NL, tl = t - tk * p.NL;
-            const uint32_t a_off = (uint32_t)(mb * 128 + tk * p.PJ + tl) * 16u;
-            const uint64_t a_hi = make_desc(Asm_addr + a_off, (uint32_t)a_plane, 128);
-            const uint64_t b_hi = make_desc(Wsm_addr + t * w_tap, 16u * p.N, 128);
-            mma_bf16(d, a_hi, b_hi, idesc, !(ks == 0 && t == 0));
-            if (p.passes == 3) {
-              const uint64_t a_lo = make_desc(Asm_addr + 2u * a_plane + a_off, (uint32_t)a_plane, 128);
-              const uint64_t b_lo = make_desc(Wsm_addr + w_pass + t * w_tap, 16u * p.N, 128);
-              mma_bf16(d, a_hi, b_lo, idesc, true);
-              mma_bf16(d, a_lo, b_hi, idesc, true);
+          uint32_t t = 0;
+          for (int tk = 0; tk < p.NK; tk++) {
+            const uint32_t a_row = (uint32_t)(mb * 128 + tk * p.PJ);
+            for (int tp = 0; tp < NLP; tp++, t++) {
+              const uint64_t a_add = (uint64_t)(a_row + tp * tstep), b_add = (uint64_t)(t * (w_tap >> 4));
+              mma_bf16(d, a_hi0 + a_add, b_hi0 + b_add, idesc, !(ks == 0 && t == 0));
+              if (p.passes == 3) {
+                mma_bf16(d, a_hi0 + a_add, b_lo0 + b_add, idesc, true);
+                mma_bf16(d, a_lo0 + a_add, b_hi0 + b_add, idesc, true);
+              }
             }
           }
         }
@@ -204,44 +224,52 @@ int launch_conv_tc(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
                    const float* src1, float pre_div, const float* w, int64_t w_so, int64_t w_sc, const float* bias,
                    float* out, int passes) {
   const int N = (O + 15) / 16 * 16;
-  const int T = win.Nk * win.Nl;
+  const int kpack = C <= 8 ? 1 : 0;
+  const int TE = kpack ? win.Nk * ((win.Nl + 1) / 2) : win.Nk * win.Nl;
+  const int nkc = kpack ? 1 : 2;
   const int PJ = Ny + win.Nl - 1;
-  if (N > 256 || T > 64 || PJ > 4096) return AEFFT_ERR_UNSUPPORTED;
-  const int smem_budget = 220 * 1024;
-  const int w_bytes = 64 * T * N;
-  const int halo = (win.Nk - 1) * PJ + win.Nl;
-  int mb_max = 512 / N;
-  const int mb_smem = ((smem_budget - w_bytes - 64) / 64 - halo - 8) / 128;
-  if (mb_smem < mb_max) mb_max = mb_smem;
-  if (mb_max < 1) return AEFFT_ERR_UNSUPPORTED;
-  int TI = mb_max * 128 / PJ;
-  if (TI < 1) return AEFFT_ERR_UNSUPPORTED;
+  if (N > 256 || TE > 64 || PJ > 4096) return AEFFT_ERR_UNSUPPORTED;
+  const int w_bytes = 64 * TE * N;
+  const int halo = (win.Nk - 1) * PJ + win.Nl + 8;
+  // two co-resident CTAs per SM (one stages / stores while the other's MMAs run) when the tile still holds >= 2
+  // M-blocks; otherwise one CTA with the whole SM
+  int ctas = 2, TI = 0, mb_max = 0;
+  for (; ctas >= 1; ctas--) {
+    const int smem_budget = ctas == 2 ? 112 * 1024 : 224 * 1024;
+    mb_max = (ctas == 2 ? 256 : 512) / N;
+    const int mb_smem = ((smem_budget - w_bytes - 64) / (32 * nkc) - halo) / 128;
+    if (mb_smem < mb_max) mb_max = mb_smem;
+    TI = mb_max >= 1 ? mb_max * 128 / PJ : 0;
+    if (TI >= 1 && (ctas == 1 || mb_max >= 2)) break;
+  }
+  if (ctas < 1 || TI < 1) return AEFFT_ERR_UNSUPPORTED;
   if (TI > Nx) TI = Nx;
   // enough tiles to occupy every SM
-  while (TI > 1 && (long long)B * ((Nx + TI - 1) / TI) < ctx->sm_count) TI = (TI + 1) / 2;
+  while (TI > 1 && (long long)B * ((Nx + TI - 1) / TI) < (long long)ctas * ctx->sm_count) TI = (TI + 1) / 2;
   ConvTcParams p;
   p.src0 = src0; p.src1 = src1; p.bias = bias; p.out = out; p.pre_div = pre_div;
   p.C = C; p.O = O; p.N = N; p.Nx = Nx; p.Ny = Ny;
-  p.NK = win.Nk; p.NL = win.Nl; p.T = T;
+  p.NK = win.Nk; p.NL = win.Nl; p.T = win.Nk * win.Nl;
   p.ai0 = win.ai0; p.aj0 = win.aj0; p.lo = win.lo;
   p.PJ = PJ; p.TI = TI;
   p.MB = (TI * PJ + 127) / 128;
   p.HP = (p.MB * 128 + halo + 7) / 8 * 8;
-  p.KS = (C + KC - 1) / KC;
+  p.KS = kpack ? 1 : (C + KC - 1) / KC;
+  p.kpack = kpack; p.TE = TE;
   p.tiles_per_frame = (Nx + TI - 1) / TI;
   p.n_tiles = (long long)B * p.tiles_per_frame;
   p.passes = passes;
   p.tmem_cols = pow2_cols(p.MB * N);
-  if (p.tmem_cols > 512 || (size_t)p.HP * 16 > 262000) return AEFFT_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)w_bytes + 64 * (size_t)p.HP + 64;
-  if (smem > 227 * 1024) return AEFFT_ERR_UNSUPPORTED;
+  if (p.tmem_cols > (ctas == 2 ? 256u : 512u) || (size_t)p.HP * 16 > 262000) return AEFFT_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)w_bytes + 32 * (size_t)nkc * p.HP + 64;
+  if (smem > (size_t)(ctas == 2 ? 113 : 227) * 1024) return AEFFT_ERR_UNSUPPORTED;
   // weights -> bf16 hi/lo shared-memory images
   __nv_bfloat16* wprep;
-  AE_TRY(ctx->getT(win.flip ? "tc_wprep_f" : "tc_wprep_t", (size_t)p.KS * 2 * T * 2 * N * 8, &wprep));
+  AE_TRY(ctx->getT(win.flip ? "tc_wprep_f" : "tc_wprep_t", (size_t)p.KS * 2 * TE * 2 * N * 8, &wprep));
   {
-    const long long total = (long long)p.KS * T * 2 * N * 8;
+    const long long total = (long long)p.KS * TE * 2 * N * 8;
     weight_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(w, w_so, w_sc, C, O, N, win.Nk, win.Nl, win.flip,
-                                                                              p.KS, wprep);
+                                                                              p.KS, kpack, wprep);
     ctx->launches++;
   }
   p.wprep = reinterpret_cast<const uint4*>(wprep);
@@ -251,9 +279,10 @@ int launch_conv_tc(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
     attr_smem = 227 * 1024;
   }
   const double px = (double)B * Nx * Ny;
-  ProfScope prof(ctx, win.flip ? "conv_fwd_tc" : "conv_dgrad_tc", 2.0 * px * C * O * T,
-                 4.0 * (px * C * (src1 ? 2 : 1) + px * O + (double)C * O * T));
-  const unsigned grid = (unsigned)(p.n_tiles < ctx->sm_count ? p.n_tiles : ctx->sm_count);
+  ProfScope prof(ctx, win.flip ? "conv_fwd_tc" : "conv_dgrad_tc", 2.0 * px * C * O * p.T,
+                 4.0 * (px * C * (src1 ? 2 : 1) + px * O + (double)C * O * p.T));
+  const long long slots = (long long)ctas * ctx->sm_count;
+  const unsigned grid = (unsigned)(p.n_tiles < slots ? p.n_tiles : slots);
   conv_tc_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(p);
   ctx->launches++;
   AE_CUDA(cudaGetLastError());

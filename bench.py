@@ -220,6 +220,7 @@ def run_ours(args, w, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = A.Ctx(local_rank)
+    ctx.set_precision({"fp32": A.PRECISION_FP32, "bf16x3": A.PRECISION_BF16X3, "bf16": A.PRECISION_BF16}[args.precision])
     # all engine work, the NCCL collectives and the timing events share ONE non-default torch stream
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -345,7 +346,9 @@ def run_ours(args, w, rank, world, local_rank):
         line = {
             "metric": "training frames/sec (fwd+backprop)", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16x3": "f32 (bf16x3 split on tcgen05, fp32 accumulate)", "bf16": "bf16"}[args.precision],
+            "data": "synthetic",
             "config": config_dict(w, args, world),
             "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": n0 * 4,
                     "d2h_bytes_per_step": 4 * P, "ms_per_step": e2e_ms / args.steps},
@@ -376,6 +379,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.batch is None:
