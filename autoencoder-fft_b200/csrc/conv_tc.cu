@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(ConvTcParams p) 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 0) tmem_alloc(tmem_slot, p.tmem_cols);
   if (tid == 32) {
-    mbar_init(bar, 1);
+    mbar_init(bar, 4);
     fence_mbar_init();
   }
   fence_before_sync();
@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(ConvTcParams p) 
       }
       fence_proxy_async();
       __syncthreads();
-      // ---- one thread issues every MMA of this stage, then commits to the mbarrier ----
-      if (tid == 0) {
+      // ---- issue every MMA of this stage, then commit to the mbarrier ----
+      if (warp < 4 && lane == 0) {  // four issuing threads, M-blocks interleaved between them
         fence_after_sync();
         const uint32_t w_pass = (uint32_t)w_bytes / 2, w_tap = 32u * p.N;
         const uint32_t a_lbo = p.kpack ? 16u : (uint32_t)a_plane;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(ConvTcParams p) 
         // descriptors differ only in their 14-bit start-address field: build once, then add (bytes >> 4)
         const uint64_t a_hi0 = make_desc(Asm_addr, a_lbo, 128), a_lo0 = make_desc(Asm_addr + nkc * a_plane, a_lbo, 128);
         const uint64_t b_hi0 = make_desc(Wsm_addr, 16u * p.N, 128), b_lo0 = make_desc(Wsm_addr + w_pass, 16u * p.N, 128);
-        for (int mb = 0; mb < p.MB; mb++) {
+        for (int mb = warp; mb < p.MB; mb += 4) {
           const uint32_t d = tmem_base + (uint32_t)(mb * p.N);
           uint32_t t = 0;
           for (int tk = 0; tk < p.NK; tk++) {

@@ -33,16 +33,28 @@ __global__ void pool_down_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
+// One thread per 4 consecutive OUTPUT pixels of a row (128-bit store) when the row length allows it.
 __global__ void pool_up_kernel(const float* __restrict__ in, float* __restrict__ out, long long planes, int Nx,
-                               int Ny, int oNx, int oNy, int s) {
+                               int Ny, int oNx, int oNy, int s, int vec) {
   long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = planes * oNx * oNy;
+  const int w = vec ? oNy / 4 : oNy;
+  long long total = planes * oNx * w;
   if (n >= total) return;
-  int oj = n % oNy;
-  int oi = (n / oNy) % oNx;
-  long long pl = n / ((long long)oNy * oNx);
-  int si = min(oi / s, Nx - 1), sj = min(oj / s, Ny - 1);
-  out[n] = __ldg(in + pl * Nx * Ny + (long long)si * Ny + sj);
+  int oj = (int)(n % w) * (vec ? 4 : 1);
+  int oi = (n / w) % oNx;
+  long long pl = n / ((long long)w * oNx);
+  const float* src = in + pl * Nx * Ny + (long long)min(oi / s, Nx - 1) * Ny;
+  float* dst = out + (pl * oNx + oi) * oNy + oj;
+  if (vec) {
+    float4 v;
+    v.x = __ldg(src + min(oj / s, Ny - 1));
+    v.y = __ldg(src + min((oj + 1) / s, Ny - 1));
+    v.z = __ldg(src + min((oj + 2) / s, Ny - 1));
+    v.w = __ldg(src + min((oj + 3) / s, Ny - 1));
+    *reinterpret_cast<float4*>(dst) = v;
+  } else {
+    *dst = __ldg(src + min(oj / s, Ny - 1));
+  }
 }
 
 int launch_pool(aefft_ctx* ctx, int64_t B, int D, int Nx, int Ny, int oNx, int oNy, int scale, const float* in,
@@ -52,10 +64,13 @@ int launch_pool(aefft_ctx* ctx, int64_t B, int D, int Nx, int Ny, int oNx, int o
   long long total = planes * oNx * oNy;
   unsigned blocks = (unsigned)((total + 255) / 256);
   ProfScope prof(ctx, scale > 0 ? "pool_down" : "pool_up", 0.0, 4.0 * (planes * (double)Nx * Ny + (double)total));
-  if (scale > 0)
+  if (scale > 0) {
     pool_down_kernel<<<blocks, 256, 0, ctx->stream>>>(in, out, planes, Nx, Ny, oNx, oNy, scale);
-  else
-    pool_up_kernel<<<blocks, 256, 0, ctx->stream>>>(in, out, planes, Nx, Ny, oNx, oNy, -scale);
+  } else {
+    const int vec = (oNy % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const long long items = vec ? total / 4 : total;
+    pool_up_kernel<<<(unsigned)((items + 255) / 256), 256, 0, ctx->stream>>>(in, out, planes, Nx, Ny, oNx, oNy, -scale, vec);
+  }
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
   return AEFFT_OK;

@@ -6,8 +6,10 @@
 // Both are the SAME job shape: an unshifted "M-side" operand with dM channels (dh or hin) against a shifted "N-side"
 // operand with a chunk of <= 16 of the dD channels (in, shifted by +s_t; or e = out-in, shifted by -s_t, i.e. the
 // mirrored window).  GEMM view per tap:  D_t[m][x] += sum_pixels  Mop[pixel][m] * Nop[pixel + shift_t][x]
-//   M = 64 (channels m, TMEM rows), N = 16 (channels x), K = 16 pixels per MMA, one fp32 accumulator per tap in TMEM
-//   (25 taps x 16 columns = 400 of the 512 columns), accumulated over ALL tiles a CTA processes.
+//   M = 64 (channels m, TMEM rows), K = 16 pixels per MMA, and N = NL taps x 8 channels: the N-side chunk is ONE
+//   8-channel plane, and consecutive 8-column groups of N are the same plane advanced by one pixel (SBO = 16 bytes),
+//   so one MMA covers a whole window row (tl = 0..NL-1).  NK accumulators of 8*NL columns live in TMEM (200 of 256
+//   columns for 5x5) and are accumulated over ALL tiles a CTA processes; warp tk issues the MMAs of window row tk.
 // Operands are staged in shared memory as 8-channel planes [plane][linear pixel][8 x bf16] (16 bytes per pixel), the
 // SWIZZLE_NONE MN-major canonical layout (K = pixel rows at 16-byte pitch, 8-row core matrices contiguous), so the tap
 // shift is again just a start-address offset on the N-side descriptor: 25 taps reuse one staged tile.
@@ -23,7 +25,7 @@ namespace aefft {
 using namespace umma;
 
 constexpr int WT_THREADS = 256;
-constexpr int WT_N = 16;  // N-side channels per job
+constexpr int WT_N = 8;   // N-side channels per job (one plane)
 
 struct WgJob {
   const float* m0;   // M-side operand [B][dM][Nx][Ny]
@@ -92,7 +94,7 @@ __device__ __forceinline__ void stage_planes(unsigned char* hi_base, unsigned ch
   }
 }
 
-__global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(WgradTcParams p) {
+__global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradTcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   // [M hi: MPl planes][M lo: MPl planes][N hi: 2 planes][N lo: 2 planes] ... the M=64 MMA addresses 8 M-side planes from
   // each base; planes beyond MPl alias whatever follows (their TMEM rows are never read), the host sizes the
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(WgradTcParams p
   unsigned char* Mhi = smem;
   unsigned char* Mlo = Mhi + (size_t)p.MPl * p.m_plane;
   unsigned char* Nhi = Mlo + (size_t)p.MPl * p.m_plane;
-  unsigned char* Nlo = Nhi + 2 * (size_t)p.n_plane;
+  unsigned char* Nlo = Nhi + (size_t)p.n_plane;
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_slot;
 
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(WgradTcParams p
   const WgJob& J = p.job[jb];
   if (warp == 0) tmem_alloc(&tmem_slot, p.tmem_cols);
   if (tid == 32) {
-    mbar_init(&bar, 4);
+    mbar_init(&bar, p.NK);
     fence_mbar_init();
   }
   fence_before_sync();
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(WgradTcParams p
   fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
   uint32_t phase = 0;
-  const uint32_t idesc = make_idesc_bf16(64, WT_N, 1, 1);
+  const uint32_t idesc = make_idesc_bf16(64, WT_N * p.NL, 1, 1);
   const long long plane = (long long)p.Nx * p.Ny;
   const int nch = min(WT_N, p.dD - J.nch0);
   bool first = true;
@@ -129,27 +131,24 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(WgradTcParams p
     // M-side on the output grid (zero in the pad columns and beyond the tile), N-side on its halo grid
     stage_planes(Mhi, Mlo, p.m_plane, p.MPl, p.KQ, p.PJ, J.m0 + b * p.dM * plane, nullptr, 0, p.dM, plane, p.Nx, p.Ny, i0, 0,
                  rows_valid, p.Ny);
-    stage_planes(Nhi, Nlo, p.n_plane, 2, p.HPn, p.PJ, J.n0 + b * p.dD * plane, J.n1 ? J.n1 + b * p.dD * plane : nullptr, J.nch0,
+    stage_planes(Nhi, Nlo, p.n_plane, 1, p.HPn, p.PJ, J.n0 + b * p.dD * plane, J.n1 ? J.n1 + b * p.dD * plane : nullptr, J.nch0,
                  nch, plane, p.Nx, p.Ny, i0 + J.oi, J.oj, 1 << 30, 1 << 30);
     fence_proxy_async();
     __syncthreads();
-    // ---- four issuing threads (lane 0 of warps 0..3) split the taps; each owns its taps' accumulators ----
-    if (warp < 4 && lane == 0) {
+    // ---- NK issuing threads (lane 0 of warps 0..NK-1): warp tk owns window row tk and its accumulator ----
+    if (warp < p.NK && lane == 0) {
       fence_after_sync();
       const uint64_t m_hi0 = make_desc(smem_u32(Mhi), 128, p.m_plane), m_lo0 = make_desc(smem_u32(Mlo), 128, p.m_plane);
-      const uint64_t n_hi0 = make_desc(smem_u32(Nhi), 128, p.n_plane), n_lo0 = make_desc(smem_u32(Nlo), 128, p.n_plane);
+      const uint64_t n_hi0 = make_desc(smem_u32(Nhi), 128, 16), n_lo0 = make_desc(smem_u32(Nlo), 128, 16);
       const int ksteps = p.KQ / 16;
-      for (int t = warp; t < p.T; t += 4) {
-        const int tk = t / p.NL, tl = t - tk * p.NL;
-        const uint32_t d = tmem_base + (uint32_t)(t * WT_N);
-        const uint64_t shift = (uint64_t)(tk * p.PJ + tl);
-        for (int ks = 0; ks < ksteps; ks++) {
-          const uint64_t q = (uint64_t)(ks * 16);
-          mma_bf16(d, m_hi0 + q, n_hi0 + q + shift, idesc, !(first && ks == 0));
-          if (p.passes == 3) {
-            mma_bf16(d, m_hi0 + q, n_lo0 + q + shift, idesc, true);
-            mma_bf16(d, m_lo0 + q, n_hi0 + q + shift, idesc, true);
-          }
+      const uint32_t d = tmem_base + (uint32_t)(warp * WT_N * p.NL);
+      const uint64_t shift = (uint64_t)(warp * p.PJ);
+      for (int ks = 0; ks < ksteps; ks++) {
+        const uint64_t q = (uint64_t)(ks * 16);
+        mma_bf16(d, m_hi0 + q, n_hi0 + q + shift, idesc, !(first && ks == 0));
+        if (p.passes == 3) {
+          mma_bf16(d, m_hi0 + q, n_lo0 + q + shift, idesc, true);
+          mma_bf16(d, m_lo0 + q, n_hi0 + q + shift, idesc, true);
         }
       }
       commit(&bar);
@@ -164,17 +163,19 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(WgradTcParams p
     float* part = p.part + (long long)cta * p.n_out + J.g_off;
     const int m = warp * 16 + lane;
     const int TT = p.NK * p.NL;
-    for (int t = 0; t < p.T; t++) {
+    const int ncols = p.T * WT_N;  // column = (tk*NL + tl)*8 + x
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
       float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * WT_N), v);
+      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
       if (lane < 16 && m < p.dM) {
-        int tk = t / p.NL, tl = t - tk * p.NL;
-        if (J.rev) { tk = p.NK - 1 - tk; tl = p.NL - 1 - tl; }
-        const int k = p.flip ? p.NK - 1 - tk : tk, l = p.flip ? p.NL - 1 - tl : tl;
 #pragma unroll
         for (int e = 0; e < 16; e++) {
-          const int d = J.nch0 + e;
-          if (e < nch) {
+          const int col = c0 + e, t = col >> 3, x = col & 7;
+          if (col < ncols && x < nch) {
+            int tk = t / p.NL, tl = t - tk * p.NL;
+            if (J.rev) { tk = p.NK - 1 - tk; tl = p.NL - 1 - tl; }
+            const int k = p.flip ? p.NK - 1 - tk : tk, l = p.flip ? p.NL - 1 - tl : tl;
+            const int d = J.nch0 + x;
             const long long gi = J.is_gf ? (((long long)d * p.dM + m) * TT + k * p.NL + l)
                                          : (((long long)m * p.dD + d) * TT + k * p.NL + l);
             part[gi] = v[e];
@@ -192,21 +193,29 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(WgradTcParams p
 //   sum[c] = sum_{b,pix} (a0 - a1)[b][c](pix) ;  sumsq = sum (a0 - a1)^2          (bias gradients and the printed mse)
 __global__ void channel_sums_kernel(const float* __restrict__ a0, const float* __restrict__ a1, long long B, int ch,
                                     long long plane, int nsplit, double* __restrict__ part_sum, double* __restrict__ part_sq) {
+  // block (c, sp): frame b = sp / per_frame, segment seg = sp % per_frame of that frame's channel plane
   const int c = blockIdx.x, sp = blockIdx.y;
-  const long long total = B * plane;
-  const long long lo = total * sp / nsplit, hi = total * (sp + 1) / nsplit;
-  double s = 0.0, q = 0.0;
+  const int per_frame = nsplit / (int)B;
+  const long long b = sp / per_frame;
+  const int seg = sp - (int)b * per_frame;
+  const long long lo = plane * seg / per_frame, hi = plane * (seg + 1) / per_frame;
+  const float* p0 = a0 + (b * ch + c) * plane;
+  const float* p1 = a1 ? a1 + (b * ch + c) * plane : nullptr;
+  float s = 0.f, q = 0.f;  // short per-thread runs in fp32, everything across threads / blocks in double
+  double ds = 0.0, dq = 0.0;
+  int run = 0;
   for (long long n = lo + threadIdx.x; n < hi; n += blockDim.x) {
-    const long long b = n / plane, pix = n - b * plane;
-    const long long off = (b * ch + c) * plane + pix;
-    float v = __ldg(a0 + off);
-    if (a1) v -= __ldg(a1 + off);
-    s += (double)v;
-    q += (double)v * (double)v;
+    float v = __ldg(p0 + n);
+    if (p1) v -= __ldg(p1 + n);
+    s += v;
+    q = fmaf(v, v, q);
+    if (++run == 16) { ds += (double)s; dq += (double)q; s = 0.f; q = 0.f; run = 0; }
   }
+  ds += (double)s;
+  dq += (double)q;
   __shared__ double rs[256], rq[256];
-  rs[threadIdx.x] = s;
-  rq[threadIdx.x] = q;
+  rs[threadIdx.x] = ds;
+  rq[threadIdx.x] = dq;
   __syncthreads();
   for (int h = 128; h > 0; h >>= 1) {
     if (threadIdx.x < h) { rs[threadIdx.x] += rs[threadIdx.x + h]; rq[threadIdx.x] += rq[threadIdx.x + h]; }
@@ -237,8 +246,11 @@ __global__ void channel_sums_final_kernel(const double* __restrict__ part_sum, c
 int launch_channel_sums(aefft_ctx* ctx, int64_t B, int ch, int Nx, int Ny, const float* a0, const float* a1, float* sum,
                         float* sumsq) {
   AE_ARG(ch > 0 && ch <= 256);
-  int nsplit = (2 * ctx->sm_count + ch - 1) / ch;
-  if (nsplit < 1) nsplit = 1;
+  // enough blocks to fill the machine: every frame's channel plane is cut into per_frame segments
+  int per_frame = (int)((4LL * ctx->sm_count + (long long)ch * B - 1) / ((long long)ch * B));
+  if (per_frame < 1) per_frame = 1;
+  AE_ARG(B * per_frame <= 65535);
+  const int nsplit = (int)B * per_frame;
   double* part;
   AE_TRY(ctx->getT("chsum_part", (size_t)2 * ch * nsplit, &part));
   const double px = (double)B * Nx * Ny;
@@ -264,12 +276,19 @@ __global__ void reduce_parts_kernel(const float* __restrict__ part, int n_parts,
 int launch_wgrad_tc(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM, int Nx, int Ny, const float* in,
                     const float* out, const float* hin, const float* dh, float* G, int passes) {
   const int T = win.Nk * win.Nl;
-  if (dM % 8 != 0 || dM < 8 || dM > 64 || T * WT_N > 512 || win.lo != 0) return AEFFT_ERR_UNSUPPORTED;
+  const int ncols = T * WT_N;
+  if (dM % 8 != 0 || dM < 8 || dM > 64 || ncols > 512 || win.Nk > 8 || WT_N * win.Nl > 256 || win.lo != 0)
+    return AEFFT_ERR_UNSUPPORTED;
   const int n_chunks = (dD + WT_N - 1) / WT_N;
   if (2 * n_chunks > 8) return AEFFT_ERR_UNSUPPORTED;
   const int PJ = Ny + win.Nl - 1;
   const int halo = (win.Nk - 1) * PJ + win.Nl + 8;
   const int MPl = dM / 8;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < ncols + 16) tmem_cols <<= 1;  // +16: the last 16-column epilogue load may overhang
+  if (tmem_cols > 512) return AEFFT_ERR_UNSUPPORTED;
+  const int ctas = tmem_cols <= 256 ? 2 : 1;           // co-resident CTAs per SM
+  const size_t budget = ctas == 2 ? 110 * 1024 : 220 * 1024;
   // largest tile (rows) whose staging fits in shared memory
   int TI = Nx, KQ = 0, HPn = 0;
   size_t smem = 0;
@@ -277,10 +296,10 @@ int launch_wgrad_tc(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
     KQ = (TI * PJ + 15) / 16 * 16;
     HPn = (KQ + halo + 7) / 8 * 8;
     const size_t m_plane = (size_t)KQ * 16, n_plane = (size_t)HPn * 16;
-    smem = 2 * MPl * m_plane + 4 * n_plane;
+    smem = 2 * MPl * m_plane + 2 * n_plane;
     const size_t span = (size_t)(MPl + 8) * m_plane;  // reach of the junk planes of the "lo" descriptor
     if (span > smem) smem = span;
-    if (smem <= 220 * 1024 && m_plane < 262000 && n_plane < 262000) break;
+    if (smem <= budget && m_plane < 262000 && n_plane < 262000) break;
   }
   if (TI < 1) return AEFFT_ERR_UNSUPPORTED;
   WgradTcParams p;
@@ -290,9 +309,9 @@ int launch_wgrad_tc(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   p.tiles_per_frame = (Nx + TI - 1) / TI;
   p.n_tiles = (long long)B * p.tiles_per_frame;
   p.passes = passes; p.flip = win.flip;
-  p.tmem_cols = 512;
+  p.tmem_cols = tmem_cols;
   p.n_jobs = 2 * n_chunks;
-  int cpj = ctx->sm_count / p.n_jobs;
+  int cpj = ctas * ctx->sm_count / p.n_jobs;
   if (cpj < 1) cpj = 1;
   if (cpj > p.n_tiles) cpj = (int)p.n_tiles;
   p.ctas_per_job = cpj;
@@ -310,10 +329,10 @@ int launch_wgrad_tc(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   float* part;
   AE_TRY(ctx->getT("wgtc_part", (size_t)cpj * p.n_out, &part));
   p.part = part;
-  static bool attr = false;
-  if (!attr) {
-    AE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64));
-    attr = true;
+  static size_t attr = 0;
+  if (smem > attr) {
+    AE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
   }
   {
     const double px = (double)B * Nx * Ny;
