@@ -256,6 +256,7 @@ int aefft_create(aefft_ctx** out, int device) {
   }
   AE_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
+  ctx->precision = AEFFT_PRECISION_BF16X3;  // tensor-core path with fp32-grade accuracy is the default
   *out = ctx;
   return AEFFT_OK;
 }

@@ -136,8 +136,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(ConvTcParams p) 
 #pragma unroll
           for (int e = 0; e < 8; e++) v[e] -= u[e];
         } else if (p.pre_div != 0.f) {
+          const float rinv = 1.f / p.pre_div;  // exact for the power-of-two channel counts; 1 ulp otherwise
 #pragma unroll
-          for (int e = 0; e < 8; e++) v[e] = __fdiv_rn(v[e], p.pre_div);
+          for (int e = 0; e < 8; e++) v[e] *= rinv;
         }
         __nv_bfloat16 hi[8], lo[8];
 #pragma unroll

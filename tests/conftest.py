@@ -22,6 +22,8 @@ def ctx():
     import aefft_ctypes as A
 
     c = A.Ctx(0)
+    assert c.precision == A.PRECISION_BF16X3, "library default is the tensor-core BF16X3 mode"
+    c.set_precision(A.PRECISION_FP32)  # the fp32 CUDA-core kernels are what test_coord_gpu pins; test_tc_gpu switches modes
     yield c
     c.close()
 

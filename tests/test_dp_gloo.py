@@ -1,0 +1,94 @@
+"""CPU test of the multi-rank path (world_size 2, gloo): rank r computes the oracle's raw gradient sums of ITS frames
+(dp.frame_range), the block is all-reduced (dp.allreduce_gradient_block), every rank applies the same clipped-momentum
+update -> identical weights on both ranks, equal to the single-process full-batch step.  Also shows why the reduction
+must come before the clip."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "autoencoder-fft_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def _case():
+    import oracle_np as O
+
+    rng = np.random.default_rng(0)
+    B, dD, dM, Nk, Nl, Nx, Ny = 4, 2, 3, 3, 3, 10, 8
+    inp = O.synth_frames(1234, B, dD, Nx, Ny)
+    c = ((rng.random((dM, dD, Nk, Nl)) * 2 - 1) * 0.2).astype(np.float32)
+    f = np.ascontiguousarray(np.swapaxes(c, 0, 1))
+    b = (rng.random(dM) * 2 - 1).astype(np.float32)
+    p = (rng.random(dD) * 2 - 1).astype(np.float32)
+    hin = O.conv_gpu(inp, c, b).astype(np.float32)
+    out = O.conv_gpu(hin, f, p).astype(np.float32)
+    return inp, out, hin, c, b, f, p
+
+
+def _raw_sums(inp, out, hin, c, f):
+    """[g | gB | gP | sq] summed over the given frames (what aefft_coord_gradients returns for CUDA_REF_SYM, in the
+    combined form g = gC + gF^T), un-normalised."""
+    import oracle_np as O
+
+    acc = None
+    for n in range(inp.shape[0]):
+        g, gB, gP, mse = O.coord_gradients_cuda(inp[n], out[n], hin[n], c, f, True)
+        v = np.concatenate([g.ravel(), gB.ravel(), gP.ravel(), [mse]])
+        acc = v if acc is None else acc + v
+    return acc
+
+
+def _worker(rank, world, port, ret):
+    import dp
+    import oracle_np as O
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    inp, out, hin, c, b, f, p = _case()
+    b0, n = dp.frame_range(rank, world, inp.shape[0] // world)
+    sl = slice(b0, b0 + n)
+    g = torch.from_numpy(_raw_sums(inp[sl], out[sl], hin[sl], c, f))
+    dp.allreduce_gradient_block(g, world)
+    g = g.numpy() / inp.shape[0]  # mean over the GLOBAL batch
+    nC = c.size
+    c2, _ = O.momentum_update(c, np.zeros_like(c), g[:nC].reshape(c.shape), 0.2, 0.9)
+    b2, _ = O.momentum_update(b, np.zeros_like(b), g[nC:nC + b.size], 0.2, 0.9)
+    ret[rank] = (c2, b2)
+    dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_full_batch():
+    import oracle_np as O
+
+    world, port = 2, 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    inp, out, hin, c, b, f, p = _case()
+    z = lambda a: np.zeros_like(a)
+    want = O.backprop_gpu_cc(inp, out, hin, c, b, f, p, z(c), z(b), z(f), z(p), z(c), z(b), z(f), z(p), 0.2, 0.9)
+    for r in range(world):
+        c2, b2 = ret[r]
+        assert O.rel_l2(c2, want["c"]) < 1e-12 and O.rel_l2(b2, want["b"]) < 1e-12
+    assert np.array_equal(ret[0][0], ret[1][0])  # replicas stay bit-identical without any broadcast
+
+
+def test_clip_is_nonlinear_so_reduce_raw_gradients():
+    import oracle_np as O
+
+    g1, g2 = np.array([30.0, 2.0]), np.array([-10.0, 2.0])
+    assert not np.allclose(O.clip10((g1 + g2) / 2), (O.clip10(g1) + O.clip10(g2)) / 2)
+
+
+def test_frame_range_partitions_the_global_batch():
+    import dp
+
+    owned = [dp.frame_range(r, 4, 16) for r in range(4)]
+    assert owned == [(0, 16), (16, 16), (32, 16), (48, 16)]
