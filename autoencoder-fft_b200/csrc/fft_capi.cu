@@ -349,3 +349,35 @@ int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int N
 }
 
 }  // extern "C"
+
+extern "C" {
+
+// backprop_fft on layers that live inside a per-frame strided layer block (the layout aefft_autoenc_fft writes):
+// frame b's `in` / `out` start at in + b*frame_stride / out + b*frame_stride (device pointers).  expout = in, as the
+// reference's app calls it (autoencoder.cpp:194).  The frames are gathered once into contiguous scratch.
+int aefft_backprop_fft_strided(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl, const float* in,
+                               const float* out, int64_t frame_stride, float* c, float* f, float* b, float* p, float del0,
+                               int maxdiff, int n_iter, float* mse_trace) {
+  AE_ARG(ctx && in && out && B > 0 && frame_stride >= (int64_t)dD * Nx * Ny);
+  AE_CUDA(cudaSetDevice(ctx->device));
+  const size_t w = (size_t)dD * Nx * Ny * sizeof(float);
+  float *gin, *gout;
+  AE_TRY(ctx->getT("bpfs_in", (size_t)B * dD * Nx * Ny, &gin));
+  AE_TRY(ctx->getT("bpfs_out", (size_t)B * dD * Nx * Ny, &gout));
+  AE_CUDA(cudaMemcpy2DAsync(gin, w, in, (size_t)frame_stride * sizeof(float), w, (size_t)B, cudaMemcpyDeviceToDevice, ctx->stream));
+  AE_CUDA(cudaMemcpy2DAsync(gout, w, out, (size_t)frame_stride * sizeof(float), w, (size_t)B, cudaMemcpyDeviceToDevice, ctx->stream));
+  return aefft_backprop_fft(ctx, AEFFT_DEVICE, B, dD, dM, Nx, Ny, Nk, Nl, gin, gin, gout, nullptr, c, nullptr, f, b, p, del0, maxdiff,
+                            n_iter, mse_trace);
+}
+
+// Strided 2-D copy (rows of `width` bytes, `height` rows) ordered on the ctx stream; kind as in aefft_memcpy.
+int aefft_memcpy2d(aefft_ctx* ctx, void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width, int64_t height,
+                   int kind) {
+  AE_ARG(ctx && dst && src && width >= 0 && height >= 0 && dpitch >= width && spitch >= width && kind >= 0 && kind <= 2);
+  AE_CUDA(cudaSetDevice(ctx->device));
+  const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  AE_CUDA(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height, k, ctx->stream));
+  return AEFFT_OK;
+}
+
+}  // extern "C"

@@ -209,6 +209,180 @@ class CudaArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
 
+class CoordWorkload:
+    """c2: device-resident net, CUDA_REF_SYM step (forward + every pair), data-parallel all-reduce per pair."""
+
+    def __init__(self, A, ctx, w, args, rank, world, dev, torch, dist):
+        self.A, self.ctx, self.w, self.world, self.torch, self.dist, self.dev = A, ctx, w, world, torch, dist, dev
+        B = self.B = args.batch
+        ctypes.CDLL("libc.so.6").srand(SEED)
+        self.net = net = A.Net(ctx, w["D"], w["Nx"], w["Ny"], B)
+        for m in w["widths"]:
+            net.add_layer(m, w["Lk"], w["Ll"], w["pool"], w["rmax"])
+        self.P = net.num_pairs
+        for n in range(self.P):
+            net.set_symmetric(n)  # 'p' key: decoder = transposed encoder before symmetric training
+        self.mode = A.MODE_CUDA_REF_SYM
+        _, _, _, self.l0 = net.layer_info(0)
+        self.n0 = B * w["D"] * w["Nx"] * w["Ny"]
+        ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=rank * B, out=self.l0, loc=A.DEVICE)
+        self.gviews = []
+        self.h2d_bytes, self.d2h_bytes = self.n0 * 4, 4 * self.P
+        # end-to-end: pinned host frames, two device staging buffers, uploads on a second stream
+        self.host = torch.empty(self.n0, dtype=torch.float32).pin_memory()
+        A.lib().aefft_memcpy(ctx.h, ctypes.c_void_p(self.host.data_ptr()), ctypes.c_void_p(self.l0), ctypes.c_int64(self.n0 * 4), 1)
+        self.mse_host = torch.zeros(64, dtype=torch.float32).pin_memory()
+        self.stage = [torch.empty(self.n0, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.copied = [torch.cuda.Event() for _ in range(2)]
+        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+
+    def _train(self, frames_ptr, want_mse):
+        A, net = self.A, self.net
+        if self.world == 1:
+            net.step(frames_ptr, self.mode, DELMAX, ALPHA, loc=A.DEVICE, mse=self.mse_host if want_mse else None)
+            return
+        net.forward(frames_ptr, loc=A.DEVICE)
+        for n in range(self.P):
+            ptr, glen = net.pair_gradients(n, self.mode)
+            if len(self.gviews) <= n:
+                self.gviews.append(self.torch.as_tensor(CudaArray(ptr, glen), device=self.dev))
+            self.dist.all_reduce(self.gviews[n])
+            net.pair_update(n, self.mode, self.B * self.world, DELMAX, ALPHA, want_mse=(want_mse and n == self.P - 1))
+
+    def step_resident(self):
+        self._train(None, False)
+
+    def e2e_begin(self):
+        """Queue the upload of the first batch."""
+        self.k = 0
+        self._upload(0)
+
+    def _upload(self, slot):
+        torch = self.torch
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.consumed[slot])  # the step that last read this buffer has finished
+            self.stage[slot].copy_(self.host, non_blocking=True)
+            self.copied[slot].record(self.copy_stream)
+
+    def step_e2e(self):
+        """One step on host frames: its own H2D (overlapped with the previous step's compute) + mse read back."""
+        torch = self.torch
+        slot = self.k % 2
+        self._upload(1 - slot)  # next step's frames travel while this step computes
+        torch.cuda.current_stream().wait_event(self.copied[slot])
+        self._train(self.stage[slot], True)
+        self.consumed[slot].record(torch.cuda.current_stream())
+        self.k += 1
+
+    def describe_e2e(self):
+        return ("pinned host frames -> double-buffered device staging on a copy stream (upload of step k+1 overlaps step k), "
+                "aefft_net_step(AEFFT_DEVICE) + mse D2H and stream sync every step")
+
+    def close(self):
+        self.net.close()
+
+
+class FftWorkload:
+    """c3: momentum-space training.  One step = autoenc_fft forward of the whole stack (all layers materialised, as the
+    reference needs them for training) + ONE iteration of backprop_fft's loop for every pair (the survey's
+    definition of an FFT-space training step), on B frames, through the C ABI with device pointers."""
+
+    def __init__(self, A, ctx, w, args, rank, world, dev, torch, dist):
+        self.A, self.ctx, self.w, self.world, self.torch, self.dist = A, ctx, w, world, torch, dist
+        B = self.B = args.batch
+        import oracle_np as O  # only for the seeded Init_conv draw order (host glue), not on the timed path
+
+        Nk, Nl = 2 * (w["Lk"] + 1) + 1, 2 * (w["Ll"] + 1) + 1
+        rng = O.GlibcRand(SEED)
+        encs, d, nx, ny = [], w["D"], w["Nx"], w["Ny"]
+        shapes = [(d, nx, ny)]
+        for m in w["widths"]:
+            c, b = O.init_conv(rng, m, d, Nk, Nl, w["rmax"] / 10.0)
+            f = np.ascontiguousarray(np.swapaxes(c, 0, 1))
+            p_ = np.zeros(d, np.float32)
+            encs.append((c, b, f, p_, d, nx, ny))
+            nx, ny = nx // w["pool"], ny // w["pool"]
+            shapes += [(d, nx, ny), (m, nx, ny)]
+            d = m
+        for (c, b, f, p_, d0, nx0, ny0) in reversed(encs):
+            shapes += [(d0, nx0 // w["pool"], ny0 // w["pool"]), (d0, nx0, ny0)]
+        net_c = [e[0] for e in encs] + [e[2] for e in reversed(encs)]
+        net_b = [e[1] for e in encs] + [e[3] for e in reversed(encs)]
+        self.scale = np.array([w["pool"]] * len(encs) + [-w["pool"]] * len(encs), np.int32)
+        self.n_conv, self.shapes = len(net_c), shapes
+        self.dims = np.array([x for c in net_c for x in c.shape], np.int32)
+        self.coff = np.cumsum([0] + [c.size for c in net_c[:-1]]).astype(np.int64)
+        self.boff = np.cumsum([0] + [b.size for b in net_b[:-1]]).astype(np.int64)
+        self.ldims = np.array([x for s_ in shapes for x in s_], np.int32)
+        lsz = [int(np.prod(s_)) for s_ in shapes]
+        self.loff = np.cumsum([0] + lsz[:-1]).astype(np.int64)
+        self.lstride = int(sum(lsz))
+        self.c_all = ctx.to_device(np.concatenate([c.ravel() for c in net_c]))
+        self.b_all = ctx.to_device(np.concatenate([b.ravel() for b in net_b]))
+        self.layers = A.DevBuf(ctx, (B, self.lstride))
+        self.n0 = lsz[0]
+        frames = A.DevBuf(ctx, (B, self.n0))
+        ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=rank * B, out=frames.ptr, loc=A.DEVICE)
+        self.frames = frames
+        self.host = torch.empty(B * self.n0, dtype=torch.float32).pin_memory()
+        ctx.memcpy(self.host.data_ptr(), frames.ptr, B * self.n0 * 4, 1)
+        self.trace = np.zeros(2, np.float32)
+        self.pairs = []
+        P = len(encs)
+        for n in range(P):
+            dM, dD = net_c[n].shape[:2]
+            _, nx, ny = shapes[2 * n + 1]
+            self.pairs.append(dict(dM=dM, dD=dD, Nx=nx, Ny=ny, Nk=Nk, Nl=Nl, l_in=2 * n + 1, l_out=len(shapes) - 2 - 2 * n,
+                                   c=int(self.coff[n]), f=int(self.coff[2 * P - 1 - n]), b=int(self.boff[n]),
+                                   p=int(self.boff[2 * P - 1 - n])))
+        self.h2d_bytes, self.d2h_bytes = B * self.n0 * 4, 4 * P
+        self._put_frames(A.DEVICE, frames.ptr)
+
+    def _put_frames(self, kind_loc, src_ptr):
+        """layer 0 of every frame lives at layers[b*lstride]: strided copy of the batch's frames."""
+        A, ctx = self.A, self.ctx
+        A._chk(A.lib().aefft_memcpy2d(ctx.h, ctypes.c_void_p(self.layers.ptr), ctypes.c_int64(self.lstride * 4),
+                                      ctypes.c_void_p(src_ptr), ctypes.c_int64(self.n0 * 4), ctypes.c_int64(self.n0 * 4),
+                                      ctypes.c_int64(self.B), 0 if kind_loc == A.HOST else 2))
+
+    def _train(self):
+        A, ctx = self.A, self.ctx
+        I32, I64, FP = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64), A.FP
+        A._chk(A.lib().aefft_autoenc_fft(ctx.h, A.DEVICE, ctypes.c_int64(self.B), self.n_conv, self.dims.ctypes.data_as(I32),
+                                         A._ptr(self.c_all), self.coff.ctypes.data_as(I64), A._ptr(self.b_all),
+                                         self.boff.ctypes.data_as(I64), self.scale.ctypes.data_as(I32), len(self.shapes),
+                                         self.ldims.ctypes.data_as(I32), A._ptr(self.layers), self.loff.ctypes.data_as(I64),
+                                         ctypes.c_int64(self.lstride), 0, None, None, 1))
+        raise_if = A._chk
+        for q in self.pairs:
+            # the pair's in/out layers are strided per frame inside `layers`; backprop_fft wants [B][dD][Nx][Ny] contiguous
+            raise_if(A.lib().aefft_backprop_fft_strided(ctx.h, ctypes.c_int64(self.B), q["dD"], q["dM"], q["Nx"], q["Ny"], q["Nk"],
+                                                        q["Nl"], ctypes.c_void_p(self.layers.ptr + int(self.loff[q["l_in"]]) * 4),
+                                                        ctypes.c_void_p(self.layers.ptr + int(self.loff[q["l_out"]]) * 4),
+                                                        ctypes.c_int64(self.lstride),
+                                                        ctypes.c_void_p(self.c_all.ptr + q["c"] * 4), ctypes.c_void_p(self.c_all.ptr + q["f"] * 4),
+                                                        ctypes.c_void_p(self.b_all.ptr + q["b"] * 4), ctypes.c_void_p(self.b_all.ptr + q["p"] * 4),
+                                                        ctypes.c_float(DELMAX), 0, 1, self.trace.ctypes.data_as(FP)))
+
+    def step_resident(self):
+        self._train()
+
+    def e2e_begin(self):
+        pass
+
+    def step_e2e(self):
+        self._put_frames(self.A.HOST, self.host.data_ptr())
+        self._train()  # ends with the mse trace D2H + stream sync inside aefft_backprop_fft
+
+    def describe_e2e(self):
+        return "pinned host frames -> layer 0 (strided H2D) every step, mse trace read back per pair"
+
+    def close(self):
+        pass
+
+
 def run_ours(args, w, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -226,56 +400,32 @@ def run_ours(args, w, rank, world, local_rank):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     A._chk(A.lib().aefft_set_stream(ctx.h, ctypes.c_void_p(stream.cuda_stream)))
-    B = args.batch
-    if w["space"] != "coordinate":
-        raise SystemExit("workload c3 (FFT space) is benchmarked by bench_fft in a later round-1 milestone")
-    ctypes.CDLL("libc.so.6").srand(SEED)
-    net = A.Net(ctx, w["D"], w["Nx"], w["Ny"], B)
-    for m in w["widths"]:
-        net.add_layer(m, w["Lk"], w["Ll"], w["pool"], w["rmax"])
-    P = net.num_pairs
-    for n in range(P):
-        net.set_symmetric(n)  # 'p' key: decoder = transposed encoder before symmetric training
-    mode = A.MODE_CUDA_REF_SYM
-    _, _, _, l0 = net.layer_info(0)
-    n0 = B * w["D"] * w["Nx"] * w["Ny"]
-    ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=rank * B, out=l0, loc=A.DEVICE)
-    gviews = []
-
-    def step_resident():
-        if world == 1:
-            net.step(None, mode, DELMAX, ALPHA, loc=A.DEVICE)
-            return
-        net.forward(None, loc=A.DEVICE)
-        for n in range(P):
-            ptr, glen = net.pair_gradients(n, mode)
-            if len(gviews) <= n:
-                gviews.append(torch.as_tensor(CudaArray(ptr, glen), device=dev))
-            dist.all_reduce(gviews[n])
-            net.pair_update(n, mode, B * world, DELMAX, ALPHA)
+    if w["space"] == "fft" and world > 1:
+        raise SystemExit("the FFT-space workload is single-GPU in this round (DESIGN.md section 6)")
+    wl = (CoordWorkload if w["space"] == "coordinate" else FftWorkload)(A, ctx, w, args, rank, world, dev, torch, dist)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # started before the warm-up so that samples exist for short timed regions
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        wl.step_resident()
+    barrier()
     A._chk(A.lib().aefft_profile_enable(ctx.h, 1))
     l_before = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        step_resident()
+        wl.step_resident()
     e1.record()
     barrier()
     A._chk(A.lib().aefft_profile_enable(ctx.h, 0))
     launches = ctx.launches - l_before
-    clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -295,29 +445,18 @@ def run_ours(args, w, rank, world, local_rank):
         kernels.append(dict(name=nm, ms=float(kms[k]), launches=int(cnt[k]), flops=float(fl[k]), bytes=float(by[k])))
     kernels.sort(key=lambda r: -r["ms"])
 
-    # ---- end to end: pinned host frames -> device every step, mse read back every step
-    host = torch.empty(n0, dtype=torch.float32).pin_memory()
-    A.lib().aefft_memcpy(ctx.h, ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(l0), ctypes.c_int64(n0 * 4), 1)
-    mse_host = torch.zeros(64, dtype=torch.float32).pin_memory()
-
-    def step_e2e():
-        if world == 1:
-            net.step(host, mode, DELMAX, ALPHA, loc=A.HOST, mse=mse_host)
-            return
-        net.forward(host, loc=A.HOST)
-        for n in range(P):
-            net.pair_gradients(n, mode)
-            dist.all_reduce(gviews[n])
-            net.pair_update(n, mode, B * world, DELMAX, ALPHA, want_mse=(n == P - 1))
-
+    # ---- end to end: host frames every step, result read back every step
+    wl.e2e_begin()
     for _ in range(2):
-        step_e2e()
+        wl.step_e2e()
     barrier()
+    wl.e2e_begin()
     e0.record()
     for _ in range(args.steps):
-        step_e2e()
+        wl.step_e2e()
     e1.record()
     barrier()
+    clocks = sampler.stop() if rank == 0 else None
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
@@ -325,6 +464,7 @@ def run_ours(args, w, rank, world, local_rank):
 
     if rank == 0:
         pk = peaks()
+        B = args.batch
         frames = B * world * args.steps
         value = frames / (ms_total * 1e-3)
         top = kernels[0] if kernels else None
@@ -343,15 +483,17 @@ def run_ours(args, w, rank, world, local_rank):
             roof.update({"traffic": None, "kernel": top["name"], "avg_launch_ms": per_ms, "share_of_step": top["ms"] / ms_total,
                          "peak_source": pk["source"] + (", sustained bf16" if roof["bound"] == "tensor" else ""),
                          "algorithmic_flops_per_launch": fl_l, "algorithmic_bytes_per_launch": by_l})
+        cfg = config_dict(w, args, world)
+        cfg["e2e_path"] = wl.describe_e2e()
         line = {
             "metric": "training frames/sec (fwd+backprop)", "value": value, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16x3": "f32 (bf16x3 split on tcgen05, fp32 accumulate)", "bf16": "bf16"}[args.precision],
-            "data": "synthetic",
-            "config": config_dict(w, args, world),
-            "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": n0 * 4,
-                    "d2h_bytes_per_step": 4 * P, "ms_per_step": e2e_ms / args.steps},
+            "dtype": "c64/f32" if w["space"] == "fft" else
+                     {"fp32": "f32", "bf16x3": "f32 (bf16x3 split on tcgen05, fp32 accumulate)", "bf16": "bf16"}[args.precision],
+            "data": "synthetic", "config": cfg,
+            "e2e": {"value": frames / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": wl.h2d_bytes,
+                    "d2h_bytes_per_step": wl.d2h_bytes, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches) * world,
             "clocks": clocks,
             "roofline": roof,
@@ -364,7 +506,7 @@ def run_ours(args, w, rank, world, local_rank):
             line["cpu_baseline"] = {"value": cb["value"], "unit": "frames/s", "cores": cb["cores"], "kind": cb["kind"],
                                     "sample": cb["sample"]}
         print(json.dumps(line))
-    net.close()
+    wl.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

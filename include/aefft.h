@@ -170,6 +170,15 @@ int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int N
                        const float* in, const float* expout, const float* out, float* cfreq, float* c, float* ffreq,
                        float* f, float* b, float* p, float del0, int maxdiff, int n_iter, float* mse_trace);
 
+/* backprop_fft on layers stored per frame with stride `frame_stride` floats (the layer block aefft_autoenc_fft writes);
+ * device pointers, expout = in (autoencoder.cpp:194), spectra derived from c,f. */
+int aefft_backprop_fft_strided(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl, const float* in,
+                               const float* out, int64_t frame_stride, float* c, float* f, float* b, float* p, float del0,
+                               int maxdiff, int n_iter, float* mse_trace);
+/* Strided 2-D copy on the ctx stream (asynchronous): `height` rows of `width` bytes; kind as in aefft_memcpy. */
+int aefft_memcpy2d(aefft_ctx* ctx, void* dst, int64_t dpitch, const void* src, int64_t spitch, int64_t width,
+                   int64_t height, int kind);
+
 /* ------------------------------------------------------------------ glue (netlib.cpp:167-289) */
 
 /* Init_conv (netlib.cpp:167-197): consumes libc rand() in the reference's order; call srand() first. */
