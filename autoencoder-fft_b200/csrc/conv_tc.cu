@@ -214,6 +214,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(ConvTcParams p) 
   if (warp == 0) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// host wrapper shared with conv_tc_ws.cu
+void conv_weight_prep(aefft_ctx* ctx, const float* w, long long w_so, long long w_sc, int C, int O, int N, int NK, int NL,
+                      int flip, int KS, int kpack, void* wprep, long long total) {
+  weight_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(w, w_so, w_sc, C, O, N, NK, NL, flip, KS, kpack,
+                                                                            reinterpret_cast<__nv_bfloat16*>(wprep));
+  ctx->launches++;
+}
+
 static uint32_t pow2_cols(int n) {
   uint32_t c = 32;
   while ((int)c < n) c <<= 1;

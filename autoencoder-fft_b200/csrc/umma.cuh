@@ -87,7 +87,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   uint32_t spins = 0;
   do {
-    if (++spins > (1u << 24)) __trap();  // a lost arrival must fail loudly, never hang the GPU
+    if (++spins > (1u << 22)) __trap();  // a lost arrival must fail loudly, never hang the GPU
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
