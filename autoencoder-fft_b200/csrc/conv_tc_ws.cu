@@ -8,7 +8,10 @@
 // two accumulator buffers (2 x MB x N columns); all weights of all K stages stay resident in shared memory (this
 // variant is selected only when they fit).  Tiles are TI rows x TJ columns of one frame; an M-block is 128
 // consecutive linear pixels of the (TJ + NL - 1)-wide halo grid.
+#include <cstdlib>
+
 #include "common.cuh"
+#include "staging.cuh"
 #include "umma.cuh"
 
 namespace aefft {
@@ -34,6 +37,7 @@ struct ConvWsParams {
   long long n_tiles;
   int passes, kpack, TE;
   uint32_t tmem_cols;
+  int dbg;  // AEFFT_DEBUG_SKIP bitmask (profiling experiments only): 1 skip staging, 2 skip MMAs, 4 skip stores
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -93,37 +97,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc_ws_kernel(ConvWsParams 
         const int slot = stage & 1;
         mbar_wait(&empty[slot], ((stage >> 1) & 1) ^ 1);  // first use of each slot passes immediately
         unsigned char* A = Asm + (size_t)slot * a_stage;
-        for (int idx = ptid; idx < nkc * p.HP; idx += 32 * WS_PROD_WARPS) {
-          const int kchunk = idx / p.HP, h = idx - kchunk * p.HP;
-          const int r = h / p.PJ, col = h - r * p.PJ;
-          const int si = i0 + p.ai0 + r, sj = j0 + p.aj0 + col;
-          const bool inb = r < HI && si >= p.lo && si < p.Nx && sj >= p.lo && sj < p.Ny;
-          const int c0 = ks * WS_KC + kchunk * 8;
-          const long long pix = inb ? (long long)si * p.Ny + sj : 0;
-          float v[8], u[8];
-#pragma unroll
-          for (int e = 0; e < 8; e++) v[e] = __ldg(s0 + (long long)min(c0 + e, p.C - 1) * plane + pix);
-          if (s1) {
-#pragma unroll
-            for (int e = 0; e < 8; e++) u[e] = __ldg(s1 + (long long)min(c0 + e, p.C - 1) * plane + pix);
-#pragma unroll
-            for (int e = 0; e < 8; e++) v[e] -= u[e];
-          } else if (p.pre_div != 0.f) {
-            const float rinv = 1.f / p.pre_div;
-#pragma unroll
-            for (int e = 0; e < 8; e++) v[e] *= rinv;
-          }
-          __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-          for (int e = 0; e < 8; e++) {
-            if (!inb || c0 + e >= p.C) v[e] = 0.f;
-            split_bf16(v[e], hi[e], lo[e]);
-          }
-          *reinterpret_cast<uint4*>(A + (size_t)kchunk * a_plane + (size_t)h * 16) =
-              make_uint4(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]), pack2(hi[4], hi[5]), pack2(hi[6], hi[7]));
-          *reinterpret_cast<uint4*>(A + (size_t)(nkc + kchunk) * a_plane + (size_t)h * 16) =
-              make_uint4(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]), pack2(lo[4], lo[5]), pack2(lo[6], lo[7]));
-        }
+        if (!(p.dbg & 1))
+        stage_planes4<32 * WS_PROD_WARPS>(A, A + (size_t)nkc * a_plane, (uint32_t)a_plane, nkc, p.HP, p.PJ, s0, s1,
+                                          (!s1 && p.pre_div != 0.f) ? 1.f / p.pre_div : 1.f, ks * WS_KC, p.C - ks * WS_KC, plane,
+                                          p.Nx, p.Ny, i0 + p.ai0, j0 + p.aj0, HI, p.PJ, p.lo, ptid);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[slot]);
@@ -131,42 +108,50 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc_ws_kernel(ConvWsParams 
     }
   } else if (warp < WS_PROD_WARPS + WS_MMA_WARPS) {
     // ================================================================== MMA issuers
+    // Every lane runs the loops so that the descriptor arithmetic stays warp-uniform (uniform datapath, no per-thread
+    // register -> uniform-register moves in front of each UTCHMMA); only the tcgen05 instructions are predicated.
     const int mw = warp - WS_PROD_WARPS;
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
-      const uint32_t w_pass = (uint32_t)w_stage / 2, w_tap = 32u * p.N;
-      const uint32_t a_lbo = p.kpack ? 16u : (uint32_t)a_plane;
-      const int NLP = p.kpack ? (p.NL + 1) / 2 : p.NL, tstep = p.kpack ? 2 : 1;
-      uint32_t stage = 0, tcount = 0;
-      for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, tcount++) {
-        const int abuf = tcount & 1;
-        mbar_wait(&acc_empty[abuf], ((tcount >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
+    const bool leader = lane == 0;
+    const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
+    const uint32_t w_pass = (uint32_t)w_stage / 2, w_tap16 = 2u * p.N;  // 16-byte units
+    const uint32_t a_lbo = p.kpack ? 16u : (uint32_t)a_plane;
+    const int NLP = p.kpack ? (p.NL + 1) / 2 : p.NL, tstep = p.kpack ? 2 : 1;
+    uint32_t stage = 0, tcount = 0;
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, tcount++) {
+      const int abuf = tcount & 1;
+      mbar_wait(&acc_empty[abuf], ((tcount >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
+      fence_after_sync();
+      for (int ks = 0; ks < p.KS; ks++, stage++) {
+        const int slot = stage & 1;
+        mbar_wait(&full[slot], (stage >> 1) & 1);
         fence_after_sync();
-        for (int ks = 0; ks < p.KS; ks++, stage++) {
-          const int slot = stage & 1;
-          mbar_wait(&full[slot], (stage >> 1) & 1);
-          fence_after_sync();
-          const uint32_t A_addr = smem_u32(Asm + (size_t)slot * a_stage), W_addr = smem_u32(Wsm + (size_t)ks * w_stage);
-          const uint64_t a_hi0 = make_desc(A_addr, a_lbo, 128), a_lo0 = make_desc(A_addr + nkc * a_plane, a_lbo, 128);
-          const uint64_t b_hi0 = make_desc(W_addr, 16u * p.N, 128), b_lo0 = make_desc(W_addr + w_pass, 16u * p.N, 128);
+        const uint32_t A_addr = smem_u32(Asm + (size_t)slot * a_stage), W_addr = smem_u32(Wsm + (size_t)ks * w_stage);
+        const uint64_t a_hi0 = make_desc(A_addr, a_lbo, 128), a_lo0 = make_desc(A_addr + nkc * a_plane, a_lbo, 128);
+        const uint64_t b_hi0 = make_desc(W_addr, 16u * p.N, 128), b_lo0 = make_desc(W_addr + w_pass, 16u * p.N, 128);
+        if (!(p.dbg & 2)) {
           for (int mb = mw; mb < p.MB; mb += WS_MMA_WARPS) {
             const uint32_t d = tmem_base + (uint32_t)(abuf * acc_cols + mb * p.N);
             uint32_t t = 0;
             for (int tk = 0; tk < p.NK; tk++) {
               const uint32_t a_row = (uint32_t)(mb * 128 + tk * p.PJ);
               for (int tp = 0; tp < NLP; tp++, t++) {
-                const uint64_t a_add = (uint64_t)(a_row + tp * tstep), b_add = (uint64_t)(t * (w_tap >> 4));
-                mma_bf16(d, a_hi0 + a_add, b_hi0 + b_add, idesc, !(ks == 0 && t == 0));
-                if (p.passes == 3) {
-                  mma_bf16(d, a_hi0 + a_add, b_lo0 + b_add, idesc, true);
-                  mma_bf16(d, a_lo0 + a_add, b_hi0 + b_add, idesc, true);
+                const uint64_t a_add = (uint64_t)(a_row + tp * tstep), b_add = (uint64_t)(t * w_tap16);
+                if (leader) {
+                  mma_bf16(d, a_hi0 + a_add, b_hi0 + b_add, idesc, !(ks == 0 && t == 0));
+                  if (p.passes == 3) {
+                    mma_bf16(d, a_hi0 + a_add, b_lo0 + b_add, idesc, true);
+                    mma_bf16(d, a_lo0 + a_add, b_hi0 + b_add, idesc, true);
+                  }
                 }
               }
             }
           }
-          commit(&empty[slot]);                       // ring slot reusable once these MMAs have read it
+        }
+        if (leader) {
+          commit(&empty[slot]);                         // ring slot reusable once these MMAs have read it
           if (ks == p.KS - 1) commit(&acc_full[abuf]);  // accumulators of this tile complete
         }
+        __syncwarp();
       }
     }
   } else {
@@ -190,7 +175,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc_ws_kernel(ConvWsParams 
         for (int n0 = 0; n0 < p.N; n0 += 16) {
           float v[16];
           tmem_ld16(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(abuf * acc_cols + mb * p.N + n0), v);
-          if (valid) {
+          if (valid && !(p.dbg & 4)) {
 #pragma unroll
             for (int e = 0; e < 16; e++) {
               const int o = n0 + e;
@@ -255,6 +240,10 @@ int launch_conv_tc_ws(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O
   p.tiles_i = (Nx + p.TI - 1) / p.TI; p.tiles_j = (Ny + p.TJ - 1) / p.TJ;
   p.n_tiles = (long long)B * p.tiles_i * p.tiles_j;
   p.passes = passes; p.kpack = kpack; p.TE = TE;
+  {
+    const char* e = getenv("AEFFT_DEBUG_SKIP");
+    p.dbg = e ? atoi(e) : 0;
+  }
   p.tmem_cols = 32;
   while ((int)p.tmem_cols < 2 * p.MB * N) p.tmem_cols <<= 1;
   if (p.tmem_cols > 512) return AEFFT_ERR_UNSUPPORTED;

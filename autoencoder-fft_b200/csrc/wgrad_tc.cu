@@ -18,6 +18,7 @@
 // fp32 parity: bf16 hi/lo split of both operands, three products per step (BF16X3), fp32 accumulation.
 // Per-CTA partial sums go to global memory and are summed in fixed order by reduce_partials (deterministic).
 #include "common.cuh"
+#include "staging.cuh"
 #include "umma.cuh"
 
 namespace aefft {
@@ -129,15 +130,17 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradTcParams p
     const int i0 = (int)(tile % p.tiles_per_frame) * p.TI;
     const int rows_valid = min(p.TI, p.Nx - i0);
     // M-side on the output grid (zero in the pad columns and beyond the tile), N-side on its halo grid
-    stage_planes(Mhi, Mlo, p.m_plane, p.MPl, p.KQ, p.PJ, J.m0 + b * p.dM * plane, nullptr, 0, p.dM, plane, p.Nx, p.Ny, i0, 0,
-                 rows_valid, p.Ny);
-    stage_planes(Nhi, Nlo, p.n_plane, 1, p.HPn, p.PJ, J.n0 + b * p.dD * plane, J.n1 ? J.n1 + b * p.dD * plane : nullptr, J.nch0,
-                 nch, plane, p.Nx, p.Ny, i0 + J.oi, J.oj, 1 << 30, 1 << 30);
+    stage_planes4<WT_THREADS>(Mhi, Mlo, p.m_plane, p.MPl, p.KQ, p.PJ, J.m0 + b * p.dM * plane, nullptr, 1.f, 0, p.dM, plane,
+                              p.Nx, p.Ny, i0, 0, rows_valid, p.Ny, 0, tid);
+    stage_planes4<WT_THREADS>(Nhi, Nlo, p.n_plane, 1, p.HPn, p.PJ, J.n0 + b * p.dD * plane,
+                              J.n1 ? J.n1 + b * p.dD * plane : nullptr, 1.f, J.nch0, nch, plane, p.Nx, p.Ny, i0 + J.oi, J.oj,
+                              1 << 30, 1 << 30, 0, tid);
     fence_proxy_async();
     __syncthreads();
     // ---- NK issuing threads (lane 0 of warps 0..NK-1): warp tk owns window row tk and its accumulator ----
-    if (warp < p.NK && lane == 0) {
+    if (warp < p.NK) {  // all lanes run the loop (uniform descriptor arithmetic); lane 0 issues
       fence_after_sync();
+      const bool leader = lane == 0;
       const uint64_t m_hi0 = make_desc(smem_u32(Mhi), 128, p.m_plane), m_lo0 = make_desc(smem_u32(Mlo), 128, p.m_plane);
       const uint64_t n_hi0 = make_desc(smem_u32(Nhi), 128, 16), n_lo0 = make_desc(smem_u32(Nlo), 128, 16);
       const int ksteps = p.KQ / 16;
@@ -145,13 +148,16 @@ __global__ void __launch_bounds__(WT_THREADS, 2) wgrad_tc_kernel(WgradTcParams p
       const uint64_t shift = (uint64_t)(warp * p.PJ);
       for (int ks = 0; ks < ksteps; ks++) {
         const uint64_t q = (uint64_t)(ks * 16);
-        mma_bf16(d, m_hi0 + q, n_hi0 + q + shift, idesc, !(first && ks == 0));
-        if (p.passes == 3) {
-          mma_bf16(d, m_hi0 + q, n_lo0 + q + shift, idesc, true);
-          mma_bf16(d, m_lo0 + q, n_hi0 + q + shift, idesc, true);
+        if (leader) {
+          mma_bf16(d, m_hi0 + q, n_hi0 + q + shift, idesc, !(first && ks == 0));
+          if (p.passes == 3) {
+            mma_bf16(d, m_hi0 + q, n_lo0 + q + shift, idesc, true);
+            mma_bf16(d, m_lo0 + q, n_hi0 + q + shift, idesc, true);
+          }
         }
       }
-      commit(&bar);
+      if (leader) commit(&bar);
+      __syncwarp();
     }
     first = false;
     mbar_wait(&bar, phase);
