@@ -139,6 +139,25 @@ class Ctx:
         self.memcpy(buf.ptr, a.ctypes.data, a.nbytes, 0)
         return buf
 
+    def profile_enable(self, on: bool):
+        """Bracket every kernel launch of this ctx with a CUDA event pair (aefft_profile_enable)."""
+        _chk(lib().aefft_profile_enable(self.h, 1 if on else 0))
+
+    def profile_records(self, max_rows: int = 64):
+        """Synchronise, aggregate by kernel name and clear: [{name, ms, launches, flops, bytes}] (algorithmic work)."""
+        names = C.create_string_buffer(64 * max_rows)
+        kms = (C.c_float * max_rows)()
+        cnt = (C.c_int64 * max_rows)()
+        fl = (C.c_double * max_rows)()
+        by = (C.c_double * max_rows)()
+        nrows = C.c_int()
+        _chk(lib().aefft_profile_read(self.h, max_rows, names, kms, cnt, fl, by, C.byref(nrows)))
+        rows = []
+        for k in range(nrows.value):
+            nm = names.raw[64 * k: 64 * k + 64].split(b"\0")[0].decode()
+            rows.append(dict(name=nm, ms=float(kms[k]), launches=int(cnt[k]), flops=float(fl[k]), bytes=float(by[k])))
+        return rows
+
     @property
     def launches(self) -> int:
         return int(lib().aefft_launch_count(self.h))

@@ -164,9 +164,17 @@ int coord_gradients_dev(aefft_ctx* ctx, int mode, int quirks, int64_t B, int dD,
   bool done = false;
   if (ctx->precision != AEFFT_PRECISION_FP32) {
     // tensor-core path: GC and GF in one launch (adjacent in gbuf), bias sums / sum e^2 by a streaming reduction
-    const int rc = launch_wgrad_tc(ctx, wg, B, dD, dM, Nx, Ny, in, out, hin, dh, GC,
-                                   ctx->precision == AEFFT_PRECISION_BF16X3 ? 3 : 1);
+    const int passes = ctx->precision == AEFFT_PRECISION_BF16X3 ? 3 : 1;
+    // streaming TMEM-operand kernel: weight gradients, bias gradients and sum e^2 in one pass
+    int rc = launch_wgrad_ts(ctx, wg, B, dD, dM, Nx, Ny, in, out, hin, dh, GC, GB, GP, SQ, passes);
     if (rc == AEFFT_OK) {
+      done = true;
+    } else if (rc != AEFFT_ERR_UNSUPPORTED) {
+      return rc;
+    }
+    if (!done) rc = launch_wgrad_tc(ctx, wg, B, dD, dM, Nx, Ny, in, out, hin, dh, GC, passes);
+    if (done) {
+    } else if (rc == AEFFT_OK) {
       AE_TRY(launch_channel_sums(ctx, B, dM, Nx, Ny, dh, nullptr, GB, nullptr));
       AE_TRY(launch_channel_sums(ctx, B, dD, Nx, Ny, out, in, GP, SQ));
       done = true;

@@ -175,6 +175,11 @@ int launch_wgrad(aefft_ctx* ctx, const Window& win, int64_t B, int Nx, int Ny, c
 // GC = corr(dh, in), GF = corr(out-in, hin) with the forward window `win`.  AEFFT_ERR_UNSUPPORTED outside its envelope.
 int launch_wgrad_tc(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM, int Nx, int Ny, const float* in,
                     const float* out, const float* hin, const float* dh, float* G, int passes);
+// Streaming TMEM-operand variant (wgrad_ts.cu): GC | GF into G plus GB = sum dh, GP = sum (out-in), SQ = sum (out-in)^2
+// in the same pass.  AEFFT_ERR_UNSUPPORTED outside its envelope.
+int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM, int Nx, int Ny, const float* in,
+                    const float* out, const float* hin, const float* dh, float* G, float* GB, float* GP, float* SQ,
+                    int passes);
 // sum[c] = sum_{b,pix} (a0-a1)[b][c], *sumsq = sum (a0-a1)^2 (double accumulation, deterministic); a1/sum/sumsq optional
 int launch_channel_sums(aefft_ctx* ctx, int64_t B, int ch, int Nx, int Ny, const float* a0, const float* a1, float* sum,
                         float* sumsq);

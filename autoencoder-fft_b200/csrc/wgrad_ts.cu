@@ -1,0 +1,674 @@
+// Streaming weight-gradient kernel: both correlation gradients of a layer pair, the bias gradients and sum e^2 in ONE
+// pass over the activations, on tcgen05 with the A operand in TENSOR MEMORY.
+//
+//   GC[m][d][k][l] = sum_{b,q} dh[b][m](q)  * in[b][d](q + s_t)               (U = dh,  S = in,        window origin ( ai0,  aj0))
+//   GF[d][m][k][l] = sum_{b,q} hin[b][m](q) * (out-in)[b][d](q - s_t)         (U = hin, S = out - in,  mirrored window)
+//   GB[m] = sum dh[m],  GP[d] = sum (out-in)[d],  SQ = sum (out-in)^2
+//
+// Why this shape.  With both operands in shared memory the M=64/128 x N=40 MMAs of wgrad_tc.cu are bound by the
+// 128 B/clk shared-memory operand bandwidth (A = 2-4 KB per MMA against 20 cycles of math) and most of the M x N tile
+// is padding.  Here:
+//   * A (TMEM) = the UNSHIFTED operand U, 128 lanes = dM channels x RS row-replicas: lane (rho, m) holds U[m] delayed by
+//     rho image rows, so one MMA covers RS window rows at once and every TMEM lane is useful (RS = 128 / dM).  TMEM
+//     operands cost no shared-memory bandwidth; the replicas are free because the converter warps write TMEM themselves
+//     (tcgen05.st) from an fp32 row ring.
+//   * B (smem) = one 8-channel bf16 plane of the SHIFTED operand S in the SWIZZLE_NONE MN-major layout [pixel][8 ch]:
+//     consecutive 8-column groups of N are the plane advanced by one pixel (SBO = 16 B), so N = 48 covers a window row
+//     (NL <= 6 taps) and a window-row offset is a different ring slot.  1.5 KB per MMA: the MMA is math bound.
+//   * K = 16 consecutive pixels of one image row of the strip (pitch PJ = 64 or 128 incl. the NL-1 halo columns); rows
+//     STREAM through rings (TMA -> fp32 rows -> converters -> TMEM / bf16 planes), so the halo is paid once per band.
+//   * fp32 parity: bf16 hi/lo split of both operands, products hi*hi + hi*lo + lo*hi (BF16X3), fp32 TMEM accumulators
+//     kept for ALL items of a CTA; per-CTA partials are reduced in fixed order (deterministic).
+// Roles (512 threads): warp 0 TMA producer, warps 2-3 S converters (+ sum e, e^2), warps 4-11 U converters (+ sum U),
+// warps 12-15 MMA issuers, warps 4-7 epilogue.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "common.cuh"
+#include "tma.cuh"
+#include "umma.cuh"
+
+namespace aefft {
+
+using namespace umma;
+using namespace tma;
+
+constexpr int TS_THREADS = 512;
+constexpr int TS_NI = 4;      // MMA issuer warps
+constexpr int TS_CHUNK = 64;  // pixels per TMEM A chunk = 4 MMA K-steps
+constexpr int TS_MAX_JOBS = 8;
+constexpr int TS_NSF = 2;     // fp32 S staging slots
+constexpr int TS_MAXRING = 24;
+
+struct TsJob {
+  CUtensorMap u_map;   // U [B*dM][Nx][Ny], box {32, 1, dM}, 128-byte swizzle
+  CUtensorMap s0_map;  // S source 0 [B*dD][Nx][Ny], box {PJ+4, 1, nch}
+  CUtensorMap s1_map;  // GF: S = s0 - s1
+  int has_s1;
+  int ch0, nch;        // S channels [ch0, ch0+nch) of this job
+  int oi, oj;          // S grid origin relative to the item origin
+  int rev, is_gf, want_usum;
+  long long g_off;
+};
+
+struct WgradTsParams {
+  TsJob job[TS_MAX_JOBS];
+  int n_jobs, cpj;
+  float* part;  // [cpj][n_tot]
+  long long n_tot, n_main;
+  int dM, dD, Nx, Ny, NK, NL;
+  int PJ, TJ, CPR, RS, NR, np, Ncol, Acol0, NA, NU, NSB;
+  int strips, bands, BR;
+  long long items;
+  int passes, flip, by_chunk;
+  uint32_t u_slot_bytes, s_slot_bytes, s_src_bytes, sb_pitch;
+  uint32_t off_u, off_s, off_sb;
+  long long* dbg;  // AEFFT_TS_DEBUG: [cta][warp][4] cycles (wait A, wait B, total, -)
+};
+
+__device__ __forceinline__ uint32_t cvt_pack_bf16(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+// (a, b) -> packed hi parts and packed lo parts (x ~= hi + lo)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_pack_bf16(a, b);
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+  lo = cvt_pack_bf16(ra, rb);
+}
+
+// one lane of a converged warp (warp-uniform predicate)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// position in a ring of n barrier-guarded slots: slot index + phase parity of the current lap
+struct Ring {
+  int slot = 0, n;
+  uint32_t phase = 0;
+  __device__ __forceinline__ explicit Ring(int n_) : n(n_) {}
+  __device__ __forceinline__ void next() {
+    if (++slot == n) { slot = 0; phase ^= 1; }
+  }
+  __device__ __forceinline__ void skip(int k) {
+    slot += k;
+    while (slot >= n) { slot -= n; phase ^= 1; }
+  }
+};
+
+__device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
+__global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_constant__ WgradTsParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t u_full[TS_MAXRING], u_empty[TS_MAXRING], s_full[TS_NSF], s_empty[TS_NSF],
+      sb_full[TS_MAXRING], sb_empty[TS_MAXRING], a_full[8], a_empty[8], done_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ double usum[128], esum[16], esq;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int jb = blockIdx.y, cta = blockIdx.x;
+  const TsJob& J = p.job[jb];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* u_ring = smem + p.off_u;
+  unsigned char* s_ring = smem + p.off_s;
+  unsigned char* sb_ring = smem + p.off_sb;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 32) {
+    for (int i = 0; i < p.NU; i++) { mbar_init(&u_full[i], 1); mbar_init(&u_empty[i], 8); }
+    for (int i = 0; i < TS_NSF; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 2); }
+    for (int i = 0; i < p.NSB; i++) { mbar_init(&sb_full[i], 2); mbar_init(&sb_empty[i], TS_NI); }
+    for (int i = 0; i < p.NA; i++) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], p.by_chunk ? 1 : TS_NI); }
+    mbar_init(&done_bar, TS_NI);
+    fence_mbar_init();
+  }
+  if (tid < 128) usum[tid] = 0.0;
+  if (tid < 16) esum[tid] = 0.0;
+  if (tid == 0) esq = 0.0;
+  // zero the bf16 S ring once: the 8 pad pixels behind every row slot are read (times zero A lanes) and must be finite
+  {
+    const uint32_t n16 = (uint32_t)(2 * p.np * p.NSB) * p.sb_pitch / 16;
+    uint4* z = reinterpret_cast<uint4*>(sb_ring);
+    for (uint32_t i = tid; i < n16; i += TS_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tmem_slot;
+  if (warp >= 4 && warp < 8) {
+    // accumulators start at zero: every MMA accumulates (the issue order across issuer warps is not fixed)
+    uint32_t z[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) z[e] = 0u;
+    for (int c0 = 0; c0 < p.Acol0; c0 += 16) tmem_st16(tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, z);
+    tmem_wait_st();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  long long wA = 0, wB = 0, wC = 0;
+  const long long t_start = clock64();
+
+  const int items_per_frame = p.strips * p.bands;
+  const int Rmax = (p.NR - 1) * p.RS;
+  const int CU = p.dM;
+  const int n_items = (int)p.items, cpj = p.cpj;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&J.u_map);
+      tma_prefetch_desc(&J.s0_map);
+      if (J.has_s1) tma_prefetch_desc(&J.s1_map);
+      const int cs_off = J.oj & ~3;  // aligned start column offset (the hardware needs 16-byte aligned inner coordinates)
+      const uint32_t s_bytes = (uint32_t)(J.has_s1 ? 2 : 1) * J.nch * (p.PJ + 4) * 4;
+      Ring su(p.NU), ss(TS_NSF);
+      for (int item = cta; item < n_items; item += cpj) {
+        const int b = item / items_per_frame;
+        const int rem = item - b * items_per_frame;
+        const int strip = rem / p.bands;
+        const int j0 = strip * p.TJ, i0 = (rem - strip * p.bands) * p.BR;
+        const int nrows = min(p.BR, p.Nx - i0);
+        const int n_srows = nrows + p.RS - 1 + Rmax;
+        for (int k = 0; k < n_srows; k++) {
+          {
+            wait_t(&s_empty[ss.slot], ss.phase ^ 1, wA);
+            unsigned char* dst = s_ring + (size_t)ss.slot * p.s_slot_bytes;
+            mbar_expect_tx(&s_full[ss.slot], s_bytes);
+            tma_load_3d(dst, &J.s0_map, j0 + cs_off, i0 + J.oi + k, b * p.dD + J.ch0, &s_full[ss.slot]);
+            if (J.has_s1)
+              tma_load_3d(dst + p.s_src_bytes, &J.s1_map, j0 + cs_off, i0 + J.oi + k, b * p.dD + J.ch0, &s_full[ss.slot]);
+            ss.next();
+          }
+          const int ru = k - Rmax;
+          if (ru >= 0 && ru < nrows) {
+            wait_t(&u_empty[su.slot], su.phase ^ 1, wB);
+            unsigned char* dst = u_ring + (size_t)su.slot * p.u_slot_bytes;
+            mbar_expect_tx(&u_full[su.slot], p.u_slot_bytes);
+            for (int sub = 0; sub < p.PJ / 32; sub++)
+              tma_load_3d(dst + (size_t)sub * CU * 128, &J.u_map, j0 + sub * 32, i0 + ru, b * CU, &u_full[su.slot]);
+            su.next();
+          }
+        }
+      }
+    }
+  } else if (warp >= 12) {
+    // ============================================================ MMA issuers (TS_NI warps).  Each warp runs the
+    // (compact, not unrolled) loops with warp-uniform operands; one elected lane issues.  A single issuing thread
+    // sustains only ~1 MMA group per 200 cycles (descriptor arithmetic + R2UR latency), so the work is split:
+    //   by_chunk (one window-row group, NR == 1): issuer q owns the A chunks cc = q (mod TS_NI) and its OWN copy of the
+    //             accumulators (summed in fixed order by the epilogue);
+    //   by_acc   : issuer q owns the accumulators a = q (mod TS_NI) for every chunk.
+    // Either way each accumulator (copy) receives its MMAs from one thread in program order: results are deterministic.
+    const int q = warp - 12;
+    const uint32_t idesc = make_idesc_bf16(128, p.Ncol, 0, 1);
+    const uint32_t sb_base16 = smem_u32(sb_ring) >> 4, pitch16 = p.sb_pitch >> 4;
+    const uint32_t lo_off16 = (uint32_t)(p.np * p.NSB) * pitch16;
+    const uint64_t desc_const = make_desc(0, 128, 16);
+    const int NR = p.NR, NSB = p.NSB, np = p.np, RS = p.RS, CPR = p.CPR;
+    const int nacc = NR * np;
+    const uint32_t Ncol = (uint32_t)p.Ncol;
+    const bool three = p.passes == 3, by_chunk = p.by_chunk != 0;
+    const uint32_t d_base = tb + (by_chunk ? (uint32_t)(q * nacc) * Ncol : 0u);
+    Ring ra(p.NA);         // TMEM A chunk ring (advanced for every chunk, owned or not)
+    Ring rw(NSB);          // ring position of S row `sb_row` of the current item
+    int sb_row = 0;        // next S row of the current item this warp has not waited for
+    int s0slot = 0;        // ring slot of the S row of the current K-row (window row offset 0)
+    int cc4 = 0;           // chunk counter mod TS_NI
+    for (int item = cta; item < n_items; item += cpj) {
+      const int rem = item % items_per_frame;
+      const int i0 = (rem % p.bands) * p.BR;
+      const int nrows = min(p.BR, p.Nx - i0);
+      const int n_krows = nrows + RS - 1, n_srows = n_krows + Rmax;
+      for (int r = 0; r < n_krows; r++) {
+        // S rows [r, r+Rmax].  EVERY issuer waits for EVERY row in order and commits every row's release (count TS_NI),
+        // also for K-rows whose chunks belong to other issuers: a parity wait is only sound for a waiter that is neither
+        // ahead of the previous phase nor lapped, which in-order waiting + all-issuer release guarantee.
+        for (; sb_row < r + Rmax + 1; sb_row++) {
+          wait_t(&sb_full[rw.slot], rw.phase, wA);
+          rw.next();
+        }
+        for (int h = 0; h < CPR; h++, cc4 = (cc4 + 1) & (TS_NI - 1)) {
+          const bool mine = !by_chunk || cc4 == q;
+          if (mine) {
+            wait_t(&a_full[ra.slot], ra.phase, wB);
+            fence_after_sync();
+            const long long t_m0 = clock64();
+            const uint32_t a_base = tb + (uint32_t)(p.Acol0 + ra.slot * 64);
+#pragma unroll 1
+            for (int ks = 0; ks < 4; ks++) {
+              const uint32_t a_hi = a_base + ks * 8, a_lo = a_hi + 32;
+              const uint32_t px16 = (uint32_t)(h * TS_CHUNK + ks * 16);
+              uint32_t d = d_base;
+              int slot = s0slot, a = 0;
+#pragma unroll 1
+              for (int Ri = 0; Ri < NR; Ri++) {
+#pragma unroll 1
+                for (int pl = 0; pl < np; pl++, d += Ncol, a++) {
+                  if (by_chunk || (a & (TS_NI - 1)) == q) {
+                    const uint32_t lo32 = sb_base16 + (uint32_t)(pl * NSB + slot) * pitch16 + px16;
+                    const uint64_t b_hi = desc_const + (uint64_t)lo32, b_lo = b_hi + (uint64_t)lo_off16;
+                    if (elect_one()) {
+                      mma_bf16_ts(d, a_hi, b_hi, idesc, true);
+                      if (three) {
+                        mma_bf16_ts(d, a_hi, b_lo, idesc, true);
+                        mma_bf16_ts(d, a_lo, b_hi, idesc, true);
+                      }
+                    }
+                  }
+                }
+                slot += RS;
+                if (slot >= NSB) slot -= NSB;
+              }
+            }
+            wC += clock64() - t_m0;
+            if (elect_one()) commit(&a_empty[ra.slot]);
+          }
+          ra.next();
+        }
+        if (elect_one()) commit(&sb_empty[s0slot]);
+        if (++s0slot == NSB) s0slot = 0;
+      }
+      // S rows that were only ever read at a window-row offset (by_acc only: Rmax == 0 in by_chunk mode)
+      for (int k = n_krows; k < n_srows; k++) {
+        for (; sb_row < k + 1; sb_row++) {
+          wait_t(&sb_full[rw.slot], rw.phase, wA);
+          rw.next();
+        }
+        if (elect_one()) commit(&sb_empty[s0slot]);
+        if (++s0slot == NSB) s0slot = 0;
+      }
+      sb_row = 0;
+    }
+    if (elect_one()) commit(&done_bar);
+  } else if (warp == 1) {
+    // spare warp
+  } else if (warp < 4) {
+    // ============================================================ S converters (64 threads)
+    const int t = tid - 64;
+    const int d_off = J.oj - (J.oj & ~3);  // sub-offset of the halo origin inside the aligned box
+    const int SP = p.PJ + 4;
+    Ring ss(TS_NSF), sb(p.NSB);
+    float fs[16], fq = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; e++) fs[e] = 0.f;
+    for (int item = cta; item < n_items; item += cpj) {
+      const int rem = item % items_per_frame;
+      const int i0 = (rem % p.bands) * p.BR;
+      const int nrows = min(p.BR, p.Nx - i0);
+      const int n_srows = nrows + p.RS - 1 + Rmax;
+      for (int k = 0; k < n_srows; k++) {
+        wait_t(&s_full[ss.slot], ss.phase, wA);
+        wait_t(&sb_empty[sb.slot], sb.phase ^ 1, wB);
+        const float* s0 = reinterpret_cast<const float*>(s_ring + (size_t)ss.slot * p.s_slot_bytes);
+        const float* s1 = reinterpret_cast<const float*>(s_ring + (size_t)ss.slot * p.s_slot_bytes + p.s_src_bytes);
+        const bool own_row = J.is_gf && (k + J.oi >= 0) && (k + J.oi < nrows);
+        int pl = 0, px = t;
+        for (int idx = t; idx < p.np * p.PJ; idx += 64, px += 64) {
+          if (px >= p.PJ) { px -= p.PJ; pl++; }
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            const int ch = pl * 8 + e;
+            float x = 0.f;
+            if (ch < J.nch) {
+              x = s0[ch * SP + px + d_off];
+              if (J.has_s1) x -= s1[ch * SP + px + d_off];
+            }
+            v[e] = x;
+          }
+          if (own_row && px + J.oj >= 0 && px + J.oj < p.TJ) {
+            if (pl == 0) {
+#pragma unroll
+              for (int e = 0; e < 8; e++) { fs[e] += v[e]; fq = fmaf(v[e], v[e], fq); }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; e++) { fs[8 + e] += v[e]; fq = fmaf(v[e], v[e], fq); }
+            }
+          }
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+          unsigned char* dst = sb_ring + ((size_t)(pl * p.NSB) + sb.slot) * p.sb_pitch + (size_t)px * 16;
+          *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(dst + (size_t)(p.np * p.NSB) * p.sb_pitch) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&sb_full[sb.slot]);
+          mbar_arrive(&s_empty[ss.slot]);
+        }
+        ss.next();
+        sb.next();
+      }
+      if (J.is_gf) {
+        // per-item flush of the fp32 running sums into double accumulators (few hundred values per thread and item)
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          if (fs[e] != 0.f) atomicAdd(&esum[e], (double)fs[e]);
+          fs[e] = 0.f;
+        }
+        if (fq != 0.f) atomicAdd(&esq, (double)fq);
+        fq = 0.f;
+      }
+    }
+  } else {
+    // ============================================================ U converters (8 warps): fp32 rows -> TMEM A chunks
+    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    const int L = quarter * 32 + lane;
+    const int rho = L / CU, m = L - rho * CU;
+    const int rho_lo = (quarter * 32) / CU, rho_hi = (quarter * 32 + 31) / CU;
+    const bool sum_lane = J.want_usum && rho == 0;
+    const uint32_t t_lane = tb + ((uint32_t)(quarter * 32) << 16) + (uint32_t)p.Acol0;
+    const int NU = p.NU, NA = p.NA;
+    int base_slot = 0;             // ring slot of U row 0 of the current item
+    int w_row = 0;                 // running index (over all items) of the next U row this warp has not waited for
+    Ring rw(NU);                   // ring position of w_row
+    int row_base = 0;              // running index of U row 0 of the current item
+    int ca = half, ca_phase = 0;   // this warp's chunks are cc = half, half+2, ...: A ring slot / phase of chunk cc
+    if (ca >= NA) { ca -= NA; ca_phase ^= 1; }
+    int parity = 0;                // (chunk index & 1) of the next chunk in program order
+    int rel_row = 0, rel_slot = 0; // next U row of the current item this warp has not released yet / its ring slot
+    double dsum = 0.0;
+    for (int item = cta; item < n_items; item += cpj) {
+      const int rem = item % items_per_frame;
+      const int i0 = (rem % p.bands) * p.BR;
+      const int nrows = min(p.BR, p.Nx - i0);
+      const int n_krows = nrows + p.RS - 1;
+      for (int r = 0; r < n_krows; r++) {
+        for (int h = 0; h < p.CPR; h++, parity ^= 1) {
+          if (parity != half) continue;
+          // rows this warp will never read again (its chunks run in order): release them to the producer
+          for (; rel_row <= r - p.RS && rel_row < nrows; rel_row++) {
+            if (lane == 0) mbar_arrive(&u_empty[rel_slot]);
+            if (++rel_slot == NU) rel_slot = 0;
+          }
+          // U rows this warp reads now: r - rho for rho in [rho_lo, rho_hi], clipped to the band
+          {
+            const int newest = min(r - rho_lo, nrows - 1), oldest = max(r - rho_hi, 0);
+            if (newest >= oldest) {
+              int g = row_base + oldest;
+              if (g > w_row) { rw.skip(g - w_row); w_row = g; }
+              for (; w_row <= row_base + newest; w_row++) {
+                wait_t(&u_full[rw.slot], rw.phase, wA);
+                rw.next();
+              }
+            }
+          }
+          wait_t(&a_empty[ca], (uint32_t)ca_phase ^ 1, wB);
+          fence_after_sync();
+          const int ru = r - rho;
+          const bool valid = ru >= 0 && ru < nrows;
+          int uslot = base_slot + (valid ? ru : 0);
+          uslot %= NU;
+          const unsigned char* urow = u_ring + (size_t)uslot * p.u_slot_bytes;
+          float fsum = 0.f;
+#pragma unroll
+          for (int hh = 0; hh < 2; hh++) {
+            const int sub = h * 2 + hh, px0 = sub * 32;
+            const unsigned char* src = urow + (size_t)sub * CU * 128 + (size_t)m * 128;
+            float v[32];
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+              float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (valid && px0 + 4 * g < p.TJ) q = *reinterpret_cast<const float4*>(src + ((g ^ (m & 7)) << 4));
+              v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
+            }
+            if (sum_lane) {
+#pragma unroll
+              for (int e = 0; e < 32; e++) fsum += v[e];
+            }
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int e = 0; e < 16; e++) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+            tmem_st16(t_lane + (uint32_t)(ca * 64 + hh * 16), hi);
+            tmem_st16(t_lane + (uint32_t)(ca * 64 + 32 + hh * 16), lo);
+          }
+          if (sum_lane) dsum += (double)fsum;
+          tmem_wait_st();
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[ca]);
+          ca += 2;
+          if (ca >= NA) { ca -= NA; ca_phase ^= 1; }
+        }
+      }
+      for (; rel_row < nrows; rel_row++) {
+        if (lane == 0) mbar_arrive(&u_empty[rel_slot]);
+        if (++rel_slot == NU) rel_slot = 0;
+      }
+      rel_row = 0;
+      row_base += nrows;
+      base_slot = (base_slot + nrows) % NU;
+    }
+    if (sum_lane) atomicAdd(&usum[m], dsum);
+    // ============================================================ epilogue (warps 4-7)
+    if (half == 0) {
+      mbar_wait(&done_bar, 0);
+      fence_after_sync();
+      const bool had_items = cta < n_items;
+      float* part = p.part + (long long)cta * p.n_tot + J.g_off;
+      const int TT = p.NK * p.NL;
+      for (int acc = 0; acc < p.NR * p.np; acc++) {
+        const int Ri = acc / p.np, pl = acc - Ri * p.np;
+        const int tk0 = Ri * p.RS + rho;
+        for (int c0 = 0; c0 < p.Ncol; c0 += 16) {
+          float v[16];
+          tmem_ld16(tb + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.Ncol + c0), v);
+          if (p.by_chunk) {
+            for (int cp = 1; cp < TS_NI; cp++) {  // issuer copies, fixed order
+              float w[16];
+              tmem_ld16(tb + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((cp * p.NR * p.np + acc) * p.Ncol + c0), w);
+#pragma unroll
+              for (int e = 0; e < 16; e++) v[e] += w[e];
+            }
+          }
+          if (tk0 < p.NK) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) {
+              const int col = c0 + e, s = col >> 3, x = col & 7;
+              const int ch = pl * 8 + x;
+              if (s < p.NL && ch < J.nch) {
+                int tk = tk0, tl = s;
+                if (J.rev) { tk = p.NK - 1 - tk; tl = p.NL - 1 - tl; }
+                const int k = p.flip ? p.NK - 1 - tk : tk, l = p.flip ? p.NL - 1 - tl : tl;
+                const int d = J.ch0 + ch;
+                const long long gi = J.is_gf ? (((long long)d * p.dM + m) * TT + k * p.NL + l)
+                                             : (((long long)m * p.dD + d) * TT + k * p.NL + l);
+                part[gi] = had_items ? v[e] : 0.f;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (p.dbg && lane == 0) {
+    long long* d = p.dbg + ((long long)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + warp) * 4;
+    d[0] = wA; d[1] = wB; d[2] = clock64() - t_start; d[3] = wC;
+  }
+  fence_before_sync();
+  __syncthreads();
+  // bias-gradient sums and sum e^2 of this CTA
+  {
+    float* prow = p.part + (long long)cta * p.n_tot;
+    const long long nC2 = 2LL * p.dM * p.dD * p.NK * p.NL;
+    if (J.want_usum && tid < CU) prow[nC2 + tid] = (float)usum[tid];
+    if (J.is_gf && tid < J.nch) prow[nC2 + p.dM + J.ch0 + tid] = (float)esum[tid];
+    if (tid == 0) prow[p.n_main + jb] = J.is_gf ? (float)esq : 0.f;
+  }
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+// out[0 .. n_main) = sum over CTAs of the partial blocks; *sq = sum over CTAs and jobs of the per-job sum e^2 slots
+__global__ void wgrad_ts_reduce_kernel(const float* __restrict__ part, int n_parts, long long n_tot, long long n_main,
+                                       int n_jobs, long long nC2, int dM, int dD, float* __restrict__ G, float* __restrict__ GB,
+                                       float* __restrict__ GP, float* __restrict__ SQ) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx > n_main) return;
+  double s = 0.0;
+  if (idx < n_main) {
+    for (int c = 0; c < n_parts; c++) s += (double)part[(long long)c * n_tot + idx];
+    if (idx < nC2) G[idx] = (float)s;
+    else if (idx < nC2 + dM) GB[idx - nC2] = (float)s;
+    else GP[idx - nC2 - dM] = (float)s;
+  } else {
+    for (int c = 0; c < n_parts; c++)
+      for (int j = 0; j < n_jobs; j++) s += (double)part[(long long)c * n_tot + n_main + j];
+    if (SQ) *SQ = (float)s;
+  }
+}
+
+// GC | GF (raw sums over the B frames) into G, GB[dM], GP[dD], SQ[1].  AEFFT_ERR_UNSUPPORTED outside the envelope
+// (the caller then uses wgrad_tc / the fp32 kernels + channel sums).
+int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM, int Nx, int Ny, const float* in,
+                    const float* out, const float* hin, const float* dh, float* G, float* GB, float* GP, float* SQ,
+                    int passes) {
+  if (getenv("AEFFT_NO_WGRAD_TS")) return AEFFT_ERR_UNSUPPORTED;
+  if (win.lo != 0 || win.Nl > 6 || win.Nk > 16 || Ny % 4 != 0 || dM < 8 || dM > 128 || (128 % dM) != 0 || dD < 1)
+    return AEFFT_ERR_UNSUPPORTED;
+  if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)hin | (uintptr_t)dh) & 15) != 0) return AEFFT_ERR_UNSUPPORTED;
+  if (B * (int64_t)dM > 0x7fffffffLL || B * (int64_t)dD > 0x7fffffffLL) return AEFFT_ERR_UNSUPPORTED;
+  WgradTsParams p;
+  p.dM = dM; p.dD = dD; p.Nx = Nx; p.Ny = Ny; p.NK = win.Nk; p.NL = win.Nl;
+  p.passes = passes; p.flip = win.flip;
+  p.RS = 128 / dM;
+  p.NR = (win.Nk + p.RS - 1) / p.RS;
+  p.Ncol = 48;
+  p.np = dD > 8 ? 2 : 1;
+  while (p.np > 1 && p.NR * p.np * p.Ncol > 512 - 2 * 64) p.np--;
+  if (p.NR * p.np * p.Ncol > 512 - 2 * 64) return AEFFT_ERR_UNSUPPORTED;
+  const int jobs_per_grad = (dD + 8 * p.np - 1) / (8 * p.np);
+  p.n_jobs = 2 * jobs_per_grad;
+  if (p.n_jobs > TS_MAX_JOBS) return AEFFT_ERR_UNSUPPORTED;
+  // strip geometry: pitch 64 when one 64-wide strip covers the row, else 128
+  const int halo = win.Nl - 1;
+  p.PJ = (Ny + halo <= 64) ? 64 : 128;
+  p.TJ = (p.PJ - halo) & ~3;
+  p.CPR = p.PJ / TS_CHUNK;
+  p.strips = (Ny + p.TJ - 1) / p.TJ;
+  const int Rmax = (p.NR - 1) * p.RS;
+  p.by_chunk = (p.NR == 1 && TS_NI * p.np * p.Ncol + 2 * 64 <= 512) ? 1 : 0;
+  p.Acol0 = (p.by_chunk ? TS_NI : 1) * p.NR * p.np * p.Ncol;
+  p.NA = (512 - p.Acol0) / 64;
+  if (p.NA > 4) p.NA = 4;
+  p.NSB = Rmax + 3;
+  p.sb_pitch = (uint32_t)(p.PJ + 8) * 16;
+  p.u_slot_bytes = (uint32_t)dM * p.PJ * 4;
+  p.s_src_bytes = (uint32_t)(8 * p.np) * (p.PJ + 4) * 4;
+  p.s_src_bytes = (p.s_src_bytes + 127) & ~127u;
+  p.s_slot_bytes = 2 * p.s_src_bytes;
+  const size_t sb_bytes = (size_t)2 * p.np * p.NSB * p.sb_pitch;
+  const size_t s_bytes = (size_t)TS_NSF * p.s_slot_bytes;
+  const size_t budget = 225 * 1024 - 1024;
+  p.NU = p.RS + 3;
+  while (p.NU > p.RS + 1 && (size_t)p.NU * p.u_slot_bytes + s_bytes + sb_bytes + 2048 > budget) p.NU--;
+  if ((size_t)p.NU * p.u_slot_bytes + s_bytes + sb_bytes + 2048 > budget || p.NU > TS_MAXRING || p.NSB > TS_MAXRING)
+    return AEFFT_ERR_UNSUPPORTED;
+  p.off_u = 0;
+  p.off_s = (uint32_t)(((size_t)p.NU * p.u_slot_bytes + 1023) & ~(size_t)1023);
+  p.off_sb = (uint32_t)((p.off_s + s_bytes + 1023) & ~(size_t)1023);
+  const size_t smem = p.off_sb + sb_bytes + 1024;
+  // work split: cpj CTAs per job, every frame cut into `bands` row bands; minimise rounds x rows per band
+  int cpj = ctx->sm_count / p.n_jobs;
+  if (cpj < 1) cpj = 1;
+  {
+    const int over = p.RS - 1 + Rmax;
+    long long best = -1;
+    int best_bands = 1;
+    for (int bands = 1; bands <= 32 && bands <= Nx; bands++) {
+      const int BR = (Nx + bands - 1) / bands;
+      const int nb = (Nx + BR - 1) / BR;
+      const long long items = (long long)B * p.strips * nb;
+      const long long rounds = (items + cpj - 1) / cpj;
+      const long long cost = rounds * (BR + over);
+      if (best < 0 || cost < best) { best = cost; best_bands = nb; p.BR = BR; }
+    }
+    p.bands = best_bands;
+    p.BR = (Nx + p.bands - 1) / p.bands;
+    p.bands = (Nx + p.BR - 1) / p.BR;
+  }
+  p.items = (long long)B * p.strips * p.bands;
+  if (p.items < cpj) cpj = (int)p.items;
+  p.cpj = cpj;
+  const int T = win.Nk * win.Nl;
+  const long long nC = (long long)dM * dD * T;
+  p.n_main = 2 * nC + dM + dD;
+  p.n_tot = p.n_main + p.n_jobs;
+  float* part;
+  AE_TRY(ctx->getT("wgts_part", (size_t)cpj * p.n_tot, &part));
+  p.part = part;
+  for (int c = 0; c < jobs_per_grad; c++) {
+    const int ch0 = c * 8 * p.np, nch = (dD - ch0 < 8 * p.np) ? dD - ch0 : 8 * p.np;
+    TsJob& gc = p.job[c];
+    TsJob& gf = p.job[jobs_per_grad + c];
+    gc.has_s1 = 0; gc.ch0 = ch0; gc.nch = nch; gc.oi = win.ai0; gc.oj = win.aj0; gc.rev = 0; gc.is_gf = 0;
+    gc.want_usum = (c == 0); gc.g_off = 0;
+    gf.has_s1 = 1; gf.ch0 = ch0; gf.nch = nch;
+    gf.oi = -(win.ai0 + win.Nk - 1); gf.oj = -(win.aj0 + win.Nl - 1); gf.rev = 1; gf.is_gf = 1; gf.want_usum = 0; gf.g_off = nC;
+    int rc = make_tmap_3d_f32(&gc.u_map, dh, Ny, Nx, (uint64_t)B * dM, 32, 1, dM, true);
+    rc |= make_tmap_3d_f32(&gf.u_map, hin, Ny, Nx, (uint64_t)B * dM, 32, 1, dM, true);
+    rc |= make_tmap_3d_f32(&gc.s0_map, in, Ny, Nx, (uint64_t)B * dD, p.PJ + 4, 1, nch);
+    gc.s1_map = gc.s0_map;
+    rc |= make_tmap_3d_f32(&gf.s0_map, out, Ny, Nx, (uint64_t)B * dD, p.PJ + 4, 1, nch);
+    rc |= make_tmap_3d_f32(&gf.s1_map, in, Ny, Nx, (uint64_t)B * dD, p.PJ + 4, 1, nch);
+    if (rc != 0) return AEFFT_ERR_UNSUPPORTED;
+  }
+  const bool debug = getenv("AEFFT_TS_DEBUG") != nullptr;
+  p.dbg = nullptr;
+  const size_t n_dbg = (size_t)cpj * p.n_jobs * 16 * 4;
+  if (debug) {
+    AE_TRY(ctx->getT("wgts_dbg", n_dbg, &p.dbg));
+    AE_CUDA(cudaMemsetAsync(p.dbg, 0, n_dbg * sizeof(long long), ctx->stream));
+  }
+  static size_t attr = 0;
+  if (smem > attr) {
+    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  {
+    const double px = (double)B * Nx * Ny;
+    ProfScope prof(ctx, "wgrad_ts", 2.0 * 2.0 * px * dM * dD * T, 4.0 * px * (3.0 * dD + 2.0 * dM));
+    wgrad_ts_kernel<<<dim3(cpj, p.n_jobs), TS_THREADS, smem, ctx->stream>>>(p);
+  }
+  wgrad_ts_reduce_kernel<<<(unsigned)((p.n_main + 1 + 255) / 256), 256, 0, ctx->stream>>>(part, cpj, p.n_tot, p.n_main, p.n_jobs,
+                                                                                          2 * nC, dM, dD, G, GB, GP, SQ);
+  ctx->launches += 2;
+  AE_CUDA(cudaGetLastError());
+  if (debug) {
+    // development aid: average cycles each role spent waiting on its two barrier classes
+    std::vector<long long> h(n_dbg);
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
+    AE_CUDA(cudaMemcpy(h.data(), p.dbg, n_dbg * sizeof(long long), cudaMemcpyDeviceToHost));
+    const char* role[4] = {"producer (s_empty, u_empty)", "issuer   (sb_full, a_full)", "S conv   (s_full, sb_empty)",
+                           "U conv   (u_full, a_empty)"};
+    double acc[4][4] = {};
+    int cnt[4] = {};
+    for (int c = 0; c < cpj * p.n_jobs; c++)
+      for (int w = 0; w < 16; w++) {
+        if (w == 1) continue;
+        const int r = w == 0 ? 0 : w >= 12 ? 1 : w < 4 ? 2 : 3;
+        for (int q = 0; q < 4; q++) acc[r][q] += (double)h[((size_t)c * 16 + w) * 4 + q];
+        cnt[r]++;
+      }
+    fprintf(stderr, "[wgrad_ts] dM=%d dD=%d %dx%d B=%lld PJ=%d RS=%d NR=%d np=%d jobs=%d cpj=%d bands=%d BR=%d NU=%d NSB=%d NA=%d smem=%zu\n",
+            dM, dD, Nx, Ny, (long long)B, p.PJ, p.RS, p.NR, p.np, p.n_jobs, cpj, p.bands, p.BR, p.NU, p.NSB, p.NA, smem);
+    for (int r = 0; r < 4; r++)
+      fprintf(stderr, "[wgrad_ts]   %-30s waitA %9.0f  waitB %9.0f  total %9.0f  mma-issue %9.0f cycles\n", role[r],
+              acc[r][0] / cnt[r], acc[r][1] / cnt[r], acc[r][2] / cnt[r], acc[r][3] / cnt[r]);
+  }
+  return AEFFT_OK;
+}
+
+}  // namespace aefft
