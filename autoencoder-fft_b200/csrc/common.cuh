@@ -151,6 +151,11 @@ int launch_conv_tc_ws(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O
                       const float* src1, float pre_div, const float* w, int64_t w_so, int64_t w_sc, const float* bias,
                       float* out, int passes);
 
+// Row-streaming variant (conv_rs.cu): window rows stacked along N, TMA-fed row rings; same contract.
+int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, int Nx, int Ny, const float* src0,
+                   const float* src1, float pre_div, const float* w, int64_t w_so, int64_t w_sc, const float* bias,
+                   float* out, int passes);
+
 // Correlation (weight-gradient) contraction, summed over all frames and pixels:
 //   G[a][x][k][l] = sum_{b,i,j} A[b][a](i,j) * X[b][x](i+ai0+tk, j+aj0+tl)          (k,l) <-> (tk,tl) per win.flip
 //   sumA[a] = sum A[b][a](i,j);  sumsq = sum A^2

@@ -182,7 +182,9 @@ int launch_conv(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, int 
   if (ctx->precision != AEFFT_PRECISION_FP32) {
     const int passes = ctx->precision == AEFFT_PRECISION_BF16X3 ? 3 : 1;
     // warp-specialised pipeline when all weights fit in shared memory, else the two-CTA-per-SM kernel, else fp32
-    int rc = launch_conv_tc_ws(ctx, win, B, C, O, Nx, Ny, src0, src1, pre_div, w, w_so, w_sc, bias, out, passes);
+    int rc = launch_conv_rs(ctx, win, B, C, O, Nx, Ny, src0, src1, pre_div, w, w_so, w_sc, bias, out, passes);
+    if (rc == AEFFT_ERR_UNSUPPORTED)
+      rc = launch_conv_tc_ws(ctx, win, B, C, O, Nx, Ny, src0, src1, pre_div, w, w_so, w_sc, bias, out, passes);
     if (rc == AEFFT_ERR_UNSUPPORTED)
       rc = launch_conv_tc(ctx, win, B, C, O, Nx, Ny, src0, src1, pre_div, w, w_so, w_sc, bias, out, passes);
     if (rc != AEFFT_ERR_UNSUPPORTED) return rc;

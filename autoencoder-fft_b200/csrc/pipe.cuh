@@ -1,0 +1,50 @@
+// Small device helpers shared by the streaming (TMA -> converter -> tcgen05) kernels: bf16 hi/lo splitting, ring
+// positions for mbarrier-guarded slot rings, single-lane election, timed barrier waits.
+#pragma once
+#include "umma.cuh"
+
+namespace aefft {
+
+using namespace umma;
+
+__device__ __forceinline__ uint32_t cvt_pack_bf16(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+// (a, b) -> packed hi parts and packed lo parts (x ~= hi + lo)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_pack_bf16(a, b);
+  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+  lo = cvt_pack_bf16(ra, rb);
+}
+
+// one lane of a converged warp (warp-uniform predicate)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// position in a ring of n barrier-guarded slots: slot index + phase parity of the current lap
+struct Ring {
+  int slot = 0, n;
+  uint32_t phase = 0;
+  __device__ __forceinline__ explicit Ring(int n_) : n(n_) {}
+  __device__ __forceinline__ void next() {
+    if (++slot == n) { slot = 0; phase ^= 1; }
+  }
+  __device__ __forceinline__ void skip(int k) {
+    slot += k;
+    while (slot >= n) { slot -= n; phase ^= 1; }
+  }
+};
+
+__device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
+}  // namespace aefft

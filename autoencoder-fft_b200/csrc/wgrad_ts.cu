@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "pipe.cuh"
 #include "tma.cuh"
 #include "umma.cuh"
 
@@ -67,46 +68,6 @@ struct WgradTsParams {
   long long* dbg;  // AEFFT_TS_DEBUG: [cta][warp][4] cycles (wait A, wait B, total, -)
 };
 
-__device__ __forceinline__ uint32_t cvt_pack_bf16(float lo_elem, float hi_elem) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
-  return r;
-}
-// (a, b) -> packed hi parts and packed lo parts (x ~= hi + lo)
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  hi = cvt_pack_bf16(a, b);
-  const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
-  lo = cvt_pack_bf16(ra, rb);
-}
-
-// one lane of a converged warp (warp-uniform predicate)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
-  return pred != 0;
-}
-
-// position in a ring of n barrier-guarded slots: slot index + phase parity of the current lap
-struct Ring {
-  int slot = 0, n;
-  uint32_t phase = 0;
-  __device__ __forceinline__ explicit Ring(int n_) : n(n_) {}
-  __device__ __forceinline__ void next() {
-    if (++slot == n) { slot = 0; phase ^= 1; }
-  }
-  __device__ __forceinline__ void skip(int k) {
-    slot += k;
-    while (slot >= n) { slot -= n; phase ^= 1; }
-  }
-};
-
-__device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
-  const long long t0 = clock64();
-  mbar_wait(bar, parity);
-  acc += clock64() - t0;
-}
-
 __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_constant__ WgradTsParams p) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t u_full[TS_MAXRING], u_empty[TS_MAXRING], s_full[TS_NSF], s_empty[TS_NSF],
@@ -114,7 +75,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
   __shared__ uint32_t tmem_slot;
   __shared__ double usum[128], esum[16], esq;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index via a broadcast shuffle: the compiler then knows it is warp-uniform and keeps the role loops (MMA
+  // descriptors, ring positions) in uniform registers instead of moving them there lane by lane
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int jb = blockIdx.y, cta = blockIdx.x;
   const TsJob& J = p.job[jb];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);

@@ -29,3 +29,18 @@ for dM, dD, Nx, Ny in [(16, 3, 320, 240), (32, 16, 160, 120), (64, 32, 80, 60)]:
     for d in dev:
         d.free()
     g.free()
+
+# forward / decoder convolutions of each pair (host arrays in, only the kernels are timed)
+for dM, dD, Nx, Ny in [(16, 3, 320, 240), (32, 16, 160, 120), (64, 32, 80, 60)]:
+    x = np.floor(rng.random((B, dD, Nx, Ny)) * 256).astype(np.float32)
+    c = ((rng.random((dM, dD, 5, 5)) * 2 - 1) * 0.2).astype(np.float32)
+    f = ((rng.random((dD, dM, 5, 5)) * 2 - 1) * 0.2).astype(np.float32)
+    b = np.zeros(dM, np.float32)
+    pb = np.zeros(dD, np.float32)
+    for it in range(2):
+        ctx.profile_enable(it == 1)
+        h = ctx.conv_fwd(x, c, b)
+        y = ctx.conv_fwd(h, f, pb)
+    rows = ctx.profile_records()
+    ctx.profile_enable(False)
+    print(f"conv pair {dD}->{dM}->{dD} {Nx}x{Ny} B={B}: " + ", ".join(f"{r['name']} {r['ms']:.3f} ms/{r['launches']}" for r in rows), flush=True)
