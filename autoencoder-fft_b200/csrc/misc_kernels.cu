@@ -57,6 +57,46 @@ __global__ void pool_up_kernel(const float* __restrict__ in, float* __restrict__
   }
 }
 
+
+// Fast paths for the shipped pooling factor 2 (New_Layer_Param.txt) on frames whose row length is a multiple of 8
+// (down) / 4 (up): 128-bit accesses, 32-bit index arithmetic, every input byte read exactly once.
+// down: one thread = 4 output pixels of one row <- 2 input rows x 8 pixels
+__global__ void pool_down2_kernel(const float4* __restrict__ in, float4* __restrict__ out, unsigned total, int oNx, int w4,
+                                  int in_row4) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= total) return;
+  const unsigned q = n % (unsigned)w4, r = n / (unsigned)w4;          // r = plane * oNx + oi
+  const unsigned pl = r / (unsigned)oNx, oi = r - pl * (unsigned)oNx;
+  const size_t src = ((size_t)pl * oNx * 2 + 2 * oi) * in_row4 + 2 * q;  // float4 units; input plane has 2*oNx rows
+  const float4 a0 = __ldg(in + src), a1 = __ldg(in + src + 1);
+  const float4 b0 = __ldg(in + src + in_row4), b1 = __ldg(in + src + in_row4 + 1);
+  auto red = [](float x, float y, float z, float w) {
+    int smax = 0;  // netlib.cpp:127-136: running int maximum, scan order (k,l)
+    if (x > (float)smax) smax = (int)x;
+    if (y > (float)smax) smax = (int)y;
+    if (z > (float)smax) smax = (int)z;
+    if (w > (float)smax) smax = (int)w;
+    return (float)smax;
+  };
+  float4 o;
+  o.x = red(a0.x, a0.y, b0.x, b0.y);
+  o.y = red(a0.z, a0.w, b0.z, b0.w);
+  o.z = red(a1.x, a1.y, b1.x, b1.y);
+  o.w = red(a1.z, a1.w, b1.z, b1.w);
+  out[n] = o;
+}
+// up: one thread = 4 input pixels of one row -> 2 output rows x 8 pixels
+__global__ void pool_up2_kernel(const float4* __restrict__ in, float4* __restrict__ out, unsigned total, int Nx, int w4) {
+  const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= total) return;
+  const unsigned q = n % (unsigned)w4, r = n / (unsigned)w4;  // r = plane * Nx + i
+  const float4 v = __ldg(in + n);
+  const float4 lo = make_float4(v.x, v.x, v.y, v.y), hi = make_float4(v.z, v.z, v.w, v.w);
+  const size_t dst = (size_t)r * 4 * w4 + 2 * q;  // output row 2*(plane*Nx+i), 2*w4 float4 per output row
+  out[dst] = lo; out[dst + 1] = hi;
+  out[dst + 2 * w4] = lo; out[dst + 2 * w4 + 1] = hi;
+}
+
 int launch_pool(aefft_ctx* ctx, int64_t B, int D, int Nx, int Ny, int oNx, int oNy, int scale, const float* in,
                 float* out) {
   AE_ARG(scale != 0 && B > 0 && D > 0);
@@ -64,7 +104,16 @@ int launch_pool(aefft_ctx* ctx, int64_t B, int D, int Nx, int Ny, int oNx, int o
   long long total = planes * oNx * oNy;
   unsigned blocks = (unsigned)((total + 255) / 256);
   ProfScope prof(ctx, scale > 0 ? "pool_down" : "pool_up", 0.0, 4.0 * (planes * (double)Nx * Ny + (double)total));
-  if (scale > 0) {
+  const bool al16 = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (scale == 2 && al16 && Nx == 2 * oNx && Ny == 2 * oNy && Ny % 8 == 0 && total / 4 < 0xffffffffLL) {
+    const unsigned n4 = (unsigned)(total / 4);
+    pool_down2_kernel<<<(n4 + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(in),
+                                                                reinterpret_cast<float4*>(out), n4, oNx, oNy / 4, Ny / 4);
+  } else if (scale == -2 && al16 && oNx == 2 * Nx && oNy == 2 * Ny && Ny % 4 == 0 && total / 16 < 0xffffffffLL) {
+    const unsigned n4 = (unsigned)(planes * Nx * (Ny / 4));
+    pool_up2_kernel<<<(n4 + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(in),
+                                                              reinterpret_cast<float4*>(out), n4, Nx, Ny / 4);
+  } else if (scale > 0) {
     pool_down_kernel<<<blocks, 256, 0, ctx->stream>>>(in, out, planes, Nx, Ny, oNx, oNy, scale);
   } else {
     const int vec = (oNy % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);

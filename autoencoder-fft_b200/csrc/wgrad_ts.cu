@@ -208,20 +208,22 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
             fence_after_sync();
             const long long t_m0 = clock64();
             const uint32_t a_base = tb + (uint32_t)(p.Acol0 + ra.slot * 64);
+            if (elect_one()) {
+              // one lane walks the (K-step, window-row group, plane) nest; operands advance by constant increments
+              const uint32_t pl_step16 = (uint32_t)NSB * pitch16;
 #pragma unroll 1
-            for (int ks = 0; ks < 4; ks++) {
-              const uint32_t a_hi = a_base + ks * 8, a_lo = a_hi + 32;
-              const uint32_t px16 = (uint32_t)(h * TS_CHUNK + ks * 16);
-              uint32_t d = d_base;
-              int slot = s0slot, a = 0;
+              for (int ks = 0; ks < 4; ks++) {
+                const uint32_t a_hi = a_base + ks * 8, a_lo = a_hi + 32;
+                const uint32_t px16 = sb_base16 + (uint32_t)(h * TS_CHUNK + ks * 16);
+                uint32_t d = d_base;
+                int slot = s0slot, a = 0;
 #pragma unroll 1
-              for (int Ri = 0; Ri < NR; Ri++) {
+                for (int Ri = 0; Ri < NR; Ri++) {
+                  uint32_t lo32 = px16 + (uint32_t)slot * pitch16;
 #pragma unroll 1
-                for (int pl = 0; pl < np; pl++, d += Ncol, a++) {
-                  if (by_chunk || (a & (TS_NI - 1)) == q) {
-                    const uint32_t lo32 = sb_base16 + (uint32_t)(pl * NSB + slot) * pitch16 + px16;
-                    const uint64_t b_hi = desc_const + (uint64_t)lo32, b_lo = b_hi + (uint64_t)lo_off16;
-                    if (elect_one()) {
+                  for (int pl = 0; pl < np; pl++, d += Ncol, a++, lo32 += pl_step16) {
+                    if (by_chunk || (a & (TS_NI - 1)) == q) {
+                      const uint64_t b_hi = desc_const + (uint64_t)lo32, b_lo = b_hi + (uint64_t)lo_off16;
                       mma_bf16_ts(d, a_hi, b_hi, idesc, true);
                       if (three) {
                         mma_bf16_ts(d, a_hi, b_lo, idesc, true);
@@ -229,11 +231,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
                       }
                     }
                   }
+                  slot += RS;
+                  if (slot >= NSB) slot -= NSB;
                 }
-                slot += RS;
-                if (slot >= NSB) slot -= NSB;
               }
             }
+            __syncwarp();
             wC += clock64() - t_m0;
             if (elect_one()) commit(&a_empty[ra.slot]);
           }
@@ -260,7 +263,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
     // ============================================================ S converters (64 threads)
     const int t = tid - 64;
     const int d_off = J.oj - (J.oj & ~3);  // sub-offset of the halo origin inside the aligned box
-    const int SP = p.PJ + 4;
+    const int SP = p.PJ + 4, PJ = p.PJ, TJ = p.TJ, n_it = p.np * p.PJ;
+    const int nch = J.nch, oj = J.oj, oi = J.oi;
+    const bool has_s1 = J.has_s1 != 0, is_gf = J.is_gf != 0;
+    const size_t lo_part = (size_t)(p.np * p.NSB) * p.sb_pitch;
     Ring ss(TS_NSF), sb(p.NSB);
     float fs[16], fq = 0.f;
 #pragma unroll
@@ -275,36 +281,52 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
         wait_t(&sb_empty[sb.slot], sb.phase ^ 1, wB);
         const float* s0 = reinterpret_cast<const float*>(s_ring + (size_t)ss.slot * p.s_slot_bytes);
         const float* s1 = reinterpret_cast<const float*>(s_ring + (size_t)ss.slot * p.s_slot_bytes + p.s_src_bytes);
-        const bool own_row = J.is_gf && (k + J.oi >= 0) && (k + J.oi < nrows);
-        int pl = 0, px = t;
-        for (int idx = t; idx < p.np * p.PJ; idx += 64, px += 64) {
-          if (px >= p.PJ) { px -= p.PJ; pl++; }
-          float v[8];
+        const bool own_row = is_gf && (k + oi >= 0) && (k + oi < nrows);
+        // two (pixel, plane) work items per iteration, all shared-memory loads issued before the first use: the two
+        // converter warps are latency bound (dependent load -> split -> store chains), not throughput bound
+        for (int base = t; base < n_it; base += 128) {
+          float v[2][8];
+          int pls[2], pxs[2];
 #pragma unroll
-          for (int e = 0; e < 8; e++) {
-            const int ch = pl * 8 + e;
-            float x = 0.f;
-            if (ch < J.nch) {
-              x = s0[ch * SP + px + d_off];
-              if (J.has_s1) x -= s1[ch * SP + px + d_off];
+          for (int u = 0; u < 2; u++) {
+            const int idx = base + 64 * u;
+            const int pl = idx >= PJ ? 1 : 0, px = idx - pl * PJ;
+            pls[u] = pl; pxs[u] = px;
+            const bool live = idx < n_it;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              const int ch = pl * 8 + e;
+              v[u][e] = (live && ch < nch) ? s0[ch * SP + px + d_off] : 0.f;
             }
-            v[e] = x;
-          }
-          if (own_row && px + J.oj >= 0 && px + J.oj < p.TJ) {
-            if (pl == 0) {
+            if (has_s1) {
 #pragma unroll
-              for (int e = 0; e < 8; e++) { fs[e] += v[e]; fq = fmaf(v[e], v[e], fq); }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; e++) { fs[8 + e] += v[e]; fq = fmaf(v[e], v[e], fq); }
+              for (int e = 0; e < 8; e++) {
+                const int ch = pl * 8 + e;
+                if (live && ch < nch) v[u][e] -= s1[ch * SP + px + d_off];
+              }
             }
           }
-          uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int e = 0; e < 4; e++) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-          unsigned char* dst = sb_ring + ((size_t)(pl * p.NSB) + sb.slot) * p.sb_pitch + (size_t)px * 16;
-          *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(dst + (size_t)(p.np * p.NSB) * p.sb_pitch) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          for (int u = 0; u < 2; u++) {
+            if (base + 64 * u < n_it) {
+              const int pl = pls[u], px = pxs[u];
+              if (own_row && px + oj >= 0 && px + oj < TJ) {
+                if (pl == 0) {
+#pragma unroll
+                  for (int e = 0; e < 8; e++) { fs[e] += v[u][e]; fq = fmaf(v[u][e], v[u][e], fq); }
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 8; e++) { fs[8 + e] += v[u][e]; fq = fmaf(v[u][e], v[u][e], fq); }
+                }
+              }
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 4; e++) split2(v[u][2 * e], v[u][2 * e + 1], hi[e], lo[e]);
+              unsigned char* dst = sb_ring + ((size_t)(pl * p.NSB) + sb.slot) * p.sb_pitch + (size_t)px * 16;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(dst + lo_part) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -315,7 +337,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
         ss.next();
         sb.next();
       }
-      if (J.is_gf) {
+      if (is_gf) {
         // per-item flush of the fp32 running sums into double accumulators (few hundred values per thread and item)
 #pragma unroll
         for (int e = 0; e < 16; e++) {

@@ -53,7 +53,10 @@ def test_synth_frames_bit_exact(ctx):
 
 
 @pytest.mark.parametrize("scale,shape,oshape", [(2, (3, 12, 10), (6, 5)), (1, (2, 9, 7), (9, 7)), (3, (1, 12, 9), (4, 3)),
-                                               (-2, (3, 6, 5), (12, 10)), (-3, (2, 4, 3), (12, 9))])
+                                               (-2, (3, 6, 5), (12, 10)), (-3, (2, 4, 3), (12, 9)),
+                                               # the vectorised factor-2 fast paths (row length % 8 / % 4)
+                                               (2, (3, 12, 16), (6, 8)), (2, (5, 20, 40), (10, 20)), (-2, (3, 6, 8), (12, 16)),
+                                               (-2, (4, 10, 20), (20, 40))])
 def test_pool_bit_exact(ctx, scale, shape, oshape):
     rng = np.random.default_rng(1)
     x = (rng.random((2,) + shape) * 300 - 40).astype(np.float32)  # negatives and fractions exercise the int quirk (N1)
