@@ -48,7 +48,7 @@ struct ConvRsParams {
   int Oj, O_pad, n_jobs;
   int PJs, G, TJ, strips, bands, BR;
   int n_sub, items, cpj;
-  int KS, NP, kpack, NLg, Ntot, Rr, NSB, passes;
+  int KS, NP, kpack, NLg, Ntot, Rr, NSB, NSF, passes;
   uint32_t w_bytes, seg_bytes, src_bytes, x_slot_bytes, sb_pitch;
   uint32_t off_w, off_x, off_sb;
   long long* dbg;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 32) {
-    for (int i = 0; i < RS_NSF; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], RS_CONV_WARPS); }
+    for (int i = 0; i < p.NSF; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], RS_CONV_WARPS); }
     for (int i = 0; i < p.NSB; i++) { mbar_init(&xb_full[i], RS_CONV_WARPS); mbar_init(&xb_empty[i], 1); }
     for (int i = 0; i < p.Rr; i++) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_mbar_init();
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     if (lane == 0) {
       tma_prefetch_desc(&p.x0_map);
       if (p.has_x1) tma_prefetch_desc(&p.x1_map);
-      Ring ss(RS_NSF);
+      Ring ss(p.NSF);
       const uint32_t seg_tx = (uint32_t)p.C * SP * 4;
       for (int item = cta; item < n_items; item += cpj) {
         const int ug = item / p.bands, band = item - ug * p.bands;
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     // ============================================================ converters (6 warps): fp32 rows -> bf16 hi/lo planes
     const int t = tid - 64;
     constexpr int NT = RS_CONV_WARPS * 32;
-    Ring ss(RS_NSF), sb(p.NSB);
+    Ring ss(p.NSF), sb(p.NSB);
     const int n_it = p.NP * 128;
     for (int item = cta; item < n_items; item += cpj) {
       const int ug = item / p.bands, band = item - ug * p.bands;
@@ -391,7 +391,7 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
                    const float* src1, float pre_div, const float* w, int64_t w_so, int64_t w_sc, const float* bias,
                    float* out, int passes) {
   if (getenv("AEFFT_NO_CONV_RS")) return AEFFT_ERR_UNSUPPORTED;
-  if (win.lo != 0 || Ny % 4 != 0 || win.Nk > 8 || win.Nl > 8 || C > 64) return AEFFT_ERR_UNSUPPORTED;
+  if (win.lo != 0 || Ny % 4 != 0 || win.Nk > 8 || win.Nl > 8 || C > 128) return AEFFT_ERR_UNSUPPORTED;
   if ((((uintptr_t)src0 | (uintptr_t)src1) & 15) != 0) return AEFFT_ERR_UNSUPPORTED;
   if (B * (int64_t)C > 0x7fffffffLL) return AEFFT_ERR_UNSUPPORTED;
   ConvRsParams p;
@@ -416,20 +416,24 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
   p.x_slot_bytes = (p.has_x1 ? 2 : 1) * p.src_bytes;
   // outputs per job: as many as fit next to the rings (weights of all K stages stay resident)
   const size_t budget = 225 * 1024 - 1024;
-  const size_t x_bytes = (size_t)RS_NSF * p.x_slot_bytes;
+  size_t x_bytes = 0;
   int found = 0;
-  for (int split = 1; split <= 8 && !found; split++) {
-    const int Oj = ((O + split - 1) / split + 15) / 16 * 16;
-    const int O_pad = Oj;
-    const int Rr = 512 / O_pad > RS_MAXACC ? RS_MAXACC : 512 / O_pad;
-    if (Rr < win.Nk + 1) continue;
-    const size_t w_bytes = (size_t)p.KS * 2 * p.NLg * 2 * (win.Nk * O_pad) * 16;
-    for (int NSB = 4; NSB >= 2 && !found; NSB--) {
-      const size_t sb_bytes = (size_t)2 * p.NP * NSB * p.sb_pitch;
-      if (w_bytes + x_bytes + sb_bytes + 3 * 1024 <= budget) {
-        p.Oj = Oj; p.O_pad = O_pad; p.Rr = Rr; p.NSB = NSB; p.w_bytes = (uint32_t)w_bytes;
-        p.n_jobs = (O + Oj - 1) / Oj;
-        found = 1;
+  // preference order: double-buffered fp32 staging, few output jobs, deep bf16 ring
+  for (int NSF = RS_NSF; NSF >= 1 && !found; NSF--) {
+    x_bytes = (size_t)NSF * p.x_slot_bytes;
+    for (int split = 1; split <= 8 && !found; split++) {
+      const int Oj = ((O + split - 1) / split + 15) / 16 * 16;
+      const int O_pad = Oj;
+      const int Rr = 512 / O_pad > RS_MAXACC ? RS_MAXACC : 512 / O_pad;
+      if (Rr < win.Nk + 1) continue;
+      const size_t w_bytes = (size_t)p.KS * 2 * p.NLg * 2 * (win.Nk * O_pad) * 16;
+      for (int NSB = 4; NSB >= 2 && !found; NSB--) {
+        const size_t sb_bytes = (size_t)2 * p.NP * NSB * p.sb_pitch;
+        if (w_bytes + x_bytes + sb_bytes + 3 * 1024 <= budget) {
+          p.Oj = Oj; p.O_pad = O_pad; p.Rr = Rr; p.NSB = NSB; p.NSF = NSF; p.w_bytes = (uint32_t)w_bytes;
+          p.n_jobs = (O + Oj - 1) / Oj;
+          found = 1;
+        }
       }
     }
   }
