@@ -84,6 +84,10 @@ class DevBuf:
     def data_ptr(self):
         return self.ptr
 
+    @property
+    def ndim(self):
+        return len(self.shape)
+
     def numpy(self):
         out = np.empty(self.shape, np.float32)
         self.ctx.memcpy(out.ctypes.data, self.ptr, self.nbytes, 1)

@@ -236,6 +236,246 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const float2* __restrict_
   }
 }
 
+
+// ================================================================================================ compile-time sizes
+// The kernels above take the transform length at run time (digit reversal and butterfly indexing through integer
+// divisions): they are instruction bound (~0.7-0.9 TB/s).  For N = 8..4096 the same algorithm is instantiated with the
+// length, the radix schedule and every stride as compile-time constants (shifts and masks only), smaller tiles (more
+// CTAs per SM so that the load, butterfly and store phases of different CTAs overlap) and division-free staging loops.
+template <int LOG2N>
+struct Sched {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int first = (LOG2N % 3 == 1) ? 1 : ((LOG2N % 3 == 2) ? 2 : 3);  // log2 of the first radix
+  static constexpr int npass = 1 + (LOG2N - first) / 3;
+  __host__ __device__ static constexpr int lr(int i) { return i == 0 ? first : 3; }
+};
+
+template <int LOG2N>
+__device__ __forceinline__ int digit_reverse_t(int n) {
+  using S = Sched<LOG2N>;
+  int pos = 0;
+  int shift = LOG2N;
+#pragma unroll
+  for (int i = S::npass - 1; i >= 0; i--) {
+    const int lr = S::lr(i);
+    shift -= lr;
+    pos += (n & ((1 << lr) - 1)) << shift;
+    n >>= lr;
+  }
+  return pos;
+}
+
+// element n of sequence c: rows s[c*SP + n], columns s[n*SC + c]
+template <int DIR, int LR, int LOG2N, int LOG2M, bool COLS, int LOG2SEQ, int PITCH>
+__device__ __forceinline__ void fft_pass_t(float2* s, const float2* __restrict__ tw) {
+  constexpr int R = 1 << LR, N = 1 << LOG2N, M = 1 << LOG2M;
+  constexpr int LOG2NBF = LOG2N - LR;
+  constexpr int tstep = N >> (LOG2M + LR);
+  constexpr int items = 1 << (LOG2NBF + LOG2SEQ);
+  for (int item = threadIdx.x; item < items; item += blockDim.x) {
+    int c, t;
+    if (COLS) { c = item & ((1 << LOG2SEQ) - 1); t = item >> LOG2SEQ; }
+    else { t = item & ((1 << LOG2NBF) - 1); c = item >> LOG2NBF; }
+    const int k = t & (M - 1), blk = t >> LOG2M;
+    const int n0 = (blk << (LOG2M + LR)) + k;
+    float2* base = COLS ? s + n0 * PITCH + c : s + c * PITCH + n0;
+    constexpr int step = COLS ? M * PITCH : M;
+    float2 a[R];
+#pragma unroll
+    for (int q = 0; q < R; q++) a[q] = base[q * step];
+    if (LOG2M > 0) {
+#pragma unroll
+      for (int q = 1; q < R; q++) {
+        float2 w = __ldg(tw + (q * k * tstep));
+        if (DIR > 0) w.y = -w.y;
+        a[q] = cmul(a[q], w);
+      }
+    }
+    if (R == 2) dft2<DIR>(a);
+    else if (R == 4) dft4<DIR>(a);
+    else dft8<DIR>(a);
+#pragma unroll
+    for (int j = 0; j < R; j++) base[j * step] = a[j];
+  }
+}
+
+template <int DIR, int LOG2N, bool COLS, int LOG2SEQ, int PITCH, int I = 0, int LOG2M = 0>
+__device__ __forceinline__ void fft_smem_t(float2* s, const float2* __restrict__ tw) {
+  __syncthreads();
+  if constexpr (LOG2M < LOG2N) {
+    constexpr int LR = Sched<LOG2N>::lr(I);
+    fft_pass_t<DIR, LR, LOG2N, LOG2M, COLS, LOG2SEQ, PITCH>(s, tw);
+    fft_smem_t<DIR, LOG2N, COLS, LOG2SEQ, PITCH, I + 1, LOG2M + LR>(s, tw);
+  }
+}
+
+// row pairs per CTA: ~32 KB of shared memory
+template <int LOG2N>
+struct RowCfg {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int LOG2RP = LOG2N >= 12 ? 0 : (12 - LOG2N > 5 ? 5 : 12 - LOG2N);
+  static constexpr int RP = 1 << LOG2RP;
+  static constexpr int SP = N + 1;
+  static constexpr size_t smem = (size_t)RP * SP * sizeof(float2);
+};
+
+template <int LOG2N>
+__global__ void __launch_bounds__(256) fft_rows_r2c_t(const float* __restrict__ in, float2* __restrict__ out, int Nx,
+                                                      const float2* __restrict__ tw) {
+  using C = RowCfg<LOG2N>;
+  constexpr int Ny = C::N, Nyr = Ny / 2 + 1, SP = C::SP, RP = C::RP;
+  extern __shared__ __align__(16) float2 sm[];
+  const long long img = blockIdx.y;
+  const int rp0 = blockIdx.x * RP;
+  const float* src = in + img * (long long)Nx * Ny;
+  for (int idx = threadIdx.x; idx < RP * Ny; idx += blockDim.x) {
+    const int r = idx >> LOG2N, n = idx & (Ny - 1);
+    const int row = 2 * (rp0 + r);
+    float2 v = make_float2(0.f, 0.f);
+    if (row < Nx) {
+      v.x = __ldg(src + (long long)row * Ny + n);
+      v.y = __ldg(src + (long long)(row + 1) * Ny + n);
+    }
+    sm[r * SP + digit_reverse_t<LOG2N>(n)] = v;
+  }
+  fft_smem_t<-1, LOG2N, false, C::LOG2RP, SP>(sm, tw);
+  float2* dst = out + img * (long long)Nx * Nyr;
+  for (int r = 0; r < RP; r++) {
+    const int row = 2 * (rp0 + r);
+    if (row >= Nx) break;
+    for (int k = threadIdx.x; k < Nyr; k += blockDim.x) {
+      const float2 z1 = sm[r * SP + k];
+      const float2 z2 = sm[r * SP + ((Ny - k) & (Ny - 1))];
+      dst[(long long)row * Nyr + k] = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+      dst[(long long)(row + 1) * Nyr + k] = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+    }
+  }
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(256) fft_rows_c2r_t(const float2* __restrict__ in, float* __restrict__ out, int Nx,
+                                                      const float2* __restrict__ tw, float scale) {
+  using C = RowCfg<LOG2N>;
+  constexpr int Ny = C::N, Nyr = Ny / 2 + 1, SP = C::SP, RP = C::RP;
+  extern __shared__ __align__(16) float2 sm[];
+  const long long img = blockIdx.y;
+  const int rp0 = blockIdx.x * RP;
+  const float2* src = in + img * (long long)Nx * Nyr;
+  for (int r = 0; r < RP; r++) {
+    const int row = 2 * (rp0 + r);
+    for (int k = threadIdx.x; k < Nyr; k += blockDim.x) {
+      float2 a = make_float2(0.f, 0.f), b = a;
+      if (row < Nx) {
+        a = __ldg(src + (long long)row * Nyr + k);
+        b = __ldg(src + (long long)(row + 1) * Nyr + k);
+      }
+      if (k == 0 || k == Ny / 2) { a.y = 0.f; b.y = 0.f; }
+      sm[r * SP + digit_reverse_t<LOG2N>(k)] = make_float2(a.x - b.y, a.y + b.x);
+      if (k > 0 && k < Ny / 2) sm[r * SP + digit_reverse_t<LOG2N>(Ny - k)] = make_float2(a.x + b.y, b.x - a.y);
+    }
+  }
+  fft_smem_t<+1, LOG2N, false, C::LOG2RP, SP>(sm, tw);
+  float* dst = out + img * (long long)Nx * Ny;
+  for (int idx = threadIdx.x; idx < RP * Ny; idx += blockDim.x) {
+    const int r = idx >> LOG2N, n = idx & (Ny - 1);
+    const int row = 2 * (rp0 + r);
+    if (row >= Nx) continue;
+    const float2 z = sm[r * SP + n];
+    dst[(long long)row * Ny + n] = z.x * scale;
+    dst[(long long)(row + 1) * Ny + n] = z.y * scale;
+  }
+}
+
+// columns per CTA: 8 (64-byte row segments) while the tile stays <= ~74 KB, fewer for the longest transforms
+template <int LOG2N>
+struct ColCfg {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int LOG2CT = LOG2N <= 10 ? 3 : (LOG2N == 11 ? 2 : 1);
+  static constexpr int CT = 1 << LOG2CT;
+  static constexpr int SC = CT + 1;
+  static constexpr size_t smem = (size_t)N * SC * sizeof(float2);
+};
+
+template <int DIR, int LOG2N>
+__global__ void __launch_bounds__(256) fft_cols_t(const float2* __restrict__ in, float2* __restrict__ out, int W,
+                                                  const float2* __restrict__ tw) {
+  using C = ColCfg<LOG2N>;
+  constexpr int Nx = C::N, CT = C::CT, SC = C::SC;
+  extern __shared__ __align__(16) float2 sm[];
+  const long long img = blockIdx.y;
+  const int c0 = blockIdx.x * CT;
+  const float2* src = in + img * (long long)Nx * W;
+  for (int idx = threadIdx.x; idx < Nx * CT; idx += blockDim.x) {
+    const int n = idx >> C::LOG2CT, c = idx & (CT - 1);
+    float2 v = make_float2(0.f, 0.f);
+    if (c0 + c < W) v = __ldg(src + (long long)n * W + c0 + c);
+    sm[digit_reverse_t<LOG2N>(n) * SC + c] = v;
+  }
+  fft_smem_t<DIR, LOG2N, true, C::LOG2CT, SC>(sm, tw);
+  float2* dst = out + img * (long long)Nx * W;
+  for (int idx = threadIdx.x; idx < Nx * CT; idx += blockDim.x) {
+    const int n = idx >> C::LOG2CT, c = idx & (CT - 1);
+    if (c0 + c < W) dst[(long long)n * W + c0 + c] = sm[n * SC + c];
+  }
+}
+
+template <int LOG2N>
+static int run_rows_r2c(aefft_ctx* ctx, int64_t batch, int Nx, const float* in, float2* out, const float2* tw) {
+  using C = RowCfg<LOG2N>;
+  static bool attr = false;
+  if (!attr) { AE_CUDA(cudaFuncSetAttribute(fft_rows_r2c_t<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem)); attr = true; }
+  dim3 grid((Nx / 2 + C::RP - 1) / C::RP, (unsigned)batch);
+  fft_rows_r2c_t<LOG2N><<<grid, 256, C::smem, ctx->stream>>>(in, out, Nx, tw);
+  return AEFFT_OK;
+}
+template <int LOG2N>
+static int run_rows_c2r(aefft_ctx* ctx, int64_t batch, int Nx, const float2* in, float* out, const float2* tw, float scale) {
+  using C = RowCfg<LOG2N>;
+  static bool attr = false;
+  if (!attr) { AE_CUDA(cudaFuncSetAttribute(fft_rows_c2r_t<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem)); attr = true; }
+  dim3 grid((Nx / 2 + C::RP - 1) / C::RP, (unsigned)batch);
+  fft_rows_c2r_t<LOG2N><<<grid, 256, C::smem, ctx->stream>>>(in, out, Nx, tw, scale);
+  return AEFFT_OK;
+}
+template <int DIR, int LOG2N>
+static int run_cols(aefft_ctx* ctx, int64_t batch, int W, const float2* in, float2* out, const float2* tw) {
+  using C = ColCfg<LOG2N>;
+  static bool attr = false;
+  if (!attr) { AE_CUDA(cudaFuncSetAttribute(fft_cols_t<DIR, LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem)); attr = true; }
+  dim3 grid((W + C::CT - 1) / C::CT, (unsigned)batch);
+  fft_cols_t<DIR, LOG2N><<<grid, 256, C::smem, ctx->stream>>>(in, out, W, tw);
+  return AEFFT_OK;
+}
+#define AEFFT_FOR_LOG2N(X) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+// return AEFFT_ERR_UNSUPPORTED for lengths without a compile-time instantiation
+static int rows_r2c_fast(aefft_ctx* ctx, int log2n, int64_t batch, int Nx, const float* in, float2* out, const float2* tw) {
+  switch (log2n) {
+#define X(L) case L: return run_rows_r2c<L>(ctx, batch, Nx, in, out, tw);
+    AEFFT_FOR_LOG2N(X)
+#undef X
+  }
+  return AEFFT_ERR_UNSUPPORTED;
+}
+static int rows_c2r_fast(aefft_ctx* ctx, int log2n, int64_t batch, int Nx, const float2* in, float* out, const float2* tw,
+                         float scale) {
+  switch (log2n) {
+#define X(L) case L: return run_rows_c2r<L>(ctx, batch, Nx, in, out, tw, scale);
+    AEFFT_FOR_LOG2N(X)
+#undef X
+  }
+  return AEFFT_ERR_UNSUPPORTED;
+}
+template <int DIR>
+static int cols_fast(aefft_ctx* ctx, int log2n, int64_t batch, int W, const float2* in, float2* out, const float2* tw) {
+  switch (log2n) {
+#define X(L) case L: return run_cols<DIR, L>(ctx, batch, W, in, out, tw);
+    AEFFT_FOR_LOG2N(X)
+#undef X
+  }
+  return AEFFT_ERR_UNSUPPORTED;
+}
+static int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
+
 // ------------------------------------------------------------------------------------------------ host side
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
@@ -293,7 +533,9 @@ int launch_fft_r2c(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float* i
     AE_TRY(set_smem(fft_rows_r2c_kernel, smem));
     dim3 grid((Nx / 2 + RP - 1) / RP, (unsigned)batch);
     ProfScope prof(ctx, "fft_rows_r2c", 2.5 * px * log2((double)Ny), 4.0 * px + 8.0 * sp);
-    fft_rows_r2c_kernel<<<grid, 256, smem, ctx->stream>>>(in, spec, Nx, Ny, RP, make_plan(Ny), twy);
+    const int rc = rows_r2c_fast(ctx, ilog2(Ny), batch, Nx, in, spec, twy);
+    if (rc == AEFFT_ERR_UNSUPPORTED) fft_rows_r2c_kernel<<<grid, 256, smem, ctx->stream>>>(in, spec, Nx, Ny, RP, make_plan(Ny), twy);
+    else if (rc != AEFFT_OK) return rc;
   }
   {
     const int CT = col_tile(Nx);
@@ -301,7 +543,9 @@ int launch_fft_r2c(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float* i
     AE_TRY(set_smem(fft_cols_kernel<-1>, smem));
     dim3 grid((Nyr + CT - 1) / CT, (unsigned)batch);
     ProfScope prof(ctx, "fft_cols", 5.0 * sp * log2((double)Nx), 16.0 * sp);
-    fft_cols_kernel<-1><<<grid, 256, smem, ctx->stream>>>(spec, spec, Nx, Nyr, CT, make_plan(Nx), twx);
+    const int rc = cols_fast<-1>(ctx, ilog2(Nx), batch, Nyr, spec, spec, twx);
+    if (rc == AEFFT_ERR_UNSUPPORTED) fft_cols_kernel<-1><<<grid, 256, smem, ctx->stream>>>(spec, spec, Nx, Nyr, CT, make_plan(Nx), twx);
+    else if (rc != AEFFT_OK) return rc;
   }
   ctx->launches += 2;
   AE_CUDA(cudaGetLastError());
@@ -324,7 +568,9 @@ int launch_fft_c2r(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float2* 
     AE_TRY(set_smem(fft_cols_kernel<+1>, smem));
     dim3 grid((Nyr + CT - 1) / CT, (unsigned)batch);
     ProfScope prof(ctx, "fft_cols", 5.0 * sp * log2((double)Nx), 16.0 * sp);
-    fft_cols_kernel<+1><<<grid, 256, smem, ctx->stream>>>(spec, work, Nx, Nyr, CT, make_plan(Nx), twx);
+    const int rc = cols_fast<+1>(ctx, ilog2(Nx), batch, Nyr, spec, work, twx);
+    if (rc == AEFFT_ERR_UNSUPPORTED) fft_cols_kernel<+1><<<grid, 256, smem, ctx->stream>>>(spec, work, Nx, Nyr, CT, make_plan(Nx), twx);
+    else if (rc != AEFFT_OK) return rc;
   }
   {
     const int RP = row_pairs(Nx, Ny);
@@ -332,7 +578,9 @@ int launch_fft_c2r(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float2* 
     AE_TRY(set_smem(fft_rows_c2r_kernel, smem));
     dim3 grid((Nx / 2 + RP - 1) / RP, (unsigned)batch);
     ProfScope prof(ctx, "fft_rows_c2r", 2.5 * px * log2((double)Ny), 4.0 * px + 8.0 * sp);
-    fft_rows_c2r_kernel<<<grid, 256, smem, ctx->stream>>>(work, out, Nx, Ny, RP, make_plan(Ny), twy, scale);
+    const int rc = rows_c2r_fast(ctx, ilog2(Ny), batch, Nx, work, out, twy, scale);
+    if (rc == AEFFT_ERR_UNSUPPORTED) fft_rows_c2r_kernel<<<grid, 256, smem, ctx->stream>>>(work, out, Nx, Ny, RP, make_plan(Ny), twy, scale);
+    else if (rc != AEFFT_OK) return rc;
   }
   ctx->launches += 2;
   AE_CUDA(cudaGetLastError());
