@@ -143,6 +143,28 @@ class Ctx:
         self.memcpy(buf.ptr, a.ctypes.data, a.nbytes, 0)
         return buf
 
+    def set_gradient_hook(self, fn):
+        """fn(dev_ptr: int, n_floats: int) -> None averages the raw momentum-space gradient block over the ranks in place
+        (work ordered on the ctx stream); None removes the hook (aefft_set_gradient_hook)."""
+        HOOK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64)
+        if fn is None:
+            self._hook = None
+            _chk(lib().aefft_set_gradient_hook(self.h, C.cast(None, HOOK), None))
+            return
+
+        def tramp(user, ptr, n):
+            try:
+                fn(int(ptr), int(n))
+                return 0
+            except Exception:  # the C side turns a non-zero return into an AefftError
+                import traceback
+
+                traceback.print_exc()
+                return 1
+
+        self._hook = HOOK(tramp)  # keep the trampoline alive
+        _chk(lib().aefft_set_gradient_hook(self.h, self._hook, None))
+
     def profile_enable(self, on: bool):
         """Bracket every kernel launch of this ctx with a CUDA event pair (aefft_profile_enable)."""
         _chk(lib().aefft_profile_enable(self.h, 1 if on else 0))

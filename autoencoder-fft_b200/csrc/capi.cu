@@ -292,6 +292,13 @@ int aefft_sync(aefft_ctx* ctx) {
 
 void* aefft_stream(aefft_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+int aefft_set_gradient_hook(aefft_ctx* ctx, aefft_gradient_hook_fn fn, void* user) {
+  AE_ARG(ctx);
+  ctx->grad_hook = fn;
+  ctx->grad_hook_user = user;
+  return AEFFT_OK;
+}
+
 int aefft_set_stream(aefft_ctx* ctx, void* cuda_stream) {
   AE_ARG(ctx);
   AE_CUDA(cudaSetDevice(ctx->device));

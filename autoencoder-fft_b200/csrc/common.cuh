@@ -60,6 +60,8 @@ struct aefft_ctx {
   int64_t launches = 0;
   int precision = AEFFT_PRECISION_FP32;  // arithmetic of the coordinate-space contractions (aefft_set_precision)
   bool profiling = false;
+  aefft_gradient_hook_fn grad_hook = nullptr;  // data-parallel momentum-space training (aefft_set_gradient_hook)
+  void* grad_hook_user = nullptr;
   std::vector<aefft::ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;
   cudaEvent_t get_event();

@@ -269,11 +269,11 @@ int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int N
   AE_TRY(ctx->getT("bpf_work", 2 * nKS > nXs ? 2 * nKS : nXs, &q.work));
   AE_TRY(ctx->getT("bpf_img", 2 * (size_t)dM * dD * P, &q.img));
   AE_TRY(ctx->getT("bpf_real", (size_t)B * dD * P, &real));
-  AE_TRY(ctx->getT("bpf_taps", 2 * nC, &q.taps));
+  AE_TRY(ctx->getT("bpf_taps", 2 * nC + dM + dD, &q.taps));  // raw gradient block [dck | dfk | db | dp]
   AE_TRY(ctx->getT("bpf_wts", 2 * nC + dM + dD, &wts));
   float* small;
   AE_TRY(ctx->getT("bpf_small", 2 * (size_t)(dM + dD) + 2 * nC + 2 * nC + dM + dD + (size_t)n_iter + 1, &small));
-  q.db = small; q.dp = q.db + dM; q.Db = q.dp + dD; q.Dp = q.Db + dM;
+  q.db = q.taps + 2 * nC; q.dp = q.db + dM; q.Db = small + dM + dD; q.Dp = q.Db + dM;
   q.Dc = q.Dp + dD; q.Df = q.Dc + nC; q.div = q.Df + nC; q.mse = q.div + 2 * nC + dM + dD;
   float *dc_w = wts, *df_w = wts + nC, *db_w = wts + 2 * nC, *dp_w = db_w + dM;
   // momentum buffers are zeroed at the start of every call (:1420-1423)
@@ -320,6 +320,11 @@ int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int N
     // kernel-space gradients: C2R (unnormalised) + shrink_k (:1219-1226)
     AE_TRY(launch_fft_c2r(ctx, 2 * (int64_t)dM * dD, Nx, Ny, q.dCF, q.work, q.img, 1.f));
     AE_TRY(launch_shrink(ctx, 2 * (int64_t)dM * dD, Nx, Ny, Nk, Nl, q.img, q.taps));
+    // data-parallel ranks average the raw gradient block here, before the non-linear clip
+    if (ctx->grad_hook && ctx->grad_hook(ctx->grad_hook_user, q.taps, (int64_t)(2 * nC + dM + dD)) != 0) {
+      set_error("aefft_backprop_fft: gradient hook failed");
+      return AEFFT_ERR_ARG;
+    }
     // clipped-momentum update in kernel space (+ multiobjective term)
     AE_TRY(launch_fft_update(ctx, dM, dD, Nk, Nl, dc_w, df_w, db_w, dp_w, q.taps, q.taps + nC, q.db, q.dp, q.Dc, q.Df, q.Db,
                              q.Dp, del, maxdiff, q.div));

@@ -292,14 +292,20 @@ class FftWorkload:
     def __init__(self, A, ctx, w, args, rank, world, dev, torch, dist):
         self.A, self.ctx, self.w, self.world, self.torch, self.dist = A, ctx, w, world, torch, dist
         B = self.B = args.batch
-        import oracle_np as O  # only for the seeded Init_conv draw order (host glue), not on the timed path
 
         Nk, Nl = 2 * (w["Lk"] + 1) + 1, 2 * (w["Ll"] + 1) + 1
-        rng = O.GlibcRand(SEED)
+        ctypes.CDLL("libc.so.6").srand(SEED)  # Init_conv draws from libc rand() (netlib.cpp:167-197), through the C ABI
+
+        def init_conv(mS, dD_, kS, lS, rmax):
+            c_ = np.empty((mS, dD_, kS, lS), np.float32)
+            b_ = np.empty(mS, np.float32)
+            A._chk(A.lib().aefft_init_conv(A._ptr(c_), A._ptr(b_), mS, dD_, kS, lS, ctypes.c_float(rmax)))
+            return c_, b_
+
         encs, d, nx, ny = [], w["D"], w["Nx"], w["Ny"]
         shapes = [(d, nx, ny)]
         for m in w["widths"]:
-            c, b = O.init_conv(rng, m, d, Nk, Nl, w["rmax"] / 10.0)
+            c, b = init_conv(m, d, Nk, Nl, w["rmax"] / 10.0)
             f = np.ascontiguousarray(np.swapaxes(c, 0, 1))
             p_ = np.zeros(d, np.float32)
             encs.append((c, b, f, p_, d, nx, ny))
@@ -339,6 +345,17 @@ class FftWorkload:
                                    p=int(self.boff[2 * P - 1 - n])))
         self.h2d_bytes, self.d2h_bytes = B * self.n0 * 4, 4 * P
         self._put_frames(A.DEVICE, frames.ptr)
+        if world > 1:
+            # data-parallel frames: every rank averages the raw kernel-space gradient block [dck | dfk | db | dp] of its own
+            # frames over the ranks (NCCL on the engine's stream) before the clipped-momentum update
+            views = {}
+
+            def hook(ptr, n):
+                if (ptr, n) not in views:
+                    views[(ptr, n)] = torch.as_tensor(CudaArray(ptr, n), device=dev)
+                dist.all_reduce(views[(ptr, n)], op=dist.ReduceOp.AVG)
+
+            ctx.set_gradient_hook(hook)
 
     def _put_frames(self, kind_loc, src_ptr):
         """layer 0 of every frame lives at layers[b*lstride]: strided copy of the batch's frames."""
@@ -400,8 +417,6 @@ def run_ours(args, w, rank, world, local_rank):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     A._chk(A.lib().aefft_set_stream(ctx.h, ctypes.c_void_p(stream.cuda_stream)))
-    if w["space"] == "fft" and world > 1:
-        raise SystemExit("the FFT-space workload is single-GPU in this round (DESIGN.md section 6)")
     wl = (CoordWorkload if w["space"] == "coordinate" else FftWorkload)(A, ctx, w, args, rank, world, dev, torch, dist)
 
     def barrier():

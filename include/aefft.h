@@ -161,6 +161,15 @@ int aefft_autoenc_fft(aefft_ctx* ctx, int loc, int64_t B, int n_conv, const int*
                       const int* ldims, float* layers_all, const int64_t* loff, int64_t lstride, int cfreq_valid,
                       float* cfreq_all, const int64_t* cfoff, int fft_l);
 
+/* Data-parallel training in momentum space: a host callback invoked by aefft_backprop_fft once per iteration, between
+ * the kernel-space gradients and the clipped-momentum update, on the contiguous RAW gradient block
+ * [dck dM*dD*Nk*Nl | dfk dD*dM*Nk*Nl | db dM | dp dD] (device memory, already averaged over this rank's B frames).
+ * The callback must average the block over the ranks IN PLACE with work ordered on the ctx stream (e.g. an NCCL
+ * all-reduce on that stream) and return 0.  The reference has no multi-GPU path; with no hook (NULL) the call is the
+ * reference's single-device algorithm.  The reduction precedes the non-linear clip g/max(10,|g|). */
+typedef int (*aefft_gradient_hook_fn)(void* user, float* dev_block, int64_t n_floats);
+int aefft_set_gradient_hook(aefft_ctx* ctx, aefft_gradient_hook_fn fn, void* user);
+
 /* backprop_fft (fft_backproplib.cu:1381-1511): n_iter (reference: 100) iterations of spectral gradients ->
  * kernel-space clipped-momentum update (lr 0.1*del0, alpha 0.9, momentum zeroed per call) -> re-forward.
  * in, expout, out [B][dD][Nx][Ny]; cfreq/ffreq wire-format spectra (in: cache, out: trained; may be NULL ->

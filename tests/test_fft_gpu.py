@@ -184,3 +184,44 @@ def test_fft_path_vs_live_reference(ctx, ref):
     assert O.rel_l2(got[-1], want[-1]) < 1e-4
     for n in range(4):
         assert O.rel_l2(gcf[n], wcf[n]) < 1e-5
+
+
+def test_gradient_hook_two_rank_emulation(ctx):
+    """Data-parallel momentum-space training (aefft_set_gradient_hook): two 'ranks' each own 2 frames; averaging their
+    raw kernel-space gradient blocks before the clipped-momentum update reproduces the 4-frame step of one device."""
+    dims = (4, 3, 5, 5, 16, 16)
+    dM, dD, Nk, Nl, Nx, Ny = dims
+    cs = fft_case(7, *dims, B=4)
+    n_block = 2 * dM * dD * Nk * Nl + dM + dD
+    # reference: the whole batch on one device, no hook
+    full = {k: cs[k].copy() for k in "cfbp"}
+    ctx.backprop_fft(cs["inp"], cs["inp"], cs["out"], full["c"], full["f"], full["b"], full["p"], 0.2, 0, 1)
+    # pass 1: capture each rank's raw gradient block
+    blocks, calls = [], []
+
+    def capture(ptr, n):
+        calls.append(n)
+        host = np.empty(n, np.float32)
+        ctx.memcpy(host.ctypes.data, ptr, n * 4, 1)
+        blocks.append(host)
+
+    ctx.set_gradient_hook(capture)
+    try:
+        for r in range(2):
+            sl = slice(2 * r, 2 * r + 2)
+            w = {k: cs[k].copy() for k in "cfbp"}
+            ctx.backprop_fft(cs["inp"][sl], cs["inp"][sl], cs["out"][sl], w["c"], w["f"], w["b"], w["p"], 0.2, 0, 1)
+        assert calls == [n_block, n_block]
+        mean = (blocks[0] + blocks[1]) / 2
+
+        # pass 2: rank 0 again, the hook now plays the all-reduce(AVG)
+        def average(ptr, n):
+            ctx.memcpy(ptr, mean.ctypes.data, n * 4, 0)
+
+        ctx.set_gradient_hook(average)
+        w = {k: cs[k].copy() for k in "cfbp"}
+        ctx.backprop_fft(cs["inp"][:2], cs["inp"][:2], cs["out"][:2], w["c"], w["f"], w["b"], w["p"], 0.2, 0, 1)
+    finally:
+        ctx.set_gradient_hook(None)
+    for k in "cfbp":
+        assert O.rel_l2(w[k], full[k]) < 1e-6, k
