@@ -6,6 +6,8 @@
 // Reference kernels replaced (fft_backproplib.cu): resize :87-157, conv_k :162-189, gradient_k_io :395-475,
 // calc_mse + thrust::reduce :480-498/1178-1192, shrink_k :535-565, pad_k :570-600, backprop_d :605-652,
 // backprop_double :657-704, gradient_diff :709-753.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace aefft {
@@ -77,6 +79,7 @@ struct ContractParams {
   float in_scale, bias_scale;
 };
 
+template <int SC_OT, int SC_FT>
 __global__ void __launch_bounds__(SC_THREADS) spec_contract_kernel(ContractParams p) {
   const long long w = (long long)blockIdx.x * SC_THREADS + threadIdx.x;
   if (w >= p.S) return;
@@ -125,15 +128,158 @@ __global__ void __launch_bounds__(SC_THREADS) spec_contract_kernel(ContractParam
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ shared-memory tiled
+// Generic per-bin contraction  Out[i][j][w] = out_scale * sum_r P(i,r)[w] * Q(j,r)[w]  (+ out_bias[i] at w == 0)
+//   P(i,r) = p_scale * (P0 - P1)[i*psi + r*psr + w]            (conjugated when conjP)
+//   Q(j,r) = q_scale * (Q0 - Q1)[j*qsi + r*qsr + w] + [w==0] q_bias[j]   (conjugated when conjQ)
+// used for both the channel contraction (i = output channel, j = frame, r = input channel) and the frame-reduced
+// outer products of the gradients (i, j = channels, r = frame).  The 4x4-register-tile kernels above re-read every
+// operand O/4 resp. B/4 times through L2 (8.7 GB per launch at 32->64 channels, 128 frames): they are L2-bandwidth
+// bound at ~1.1 TB/s algorithmic.  Here a CTA owns 32 consecutive bins x 16 i x 16 j, stages 4 reduction steps of both
+// operands in shared memory with coalesced 256-byte rows, and every thread keeps a 4 (i) x 8 (j) complex register
+// tile for its bin: operands are re-read 8x less often and the inner loop is 12 shared loads per 128 FMAs.
+constexpr int ST_BINS = 32, ST_I = 16, ST_J = 16, ST_R = 4, ST_THREADS = 256;
+
+struct TiledParams {
+  const float2 *P0, *P1, *Q0, *Q1;
+  const float *q_bias, *out_bias;
+  float2* out;
+  long long psi, psr, qsi, qsr, osi, osj, S;
+  int nI, nJ, nR, conjP, conjQ;
+  float p_scale, q_scale, out_scale, out_bias_scale, q_bias_scale;
+};
+
+__global__ void __launch_bounds__(ST_THREADS, 2) spec_tiled_kernel(TiledParams p) {
+  __shared__ float2 Ps[ST_R][ST_I][ST_BINS];
+  __shared__ float2 Qs[ST_R][ST_J][ST_BINS];
+  const int tid = threadIdx.x, bin = tid & 31, g = tid >> 5;
+  const int ig = g & 3, jg = g >> 2;  // 4 i-groups of 4, 2 j-groups of 8
+  const long long w0 = (long long)blockIdx.x * ST_BINS;
+  const int i0 = blockIdx.y * ST_I, j0 = blockIdx.z * ST_J;
+  float2 acc[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 8; b++) acc[a][b] = make_float2(0.f, 0.f);
+  for (int r0 = 0; r0 < p.nR; r0 += ST_R) {
+    // stage ST_R*(ST_I+ST_J) = 128 rows of 32 bins, one warp per row, 16 rows per warp: all 16 (32 with a second source)
+    // global loads of a thread are issued before the first use (the stage is latency bound otherwise)
+    {
+      const long long w = w0 + bin;
+      float2 v[16];
+#pragma unroll
+      for (int t = 0; t < 16; t++) {
+        const int row = g + 8 * t;              // t < 8: P rows, t >= 8: Q rows (ST_R * ST_I == 64)
+        const bool isP = t < 8;
+        const int rl = isP ? row : row - ST_R * ST_I;
+        const int rr = rl / ST_I, k = rl - rr * ST_I;   // ST_I == ST_J
+        const int r = r0 + rr;
+        const int lim = isP ? p.nI : p.nJ, base = isP ? i0 : j0;
+        const bool ok = r < p.nR && base + k < lim && w < p.S;
+        const long long off = isP ? (long long)(i0 + k) * p.psi + (long long)r * p.psr + w
+                                  : (long long)(j0 + k) * p.qsi + (long long)r * p.qsr + w;
+        const float2* s0 = isP ? p.P0 : p.Q0;
+        v[t] = ok ? __ldg(s0 + off) : make_float2(0.f, 0.f);
+      }
+      if (p.P1 || p.Q1) {
+#pragma unroll
+        for (int t = 0; t < 16; t++) {
+          const int row = g + 8 * t;
+          const bool isP = t < 8;
+          const int rl = isP ? row : row - ST_R * ST_I;
+          const int rr = rl / ST_I, k = rl - rr * ST_I;
+          const int r = r0 + rr;
+          const int lim = isP ? p.nI : p.nJ, base = isP ? i0 : j0;
+          const float2* s1 = isP ? p.P1 : p.Q1;
+          if (s1 && r < p.nR && base + k < lim && w < p.S) {
+            const long long off = isP ? (long long)(i0 + k) * p.psi + (long long)r * p.psr + w
+                                      : (long long)(j0 + k) * p.qsi + (long long)r * p.qsr + w;
+            const float2 u = __ldg(s1 + off);
+            v[t].x -= u.x; v[t].y -= u.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 16; t++) {
+        const int row = g + 8 * t;
+        const bool isP = t < 8;
+        const int rl = isP ? row : row - ST_R * ST_I;
+        const int rr = rl / ST_I, k = rl - rr * ST_I;
+        float2 x = v[t];
+        if (isP) {
+          x.x *= p.p_scale; x.y *= p.p_scale;
+          if (p.conjP) x.y = -x.y;
+          Ps[rr][k][bin] = x;
+        } else {
+          x.x *= p.q_scale; x.y *= p.q_scale;
+          if (w == 0 && p.q_bias && j0 + k < p.nJ && r0 + rr < p.nR) x.x = fmaf(p.q_bias[j0 + k], p.q_bias_scale, x.x);
+          if (p.conjQ) x.y = -x.y;
+          Qs[rr][k][bin] = x;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < ST_R; rr++) {
+      float2 pv[4], qv[8];
+#pragma unroll
+      for (int a = 0; a < 4; a++) pv[a] = Ps[rr][ig * 4 + a][bin];
+#pragma unroll
+      for (int b = 0; b < 8; b++) qv[b] = Qs[rr][jg * 8 + b][bin];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) cfma(acc[a][b], pv[a], qv[b]);
+    }
+    __syncthreads();
+  }
+  const long long w = w0 + bin;
+  if (w >= p.S) return;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int i = i0 + ig * 4 + a;
+    if (i >= p.nI) continue;
+    const float ob = (w == 0 && p.out_bias) ? p.out_bias[i] * p.out_bias_scale : 0.f;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const int j = j0 + jg * 8 + b;
+      if (j >= p.nJ) continue;
+      p.out[(long long)i * p.osi + (long long)j * p.osj + w] = make_float2(fmaf(acc[a][b].x, p.out_scale, ob), acc[a][b].y * p.out_scale);
+    }
+  }
+}
+
+static int launch_spec_tiled(aefft_ctx* ctx, const TiledParams& p) {
+  dim3 grid((unsigned)((p.S + ST_BINS - 1) / ST_BINS), (p.nI + ST_I - 1) / ST_I, (p.nJ + ST_J - 1) / ST_J);
+  AE_ARG(grid.y <= 65535 && grid.z <= 65535);
+  spec_tiled_kernel<<<grid, ST_THREADS, 0, ctx->stream>>>(p);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
 int launch_spec_contract(aefft_ctx* ctx, int64_t B, int C, int O, int64_t S, const float2* in0, const float2* in1,
                          const float2* W, int64_t w_so, int64_t w_sc, int conjW, float in_scale, const float* bias,
                          float bias_scale, float2* out) {
   AE_ARG(B > 0 && C > 0 && O > 0 && S > 0);
   ContractParams p{in0, in1, W, bias, out, w_so, w_sc, S, (int)B, C, O, conjW, in_scale, bias_scale};
-  dim3 grid((unsigned)((S + SC_THREADS - 1) / SC_THREADS), (O + SC_OT - 1) / SC_OT, (unsigned)((B + SC_FT - 1) / SC_FT));
+  if (O >= 8 && B >= 8 && !getenv("AEFFT_NO_SPEC_TILED")) {
+    // i = output channel (P = W), j = frame (Q = in), r = input channel
+    TiledParams t{W, nullptr, in0, in1, nullptr, bias, out, w_so, w_sc, (long long)C * S, S, S, (long long)O * S, S,
+                  O, (int)B, C, conjW, 0, 1.f, in_scale, 1.f, bias_scale, 0.f};
+    ProfScope prof(ctx, "spec_contract", 8.0 * B * C * O * S, 8.0 * S * ((double)B * C * (in1 ? 2 : 1) + (double)B * O + (double)C * O));
+    return launch_spec_tiled(ctx, t);
+  }
+  // register tile per thread (one bin): 8 outputs x 8 frames when both extents allow it (16 loads feed 64 complex FMAs
+  // and every operand is re-read 2x less often), else 4 x 4
+  const bool big = false;  // 8x8 register tiles measured slower (226 registers, occupancy); see spec_tiled_kernel
+  const int ot = big ? 8 : SC_OT, ft = big ? 8 : SC_FT;
+  dim3 grid((unsigned)((S + SC_THREADS - 1) / SC_THREADS), (O + ot - 1) / ot, (unsigned)((B + ft - 1) / ft));
   AE_ARG(grid.z <= 65535 && grid.y <= 65535);
   ProfScope prof(ctx, "spec_contract", 8.0 * B * C * O * S, 8.0 * S * ((double)B * C * (in1 ? 2 : 1) + (double)B * O + (double)C * O));
-  spec_contract_kernel<<<grid, SC_THREADS, 0, ctx->stream>>>(p);
+  if (big) spec_contract_kernel<8, 8><<<grid, SC_THREADS, 0, ctx->stream>>>(p);
+  else spec_contract_kernel<SC_OT, SC_FT><<<grid, SC_THREADS, 0, ctx->stream>>>(p);
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
   return AEFFT_OK;
@@ -157,6 +303,7 @@ struct OuterParams {
   float bm_alpha, bm_bias_scale, scale;
 };
 
+template <int SO_AT, int SO_CT>
 __global__ void __launch_bounds__(SC_THREADS) spec_outer_kernel(OuterParams p) {
   const long long w = (long long)blockIdx.x * SC_THREADS + threadIdx.x;
   if (w >= p.S) return;
@@ -204,11 +351,21 @@ __global__ void __launch_bounds__(SC_THREADS) spec_outer_kernel(OuterParams p) {
 int launch_spec_outer(aefft_ctx* ctx, int64_t B, int nA, int nC, int64_t S, const float2* A0, const float2* A1,
                       const float2* Bm, float bm_alpha, const float* bm_bias, float bm_bias_scale, float scale, float2* out) {
   AE_ARG(B > 0 && nA > 0 && nC > 0 && S > 0);
+  if (nA >= 8 && nC >= 8 && !getenv("AEFFT_NO_SPEC_TILED")) {
+    // i = a (P = A), j = c (Q = Bm, conjugated, + bias at DC), r = frame
+    TiledParams t{A0, A1, Bm, nullptr, bm_bias, nullptr, out, S, (long long)nA * S, S, (long long)nC * S, (long long)nC * S, S, S,
+                  nA, nC, (int)B, 0, 1, 1.f, bm_alpha, scale, 0.f, bm_bias_scale};
+    ProfScope prof(ctx, "spec_outer", 8.0 * B * nA * nC * S, 8.0 * S * ((double)B * nA * (A1 ? 2 : 1) + (double)B * nC + (double)nA * nC));
+    return launch_spec_tiled(ctx, t);
+  }
   OuterParams p{A0, A1, Bm, bm_bias, out, S, (int)B, nA, nC, bm_alpha, bm_bias_scale, scale};
-  dim3 grid((unsigned)((S + SC_THREADS - 1) / SC_THREADS), (nA + SO_AT - 1) / SO_AT, (nC + SO_CT - 1) / SO_CT);
+  const bool big = false;
+  const int at = big ? 8 : SO_AT, ct = big ? 8 : SO_CT;
+  dim3 grid((unsigned)((S + SC_THREADS - 1) / SC_THREADS), (nA + at - 1) / at, (nC + ct - 1) / ct);
   AE_ARG(grid.z <= 65535 && grid.y <= 65535);
   ProfScope prof(ctx, "spec_outer", 8.0 * B * nA * nC * S, 8.0 * S * ((double)B * nA * (A1 ? 2 : 1) + (double)B * nC + (double)nA * nC));
-  spec_outer_kernel<<<grid, SC_THREADS, 0, ctx->stream>>>(p);
+  if (big) spec_outer_kernel<8, 8><<<grid, SC_THREADS, 0, ctx->stream>>>(p);
+  else spec_outer_kernel<SO_AT, SO_CT><<<grid, SC_THREADS, 0, ctx->stream>>>(p);
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
   return AEFFT_OK;
