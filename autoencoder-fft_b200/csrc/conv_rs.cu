@@ -85,6 +85,7 @@ __global__ void conv_rs_weight_prep_kernel(const float* __restrict__ w, long lon
   }
 }
 
+template <bool DBG>
 __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_constant__ ConvRsParams p) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_full[RS_NSF], s_empty[RS_NSF], xb_full[RS_MAXSB], xb_empty[RS_MAXSB],
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
   __syncthreads();
   fence_after_sync();
   long long wA = 0, wB = 0, wC = 0;
-  const long long t_start = clock64();
+  const long long t_start = DBG ? clock64() : 0;
 
   const int n_items = p.items, cpj = p.cpj;
   const int G = p.G, PJs = p.PJs, NK = p.NK;
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         const int n_in = nrows + NK - 1;
         const int nseg = min(G, p.n_sub - ug * G);
         for (int k = 0; k < n_in; k++) {
-          wait_t(&s_empty[ss.slot], ss.phase ^ 1, wA);
+          wait_t<DBG>(&s_empty[ss.slot], ss.phase ^ 1, wA);
           unsigned char* dst = x_ring + (size_t)ss.slot * p.x_slot_bytes;
           mbar_expect_tx(&s_full[ss.slot], seg_tx * nseg * (p.has_x1 ? 2 : 1));
           for (int g = 0; g < nseg; g++) {
@@ -188,14 +189,14 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
       const int nrows = min(p.BR, p.Nx - i0);
       const int n_in = nrows + NK - 1;
       for (int k = 0; k < n_in; k++) {
-        wait_t(&xb_full[rx.slot], rx.phase, wA);
+        wait_t<DBG>(&xb_full[rx.slot], rx.phase, wA);
         if (k < nrows) {
           // the accumulator slot of the newest output row (rho = k) must have been drained and zeroed
-          wait_t(&acc_empty[rn.slot], rn.phase ^ 1, wB);
+          wait_t<DBG>(&acc_empty[rn.slot], rn.phase ^ 1, wB);
           rn.next();
         }
         fence_after_sync();
-        const long long t_m0 = clock64();
+        const long long t_m0 = DBG ? clock64() : 0;
         // pieces: output rows rho_lo..rho_hi (ascending) = window rows tk_hi..tk_lo, split at the ring wrap and at N = 256
         const int tk_lo = max(0, k - nrows + 1), tk_hi = min(NK - 1, k);
         int pc_n0[4], pc_N[4], pc_d[4], npc = 0;
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
             }
           }
         }
-        wC += clock64() - t_m0;
+        if (DBG) wC += clock64() - t_m0;
         if (elect_one()) {
           commit(&xb_empty[rx.slot]);
           const int done = k - NK + 1;  // output row completed by this input row
@@ -294,8 +295,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
       const int n_in = nrows + NK - 1;
       const int nseg = min(G, p.n_sub - ug * G);
       for (int k = 0; k < n_in; k++) {
-        wait_t(&s_full[ss.slot], ss.phase, wA);
-        wait_t(&xb_empty[sb.slot], sb.phase ^ 1, wB);
+        wait_t<DBG>(&s_full[ss.slot], ss.phase, wA);
+        wait_t<DBG>(&xb_empty[sb.slot], sb.phase ^ 1, wB);
         const unsigned char* xs = x_ring + (size_t)ss.slot * p.x_slot_bytes;
         for (int idx = t; idx < n_it; idx += NT) {
           const int pl = idx >> 7, px = idx & 127;
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
       const bool lane_ok = u < p.n_sub && c < p.TJ && j0 + c < p.Ny;
       float* obase = p.out + ((long long)b * p.O + o0) * plane + (long long)i0 * p.Ny + j0 + c;
       for (int rho = 0; rho < nrows; rho++) {
-        wait_t(&acc_full[slot], phase, wA);
+        wait_t<DBG>(&acc_full[slot], phase, wA);
         fence_after_sync();
         float* orow = obase + (long long)rho * p.Ny;
         for (int c0 = 0; c0 < p.O_pad; c0 += 16) {
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
       }
     }
   }
-  if (p.dbg && lane == 0) {
+  if (DBG && p.dbg && lane == 0) {
     long long* d = p.dbg + ((long long)(blockIdx.y * gridDim.x + blockIdx.x) * 12 + warp) * 4;
     d[0] = wA; d[1] = wB; d[2] = clock64() - t_start; d[3] = wC;
   }
@@ -491,14 +492,16 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
   }
   static size_t attr = 0;
   if (smem > attr) {
-    AE_CUDA(cudaFuncSetAttribute(conv_rs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AE_CUDA(cudaFuncSetAttribute(conv_rs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AE_CUDA(cudaFuncSetAttribute(conv_rs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   {
     const double px = (double)B * Nx * Ny;
     ProfScope prof(ctx, win.flip ? "conv_fwd_rs" : "conv_dgrad_rs", 2.0 * px * C * O * win.Nk * win.Nl,
                    4.0 * (px * C * (src1 ? 2 : 1) + px * O + (double)C * O * win.Nk * win.Nl));
-    conv_rs_kernel<<<dim3(cpj, p.n_jobs), RS_THREADS, smem, ctx->stream>>>(p);
+    if (debug) conv_rs_kernel<true><<<dim3(cpj, p.n_jobs), RS_THREADS, smem, ctx->stream>>>(p);
+    else conv_rs_kernel<false><<<dim3(cpj, p.n_jobs), RS_THREADS, smem, ctx->stream>>>(p);
   }
   ctx->launches++;
   AE_CUDA(cudaGetLastError());

@@ -41,10 +41,16 @@ struct Ring {
   }
 };
 
+// barrier wait; with DBG the cycles spent waiting are accumulated (role-stall attribution, AEFFT_*_DEBUG=1)
+template <bool DBG>
 __device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
-  const long long t0 = clock64();
-  mbar_wait(bar, parity);
-  acc += clock64() - t0;
+  if (DBG) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+  } else {
+    mbar_wait(bar, parity);
+  }
 }
 
 }  // namespace aefft

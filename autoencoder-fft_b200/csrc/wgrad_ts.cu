@@ -68,6 +68,7 @@ struct WgradTsParams {
   long long* dbg;  // AEFFT_TS_DEBUG: [cta][warp][4] cycles (wait A, wait B, total, -)
 };
 
+template <bool DBG>
 __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_constant__ WgradTsParams p) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t u_full[TS_MAXRING], u_empty[TS_MAXRING], s_full[TS_NSF], s_empty[TS_NSF],
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
   __syncthreads();
   fence_after_sync();
   long long wA = 0, wB = 0, wC = 0;
-  const long long t_start = clock64();
+  const long long t_start = DBG ? clock64() : 0;
 
   const int items_per_frame = p.strips * p.bands;
   const int Rmax = (p.NR - 1) * p.RS;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
         const int n_srows = nrows + p.RS - 1 + Rmax;
         for (int k = 0; k < n_srows; k++) {
           {
-            wait_t(&s_empty[ss.slot], ss.phase ^ 1, wA);
+            wait_t<DBG>(&s_empty[ss.slot], ss.phase ^ 1, wA);
             unsigned char* dst = s_ring + (size_t)ss.slot * p.s_slot_bytes;
             mbar_expect_tx(&s_full[ss.slot], s_bytes);
             tma_load_3d(dst, &J.s0_map, j0 + cs_off, i0 + J.oi + k, b * p.dD + J.ch0, &s_full[ss.slot]);
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
           }
           const int ru = k - Rmax;
           if (ru >= 0 && ru < nrows) {
-            wait_t(&u_empty[su.slot], su.phase ^ 1, wB);
+            wait_t<DBG>(&u_empty[su.slot], su.phase ^ 1, wB);
             unsigned char* dst = u_ring + (size_t)su.slot * p.u_slot_bytes;
             mbar_expect_tx(&u_full[su.slot], p.u_slot_bytes);
             for (int sub = 0; sub < p.PJ / 32; sub++)
@@ -198,15 +199,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
         // also for K-rows whose chunks belong to other issuers: a parity wait is only sound for a waiter that is neither
         // ahead of the previous phase nor lapped, which in-order waiting + all-issuer release guarantee.
         for (; sb_row < r + Rmax + 1; sb_row++) {
-          wait_t(&sb_full[rw.slot], rw.phase, wA);
+          wait_t<DBG>(&sb_full[rw.slot], rw.phase, wA);
           rw.next();
         }
         for (int h = 0; h < CPR; h++, cc4 = (cc4 + 1) & (TS_NI - 1)) {
           const bool mine = !by_chunk || cc4 == q;
           if (mine) {
-            wait_t(&a_full[ra.slot], ra.phase, wB);
+            wait_t<DBG>(&a_full[ra.slot], ra.phase, wB);
             fence_after_sync();
-            const long long t_m0 = clock64();
+            const long long t_m0 = DBG ? clock64() : 0;
             const uint32_t a_base = tb + (uint32_t)(p.Acol0 + ra.slot * 64);
             if (elect_one()) {
               // one lane walks the (K-step, window-row group, plane) nest; operands advance by constant increments
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
               }
             }
             __syncwarp();
-            wC += clock64() - t_m0;
+            if (DBG) wC += clock64() - t_m0;
             if (elect_one()) commit(&a_empty[ra.slot]);
           }
           ra.next();
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
       // S rows that were only ever read at a window-row offset (by_acc only: Rmax == 0 in by_chunk mode)
       for (int k = n_krows; k < n_srows; k++) {
         for (; sb_row < k + 1; sb_row++) {
-          wait_t(&sb_full[rw.slot], rw.phase, wA);
+          wait_t<DBG>(&sb_full[rw.slot], rw.phase, wA);
           rw.next();
         }
         if (elect_one()) commit(&sb_empty[s0slot]);
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
       const int nrows = min(p.BR, p.Nx - i0);
       const int n_srows = nrows + p.RS - 1 + Rmax;
       for (int k = 0; k < n_srows; k++) {
-        wait_t(&s_full[ss.slot], ss.phase, wA);
-        wait_t(&sb_empty[sb.slot], sb.phase ^ 1, wB);
+        wait_t<DBG>(&s_full[ss.slot], ss.phase, wA);
+        wait_t<DBG>(&sb_empty[sb.slot], sb.phase ^ 1, wB);
         const float* s0 = reinterpret_cast<const float*>(s_ring + (size_t)ss.slot * p.s_slot_bytes);
         const float* s1 = reinterpret_cast<const float*>(s_ring + (size_t)ss.slot * p.s_slot_bytes + p.s_src_bytes);
         const bool own_row = is_gf && (k + oi >= 0) && (k + oi < nrows);
@@ -386,12 +387,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
               int g = row_base + oldest;
               if (g > w_row) { rw.skip(g - w_row); w_row = g; }
               for (; w_row <= row_base + newest; w_row++) {
-                wait_t(&u_full[rw.slot], rw.phase, wA);
+                wait_t<DBG>(&u_full[rw.slot], rw.phase, wA);
                 rw.next();
               }
             }
           }
-          wait_t(&a_empty[ca], (uint32_t)ca_phase ^ 1, wB);
+          wait_t<DBG>(&a_empty[ca], (uint32_t)ca_phase ^ 1, wB);
           fence_after_sync();
           const int ru = r - rho;
           const bool valid = ru >= 0 && ru < nrows;
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
       }
     }
   }
-  if (p.dbg && lane == 0) {
+  if (DBG && p.dbg && lane == 0) {
     long long* d = p.dbg + ((long long)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + warp) * 4;
     d[0] = wA; d[1] = wB; d[2] = clock64() - t_start; d[3] = wC;
   }
@@ -619,13 +620,15 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   }
   static size_t attr = 0;
   if (smem > attr) {
-    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   {
     const double px = (double)B * Nx * Ny;
     ProfScope prof(ctx, "wgrad_ts", 2.0 * 2.0 * px * dM * dD * T, 4.0 * px * (3.0 * dD + 2.0 * dM));
-    wgrad_ts_kernel<<<dim3(cpj, p.n_jobs), TS_THREADS, smem, ctx->stream>>>(p);
+    if (debug) wgrad_ts_kernel<true><<<dim3(cpj, p.n_jobs), TS_THREADS, smem, ctx->stream>>>(p);
+    else wgrad_ts_kernel<false><<<dim3(cpj, p.n_jobs), TS_THREADS, smem, ctx->stream>>>(p);
   }
   wgrad_ts_reduce_kernel<<<(unsigned)((p.n_main + 1 + 255) / 256), 256, 0, ctx->stream>>>(part, cpj, p.n_tot, p.n_main, p.n_jobs,
                                                                                           2 * nC, dM, dD, G, GB, GP, SQ);
