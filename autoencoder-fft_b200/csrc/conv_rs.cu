@@ -49,6 +49,7 @@ struct ConvRsParams {
   int PJs, G, TJ, strips, bands, BR;
   int n_sub, items, cpj;
   int KS, NP, kpack, NLg, Ntot, Rr, NSB, NSF, passes;
+  int stack2, CW;  // stack2: B rows = [W_hi | W_lo] per window row (2 MMAs instead of 3); CW = accumulator columns per output row
   uint32_t w_bytes, seg_bytes, src_bytes, x_slot_bytes, sb_pitch;
   uint32_t off_w, off_x, off_sb;
   long long* dbg;
@@ -56,7 +57,7 @@ struct ConvRsParams {
 
 __global__ void conv_rs_weight_prep_kernel(const float* __restrict__ w, long long w_so, long long w_sc, int C, int O, int Oj,
                                            int O_pad, int NK, int NL, int NLg, int flip, int KS, int kpack, int n_jobs,
-                                           __nv_bfloat16* __restrict__ wprep) {
+                                           int stack2, __nv_bfloat16* __restrict__ wprep) {
   const int Ntot = NK * O_pad;
   const long long per_part = (long long)NLg * 2 * Ntot * 8;
   const long long per_job = (long long)KS * 2 * per_part;
@@ -78,10 +79,19 @@ __global__ void conv_rs_weight_prep_kernel(const float* __restrict__ w, long lon
     if (c < C && o < Oj && og < O && tl < NL) v = w[og * w_so + c * w_sc + k * NL + l];
     __nv_bfloat16 hi, lo;
     split_bf16(v, hi, lo);
-    const long long within = (((long long)tlg * 2 + kchunk) * Ntot + n) * 8 + e;
-    const long long base = (long long)job * per_job + (long long)ks * 2 * per_part + within;
-    wprep[base] = hi;
-    wprep[base + per_part] = lo;
+    if (stack2) {
+      // rows [tk descending][hi | lo][o]: one B operand yields A*W_hi and A*W_lo in adjacent accumulator columns
+      const int tkd = n / O_pad;
+      const long long row_hi = (long long)(tkd * 2) * O_pad + o, rows = 2LL * Ntot;
+      const long long base = (long long)job * per_job + (long long)ks * 2 * per_part + (((long long)tlg * 2 + kchunk) * rows) * 8 + e;
+      wprep[base + row_hi * 8] = hi;
+      wprep[base + (row_hi + O_pad) * 8] = lo;
+    } else {
+      const long long within = (((long long)tlg * 2 + kchunk) * Ntot + n) * 8 + e;
+      const long long base = (long long)job * per_job + (long long)ks * 2 * per_part + within;
+      wprep[base] = hi;
+      wprep[base + per_part] = lo;
+    }
   }
 }
 
@@ -126,7 +136,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     uint32_t z[16];
 #pragma unroll
     for (int e = 0; e < 16; e++) z[e] = 0u;
-    for (int c0 = 0; c0 < p.Rr * p.O_pad; c0 += 16) tmem_st16(tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, z);
+    for (int c0 = 0; c0 < p.Rr * p.CW; c0 += 16) tmem_st16(tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0, z);
     tmem_wait_st();
   }
   fence_before_sync();
@@ -173,13 +183,15 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     // ============================================================ MMA issuer (whole warp runs the loops, one lane issues)
     const uint32_t sb_base = smem_u32(sb_ring), w_base = smem_u32(w_sm);
     const uint32_t pitch = p.sb_pitch;
-    const int NSB = p.NSB, NP = p.NP, KS = p.KS, NLg = p.NLg, Rr = p.Rr, O_pad = p.O_pad, Ntot = p.Ntot;
+    const int NSB = p.NSB, NP = p.NP, KS = p.KS, NLg = p.NLg, Rr = p.Rr, CW = p.CW;
+    const bool stack2 = p.stack2 != 0;
+    const int Ntot = stack2 ? 2 * p.Ntot : p.Ntot;  // B rows per K chunk
     const uint32_t a_lbo = p.kpack ? 16u : (uint32_t)NSB * pitch;
     const uint64_t a_desc0 = make_desc(0, a_lbo, 128), b_desc0 = make_desc(0, (uint32_t)Ntot * 16, 128);
     const uint32_t part_off16 = ((uint32_t)(NP * NSB) * pitch) >> 4;               // A: hi -> lo part
-    const uint32_t wpart_off16 = (uint32_t)(NLg * 2 * Ntot);                       // W: hi -> lo part (16-byte units)
+    const uint32_t wpart_off16 = (uint32_t)(NLg * 2 * Ntot);                       // W: hi -> lo part (16-byte units; !stack2)
     const bool three = p.passes == 3;
-    const int maxchunks = 256 / O_pad;
+    const int maxchunks = 256 / CW;
     Ring rx(NSB);
     Ring rn(Rr);  // accumulator ring position of the newest output row (rho = k)
     int gro = 0;  // accumulator slot of output row 0 of the current item
@@ -210,9 +222,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
               int len = rho_hi - rho + 1;
               if (len > Rr - slot) len = Rr - slot;
               if (len > maxchunks) len = maxchunks;
-              pc_n0[i] = (NK - 1 - k + rho) * O_pad;
-              pc_N[i] = len * O_pad;
-              pc_d[i] = slot * O_pad;
+              pc_n0[i] = (NK - 1 - k + rho) * CW;
+              pc_N[i] = len * CW;
+              pc_d[i] = slot * CW;
               rho += len;
               slot += len;
               if (slot >= Rr) slot -= Rr;
@@ -223,7 +235,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         const uint32_t a_row16 = (sb_base + (uint32_t)rx.slot * pitch) >> 4;
         const uint32_t a_ks_step16 = p.kpack ? 0u : (((uint32_t)(2 * NSB) * pitch) >> 4);
         const uint32_t a_tl_step16 = p.kpack ? 2u : 1u;
-        const uint32_t w_ks_step16 = (uint32_t)(2 * NLg * 2 * Ntot), w_tl_step16 = (uint32_t)(2 * Ntot);
+        const uint32_t w_ks_step16 = (uint32_t)((stack2 ? 1 : 2) * NLg * 2 * Ntot), w_tl_step16 = (uint32_t)(2 * Ntot);
         if (npc == 1) {
           // common case (no ring wrap inside the stack): one elected lane walks the descriptors with constant increments
           if (elect_one()) {
@@ -237,7 +249,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
 #pragma unroll 1
               for (int tlg = 0; tlg < NLg; tlg++, a_hi += a_tl_step16, b_hi += w_tl_step16) {
                 mma_bf16(d, a_hi, b_hi, idesc, true);
-                if (three) {
+                if (stack2) {
+                  mma_bf16(d, a_hi + (uint64_t)part_off16, b_hi, idesc, true);
+                } else if (three) {
                   mma_bf16(d, a_hi, b_hi + (uint64_t)wpart_off16, idesc, true);
                   mma_bf16(d, a_hi + (uint64_t)part_off16, b_hi, idesc, true);
                 }
@@ -262,7 +276,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
                   const uint32_t d = tb + (uint32_t)pc_d[i];
                   if (elect_one()) {
                     mma_bf16(d, a_hi, b_hi, idesc, true);
-                    if (three) {
+                    if (stack2) {
+                      mma_bf16(d, a_lo, b_hi, idesc, true);
+                    } else if (three) {
                       mma_bf16(d, a_hi, b_lo, idesc, true);
                       mma_bf16(d, a_lo, b_hi, idesc, true);
                     }
@@ -360,8 +376,15 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         float* orow = obase + (long long)rho * p.Ny;
         for (int c0 = 0; c0 < p.O_pad; c0 += 16) {
           float v[16];
-          tmem_ld16(t_lane + (uint32_t)(slot * p.O_pad + c0), v);
-          tmem_st16(t_lane + (uint32_t)(slot * p.O_pad + c0), z);
+          tmem_ld16(t_lane + (uint32_t)(slot * p.CW + c0), v);
+          tmem_st16(t_lane + (uint32_t)(slot * p.CW + c0), z);
+          if (p.stack2) {  // (A_hi + A_lo) W_hi  +  (A_hi + A_lo) W_lo
+            float u[16];
+            tmem_ld16(t_lane + (uint32_t)(slot * p.CW + p.O_pad + c0), u);
+            tmem_st16(t_lane + (uint32_t)(slot * p.CW + p.O_pad + c0), z);
+#pragma unroll
+            for (int e = 0; e < 16; e++) v[e] += u[e];
+          }
           if (lane_ok) {
 #pragma unroll
             for (int e = 0; e < 16; e++) {
@@ -425,13 +448,18 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
     for (int split = 1; split <= 8 && !found; split++) {
       const int Oj = ((O + split - 1) / split + 15) / 16 * 16;
       const int O_pad = Oj;
-      const int Rr = 512 / O_pad > RS_MAXACC ? RS_MAXACC : 512 / O_pad;
+      // [W_hi | W_lo] stacking (2 MMAs of 2N instead of 3 of N) measured no faster on B200 (the N = 80 MMAs are not purely
+      // A-read bound): opt-in for experiments only
+      const int stack2 = (getenv("AEFFT_RS_STACK2") && passes == 3 && 2 * win.Nk * O_pad <= 256) ? 1 : 0;
+      const int CW = stack2 ? 2 * O_pad : O_pad;
+      const int Rr = 512 / CW > RS_MAXACC ? RS_MAXACC : 512 / CW;
       if (Rr < win.Nk + 1) continue;
       const size_t w_bytes = (size_t)p.KS * 2 * p.NLg * 2 * (win.Nk * O_pad) * 16;
       for (int NSB = 4; NSB >= 2 && !found; NSB--) {
         const size_t sb_bytes = (size_t)2 * p.NP * NSB * p.sb_pitch;
         if (w_bytes + x_bytes + sb_bytes + 3 * 1024 <= budget) {
           p.Oj = Oj; p.O_pad = O_pad; p.Rr = Rr; p.NSB = NSB; p.NSF = NSF; p.w_bytes = (uint32_t)w_bytes;
+          p.stack2 = stack2; p.CW = CW;
           p.n_jobs = (O + Oj - 1) / Oj;
           found = 1;
         }
@@ -478,7 +506,7 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
     const long long total = w_elems / 2;
     const unsigned blocks = (unsigned)((total + 255) / 256 > 1024 ? 1024 : (total + 255) / 256);
     conv_rs_weight_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(w, w_so, w_sc, C, O, p.Oj, p.O_pad, win.Nk, win.Nl, p.NLg,
-                                                               win.flip, p.KS, p.kpack, p.n_jobs,
+                                                               win.flip, p.KS, p.kpack, p.n_jobs, p.stack2,
                                                                reinterpret_cast<__nv_bfloat16*>(wprep));
     ctx->launches++;
   }
