@@ -446,6 +446,11 @@ class Net:
                                          C.byref(mse) if want_mse else None))
         return float(mse.value)
 
+    def set_frames_u8(self, images, loc=HOST):
+        """ImageToSpin_C on the device: images uint8 [B][Ny][Nx][D] (numpy array, or a raw address with loc)."""
+        ptr = images.ctypes.data if isinstance(images, np.ndarray) else int(images)
+        _chk(lib().aefft_net_set_frames_u8(self.h, loc, C.c_void_p(ptr)))
+
     def step(self, frames, mode, delmax=0.2, alpha=0.9, quirks=QUIRKS_ALL, loc=HOST, mse=None):
         _chk(lib().aefft_net_step(self.h, loc, _ptr(frames), mode, quirks, C.c_float(delmax), C.c_float(alpha),
                                   _ptr(mse)))

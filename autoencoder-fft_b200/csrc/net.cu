@@ -250,6 +250,53 @@ int aefft_net_layer(aefft_net* net, int l, int* D, int* Nx, int* Ny, float** dev
 
 int aefft_net_num_layers(const aefft_net* net) { return net ? (int)net->layers.size() : -1; }
 
+
+// ImageToSpin_C: img[b][j][i][d] (bytes) -> spin[b][d][i][j] (float).  32 x 32 (i, j) tiles through shared memory so that
+// both the byte reads (contiguous in i,d) and the float writes (contiguous in j) are coalesced.
+}  // extern "C"
+
+__global__ void image_to_spin_kernel(const unsigned char* __restrict__ img, float* __restrict__ spin, int D, int Nx, int Ny) {
+  __shared__ unsigned char tile[32][32 * 4 + 4];  // [j][i*D + d], D <= 4
+  const long long b = blockIdx.z;
+  const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  const unsigned char* src = img + b * (long long)Ny * Nx * D;
+  const int wbytes = 32 * D;
+  for (int idx = threadIdx.x; idx < 32 * wbytes; idx += blockDim.x) {
+    const int j = idx / wbytes, x = idx - j * wbytes;
+    const long long col = (long long)i0 * D + x;
+    tile[j][x] = (j0 + j < Ny && col < (long long)Nx * D) ? src[(long long)(j0 + j) * Nx * D + col] : 0;
+  }
+  __syncthreads();
+  float* dst = spin + b * (long long)D * Nx * Ny;
+  for (int idx = threadIdx.x; idx < D * 32 * 32; idx += blockDim.x) {
+    const int j = idx & 31, i = (idx >> 5) & 31, d = idx >> 10;
+    if (i0 + i < Nx && j0 + j < Ny) dst[((long long)d * Nx + i0 + i) * Ny + j0 + j] = (float)tile[j][i * D + d];
+  }
+}
+
+extern "C" {
+
+int aefft_net_set_frames_u8(aefft_net* net, int loc, const unsigned char* images) {
+  AE_ARG(net && images);
+  aefft_ctx* ctx = net->ctx;
+  AE_CUDA(cudaSetDevice(ctx->device));
+  LayerL& L0 = net->layers[0];
+  AE_ARG(L0.D <= 4 && net->B <= 65535);
+  const size_t nbytes = (size_t)net->B * L0.D * L0.Nx * L0.Ny;
+  const unsigned char* dev = images;
+  if (loc == AEFFT_HOST) {
+    void* stage;
+    AE_TRY(ctx->get("net_frames_u8", nbytes, &stage));
+    AE_CUDA(cudaMemcpyAsync(stage, images, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    dev = (const unsigned char*)stage;
+  }
+  dim3 grid((L0.Nx + 31) / 32, (L0.Ny + 31) / 32, (unsigned)net->B);
+  image_to_spin_kernel<<<grid, 256, 0, ctx->stream>>>(dev, L0.p, L0.D, L0.Nx, L0.Ny);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
 // forward, coordinate space (autoencoder.cpp:135-150)
 int aefft_net_forward(aefft_net* net, int loc, const float* frames) {
   AE_ARG(net && net->convs.size() >= 2);

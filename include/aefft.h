@@ -229,6 +229,11 @@ int aefft_net_num_layers(const aefft_net* net);
 int aefft_net_layer(aefft_net* net, int l, int* D, int* Nx, int* Ny, float** dev_ptr);
 /* forward, coordinate space (autoencoder.cpp:135-150): frames = layer 0 ([B][D][Nx][Ny], per `loc`) */
 int aefft_net_forward(aefft_net* net, int loc, const float* frames);
+/* ImageToSpin_C (netlib.cpp:37-50) on the device: B interleaved 8-bit images [B][rows = Ny][cols = Nx][D] (a cv::Mat's
+ * data for D = 3: B,G,R bytes) become layer 0, spin[d][i][j] = (float)img(row j, col i)[d] -- raw 0..255, not
+ * normalised.  Uploading bytes moves 4x less data over PCIe than float frames; follow with aefft_net_forward /
+ * aefft_net_step with frames == NULL (layer 0 already set). */
+int aefft_net_set_frames_u8(aefft_net* net, int loc, const unsigned char* images);
 /* train pair n_l on the activations of the last forward (autoencoder.cpp:158-201, q=1).  *mse host or NULL. */
 int aefft_net_train_pair(aefft_net* net, int n_l, int mode, int quirks, float delmax, float alpha, float* mse);
 /* raw gradient block of pair n_l into the net's gradient buffer (device ptr returned), then update: the

@@ -347,3 +347,22 @@ def test_data_parallel_split_equals_full_batch(ctx):
     ctx.sync()
     for k in "cbfp":
         assert O.rel_l2(dev[k].numpy(), full[k]) < 1e-6, k
+
+
+def test_image_to_spin_u8_bit_exact(ctx):
+    """aefft_net_set_frames_u8 = ImageToSpin_C (netlib.cpp:37-50): spin[d][i][j] = (float)img(row j, col i)[d]."""
+    B, D, Nx, Ny = 3, 3, 70, 44
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(B, Ny, Nx, D), dtype=np.uint8)
+    net = A.Net(ctx, D, Nx, Ny, B)
+    try:
+        net.add_layer(4, 1, 1, 2, 1.0)
+        net.set_frames_u8(img)
+        ctx.sync()
+        _, _, _, ptr = net.layer_info(0)
+        got = np.empty((B, D, Nx, Ny), np.float32)
+        ctx.memcpy(got.ctypes.data, ptr, got.nbytes, 1)
+    finally:
+        net.close()
+    want = img.transpose(0, 3, 2, 1).astype(np.float32)
+    assert np.array_equal(got, want)
