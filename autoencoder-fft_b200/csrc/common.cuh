@@ -228,6 +228,16 @@ int launch_spec_outer(aefft_ctx* ctx, int64_t B, int nA, int nC, int64_t S, cons
                       const float2* Bm, float bm_alpha, const float* bm_bias, float bm_bias_scale, float scale, float2* out);
 int launch_spec_dc_sums(aefft_ctx* ctx, int64_t B, int dM, int dD, int64_t S, const float2* G, const float2* O,
                         const float2* Xt, float* db, float* dp, float gscale);
+// W_N^t = exp(-2 pi i t / N), t = 0..N-1, computed in double on the host once per length (device table, L1 resident)
+int get_twiddles(aefft_ctx* ctx, int N, const float2** out);
+// Pruned DFTs of the Nk x Nl-tap kernels (replace pad_k + full-size R2C and full-size C2R + shrink_k, which move
+// >= 20 bytes per bin to obtain / consume 25 numbers per image):
+//   spectrum : spec[n][wx][wy] = sum_{k,l} taps[n][k][l] W_Nx^(wx*i_k) W_Ny^(wy*j_l),  (i_k, j_l) = ((k-Nk/2) mod Nx, (l-Nl/2) mod Ny)
+//   taps     : taps[n][k][l] = scale * sum_{wx,wy} h(wy) Re( spec[n][wx][wy] conj(W_Nx^(wx*i_k)) conj(W_Ny^(wy*j_l)) ),
+//              h = 1 for wy in {0, Ny/2}, else 2  (= shrink_k(C2R(spec)) with the C2R's Hermitian convention)
+int launch_kernel_spectrum_direct(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* taps, float2* spec);
+int launch_spectrum_to_taps(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float2* spec, float* taps,
+                            float scale);
 int launch_pad(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* taps, float* img);
 int launch_shrink(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* img, float* taps);
 int launch_fft_update(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, float* c, float* f, float* b, float* p,

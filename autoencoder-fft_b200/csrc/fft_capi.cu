@@ -1,5 +1,6 @@
 // C ABI, momentum (FFT) space: batched transforms, kernel spectra, autoenc_fft and backprop_fft.
 // Host orchestration only; the kernels live in fft_kernels.cu and spectral_kernels.cu.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -12,10 +13,34 @@ namespace aefft {
 static bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
 // C = R2C(pad(c)) for n_img kernels (StoreLoad_cfreq first-time branch, fft_backproplib.cu:1148-1157; backprop :1274-1282)
+// Evaluated directly from the Nk x Nl taps (pruned DFT): mathematically the same spectrum, no padded image, one write.
+// Batches above the grid limit and taps beyond the pruned kernel's envelope go through pad_k + R2C.
 static int kernel_spectrum_dev(aefft_ctx* ctx, int64_t n_img, int Nk, int Nl, int Nx, int Ny, const float* taps, float* img,
                                float2* spec) {
+  if (Nk <= 8 && Nl <= 8 && !getenv("AEFFT_NO_PRUNED_DFT")) {
+    const int64_t S = (int64_t)Nx * (Ny / 2 + 1);
+    for (int64_t n0 = 0; n0 < n_img; n0 += 65535) {
+      const int64_t cnt = n_img - n0 < 65535 ? n_img - n0 : 65535;
+      AE_TRY(launch_kernel_spectrum_direct(ctx, cnt, Nx, Ny, Nk, Nl, taps + n0 * Nk * Nl, spec + n0 * S));
+    }
+    return AEFFT_OK;
+  }
   AE_TRY(launch_pad(ctx, n_img, Nx, Ny, Nk, Nl, taps, img));
   return launch_fft_r2c(ctx, n_img, Nx, Ny, img, spec);
+}
+// taps = scale * shrink_k(C2R(spec)) for n_img spectra
+static int spectrum_taps_dev(aefft_ctx* ctx, int64_t n_img, int Nk, int Nl, int Nx, int Ny, const float2* spec, float2* work,
+                             float* img, float* taps, float scale) {
+  if (Nk <= 8 && Nl <= 8 && !getenv("AEFFT_NO_PRUNED_DFT")) {
+    const int64_t S = (int64_t)Nx * (Ny / 2 + 1);
+    for (int64_t n0 = 0; n0 < n_img; n0 += 65535) {
+      const int64_t cnt = n_img - n0 < 65535 ? n_img - n0 : 65535;
+      AE_TRY(launch_spectrum_to_taps(ctx, cnt, Nx, Ny, Nk, Nl, spec + n0 * S, taps + n0 * Nk * Nl, scale));
+    }
+    return AEFFT_OK;
+  }
+  AE_TRY(launch_fft_c2r(ctx, n_img, Nx, Ny, spec, work, img, scale));
+  return launch_shrink(ctx, n_img, Nx, Ny, Nk, Nl, img, taps);
 }
 
 struct FftPairBufs {
@@ -318,8 +343,7 @@ int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int N
     AE_TRY(launch_spec_outer(ctx, B, dD, dM, S, q.O, Xt, q.H, (float)dM, db_w, -(float)(dM - 1) * norm, gscale, q.dCF + nKS));
     AE_TRY(launch_spec_dc_sums(ctx, B, dM, dD, S, q.G, q.O, Xt, q.db, q.dp, (float)((double)norm / (Norm * (double)B))));
     // kernel-space gradients: C2R (unnormalised) + shrink_k (:1219-1226)
-    AE_TRY(launch_fft_c2r(ctx, 2 * (int64_t)dM * dD, Nx, Ny, q.dCF, q.work, q.img, 1.f));
-    AE_TRY(launch_shrink(ctx, 2 * (int64_t)dM * dD, Nx, Ny, Nk, Nl, q.img, q.taps));
+    AE_TRY(spectrum_taps_dev(ctx, 2 * (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.dCF, q.work, q.img, q.taps, 1.f));
     // data-parallel ranks average the raw gradient block here, before the non-linear clip
     if (ctx->grad_hook && ctx->grad_hook(ctx->grad_hook_user, q.taps, (int64_t)(2 * nC + dM + dD)) != 0) {
       set_error("aefft_backprop_fft: gradient hook failed");
@@ -329,9 +353,8 @@ int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int N
     AE_TRY(launch_fft_update(ctx, dM, dD, Nk, Nl, dc_w, df_w, db_w, dp_w, q.taps, q.taps + nC, q.db, q.dp, q.Dc, q.Df, q.Db,
                              q.Dp, del, maxdiff, q.div));
     // new kernel spectra: pad_k + R2C (:1274-1282); c and f are adjacent in wts -> one batched transform
-    AE_TRY(launch_pad(ctx, 2 * (int64_t)dM * dD, Nx, Ny, Nk, Nl, wts, q.img));
-    AE_TRY(launch_fft_r2c(ctx, (int64_t)dM * dD, Nx, Ny, q.img, q.C));
-    AE_TRY(launch_fft_r2c(ctx, (int64_t)dM * dD, Nx, Ny, q.img + (size_t)dM * dD * P, q.F));
+    AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C));
+    AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F));
     // re-forward (:1460-1461) and mse (:1463)
     AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, db_w, norm, q.H));
     AE_TRY(launch_spec_contract(ctx, B, dM, dD, S, q.H, nullptr, q.F, (int64_t)dM * S, S, 0, 1.f / (float)dD, dp_w, norm, q.O));
@@ -340,9 +363,9 @@ int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int N
   // store_cfreq (:1484-1485) and export_cfreq (:1487-1488: c,f re-derived from the spectra: C2R/(NxNy) + kernel_invpad)
   if (cfreq) AE_CUDA(cudaMemcpyAsync(cfreq, q.C, nKS * sizeof(float2), k_out, st));
   if (ffreq) AE_CUDA(cudaMemcpyAsync(ffreq, q.F, nKS * sizeof(float2), k_out, st));
-  AE_TRY(launch_fft_c2r(ctx, (int64_t)dM * dD, Nx, Ny, q.C, q.work, q.img, 1.f / norm));
-  AE_TRY(launch_fft_c2r(ctx, (int64_t)dM * dD, Nx, Ny, q.F, q.work, q.img + (size_t)dM * dD * P, 1.f / norm));
-  AE_TRY(launch_shrink(ctx, 2 * (int64_t)dM * dD, Nx, Ny, Nk, Nl, q.img, q.taps));
+  AE_TRY(spectrum_taps_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.C, q.work, q.img, q.taps, 1.f / norm));
+  AE_TRY(spectrum_taps_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.F, q.work, q.img + (size_t)dM * dD * P, q.taps + nC,
+                           1.f / norm));
   AE_CUDA(cudaMemcpyAsync(c, q.taps, nC * sizeof(float), k_out, st));
   AE_CUDA(cudaMemcpyAsync(f, q.taps + nC, nC * sizeof(float), k_out, st));
   AE_CUDA(cudaMemcpyAsync(b, db_w, dM * sizeof(float), k_out, st));

@@ -479,7 +479,7 @@ static int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
 // ------------------------------------------------------------------------------------------------ host side
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
-static int get_twiddles(aefft_ctx* ctx, int N, const float2** out) {
+int get_twiddles(aefft_ctx* ctx, int N, const float2** out) {
   char name[32];
   snprintf(name, sizeof(name), "fft_tw_%d", N);
   auto it = ctx->scratch.find(name);

@@ -447,6 +447,174 @@ int launch_shrink(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl,
   return AEFFT_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ pruned kernel DFTs
+constexpr int PD_MAXT = 8;  // taps per axis
+
+// Both kernels are instantiated for the tap counts the reference's parameter file can produce (3, 5, 7 per axis) plus a
+// generic 8 x 8 variant; index arithmetic is 32-bit (bins per image < 2^31).
+
+// one CTA row of 256 threads per 256 consecutive bins of one spectrum row pair: grid (ceil(Nyr/256), Nx, n_img)
+template <int NK, int NL>
+__global__ void __launch_bounds__(256) kernel_spectrum_direct_kernel(const float* __restrict__ taps, float2* __restrict__ spec,
+                                                                      int Nx, int Ny, int Nk, int Nl,
+                                                                      const float2* __restrict__ twx,
+                                                                      const float2* __restrict__ twy) {
+  __shared__ float c[PD_MAXT * PD_MAXT];
+  __shared__ float2 exs[PD_MAXT];
+  const int nk = NK ? NK : Nk, nl = NL ? NL : Nl;
+  const int Nyr = Ny / 2 + 1;
+  const unsigned n = blockIdx.z, wx = blockIdx.y;
+  if (threadIdx.x < nk * nl) c[threadIdx.x] = taps[(size_t)n * nk * nl + threadIdx.x];
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + nk) {
+    const int k = threadIdx.x - 64;
+    exs[k] = __ldg(twx + ((wx * ((k - nk / 2) & (Nx - 1))) & (Nx - 1)));
+  }
+  __syncthreads();
+  const int wy = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wy >= Nyr) return;
+  float2 ey[NL ? NL : PD_MAXT];
+#pragma unroll
+  for (int l = 0; l < (NL ? NL : PD_MAXT); l++)
+    if (l < nl) ey[l] = __ldg(twy + ((wy * ((l - nl / 2) & (Ny - 1))) & (Ny - 1)));
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < (NK ? NK : PD_MAXT); k++) {
+    if (k < nk) {
+      float2 t = make_float2(0.f, 0.f);  // sum_l c[k][l] Ey[l]
+#pragma unroll
+      for (int l = 0; l < (NL ? NL : PD_MAXT); l++) {
+        if (l < nl) {
+          const float cv = c[k * nl + l];
+          t.x = fmaf(cv, ey[l].x, t.x);
+          t.y = fmaf(cv, ey[l].y, t.y);
+        }
+      }
+      cfma(acc, exs[k], t);
+    }
+  }
+  spec[((size_t)n * Nx + wx) * Nyr + wy] = acc;
+}
+
+int launch_kernel_spectrum_direct(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* taps,
+                                  float2* spec) {
+  AE_ARG(n_img > 0 && n_img <= 65535 && Nx <= 65535 && Nk <= PD_MAXT && Nl <= PD_MAXT && Nk <= Nx && Nl <= Ny);
+  const float2 *twx, *twy;
+  AE_TRY(get_twiddles(ctx, Nx, &twx));
+  AE_TRY(get_twiddles(ctx, Ny, &twy));
+  const int Nyr = Ny / 2 + 1;
+  const long long S = (long long)Nx * Nyr;
+  ProfScope prof(ctx, "kernel_spectrum", 8.0 * n_img * S * (Nk + Nk * Nl / 4.0), 8.0 * n_img * S);
+  const int threads = Nyr >= 256 ? 256 : (Nyr > 128 ? 256 : 128);
+  dim3 grid((Nyr + threads - 1) / threads, Nx, (unsigned)n_img);
+  if (Nk == 5 && Nl == 5) kernel_spectrum_direct_kernel<5, 5><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy);
+  else if (Nk == 3 && Nl == 3) kernel_spectrum_direct_kernel<3, 3><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy);
+  else if (Nk == 7 && Nl == 7) kernel_spectrum_direct_kernel<7, 7><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy);
+  else kernel_spectrum_direct_kernel<0, 0><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// grid (n_split, n_img): every CTA reduces a contiguous range of spectrum ROWS of one image to Nk*Nl partial sums (fixed
+// order: per-thread sums over the rows, warp shuffles, shared memory), a second tiny kernel adds the splits --
+// deterministic.  A thread owns one column wy (its Ey factors stay in registers) and walks down the rows.
+template <int NK, int NL>
+__global__ void __launch_bounds__(256) spectrum_to_taps_kernel(const float2* __restrict__ spec, float* __restrict__ part, int Nx,
+                                                                int Ny, int Nk, int Nl, const float2* __restrict__ twx,
+                                                                const float2* __restrict__ twy) {
+  constexpr int TK = NK ? NK : PD_MAXT, TL = NL ? NL : PD_MAXT;
+  const int nk = NK ? NK : Nk, nl = NL ? NL : Nl;
+  const int Nyr = Ny / 2 + 1;
+  const unsigned n = blockIdx.y;
+  const int nsplit = gridDim.x, sp = blockIdx.x;
+  const int r_lo = (int)((long long)Nx * sp / nsplit), r_hi = (int)((long long)Nx * (sp + 1) / nsplit);
+  const float2* z = spec + (size_t)n * Nx * Nyr;
+  float g[TK * TL];
+#pragma unroll
+  for (int t = 0; t < TK * TL; t++) g[t] = 0.f;
+  for (int wy = threadIdx.x; wy < Nyr; wy += blockDim.x) {
+    const float h = (wy == 0 || wy == Ny / 2) ? 1.f : 2.f;
+    float2 ey[TL];
+#pragma unroll
+    for (int l = 0; l < TL; l++)
+      if (l < nl) ey[l] = __ldg(twy + ((wy * ((l - nl / 2) & (Ny - 1))) & (Ny - 1)));
+    for (int wx = r_lo; wx < r_hi; wx++) {
+      float2 v = z[(size_t)wx * Nyr + wy];
+      v.x *= h; v.y *= h;
+      float2 a[TL];  // v * conj(Ey[l])
+#pragma unroll
+      for (int l = 0; l < TL; l++)
+        if (l < nl) a[l] = make_float2(v.x * ey[l].x + v.y * ey[l].y, v.y * ey[l].x - v.x * ey[l].y);
+#pragma unroll
+      for (int k = 0; k < TK; k++) {
+        if (k < nk) {
+          const float2 e = __ldg(twx + ((wx * ((k - nk / 2) & (Nx - 1))) & (Nx - 1)));
+#pragma unroll
+          for (int l = 0; l < TL; l++)
+            if (l < nl) g[k * TL + l] += a[l].x * e.x + a[l].y * e.y;  // Re(a * conj(e))
+        }
+      }
+    }
+  }
+  __shared__ float red[8][TK * TL];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int t = 0; t < TK * TL; t++) {
+    float v = g[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < nk * nl) {
+    const int k = threadIdx.x / nl, l = threadIdx.x - k * nl;
+    float v = 0.f;
+    for (int wq = 0; wq < (int)(blockDim.x >> 5); wq++) v += red[wq][k * TL + l];
+    part[((size_t)n * nsplit + sp) * nk * nl + threadIdx.x] = v;
+  }
+}
+__global__ void spectrum_to_taps_final_kernel(const float* __restrict__ part, float* __restrict__ taps, long long total, int nsplit,
+                                              int T, float scale) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long n = idx / T;
+  const int t = (int)(idx - n * T);
+  double s = 0.0;
+  for (int sp = 0; sp < nsplit; sp++) s += (double)part[(n * nsplit + sp) * T + t];
+  taps[idx] = (float)(s * (double)scale);
+}
+
+int launch_spectrum_to_taps(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float2* spec, float* taps,
+                            float scale) {
+  AE_ARG(n_img > 0 && n_img <= 65535 && Nk <= PD_MAXT && Nl <= PD_MAXT && Nk <= Nx && Nl <= Ny);
+  const float2 *twx, *twy;
+  AE_TRY(get_twiddles(ctx, Nx, &twx));
+  AE_TRY(get_twiddles(ctx, Ny, &twy));
+  const int Nyr = Ny / 2 + 1;
+  const long long S = (long long)Nx * Nyr;
+  // enough CTAs to fill the machine (row ranges of >= 8 rows)
+  int nsplit = (int)((4LL * ctx->sm_count + n_img - 1) / n_img);
+  if (nsplit > Nx / 8) nsplit = Nx / 8;
+  if (nsplit < 1) nsplit = 1;
+  const int threads = Nyr > 128 ? 256 : (Nyr > 64 ? 128 : 64);
+  float* part;
+  AE_TRY(ctx->getT("s2t_part", (size_t)n_img * nsplit * Nk * Nl, &part));
+  {
+    ProfScope prof(ctx, "spectrum_to_taps", 2.0 * n_img * S * (4.0 * Nl + 2.0 * Nk * Nl), 8.0 * n_img * S);
+    dim3 grid(nsplit, (unsigned)n_img);
+    if (Nk == 5 && Nl == 5) spectrum_to_taps_kernel<5, 5><<<grid, threads, 0, ctx->stream>>>(spec, part, Nx, Ny, Nk, Nl, twx, twy);
+    else if (Nk == 3 && Nl == 3) spectrum_to_taps_kernel<3, 3><<<grid, threads, 0, ctx->stream>>>(spec, part, Nx, Ny, Nk, Nl, twx, twy);
+    else if (Nk == 7 && Nl == 7) spectrum_to_taps_kernel<7, 7><<<grid, threads, 0, ctx->stream>>>(spec, part, Nx, Ny, Nk, Nl, twx, twy);
+    else spectrum_to_taps_kernel<0, 0><<<grid, threads, 0, ctx->stream>>>(spec, part, Nx, Ny, Nk, Nl, twx, twy);
+  }
+  const long long total = (long long)n_img * Nk * Nl;
+  spectrum_to_taps_final_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(part, taps, total, nsplit, Nk * Nl, scale);
+  ctx->launches += 2;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ update
 // gradient_diff (:709-753): cd[m][d][k][l] = sum_{m1!=m, d1!=d} (c[m][d][k][l]-c[m1][d1][k][l]) / |c[m][d]-c[m1][d1]|^2,
 // fd likewise on f[d][m]; bd[m] = sum_{m1!=m} 1/(b[m]-b[m1]); pd[d] = sum_{d1!=d} 1/(p[d]-p[d1]).
