@@ -123,6 +123,22 @@ def cpu_reference_sample(w, budget_s, repeats=1):
     return dict(value=1.0 / per_frame, seconds=t, sample=desc, kind=kind, cores=1, q=q)
 
 
+def ref_cuda_sample():
+    """The reference's own CUDA kernels on this box (reported baseline): tools/ref_cuda_sample.py in a subprocess, so
+    that a fault inside the reference cannot take the bench down.  None-like dict on failure."""
+    import subprocess
+
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_cuda_sample.py")], capture_output=True,
+                             text=True, timeout=180)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"unavailable": f"no result (rc={out.returncode}): {out.stderr.strip()[-200:]}"}
+    except Exception as e:  # timeout, missing interpreter, ...
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_reference(args, w, rank, world):
     if rank != 0:
         return
@@ -560,6 +576,8 @@ def run_ours(args, w, rank, world, local_rank):
             cb = cpu_reference_sample(w, 15.0)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "frames/s", "cores": cb["cores"], "kind": cb["kind"],
                                     "sample": cb["sample"]}
+            if w["space"] == "coordinate":
+                line["ref_cuda_baseline"] = ref_cuda_sample()
         print(json.dumps(line))
     wl.close()
     ctx.close()
