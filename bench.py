@@ -593,10 +593,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--size", type=int, default=None, help="square frames of this edge instead of the workload's (sweeps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
     args = ap.parse_args()
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.size:
+        w["Nx"] = w["Ny"] = args.size
     if args.batch is None:
         args.batch = w["batch"]
     rank = int(os.environ.get("RANK", "0"))
