@@ -13,6 +13,7 @@
 // permutation is applied while staging, each pass keeps its r points in registers, and twiddles come from a
 // per-length table computed in double precision on the host (L1-resident via __ldg).
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -419,8 +420,260 @@ __global__ void __launch_bounds__(256) fft_cols_t(const float2* __restrict__ in,
   }
 }
 
+
+// ================================================================================================ Stockham kernels
+// Same transforms with the autosort (Stockham) data flow: a radix-R pass reads element j + q*N/R (consecutive threads ->
+// consecutive addresses), multiplies by W_{Ns*R}^{(j mod Ns) q}, and writes the butterfly outputs to
+// expand(j) + q*Ns, ping-ponging between two shared-memory buffers; the result is in natural order, so there is no
+// digit-reversal scatter (which serialised the staging stores 8-16x on bank conflicts).  The FIRST pass loads straight
+// from global memory and -- for the column and the C2R row kernels -- the LAST pass stores straight to global memory:
+// a 512-point transform makes 2 shared-memory exchanges instead of 4 staging/pass/readout round trips.
+// Buffer index padding pad(i) = i + (i >> 3) makes the stride-R stores of the first passes conflict free.
+__device__ __forceinline__ int padi(int i) { return i + (i >> 3); }
+
+// one butterfly of pass I: loads + twiddles + DFT into a[], returns the output base index j0 (outputs go to j0 + q*NS)
+template <int DIR, int LOG2N, int I, int LOG2NS, class Load>
+__device__ __forceinline__ int stockham_load(int j, Load ld, const float2* __restrict__ tw, float2* a) {
+  constexpr int LR = Sched<LOG2N>::lr(I), R = 1 << LR, NS = 1 << LOG2NS;
+  const int k = j & (NS - 1);
+#pragma unroll
+  for (int q = 0; q < R; q++) a[q] = ld(j + (q << (LOG2N - LR)));
+  if (LOG2NS > 0) {
+#pragma unroll
+    for (int q = 1; q < R; q++) {
+      float2 w = __ldg(tw + ((k * q) << (LOG2N - LOG2NS - LR)));
+      if (DIR > 0) w.y = -w.y;
+      a[q] = cmul(a[q], w);
+    }
+  }
+  if (R == 2) dft2<DIR>(a);
+  else if (R == 4) dft4<DIR>(a);
+  else dft8<DIR>(a);
+  return ((j - k) << LR) + k;
+}
+template <int DIR, int LOG2N, int I, int LOG2NS, class Load, class Store>
+__device__ __forceinline__ void stockham_item(int j, Load ld, Store st, const float2* __restrict__ tw) {
+  constexpr int LR = Sched<LOG2N>::lr(I), R = 1 << LR;
+  float2 a[R];
+  const int j0 = stockham_load<DIR, LOG2N, I, LOG2NS>(j, ld, tw, a);
+#pragma unroll
+  for (int q = 0; q < R; q++) st(j0 + (q << LOG2NS), a[q]);
+}
+
+template <int LOG2N>
+struct SRowCfg {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int LOG2RP = LOG2N >= 11 ? 0 : (11 - LOG2N > 5 ? 5 : 11 - LOG2N);  // ~18 KB
+  static constexpr int RP = 1 << LOG2RP;
+  static constexpr int SP = N + (N >> 3) + 2;
+  static constexpr size_t smem = (size_t)RP * SP * sizeof(float2);
+  static constexpr int npass = Sched<LOG2N>::npass;
+};
+
+// middle passes I = 1 .. npass-1 (shared -> shared) IN PLACE: every thread first loads and transforms all its butterflies
+// (registers), the CTA synchronises, then the outputs overwrite the buffer -- one buffer instead of a ping-pong pair
+// doubles the CTAs per SM.  256 threads per CTA.
+template <int DIR, int LOG2N, int LOG2SEQ, int I, int LOG2NS, bool LAST_TO_CALLER, class Seq>
+__device__ __forceinline__ void stockham_middle(float2* buf, const float2* __restrict__ tw, Seq sq) {
+  constexpr int npass = Sched<LOG2N>::npass;
+  if constexpr (I < npass - (LAST_TO_CALLER ? 1 : 0)) {
+    constexpr int LR = Sched<LOG2N>::lr(I), R = 1 << LR;
+    constexpr int TOTAL = 1 << (LOG2N - LR + LOG2SEQ);
+    constexpr int ITEMS = TOTAL >= 256 ? TOTAL / 256 : 1;
+    float2 a[ITEMS][R];
+    int j0[ITEMS];
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < ITEMS; t++) {
+      const int item = threadIdx.x + t * 256;
+      if (item < TOTAL) {
+        const int c = sq.seq(item, LOG2N - LR), j = sq.idx(item, LOG2N - LR);
+        j0[t] = stockham_load<DIR, LOG2N, I, LOG2NS>(j, [&](int n) { return buf[sq.addr(c, n)]; }, tw, a[t]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < ITEMS; t++) {
+      const int item = threadIdx.x + t * 256;
+      if (item < TOTAL) {
+        const int c = sq.seq(item, LOG2N - LR);
+#pragma unroll
+        for (int q = 0; q < R; q++) buf[sq.addr(c, j0[t] + (q << LOG2NS))] = a[t][q];
+      }
+    }
+    stockham_middle<DIR, LOG2N, LOG2SEQ, I + 1, LOG2NS + LR, LAST_TO_CALLER>(buf, tw, sq);
+  }
+}
+
+// addressing of `nseq` sequences inside a shared buffer
+struct RowSeq {   // rows: sequence c contiguous with pitch SP; items: j fastest
+  int SP;
+  __device__ __forceinline__ int seq(int item, int log2nbf) const { return item >> log2nbf; }
+  __device__ __forceinline__ int idx(int item, int log2nbf) const { return item & ((1 << log2nbf) - 1); }
+  __device__ __forceinline__ int addr(int c, int n) const { return c * SP + padi(n); }
+};
+template <int LOG2CT>
+struct ColSeq {   // columns: element n of column c at padi(n)*CT + c; items: c fastest
+  __device__ __forceinline__ int seq(int item, int) const { return item & ((1 << LOG2CT) - 1); }
+  __device__ __forceinline__ int idx(int item, int) const { return item >> LOG2CT; }
+  __device__ __forceinline__ int addr(int c, int n) const { return (padi(n) << LOG2CT) + c; }
+};
+
+template <int LOG2N>
+__global__ void __launch_bounds__(256) fft_rows_r2c_s(const float* __restrict__ in, float2* __restrict__ out, int Nx,
+                                                      const float2* __restrict__ tw) {
+  using C = SRowCfg<LOG2N>;
+  constexpr int Ny = C::N, Nyr = Ny / 2 + 1, SP = C::SP, RP = C::RP, LR0 = Sched<LOG2N>::lr(0);
+  extern __shared__ __align__(16) float2 sm[];
+  float2* src = sm;
+  const long long img = blockIdx.y;
+  const int rp0 = blockIdx.x * RP;
+  const float* base = in + img * (long long)Nx * Ny;
+  RowSeq rs{SP};
+  // pass 0: global (two real rows = one complex sequence) -> shared
+  for (int item = threadIdx.x; item < (RP << (LOG2N - LR0)); item += blockDim.x) {
+    const int r = item >> (LOG2N - LR0), j = item & ((1 << (LOG2N - LR0)) - 1);
+    const int row = 2 * (rp0 + r);
+    const bool ok = row < Nx;
+    const float* ra = base + (long long)row * Ny;
+    float2* d = src;
+    stockham_item<-1, LOG2N, 0, 0>(
+        j, [&](int n) { return ok ? make_float2(__ldg(ra + n), __ldg(ra + Ny + n)) : make_float2(0.f, 0.f); },
+        [&](int i, float2 v) { d[rs.addr(r, i)] = v; }, tw);
+  }
+  stockham_middle<-1, LOG2N, C::LOG2RP, 1, LR0, false>(src, tw, rs);
+  __syncthreads();
+  float2* o = out + img * (long long)Nx * Nyr;
+  for (int r = 0; r < RP; r++) {
+    const int row = 2 * (rp0 + r);
+    if (row >= Nx) break;
+    for (int k = threadIdx.x; k < Nyr; k += blockDim.x) {
+      const float2 z1 = src[rs.addr(r, k)];
+      const float2 z2 = src[rs.addr(r, (Ny - k) & (Ny - 1))];
+      o[(long long)row * Nyr + k] = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+      o[(long long)(row + 1) * Nyr + k] = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+    }
+  }
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(256) fft_rows_c2r_s(const float2* __restrict__ in, float* __restrict__ out, int Nx,
+                                                      const float2* __restrict__ tw, float scale) {
+  using C = SRowCfg<LOG2N>;
+  constexpr int Ny = C::N, Nyr = Ny / 2 + 1, SP = C::SP, RP = C::RP, LR0 = Sched<LOG2N>::lr(0), NP = C::npass;
+  constexpr int LRL = Sched<LOG2N>::lr(NP - 1);
+  extern __shared__ __align__(16) float2 sm[];
+  float2* src = sm;
+  const long long img = blockIdx.y;
+  const int rp0 = blockIdx.x * RP;
+  const float2* base = in + img * (long long)Nx * Nyr;
+  float* obase = out + img * (long long)Nx * Ny;
+  RowSeq rs{SP};
+  // Z[n] = A[n] + i B[n] for n <= N/2, conj(A[N-n]) + i conj(B[N-n]) above; imaginary parts of DC / Nyquist ignored
+  auto load_z = [&](const float2* ra, bool ok, int n) {
+    if (!ok) return make_float2(0.f, 0.f);
+    const int m = n <= Ny / 2 ? n : Ny - n;
+    float2 a = __ldg(ra + m), b = __ldg(ra + Nyr + m);
+    if (m == 0 || m == Ny / 2) { a.y = 0.f; b.y = 0.f; }
+    return n <= Ny / 2 ? make_float2(a.x - b.y, a.y + b.x) : make_float2(a.x + b.y, b.x - a.y);
+  };
+  auto store_out = [&](int row, int i, float2 v) {
+    obase[(long long)row * Ny + i] = v.x * scale;
+    obase[(long long)(row + 1) * Ny + i] = v.y * scale;
+  };
+  if constexpr (NP == 1) {
+    for (int item = threadIdx.x; item < (RP << (LOG2N - LR0)); item += blockDim.x) {
+      const int r = item >> (LOG2N - LR0), j = item & ((1 << (LOG2N - LR0)) - 1);
+      const int row = 2 * (rp0 + r);
+      const bool ok = row < Nx;
+      const float2* ra = base + (long long)row * Nyr;
+      stockham_item<+1, LOG2N, 0, 0>(j, [&](int n) { return load_z(ra, ok, n); },
+                                     [&](int i, float2 v) { if (ok) store_out(row, i, v); }, tw);
+    }
+  } else {
+    for (int item = threadIdx.x; item < (RP << (LOG2N - LR0)); item += blockDim.x) {
+      const int r = item >> (LOG2N - LR0), j = item & ((1 << (LOG2N - LR0)) - 1);
+      const int row = 2 * (rp0 + r);
+      const bool ok = row < Nx;
+      const float2* ra = base + (long long)row * Nyr;
+      float2* d = src;
+      stockham_item<+1, LOG2N, 0, 0>(j, [&](int n) { return load_z(ra, ok, n); }, [&](int i, float2 v) { d[rs.addr(r, i)] = v; },
+                                     tw);
+    }
+    stockham_middle<+1, LOG2N, C::LOG2RP, 1, LR0, true>(src, tw, rs);
+    __syncthreads();
+    // last pass: shared -> global (natural order: consecutive threads write consecutive pixels)
+    for (int item = threadIdx.x; item < (RP << (LOG2N - LRL)); item += blockDim.x) {
+      const int r = item >> (LOG2N - LRL), j = item & ((1 << (LOG2N - LRL)) - 1);
+      const int row = 2 * (rp0 + r);
+      const bool ok = row < Nx;
+      const float2* s = src;
+      stockham_item<+1, LOG2N, NP - 1, LOG2N - LRL>(j, [&](int n) { return s[rs.addr(r, n)]; },
+                                                    [&](int i, float2 v) { if (ok) store_out(row, i, v); }, tw);
+    }
+  }
+}
+
+template <int LOG2N>
+struct SColCfg {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int LOG2CT = LOG2N <= 9 ? 3 : (LOG2N == 10 ? 2 : (LOG2N == 11 ? 1 : 0));
+  static constexpr int CT = 1 << LOG2CT;
+  static constexpr size_t smem = (size_t)(N + (N >> 3) + 2) * CT * sizeof(float2);
+};
+
+template <int DIR, int LOG2N>
+__global__ void __launch_bounds__(256) fft_cols_s(const float2* __restrict__ in, float2* __restrict__ out, int W,
+                                                  const float2* __restrict__ tw) {
+  using C = SColCfg<LOG2N>;
+  constexpr int Nx = C::N, CT = C::CT, LOG2CT = C::LOG2CT, LR0 = Sched<LOG2N>::lr(0), NP = Sched<LOG2N>::npass;
+  constexpr int LRL = Sched<LOG2N>::lr(NP - 1);
+  extern __shared__ __align__(16) float2 sm[];
+  float2* src = sm;
+  const long long img = blockIdx.y;
+  const int c0 = blockIdx.x * CT;
+  const float2* gin = in + img * (long long)Nx * W;
+  float2* gout = out + img * (long long)Nx * W;
+  ColSeq<LOG2CT> cs;
+  if constexpr (NP == 1) {
+    for (int item = threadIdx.x; item < (1 << (LOG2N - LR0 + LOG2CT)); item += blockDim.x) {
+      const int c = item & (CT - 1), j = item >> LOG2CT;
+      const bool ok = c0 + c < W;
+      stockham_item<DIR, LOG2N, 0, 0>(
+          j, [&](int n) { return ok ? __ldg(gin + (long long)n * W + c0 + c) : make_float2(0.f, 0.f); },
+          [&](int i, float2 v) { if (ok) gout[(long long)i * W + c0 + c] = v; }, tw);
+    }
+  } else {
+    for (int item = threadIdx.x; item < (1 << (LOG2N - LR0 + LOG2CT)); item += blockDim.x) {
+      const int c = item & (CT - 1), j = item >> LOG2CT;
+      const bool ok = c0 + c < W;
+      float2* d = src;
+      stockham_item<DIR, LOG2N, 0, 0>(
+          j, [&](int n) { return ok ? __ldg(gin + (long long)n * W + c0 + c) : make_float2(0.f, 0.f); },
+          [&](int i, float2 v) { d[cs.addr(c, i)] = v; }, tw);
+    }
+    stockham_middle<DIR, LOG2N, LOG2CT, 1, LR0, true>(src, tw, cs);
+    __syncthreads();
+    for (int item = threadIdx.x; item < (1 << (LOG2N - LRL + LOG2CT)); item += blockDim.x) {
+      const int c = item & (CT - 1), j = item >> LOG2CT;
+      const bool ok = c0 + c < W;
+      const float2* s = src;
+      stockham_item<DIR, LOG2N, NP - 1, LOG2N - LRL>(j, [&](int n) { return s[cs.addr(c, n)]; },
+                                                     [&](int i, float2 v) { if (ok) gout[(long long)i * W + c0 + c] = v; }, tw);
+    }
+  }
+}
+
 template <int LOG2N>
 static int run_rows_r2c(aefft_ctx* ctx, int64_t batch, int Nx, const float* in, float2* out, const float2* tw) {
+  if (!getenv("AEFFT_FFT_V1")) {
+    using S = SRowCfg<LOG2N>;
+    static bool attr_s = false;
+    if (!attr_s) { AE_CUDA(cudaFuncSetAttribute(fft_rows_r2c_s<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem)); attr_s = true; }
+    dim3 grid_s((Nx / 2 + S::RP - 1) / S::RP, (unsigned)batch);
+    fft_rows_r2c_s<LOG2N><<<grid_s, 256, S::smem, ctx->stream>>>(in, out, Nx, tw);
+    return AEFFT_OK;
+  }
   using C = RowCfg<LOG2N>;
   static bool attr = false;
   if (!attr) { AE_CUDA(cudaFuncSetAttribute(fft_rows_r2c_t<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem)); attr = true; }
@@ -430,6 +683,14 @@ static int run_rows_r2c(aefft_ctx* ctx, int64_t batch, int Nx, const float* in, 
 }
 template <int LOG2N>
 static int run_rows_c2r(aefft_ctx* ctx, int64_t batch, int Nx, const float2* in, float* out, const float2* tw, float scale) {
+  if (!getenv("AEFFT_FFT_V1")) {
+    using S = SRowCfg<LOG2N>;
+    static bool attr_s = false;
+    if (!attr_s) { AE_CUDA(cudaFuncSetAttribute(fft_rows_c2r_s<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem)); attr_s = true; }
+    dim3 grid_s((Nx / 2 + S::RP - 1) / S::RP, (unsigned)batch);
+    fft_rows_c2r_s<LOG2N><<<grid_s, 256, S::smem, ctx->stream>>>(in, out, Nx, tw, scale);
+    return AEFFT_OK;
+  }
   using C = RowCfg<LOG2N>;
   static bool attr = false;
   if (!attr) { AE_CUDA(cudaFuncSetAttribute(fft_rows_c2r_t<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem)); attr = true; }
@@ -439,6 +700,15 @@ static int run_rows_c2r(aefft_ctx* ctx, int64_t batch, int Nx, const float2* in,
 }
 template <int DIR, int LOG2N>
 static int run_cols(aefft_ctx* ctx, int64_t batch, int W, const float2* in, float2* out, const float2* tw) {
+  if (!getenv("AEFFT_FFT_V1")) {
+    // in place is fine: a CTA owns its CT columns, reads all of them in the first pass and writes them in the last
+    using S = SColCfg<LOG2N>;
+    static bool attr_s = false;
+    if (!attr_s) { AE_CUDA(cudaFuncSetAttribute(fft_cols_s<DIR, LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem)); attr_s = true; }
+    dim3 grid_s((W + S::CT - 1) / S::CT, (unsigned)batch);
+    fft_cols_s<DIR, LOG2N><<<grid_s, 256, S::smem, ctx->stream>>>(in, out, W, tw);
+    return AEFFT_OK;
+  }
   using C = ColCfg<LOG2N>;
   static bool attr = false;
   if (!attr) { AE_CUDA(cudaFuncSetAttribute(fft_cols_t<DIR, LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem)); attr = true; }
