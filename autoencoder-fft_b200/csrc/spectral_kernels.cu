@@ -250,10 +250,148 @@ __global__ void __launch_bounds__(ST_THREADS, 2) spec_tiled_kernel(TiledParams p
   }
 }
 
+
+// ---- pipelined variant: the operand rows are copied global -> shared with cp.async (16 bytes per thread and copy, no
+// registers), double buffered, so the copies of reduction chunk r+1 overlap the FMAs of chunk r.  Raw values are staged;
+// the optional second source, conjugation and the DC bias are applied when the operands are read into registers, the
+// operand scales are folded into the output scale.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int CONJP, int CONJQ, int HASP1, int HASQ1>
+__global__ void __launch_bounds__(ST_THREADS, 2) spec_tiled2_kernel(TiledParams p) {
+  extern __shared__ __align__(16) float2 dyn[];
+  constexpr int TILE = ST_R * ST_I * ST_BINS;                 // float2 per operand per stage (ST_I == ST_J)
+  constexpr int NBUF = 2 + HASP1 + HASQ1;                     // operand arrays per stage
+  float2* stage_base[2] = {dyn, dyn + NBUF * TILE};
+  const int tid = threadIdx.x, bin = tid & 31, g = tid >> 5;
+  const int ig = g & 3, jg = g >> 2;
+  const long long w0 = (long long)blockIdx.x * ST_BINS;
+  const int i0 = blockIdx.y * ST_I, j0 = blockIdx.z * ST_J;
+  // copy assignment: 64 rows per operand per stage, 16 threads (16 bytes = 2 bins each) per row, 4 rows per thread
+  const int crow = tid >> 4, cseg = tid & 15;
+  const long long wseg = w0 + 2 * cseg;
+  const int seg_bytes = wseg + 2 <= p.S ? 16 : (wseg < p.S ? 8 : 0);
+  auto issue = [&](int r0, float2* base) {
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int row = crow + 16 * t;                 // 0..63 = rr*16 + k
+      const int rr = row >> 4, k = row & 15;
+      const int r = r0 + rr;
+      float2* dstrow = base + row * ST_BINS + 2 * cseg;
+      {
+        const bool ok = r < p.nR && i0 + k < p.nI;
+        const long long off = (long long)(i0 + k) * p.psi + (long long)r * p.psr + wseg;
+        cp_async16(dstrow, ok ? (const void*)(p.P0 + off) : (const void*)p.P0, ok ? seg_bytes : 0);
+        if (HASP1) cp_async16(dstrow + 2 * TILE, ok ? (const void*)(p.P1 + off) : (const void*)p.P0, ok ? seg_bytes : 0);
+      }
+      {
+        const bool ok = r < p.nR && j0 + k < p.nJ;
+        const long long off = (long long)(j0 + k) * p.qsi + (long long)r * p.qsr + wseg;
+        cp_async16(dstrow + TILE, ok ? (const void*)(p.Q0 + off) : (const void*)p.Q0, ok ? seg_bytes : 0);
+        if (HASQ1) cp_async16(dstrow + (2 + HASP1) * TILE, ok ? (const void*)(p.Q1 + off) : (const void*)p.Q0, ok ? seg_bytes : 0);
+      }
+    }
+    cp_async_commit();
+  };
+  float2 acc[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 8; b++) acc[a][b] = make_float2(0.f, 0.f);
+  float qb[8];
+#pragma unroll
+  for (int b = 0; b < 8; b++)
+    qb[b] = (w0 + bin == 0 && p.q_bias && j0 + jg * 8 + b < p.nJ) ? p.q_bias[j0 + jg * 8 + b] * p.q_bias_scale / p.q_scale : 0.f;
+  const int nchunks = (p.nR + ST_R - 1) / ST_R;
+  issue(0, stage_base[0]);
+  for (int ch = 0; ch < nchunks; ch++) {
+    if (ch + 1 < nchunks) {
+      issue((ch + 1) * ST_R, stage_base[(ch + 1) & 1]);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float2* Ps = stage_base[ch & 1];
+    const float2* Qs = Ps + TILE;
+#pragma unroll
+    for (int rr = 0; rr < ST_R; rr++) {
+      float2 pv[4], qv[8];
+      const bool live = ch * ST_R + rr < p.nR;  // (rows beyond nR were zero-filled; the bias must not be added there)
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int idx = (rr * ST_I + ig * 4 + a) * ST_BINS + bin;
+        pv[a] = Ps[idx];
+        if (HASP1) { const float2 u = Ps[idx + 2 * TILE]; pv[a].x -= u.x; pv[a].y -= u.y; }
+      }
+#pragma unroll
+      for (int b = 0; b < 8; b++) {
+        const int idx = (rr * ST_J + jg * 8 + b) * ST_BINS + bin;
+        qv[b] = Qs[idx];
+        if (HASQ1) { const float2 u = Ps[idx + (2 + HASP1) * TILE]; qv[b].x -= u.x; qv[b].y -= u.y; }
+        if (live) qv[b].x += qb[b];
+      }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+          if (CONJQ) cfma_conj(acc[a][b], pv[a], qv[b]);
+          else if (CONJP) cfma_conj(acc[a][b], qv[b], pv[a]);
+          else cfma(acc[a][b], pv[a], qv[b]);
+        }
+    }
+    __syncthreads();
+  }
+  const long long w = w0 + bin;
+  if (w >= p.S) return;
+  const float sc = p.out_scale * p.p_scale * p.q_scale;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int i = i0 + ig * 4 + a;
+    if (i >= p.nI) continue;
+    const float ob = (w == 0 && p.out_bias) ? p.out_bias[i] * p.out_bias_scale : 0.f;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const int j = j0 + jg * 8 + b;
+      if (j >= p.nJ) continue;
+      p.out[(long long)i * p.osi + (long long)j * p.osj + w] = make_float2(fmaf(acc[a][b].x, sc, ob), acc[a][b].y * sc);
+    }
+  }
+}
+
+template <int CONJP, int CONJQ, int HASP1, int HASQ1>
+static int run_spec_tiled2(aefft_ctx* ctx, const TiledParams& p, dim3 grid) {
+  const size_t smem = (size_t)2 * (2 + HASP1 + HASQ1) * ST_R * ST_I * ST_BINS * sizeof(float2);
+  static bool attr = false;
+  if (!attr) {
+    AE_CUDA(cudaFuncSetAttribute(spec_tiled2_kernel<CONJP, CONJQ, HASP1, HASQ1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  spec_tiled2_kernel<CONJP, CONJQ, HASP1, HASQ1><<<grid, ST_THREADS, smem, ctx->stream>>>(p);
+  return AEFFT_OK;
+}
+
 static int launch_spec_tiled(aefft_ctx* ctx, const TiledParams& p) {
   dim3 grid((unsigned)((p.S + ST_BINS - 1) / ST_BINS), (p.nI + ST_I - 1) / ST_I, (p.nJ + ST_J - 1) / ST_J);
   AE_ARG(grid.y <= 65535 && grid.z <= 65535);
-  spec_tiled_kernel<<<grid, ST_THREADS, 0, ctx->stream>>>(p);
+  // pipelined cp.async variant when every operand row is 16-byte aligned (S even, even strides) and q_scale != 0
+  const bool al = p.S % 2 == 0 && p.psi % 2 == 0 && p.psr % 2 == 0 && p.qsi % 2 == 0 && p.qsr % 2 == 0 &&
+                  ((((uintptr_t)p.P0 | (uintptr_t)p.P1 | (uintptr_t)p.Q0 | (uintptr_t)p.Q1) & 15) == 0) && p.q_scale != 0.f;
+  int rc = AEFFT_ERR_UNSUPPORTED;
+  if (al && !getenv("AEFFT_NO_SPEC_PIPE")) {
+    if (!p.conjP && !p.conjQ && !p.P1 && !p.Q1) rc = run_spec_tiled2<0, 0, 0, 0>(ctx, p, grid);
+    else if (p.conjP && !p.conjQ && !p.P1 && p.Q1) rc = run_spec_tiled2<1, 0, 0, 1>(ctx, p, grid);
+    else if (!p.conjP && p.conjQ && !p.P1 && !p.Q1) rc = run_spec_tiled2<0, 1, 0, 0>(ctx, p, grid);
+    else if (!p.conjP && p.conjQ && p.P1 && !p.Q1) rc = run_spec_tiled2<0, 1, 1, 0>(ctx, p, grid);
+  }
+  if (rc == AEFFT_ERR_UNSUPPORTED) spec_tiled_kernel<<<grid, ST_THREADS, 0, ctx->stream>>>(p);
+  else if (rc != AEFFT_OK) return rc;
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
   return AEFFT_OK;
