@@ -220,6 +220,12 @@ int launch_update(aefft_ctx* ctx, const UpdateArgs& a);
 int launch_fft_r2c(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float* in, float2* spec);
 int launch_fft_c2r(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float2* spec, float2* work, float* out,
                    float scale);
+// frame-strided real side: image (frame f, channel c) at base + f*fstride + c*Nx*Ny, batch = frames*ch (the per-frame layer
+// blocks of the net); AEFFT_ERR_UNSUPPORTED when that layout cannot be addressed directly (caller gathers instead)
+int launch_fft_r2c_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float* in, int ch, long long fstride,
+                           float2* spec);
+int launch_fft_c2r_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float2* spec, float2* work, float* out, int ch,
+                           long long fstride, float scale);
 int launch_spec_resize(aefft_ctx* ctx, int64_t planes, int Nx, int Ny, int Nxs, int Nys, const float2* in, float2* out);
 int launch_spec_contract(aefft_ctx* ctx, int64_t B, int C, int O, int64_t S, const float2* in0, const float2* in1,
                          const float2* W, int64_t w_so, int64_t w_sc, int conjW, float in_scale, const float* bias,

@@ -209,17 +209,30 @@ int aefft_autoenc_fft(aefft_ctx* ctx, int loc, int64_t B, int n_conv, const int*
   }
   const cudaMemcpyKind k_in = loc == AEFFT_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
   const cudaMemcpyKind k_out = loc == AEFFT_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-  // gather layer 0 of every frame into a contiguous [B][D][Nx][Ny] block
+  // layer 0 of every frame: transformed in place of the caller's per-frame block when it is device memory, else
+  // gathered into a contiguous [B][D][Nx][Ny] block first
   {
-    const size_t w = (size_t)D * Nx * Ny * sizeof(float);
-    AE_CUDA(cudaMemcpy2DAsync(real, w, layers_all + loff[0], (size_t)lstride * sizeof(float), w, (size_t)B, k_in, st));
+    int rc = AEFFT_ERR_UNSUPPORTED;
+    if (loc == AEFFT_DEVICE) rc = launch_fft_r2c_strided(ctx, B * D, Nx, Ny, layers_all + loff[0], D, (long long)lstride, fa);
+    if (rc == AEFFT_ERR_UNSUPPORTED) {
+      const size_t w = (size_t)D * Nx * Ny * sizeof(float);
+      AE_CUDA(cudaMemcpy2DAsync(real, w, layers_all + loff[0], (size_t)lstride * sizeof(float), w, (size_t)B, k_in, st));
+      AE_TRY(launch_fft_r2c(ctx, B * D, Nx, Ny, real, fa));
+    } else if (rc != AEFFT_OK) {
+      return rc;
+    }
   }
-  AE_TRY(launch_fft_r2c(ctx, B * D, Nx, Ny, real, fa));
   float2 *freq = fa, *other = fb;
   int l = 1;
   auto emit_layer = [&](const float2* spec, int ch, int nx, int ny) -> int {
     AE_ARG(l < n_layers && ldims[3 * l] == ch && ldims[3 * l + 1] == nx && ldims[3 * l + 2] == ny);
-    AE_TRY(launch_fft_c2r(ctx, B * ch, nx, ny, spec, work, real, 1.f / ((float)nx * (float)ny)));  // fft_inv :831
+    const float inv = 1.f / ((float)nx * (float)ny);  // fft_inv :831
+    if (loc == AEFFT_DEVICE) {
+      // inverse transform straight into the caller's per-frame layer block (no gather / scatter copy)
+      const int rc = launch_fft_c2r_strided(ctx, B * ch, nx, ny, spec, work, layers_all + loff[l], ch, (long long)lstride, inv);
+      if (rc != AEFFT_ERR_UNSUPPORTED) return rc;
+    }
+    AE_TRY(launch_fft_c2r(ctx, B * ch, nx, ny, spec, work, real, inv));
     const size_t w = (size_t)ch * nx * ny * sizeof(float);
     AE_CUDA(cudaMemcpy2DAsync(layers_all + loff[l], (size_t)lstride * sizeof(float), real, w, w, (size_t)B, k_out, st));
     return AEFFT_OK;
@@ -269,9 +282,11 @@ int aefft_autoenc_fft(aefft_ctx* ctx, int loc, int64_t B, int n_conv, const int*
 }
 
 // backprop_fft (fft_backproplib.cu:1381-1511).
-int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl,
-                       const float* in, const float* expout, const float* out, float* cfreq, float* c, float* ffreq,
-                       float* f, float* b, float* p, float del0, int maxdiff, int n_iter, float* mse_trace) {
+// in_fstride != 0 (device pointers only): frame n of in / expout / out starts at ptr + n*in_fstride (per-frame layer blocks)
+static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl,
+                             const float* in, const float* expout, const float* out, int64_t in_fstride, float* cfreq,
+                             float* c, float* ffreq, float* f, float* b, float* p, float del0, int maxdiff, int n_iter,
+                             float* mse_trace) {
   AE_ARG(ctx && in && expout && out && c && f && b && p);
   AE_ARG(B > 0 && dD > 0 && dM > 0 && pow2(Nx) && pow2(Ny) && Nk <= Nx && Nl <= Ny && n_iter >= 0);
   AE_CUDA(cudaSetDevice(ctx->device));
@@ -314,6 +329,7 @@ int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int N
       AE_CUDA(cudaMemcpyAsync(real, src, (size_t)B * dD * P * sizeof(float), cudaMemcpyHostToDevice, st));
       d = real;
     }
+    if (in_fstride) return launch_fft_r2c_strided(ctx, B * dD, Nx, Ny, d, dD, (long long)in_fstride, dst);
     return launch_fft_r2c(ctx, B * dD, Nx, Ny, d, dst);
   };
   AE_TRY(load_fft(in, q.X));
@@ -376,6 +392,13 @@ int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int N
   return AEFFT_OK;
 }
 
+int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl,
+                       const float* in, const float* expout, const float* out, float* cfreq, float* c, float* ffreq,
+                       float* f, float* b, float* p, float del0, int maxdiff, int n_iter, float* mse_trace) {
+  return backprop_fft_core(ctx, loc, B, dD, dM, Nx, Ny, Nk, Nl, in, expout, out, 0, cfreq, c, ffreq, f, b, p, del0, maxdiff,
+                           n_iter, mse_trace);
+}
+
 }  // extern "C"
 
 extern "C" {
@@ -388,6 +411,10 @@ int aefft_backprop_fft_strided(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx
                                int maxdiff, int n_iter, float* mse_trace) {
   AE_ARG(ctx && in && out && B > 0 && frame_stride >= (int64_t)dD * Nx * Ny);
   AE_CUDA(cudaSetDevice(ctx->device));
+  // transform the frames where they lie when the row kernels can address the per-frame blocks, else gather
+  if (Ny >= 8 && Ny <= 4096 && !getenv("AEFFT_FFT_V1"))
+    return backprop_fft_core(ctx, AEFFT_DEVICE, B, dD, dM, Nx, Ny, Nk, Nl, in, in, out, frame_stride, nullptr, c, nullptr, f, b, p,
+                             del0, maxdiff, n_iter, mse_trace);
   const size_t w = (size_t)dD * Nx * Ny * sizeof(float);
   float *gin, *gout;
   AE_TRY(ctx->getT("bpfs_in", (size_t)B * dD * Nx * Ny, &gin));

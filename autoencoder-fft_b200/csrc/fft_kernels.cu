@@ -521,14 +521,15 @@ struct ColSeq {   // columns: element n of column c at padi(n)*CT + c; items: c 
 
 template <int LOG2N>
 __global__ void __launch_bounds__(256) fft_rows_r2c_s(const float* __restrict__ in, float2* __restrict__ out, int Nx,
-                                                      const float2* __restrict__ tw) {
+                                                      const float2* __restrict__ tw, int ch, long long fstride) {
   using C = SRowCfg<LOG2N>;
   constexpr int Ny = C::N, Nyr = Ny / 2 + 1, SP = C::SP, RP = C::RP, LR0 = Sched<LOG2N>::lr(0);
   extern __shared__ __align__(16) float2 sm[];
   float2* src = sm;
   const long long img = blockIdx.y;
   const int rp0 = blockIdx.x * RP;
-  const float* base = in + img * (long long)Nx * Ny;
+  // real image `img` = (frame, channel): frames may be `fstride` floats apart (layers kept per frame by the caller)
+  const float* base = in + (img / ch) * fstride + (img % ch) * (long long)Nx * Ny;
   RowSeq rs{SP};
   // pass 0: global (two real rows = one complex sequence) -> shared
   for (int item = threadIdx.x; item < (RP << (LOG2N - LR0)); item += blockDim.x) {
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(256) fft_rows_r2c_s(const float* __restrict__ 
 
 template <int LOG2N>
 __global__ void __launch_bounds__(256) fft_rows_c2r_s(const float2* __restrict__ in, float* __restrict__ out, int Nx,
-                                                      const float2* __restrict__ tw, float scale) {
+                                                      const float2* __restrict__ tw, float scale, int ch, long long fstride) {
   using C = SRowCfg<LOG2N>;
   constexpr int Ny = C::N, Nyr = Ny / 2 + 1, SP = C::SP, RP = C::RP, LR0 = Sched<LOG2N>::lr(0), NP = C::npass;
   constexpr int LRL = Sched<LOG2N>::lr(NP - 1);
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(256) fft_rows_c2r_s(const float2* __restrict__
   const long long img = blockIdx.y;
   const int rp0 = blockIdx.x * RP;
   const float2* base = in + img * (long long)Nx * Nyr;
-  float* obase = out + img * (long long)Nx * Ny;
+  float* obase = out + (img / ch) * fstride + (img % ch) * (long long)Nx * Ny;
   RowSeq rs{SP};
   // Z[n] = A[n] + i B[n] for n <= N/2, conj(A[N-n]) + i conj(B[N-n]) above; imaginary parts of DC / Nyquist ignored
   auto load_z = [&](const float2* ra, bool ok, int n) {
@@ -665,15 +666,17 @@ __global__ void __launch_bounds__(256) fft_cols_s(const float2* __restrict__ in,
 }
 
 template <int LOG2N>
-static int run_rows_r2c(aefft_ctx* ctx, int64_t batch, int Nx, const float* in, float2* out, const float2* tw) {
+static int run_rows_r2c(aefft_ctx* ctx, int64_t batch, int Nx, const float* in, float2* out, const float2* tw, int ch,
+                        long long fstride) {
   if (!getenv("AEFFT_FFT_V1")) {
     using S = SRowCfg<LOG2N>;
     static bool attr_s = false;
     if (!attr_s) { AE_CUDA(cudaFuncSetAttribute(fft_rows_r2c_s<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem)); attr_s = true; }
     dim3 grid_s((Nx / 2 + S::RP - 1) / S::RP, (unsigned)batch);
-    fft_rows_r2c_s<LOG2N><<<grid_s, 256, S::smem, ctx->stream>>>(in, out, Nx, tw);
+    fft_rows_r2c_s<LOG2N><<<grid_s, 256, S::smem, ctx->stream>>>(in, out, Nx, tw, ch, fstride);
     return AEFFT_OK;
   }
+  if (fstride != (long long)ch * Nx * (1 << LOG2N)) return AEFFT_ERR_UNSUPPORTED;
   using C = RowCfg<LOG2N>;
   static bool attr = false;
   if (!attr) { AE_CUDA(cudaFuncSetAttribute(fft_rows_r2c_t<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem)); attr = true; }
@@ -682,15 +685,17 @@ static int run_rows_r2c(aefft_ctx* ctx, int64_t batch, int Nx, const float* in, 
   return AEFFT_OK;
 }
 template <int LOG2N>
-static int run_rows_c2r(aefft_ctx* ctx, int64_t batch, int Nx, const float2* in, float* out, const float2* tw, float scale) {
+static int run_rows_c2r(aefft_ctx* ctx, int64_t batch, int Nx, const float2* in, float* out, const float2* tw, float scale,
+                        int ch, long long fstride) {
   if (!getenv("AEFFT_FFT_V1")) {
     using S = SRowCfg<LOG2N>;
     static bool attr_s = false;
     if (!attr_s) { AE_CUDA(cudaFuncSetAttribute(fft_rows_c2r_s<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem)); attr_s = true; }
     dim3 grid_s((Nx / 2 + S::RP - 1) / S::RP, (unsigned)batch);
-    fft_rows_c2r_s<LOG2N><<<grid_s, 256, S::smem, ctx->stream>>>(in, out, Nx, tw, scale);
+    fft_rows_c2r_s<LOG2N><<<grid_s, 256, S::smem, ctx->stream>>>(in, out, Nx, tw, scale, ch, fstride);
     return AEFFT_OK;
   }
+  if (fstride != (long long)ch * Nx * (1 << LOG2N)) return AEFFT_ERR_UNSUPPORTED;
   using C = RowCfg<LOG2N>;
   static bool attr = false;
   if (!attr) { AE_CUDA(cudaFuncSetAttribute(fft_rows_c2r_t<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem)); attr = true; }
@@ -718,18 +723,19 @@ static int run_cols(aefft_ctx* ctx, int64_t batch, int W, const float2* in, floa
 }
 #define AEFFT_FOR_LOG2N(X) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
 // return AEFFT_ERR_UNSUPPORTED for lengths without a compile-time instantiation
-static int rows_r2c_fast(aefft_ctx* ctx, int log2n, int64_t batch, int Nx, const float* in, float2* out, const float2* tw) {
+static int rows_r2c_fast(aefft_ctx* ctx, int log2n, int64_t batch, int Nx, const float* in, float2* out, const float2* tw,
+                         int ch, long long fstride) {
   switch (log2n) {
-#define X(L) case L: return run_rows_r2c<L>(ctx, batch, Nx, in, out, tw);
+#define X(L) case L: return run_rows_r2c<L>(ctx, batch, Nx, in, out, tw, ch, fstride);
     AEFFT_FOR_LOG2N(X)
 #undef X
   }
   return AEFFT_ERR_UNSUPPORTED;
 }
 static int rows_c2r_fast(aefft_ctx* ctx, int log2n, int64_t batch, int Nx, const float2* in, float* out, const float2* tw,
-                         float scale) {
+                         float scale, int ch, long long fstride) {
   switch (log2n) {
-#define X(L) case L: return run_rows_c2r<L>(ctx, batch, Nx, in, out, tw, scale);
+#define X(L) case L: return run_rows_c2r<L>(ctx, batch, Nx, in, out, tw, scale, ch, fstride);
     AEFFT_FOR_LOG2N(X)
 #undef X
   }
@@ -790,6 +796,13 @@ static int set_smem(K kern, size_t bytes) {
 }
 
 int launch_fft_r2c(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float* in, float2* spec) {
+  return launch_fft_r2c_strided(ctx, batch, Nx, Ny, in, 1, (long long)Nx * Ny, spec);
+}
+
+// real images grouped per frame: image (frame f, channel c) at in + f*fstride + c*Nx*Ny, batch = frames*ch.
+// AEFFT_ERR_UNSUPPORTED when the layout is not contiguous and the length has no strided-capable kernel.
+int launch_fft_r2c_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float* in, int ch, long long fstride,
+                           float2* spec) {
   AE_ARG(batch > 0 && is_pow2(Nx) && is_pow2(Ny) && Nx >= 2 && Ny >= 2 && Nx <= 8192 && Ny <= 8192);
   AE_ARG(batch <= 65535);
   const int Nyr = Ny / 2 + 1;
@@ -803,7 +816,9 @@ int launch_fft_r2c(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float* i
     AE_TRY(set_smem(fft_rows_r2c_kernel, smem));
     dim3 grid((Nx / 2 + RP - 1) / RP, (unsigned)batch);
     ProfScope prof(ctx, "fft_rows_r2c", 2.5 * px * log2((double)Ny), 4.0 * px + 8.0 * sp);
-    const int rc = rows_r2c_fast(ctx, ilog2(Ny), batch, Nx, in, spec, twy);
+    const bool contiguous = fstride == (long long)ch * Nx * Ny;
+    const int rc = rows_r2c_fast(ctx, ilog2(Ny), batch, Nx, in, spec, twy, ch, fstride);
+    if (rc == AEFFT_ERR_UNSUPPORTED && !contiguous) return rc;
     if (rc == AEFFT_ERR_UNSUPPORTED) fft_rows_r2c_kernel<<<grid, 256, smem, ctx->stream>>>(in, spec, Nx, Ny, RP, make_plan(Ny), twy);
     else if (rc != AEFFT_OK) return rc;
   }
@@ -825,6 +840,11 @@ int launch_fft_r2c(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float* i
 // spec is NOT modified: the column pass writes into `work` (batch*Nx*Nyr complex).
 int launch_fft_c2r(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float2* spec, float2* work, float* out,
                    float scale) {
+  return launch_fft_c2r_strided(ctx, batch, Nx, Ny, spec, work, out, 1, (long long)Nx * Ny, scale);
+}
+
+int launch_fft_c2r_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float2* spec, float2* work, float* out, int ch,
+                           long long fstride, float scale) {
   AE_ARG(batch > 0 && is_pow2(Nx) && is_pow2(Ny) && Nx >= 2 && Ny >= 2 && Nx <= 8192 && Ny <= 8192);
   AE_ARG(batch <= 65535);
   const int Nyr = Ny / 2 + 1;
@@ -848,7 +868,9 @@ int launch_fft_c2r(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float2* 
     AE_TRY(set_smem(fft_rows_c2r_kernel, smem));
     dim3 grid((Nx / 2 + RP - 1) / RP, (unsigned)batch);
     ProfScope prof(ctx, "fft_rows_c2r", 2.5 * px * log2((double)Ny), 4.0 * px + 8.0 * sp);
-    const int rc = rows_c2r_fast(ctx, ilog2(Ny), batch, Nx, work, out, twy, scale);
+    const bool contiguous = fstride == (long long)ch * Nx * Ny;
+    const int rc = rows_c2r_fast(ctx, ilog2(Ny), batch, Nx, work, out, twy, scale, ch, fstride);
+    if (rc == AEFFT_ERR_UNSUPPORTED && !contiguous) return rc;
     if (rc == AEFFT_ERR_UNSUPPORTED) fft_rows_c2r_kernel<<<grid, 256, smem, ctx->stream>>>(work, out, Nx, Ny, RP, make_plan(Ny), twy, scale);
     else if (rc != AEFFT_OK) return rc;
   }
