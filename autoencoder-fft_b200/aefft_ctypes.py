@@ -165,6 +165,10 @@ class Ctx:
         self._hook = HOOK(tramp)  # keep the trampoline alive
         _chk(lib().aefft_set_gradient_hook(self.h, self._hook, None))
 
+    def set_bin_shard(self, rank: int, world: int):
+        """Frequency-bin sharding of backprop_fft (aefft_set_bin_shard); the gradient hook must then SUM over devices."""
+        _chk(lib().aefft_set_bin_shard(self.h, int(rank), int(world)))
+
     def profile_enable(self, on: bool):
         """Bracket every kernel launch of this ctx with a CUDA event pair (aefft_profile_enable)."""
         _chk(lib().aefft_profile_enable(self.h, 1 if on else 0))

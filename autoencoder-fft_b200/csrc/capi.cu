@@ -299,6 +299,13 @@ int aefft_set_gradient_hook(aefft_ctx* ctx, aefft_gradient_hook_fn fn, void* use
   return AEFFT_OK;
 }
 
+int aefft_set_bin_shard(aefft_ctx* ctx, int rank, int world) {
+  AE_ARG(ctx && world >= 1 && rank >= 0 && rank < world);
+  ctx->shard_rank = rank;
+  ctx->shard_world = world;
+  return AEFFT_OK;
+}
+
 int aefft_set_stream(aefft_ctx* ctx, void* cuda_stream) {
   AE_ARG(ctx);
   AE_CUDA(cudaSetDevice(ctx->device));

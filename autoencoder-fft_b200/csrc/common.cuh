@@ -60,6 +60,7 @@ struct aefft_ctx {
   int64_t launches = 0;
   int precision = AEFFT_PRECISION_FP32;  // arithmetic of the coordinate-space contractions (aefft_set_precision)
   bool profiling = false;
+  int shard_rank = 0, shard_world = 1;  // frequency-bin sharding of aefft_backprop_fft (aefft_set_bin_shard)
   aefft_gradient_hook_fn grad_hook = nullptr;  // data-parallel momentum-space training (aefft_set_gradient_hook)
   void* grad_hook_user = nullptr;
   std::vector<aefft::ProfRec> prof;
@@ -241,15 +242,18 @@ int get_twiddles(aefft_ctx* ctx, int N, const float2** out);
 //   spectrum : spec[n][wx][wy] = sum_{k,l} taps[n][k][l] W_Nx^(wx*i_k) W_Ny^(wy*j_l),  (i_k, j_l) = ((k-Nk/2) mod Nx, (l-Nl/2) mod Ny)
 //   taps     : taps[n][k][l] = scale * sum_{wx,wy} h(wy) Re( spec[n][wx][wy] conj(W_Nx^(wx*i_k)) conj(W_Ny^(wy*j_l)) ),
 //              h = 1 for wy in {0, Ny/2}, else 2  (= shrink_k(C2R(spec)) with the C2R's Hermitian convention)
-int launch_kernel_spectrum_direct(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* taps, float2* spec);
+int launch_kernel_spectrum_direct(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* taps, float2* spec,
+                                  int col0 = 0, int ncols = 0);  // column slab [col0, col0+ncols) (0: whole half spectrum)
 int launch_spectrum_to_taps(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float2* spec, float* taps,
-                            float scale);
+                            float scale, int col0 = 0, int ncols = 0);
+int launch_spec_slab(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, const float2* full, float2* slab, int col0, int ncols);
 int launch_pad(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* taps, float* img);
 int launch_shrink(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* img, float* taps);
 int launch_fft_update(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, float* c, float* f, float* b, float* p,
                       const float* dck, const float* dfk, const float* db, const float* dp, float* Dc, float* Df, float* Db,
                       float* Dp, float del, int maxdiff, float* div_scratch);
-int launch_spec_mse(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx, int Ny, const float2* Xt, const float2* O, float* out);
+int launch_spec_mse(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx, int Ny, const float2* Xt, const float2* O, float* out,
+                    int col0 = 0, int ncols = 0);
 
 // ---- host orchestration shared by capi.cu and net.cu ------------------------------------------------
 int64_t gbuf_len(int mode, int dD, int dM, int Nk, int Nl);

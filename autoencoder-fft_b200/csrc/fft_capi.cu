@@ -16,29 +16,33 @@ static bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 // Evaluated directly from the Nk x Nl taps (pruned DFT): mathematically the same spectrum, no padded image, one write.
 // Batches above the grid limit and taps beyond the pruned kernel's envelope go through pad_k + R2C.
 static int kernel_spectrum_dev(aefft_ctx* ctx, int64_t n_img, int Nk, int Nl, int Nx, int Ny, const float* taps, float* img,
-                               float2* spec) {
-  if (Nk <= 8 && Nl <= 8 && !getenv("AEFFT_NO_PRUNED_DFT")) {
-    const int64_t S = (int64_t)Nx * (Ny / 2 + 1);
+                               float2* spec, int col0 = 0, int ncols = 0) {
+  const bool slab = ncols > 0 && ncols != Ny / 2 + 1;
+  if (Nk <= 8 && Nl <= 8 && (slab || !getenv("AEFFT_NO_PRUNED_DFT"))) {
+    const int64_t S = (int64_t)Nx * (ncols > 0 ? ncols : Ny / 2 + 1);
     for (int64_t n0 = 0; n0 < n_img; n0 += 65535) {
       const int64_t cnt = n_img - n0 < 65535 ? n_img - n0 : 65535;
-      AE_TRY(launch_kernel_spectrum_direct(ctx, cnt, Nx, Ny, Nk, Nl, taps + n0 * Nk * Nl, spec + n0 * S));
+      AE_TRY(launch_kernel_spectrum_direct(ctx, cnt, Nx, Ny, Nk, Nl, taps + n0 * Nk * Nl, spec + n0 * S, col0, ncols));
     }
     return AEFFT_OK;
   }
+  if (slab) { set_error("bin-sharded kernel spectra need Nk, Nl <= 8"); return AEFFT_ERR_UNSUPPORTED; }
   AE_TRY(launch_pad(ctx, n_img, Nx, Ny, Nk, Nl, taps, img));
   return launch_fft_r2c(ctx, n_img, Nx, Ny, img, spec);
 }
 // taps = scale * shrink_k(C2R(spec)) for n_img spectra
 static int spectrum_taps_dev(aefft_ctx* ctx, int64_t n_img, int Nk, int Nl, int Nx, int Ny, const float2* spec, float2* work,
-                             float* img, float* taps, float scale) {
-  if (Nk <= 8 && Nl <= 8 && !getenv("AEFFT_NO_PRUNED_DFT")) {
-    const int64_t S = (int64_t)Nx * (Ny / 2 + 1);
+                             float* img, float* taps, float scale, int col0 = 0, int ncols = 0) {
+  const bool slab = ncols > 0 && ncols != Ny / 2 + 1;
+  if (Nk <= 8 && Nl <= 8 && (slab || !getenv("AEFFT_NO_PRUNED_DFT"))) {
+    const int64_t S = (int64_t)Nx * (ncols > 0 ? ncols : Ny / 2 + 1);
     for (int64_t n0 = 0; n0 < n_img; n0 += 65535) {
       const int64_t cnt = n_img - n0 < 65535 ? n_img - n0 : 65535;
-      AE_TRY(launch_spectrum_to_taps(ctx, cnt, Nx, Ny, Nk, Nl, spec + n0 * S, taps + n0 * Nk * Nl, scale));
+      AE_TRY(launch_spectrum_to_taps(ctx, cnt, Nx, Ny, Nk, Nl, spec + n0 * S, taps + n0 * Nk * Nl, scale, col0, ncols));
     }
     return AEFFT_OK;
   }
+  if (slab) { set_error("bin-sharded kernel gradients need Nk, Nl <= 8"); return AEFFT_ERR_UNSUPPORTED; }
   AE_TRY(launch_fft_c2r(ctx, n_img, Nx, Ny, spec, work, img, scale));
   return launch_shrink(ctx, n_img, Nx, Ny, Nk, Nl, img, taps);
 }
@@ -291,7 +295,19 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
   AE_ARG(B > 0 && dD > 0 && dM > 0 && pow2(Nx) && pow2(Ny) && Nk <= Nx && Nl <= Ny && n_iter >= 0);
   AE_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  const int64_t S = (int64_t)Nx * (Ny / 2 + 1);
+  // frequency-bin sharding (aefft_set_bin_shard): this device owns the spectrum columns [col0, col0+ncols) of every
+  // image; every per-bin kernel below then runs on the slab only, the kernel-space gradient block and the mse are
+  // partial sums that the gradient hook adds over the devices.  Unsharded: the whole half spectrum.
+  const int Nyr = Ny / 2 + 1;
+  const int world = ctx->shard_world, srank = ctx->shard_rank;
+  const int col0 = (int)((long long)srank * Nyr / world), ncols = (int)((long long)(srank + 1) * Nyr / world) - col0;
+  const bool sharded = world > 1;
+  if (sharded) {
+    AE_ARG(ncols > 0 && !cfreq && !ffreq && loc == AEFFT_DEVICE);
+    if (!ctx->grad_hook) { set_error("bin-sharded aefft_backprop_fft needs a gradient hook (sum over devices)"); return AEFFT_ERR_ARG; }
+  }
+  const bool own_dc = col0 == 0;  // the DC bin (biases, db/dp) lives on the device that owns column 0
+  const int64_t S = (int64_t)Nx * ncols;
   const size_t P = (size_t)Nx * Ny, nC = (size_t)dM * dD * Nk * Nl, nKS = (size_t)dM * dD * S;
   const size_t nXs = (size_t)B * dD * S, nHs = (size_t)B * dM * S;
   const cudaMemcpyKind k_in = loc == AEFFT_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
@@ -329,8 +345,12 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
       AE_CUDA(cudaMemcpyAsync(real, src, (size_t)B * dD * P * sizeof(float), cudaMemcpyHostToDevice, st));
       d = real;
     }
-    if (in_fstride) return launch_fft_r2c_strided(ctx, B * dD, Nx, Ny, d, dD, (long long)in_fstride, dst);
-    return launch_fft_r2c(ctx, B * dD, Nx, Ny, d, dst);
+    float2* tgt = dst;
+    if (sharded) AE_TRY(ctx->getT("bpf_full", (size_t)B * dD * Nx * Nyr, &tgt));  // full spectrum, then keep the slab
+    if (in_fstride) AE_TRY(launch_fft_r2c_strided(ctx, B * dD, Nx, Ny, d, dD, (long long)in_fstride, tgt));
+    else AE_TRY(launch_fft_r2c(ctx, B * dD, Nx, Ny, d, tgt));
+    if (sharded) AE_TRY(launch_spec_slab(ctx, B * dD, Nx, Ny, tgt, dst, col0, ncols));
+    return AEFFT_OK;
   };
   AE_TRY(load_fft(in, q.X));
   const float2* Xt = q.X;
@@ -341,13 +361,23 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
   AE_TRY(load_fft(out, q.O));
   // kernel spectra: the caller's cache (load_cfreq :1434-1435) or derived from c,f
   if (cfreq) AE_CUDA(cudaMemcpyAsync(q.C, cfreq, nKS * sizeof(float2), k_in, st));
-  else AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C));
+  else AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C, col0, ncols));
   if (ffreq) AE_CUDA(cudaMemcpyAsync(q.F, ffreq, nKS * sizeof(float2), k_in, st));
-  else AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F));
+  else AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F, col0, ncols));
   const float norm = (float)Nx * (float)Ny;
-  AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse));  // "mse fft:" (:1440)
+  auto reduce_over_devices = [&](float* block, int64_t n) -> int {
+    if (ctx->grad_hook && ctx->grad_hook(ctx->grad_hook_user, block, n) != 0) {
+      set_error("aefft_backprop_fft: gradient hook failed");
+      return AEFFT_ERR_ARG;
+    }
+    return AEFFT_OK;
+  };
+  const float* bias_b = own_dc ? db_w : nullptr;
+  const float* bias_p = own_dc ? dp_w : nullptr;
+  AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse, col0, ncols));  // "mse fft:" (:1440)
+  if (sharded) AE_TRY(reduce_over_devices(q.mse, 1));
   // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1)
-  AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, db_w, norm, q.H));
+  AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, bias_b, norm, q.H));
   const float del = 0.1f * del0;                                        // :1445
   const double Norm = (double)norm * 2.0 * dM * dD * (double)Nx * Ny;   // :399
   const float gscale = (float)(1.0 / (Norm * (double)B));
@@ -356,32 +386,36 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
     AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.O, Xt, q.F, S, (int64_t)dM * S, 1, 1.f, nullptr, 0.f, q.G));
     // dC[m][d] = G[m] conj(X[d]) / Norm ; dF[d][m] = E[d] conj(H-hat[m]) / Norm, averaged over frames
     AE_TRY(launch_spec_outer(ctx, B, dM, dD, S, q.G, nullptr, q.X, 1.f, nullptr, 0.f, gscale, q.dCF));
-    AE_TRY(launch_spec_outer(ctx, B, dD, dM, S, q.O, Xt, q.H, (float)dM, db_w, -(float)(dM - 1) * norm, gscale, q.dCF + nKS));
-    AE_TRY(launch_spec_dc_sums(ctx, B, dM, dD, S, q.G, q.O, Xt, q.db, q.dp, (float)((double)norm / (Norm * (double)B))));
+    AE_TRY(launch_spec_outer(ctx, B, dD, dM, S, q.O, Xt, q.H, (float)dM, bias_b, -(float)(dM - 1) * norm, gscale, q.dCF + nKS));
+    if (own_dc) AE_TRY(launch_spec_dc_sums(ctx, B, dM, dD, S, q.G, q.O, Xt, q.db, q.dp, (float)((double)norm / (Norm * (double)B))));
+    else AE_CUDA(cudaMemsetAsync(q.db, 0, (size_t)(dM + dD) * sizeof(float), st));
     // kernel-space gradients: C2R (unnormalised) + shrink_k (:1219-1226)
-    AE_TRY(spectrum_taps_dev(ctx, 2 * (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.dCF, q.work, q.img, q.taps, 1.f));
-    // data-parallel ranks average the raw gradient block here, before the non-linear clip
-    if (ctx->grad_hook && ctx->grad_hook(ctx->grad_hook_user, q.taps, (int64_t)(2 * nC + dM + dD)) != 0) {
-      set_error("aefft_backprop_fft: gradient hook failed");
-      return AEFFT_ERR_ARG;
-    }
+    AE_TRY(spectrum_taps_dev(ctx, 2 * (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.dCF, q.work, q.img, q.taps, 1.f, col0, ncols));
+    // data-parallel ranks average (bin-sharded devices: add) the raw gradient block here, before the non-linear clip
+    AE_TRY(reduce_over_devices(q.taps, (int64_t)(2 * nC + dM + dD)));
     // clipped-momentum update in kernel space (+ multiobjective term)
     AE_TRY(launch_fft_update(ctx, dM, dD, Nk, Nl, dc_w, df_w, db_w, dp_w, q.taps, q.taps + nC, q.db, q.dp, q.Dc, q.Df, q.Db,
                              q.Dp, del, maxdiff, q.div));
     // new kernel spectra: pad_k + R2C (:1274-1282); c and f are adjacent in wts -> one batched transform
-    AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C));
-    AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F));
+    AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C, col0, ncols));
+    AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F, col0, ncols));
     // re-forward (:1460-1461) and mse (:1463)
-    AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, db_w, norm, q.H));
-    AE_TRY(launch_spec_contract(ctx, B, dM, dD, S, q.H, nullptr, q.F, (int64_t)dM * S, S, 0, 1.f / (float)dD, dp_w, norm, q.O));
-    AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse + n + 1));
+    AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, bias_b, norm, q.H));
+    AE_TRY(launch_spec_contract(ctx, B, dM, dD, S, q.H, nullptr, q.F, (int64_t)dM * S, S, 0, 1.f / (float)dD, bias_p, norm, q.O));
+    AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse + n + 1, col0, ncols));
+    if (sharded) AE_TRY(reduce_over_devices(q.mse + n + 1, 1));
   }
   // store_cfreq (:1484-1485) and export_cfreq (:1487-1488: c,f re-derived from the spectra: C2R/(NxNy) + kernel_invpad)
   if (cfreq) AE_CUDA(cudaMemcpyAsync(cfreq, q.C, nKS * sizeof(float2), k_out, st));
   if (ffreq) AE_CUDA(cudaMemcpyAsync(ffreq, q.F, nKS * sizeof(float2), k_out, st));
-  AE_TRY(spectrum_taps_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.C, q.work, q.img, q.taps, 1.f / norm));
-  AE_TRY(spectrum_taps_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.F, q.work, q.img + (size_t)dM * dD * P, q.taps + nC,
-                           1.f / norm));
+  if (sharded) {
+    // the kernels in tap space are the master copy (identical on every device); no device holds a whole spectrum
+    AE_CUDA(cudaMemcpyAsync(q.taps, wts, 2 * nC * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    AE_TRY(spectrum_taps_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.C, q.work, q.img, q.taps, 1.f / norm));
+    AE_TRY(spectrum_taps_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.F, q.work, q.img + (size_t)dM * dD * P, q.taps + nC,
+                             1.f / norm));
+  }
   AE_CUDA(cudaMemcpyAsync(c, q.taps, nC * sizeof(float), k_out, st));
   AE_CUDA(cudaMemcpyAsync(f, q.taps + nC, nC * sizeof(float), k_out, st));
   AE_CUDA(cudaMemcpyAsync(b, db_w, dM * sizeof(float), k_out, st));

@@ -597,11 +597,11 @@ template <int NK, int NL>
 __global__ void __launch_bounds__(256) kernel_spectrum_direct_kernel(const float* __restrict__ taps, float2* __restrict__ spec,
                                                                       int Nx, int Ny, int Nk, int Nl,
                                                                       const float2* __restrict__ twx,
-                                                                      const float2* __restrict__ twy) {
+                                                                      const float2* __restrict__ twy, int col0, int Nyr) {
+  // (col0, Nyr): the slab of spectrum columns [col0, col0 + Nyr) this device owns (whole half spectrum: 0, Ny/2+1)
   __shared__ float c[PD_MAXT * PD_MAXT];
   __shared__ float2 exs[PD_MAXT];
   const int nk = NK ? NK : Nk, nl = NL ? NL : Nl;
-  const int Nyr = Ny / 2 + 1;
   const unsigned n = blockIdx.z, wx = blockIdx.y;
   if (threadIdx.x < nk * nl) c[threadIdx.x] = taps[(size_t)n * nk * nl + threadIdx.x];
   if (threadIdx.x >= 64 && threadIdx.x < 64 + nk) {
@@ -609,8 +609,9 @@ __global__ void __launch_bounds__(256) kernel_spectrum_direct_kernel(const float
     exs[k] = __ldg(twx + ((wx * ((k - nk / 2) & (Nx - 1))) & (Nx - 1)));
   }
   __syncthreads();
-  const int wy = blockIdx.x * blockDim.x + threadIdx.x;
-  if (wy >= Nyr) return;
+  const int wl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wl >= Nyr) return;
+  const int wy = col0 + wl;
   float2 ey[NL ? NL : PD_MAXT];
 #pragma unroll
   for (int l = 0; l < (NL ? NL : PD_MAXT); l++)
@@ -631,24 +632,24 @@ __global__ void __launch_bounds__(256) kernel_spectrum_direct_kernel(const float
       cfma(acc, exs[k], t);
     }
   }
-  spec[((size_t)n * Nx + wx) * Nyr + wy] = acc;
+  spec[((size_t)n * Nx + wx) * Nyr + wl] = acc;
 }
 
 int launch_kernel_spectrum_direct(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* taps,
-                                  float2* spec) {
+                                  float2* spec, int col0, int ncols) {
   AE_ARG(n_img > 0 && n_img <= 65535 && Nx <= 65535 && Nk <= PD_MAXT && Nl <= PD_MAXT && Nk <= Nx && Nl <= Ny);
   const float2 *twx, *twy;
   AE_TRY(get_twiddles(ctx, Nx, &twx));
   AE_TRY(get_twiddles(ctx, Ny, &twy));
-  const int Nyr = Ny / 2 + 1;
+  const int Nyr = ncols > 0 ? ncols : Ny / 2 + 1;
   const long long S = (long long)Nx * Nyr;
   ProfScope prof(ctx, "kernel_spectrum", 8.0 * n_img * S * (Nk + Nk * Nl / 4.0), 8.0 * n_img * S);
   const int threads = Nyr >= 256 ? 256 : (Nyr > 128 ? 256 : 128);
   dim3 grid((Nyr + threads - 1) / threads, Nx, (unsigned)n_img);
-  if (Nk == 5 && Nl == 5) kernel_spectrum_direct_kernel<5, 5><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy);
-  else if (Nk == 3 && Nl == 3) kernel_spectrum_direct_kernel<3, 3><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy);
-  else if (Nk == 7 && Nl == 7) kernel_spectrum_direct_kernel<7, 7><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy);
-  else kernel_spectrum_direct_kernel<0, 0><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy);
+  if (Nk == 5 && Nl == 5) kernel_spectrum_direct_kernel<5, 5><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr);
+  else if (Nk == 3 && Nl == 3) kernel_spectrum_direct_kernel<3, 3><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr);
+  else if (Nk == 7 && Nl == 7) kernel_spectrum_direct_kernel<7, 7><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr);
+  else kernel_spectrum_direct_kernel<0, 0><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr);
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
   return AEFFT_OK;
@@ -660,10 +661,9 @@ int launch_kernel_spectrum_direct(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny,
 template <int NK, int NL>
 __global__ void __launch_bounds__(256) spectrum_to_taps_kernel(const float2* __restrict__ spec, float* __restrict__ part, int Nx,
                                                                 int Ny, int Nk, int Nl, const float2* __restrict__ twx,
-                                                                const float2* __restrict__ twy) {
+                                                                const float2* __restrict__ twy, int col0, int Nyr) {
   constexpr int TK = NK ? NK : PD_MAXT, TL = NL ? NL : PD_MAXT;
   const int nk = NK ? NK : Nk, nl = NL ? NL : Nl;
-  const int Nyr = Ny / 2 + 1;
   const unsigned n = blockIdx.y;
   const int nsplit = gridDim.x, sp = blockIdx.x;
   const int r_lo = (int)((long long)Nx * sp / nsplit), r_hi = (int)((long long)Nx * (sp + 1) / nsplit);
@@ -671,14 +671,15 @@ __global__ void __launch_bounds__(256) spectrum_to_taps_kernel(const float2* __r
   float g[TK * TL];
 #pragma unroll
   for (int t = 0; t < TK * TL; t++) g[t] = 0.f;
-  for (int wy = threadIdx.x; wy < Nyr; wy += blockDim.x) {
+  for (int wl = threadIdx.x; wl < Nyr; wl += blockDim.x) {
+    const int wy = col0 + wl;
     const float h = (wy == 0 || wy == Ny / 2) ? 1.f : 2.f;
     float2 ey[TL];
 #pragma unroll
     for (int l = 0; l < TL; l++)
       if (l < nl) ey[l] = __ldg(twy + ((wy * ((l - nl / 2) & (Ny - 1))) & (Ny - 1)));
     for (int wx = r_lo; wx < r_hi; wx++) {
-      float2 v = z[(size_t)wx * Nyr + wy];
+      float2 v = z[(size_t)wx * Nyr + wl];
       v.x *= h; v.y *= h;
       float2 a[TL];  // v * conj(Ey[l])
 #pragma unroll
@@ -724,12 +725,12 @@ __global__ void spectrum_to_taps_final_kernel(const float* __restrict__ part, fl
 }
 
 int launch_spectrum_to_taps(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float2* spec, float* taps,
-                            float scale) {
+                            float scale, int col0, int ncols) {
   AE_ARG(n_img > 0 && n_img <= 65535 && Nk <= PD_MAXT && Nl <= PD_MAXT && Nk <= Nx && Nl <= Ny);
   const float2 *twx, *twy;
   AE_TRY(get_twiddles(ctx, Nx, &twx));
   AE_TRY(get_twiddles(ctx, Ny, &twy));
-  const int Nyr = Ny / 2 + 1;
+  const int Nyr = ncols > 0 ? ncols : Ny / 2 + 1;
   const long long S = (long long)Nx * Nyr;
   // enough CTAs to fill the machine (row ranges of >= 8 rows)
   int nsplit = (int)((4LL * ctx->sm_count + n_img - 1) / n_img);
@@ -741,10 +742,10 @@ int launch_spectrum_to_taps(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int N
   {
     ProfScope prof(ctx, "spectrum_to_taps", 2.0 * n_img * S * (4.0 * Nl + 2.0 * Nk * Nl), 8.0 * n_img * S);
     dim3 grid(nsplit, (unsigned)n_img);
-    if (Nk == 5 && Nl == 5) spectrum_to_taps_kernel<5, 5><<<grid, threads, 0, ctx->stream>>>(spec, part, Nx, Ny, Nk, Nl, twx, twy);
-    else if (Nk == 3 && Nl == 3) spectrum_to_taps_kernel<3, 3><<<grid, threads, 0, ctx->stream>>>(spec, part, Nx, Ny, Nk, Nl, twx, twy);
-    else if (Nk == 7 && Nl == 7) spectrum_to_taps_kernel<7, 7><<<grid, threads, 0, ctx->stream>>>(spec, part, Nx, Ny, Nk, Nl, twx, twy);
-    else spectrum_to_taps_kernel<0, 0><<<grid, threads, 0, ctx->stream>>>(spec, part, Nx, Ny, Nk, Nl, twx, twy);
+    if (Nk == 5 && Nl == 5) spectrum_to_taps_kernel<5, 5><<<grid, threads, 0, ctx->stream>>>(spec, part, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr);
+    else if (Nk == 3 && Nl == 3) spectrum_to_taps_kernel<3, 3><<<grid, threads, 0, ctx->stream>>>(spec, part, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr);
+    else if (Nk == 7 && Nl == 7) spectrum_to_taps_kernel<7, 7><<<grid, threads, 0, ctx->stream>>>(spec, part, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr);
+    else spectrum_to_taps_kernel<0, 0><<<grid, threads, 0, ctx->stream>>>(spec, part, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr);
   }
   const long long total = (long long)n_img * Nk * Nl;
   spectrum_to_taps_final_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(part, taps, total, nsplit, Nk * Nl, scale);
@@ -870,14 +871,32 @@ int launch_fft_update(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, float* c, 
   return AEFFT_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ column slabs
+// Frequency-bin sharding: device r of G owns the spectrum columns [col0, col0+ncols); slab[img][wx][l] = full[img][wx][col0+l]
+__global__ void spec_slab_kernel(const float2* __restrict__ full, float2* __restrict__ slab, long long rows, int Nyr, int col0,
+                                 int ncols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * ncols) return;
+  const long long r = idx / ncols;
+  const int l = (int)(idx - r * ncols);
+  slab[idx] = full[r * Nyr + col0 + l];
+}
+int launch_spec_slab(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, const float2* full, float2* slab, int col0, int ncols) {
+  const long long rows = (long long)n_img * Nx, total = rows * ncols;
+  spec_slab_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(full, slab, rows, Ny / 2 + 1, col0, ncols);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ mse
 // calc_mse + thrust::reduce (:480-498, 1178-1192): sum_w |Xt-O|^2 / n_w, n_w = dD*Nx*Ny halved for 0<j<Nyr-1.
 // Deterministic two-stage reduction in double; *out = scale * total.
-__global__ void spec_mse_kernel(const float2* __restrict__ Xt, const float2* __restrict__ O, long long total, int Nyr,
-                                double* __restrict__ part) {
+__global__ void spec_mse_kernel(const float2* __restrict__ Xt, const float2* __restrict__ O, long long total, int ncols,
+                                int col0, int Nyr, double* __restrict__ part) {
   double s = 0.0;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int j = idx % Nyr;
+    const int j = col0 + (int)(idx % ncols);  // global spectrum column (the device may own a slab of columns)
     float2 a = Xt[idx], b = O[idx];
     float dx = a.x - b.x, dy = a.y - b.y;
     float v = dx * dx + dy * dy;
@@ -905,15 +924,17 @@ __global__ void spec_mse_final_kernel(const double* __restrict__ part, int n, do
   if (threadIdx.x == 0) *out = (float)(red[0] * scale);
 }
 
-int launch_spec_mse(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx, int Ny, const float2* Xt, const float2* O, float* out) {
+int launch_spec_mse(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx, int Ny, const float2* Xt, const float2* O, float* out,
+                    int col0, int ncols) {
   const int Nyr = Ny / 2 + 1;
-  const long long total = (long long)B * dD * Nx * Nyr;
+  if (ncols <= 0) ncols = Nyr;
+  const long long total = (long long)B * dD * Nx * ncols;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4 * ctx->sm_count) blocks = 4 * ctx->sm_count;
   double* part;
   AE_TRY(ctx->getT("mse_part", (size_t)blocks, &part));
   ProfScope prof(ctx, "spec_mse", 0.0, 16.0 * total);
-  spec_mse_kernel<<<blocks, 256, 0, ctx->stream>>>(Xt, O, total, Nyr, part);
+  spec_mse_kernel<<<blocks, 256, 0, ctx->stream>>>(Xt, O, total, ncols, col0, Nyr, part);
   // per frame: [sum |.|^2 / (dD Nx Ny)] / (2 dM Nx Ny); mean over frames
   const double scale = 1.0 / ((double)dD * Nx * Ny) / (2.0 * dM * Nx * Ny) / (double)B;
   spec_mse_final_kernel<<<1, 256, 0, ctx->stream>>>(part, blocks, scale, out);

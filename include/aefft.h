@@ -169,6 +169,13 @@ int aefft_autoenc_fft(aefft_ctx* ctx, int loc, int64_t B, int n_conv, const int*
  * reference's single-device algorithm.  The reduction precedes the non-linear clip g/max(10,|g|). */
 typedef int (*aefft_gradient_hook_fn)(void* user, float* dev_block, int64_t n_floats);
 int aefft_set_gradient_hook(aefft_ctx* ctx, aefft_gradient_hook_fn fn, void* user);
+/* Frequency-bin sharding of aefft_backprop_fft over `world` devices (BASELINE config 4): every device receives ALL frames
+ * (device pointers), transforms them once per call and keeps only its slab of spectrum columns
+ * [rank*Nyr/world, (rank+1)*Nyr/world); the per-bin contractions, the pruned kernel DFTs and the mse then run on the
+ * slab.  The gradient hook (required) is called on the PARTIAL gradient block and on each mse value and must ADD them
+ * over the devices (NCCL all-reduce(sum) on the ctx stream); kernels / biases end identical everywhere.  The one-off
+ * frame transform is amortised over the n_iter (reference: 100) iterations of a call.  world == 1 restores the default. */
+int aefft_set_bin_shard(aefft_ctx* ctx, int rank, int world);
 
 /* backprop_fft (fft_backproplib.cu:1381-1511): n_iter (reference: 100) iterations of spectral gradients ->
  * kernel-space clipped-momentum update (lr 0.1*del0, alpha 0.9, momentum zeroed per call) -> re-forward.

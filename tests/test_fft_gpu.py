@@ -225,3 +225,65 @@ def test_gradient_hook_two_rank_emulation(ctx):
         ctx.set_gradient_hook(None)
     for k in "cfbp":
         assert O.rel_l2(w[k], full[k]) < 1e-6, k
+
+
+def test_bin_sharding_two_device_emulation(ctx):
+    """aefft_set_bin_shard: two 'devices' each own half of the spectrum columns; adding their partial gradient blocks
+    (and partial mse values) in the hook reproduces the single-device iteration."""
+    dims = (4, 3, 5, 5, 16, 32)
+    dM, dD, Nk, Nl, Nx, Ny = dims
+    cs = fft_case(9, *dims, B=3)
+    n_block = 2 * dM * dD * Nk * Nl + dM + dD
+    full = {k: cs[k].copy() for k in "cfbp"}
+    want_trace = ctx.backprop_fft(cs["inp"], cs["inp"], cs["out"], full["c"], full["f"], full["b"], full["p"], 0.2, 0, 1)
+
+    def run(rank, hook):
+        dev = {k: ctx.to_device(cs[k]) for k in ("inp", "out", "c", "f", "b", "p")}
+        ctx.set_bin_shard(rank, 2)
+        ctx.set_gradient_hook(hook)
+        try:
+            trace = ctx.backprop_fft(dev["inp"], dev["inp"], dev["out"], dev["c"], dev["f"], dev["b"], dev["p"], 0.2, 0, 1,
+                                     loc=A.DEVICE)
+        finally:
+            ctx.set_gradient_hook(None)
+            ctx.set_bin_shard(0, 1)
+        res = {k: dev[k].numpy() for k in "cfbp"}
+        for d in dev.values():
+            d.free()
+        return trace, res
+
+    parts = {0: [], 1: []}
+
+    def capture(rank):
+        def hook(ptr, n):
+            host = np.empty(n, np.float32)
+            ctx.memcpy(host.ctypes.data, ptr, n * 4, 1)
+            parts[rank].append(host)
+        return hook
+
+    run(0, capture(0))
+    run(1, capture(1))
+    assert [len(a) for a in parts[0]] == [1, n_block, 1] and [len(a) for a in parts[1]] == [1, n_block, 1]
+    sums = [a + b for a, b in zip(parts[0], parts[1])]
+    post = {}
+
+    def allreduce_sum(rank):
+        calls = []
+
+        def hook(ptr, n):
+            k = len(calls)
+            calls.append(n)
+            if k < 2:  # initial mse and the gradient block: play the all-reduce(sum) with the captured partials
+                ctx.memcpy(ptr, sums[k].ctypes.data, n * 4, 0)
+            else:      # mse after the (now correct) update: keep this device's partial value for the check below
+                host = np.empty(n, np.float32)
+                ctx.memcpy(host.ctypes.data, ptr, n * 4, 1)
+                post[rank] = host
+        return hook
+
+    for rank in (0, 1):
+        trace, got = run(rank, allreduce_sum(rank))
+        assert np.isclose(trace[0], want_trace[0], rtol=1e-5)
+        for k in "cfbp":
+            assert O.rel_l2(got[k], full[k]) < 1e-6, (rank, k)
+    assert np.isclose(post[0][0] + post[1][0], want_trace[1], rtol=1e-5), (post, want_trace)
