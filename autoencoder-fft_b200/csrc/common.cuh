@@ -252,6 +252,9 @@ int launch_shrink(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl,
 int launch_fft_update(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, float* c, float* f, float* b, float* p,
                       const float* dck, const float* dfk, const float* db, const float* dp, float* Dc, float* Df, float* Db,
                       float* Dp, float del, int maxdiff, float* div_scratch);
+int launch_gradient_diff(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, const float* c, const float* f, const float* b,
+                         const float* p, float* div, int rank, int world);
+int launch_axpby(aefft_ctx* ctx, float* y, const float* x, float a, float b, long long n);
 int launch_spec_mse(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx, int Ny, const float2* Xt, const float2* O, float* out,
                     int col0 = 0, int ncols = 0);
 

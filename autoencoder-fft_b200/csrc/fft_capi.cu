@@ -391,11 +391,18 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
     else AE_CUDA(cudaMemsetAsync(q.db, 0, (size_t)(dM + dD) * sizeof(float), st));
     // kernel-space gradients: C2R (unnormalised) + shrink_k (:1219-1226)
     AE_TRY(spectrum_taps_dev(ctx, 2 * (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.dCF, q.work, q.img, q.taps, 1.f, col0, ncols));
+    // bin-sharded devices also split the kernel-space multiobjective term: each folds its share into its partial block,
+    // g = 1*g_mse - 10*g_div (:1252), so that the sum over devices is the whole combined gradient
+    const bool fold_div = sharded && maxdiff;
+    if (fold_div) {
+      AE_TRY(launch_gradient_diff(ctx, dM, dD, Nk, Nl, dc_w, df_w, db_w, dp_w, q.div, srank, world));
+      AE_TRY(launch_axpby(ctx, q.taps, q.div, 1.f, -10.f, (long long)(2 * nC + dM + dD)));
+    }
     // data-parallel ranks average (bin-sharded devices: add) the raw gradient block here, before the non-linear clip
     AE_TRY(reduce_over_devices(q.taps, (int64_t)(2 * nC + dM + dD)));
     // clipped-momentum update in kernel space (+ multiobjective term)
     AE_TRY(launch_fft_update(ctx, dM, dD, Nk, Nl, dc_w, df_w, db_w, dp_w, q.taps, q.taps + nC, q.db, q.dp, q.Dc, q.Df, q.Db,
-                             q.Dp, del, maxdiff, q.div));
+                             q.Dp, del, fold_div ? 0 : maxdiff, q.div));
     // new kernel spectra: pad_k + R2C (:1274-1282); c and f are adjacent in wts -> one batched transform
     AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C, col0, ncols));
     AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F, col0, ncols));

@@ -592,25 +592,23 @@ constexpr int PD_MAXT = 8;  // taps per axis
 // Both kernels are instantiated for the tap counts the reference's parameter file can produce (3, 5, 7 per axis) plus a
 // generic 8 x 8 variant; index arithmetic is 32-bit (bins per image < 2^31).
 
-// one CTA row of 256 threads per 256 consecutive bins of one spectrum row pair: grid (ceil(Nyr/256), Nx, n_img)
+// 256 threads = TW columns x (256/TW) rows of one image's (slab of the) half spectrum: grid (col tiles, row tiles, n_img)
 template <int NK, int NL>
 __global__ void __launch_bounds__(256) kernel_spectrum_direct_kernel(const float* __restrict__ taps, float2* __restrict__ spec,
                                                                       int Nx, int Ny, int Nk, int Nl,
                                                                       const float2* __restrict__ twx,
-                                                                      const float2* __restrict__ twy, int col0, int Nyr) {
+                                                                      const float2* __restrict__ twy, int col0, int Nyr,
+                                                                      int log2tw) {
   // (col0, Nyr): the slab of spectrum columns [col0, col0 + Nyr) this device owns (whole half spectrum: 0, Ny/2+1)
   __shared__ float c[PD_MAXT * PD_MAXT];
-  __shared__ float2 exs[PD_MAXT];
   const int nk = NK ? NK : Nk, nl = NL ? NL : Nl;
-  const unsigned n = blockIdx.z, wx = blockIdx.y;
+  const unsigned n = blockIdx.z;
   if (threadIdx.x < nk * nl) c[threadIdx.x] = taps[(size_t)n * nk * nl + threadIdx.x];
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + nk) {
-    const int k = threadIdx.x - 64;
-    exs[k] = __ldg(twx + ((wx * ((k - nk / 2) & (Nx - 1))) & (Nx - 1)));
-  }
   __syncthreads();
-  const int wl = blockIdx.x * blockDim.x + threadIdx.x;
-  if (wl >= Nyr) return;
+  const int tw = 1 << log2tw;
+  const int wl = blockIdx.x * tw + (threadIdx.x & (tw - 1));
+  const int wx = blockIdx.y * (256 >> log2tw) + (threadIdx.x >> log2tw);
+  if (wl >= Nyr || wx >= Nx) return;
   const int wy = col0 + wl;
   float2 ey[NL ? NL : PD_MAXT];
 #pragma unroll
@@ -620,6 +618,7 @@ __global__ void __launch_bounds__(256) kernel_spectrum_direct_kernel(const float
 #pragma unroll
   for (int k = 0; k < (NK ? NK : PD_MAXT); k++) {
     if (k < nk) {
+      const float2 ex = __ldg(twx + ((wx * ((k - nk / 2) & (Nx - 1))) & (Nx - 1)));
       float2 t = make_float2(0.f, 0.f);  // sum_l c[k][l] Ey[l]
 #pragma unroll
       for (int l = 0; l < (NL ? NL : PD_MAXT); l++) {
@@ -629,7 +628,7 @@ __global__ void __launch_bounds__(256) kernel_spectrum_direct_kernel(const float
           t.y = fmaf(cv, ey[l].y, t.y);
         }
       }
-      cfma(acc, exs[k], t);
+      cfma(acc, ex, t);
     }
   }
   spec[((size_t)n * Nx + wx) * Nyr + wl] = acc;
@@ -644,12 +643,14 @@ int launch_kernel_spectrum_direct(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny,
   const int Nyr = ncols > 0 ? ncols : Ny / 2 + 1;
   const long long S = (long long)Nx * Nyr;
   ProfScope prof(ctx, "kernel_spectrum", 8.0 * n_img * S * (Nk + Nk * Nl / 4.0), 8.0 * n_img * S);
-  const int threads = Nyr >= 256 ? 256 : (Nyr > 128 ? 256 : 128);
-  dim3 grid((Nyr + threads - 1) / threads, Nx, (unsigned)n_img);
-  if (Nk == 5 && Nl == 5) kernel_spectrum_direct_kernel<5, 5><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr);
-  else if (Nk == 3 && Nl == 3) kernel_spectrum_direct_kernel<3, 3><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr);
-  else if (Nk == 7 && Nl == 7) kernel_spectrum_direct_kernel<7, 7><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr);
-  else kernel_spectrum_direct_kernel<0, 0><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr);
+  int log2tw = 8;
+  while (log2tw > 3 && (1 << (log2tw - 1)) >= Nyr) log2tw--;
+  const int threads = 256, tw = 1 << log2tw, rows = 256 >> log2tw;
+  dim3 grid((Nyr + tw - 1) / tw, (Nx + rows - 1) / rows, (unsigned)n_img);
+  if (Nk == 5 && Nl == 5) kernel_spectrum_direct_kernel<5, 5><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr, log2tw);
+  else if (Nk == 3 && Nl == 3) kernel_spectrum_direct_kernel<3, 3><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr, log2tw);
+  else if (Nk == 7 && Nl == 7) kernel_spectrum_direct_kernel<7, 7><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr, log2tw);
+  else kernel_spectrum_direct_kernel<0, 0><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr, log2tw);
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
   return AEFFT_OK;
@@ -758,43 +759,50 @@ int launch_spectrum_to_taps(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int N
 // gradient_diff (:709-753): cd[m][d][k][l] = sum_{m1!=m, d1!=d} (c[m][d][k][l]-c[m1][d1][k][l]) / |c[m][d]-c[m1][d1]|^2,
 // fd likewise on f[d][m]; bd[m] = sum_{m1!=m} 1/(b[m]-b[m1]); pd[d] = sum_{d1!=d} 1/(p[d]-p[d1]).
 // One CTA per kernel (m,d): squared distances to every other kernel first (shared memory), then the tap sums.
+constexpr int GD_CHUNK = 4096;
 __global__ void gradient_diff_kernel(const float* __restrict__ c, const float* __restrict__ f, const float* __restrict__ b,
                                      const float* __restrict__ p, float* __restrict__ cd, float* __restrict__ fd,
                                      float* __restrict__ bd, float* __restrict__ pd, int dM, int dD, int T) {
-  extern __shared__ float sh[];  // [2][dM*dD] inverse squared distances
+  // inverse squared distances to the other kernels, GD_CHUNK of them at a time (any dM*dD fits; the o = m1*dD+d1 order of
+  // the sums is the reference's loop order)
+  __shared__ float inv_c[GD_CHUNK], inv_f[GD_CHUNK];
   const int m = blockIdx.x / dD, d = blockIdx.x % dD;
-  float* inv_c = sh;
-  float* inv_f = sh + dM * dD;
   const float* cm = c + (m * dD + d) * T;
   const float* fm = f + (d * dM + m) * T;
-  for (int o = threadIdx.x; o < dM * dD; o += blockDim.x) {
-    const int m1 = o / dD, d1 = o % dD;
-    float dc = 0.f, df = 0.f;
-    if (m1 != m && d1 != d) {
-      const float* c1 = c + (m1 * dD + d1) * T;
-      const float* f1 = f + (d1 * dM + m1) * T;
-      for (int t = 0; t < T; t++) {
-        float x = cm[t] - c1[t], y = fm[t] - f1[t];
-        dc = fmaf(x, x, dc);
-        df = fmaf(y, y, df);
+  float sc = 0.f, sf = 0.f;  // thread t < T owns tap t
+  for (int o0 = 0; o0 < dM * dD; o0 += GD_CHUNK) {
+    const int o1 = min(o0 + GD_CHUNK, dM * dD);
+    for (int o = o0 + threadIdx.x; o < o1; o += blockDim.x) {
+      const int m1 = o / dD, d1 = o % dD;
+      float dc = 0.f, df = 0.f;
+      if (m1 != m && d1 != d) {
+        const float* c1 = c + (m1 * dD + d1) * T;
+        const float* f1 = f + (d1 * dM + m1) * T;
+        for (int t = 0; t < T; t++) {
+          float x = cm[t] - c1[t], y = fm[t] - f1[t];
+          dc = fmaf(x, x, dc);
+          df = fmaf(y, y, df);
+        }
+        dc = 1.f / dc;
+        df = 1.f / df;
       }
-      dc = 1.f / dc;
-      df = 1.f / df;
+      inv_c[o - o0] = dc;
+      inv_f[o - o0] = df;
     }
-    inv_c[o] = dc;
-    inv_f[o] = df;
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    float sc = 0.f, sf = 0.f;
-    for (int m1 = 0; m1 < dM; m1++)
-      for (int d1 = 0; d1 < dD; d1++) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      for (int o = o0; o < o1; o++) {
+        const int m1 = o / dD, d1 = o - m1 * dD;
         if (m1 == m || d1 == d) continue;
-        sc += (cm[t] - c[(m1 * dD + d1) * T + t]) * inv_c[m1 * dD + d1];
-        sf += (fm[t] - f[(d1 * dM + m1) * T + t]) * inv_f[m1 * dD + d1];
+        sc += (cm[t] - c[(m1 * dD + d1) * T + t]) * inv_c[o - o0];
+        sf += (fm[t] - f[(d1 * dM + m1) * T + t]) * inv_f[o - o0];
       }
-    cd[(m * dD + d) * T + t] = sc;
-    fd[(d * dM + m) * T + t] = sf;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < T) {
+    cd[(m * dD + d) * T + threadIdx.x] = sc;
+    fd[(d * dM + m) * T + threadIdx.x] = sf;
   }
   if (threadIdx.x == 0) {
     if (d == 0) {
@@ -809,6 +817,86 @@ __global__ void gradient_diff_kernel(const float* __restrict__ c, const float* _
         if (d1 != d) s += 1.f / (p[d] - p[d1]);
       pd[d] = s;
     }
+  }
+}
+
+
+// Tiled form of the same sums (the one-CTA-per-kernel version above is O((dM dD)^2) with 25 active threads: 400 ms per call
+// at 128 -> 256 channels).  X is [n1][n2][T]; kernel a = (a1, a2) interacts with b = (b1, b2) iff a1 != b1 and a2 != b2:
+//   xd[a][t] = sum_b w_ab (x[a][t] - x[b][t]) = x[a][t] * sum_b w_ab - sum_b w_ab x[b][t],  w_ab = 1 / |x[a] - x[b]|^2
+// A CTA owns 64 kernels a (one per thread, its taps in registers) and streams all b through shared memory in tiles of
+// 64; the 4 thread groups of a CTA take every fourth b of a tile and are combined at the end.  Distances are computed
+// directly (no Gram-matrix cancellation).  grid.y selects the tensor (c or f).
+template <int T>
+__global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* __restrict__ c, const float* __restrict__ f,
+                                                                   float* __restrict__ cd, float* __restrict__ fd, int dM, int dD,
+                                                                   int tile0) {
+  // tile0: first 64-kernel tile of this launch (bin-sharded devices split the rows; the hook adds the results)
+  const bool isf = blockIdx.y == 1;
+  const float* x = isf ? f : c;
+  float* xd = isf ? fd : cd;
+  const int n2 = isf ? dM : dD;
+  const int n = dM * dD;
+  __shared__ float tb[64][T + 1];
+  __shared__ float red[3][64][T + 1];
+  const int la = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int a = (tile0 + blockIdx.x) * 64 + la;
+  const bool a_ok = a < n;
+  const int a1 = a_ok ? a / n2 : -1, a2 = a_ok ? a - a1 * n2 : -1;
+  float xa[T], swx[T], sw = 0.f;
+#pragma unroll
+  for (int t = 0; t < T; t++) { xa[t] = a_ok ? x[(size_t)a * T + t] : 0.f; swx[t] = 0.f; }
+  for (int b0 = 0; b0 < n; b0 += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * T; i += 256) {
+      const int r = i / T, t = i - r * T;
+      tb[r][t] = b0 + r < n ? x[(size_t)(b0 + r) * T + t] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = grp; j < 64; j += 4) {
+      const int b = b0 + j;
+      const int b1 = b / n2, b2 = b - b1 * n2;
+      float d2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < T; t++) { const float e = xa[t] - tb[j][t]; d2 = fmaf(e, e, d2); }
+      const float w = (b < n && b1 != a1 && b2 != a2) ? 1.f / d2 : 0.f;
+      sw += w;
+#pragma unroll
+      for (int t = 0; t < T; t++) swx[t] = fmaf(w, tb[j][t], swx[t]);
+    }
+  }
+  // combine the 4 groups (fixed order)
+  if (grp > 0) {
+#pragma unroll
+    for (int t = 0; t < T; t++) red[grp - 1][la][t] = swx[t];
+    red[grp - 1][la][T] = sw;
+  }
+  __syncthreads();
+  if (grp == 0 && a_ok) {
+    for (int g = 0; g < 3; g++) {
+#pragma unroll
+      for (int t = 0; t < T; t++) swx[t] += red[g][la][t];
+      sw += red[g][la][T];
+    }
+#pragma unroll
+    for (int t = 0; t < T; t++) xd[(size_t)a * T + t] = xa[t] * sw - swx[t];
+  }
+}
+__global__ void gradient_diff_bias_kernel(const float* __restrict__ b, const float* __restrict__ p, float* __restrict__ bd,
+                                          float* __restrict__ pd, int dM, int dD) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < dM) {
+    float s = 0.f;
+    for (int m1 = 0; m1 < dM; m1++)
+      if (m1 != i) s += 1.f / (b[i] - b[m1]);
+    bd[i] = s;
+  } else if (i < dM + dD) {
+    const int d = i - dM;
+    float s = 0.f;
+    for (int d1 = 0; d1 < dD; d1++)
+      if (d1 != d) s += 1.f / (p[d] - p[d1]);
+    pd[d] = s;
   }
 }
 
@@ -851,6 +939,49 @@ __global__ void fft_update_kernel(float* __restrict__ c, float* __restrict__ f, 
   }
 }
 
+// Multiobjective (kernel-diversity) term [cd | fd | bd | pd] into div (2*nC + dM + dD floats, the layout of the gradient
+// block).  rank/world split the kernels over bin-sharded devices: a device computes the rows of its share and leaves zeros
+// elsewhere (bias terms on device 0), so that the sum over devices is the whole term.
+int launch_gradient_diff(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, const float* c, const float* f, const float* b,
+                         const float* p, float* div, int rank, int world) {
+  const int T = Nk * Nl, nC = dM * dD * T, n = dM * dD;
+  float *cd = div, *fd = cd + nC, *bd = fd + nC, *pd = bd + dM;
+  AE_ARG(T <= 64 && world >= 1);
+  ProfScope prof(ctx, "gradient_diff", 2.0 * 75.0 * (double)n * n / world, 8.0 * nC);
+  if (world > 1) AE_CUDA(cudaMemsetAsync(div, 0, (size_t)(2 * nC + dM + dD) * sizeof(float), ctx->stream));
+  if (n >= 256 && (T == 25 || T == 9)) {
+    const int tiles = (n + 63) / 64;
+    const int t0 = (int)((long long)tiles * rank / world), t1 = (int)((long long)tiles * (rank + 1) / world);
+    if (t1 > t0) {
+      dim3 grid(t1 - t0, 2);
+      if (T == 25) gradient_diff_tiled_kernel<25><<<grid, 256, 0, ctx->stream>>>(c, f, cd, fd, dM, dD, t0);
+      else gradient_diff_tiled_kernel<9><<<grid, 256, 0, ctx->stream>>>(c, f, cd, fd, dM, dD, t0);
+      ctx->launches++;
+    }
+    if (rank == 0) {
+      gradient_diff_bias_kernel<<<(dM + dD + 127) / 128, 128, 0, ctx->stream>>>(b, p, bd, pd, dM, dD);
+      ctx->launches++;
+    }
+  } else if (rank == 0) {
+    gradient_diff_kernel<<<n, 64, 0, ctx->stream>>>(c, f, b, p, cd, fd, bd, pd, dM, dD, T);
+    ctx->launches++;
+  }
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// y[i] = a*y[i] + b*x[i]
+__global__ void axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, float b, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a * y[i] + b * x[i];
+}
+int launch_axpby(aefft_ctx* ctx, float* y, const float* x, float a, float b, long long n) {
+  axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(y, x, a, b, n);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
 int launch_fft_update(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, float* c, float* f, float* b, float* p,
                       const float* dck, const float* dfk, const float* db, const float* dp, float* Dc, float* Df, float* Db,
                       float* Dp, float del, int maxdiff, float* div_scratch /* 2*nC + dM + dD floats */) {
@@ -858,11 +989,7 @@ int launch_fft_update(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, float* c, 
   float *cd = nullptr, *fd = nullptr, *bd = nullptr, *pd = nullptr;
   if (maxdiff) {
     cd = div_scratch; fd = cd + nC; bd = fd + nC; pd = bd + dM;
-    const size_t smem = (size_t)2 * dM * dD * sizeof(float);
-    AE_ARG(smem <= 48 * 1024);
-    gradient_diff_kernel<<<dM * dD, 64, smem, ctx->stream>>>(c, f, b, p, cd, fd, bd, pd, dM, dD, T);
-    ctx->launches++;
-    AE_CUDA(cudaGetLastError());
+    AE_TRY(launch_gradient_diff(ctx, dM, dD, Nk, Nl, c, f, b, p, div_scratch, 0, 1));
   }
   fft_update_kernel<<<(nC + 127) / 128, 128, 0, ctx->stream>>>(c, f, b, p, dck, dfk, db, dp, Dc, Df, Db, Dp, cd, fd, bd, pd, nC,
                                                                 dM, dD, del, 1.f, 10.f);  // w0=1, w1=10 (:1252)

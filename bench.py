@@ -38,6 +38,11 @@ WORKLOADS = {
     # name: (D, Nx, Ny, widths, Lk, Ll, pool, rmax, batch per GPU, space)
     "c2": dict(D=3, Nx=640, Ny=480, widths=[16, 32, 64], Lk=1, Ll=1, pool=2, rmax=3.0, batch=64, space="coordinate"),
     "c3": dict(D=3, Nx=1024, Ny=1024, widths=[16, 32, 64], Lk=1, Ll=1, pool=2, rmax=3.0, batch=128, space="fft"),
+    # configs[3]: 5 pairs (widths assumed), multiobjective term, 2048x2048 frames, FREQUENCY-BIN SHARDED:
+    # every GPU holds all `batch` frames and owns a slab of spectrum columns (strong scaling); n_iter iterations per
+    # backprop_fft call amortise the replicated forward / frame transforms (the reference runs 100 per call)
+    "c4": dict(D=3, Nx=2048, Ny=2048, widths=[16, 32, 64, 128, 256], Lk=1, Ll=1, pool=2, rmax=3.0, batch=4, space="fft",
+               shard="bins", n_iter=10, maxdiff=1),
 }
 DELMAX, ALPHA = 0.2, 0.9  # autoencoder.cpp:87-89
 
@@ -168,9 +173,10 @@ def config_dict(w, args, world):
         "workload": f"{args.workload}: {len(w['widths'])}-pair {w['space']}-space autoencoder {w['D']}->" +
                     "->".join(map(str, w["widths"])) + f", {2 * (w['Lk'] + 1) + 1}x{2 * (w['Ll'] + 1) + 1} taps, pool {w['pool']}, "
                     f"symmetric weights, {w['Nx']}x{w['Ny']} frames, batch {args.batch} per GPU",
-        "global_batch": args.batch * world,
+        "global_batch": args.batch * (1 if w.get("shard") == "bins" else world),
         "pairs": [{"dD": d, "dM": m, "Nx": x, "Ny": y} for d, m, x, y in geo],
-        "parallelism": f"dp{world}",
+        "parallelism": (f"bins{world} (frequency-bin sharded backprop_fft, {w.get('n_iter', 1)} iterations per call, "
+                        f"forward replicated)") if w.get("shard") == "bins" else f"dp{world}",
         "cache": "inputs larger than L2 (frames + activations per step >> 126 MB); no explicit flush",
         "step": "forward of the full stack + gradients + clipped-momentum update of every pair",
     }
@@ -359,11 +365,14 @@ class FftWorkload:
         self.layers = A.DevBuf(ctx, (B, self.lstride))
         self.n0 = lsz[0]
         frames = A.DevBuf(ctx, (B, self.n0))
-        ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=rank * B, out=frames.ptr, loc=A.DEVICE)
+        self.shard = w.get("shard") == "bins"
+        self.n_iter, self.maxdiff = int(w.get("n_iter", 1)), int(w.get("maxdiff", 0))
+        # data parallel: every rank owns its own frames; bin sharded: every rank holds the SAME frames
+        ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=0 if self.shard else rank * B, out=frames.ptr, loc=A.DEVICE)
         self.frames = frames
         self.host = torch.empty(B * self.n0, dtype=torch.float32).pin_memory()
         ctx.memcpy(self.host.data_ptr(), frames.ptr, B * self.n0 * 4, 1)
-        self.trace = np.zeros(2, np.float32)
+        self.trace = np.zeros(self.n_iter + 1, np.float32)
         self.pairs = []
         P = len(encs)
         for n in range(P):
@@ -374,17 +383,23 @@ class FftWorkload:
                                    p=int(self.boff[2 * P - 1 - n])))
         self.h2d_bytes, self.d2h_bytes = B * self.n0 * 4, 4 * P
         self._put_frames(A.DEVICE, frames.ptr)
-        if world > 1:
-            # data-parallel frames: every rank averages the raw kernel-space gradient block [dck | dfk | db | dp] of its own
-            # frames over the ranks (NCCL on the engine's stream) before the clipped-momentum update
+        if world > 1 or self.shard:
+            # data-parallel frames: every rank AVERAGES the raw kernel-space gradient block [dck | dfk | db | dp] of its own
+            # frames over the ranks; bin sharded: every rank ADDS the partial block / mse of its spectrum columns (NCCL on
+            # the engine's stream), in both cases before the clipped-momentum update
             views = {}
+            op = dist.ReduceOp.SUM if self.shard else dist.ReduceOp.AVG
 
             def hook(ptr, n):
+                if world == 1:
+                    return
                 if (ptr, n) not in views:
                     views[(ptr, n)] = torch.as_tensor(CudaArray(ptr, n), device=dev)
-                dist.all_reduce(views[(ptr, n)], op=dist.ReduceOp.AVG)
+                dist.all_reduce(views[(ptr, n)], op=op)
 
             ctx.set_gradient_hook(hook)
+            if self.shard:
+                ctx.set_bin_shard(rank, world)
 
     def _put_frames(self, kind_loc, src_ptr):
         """layer 0 of every frame lives at layers[b*lstride]: strided copy of the batch's frames."""
@@ -410,7 +425,7 @@ class FftWorkload:
                                                         ctypes.c_int64(self.lstride),
                                                         ctypes.c_void_p(self.c_all.ptr + q["c"] * 4), ctypes.c_void_p(self.c_all.ptr + q["f"] * 4),
                                                         ctypes.c_void_p(self.b_all.ptr + q["b"] * 4), ctypes.c_void_p(self.b_all.ptr + q["p"] * 4),
-                                                        ctypes.c_float(DELMAX), 0, 1, self.trace.ctypes.data_as(FP)))
+                                                        ctypes.c_float(DELMAX), self.maxdiff, self.n_iter, self.trace.ctypes.data_as(FP)))
 
     def step_resident(self):
         self._train()
@@ -550,7 +565,8 @@ def run_ours(args, w, rank, world, local_rank):
     if rank == 0:
         pk = peaks()
         B = args.batch
-        frames = B * world * args.steps
+        sharded = w.get("shard") == "bins"  # every rank works on the same frames: total work is fixed (strong scaling)
+        frames = B * (1 if sharded else world) * args.steps
         value = frames / (ms_total * 1e-3)
         top = kernels[0] if kernels else None
         roof = None
@@ -576,7 +592,7 @@ def run_ours(args, w, rank, world, local_rank):
         line = {
             "metric": "training frames/sec (fwd+backprop)", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "c64/f32" if w["space"] == "fft" else
                      {"fp32": "f32", "bf16x3": "f32 (bf16x3 split on tcgen05, fp32 accumulate)", "bf16": "bf16"}[args.precision],
             "data": "synthetic", "config": cfg,

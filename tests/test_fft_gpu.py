@@ -227,22 +227,23 @@ def test_gradient_hook_two_rank_emulation(ctx):
         assert O.rel_l2(w[k], full[k]) < 1e-6, k
 
 
-def test_bin_sharding_two_device_emulation(ctx):
-    """aefft_set_bin_shard: two 'devices' each own half of the spectrum columns; adding their partial gradient blocks
-    (and partial mse values) in the hook reproduces the single-device iteration."""
-    dims = (4, 3, 5, 5, 16, 32)
+@pytest.mark.parametrize("dims,maxdiff", [((4, 3, 5, 5, 16, 32), 0), ((32, 8, 5, 5, 16, 16), 1)])
+def test_bin_sharding_two_device_emulation(ctx, dims, maxdiff):
+    """aefft_set_bin_shard: two 'devices' each own half of the spectrum columns (and, with the multiobjective term, half
+    of the kernels of that term); adding their partial gradient blocks and partial mse values in the hook reproduces
+    the single-device iteration."""
     dM, dD, Nk, Nl, Nx, Ny = dims
     cs = fft_case(9, *dims, B=3)
     n_block = 2 * dM * dD * Nk * Nl + dM + dD
     full = {k: cs[k].copy() for k in "cfbp"}
-    want_trace = ctx.backprop_fft(cs["inp"], cs["inp"], cs["out"], full["c"], full["f"], full["b"], full["p"], 0.2, 0, 1)
+    want_trace = ctx.backprop_fft(cs["inp"], cs["inp"], cs["out"], full["c"], full["f"], full["b"], full["p"], 0.2, maxdiff, 1)
 
     def run(rank, hook):
         dev = {k: ctx.to_device(cs[k]) for k in ("inp", "out", "c", "f", "b", "p")}
         ctx.set_bin_shard(rank, 2)
         ctx.set_gradient_hook(hook)
         try:
-            trace = ctx.backprop_fft(dev["inp"], dev["inp"], dev["out"], dev["c"], dev["f"], dev["b"], dev["p"], 0.2, 0, 1,
+            trace = ctx.backprop_fft(dev["inp"], dev["inp"], dev["out"], dev["c"], dev["f"], dev["b"], dev["p"], 0.2, maxdiff, 1,
                                      loc=A.DEVICE)
         finally:
             ctx.set_gradient_hook(None)
@@ -287,3 +288,19 @@ def test_bin_sharding_two_device_emulation(ctx):
         for k in "cfbp":
             assert O.rel_l2(got[k], full[k]) < 1e-6, (rank, k)
     assert np.isclose(post[0][0] + post[1][0], want_trace[1], rtol=1e-5), (post, want_trace)
+
+
+def test_multiobjective_tiled_kernel_vs_oracle(ctx):
+    """maxdiff=1 with dM*dD >= 256 kernels takes the tiled gradient_diff kernel (fft_backproplib.cu:709-753 semantics)."""
+    dims = (32, 8, 5, 5, 16, 16)
+    cs = fft_case(11, *dims)
+    w = {k: cs[k].copy() for k in "cfbp"}
+    ctx.profile_enable(True)
+    trace = ctx.backprop_fft(cs["inp"], cs["inp"], cs["out"], w["c"], w["f"], w["b"], w["p"], 0.2, 1, 2)
+    names = [r["name"] for r in ctx.profile_records()]
+    ctx.profile_enable(False)
+    assert "gradient_diff" in names
+    want = O.backprop_fft(cs["inp"], cs["inp"], cs["out"], cs["c"], cs["f"], cs["b"], cs["p"], 0.2, 1, 2)
+    assert np.allclose(trace, want["mse"], rtol=2e-4), (trace, want["mse"])
+    for k in "cfbp":
+        assert O.rel_l2(w[k], want[k]) < 1e-4, k
