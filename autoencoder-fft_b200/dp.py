@@ -18,3 +18,20 @@ def allreduce_gradient_block(gbuf, world: int):
 
         dist.all_reduce(gbuf, op=dist.ReduceOp.SUM)
     return gbuf
+
+
+def bin_slab(rank: int, world: int, Ny: int):
+    """(first column, column count) of the half spectrum (Ny//2+1 columns) owned by `rank` under frequency-bin sharding;
+    the same split as aefft_set_bin_shard / backprop_fft_core (csrc/fft_capi.cu)."""
+    nyr = Ny // 2 + 1
+    c0 = rank * nyr // world
+    return c0, (rank + 1) * nyr // world - c0
+
+
+def allreduce_partial_block(block, world: int):
+    """Bin-sharded devices hold PARTIAL sums (over their spectrum columns) of the gradient block and of the mse: add them."""
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(block, op=dist.ReduceOp.SUM)
+    return block

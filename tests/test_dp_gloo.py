@@ -92,3 +92,64 @@ def test_frame_range_partitions_the_global_batch():
 
     owned = [dp.frame_range(r, 4, 16) for r in range(4)]
     assert owned == [(0, 16), (16, 16), (32, 16), (48, 16)]
+
+
+# ---------------------------------------------------------------------------------------------- frequency-bin sharding
+def test_bin_slabs_partition_the_half_spectrum():
+    import dp
+
+    for Ny in (16, 64, 2048):
+        for world in (1, 2, 3, 8):
+            slabs = [dp.bin_slab(r, world, Ny) for r in range(world)]
+            assert slabs[0][0] == 0 and sum(n for _, n in slabs) == Ny // 2 + 1
+            for (c0, n), (c1, _) in zip(slabs, slabs[1:]):
+                assert c0 + n == c1 and n > 0
+
+
+def _pruned_taps_partial(Z, Ny, Nk, Nl, c0, n):
+    """Kernel-space taps from the spectrum columns [c0, c0+n) only: the pruned inverse DFT of csrc/spectral_kernels.cu
+    (spectrum_to_taps): taps[k][l] = sum_{wx, wy in slab} h(wy) Re(Z[wx][wy] conj(W_Nx^(wx i_k)) conj(W_Ny^(wy j_l)))."""
+    Nx = Z.shape[0]
+    wx = np.arange(Nx)[:, None]
+    wy = np.arange(c0, c0 + n)[None, :]
+    h = np.where((wy == 0) | (wy == Ny // 2), 1.0, 2.0)
+    out = np.zeros((Nk, Nl))
+    for k in range(Nk):
+        i = (k - Nk // 2) % Nx
+        for l in range(Nl):
+            j = (l - Nl // 2) % Ny
+            ph = np.exp(2j * np.pi * (wx * i / Nx + wy * j / Ny))
+            out[k, l] = np.sum(h * np.real(Z[:, c0:c0 + n] * ph))
+    return out
+
+
+def _shard_worker(rank, world, port, ret):
+    import dp
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    Nx, Ny, Nk, Nl = 8, 16, 5, 5
+    img = rng.standard_normal((Nx, Ny))
+    Z = np.fft.rfft2(img)  # every rank holds the same frames; it keeps only its slab of columns
+    c0, n = dp.bin_slab(rank, world, Ny)
+    part = torch.from_numpy(_pruned_taps_partial(Z, Ny, Nk, Nl, c0, n))
+    dp.allreduce_partial_block(part, world)
+    ret[rank] = part.numpy()
+    dist.destroy_process_group()
+
+
+def test_two_rank_bin_sharded_kernel_gradient_equals_full_transform():
+    """sum over ranks of the slab-partial pruned inverse DFT == shrink_k(C2R(spectrum)) of the whole spectrum."""
+    world, port = 2, 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_shard_worker, args=(world, port, ret), nprocs=world, join=True)
+    rng = np.random.default_rng(3)
+    Nx, Ny, Nk, Nl = 8, 16, 5, 5
+    img = rng.standard_normal((Nx, Ny))
+    full = np.fft.irfft2(np.fft.rfft2(img), s=(Nx, Ny)) * Nx * Ny  # unnormalised C2R
+    want = np.array([[full[(k - Nk // 2) % Nx, (l - Nl // 2) % Ny] for l in range(Nl)] for k in range(Nk)])
+    assert np.allclose(ret[0], want, rtol=1e-10, atol=1e-9)
+    assert np.array_equal(ret[0], ret[1])
