@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <math.h>
+#include <vector>
 
 #include "../autoencoder-fft_b200/csrc/umma.cuh"
 #include "../autoencoder-fft_b200/csrc/tma.cuh"
@@ -103,6 +104,61 @@ __global__ void tma_swz_probe(const __grid_constant__ CUtensorMap tm, int cj, in
   for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) out[i] = buf[i];
 }
 
+// Probe 3: MN-major B operand in SWIZZLE_32B layout, 16 channels per pixel (32 B per K row), N atoms one PIXEL apart
+// (LBO = 32 B): does N = 16 x NS cover NS pixel shifts of a 16-channel plane?  mode 0: LBO=32,SBO=256; mode 1: swapped.
+constexpr int NS3 = 6;
+template <int CH>
+__global__ void ts_probe_sw(const float* __restrict__ Ain /*[128][16]*/, const float* __restrict__ Sin /*[K+NS3][CH]*/,
+                            float* __restrict__ out /*[128][CH*NS3]*/, int mode) {
+  constexpr int N3 = CH * NS3, PXB = CH * 2;  // bytes per pixel row
+  __shared__ __align__(1024) unsigned char S[2048];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 32) { mbar_init(&bar, 1); fence_mbar_init(); }
+  for (int i = tid; i < 2048; i += 128) S[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < (K + NS3) * CH; i += 128) {
+    const int px = i / CH, ch = i % CH;
+    uint32_t off = px * PXB + (ch / 8) * 16 + (ch % 8) * 2;
+    if (CH == 16) off ^= ((off >> 7) & 1) << 4;   // 32-byte swizzle: address bit 4 ^= bit 7
+    else off ^= ((off >> 7) & 3) << 4;            // 64-byte swizzle: bits [4,6) ^= bits [7,9)
+    *reinterpret_cast<__nv_bfloat16*>(S + off) = __float2bfloat16_rn(Sin[i]);
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tmem_slot;
+  uint32_t r[8];
+  for (int c = 0; c < 8; c++)
+    r[c] = pack2(__float2bfloat16_rn(Ain[tid * 16 + 2 * c]), __float2bfloat16_rn(Ain[tid * 16 + 2 * c + 1]));
+  tmem_st8(tb + ((uint32_t)(warp * 32) << 16) + 0, r);
+  tmem_wait_st();
+  fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    fence_after_sync();
+    const uint32_t idesc = make_idesc_bf16(128, N3, 0, 1);
+    uint64_t bdesc = make_desc(smem_u32(S), PXB, 8 * PXB);  // LBO = one pixel, SBO = 8 pixels
+    bdesc |= (uint64_t)(CH == 16 ? 6 : 4) << 61;               // SWIZZLE_32B / SWIZZLE_64B
+    (void)mode;
+    mma_bf16_ts(tb + 64, tb + 0, bdesc, idesc, false);
+    commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  fence_after_sync();
+  for (int c0 = 0; c0 < N3; c0 += 16) {
+    float v[16];
+    tmem_ld16(tb + ((uint32_t)(warp * 32) << 16) + 64 + c0, v);
+    for (int e = 0; e < 16; e++) out[tid * N3 + c0 + e] = v[e];
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 static float bf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 int main(int argc, char** argv) {
@@ -129,6 +185,35 @@ int main(int argc, char** argv) {
         maxerr = fmax(maxerr, fabs(ref - hO[m * N + s * 8 + x]));
       }
   printf("ts_probe max abs err %.3g  (%s)\n", maxerr, maxerr < 1e-3 ? "OK" : "MISMATCH");
+  // ---------------- probe 3
+  if (argc == 2) {
+    const int CH = atoi(argv[1]);  // 16 or 32
+    const int N3 = CH * NS3;
+    std::vector<float> hS3((K + NS3) * CH), hO3(128 * N3);
+    for (auto& v : hS3) v = bf((rand() % 2001 - 1000) / 500.f);
+    float *dS3, *dO3;
+    cudaMalloc(&dS3, hS3.size() * 4); cudaMalloc(&dO3, hO3.size() * 4);
+    cudaMemcpy(dS3, hS3.data(), hS3.size() * 4, cudaMemcpyHostToDevice);
+    if (CH == 16) ts_probe_sw<16><<<1, 128>>>(dA, dS3, dO3, 0);
+    else ts_probe_sw<32><<<1, 128>>>(dA, dS3, dO3, 0);
+    e = cudaDeviceSynchronize();
+    printf("ts_probe_sw CH=%d: %s\n", CH, cudaGetErrorString(e));
+    if (e != cudaSuccess) return 1;
+    cudaMemcpy(hO3.data(), dO3, hO3.size() * 4, cudaMemcpyDeviceToHost);
+    double me = 0;
+    int nbad = 0;
+    for (int m = 0; m < 128; m++)
+      for (int s = 0; s < NS3; s++)
+        for (int x = 0; x < CH; x++) {
+          double ref = 0;
+          for (int k = 0; k < K; k++) ref += (double)hA[m * 16 + k] * hS3[(k + s) * CH + x];
+          const double d = fabs(ref - hO3[m * N3 + s * CH + x]);
+          me = fmax(me, d);
+          if (d > 1e-3) nbad++;
+        }
+    printf("ts_probe_sw CH=%d max abs err %.3g, %d of %d wrong (%s)\n", CH, me, nbad, 128 * N3, me < 1e-3 ? "OK" : "MISMATCH");
+    return 0;
+  }
   // ---------------- probe 2
   const int P = 6, NX = 10, NY = 24;
   float hT[P * NX * NY];
