@@ -63,6 +63,8 @@ struct WgradTsParams {
   int strips, bands, BR;
   long long items;
   int passes, flip, by_chunk;
+  int stack;   // B operand = [S_hi | S_lo] of 8*np channels per pixel in one swizzled plane (2 MMAs of 2N instead of 3*np of N)
+  int nacc;    // accumulators per job: NR (stack) or NR*np
   uint32_t u_slot_bytes, s_slot_bytes, s_src_bytes, sb_pitch;
   uint32_t off_u, off_s, off_sb;
   long long* dbg;  // AEFFT_TS_DEBUG: [cta][warp][4] cycles (wait A, wait B, total, -)
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
     for (int i = 0; i < p.NU; i++) { mbar_init(&u_full[i], 1); mbar_init(&u_empty[i], 8); }
     for (int i = 0; i < TS_NSF; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 2); }
     for (int i = 0; i < p.NSB; i++) { mbar_init(&sb_full[i], 2); mbar_init(&sb_empty[i], TS_NI); }
-    for (int i = 0; i < p.NA; i++) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], p.by_chunk ? 1 : TS_NI); }
+    for (int i = 0; i < p.NA; i++) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], TS_NI); }
     mbar_init(&done_bar, TS_NI);
     fence_mbar_init();
   }
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
   if (tid == 0) esq = 0.0;
   // zero the bf16 S ring once: the 8 pad pixels behind every row slot are read (times zero A lanes) and must be finite
   {
-    const uint32_t n16 = (uint32_t)(2 * p.np * p.NSB) * p.sb_pitch / 16;
+    const uint32_t n16 = (uint32_t)((p.stack ? 1 : 2 * p.np) * p.NSB) * p.sb_pitch / 16;
     uint4* z = reinterpret_cast<uint4*>(sb_ring);
     for (uint32_t i = tid; i < n16; i += TS_THREADS) z[i] = make_uint4(0, 0, 0, 0);
   }
@@ -178,9 +180,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
     const uint32_t idesc = make_idesc_bf16(128, p.Ncol, 0, 1);
     const uint32_t sb_base16 = smem_u32(sb_ring) >> 4, pitch16 = p.sb_pitch >> 4;
     const uint32_t lo_off16 = (uint32_t)(p.np * p.NSB) * pitch16;
-    const uint64_t desc_const = make_desc(0, 128, 16);
-    const int NR = p.NR, NSB = p.NSB, np = p.np, RS = p.RS, CPR = p.CPR;
-    const int nacc = NR * np;
+    const bool stack = p.stack != 0;
+    const uint32_t pxb16 = stack ? (uint32_t)p.np * 2 : 1;  // 16-byte units per pixel row of the B operand
+    // stacked: SWIZZLE_32B / 64B MN-major plane, N atoms one pixel apart (LBO), 8-pixel K groups (SBO)
+    const uint64_t desc_const = stack ? (make_desc(0, pxb16 * 16, pxb16 * 128) | ((uint64_t)(p.np == 1 ? 6 : 4) << 61))
+                                      : make_desc(0, 128, 16);
+    const int NR = p.NR, NSB = p.NSB, np = stack ? 1 : p.np, RS = p.RS, CPR = p.CPR;
+    const int nacc = p.nacc;
     const uint32_t Ncol = (uint32_t)p.Ncol;
     const bool three = p.passes == 3, by_chunk = p.by_chunk != 0;
     const uint32_t d_base = tb + (by_chunk ? (uint32_t)(q * nacc) * Ncol : 0u);
@@ -204,8 +210,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
         }
         for (int h = 0; h < CPR; h++, cc4 = (cc4 + 1) & (TS_NI - 1)) {
           const bool mine = !by_chunk || cc4 == q;
+          // every issuer waits for every A chunk in order and takes part in its release (count TS_NI), owner or not: a
+          // parity wait must neither skip phases nor be lapped (the ring length need not be a multiple of TS_NI)
+          wait_t<DBG>(&a_full[ra.slot], ra.phase, wB);
           if (mine) {
-            wait_t<DBG>(&a_full[ra.slot], ra.phase, wB);
             fence_after_sync();
             const long long t_m0 = DBG ? clock64() : 0;
             const uint32_t a_base = tb + (uint32_t)(p.Acol0 + ra.slot * 64);
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
 #pragma unroll 1
               for (int ks = 0; ks < 4; ks++) {
                 const uint32_t a_hi = a_base + ks * 8, a_lo = a_hi + 32;
-                const uint32_t px16 = sb_base16 + (uint32_t)(h * TS_CHUNK + ks * 16);
+                const uint32_t px16 = sb_base16 + (uint32_t)(h * TS_CHUNK + ks * 16) * pxb16;
                 uint32_t d = d_base;
                 int slot = s0slot, a = 0;
 #pragma unroll 1
@@ -226,7 +234,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
                     if (by_chunk || (a & (TS_NI - 1)) == q) {
                       const uint64_t b_hi = desc_const + (uint64_t)lo32, b_lo = b_hi + (uint64_t)lo_off16;
                       mma_bf16_ts(d, a_hi, b_hi, idesc, true);
-                      if (three) {
+                      if (stack) {
+                        if (three) mma_bf16_ts(d, a_lo, b_hi, idesc, true);  // (A_hi + A_lo) [S_hi | S_lo]
+                      } else if (three) {
                         mma_bf16_ts(d, a_hi, b_lo, idesc, true);
                         mma_bf16_ts(d, a_lo, b_hi, idesc, true);
                       }
@@ -239,8 +249,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
             }
             __syncwarp();
             if (DBG) wC += clock64() - t_m0;
-            if (elect_one()) commit(&a_empty[ra.slot]);
           }
+          if (elect_one()) commit(&a_empty[ra.slot]);
           ra.next();
         }
         if (elect_one()) commit(&sb_empty[s0slot]);
@@ -323,9 +333,21 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
               uint32_t hi[4], lo[4];
 #pragma unroll
               for (int e = 0; e < 4; e++) split2(v[u][2 * e], v[u][2 * e + 1], hi[e], lo[e]);
-              unsigned char* dst = sb_ring + ((size_t)(pl * p.NSB) + sb.slot) * p.sb_pitch + (size_t)px * 16;
-              *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(dst + lo_part) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              if (p.stack) {
+                // pixel row = [hi of 8*np channels | lo of 8*np channels], 16-byte chunks XOR-swizzled on address bits 7.. (32 B /
+                // 64 B swizzle; the ring base is 1024-byte aligned, so offset bits = address bits)
+                const uint32_t row = (uint32_t)sb.slot * p.sb_pitch + (uint32_t)px * (32u * p.np);
+                uint32_t o_hi = row + (uint32_t)pl * 16, o_lo = row + (uint32_t)(p.np + pl) * 16;
+                const uint32_t m = p.np == 1 ? 1u : 3u;
+                o_hi ^= ((o_hi >> 7) & m) << 4;
+                o_lo ^= ((o_lo >> 7) & m) << 4;
+                *reinterpret_cast<uint4*>(sb_ring + o_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(sb_ring + o_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              } else {
+                unsigned char* dst = sb_ring + ((size_t)(pl * p.NSB) + sb.slot) * p.sb_pitch + (size_t)px * 16;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(dst + lo_part) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              }
             }
           }
         }
@@ -362,8 +384,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
     int w_row = 0;                 // running index (over all items) of the next U row this warp has not waited for
     Ring rw(NU);                   // ring position of w_row
     int row_base = 0;              // running index of U row 0 of the current item
-    int ca = half, ca_phase = 0;   // this warp's chunks are cc = half, half+2, ...: A ring slot / phase of chunk cc
-    if (ca >= NA) { ca -= NA; ca_phase ^= 1; }
+    Ring rc(NA);                   // A ring position of the current chunk (advanced for EVERY chunk, see below)
     int parity = 0;                // (chunk index & 1) of the next chunk in program order
     int rel_row = 0, rel_slot = 0; // next U row of the current item this warp has not released yet / its ring slot
     double dsum = 0.0;
@@ -373,8 +394,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
       const int nrows = min(p.BR, p.Nx - i0);
       const int n_krows = nrows + p.RS - 1;
       for (int r = 0; r < n_krows; r++) {
-        for (int h = 0; h < p.CPR; h++, parity ^= 1) {
+        for (int h = 0; h < p.CPR; h++, parity ^= 1, rc.next()) {
+          // Every converter warp waits for the release of EVERY chunk slot in order, also for the chunks the other half
+          // writes: with an odd ring length both halves alternate on the same barriers, and a parity wait that skips a
+          // phase can pass one lap early (the slot would be overwritten while the MMAs still read it).
+          wait_t<DBG>(&a_empty[rc.slot], rc.phase ^ 1, wB);
           if (parity != half) continue;
+          const int ca = rc.slot;
           // rows this warp will never read again (its chunks run in order): release them to the producer
           for (; rel_row <= r - p.RS && rel_row < nrows; rel_row++) {
             if (lane == 0) mbar_arrive(&u_empty[rel_slot]);
@@ -392,7 +418,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
               }
             }
           }
-          wait_t<DBG>(&a_empty[ca], (uint32_t)ca_phase ^ 1, wB);
           fence_after_sync();
           const int ru = r - rho;
           const bool valid = ru >= 0 && ru < nrows;
@@ -426,8 +451,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_full[ca]);
-          ca += 2;
-          if (ca >= NA) { ca -= NA; ca_phase ^= 1; }
         }
       }
       for (; rel_row < nrows; rel_row++) {
@@ -446,8 +469,9 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
       const bool had_items = cta < n_items;
       float* part = p.part + (long long)cta * p.n_tot + J.g_off;
       const int TT = p.NK * p.NL;
-      for (int acc = 0; acc < p.NR * p.np; acc++) {
-        const int Ri = acc / p.np, pl = acc - Ri * p.np;
+      const int EL = 16 * p.np;  // stacked: accumulator columns per pixel shift = [hi 8*np | lo 8*np]
+      for (int acc = 0; acc < p.nacc; acc++) {
+        const int Ri = p.stack ? acc : acc / p.np, pl0 = p.stack ? 0 : acc - Ri * p.np;
         const int tk0 = Ri * p.RS + rho;
         for (int c0 = 0; c0 < p.Ncol; c0 += 16) {
           float v[16];
@@ -455,24 +479,37 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
           if (p.by_chunk) {
             for (int cp = 1; cp < TS_NI; cp++) {  // issuer copies, fixed order
               float w[16];
-              tmem_ld16(tb + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((cp * p.NR * p.np + acc) * p.Ncol + c0), w);
+              tmem_ld16(tb + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((cp * p.nacc + acc) * p.Ncol + c0), w);
 #pragma unroll
               for (int e = 0; e < 16; e++) v[e] += w[e];
             }
           }
+          // which (shift, channel, part) do these 16 columns hold?
+          int s, chb, nval;
+          bool lo_part = false;
+          if (!p.stack) { s = c0 >> 3; chb = pl0 * 8; nval = 16; }           // two shifts x 8 channels
+          else if (p.np == 1) { s = c0 >> 4; chb = 0; nval = 8; }             // [hi 8 | lo 8] of one shift
+          else { s = c0 >> 5; chb = 0; nval = 16; lo_part = (c0 & 16) != 0; } // hi 16 or lo 16 of one shift
+          if (p.stack && p.np == 1) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] += v[8 + e];
+          }
           if (tk0 < p.NK) {
 #pragma unroll
             for (int e = 0; e < 16; e++) {
-              const int col = c0 + e, s = col >> 3, x = col & 7;
-              const int ch = pl * 8 + x;
-              if (s < p.NL && ch < J.nch) {
-                int tk = tk0, tl = s;
+              if (e >= nval) continue;
+              const int sh = p.stack ? s : s + (e >> 3);
+              const int ch = p.stack ? chb + e : chb + (e & 7);
+              if (sh < p.NL && ch < J.nch) {
+                int tk = tk0, tl = sh;
                 if (J.rev) { tk = p.NK - 1 - tk; tl = p.NL - 1 - tl; }
                 const int k = p.flip ? p.NK - 1 - tk : tk, l = p.flip ? p.NL - 1 - tl : tl;
                 const int d = J.ch0 + ch;
                 const long long gi = J.is_gf ? (((long long)d * p.dM + m) * TT + k * p.NL + l)
                                              : (((long long)m * p.dD + d) * TT + k * p.NL + l);
-                part[gi] = had_items ? v[e] : 0.f;
+                const float val = had_items ? v[e] : 0.f;
+                if (p.stack && p.np == 2 && lo_part) part[gi] += val;  // the hi half of this shift was written just before
+                else part[gi] = val;
               }
             }
           }
@@ -531,10 +568,29 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   p.passes = passes; p.flip = win.flip;
   p.RS = 128 / dM;
   p.NR = (win.Nk + p.RS - 1) / p.RS;
-  p.Ncol = 48;
-  p.np = dD > 8 ? 2 : 1;
-  while (p.np > 1 && p.NR * p.np * p.Ncol > 512 - 2 * 64) p.np--;
-  if (p.NR * p.np * p.Ncol > 512 - 2 * 64) return AEFFT_ERR_UNSUPPORTED;
+  // Stacked B operand (opt-in, AEFFT_TS_STACK=1): one swizzled plane [pixel][hi of 8*np channels | lo of 8*np channels],
+  // N = 16*np*NL columns per MMA, 2 MMAs per (K-step, window-row group) instead of 3*np of N = 48 (validated by
+  // tools/probe_ts.cu: MN-major SWIZZLE_32B/64B with a one-pixel atom stride).  Measured on config 2: no faster (the
+  // converter warps, not the MMA count, bound the kernel: 0.89 / 0.56 / 0.66 ms vs 0.87 / 0.59 / 0.46 ms), so the
+  // separate hi / lo planes stay the default.
+  p.stack = 0;
+  if (getenv("AEFFT_TS_STACK") && win.Nl <= 6) {
+    for (int np = dD > 8 ? 2 : 1; np >= 1 && !p.stack; np--) {
+      const int ncol = 16 * np * win.Nl;
+      const int copies = (p.NR == 1 && TS_NI * ncol + 2 * 64 <= 512) ? TS_NI : 1;
+      const int jobs = 2 * ((dD + 8 * np - 1) / (8 * np));
+      if (copies * p.NR * ncol + 2 * 64 <= 512 && jobs <= TS_MAX_JOBS) {
+        p.stack = 1; p.np = np; p.Ncol = ncol; p.nacc = p.NR;
+      }
+    }
+  }
+  if (!p.stack) {
+    p.Ncol = 48;
+    p.np = dD > 8 ? 2 : 1;
+    while (p.np > 1 && p.NR * p.np * p.Ncol > 512 - 2 * 64) p.np--;
+    if (p.NR * p.np * p.Ncol > 512 - 2 * 64) return AEFFT_ERR_UNSUPPORTED;
+    p.nacc = p.NR * p.np;
+  }
   const int jobs_per_grad = (dD + 8 * p.np - 1) / (8 * p.np);
   p.n_jobs = 2 * jobs_per_grad;
   if (p.n_jobs > TS_MAX_JOBS) return AEFFT_ERR_UNSUPPORTED;
@@ -545,17 +601,17 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   p.CPR = p.PJ / TS_CHUNK;
   p.strips = (Ny + p.TJ - 1) / p.TJ;
   const int Rmax = (p.NR - 1) * p.RS;
-  p.by_chunk = (p.NR == 1 && TS_NI * p.np * p.Ncol + 2 * 64 <= 512) ? 1 : 0;
-  p.Acol0 = (p.by_chunk ? TS_NI : 1) * p.NR * p.np * p.Ncol;
+  p.by_chunk = (p.NR == 1 && TS_NI * p.nacc * p.Ncol + 2 * 64 <= 512) ? 1 : 0;
+  p.Acol0 = (p.by_chunk ? TS_NI : 1) * p.nacc * p.Ncol;
   p.NA = (512 - p.Acol0) / 64;
   if (p.NA > 4) p.NA = 4;
   p.NSB = Rmax + 3;
-  p.sb_pitch = (uint32_t)(p.PJ + 8) * 16;
+  p.sb_pitch = p.stack ? (((uint32_t)(p.PJ + 8) * 32 * p.np + 1023) & ~1023u) : (uint32_t)(p.PJ + 8) * 16;
   p.u_slot_bytes = (uint32_t)dM * p.PJ * 4;
   p.s_src_bytes = (uint32_t)(8 * p.np) * (p.PJ + 4) * 4;
   p.s_src_bytes = (p.s_src_bytes + 127) & ~127u;
   p.s_slot_bytes = 2 * p.s_src_bytes;
-  const size_t sb_bytes = (size_t)2 * p.np * p.NSB * p.sb_pitch;
+  const size_t sb_bytes = (size_t)(p.stack ? 1 : 2 * p.np) * p.NSB * p.sb_pitch;
   const size_t s_bytes = (size_t)TS_NSF * p.s_slot_bytes;
   const size_t budget = 225 * 1024 - 1024;
   p.NU = p.RS + 3;
