@@ -41,15 +41,42 @@ struct Ring {
   }
 };
 
-// barrier wait; with DBG the cycles spent waiting are accumulated (role-stall attribution, AEFFT_*_DEBUG=1)
+// Barrier wait of a pipeline role.  A failed probe backs off with nanosleep: a dozen warps re-issuing try_wait
+// back-to-back compete with the working warps for the shared-memory pipe and the issue slots of their sub-partition.
+#ifndef AEFFT_WAIT_SLEEP_NS
+#define AEFFT_WAIT_SLEEP_NS 20
+#endif
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+#if AEFFT_WAIT_SLEEP_NS > 0
+  uint32_t done, spins = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > (1u << 22)) __trap();  // a lost arrival must fail loudly, never hang the GPU
+    __nanosleep(AEFFT_WAIT_SLEEP_NS);
+  }
+#else
+  mbar_wait(bar, parity);
+#endif
+}
+
+// with DBG the cycles spent waiting are accumulated (role-stall attribution, AEFFT_*_DEBUG=1)
 template <bool DBG>
 __device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
   if (DBG) {
     const long long t0 = clock64();
-    mbar_wait(bar, parity);
+    mbar_wait_backoff(bar, parity);
     acc += clock64() - t0;
   } else {
-    mbar_wait(bar, parity);
+    mbar_wait_backoff(bar, parity);
   }
 }
 

@@ -66,9 +66,71 @@ struct WgradTsParams {
   int stack;   // B operand = [S_hi | S_lo] of 8*np channels per pixel in one swizzled plane (2 MMAs of 2N instead of 3*np of N)
   int nacc;    // accumulators per job: NR (stack) or NR*np
   uint32_t u_slot_bytes, s_slot_bytes, s_src_bytes, sb_pitch;
-  uint32_t off_u, off_s, off_sb;
-  long long* dbg;  // AEFFT_TS_DEBUG: [cta][warp][4] cycles (wait A, wait B, total, -)
+  uint32_t off_u, off_s, off_sb, off_ub, ub_pitch;
+  long long* dbg;  // AEFFT_TS_DEBUG: [cta][warp][8] cycles (wait A, wait B, total, work, work 2)
 };
+
+// S converter, one row: fp32 [channel][PJ + 4] (TMA box, halo origin at d_off) -> bf16 hi / lo rows [pixel][8 channels] of
+// plane pl (channels 8 pl .. 8 pl + 7 of the job; channels >= nch read as zero).  64 threads; thread t owns the pixels
+// t, t + 64 (, ...) of every plane, so plane and pitch are compile-time and the loads take immediate offsets.  For the
+// decoder-gradient jobs the row also feeds the bias-gradient sums fs[] and the squared error fq (own pixels only).
+template <int PJ>
+__device__ __forceinline__ void s_convert_row(const float* __restrict__ s0, const float* __restrict__ s1, int t, int np, int nch,
+                                              bool has_s1, bool own_row, int oj, int TJ, int d_off, float (&fs)[16], float& fq,
+                                              unsigned char* sb_ring, int slot, int NSB, uint32_t sb_pitch, size_t lo_part,
+                                              bool stack) {
+  constexpr int SP = PJ + 4, UPP = PJ / 64;
+#pragma unroll
+  for (int pl = 0; pl < 2; pl++) {
+    if (pl >= np) break;
+    const int nl = nch - 8 * pl;  // live channels of this plane (may be <= 0)
+    float v[UPP][8];
+#pragma unroll
+    for (int u = 0; u < UPP; u++) {
+      const float* b0 = s0 + pl * 8 * SP + t + 64 * u + d_off;
+#pragma unroll
+      for (int e = 0; e < 8; e++) v[u][e] = e < nl ? b0[e * SP] : 0.f;
+    }
+    if (has_s1) {
+#pragma unroll
+      for (int u = 0; u < UPP; u++) {
+        const float* b1 = s1 + pl * 8 * SP + t + 64 * u + d_off;
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+          if (e < nl) v[u][e] -= b1[e * SP];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UPP; u++) {
+      const int px = t + 64 * u;
+      if (own_row && px + oj >= 0 && px + oj < TJ) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          fs[pl * 8 + e] += v[u][e];
+          fq = fmaf(v[u][e], v[u][e], fq);
+        }
+      }
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) split2(v[u][2 * e], v[u][2 * e + 1], hi[e], lo[e]);
+      if (stack) {
+        // pixel row = [hi of 8*np channels | lo of 8*np channels], 16-byte chunks XOR-swizzled on address bits 7.. (32 B /
+        // 64 B swizzle; the ring base is 1024-byte aligned, so offset bits = address bits)
+        const uint32_t row = (uint32_t)slot * sb_pitch + (uint32_t)px * (32u * np);
+        uint32_t o_hi = row + (uint32_t)pl * 16, o_lo = row + (uint32_t)(np + pl) * 16;
+        const uint32_t m = np == 1 ? 1u : 3u;
+        o_hi ^= ((o_hi >> 7) & m) << 4;
+        o_lo ^= ((o_lo >> 7) & m) << 4;
+        *reinterpret_cast<uint4*>(sb_ring + o_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(sb_ring + o_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      } else {
+        unsigned char* dst = sb_ring + ((size_t)(pl * NSB) + slot) * sb_pitch + (size_t)px * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + lo_part) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+}
 
 template <bool DBG>
 __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_constant__ WgradTsParams p) {
@@ -122,7 +184,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  long long wA = 0, wB = 0, wC = 0;
+  long long wA = 0, wB = 0, wC = 0, wD = 0;
   const long long t_start = DBG ? clock64() : 0;
 
   const int items_per_frame = p.strips * p.bands;
@@ -274,7 +336,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
     // ============================================================ S converters (64 threads)
     const int t = tid - 64;
     const int d_off = J.oj - (J.oj & ~3);  // sub-offset of the halo origin inside the aligned box
-    const int SP = p.PJ + 4, PJ = p.PJ, TJ = p.TJ, n_it = p.np * p.PJ;
+    const int PJ = p.PJ, TJ = p.TJ;
     const int nch = J.nch, oj = J.oj, oi = J.oi;
     const bool has_s1 = J.has_s1 != 0, is_gf = J.is_gf != 0;
     const size_t lo_part = (size_t)(p.np * p.NSB) * p.sb_pitch;
@@ -293,64 +355,14 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
         const float* s0 = reinterpret_cast<const float*>(s_ring + (size_t)ss.slot * p.s_slot_bytes);
         const float* s1 = reinterpret_cast<const float*>(s_ring + (size_t)ss.slot * p.s_slot_bytes + p.s_src_bytes);
         const bool own_row = is_gf && (k + oi >= 0) && (k + oi < nrows);
-        // two (pixel, plane) work items per iteration, all shared-memory loads issued before the first use: the two
-        // converter warps are latency bound (dependent load -> split -> store chains), not throughput bound
-        for (int base = t; base < n_it; base += 128) {
-          float v[2][8];
-          int pls[2], pxs[2];
-#pragma unroll
-          for (int u = 0; u < 2; u++) {
-            const int idx = base + 64 * u;
-            const int pl = idx >= PJ ? 1 : 0, px = idx - pl * PJ;
-            pls[u] = pl; pxs[u] = px;
-            const bool live = idx < n_it;
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-              const int ch = pl * 8 + e;
-              v[u][e] = (live && ch < nch) ? s0[ch * SP + px + d_off] : 0.f;
-            }
-            if (has_s1) {
-#pragma unroll
-              for (int e = 0; e < 8; e++) {
-                const int ch = pl * 8 + e;
-                if (live && ch < nch) v[u][e] -= s1[ch * SP + px + d_off];
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 2; u++) {
-            if (base + 64 * u < n_it) {
-              const int pl = pls[u], px = pxs[u];
-              if (own_row && px + oj >= 0 && px + oj < TJ) {
-                if (pl == 0) {
-#pragma unroll
-                  for (int e = 0; e < 8; e++) { fs[e] += v[u][e]; fq = fmaf(v[u][e], v[u][e], fq); }
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 8; e++) { fs[8 + e] += v[u][e]; fq = fmaf(v[u][e], v[u][e], fq); }
-                }
-              }
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; e++) split2(v[u][2 * e], v[u][2 * e + 1], hi[e], lo[e]);
-              if (p.stack) {
-                // pixel row = [hi of 8*np channels | lo of 8*np channels], 16-byte chunks XOR-swizzled on address bits 7.. (32 B /
-                // 64 B swizzle; the ring base is 1024-byte aligned, so offset bits = address bits)
-                const uint32_t row = (uint32_t)sb.slot * p.sb_pitch + (uint32_t)px * (32u * p.np);
-                uint32_t o_hi = row + (uint32_t)pl * 16, o_lo = row + (uint32_t)(p.np + pl) * 16;
-                const uint32_t m = p.np == 1 ? 1u : 3u;
-                o_hi ^= ((o_hi >> 7) & m) << 4;
-                o_lo ^= ((o_lo >> 7) & m) << 4;
-                *reinterpret_cast<uint4*>(sb_ring + o_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(sb_ring + o_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              } else {
-                unsigned char* dst = sb_ring + ((size_t)(pl * p.NSB) + sb.slot) * p.sb_pitch + (size_t)px * 16;
-                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(dst + lo_part) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-              }
-            }
-          }
-        }
+        const long long t_c0 = DBG ? clock64() : 0;
+        if (PJ == 128)
+          s_convert_row<128>(s0, s1, t, p.np, nch, has_s1, own_row, oj, TJ, d_off, fs, fq, sb_ring, sb.slot, p.NSB, p.sb_pitch,
+                             lo_part, p.stack != 0);
+        else
+          s_convert_row<64>(s0, s1, t, p.np, nch, has_s1, own_row, oj, TJ, d_off, fs, fq, sb_ring, sb.slot, p.NSB, p.sb_pitch,
+                            lo_part, p.stack != 0);
+        if (DBG) wC += clock64() - t_c0;
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -372,28 +384,71 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
       }
     }
   } else {
-    // ============================================================ U converters (8 warps): fp32 rows -> TMEM A chunks
+    // ============================================================ U converters (8 warps = 256 threads), two stages per
+    // K-row r:  A) the NEW image row r is converted ONCE: fp32 (TMA ring, 128B-swizzled) -> packed bf16 hi / lo pixel pairs
+    //              in a shared ring of RS rows [slot][hi|lo][channel][pixel], halo columns zeroed, channel sums taken;
+    //           B) every TMEM lane (rho, m) copies its row r - rho of that ring into the A chunks (16-byte loads, no
+    //              arithmetic): the RS row-replicas cost loads only, not RS conversions.
+    // The two stages are separated by a named barrier of the 256 converter threads.
     const int quarter = warp & 3, half = (warp - 4) >> 2;
     const int L = quarter * 32 + lane;
     const int rho = L / CU, m = L - rho * CU;
-    const int rho_lo = (quarter * 32) / CU, rho_hi = (quarter * 32 + 31) / CU;
-    const bool sum_lane = J.want_usum && rho == 0;
+    const int t256 = tid - 128;
     const uint32_t t_lane = tb + ((uint32_t)(quarter * 32) << 16) + (uint32_t)p.Acol0;
-    const int NU = p.NU, NA = p.NA;
-    int base_slot = 0;             // ring slot of U row 0 of the current item
-    int w_row = 0;                 // running index (over all items) of the next U row this warp has not waited for
-    Ring rw(NU);                   // ring position of w_row
-    int row_base = 0;              // running index of U row 0 of the current item
+    const int NA = p.NA, RS = p.RS, PJ = p.PJ, TJ = p.TJ;
+    const uint32_t ub_pitch = p.ub_pitch, ub_part = (uint32_t)CU * ub_pitch;  // bytes: channel row, hi (or lo) block
+    unsigned char* ub = smem + p.off_ub;
+    const int units_per_m = PJ >> 3, n_units = CU * units_per_m;  // 8-pixel units of one image row
+    const int upm_shift = PJ == 128 ? 4 : 3;                     // units_per_m is 16 or 8
+    Ring ru_ring(p.NU);            // fp32 ring position of the next image row to convert
     Ring rc(NA);                   // A ring position of the current chunk (advanced for EVERY chunk, see below)
     int parity = 0;                // (chunk index & 1) of the next chunk in program order
-    int rel_row = 0, rel_slot = 0; // next U row of the current item this warp has not released yet / its ring slot
-    double dsum = 0.0;
+    auto conv_barrier = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
     for (int item = cta; item < n_items; item += cpj) {
       const int rem = item % items_per_frame;
       const int i0 = (rem % p.bands) * p.BR;
       const int nrows = min(p.BR, p.Nx - i0);
-      const int n_krows = nrows + p.RS - 1;
+      const int n_krows = nrows + RS - 1;
       for (int r = 0; r < n_krows; r++) {
+        // ---- stage A: convert image row r (if any) into ring slot r % RS
+        if (r < nrows) {
+          wait_t<DBG>(&u_full[ru_ring.slot], ru_ring.phase, wA);
+          const long long t_c0 = DBG ? clock64() : 0;
+          const unsigned char* urow = u_ring + (size_t)ru_ring.slot * p.u_slot_bytes;
+          unsigned char* dst_hi = ub + (size_t)(r & (RS - 1)) * 2 * ub_part;
+          for (int unit = t256; unit < n_units; unit += 256) {
+            const int mm = unit >> upm_shift, u8 = unit & (units_per_m - 1);
+            const int px0 = u8 * 8, sub = px0 >> 5, g0 = (px0 & 31) >> 2;
+            const unsigned char* src = urow + (size_t)sub * CU * 128 + (size_t)mm * 128;
+            float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+            if (px0 < TJ) q0 = *reinterpret_cast<const float4*>(src + ((g0 ^ (mm & 7)) << 4));
+            if (px0 + 4 < TJ) q1 = *reinterpret_cast<const float4*>(src + (((g0 + 1) ^ (mm & 7)) << 4));
+            if (J.want_usum) {
+              // 16 (PJ = 128) or 8 (PJ = 64) consecutive lanes share a channel: reduce them, one atomic per channel and row
+              float sv = (q0.x + q0.y) + (q0.z + q0.w) + (q1.x + q1.y) + (q1.z + q1.w);
+              for (int o = units_per_m >> 1; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+              if ((lane & (units_per_m - 1)) == 0) atomicAdd(&usum[mm], (double)sv);
+            }
+            uint32_t hi[4], lo[4];
+            split2(q0.x, q0.y, hi[0], lo[0]);
+            split2(q0.z, q0.w, hi[1], lo[1]);
+            split2(q1.x, q1.y, hi[2], lo[2]);
+            split2(q1.z, q1.w, hi[3], lo[3]);
+            unsigned char* d = dst_hi + (size_t)mm * ub_pitch + (size_t)u8 * 16;
+            *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(d + ub_part) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          if (DBG) wC += clock64() - t_c0;
+        }
+        conv_barrier();  // row r is in the bf16 ring; the fp32 slot is free again
+        if (r < nrows) {
+          if (lane == 0) mbar_arrive(&u_empty[ru_ring.slot]);
+          ru_ring.next();
+        }
+        // ---- stage B: TMEM lane (rho, m) <- row r - rho
+        const int rrow = r - rho;
+        const bool valid = rrow >= 0 && rrow < nrows;
+        const unsigned char* lrow = ub + (size_t)(rrow & (RS - 1)) * 2 * ub_part + (size_t)m * ub_pitch;
         for (int h = 0; h < p.CPR; h++, parity ^= 1, rc.next()) {
           // Every converter warp waits for the release of EVERY chunk slot in order, also for the chunks the other half
           // writes: with an odd ring length both halves alternate on the same barriers, and a parity wait that skips a
@@ -401,67 +456,29 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
           wait_t<DBG>(&a_empty[rc.slot], rc.phase ^ 1, wB);
           if (parity != half) continue;
           const int ca = rc.slot;
-          // rows this warp will never read again (its chunks run in order): release them to the producer
-          for (; rel_row <= r - p.RS && rel_row < nrows; rel_row++) {
-            if (lane == 0) mbar_arrive(&u_empty[rel_slot]);
-            if (++rel_slot == NU) rel_slot = 0;
-          }
-          // U rows this warp reads now: r - rho for rho in [rho_lo, rho_hi], clipped to the band
-          {
-            const int newest = min(r - rho_lo, nrows - 1), oldest = max(r - rho_hi, 0);
-            if (newest >= oldest) {
-              int g = row_base + oldest;
-              if (g > w_row) { rw.skip(g - w_row); w_row = g; }
-              for (; w_row <= row_base + newest; w_row++) {
-                wait_t<DBG>(&u_full[rw.slot], rw.phase, wA);
-                rw.next();
-              }
-            }
-          }
+          const long long t_c1 = DBG ? clock64() : 0;
           fence_after_sync();
-          const int ru = r - rho;
-          const bool valid = ru >= 0 && ru < nrows;
-          int uslot = base_slot + (valid ? ru : 0);
-          uslot %= NU;
-          const unsigned char* urow = u_ring + (size_t)uslot * p.u_slot_bytes;
-          float fsum = 0.f;
 #pragma unroll
-          for (int hh = 0; hh < 2; hh++) {
-            const int sub = h * 2 + hh, px0 = sub * 32;
-            const unsigned char* src = urow + (size_t)sub * CU * 128 + (size_t)m * 128;
-            float v[32];
+          for (int part = 0; part < 2; part++) {
+            uint32_t v[32];
 #pragma unroll
             for (int g = 0; g < 8; g++) {
-              float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (valid && px0 + 4 * g < p.TJ) q = *reinterpret_cast<const float4*>(src + ((g ^ (m & 7)) << 4));
+              uint4 q = make_uint4(0u, 0u, 0u, 0u);
+              if (valid) q = *reinterpret_cast<const uint4*>(lrow + (size_t)part * ub_part + (size_t)h * 128 + g * 16);
               v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
             }
-            if (sum_lane) {
-#pragma unroll
-              for (int e = 0; e < 32; e++) fsum += v[e];
-            }
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int e = 0; e < 16; e++) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-            tmem_st16(t_lane + (uint32_t)(ca * 64 + hh * 16), hi);
-            tmem_st16(t_lane + (uint32_t)(ca * 64 + 32 + hh * 16), lo);
+            tmem_st16(t_lane + (uint32_t)(ca * 64 + part * 32), v);
+            tmem_st16(t_lane + (uint32_t)(ca * 64 + part * 32 + 16), v + 16);
           }
-          if (sum_lane) dsum += (double)fsum;
           tmem_wait_st();
           fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_full[ca]);
+          if (DBG) wD += clock64() - t_c1;
         }
+        conv_barrier();  // every lane has read its rows before stage A overwrites the oldest slot
       }
-      for (; rel_row < nrows; rel_row++) {
-        if (lane == 0) mbar_arrive(&u_empty[rel_slot]);
-        if (++rel_slot == NU) rel_slot = 0;
-      }
-      rel_row = 0;
-      row_base += nrows;
-      base_slot = (base_slot + nrows) % NU;
     }
-    if (sum_lane) atomicAdd(&usum[m], dsum);
     // ============================================================ epilogue (warps 4-7)
     if (half == 0) {
       mbar_wait(&done_bar, 0);
@@ -469,7 +486,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
       const bool had_items = cta < n_items;
       float* part = p.part + (long long)cta * p.n_tot + J.g_off;
       const int TT = p.NK * p.NL;
-      const int EL = 16 * p.np;  // stacked: accumulator columns per pixel shift = [hi 8*np | lo 8*np]
       for (int acc = 0; acc < p.nacc; acc++) {
         const int Ri = p.stack ? acc : acc / p.np, pl0 = p.stack ? 0 : acc - Ri * p.np;
         const int tk0 = Ri * p.RS + rho;
@@ -518,8 +534,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
     }
   }
   if (DBG && p.dbg && lane == 0) {
-    long long* d = p.dbg + ((long long)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + warp) * 4;
-    d[0] = wA; d[1] = wB; d[2] = clock64() - t_start; d[3] = wC;
+    long long* d = p.dbg + ((long long)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + warp) * 8;
+    d[0] = wA; d[1] = wB; d[2] = clock64() - t_start; d[3] = wC; d[4] = wD;
   }
   fence_before_sync();
   __syncthreads();
@@ -614,14 +630,19 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   const size_t sb_bytes = (size_t)(p.stack ? 1 : 2 * p.np) * p.NSB * p.sb_pitch;
   const size_t s_bytes = (size_t)TS_NSF * p.s_slot_bytes;
   const size_t budget = 225 * 1024 - 1024;
-  p.NU = p.RS + 3;
-  while (p.NU > p.RS + 1 && (size_t)p.NU * p.u_slot_bytes + s_bytes + sb_bytes + 2048 > budget) p.NU--;
-  if ((size_t)p.NU * p.u_slot_bytes + s_bytes + sb_bytes + 2048 > budget || p.NU > TS_MAXRING || p.NSB > TS_MAXRING)
+  // U side: a short fp32 TMA ring (each image row is converted once, straight after it lands) + the bf16 hi / lo ring of
+  // the RS most recent rows the TMEM lanes replicate from; pitch + 16 B so that consecutive channels shift one bank group
+  p.ub_pitch = (uint32_t)p.PJ * 2 + 16;
+  const size_t ub_bytes = (size_t)p.RS * 2 * dM * p.ub_pitch;
+  p.NU = 4;
+  while (p.NU > 2 && (size_t)p.NU * p.u_slot_bytes + ub_bytes + s_bytes + sb_bytes + 4096 > budget) p.NU--;
+  if ((size_t)p.NU * p.u_slot_bytes + ub_bytes + s_bytes + sb_bytes + 4096 > budget || p.NSB > TS_MAXRING)
     return AEFFT_ERR_UNSUPPORTED;
   p.off_u = 0;
   p.off_s = (uint32_t)(((size_t)p.NU * p.u_slot_bytes + 1023) & ~(size_t)1023);
   p.off_sb = (uint32_t)((p.off_s + s_bytes + 1023) & ~(size_t)1023);
-  const size_t smem = p.off_sb + sb_bytes + 1024;
+  p.off_ub = (uint32_t)((p.off_sb + sb_bytes + 1023) & ~(size_t)1023);
+  const size_t smem = p.off_ub + ub_bytes + 1024;
   // work split: cpj CTAs per job, every frame cut into `bands` row bands; minimise rounds x rows per band
   int cpj = ctx->sm_count / p.n_jobs;
   if (cpj < 1) cpj = 1;
@@ -669,7 +690,7 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   }
   const bool debug = getenv("AEFFT_TS_DEBUG") != nullptr;
   p.dbg = nullptr;
-  const size_t n_dbg = (size_t)cpj * p.n_jobs * 16 * 4;
+  const size_t n_dbg = (size_t)cpj * p.n_jobs * 16 * 8;
   if (debug) {
     AE_TRY(ctx->getT("wgts_dbg", n_dbg, &p.dbg));
     AE_CUDA(cudaMemsetAsync(p.dbg, 0, n_dbg * sizeof(long long), ctx->stream));
@@ -697,20 +718,20 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
     AE_CUDA(cudaMemcpy(h.data(), p.dbg, n_dbg * sizeof(long long), cudaMemcpyDeviceToHost));
     const char* role[4] = {"producer (s_empty, u_empty)", "issuer   (sb_full, a_full)", "S conv   (s_full, sb_empty)",
                            "U conv   (u_full, a_empty)"};
-    double acc[4][4] = {};
+    double acc[4][5] = {};
     int cnt[4] = {};
     for (int c = 0; c < cpj * p.n_jobs; c++)
       for (int w = 0; w < 16; w++) {
         if (w == 1) continue;
         const int r = w == 0 ? 0 : w >= 12 ? 1 : w < 4 ? 2 : 3;
-        for (int q = 0; q < 4; q++) acc[r][q] += (double)h[((size_t)c * 16 + w) * 4 + q];
+        for (int q = 0; q < 5; q++) acc[r][q] += (double)h[((size_t)c * 16 + w) * 8 + q];
         cnt[r]++;
       }
     fprintf(stderr, "[wgrad_ts] dM=%d dD=%d %dx%d B=%lld PJ=%d RS=%d NR=%d np=%d jobs=%d cpj=%d bands=%d BR=%d NU=%d NSB=%d NA=%d smem=%zu\n",
             dM, dD, Nx, Ny, (long long)B, p.PJ, p.RS, p.NR, p.np, p.n_jobs, cpj, p.bands, p.BR, p.NU, p.NSB, p.NA, smem);
     for (int r = 0; r < 4; r++)
-      fprintf(stderr, "[wgrad_ts]   %-30s waitA %9.0f  waitB %9.0f  total %9.0f  mma-issue %9.0f cycles\n", role[r],
-              acc[r][0] / cnt[r], acc[r][1] / cnt[r], acc[r][2] / cnt[r], acc[r][3] / cnt[r]);
+      fprintf(stderr, "[wgrad_ts]   %-30s waitA %9.0f  waitB %9.0f  total %9.0f  work %9.0f + %9.0f cycles\n", role[r],
+              acc[r][0] / cnt[r], acc[r][1] / cnt[r], acc[r][2] / cnt[r], acc[r][3] / cnt[r], acc[r][4] / cnt[r]);
   }
   return AEFFT_OK;
 }
