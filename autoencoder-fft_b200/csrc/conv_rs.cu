@@ -49,6 +49,7 @@ struct ConvRsParams {
   int PJs, G, TJ, strips, bands, BR;
   int n_sub, items, cpj;
   int KS, NP, kpack, NLg, Ntot, Rr, NSB, NSF, passes;
+  int tmem_cols;   // 512 / 256 / 128 columns for 1 / 2 / 3 CTAs per SM
   int stack2, CW;  // stack2: B rows = [W_hi | W_lo] per window row (2 MMAs instead of 3); CW = accumulator columns per output row
   uint32_t w_bytes, seg_bytes, src_bytes, x_slot_bytes, sb_pitch;
   uint32_t off_w, off_x, off_sb;
@@ -96,11 +97,12 @@ __global__ void conv_rs_weight_prep_kernel(const float* __restrict__ w, long lon
 }
 
 template <bool DBG>
-__global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_constant__ ConvRsParams p) {
+__global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_constant__ ConvRsParams p) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_full[RS_NSF], s_empty[RS_NSF], xb_full[RS_MAXSB], xb_empty[RS_MAXSB],
       acc_full[RS_MAXACC], acc_empty[RS_MAXACC];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float bias_s[256];  // bias of this job's outputs (0 beyond O or without bias)
 
   // warp index via a broadcast shuffle: the compiler then knows it is warp-uniform and keeps the role loops (MMA
   // descriptors, ring positions) in uniform registers instead of moving them there lane by lane
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
   unsigned char* x_ring = smem + p.off_x;
   unsigned char* sb_ring = smem + p.off_sb;
 
-  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (warp == 0) tmem_alloc(&tmem_slot, (uint32_t)p.tmem_cols);
   if (tid == 32) {
     for (int i = 0; i < p.NSF; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], RS_CONV_WARPS); }
     for (int i = 0; i < p.NSB; i++) { mbar_init(&xb_full[i], RS_CONV_WARPS); mbar_init(&xb_empty[i], 1); }
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     const uint32_t n16 = (uint32_t)(2 * p.NP * p.NSB) * p.sb_pitch / 16;
     uint4* z = reinterpret_cast<uint4*>(sb_ring);
     for (uint32_t i = tid; i < n16; i += RS_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 256) bias_s[tid] = (p.bias && tid < p.Oj && job * p.Oj + tid < p.O) ? __ldg(p.bias + job * p.Oj + tid) : 0.f;
   }
   fence_proxy_async();
   fence_before_sync();
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
         const int n_in = nrows + NK - 1;
         const int nseg = min(G, p.n_sub - ug * G);
         for (int k = 0; k < n_in; k++) {
-          wait_t<DBG>(&s_empty[ss.slot], ss.phase ^ 1, wA);
+          wait_t<DBG, true>(&s_empty[ss.slot], ss.phase ^ 1, wA);
           unsigned char* dst = x_ring + (size_t)ss.slot * p.x_slot_bytes;
           mbar_expect_tx(&s_full[ss.slot], seg_tx * nseg * (p.has_x1 ? 2 : 1));
           for (int g = 0; g < nseg; g++) {
@@ -200,35 +203,42 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
       const int i0 = band * p.BR;
       const int nrows = min(p.BR, p.Nx - i0);
       const int n_in = nrows + NK - 1;
+      int fslot = gro;
       for (int k = 0; k < n_in; k++) {
-        wait_t<DBG>(&xb_full[rx.slot], rx.phase, wA);
+        wait_t<DBG, true>(&xb_full[rx.slot], rx.phase, wA);
         if (k < nrows) {
           // the accumulator slot of the newest output row (rho = k) must have been drained and zeroed
-          wait_t<DBG>(&acc_empty[rn.slot], rn.phase ^ 1, wB);
+          wait_t<DBG, true>(&acc_empty[rn.slot], rn.phase ^ 1, wB);
           rn.next();
         }
         fence_after_sync();
         const long long t_m0 = DBG ? clock64() : 0;
-        // pieces: output rows rho_lo..rho_hi (ascending) = window rows tk_hi..tk_lo, split at the ring wrap and at N = 256
+        // pieces: output rows rho_lo..rho_hi (ascending) = window rows tk_hi..tk_lo, split at the ring wrap and at N = 256.
+        // fslot = accumulator slot of the oldest row of the stack, advanced as rows complete (no division per row).
         const int tk_lo = max(0, k - nrows + 1), tk_hi = min(NK - 1, k);
-        int pc_n0[4], pc_N[4], pc_d[4], npc = 0;
+        int pc_n0[4], pc_N[4], pc_d[4], npc = 1;
         {
-          int rho = k - tk_hi;
-          const int rho_hi = k - tk_lo;
-          int slot = (gro + rho) % Rr;
+          const int len_all = tk_hi - tk_lo + 1;
+          int len = min(len_all, min(Rr - fslot, maxchunks));
+          pc_n0[0] = (NK - 1 - tk_hi) * CW;
+          pc_N[0] = len * CW;
+          pc_d[0] = fslot * CW;
+          if (len < len_all) {  // rare: the stack wraps around the accumulator ring or exceeds N = 256
+            int rho = k - tk_hi + len, slot = fslot + len;
+            const int rho_hi = k - tk_lo;
+            if (slot >= Rr) slot -= Rr;
 #pragma unroll
-          for (int i = 0; i < 4; i++) {
-            if (rho <= rho_hi) {
-              int len = rho_hi - rho + 1;
-              if (len > Rr - slot) len = Rr - slot;
-              if (len > maxchunks) len = maxchunks;
-              pc_n0[i] = (NK - 1 - k + rho) * CW;
-              pc_N[i] = len * CW;
-              pc_d[i] = slot * CW;
-              rho += len;
-              slot += len;
-              if (slot >= Rr) slot -= Rr;
-              npc = i + 1;
+            for (int i = 1; i < 4; i++) {
+              if (rho <= rho_hi) {
+                len = min(rho_hi - rho + 1, min(Rr - slot, maxchunks));
+                pc_n0[i] = (NK - 1 - k + rho) * CW;
+                pc_N[i] = len * CW;
+                pc_d[i] = slot * CW;
+                rho += len;
+                slot += len;
+                if (slot >= Rr) slot -= Rr;
+                npc = i + 1;
+              }
             }
           }
         }
@@ -289,11 +299,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
           }
         }
         if (DBG) wC += clock64() - t_m0;
+        const bool row_done = k >= NK - 1;  // this input row completes output row k - NK + 1, the oldest of the stack
         if (elect_one()) {
           commit(&xb_empty[rx.slot]);
-          const int done = k - NK + 1;  // output row completed by this input row
-          if (done >= 0) commit(&acc_full[(gro + done) % Rr]);
+          if (row_done) commit(&acc_full[fslot]);
         }
+        if (row_done && ++fslot == Rr) fslot = 0;
         rx.next();
       }
       gro = rn.slot;
@@ -311,8 +322,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
       const int n_in = nrows + NK - 1;
       const int nseg = min(G, p.n_sub - ug * G);
       for (int k = 0; k < n_in; k++) {
-        wait_t<DBG>(&s_full[ss.slot], ss.phase, wA);
-        wait_t<DBG>(&xb_empty[sb.slot], sb.phase ^ 1, wB);
+        wait_t<DBG, true>(&s_full[ss.slot], ss.phase, wA);
+        wait_t<DBG, true>(&xb_empty[sb.slot], sb.phase ^ 1, wB);
         const unsigned char* xs = x_ring + (size_t)ss.slot * p.x_slot_bytes;
         for (int idx = t; idx < n_it; idx += NT) {
           const int pl = idx >> 7, px = idx & 127;
@@ -355,6 +366,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
     const int seg = lg / PJs, c = lg - seg * PJs;
     const uint32_t t_lane = tb + ((uint32_t)(quarter * 32) << 16);
     const long long plane = (long long)p.Nx * p.Ny;
+    const size_t plane_u = (size_t)plane;
     const int o0 = job * p.Oj;
     const int n_o = min(p.Oj, p.O - o0);
     uint32_t z[16];
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
       const bool lane_ok = u < p.n_sub && c < p.TJ && j0 + c < p.Ny;
       float* obase = p.out + ((long long)b * p.O + o0) * plane + (long long)i0 * p.Ny + j0 + c;
       for (int rho = 0; rho < nrows; rho++) {
-        wait_t<DBG>(&acc_full[slot], phase, wA);
+        wait_t<DBG, true>(&acc_full[slot], phase, wA);
         fence_after_sync();
         float* orow = obase + (long long)rho * p.Ny;
         for (int c0 = 0; c0 < p.O_pad; c0 += 16) {
@@ -386,10 +398,23 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
             for (int e = 0; e < 16; e++) v[e] += u[e];
           }
           if (lane_ok) {
+            // one coalesced 512-byte store per output channel; the channel stride is warp-uniform
+            const int nv = n_o - c0;  // live channels of this chunk (warp-uniform)
+            float* q = orow + (size_t)c0 * plane_u;
+            const float4* bq = reinterpret_cast<const float4*>(bias_s + c0);
+            float bb[16];
 #pragma unroll
-            for (int e = 0; e < 16; e++) {
-              const int o = c0 + e;
-              if (o < n_o) orow[(long long)o * plane] = v[e] + (p.bias ? __ldg(p.bias + o0 + o) : 0.f);
+            for (int e = 0; e < 4; e++) {
+              const float4 t4 = bq[e];
+              bb[4 * e] = t4.x; bb[4 * e + 1] = t4.y; bb[4 * e + 2] = t4.z; bb[4 * e + 3] = t4.w;
+            }
+            if (nv >= 16) {
+#pragma unroll
+              for (int e = 0; e < 16; e++) q[(size_t)e * plane_u] = v[e] + bb[e];
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; e++)
+                if (e < nv) q[(size_t)e * plane_u] = v[e] + bb[e];
             }
           }
         }
@@ -407,7 +432,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1) conv_rs_kernel(const __grid_con
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tb, 512);
+  if (warp == 0) tmem_dealloc(tb, (uint32_t)p.tmem_cols);
 }
 
 // Returns AEFFT_ERR_UNSUPPORTED outside the envelope (the caller falls back to conv_tc_ws / conv_tc / fp32).
@@ -438,30 +463,42 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
   p.seg_bytes = ((uint32_t)C * (p.PJs + 4) * 4 + 127) & ~127u;
   p.src_bytes = (uint32_t)p.G * p.seg_bytes;
   p.x_slot_bytes = (p.has_x1 ? 2 : 1) * p.src_bytes;
-  // outputs per job: as many as fit next to the rings (weights of all K stages stay resident)
-  const size_t budget = 225 * 1024 - 1024;
+  // outputs per job: as many as fit next to the rings (weights of all K stages stay resident).
+  // Two or three CTAs per SM when a configuration fits in that share of the shared memory and of the tensor memory: the
+  // kernel is bound by the latency of its single MMA-issuing thread (tensor pipe 17-28 % active, ncu), and every further
+  // CTA on the SM brings another issuer, converter set and epilogue (AEFFT_RS_ONE=1 keeps one CTA per SM).
   size_t x_bytes = 0;
   int found = 0;
-  // preference order: double-buffered fp32 staging, few output jobs, deep bf16 ring
-  for (int NSF = RS_NSF; NSF >= 1 && !found; NSF--) {
-    x_bytes = (size_t)NSF * p.x_slot_bytes;
-    for (int split = 1; split <= 8 && !found; split++) {
-      const int Oj = ((O + split - 1) / split + 15) / 16 * 16;
-      const int O_pad = Oj;
-      // [W_hi | W_lo] stacking (2 MMAs of 2N instead of 3 of N) measured no faster on B200 (the N = 80 MMAs are not purely
-      // A-read bound): opt-in for experiments only
-      const int stack2 = (getenv("AEFFT_RS_STACK2") && passes == 3 && 2 * win.Nk * O_pad <= 256) ? 1 : 0;
-      const int CW = stack2 ? 2 * O_pad : O_pad;
-      const int Rr = 512 / CW > RS_MAXACC ? RS_MAXACC : 512 / CW;
-      if (Rr < win.Nk + 1) continue;
-      const size_t w_bytes = (size_t)p.KS * 2 * p.NLg * 2 * (win.Nk * O_pad) * 16;
-      for (int NSB = 4; NSB >= 2 && !found; NSB--) {
-        const size_t sb_bytes = (size_t)2 * p.NP * NSB * p.sb_pitch;
-        if (w_bytes + x_bytes + sb_bytes + 3 * 1024 <= budget) {
-          p.Oj = Oj; p.O_pad = O_pad; p.Rr = Rr; p.NSB = NSB; p.NSF = NSF; p.w_bytes = (uint32_t)w_bytes;
-          p.stack2 = stack2; p.CW = CW;
-          p.n_jobs = (O + Oj - 1) / Oj;
-          found = 1;
+  p.tmem_cols = 512;
+  int per_sm = 1;
+  const int max_per_sm = getenv("AEFFT_RS_ONE") ? 1 : getenv("AEFFT_RS_TWO") ? 2 : 3;
+  for (int ncta = max_per_sm; ncta >= 1 && !found; ncta--) {
+    const bool two = ncta > 1;
+    const size_t budget = ncta == 3 ? 74 * 1024 : ncta == 2 ? 112 * 1024 : 225 * 1024 - 1024;
+    const int cols = 512 >> (ncta == 3 ? 2 : ncta - 1);
+    // preference order: double-buffered fp32 staging, few output jobs, deep bf16 ring
+    for (int NSF = RS_NSF; NSF >= (two ? RS_NSF : 1) && !found; NSF--) {
+      x_bytes = (size_t)NSF * p.x_slot_bytes;
+      for (int split = 1; split <= (two ? 1 : 8) && !found; split++) {
+        const int Oj = ((O + split - 1) / split + 15) / 16 * 16;
+        const int O_pad = Oj;
+        // [W_hi | W_lo] stacking (2 MMAs of 2N instead of 3 of N) measured no faster on B200 (the N = 80 MMAs are not purely
+        // A-read bound): opt-in for experiments only
+        const int stack2 = (getenv("AEFFT_RS_STACK2") && passes == 3 && 2 * win.Nk * O_pad <= 256) ? 1 : 0;
+        const int CW = stack2 ? 2 * O_pad : O_pad;
+        const int Rr = cols / CW > RS_MAXACC ? RS_MAXACC : cols / CW;
+        if (Rr < win.Nk + (two ? 3 : 1)) continue;
+        const size_t w_bytes = (size_t)p.KS * 2 * p.NLg * 2 * (win.Nk * O_pad) * 16;
+        for (int NSB = 4; NSB >= (two ? 3 : 2) && !found; NSB--) {
+          const size_t sb_bytes = (size_t)2 * p.NP * NSB * p.sb_pitch;
+          if (w_bytes + x_bytes + sb_bytes + 3 * 1024 <= budget) {
+            p.Oj = Oj; p.O_pad = O_pad; p.Rr = Rr; p.NSB = NSB; p.NSF = NSF; p.w_bytes = (uint32_t)w_bytes;
+            p.stack2 = stack2; p.CW = CW;
+            p.n_jobs = (O + Oj - 1) / Oj;
+            p.tmem_cols = cols;
+            per_sm = ncta;
+            found = 1;
+          }
         }
       }
     }
@@ -473,7 +510,7 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
   p.off_sb = (uint32_t)((p.off_x + x_bytes + 1023) & ~(size_t)1023);
   const size_t smem = p.off_sb + (size_t)2 * p.NP * p.NSB * p.sb_pitch + 1024;
   // work split
-  int cpj = ctx->sm_count / p.n_jobs;
+  int cpj = per_sm * ctx->sm_count / p.n_jobs;
   if (cpj < 1) cpj = 1;
   const int n_ug = (p.n_sub + p.G - 1) / p.G;
   {
@@ -547,8 +584,8 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
         for (int q = 0; q < 4; q++) acc[r][q] += (double)h[((size_t)c * 12 + wv) * 4 + q];
         cnt[r]++;
       }
-    fprintf(stderr, "[conv_rs] C=%d O=%d %dx%d B=%lld PJs=%d G=%d Oj=%d jobs=%d cpj=%d bands=%d BR=%d Rr=%d NSB=%d KS=%d kpack=%d smem=%zu\n",
-            C, O, Nx, Ny, (long long)B, p.PJs, p.G, p.Oj, p.n_jobs, cpj, p.bands, p.BR, p.Rr, p.NSB, p.KS, p.kpack, smem);
+    fprintf(stderr, "[conv_rs] C=%d O=%d %dx%d B=%lld PJs=%d G=%d Oj=%d jobs=%d cpj=%d bands=%d BR=%d Rr=%d NSB=%d KS=%d kpack=%d smem=%zu tmem=%d\n",
+            C, O, Nx, Ny, (long long)B, p.PJs, p.G, p.Oj, p.n_jobs, cpj, p.bands, p.BR, p.Rr, p.NSB, p.KS, p.kpack, smem, p.tmem_cols);
     for (int r = 0; r < 4; r++)
       fprintf(stderr, "[conv_rs]   %-30s waitA %9.0f  waitB %9.0f  total %9.0f  mma-issue %9.0f cycles\n", role[r],
               acc[r][0] / cnt[r], acc[r][1] / cnt[r], acc[r][2] / cnt[r], acc[r][3] / cnt[r]);
