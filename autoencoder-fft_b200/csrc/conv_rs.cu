@@ -72,8 +72,10 @@ __global__ void conv_rs_weight_prep_kernel(const float* __restrict__ w, long lon
     const int ks = (int)(r % KS); r /= KS;
     const int job = (int)r;
     const int tk = NK - 1 - n / O_pad, o = n % O_pad;
-    const int tl = kpack ? 2 * tlg + kchunk : tlg;
-    const int c = kpack ? e : ks * 16 + kchunk * 8 + e;
+    // K index of this element: channel block (kpack 0), tap pair x 8 channels (kpack 1), or (tap, channel) packed (kpack 2)
+    const int kk = kchunk * 8 + e;
+    const int tl = kpack == 2 ? (kk < C * NL ? kk / C : NL) : kpack ? 2 * tlg + kchunk : tlg;
+    const int c = kpack == 2 ? kk % C : kpack ? e : ks * 16 + kchunk * 8 + e;
     const int k = flip ? NK - 1 - tk : tk, l = flip ? NL - 1 - tl : tl;
     const int og = job * Oj + o;
     float v = 0.f;
@@ -102,7 +104,8 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
   __shared__ __align__(8) uint64_t s_full[RS_NSF], s_empty[RS_NSF], xb_full[RS_MAXSB], xb_empty[RS_MAXSB],
       acc_full[RS_MAXACC], acc_empty[RS_MAXACC];
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float bias_s[256];  // bias of this job's outputs (0 beyond O or without bias)
+  __shared__ __align__(16) float bias_s[256];
+  __shared__ int voff_s[16];  // kpack 2: offset of K index (tl, c) inside the fp32 row box, -1 = padding  // bias of this job's outputs (0 beyond O or without bias)
 
   // warp index via a broadcast shuffle: the compiler then knows it is warp-uniform and keeps the role loops (MMA
   // descriptors, ring positions) in uniform registers instead of moving them there lane by lane
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
     const uint32_t n16 = (uint32_t)(2 * p.NP * p.NSB) * p.sb_pitch / 16;
     uint4* z = reinterpret_cast<uint4*>(sb_ring);
     for (uint32_t i = tid; i < n16; i += RS_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    if (tid < 16) voff_s[tid] = tid < p.C * p.NL ? (tid % p.C) * (p.PJs + 4) + tid / p.C : -1;
     if (tid < 256) bias_s[tid] = (p.bias && tid < p.Oj && job * p.Oj + tid < p.O) ? __ldg(p.bias + job * p.Oj + tid) : 0.f;
   }
   fence_proxy_async();
@@ -189,12 +193,15 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
     const int NSB = p.NSB, NP = p.NP, KS = p.KS, NLg = p.NLg, Rr = p.Rr, CW = p.CW;
     const bool stack2 = p.stack2 != 0;
     const int Ntot = stack2 ? 2 * p.Ntot : p.Ntot;  // B rows per K chunk
-    const uint32_t a_lbo = p.kpack ? 16u : (uint32_t)NSB * pitch;
+    const uint32_t a_lbo = p.kpack == 1 ? 16u : (uint32_t)NSB * pitch;
     const uint64_t a_desc0 = make_desc(0, a_lbo, 128), b_desc0 = make_desc(0, (uint32_t)Ntot * 16, 128);
     const uint32_t part_off16 = ((uint32_t)(NP * NSB) * pitch) >> 4;               // A: hi -> lo part
     const uint32_t wpart_off16 = (uint32_t)(NLg * 2 * Ntot);                       // W: hi -> lo part (16-byte units; !stack2)
     const bool three = p.passes == 3;
     const int maxchunks = 256 / CW;
+    const uint32_t a_ks_step16 = p.kpack == 1 ? 0u : (((uint32_t)(2 * NSB) * pitch) >> 4);
+    const uint32_t a_tl_step16 = p.kpack == 1 ? 2u : 1u;
+    const uint32_t w_ks_step16 = (uint32_t)((stack2 ? 1 : 2) * NLg * 2 * Ntot), w_tl_step16 = (uint32_t)(2 * Ntot);
     Ring rx(NSB);
     Ring rn(Rr);  // accumulator ring position of the newest output row (rho = k)
     int gro = 0;  // accumulator slot of output row 0 of the current item
@@ -213,46 +220,22 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
         }
         fence_after_sync();
         const long long t_m0 = DBG ? clock64() : 0;
-        // pieces: output rows rho_lo..rho_hi (ascending) = window rows tk_hi..tk_lo, split at the ring wrap and at N = 256.
-        // fslot = accumulator slot of the oldest row of the stack, advanced as rows complete (no division per row).
+        // The stack = output rows rho_lo..rho_hi (ascending) = window rows tk_hi..tk_lo, one MMA group per contiguous piece
+        // of accumulator columns (split at the ring wrap and at N = 256).  fslot = accumulator slot of the oldest row of the
+        // stack, advanced as rows complete.  One elected lane walks pieces and descriptors with constant increments; every
+        // accumulator column still receives its MMAs in (K stage, window column, pass) order.
         const int tk_lo = max(0, k - nrows + 1), tk_hi = min(NK - 1, k);
-        int pc_n0[4], pc_N[4], pc_d[4], npc = 1;
-        {
-          const int len_all = tk_hi - tk_lo + 1;
-          int len = min(len_all, min(Rr - fslot, maxchunks));
-          pc_n0[0] = (NK - 1 - tk_hi) * CW;
-          pc_N[0] = len * CW;
-          pc_d[0] = fslot * CW;
-          if (len < len_all) {  // rare: the stack wraps around the accumulator ring or exceeds N = 256
-            int rho = k - tk_hi + len, slot = fslot + len;
-            const int rho_hi = k - tk_lo;
-            if (slot >= Rr) slot -= Rr;
-#pragma unroll
-            for (int i = 1; i < 4; i++) {
-              if (rho <= rho_hi) {
-                len = min(rho_hi - rho + 1, min(Rr - slot, maxchunks));
-                pc_n0[i] = (NK - 1 - k + rho) * CW;
-                pc_N[i] = len * CW;
-                pc_d[i] = slot * CW;
-                rho += len;
-                slot += len;
-                if (slot >= Rr) slot -= Rr;
-                npc = i + 1;
-              }
-            }
-          }
-        }
         const uint32_t a_row16 = (sb_base + (uint32_t)rx.slot * pitch) >> 4;
-        const uint32_t a_ks_step16 = p.kpack ? 0u : (((uint32_t)(2 * NSB) * pitch) >> 4);
-        const uint32_t a_tl_step16 = p.kpack ? 2u : 1u;
-        const uint32_t w_ks_step16 = (uint32_t)((stack2 ? 1 : 2) * NLg * 2 * Ntot), w_tl_step16 = (uint32_t)(2 * Ntot);
-        if (npc == 1) {
-          // common case (no ring wrap inside the stack): one elected lane walks the descriptors with constant increments
-          if (elect_one()) {
-            const uint32_t idesc = make_idesc_bf16(128, pc_N[0], 0, 0);
-            const uint32_t d = tb + (uint32_t)pc_d[0];
+        if (elect_one()) {
+          int rem = tk_hi - tk_lo + 1, slot = fslot;
+          uint32_t n0 = (uint32_t)((NK - 1 - tk_hi) * CW);
+#pragma unroll 1
+          while (rem > 0) {
+            const int len = min(rem, min(Rr - slot, maxchunks));
+            const uint32_t idesc = make_idesc_bf16(128, len * CW, 0, 0);
+            const uint32_t d = tb + (uint32_t)(slot * CW);
             uint64_t a_ks = a_desc0 + (uint64_t)a_row16;
-            uint64_t b_ks = b_desc0 + (uint64_t)((w_base >> 4) + (uint32_t)pc_n0[0]);
+            uint64_t b_ks = b_desc0 + (uint64_t)((w_base >> 4) + n0);
 #pragma unroll 1
             for (int ks = 0; ks < KS; ks++, a_ks += a_ks_step16, b_ks += w_ks_step16) {
               uint64_t a_hi = a_ks, b_hi = b_ks;
@@ -267,37 +250,13 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
                 }
               }
             }
-          }
-          __syncwarp();
-        } else {
-#pragma unroll 1
-          for (int ks = 0; ks < KS; ks++) {
-            const uint32_t a_ks16 = a_row16 + (uint32_t)ks * a_ks_step16;
-#pragma unroll 1
-            for (int tlg = 0; tlg < NLg; tlg++) {
-              const uint32_t a16 = a_ks16 + (uint32_t)tlg * a_tl_step16;
-              const uint32_t w16 = (w_base >> 4) + (uint32_t)ks * w_ks_step16 + (uint32_t)tlg * w_tl_step16;
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                if (i < npc) {
-                  const uint32_t idesc = make_idesc_bf16(128, pc_N[i], 0, 0);
-                  const uint64_t a_hi = a_desc0 + (uint64_t)a16, a_lo = a_hi + (uint64_t)part_off16;
-                  const uint64_t b_hi = b_desc0 + (uint64_t)(w16 + (uint32_t)pc_n0[i]), b_lo = b_hi + (uint64_t)wpart_off16;
-                  const uint32_t d = tb + (uint32_t)pc_d[i];
-                  if (elect_one()) {
-                    mma_bf16(d, a_hi, b_hi, idesc, true);
-                    if (stack2) {
-                      mma_bf16(d, a_lo, b_hi, idesc, true);
-                    } else if (three) {
-                      mma_bf16(d, a_hi, b_lo, idesc, true);
-                      mma_bf16(d, a_lo, b_hi, idesc, true);
-                    }
-                  }
-                }
-              }
-            }
+            rem -= len;
+            n0 += (uint32_t)(len * CW);
+            slot += len;
+            if (slot >= Rr) slot -= Rr;
           }
         }
+        __syncwarp();
         if (DBG) wC += clock64() - t_m0;
         const bool row_done = k >= NK - 1;  // this input row completes output row k - NK + 1, the oldest of the stack
         if (elect_one()) {
@@ -331,16 +290,31 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
           const float* s0 = reinterpret_cast<const float*>(xs + (size_t)seg * p.seg_bytes) + c + d_off;
           const float* s1 = reinterpret_cast<const float*>(xs + p.src_bytes + (size_t)seg * p.seg_bytes) + c + d_off;
           float v[8];
+          if (p.kpack == 2) {
+            // K = (window column tl, channel c): element kk of pixel px is x[c][px + tl]
 #pragma unroll
-          for (int e = 0; e < 8; e++) {
-            const int ch = pl * 8 + e;
-            float x = 0.f;
-            if (ch < p.C && seg < nseg) {
-              x = s0[ch * SP];
-              if (p.has_x1) x -= s1[ch * SP];
-              else x *= p.scale;
+            for (int e = 0; e < 8; e++) {
+              const int off = voff_s[pl * 8 + e];
+              float x = 0.f;
+              if (off >= 0 && seg < nseg && c < p.TJ) {
+                x = s0[off];
+                if (p.has_x1) x -= s1[off];
+                else x *= p.scale;
+              }
+              v[e] = x;
             }
-            v[e] = x;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+              const int ch = pl * 8 + e;
+              float x = 0.f;
+              if (ch < p.C && seg < nseg) {
+                x = s0[ch * SP];
+                if (p.has_x1) x -= s1[ch * SP];
+                else x *= p.scale;
+              }
+              v[e] = x;
+            }
           }
           uint32_t hi[4], lo[4];
 #pragma unroll
@@ -448,10 +422,12 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
   p.has_x1 = src1 ? 1 : 0;
   p.scale = (!src1 && pre_div != 0.f) ? 1.f / pre_div : 1.f;
   p.bias = bias; p.out = out; p.passes = passes;
-  p.kpack = C <= 8 ? 1 : 0;
+  // K packing: 16 channels per MMA (0); two window columns x 8 channels for C <= 8 (1); or, when a whole window row fits
+  // (C * NL <= 16, the 3-channel image layer), K = (window column, channel): ONE MMA triple per input row instead of NLg
+  p.kpack = (C * win.Nl <= 16 && !getenv("AEFFT_RS_NO_TAPPACK")) ? 2 : C <= 8 ? 1 : 0;
   p.KS = p.kpack ? 1 : (C + 15) / 16;
-  p.NP = p.kpack ? 1 : 2 * p.KS;
-  p.NLg = p.kpack ? (win.Nl + 1) / 2 : win.Nl;
+  p.NP = p.kpack == 1 ? 1 : 2 * p.KS;
+  p.NLg = p.kpack == 2 ? 1 : p.kpack ? (win.Nl + 1) / 2 : win.Nl;
   const int halo = win.Nl - 1;
   p.PJs = (Ny + halo <= 64) ? 64 : 128;
   p.G = 128 / p.PJs;
