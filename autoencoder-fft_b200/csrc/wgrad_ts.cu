@@ -489,23 +489,33 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
       for (int acc = 0; acc < p.nacc; acc++) {
         const int Ri = p.stack ? acc : acc / p.np, pl0 = p.stack ? 0 : acc - Ri * p.np;
         const int tk0 = Ri * p.RS + rho;
-        for (int c0 = 0; c0 < p.Ncol; c0 += 16) {
+        const bool pair_cols = p.stack && p.np == 2;  // stacked, two planes: [hi 16 | lo 16] per shift, summed here
+        for (int c0 = 0; c0 < p.Ncol; c0 += pair_cols ? 32 : 16) {
           float v[16];
-          tmem_ld16(tb + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.Ncol + c0), v);
-          if (p.by_chunk) {
-            for (int cp = 1; cp < TS_NI; cp++) {  // issuer copies, fixed order
-              float w[16];
-              tmem_ld16(tb + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((cp * p.nacc + acc) * p.Ncol + c0), w);
+          // accumulator columns c0..c0+15, issuer copies added in fixed order
+          auto load_cols = [&](int col, float (&dst)[16]) {
+            tmem_ld16(tb + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.Ncol + col), dst);
+            if (p.by_chunk) {
+              for (int cp = 1; cp < TS_NI; cp++) {
+                float w[16];
+                tmem_ld16(tb + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((cp * p.nacc + acc) * p.Ncol + col), w);
 #pragma unroll
-              for (int e = 0; e < 16; e++) v[e] += w[e];
+                for (int e = 0; e < 16; e++) dst[e] += w[e];
+              }
             }
+          };
+          load_cols(c0, v);
+          if (pair_cols) {
+            float w2[16];
+            load_cols(c0 + 16, w2);
+#pragma unroll
+            for (int e = 0; e < 16; e++) v[e] += w2[e];
           }
-          // which (shift, channel, part) do these 16 columns hold?
+          // which (shift, channel) do these columns hold?
           int s, chb, nval;
-          bool lo_part = false;
           if (!p.stack) { s = c0 >> 3; chb = pl0 * 8; nval = 16; }           // two shifts x 8 channels
           else if (p.np == 1) { s = c0 >> 4; chb = 0; nval = 8; }             // [hi 8 | lo 8] of one shift
-          else { s = c0 >> 5; chb = 0; nval = 16; lo_part = (c0 & 16) != 0; } // hi 16 or lo 16 of one shift
+          else { s = c0 >> 5; chb = 0; nval = 16; }                           // [hi 16 | lo 16] of one shift, already summed
           if (p.stack && p.np == 1) {
 #pragma unroll
             for (int e = 0; e < 8; e++) v[e] += v[8 + e];
@@ -524,8 +534,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
                 const long long gi = J.is_gf ? (((long long)d * p.dM + m) * TT + k * p.NL + l)
                                              : (((long long)m * p.dD + d) * TT + k * p.NL + l);
                 const float val = had_items ? v[e] : 0.f;
-                if (p.stack && p.np == 2 && lo_part) part[gi] += val;  // the hi half of this shift was written just before
-                else part[gi] = val;
+                part[gi] = val;
               }
             }
           }
@@ -584,14 +593,21 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   p.passes = passes; p.flip = win.flip;
   p.RS = 128 / dM;
   p.NR = (win.Nk + p.RS - 1) / p.RS;
-  // Stacked B operand (opt-in, AEFFT_TS_STACK=1): one swizzled plane [pixel][hi of 8*np channels | lo of 8*np channels],
-  // N = 16*np*NL columns per MMA, 2 MMAs per (K-step, window-row group) instead of 3*np of N = 48 (validated by
-  // tools/probe_ts.cu: MN-major SWIZZLE_32B/64B with a one-pixel atom stride).  Measured on config 2: no faster (the
-  // converter warps, not the MMA count, bound the kernel: 0.89 / 0.56 / 0.66 ms vs 0.87 / 0.59 / 0.46 ms), so the
-  // separate hi / lo planes stay the default.
+  // Stacked B operand: one swizzled plane [pixel][hi of 8*np channels | lo of 8*np channels], N = 16*np*NL columns per
+  // MMA, 2 MMAs per (K-step, window-row group) instead of 3*np of N = 48 (validated by tools/probe_ts.cu: MN-major
+  // SWIZZLE_32B/64B with a one-pixel atom stride).  A TS MMA costs ~64 cycles up to N = 128 and ~110 at N = 192, so the
+  // stack pays where the kernel is MMA bound AND the stacked form keeps two channel planes per job (config 2 pair 1:
+  // 0.54 -> 0.46 ms).  With one plane (pair 0: converter bound, 0.667 vs 0.662 ms) or when stacking would halve the
+  // channels per job and double the jobs (pair 2: 0.63 vs 0.44 ms) the separate hi / lo planes stay.
+  // AEFFT_TS_STACK=0 / 1 forces the choice.
   p.stack = 0;
-  if (getenv("AEFFT_TS_STACK") && win.Nl <= 6) {
-    for (int np = dD > 8 ? 2 : 1; np >= 1 && !p.stack; np--) {
+  {
+    const char* force = getenv("AEFFT_TS_STACK");
+    int np_plain = dD > 8 ? 2 : 1;
+    while (np_plain > 1 && p.NR * np_plain * 48 > 512 - 2 * 64) np_plain--;
+    const bool allow = force ? force[0] != '0' : true;
+    for (int np = dD > 8 ? 2 : 1; allow && win.Nl <= 6 && np >= 1 && !p.stack; np--) {
+      if (!force && (np != np_plain || np != 2)) continue;
       const int ncol = 16 * np * win.Nl;
       const int copies = (p.NR == 1 && TS_NI * ncol + 2 * 64 <= 512) ? TS_NI : 1;
       const int jobs = 2 * ((dD + 8 * np - 1) / (8 * np));

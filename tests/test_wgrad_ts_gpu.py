@@ -58,10 +58,17 @@ SMALL = [(16, 3, 5, 5, 40, 48), (32, 16, 5, 5, 33, 60), (64, 32, 5, 5, 24, 20), 
          (16, 3, 5, 5, 37, 132)]
 
 
+@pytest.mark.parametrize("stack", ["auto", "0", "1"])
 @pytest.mark.parametrize("dims", SMALL)
-def test_gradient_block_vs_oracle(tc, dims):
+def test_gradient_block_vs_oracle(tc, dims, stack, monkeypatch):
+    """`stack` selects the B operand form of wgrad_ts (separate hi / lo planes or the stacked swizzled plane); the default
+    picks per layer shape, so both forms are forced here for every shape."""
     dM, dD, Nk, Nl, Nx, Ny = dims
     B = 3
+    if stack == "auto":
+        monkeypatch.delenv("AEFFT_TS_STACK", raising=False)
+    else:
+        monkeypatch.setenv("AEFFT_TS_STACK", stack)
     cs = make_case(31, *dims, B=B)
     got, names = gradient_block(tc, A.PRECISION_BF16X3, dims, B, cs["inp"], cs["out"], cs["hin"], cs["c"], cs["f"])
     assert "wgrad_ts" in names, f"streaming kernel not used: {names}"
