@@ -41,6 +41,7 @@ constexpr int TS_CHUNK = 64;  // pixels per TMEM A chunk = 4 MMA K-steps
 constexpr int TS_MAX_JOBS = 8;
 constexpr int TS_NSF = 2;     // fp32 S staging slots
 constexpr int TS_MAXRING = 24;
+constexpr int TS_MAXUB = 20;   // positions of the shared-memory U ring (asmem)
 
 struct TsJob {
   CUtensorMap u_map;   // U [B*dM][Nx][Ny], box {32, 1, dM}, 128-byte swizzle
@@ -67,6 +68,10 @@ struct WgradTsParams {
   int nacc;    // accumulators per job: NR (stack) or NR*np
   uint32_t u_slot_bytes, s_slot_bytes, s_src_bytes, sb_pitch;
   uint32_t off_u, off_s, off_sb, off_ub, ub_pitch;
+  // asmem: A operand read from SHARED memory (SS MMA) -- the bf16 U rows sit in a descending ring [part][8-px chunk]
+  // [position][channel][8 px], so the RS row-replicas of an M = 128 block are RS consecutive ring positions
+  int asmem, NUB, NUBT;      // ring positions, positions incl. the mirror of the first RS-1 (NUBT = NUB + RS - 1)
+  uint32_t a_lbo, a_part;    // bytes between 8-pixel chunks (K core matrices), bytes between the hi and lo parts
   long long* dbg;  // AEFFT_TS_DEBUG: [cta][warp][8] cycles (wait A, wait B, total, work, work 2)
 };
 
@@ -132,11 +137,11 @@ __device__ __forceinline__ void s_convert_row(const float* __restrict__ s0, cons
   }
 }
 
-template <bool DBG>
+template <bool DBG, bool ASMEM>
 __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_constant__ WgradTsParams p) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t u_full[TS_MAXRING], u_empty[TS_MAXRING], s_full[TS_NSF], s_empty[TS_NSF],
-      sb_full[TS_MAXRING], sb_empty[TS_MAXRING], a_full[8], a_empty[8], done_bar;
+      sb_full[TS_MAXRING], sb_empty[TS_MAXRING], a_full[8], a_empty[8], ub_full[TS_MAXUB], ub_empty[TS_MAXUB], done_bar;
   __shared__ uint32_t tmem_slot;
   __shared__ double usum[128], esum[16], esq;
 
@@ -156,6 +161,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
     for (int i = 0; i < TS_NSF; i++) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 2); }
     for (int i = 0; i < p.NSB; i++) { mbar_init(&sb_full[i], 2); mbar_init(&sb_empty[i], TS_NI); }
     for (int i = 0; i < p.NA; i++) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], TS_NI); }
+    if (ASMEM)
+      for (int i = 0; i < p.NUB; i++) { mbar_init(&ub_full[i], 8); mbar_init(&ub_empty[i], TS_NI); }
     mbar_init(&done_bar, TS_NI);
     fence_mbar_init();
   }
@@ -167,6 +174,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
     const uint32_t n16 = (uint32_t)((p.stack ? 1 : 2 * p.np) * p.NSB) * p.sb_pitch / 16;
     uint4* z = reinterpret_cast<uint4*>(sb_ring);
     for (uint32_t i = tid; i < n16; i += TS_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    if (ASMEM) {
+      // the U ring starts as zero rows: the RS-1 rows "before" the first band
+      uint4* zu = reinterpret_cast<uint4*>(smem + p.off_ub);
+      for (uint32_t i = tid; i < 2 * p.a_part / 16; i += TS_THREADS) zu[i] = make_uint4(0, 0, 0, 0);
+    }
   }
   fence_proxy_async();
   fence_before_sync();
@@ -257,6 +269,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
     int sb_row = 0;        // next S row of the current item this warp has not waited for
     int s0slot = 0;        // ring slot of the S row of the current K-row (window row offset 0)
     int cc4 = 0;           // chunk counter mod TS_NI
+    // asmem: ring position / phase of the U row of the current K-row (positions DEscend so that older rows follow in
+    // memory), rows seen so far, descriptor pieces in 16-byte units
+    int upos = p.NUB - 1;
+    uint32_t uph = 0;
+    const uint32_t ub_base16 = smem_u32(smem + p.off_ub) >> 4, a_lbo16 = p.a_lbo >> 4, a_part16 = p.a_part >> 4;
+    const uint32_t a_pos16 = (uint32_t)p.dM;  // one ring position = dM rows of 16 bytes
+    const uint64_t a_desc0 = make_desc(0, p.a_lbo, 128);
     for (int item = cta; item < n_items; item += cpj) {
       const int rem = item % items_per_frame;
       const int i0 = (rem % p.bands) * p.BR;
@@ -270,21 +289,29 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
           wait_t<DBG>(&sb_full[rw.slot], rw.phase, wA);
           rw.next();
         }
+        if (ASMEM) {
+          // the new U row (ring position upos) has been converted; every issuer waits for every row in order
+          wait_t<DBG>(&ub_full[upos], uph, wB);
+          fence_after_sync();
+        }
         for (int h = 0; h < CPR; h++, cc4 = (cc4 + 1) & (TS_NI - 1)) {
           const bool mine = !by_chunk || cc4 == q;
-          // every issuer waits for every A chunk in order and takes part in its release (count TS_NI), owner or not: a
-          // parity wait must neither skip phases nor be lapped (the ring length need not be a multiple of TS_NI)
-          wait_t<DBG>(&a_full[ra.slot], ra.phase, wB);
+          // TMEM A: every issuer waits for every A chunk in order and takes part in its release (count TS_NI), owner or
+          // not: a parity wait must neither skip phases nor be lapped (the ring length need not be a multiple of TS_NI)
+          if (!ASMEM) wait_t<DBG>(&a_full[ra.slot], ra.phase, wB);
           if (mine) {
             fence_after_sync();
             const long long t_m0 = DBG ? clock64() : 0;
-            const uint32_t a_base = tb + (uint32_t)(p.Acol0 + ra.slot * 64);
             if (elect_one()) {
               // one lane walks the (K-step, window-row group, plane) nest; operands advance by constant increments
               const uint32_t pl_step16 = (uint32_t)NSB * pitch16;
+              // A operand: TMEM chunk columns, or the shared-memory descriptor of rows upos .. upos+RS-1, 8-px chunk 8h
+              const uint32_t a_tm = tb + (uint32_t)(p.Acol0 + ra.slot * 64);
+              uint64_t a_sm = a_desc0 + (uint64_t)(ub_base16 + (uint32_t)(8 * h) * a_lbo16 + (uint32_t)upos * a_pos16);
 #pragma unroll 1
-              for (int ks = 0; ks < 4; ks++) {
-                const uint32_t a_hi = a_base + ks * 8, a_lo = a_hi + 32;
+              for (int ks = 0; ks < 4; ks++, a_sm += 2 * a_lbo16) {
+                const uint32_t a_hi = a_tm + ks * 8, a_lo = a_hi + 32;
+                const uint64_t as_hi = a_sm, as_lo = a_sm + (uint64_t)a_part16;
                 const uint32_t px16 = sb_base16 + (uint32_t)(h * TS_CHUNK + ks * 16) * pxb16;
                 uint32_t d = d_base;
                 int slot = s0slot, a = 0;
@@ -295,12 +322,22 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
                   for (int pl = 0; pl < np; pl++, d += Ncol, a++, lo32 += pl_step16) {
                     if (by_chunk || (a & (TS_NI - 1)) == q) {
                       const uint64_t b_hi = desc_const + (uint64_t)lo32, b_lo = b_hi + (uint64_t)lo_off16;
-                      mma_bf16_ts(d, a_hi, b_hi, idesc, true);
-                      if (stack) {
-                        if (three) mma_bf16_ts(d, a_lo, b_hi, idesc, true);  // (A_hi + A_lo) [S_hi | S_lo]
-                      } else if (three) {
-                        mma_bf16_ts(d, a_hi, b_lo, idesc, true);
-                        mma_bf16_ts(d, a_lo, b_hi, idesc, true);
+                      if (ASMEM) {
+                        mma_bf16(d, as_hi, b_hi, idesc, true);
+                        if (stack) {
+                          if (three) mma_bf16(d, as_lo, b_hi, idesc, true);  // (A_hi + A_lo) [S_hi | S_lo]
+                        } else if (three) {
+                          mma_bf16(d, as_hi, b_lo, idesc, true);
+                          mma_bf16(d, as_lo, b_hi, idesc, true);
+                        }
+                      } else {
+                        mma_bf16_ts(d, a_hi, b_hi, idesc, true);
+                        if (stack) {
+                          if (three) mma_bf16_ts(d, a_lo, b_hi, idesc, true);  // (A_hi + A_lo) [S_hi | S_lo]
+                        } else if (three) {
+                          mma_bf16_ts(d, a_hi, b_lo, idesc, true);
+                          mma_bf16_ts(d, a_lo, b_hi, idesc, true);
+                        }
                       }
                     }
                   }
@@ -312,8 +349,21 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
             __syncwarp();
             if (DBG) wC += clock64() - t_m0;
           }
-          if (elect_one()) commit(&a_empty[ra.slot]);
-          ra.next();
+          if (!ASMEM) {
+            if (elect_one()) commit(&a_empty[ra.slot]);
+            ra.next();
+          }
+        }
+        if (ASMEM) {
+          // the row RS-1 behind the newest one has been multiplied for the last time.  This also holds for the RS-1 virtual
+          // zero rows before the very first row: they live in the mirror of positions RS-2 .. 0, which the converters may
+          // only overwrite after this release (see the converter's wait).
+          {
+            int old = upos + RS - 1;
+            if (old >= p.NUB) old -= p.NUB;
+            if (elect_one()) commit(&ub_empty[old]);
+          }
+          if (--upos < 0) { upos = p.NUB - 1; uph ^= 1; }
         }
         if (elect_one()) commit(&sb_empty[s0slot]);
         if (++s0slot == NSB) s0slot = 0;
@@ -400,83 +450,150 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
     unsigned char* ub = smem + p.off_ub;
     const int units_per_m = PJ >> 3, n_units = CU * units_per_m;  // 8-pixel units of one image row
     const int upm_shift = PJ == 128 ? 4 : 3;                     // units_per_m is 16 or 8
-    Ring ru_ring(p.NU);            // fp32 ring position of the next image row to convert
-    Ring rc(NA);                   // A ring position of the current chunk (advanced for EVERY chunk, see below)
-    int parity = 0;                // (chunk index & 1) of the next chunk in program order
-    auto conv_barrier = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
-    for (int item = cta; item < n_items; item += cpj) {
-      const int rem = item % items_per_frame;
-      const int i0 = (rem % p.bands) * p.BR;
-      const int nrows = min(p.BR, p.Nx - i0);
-      const int n_krows = nrows + RS - 1;
-      for (int r = 0; r < n_krows; r++) {
-        // ---- stage A: convert image row r (if any) into ring slot r % RS
-        if (r < nrows) {
-          wait_t<DBG>(&u_full[ru_ring.slot], ru_ring.phase, wA);
+    if (ASMEM) {
+      // ---- A operand in shared memory: every image row is converted ONCE into ring position upos of the layout
+      // [hi|lo][8-px chunk][position][channel][8 px] (the SWIZZLE_NONE K-major core matrices of an M x 16 block whose M rows
+      // are `position * dM + channel`); positions descend with time, so the block of K-row r = positions upos .. upos+RS-1
+      // = rows r, r-1, .. r-RS+1: the row replicas are plain address arithmetic.  Positions < RS-1 are mirrored behind the
+      // ring so that a block never wraps.  Every band ends with RS-1 zero rows, which are also the rows "before" the next band.
+      Ring ru_ring2(p.NU);
+      int upos = p.NUB - 1;
+      uint32_t uph = 0;
+      const int kcs = PJ >> 3;                          // 8-pixel chunks per row
+      const int n_units = CU * kcs;                     // (chunk, channel) units of a row; channel varies fastest
+      const int cu_shift = 31 - __clz(CU);              // CU is a power of two (128 % dM == 0)
+      unsigned char* a_sm = smem + p.off_ub;
+      for (int item = cta; item < n_items; item += cpj) {
+        const int rem = item % items_per_frame;
+        const int i0 = (rem % p.bands) * p.BR;
+        const int nrows = min(p.BR, p.Nx - i0);
+        const int n_krows = nrows + RS - 1;
+        float us = 0.f;  // this thread's channel sum over the band (its channel is fixed: 256 % dM == 0)
+        for (int r = 0; r < n_krows; r++) {
+          const bool real = r < nrows;
+          if (real) wait_t<DBG>(&u_full[ru_ring2.slot], ru_ring2.phase, wA);
+          // Release of this position by the issuers.  Positions >= RS-1 are free on the first lap (parity trick); positions
+          // < RS-1 are NOT: their mirror holds the virtual zero rows the first RS-1 K-rows read, and the issuers release
+          // them like real rows -- so these positions have seen one more phase and wait with the un-flipped parity.
+          const bool mirror = upos < RS - 1;
+          wait_t<DBG>(&ub_empty[upos], mirror ? uph : uph ^ 1, wB);
           const long long t_c0 = DBG ? clock64() : 0;
-          const unsigned char* urow = u_ring + (size_t)ru_ring.slot * p.u_slot_bytes;
-          unsigned char* dst_hi = ub + (size_t)(r & (RS - 1)) * 2 * ub_part;
+          const unsigned char* urow = u_ring + (size_t)ru_ring2.slot * p.u_slot_bytes;
           for (int unit = t256; unit < n_units; unit += 256) {
-            const int mm = unit >> upm_shift, u8 = unit & (units_per_m - 1);
-            const int px0 = u8 * 8, sub = px0 >> 5, g0 = (px0 & 31) >> 2;
-            const unsigned char* src = urow + (size_t)sub * CU * 128 + (size_t)mm * 128;
-            float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
-            if (px0 < TJ) q0 = *reinterpret_cast<const float4*>(src + ((g0 ^ (mm & 7)) << 4));
-            if (px0 + 4 < TJ) q1 = *reinterpret_cast<const float4*>(src + (((g0 + 1) ^ (mm & 7)) << 4));
-            if (J.want_usum) {
-              // 16 (PJ = 128) or 8 (PJ = 64) consecutive lanes share a channel: reduce them, one atomic per channel and row
-              float sv = (q0.x + q0.y) + (q0.z + q0.w) + (q1.x + q1.y) + (q1.z + q1.w);
-              for (int o = units_per_m >> 1; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
-              if ((lane & (units_per_m - 1)) == 0) atomicAdd(&usum[mm], (double)sv);
+            const int kc = unit >> cu_shift, mm = unit & (CU - 1);
+            uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+            if (real) {
+              const int px0 = kc * 8, sub = px0 >> 5, g0 = (px0 & 31) >> 2;
+              const unsigned char* src = urow + (size_t)sub * CU * 128 + (size_t)mm * 128;
+              float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+              if (px0 < TJ) q0 = *reinterpret_cast<const float4*>(src + ((g0 ^ (mm & 7)) << 4));
+              if (px0 + 4 < TJ) q1 = *reinterpret_cast<const float4*>(src + (((g0 + 1) ^ (mm & 7)) << 4));
+              us += (q0.x + q0.y) + (q0.z + q0.w) + (q1.x + q1.y) + (q1.z + q1.w);
+              split2(q0.x, q0.y, hi[0], lo[0]);
+              split2(q0.z, q0.w, hi[1], lo[1]);
+              split2(q1.x, q1.y, hi[2], lo[2]);
+              split2(q1.z, q1.w, hi[3], lo[3]);
             }
-            uint32_t hi[4], lo[4];
-            split2(q0.x, q0.y, hi[0], lo[0]);
-            split2(q0.z, q0.w, hi[1], lo[1]);
-            split2(q1.x, q1.y, hi[2], lo[2]);
-            split2(q1.z, q1.w, hi[3], lo[3]);
-            unsigned char* d = dst_hi + (size_t)mm * ub_pitch + (size_t)u8 * 16;
+            unsigned char* d = a_sm + (size_t)kc * p.a_lbo + ((size_t)upos * CU + mm) * 16;
             *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(d + ub_part) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(d + p.a_part) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (mirror) {
+              unsigned char* d2 = d + (size_t)p.NUB * CU * 16;
+              *reinterpret_cast<uint4*>(d2) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(d2 + p.a_part) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
           }
           if (DBG) wC += clock64() - t_c0;
-        }
-        conv_barrier();  // row r is in the bf16 ring; the fp32 slot is free again
-        if (r < nrows) {
-          if (lane == 0) mbar_arrive(&u_empty[ru_ring.slot]);
-          ru_ring.next();
-        }
-        // ---- stage B: TMEM lane (rho, m) <- row r - rho
-        const int rrow = r - rho;
-        const bool valid = rrow >= 0 && rrow < nrows;
-        const unsigned char* lrow = ub + (size_t)(rrow & (RS - 1)) * 2 * ub_part + (size_t)m * ub_pitch;
-        for (int h = 0; h < p.CPR; h++, parity ^= 1, rc.next()) {
-          // Every converter warp waits for the release of EVERY chunk slot in order, also for the chunks the other half
-          // writes: with an odd ring length both halves alternate on the same barriers, and a parity wait that skips a
-          // phase can pass one lap early (the slot would be overwritten while the MMAs still read it).
-          wait_t<DBG>(&a_empty[rc.slot], rc.phase ^ 1, wB);
-          if (parity != half) continue;
-          const int ca = rc.slot;
-          const long long t_c1 = DBG ? clock64() : 0;
-          fence_after_sync();
-#pragma unroll
-          for (int part = 0; part < 2; part++) {
-            uint32_t v[32];
-#pragma unroll
-            for (int g = 0; g < 8; g++) {
-              uint4 q = make_uint4(0u, 0u, 0u, 0u);
-              if (valid) q = *reinterpret_cast<const uint4*>(lrow + (size_t)part * ub_part + (size_t)h * 128 + g * 16);
-              v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
-            }
-            tmem_st16(t_lane + (uint32_t)(ca * 64 + part * 32), v);
-            tmem_st16(t_lane + (uint32_t)(ca * 64 + part * 32 + 16), v + 16);
-          }
-          tmem_wait_st();
-          fence_before_sync();
+          fence_proxy_async();  // generic-proxy writes -> the MMAs' async-proxy reads
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[ca]);
-          if (DBG) wD += clock64() - t_c1;
+          if (lane == 0) {
+            mbar_arrive(&ub_full[upos]);
+            if (real) mbar_arrive(&u_empty[ru_ring2.slot]);
+          }
+          if (real) ru_ring2.next();
+          if (--upos < 0) { upos = p.NUB - 1; uph ^= 1; }
         }
-        conv_barrier();  // every lane has read its rows before stage A overwrites the oldest slot
+        if (J.want_usum && us != 0.f) atomicAdd(&usum[t256 & (CU - 1)], (double)us);
+      }
+    } else {
+      Ring ru_ring(p.NU);            // fp32 ring position of the next image row to convert
+      Ring rc(NA);                   // A ring position of the current chunk (advanced for EVERY chunk, see below)
+      int parity = 0;                // (chunk index & 1) of the next chunk in program order
+      auto conv_barrier = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+      for (int item = cta; item < n_items; item += cpj) {
+        const int rem = item % items_per_frame;
+        const int i0 = (rem % p.bands) * p.BR;
+        const int nrows = min(p.BR, p.Nx - i0);
+        const int n_krows = nrows + RS - 1;
+        for (int r = 0; r < n_krows; r++) {
+          // ---- stage A: convert image row r (if any) into ring slot r % RS
+          if (r < nrows) {
+            wait_t<DBG>(&u_full[ru_ring.slot], ru_ring.phase, wA);
+            const long long t_c0 = DBG ? clock64() : 0;
+            const unsigned char* urow = u_ring + (size_t)ru_ring.slot * p.u_slot_bytes;
+            unsigned char* dst_hi = ub + (size_t)(r & (RS - 1)) * 2 * ub_part;
+            for (int unit = t256; unit < n_units; unit += 256) {
+              const int mm = unit >> upm_shift, u8 = unit & (units_per_m - 1);
+              const int px0 = u8 * 8, sub = px0 >> 5, g0 = (px0 & 31) >> 2;
+              const unsigned char* src = urow + (size_t)sub * CU * 128 + (size_t)mm * 128;
+              float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+              if (px0 < TJ) q0 = *reinterpret_cast<const float4*>(src + ((g0 ^ (mm & 7)) << 4));
+              if (px0 + 4 < TJ) q1 = *reinterpret_cast<const float4*>(src + (((g0 + 1) ^ (mm & 7)) << 4));
+              if (J.want_usum) {
+                // 16 (PJ = 128) or 8 (PJ = 64) consecutive lanes share a channel: reduce them, one atomic per channel and row
+                float sv = (q0.x + q0.y) + (q0.z + q0.w) + (q1.x + q1.y) + (q1.z + q1.w);
+                for (int o = units_per_m >> 1; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                if ((lane & (units_per_m - 1)) == 0) atomicAdd(&usum[mm], (double)sv);
+              }
+              uint32_t hi[4], lo[4];
+              split2(q0.x, q0.y, hi[0], lo[0]);
+              split2(q0.z, q0.w, hi[1], lo[1]);
+              split2(q1.x, q1.y, hi[2], lo[2]);
+              split2(q1.z, q1.w, hi[3], lo[3]);
+              unsigned char* d = dst_hi + (size_t)mm * ub_pitch + (size_t)u8 * 16;
+              *reinterpret_cast<uint4*>(d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(d + ub_part) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            if (DBG) wC += clock64() - t_c0;
+          }
+          conv_barrier();  // row r is in the bf16 ring; the fp32 slot is free again
+          if (r < nrows) {
+            if (lane == 0) mbar_arrive(&u_empty[ru_ring.slot]);
+            ru_ring.next();
+          }
+          // ---- stage B: TMEM lane (rho, m) <- row r - rho
+          const int rrow = r - rho;
+          const bool valid = rrow >= 0 && rrow < nrows;
+          const unsigned char* lrow = ub + (size_t)(rrow & (RS - 1)) * 2 * ub_part + (size_t)m * ub_pitch;
+          for (int h = 0; h < p.CPR; h++, parity ^= 1, rc.next()) {
+            // Every converter warp waits for the release of EVERY chunk slot in order, also for the chunks the other half
+            // writes: with an odd ring length both halves alternate on the same barriers, and a parity wait that skips a
+            // phase can pass one lap early (the slot would be overwritten while the MMAs still read it).
+            wait_t<DBG>(&a_empty[rc.slot], rc.phase ^ 1, wB);
+            if (parity != half) continue;
+            const int ca = rc.slot;
+            const long long t_c1 = DBG ? clock64() : 0;
+            fence_after_sync();
+  #pragma unroll
+            for (int part = 0; part < 2; part++) {
+              uint32_t v[32];
+  #pragma unroll
+              for (int g = 0; g < 8; g++) {
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (valid) q = *reinterpret_cast<const uint4*>(lrow + (size_t)part * ub_part + (size_t)h * 128 + g * 16);
+                v[4 * g] = q.x; v[4 * g + 1] = q.y; v[4 * g + 2] = q.z; v[4 * g + 3] = q.w;
+              }
+              tmem_st16(t_lane + (uint32_t)(ca * 64 + part * 32), v);
+              tmem_st16(t_lane + (uint32_t)(ca * 64 + part * 32 + 16), v + 16);
+            }
+            tmem_wait_st();
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[ca]);
+            if (DBG) wD += clock64() - t_c1;
+          }
+          conv_barrier();  // every lane has read its rows before stage A overwrites the oldest slot
+        }
       }
     }
     // ============================================================ epilogue (warps 4-7)
@@ -626,34 +743,69 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   const int jobs_per_grad = (dD + 8 * p.np - 1) / (8 * p.np);
   p.n_jobs = 2 * jobs_per_grad;
   if (p.n_jobs > TS_MAX_JOBS) return AEFFT_ERR_UNSUPPORTED;
-  // strip geometry: pitch 64 when one 64-wide strip covers the row, else 128
+  // A operand from shared memory (asmem, default) or from tensor memory (AEFFT_TS_ASMEM=0, and the fallback when the
+  // shared-memory ring does not fit).  Strip geometry: pitch 64 when one 64-wide strip covers the row, else 128; the
+  // shared-memory A ring is large ((2 RS + slack) rows of hi + lo), so 64-pixel strips are also taken when 128 does not fit.
   const int halo = win.Nl - 1;
-  p.PJ = (Ny + halo <= 64) ? 64 : 128;
-  p.TJ = (p.PJ - halo) & ~3;
-  p.CPR = p.PJ / TS_CHUNK;
-  p.strips = (Ny + p.TJ - 1) / p.TJ;
   const int Rmax = (p.NR - 1) * p.RS;
   p.by_chunk = (p.NR == 1 && TS_NI * p.nacc * p.Ncol + 2 * 64 <= 512) ? 1 : 0;
   p.Acol0 = (p.by_chunk ? TS_NI : 1) * p.nacc * p.Ncol;
   p.NA = (512 - p.Acol0) / 64;
   if (p.NA > 4) p.NA = 4;
   p.NSB = Rmax + 3;
-  p.sb_pitch = p.stack ? (((uint32_t)(p.PJ + 8) * 32 * p.np + 1023) & ~1023u) : (uint32_t)(p.PJ + 8) * 16;
-  p.u_slot_bytes = (uint32_t)dM * p.PJ * 4;
-  p.s_src_bytes = (uint32_t)(8 * p.np) * (p.PJ + 4) * 4;
-  p.s_src_bytes = (p.s_src_bytes + 127) & ~127u;
-  p.s_slot_bytes = 2 * p.s_src_bytes;
-  const size_t sb_bytes = (size_t)(p.stack ? 1 : 2 * p.np) * p.NSB * p.sb_pitch;
-  const size_t s_bytes = (size_t)TS_NSF * p.s_slot_bytes;
+  if (p.NSB > TS_MAXRING) return AEFFT_ERR_UNSUPPORTED;
   const size_t budget = 225 * 1024 - 1024;
-  // U side: a short fp32 TMA ring (each image row is converted once, straight after it lands) + the bf16 hi / lo ring of
-  // the RS most recent rows the TMEM lanes replicate from; pitch + 16 B so that consecutive channels shift one bank group
-  p.ub_pitch = (uint32_t)p.PJ * 2 + 16;
-  const size_t ub_bytes = (size_t)p.RS * 2 * dM * p.ub_pitch;
-  p.NU = 4;
-  while (p.NU > 2 && (size_t)p.NU * p.u_slot_bytes + ub_bytes + s_bytes + sb_bytes + 4096 > budget) p.NU--;
-  if ((size_t)p.NU * p.u_slot_bytes + ub_bytes + s_bytes + sb_bytes + 4096 > budget || p.NSB > TS_MAXRING)
-    return AEFFT_ERR_UNSUPPORTED;
+  size_t sb_bytes = 0, s_bytes = 0, ub_bytes = 0;
+  p.asmem = -1;
+  // Default: shared-memory A when one window-row group covers the window (NR == 1, e.g. dM = 16): there the kernel is
+  // bound by the converter warps and the TMEM replication stage disappears (config 2 pair 0: 0.665 -> 0.60 ms).  With
+  // several groups the kernel is MMA bound and an SS MMA (4 KB of A per MMA over the 128 B/clk operand path, ~43 cycles)
+  // is no faster than the TS MMA (~50-64 cycles), while the larger ring forces 64-pixel strips (pair 1: 0.71 vs 0.47 ms).
+  const char* as_env = getenv("AEFFT_TS_ASMEM");
+  const bool want_asmem = as_env ? as_env[0] != '0' : p.NR == 1;
+  const bool narrow_ok = as_env && as_env[0] == '2';  // also try 64-pixel strips for the shared-memory ring (experiments)
+  for (int as = want_asmem ? 1 : 0; as >= 0 && p.asmem < 0; as--) {
+    const int PJ_nat = (Ny + halo <= 64) ? 64 : 128;
+    for (int PJ = PJ_nat; PJ >= 64 && p.asmem < 0; PJ -= 64) {
+      if (PJ != PJ_nat && !(as && narrow_ok)) break;  // keep the natural pitch
+      p.PJ = PJ;
+      p.TJ = (p.PJ - halo) & ~3;
+      p.CPR = p.PJ / TS_CHUNK;
+      p.strips = (Ny + p.TJ - 1) / p.TJ;
+      p.sb_pitch = p.stack ? (((uint32_t)(p.PJ + 8) * 32 * p.np + 1023) & ~1023u) : (uint32_t)(p.PJ + 8) * 16;
+      p.u_slot_bytes = (uint32_t)dM * p.PJ * 4;
+      p.s_src_bytes = (uint32_t)(8 * p.np) * (p.PJ + 4) * 4;
+      p.s_src_bytes = (p.s_src_bytes + 127) & ~127u;
+      p.s_slot_bytes = 2 * p.s_src_bytes;
+      sb_bytes = (size_t)(p.stack ? 1 : 2 * p.np) * p.NSB * p.sb_pitch;
+      s_bytes = (size_t)TS_NSF * p.s_slot_bytes;
+      const size_t fixed = s_bytes + sb_bytes + 4096;
+      if (as) {
+        // ring of NUB >= RS + 1 positions + the mirror of the first RS - 1; prefer two rows of slack and a 3-deep fp32 ring
+        for (int extra = 2; extra >= 1 && p.asmem < 0; extra--)
+          for (int NU = 3; NU >= 2 && p.asmem < 0; NU--) {
+            const int NUB = p.RS + extra, NUBT = NUB + p.RS - 1;
+            const size_t part = (size_t)(p.PJ / 8) * NUBT * dM * 16;
+            if (NUB <= TS_MAXUB && (size_t)NU * p.u_slot_bytes + 2 * part + fixed <= budget) {
+              p.asmem = 1; p.NUB = NUB; p.NUBT = NUBT; p.NU = NU;
+              p.a_lbo = (uint32_t)NUBT * dM * 16; p.a_part = (uint32_t)part;
+              ub_bytes = 2 * part;
+            }
+          }
+      } else {
+        // TMEM A: a short fp32 TMA ring + the bf16 hi / lo ring of the RS most recent rows the TMEM lanes replicate from;
+        // pitch + 16 B so that consecutive channels shift one bank group
+        p.ub_pitch = (uint32_t)p.PJ * 2 + 16;
+        ub_bytes = (size_t)p.RS * 2 * dM * p.ub_pitch;
+        for (int NU = 4; NU >= 2 && p.asmem < 0; NU--)
+          if ((size_t)NU * p.u_slot_bytes + ub_bytes + fixed <= budget) {
+            p.asmem = 0; p.NU = NU; p.NUB = 0; p.NUBT = 0; p.a_lbo = 0; p.a_part = 0;
+          }
+      }
+    }
+  }
+  if (p.asmem < 0) return AEFFT_ERR_UNSUPPORTED;
+  if (p.asmem) p.ub_pitch = 0;
   p.off_u = 0;
   p.off_s = (uint32_t)(((size_t)p.NU * p.u_slot_bytes + 1023) & ~(size_t)1023);
   p.off_sb = (uint32_t)((p.off_s + s_bytes + 1023) & ~(size_t)1023);
@@ -713,15 +865,23 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   }
   static size_t attr = 0;
   if (smem > attr) {
-    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
   {
     const double px = (double)B * Nx * Ny;
     ProfScope prof(ctx, "wgrad_ts", 2.0 * 2.0 * px * dM * dD * T, 4.0 * px * (3.0 * dD + 2.0 * dM));
-    if (debug) wgrad_ts_kernel<true><<<dim3(cpj, p.n_jobs), TS_THREADS, smem, ctx->stream>>>(p);
-    else wgrad_ts_kernel<false><<<dim3(cpj, p.n_jobs), TS_THREADS, smem, ctx->stream>>>(p);
+    const dim3 grid(cpj, p.n_jobs);
+    if (p.asmem) {
+      if (debug) wgrad_ts_kernel<true, true><<<grid, TS_THREADS, smem, ctx->stream>>>(p);
+      else wgrad_ts_kernel<false, true><<<grid, TS_THREADS, smem, ctx->stream>>>(p);
+    } else {
+      if (debug) wgrad_ts_kernel<true, false><<<grid, TS_THREADS, smem, ctx->stream>>>(p);
+      else wgrad_ts_kernel<false, false><<<grid, TS_THREADS, smem, ctx->stream>>>(p);
+    }
   }
   wgrad_ts_reduce_kernel<<<(unsigned)((p.n_main + 1 + 255) / 256), 256, 0, ctx->stream>>>(part, cpj, p.n_tot, p.n_main, p.n_jobs,
                                                                                           2 * nC, dM, dD, G, GB, GP, SQ);
@@ -743,8 +903,8 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
         for (int q = 0; q < 5; q++) acc[r][q] += (double)h[((size_t)c * 16 + w) * 8 + q];
         cnt[r]++;
       }
-    fprintf(stderr, "[wgrad_ts] dM=%d dD=%d %dx%d B=%lld PJ=%d RS=%d NR=%d np=%d jobs=%d cpj=%d bands=%d BR=%d NU=%d NSB=%d NA=%d smem=%zu\n",
-            dM, dD, Nx, Ny, (long long)B, p.PJ, p.RS, p.NR, p.np, p.n_jobs, cpj, p.bands, p.BR, p.NU, p.NSB, p.NA, smem);
+    fprintf(stderr, "[wgrad_ts] dM=%d dD=%d %dx%d B=%lld asmem=%d PJ=%d RS=%d NR=%d np=%d jobs=%d cpj=%d bands=%d BR=%d NU=%d NSB=%d NA=%d smem=%zu\n",
+            dM, dD, Nx, Ny, (long long)B, p.asmem, p.PJ, p.RS, p.NR, p.np, p.n_jobs, cpj, p.bands, p.BR, p.NU, p.NSB, p.NA, smem);
     for (int r = 0; r < 4; r++)
       fprintf(stderr, "[wgrad_ts]   %-30s waitA %9.0f  waitB %9.0f  total %9.0f  work %9.0f + %9.0f cycles\n", role[r],
               acc[r][0] / cnt[r], acc[r][1] / cnt[r], acc[r][2] / cnt[r], acc[r][3] / cnt[r], acc[r][4] / cnt[r]);

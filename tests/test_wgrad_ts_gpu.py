@@ -58,13 +58,19 @@ SMALL = [(16, 3, 5, 5, 40, 48), (32, 16, 5, 5, 33, 60), (64, 32, 5, 5, 24, 20), 
          (16, 3, 5, 5, 37, 132)]
 
 
+@pytest.mark.parametrize("asmem", ["auto", "0", "2"])
 @pytest.mark.parametrize("stack", ["auto", "0", "1"])
 @pytest.mark.parametrize("dims", SMALL)
-def test_gradient_block_vs_oracle(tc, dims, stack, monkeypatch):
-    """`stack` selects the B operand form of wgrad_ts (separate hi / lo planes or the stacked swizzled plane); the default
-    picks per layer shape, so both forms are forced here for every shape."""
+def test_gradient_block_vs_oracle(tc, dims, stack, asmem, monkeypatch):
+    """`stack` selects the B operand form of wgrad_ts (separate hi / lo planes or the stacked swizzled plane), `asmem` the
+    home of the A operand (tensor memory, or the shared-memory row ring; "2" also allows its 64-pixel strips); the
+    defaults pick per layer shape, so every form is forced here for every shape."""
     dM, dD, Nk, Nl, Nx, Ny = dims
     B = 3
+    if asmem == "auto":
+        monkeypatch.delenv("AEFFT_TS_ASMEM", raising=False)
+    else:
+        monkeypatch.setenv("AEFFT_TS_ASMEM", asmem)
     if stack == "auto":
         monkeypatch.delenv("AEFFT_TS_STACK", raising=False)
     else:
@@ -96,8 +102,13 @@ def test_gradient_block_vs_oracle(tc, dims, stack, monkeypatch):
 C2_SHAPES = [((16, 3, 5, 5, 320, 240), 4), ((32, 16, 5, 5, 160, 120), 6), ((64, 32, 5, 5, 80, 60), 16)]
 
 
-@pytest.mark.parametrize("dims,B", C2_SHAPES)
-def test_gradient_block_vs_fp32_kernels_at_config2_shapes(tc, dims, B):
+@pytest.mark.parametrize("asmem", ["auto", "0", "2"])
+@pytest.mark.parametrize("dims,B", C2_SHAPES + [((32, 16, 5, 5, 160, 60), 2)])
+def test_gradient_block_vs_fp32_kernels_at_config2_shapes(tc, dims, B, asmem, monkeypatch):
+    if asmem == "auto":
+        monkeypatch.delenv("AEFFT_TS_ASMEM", raising=False)
+    else:
+        monkeypatch.setenv("AEFFT_TS_ASMEM", asmem)
     inp, out, hin, c, f = random_case(32, dims, B)
     ref, names32 = gradient_block(tc, A.PRECISION_FP32, dims, B, inp, out, hin, c, f)
     assert "wgrad_ts" not in names32
