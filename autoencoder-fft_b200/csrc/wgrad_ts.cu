@@ -718,6 +718,7 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   // channels per job and double the jobs (pair 2: 0.63 vs 0.44 ms) the separate hi / lo planes stay.
   // AEFFT_TS_STACK=0 / 1 forces the choice.
   p.stack = 0;
+  bool stack_needs_asmem = false;
   {
     const char* force = getenv("AEFFT_TS_STACK");
     int np_plain = dD > 8 ? 2 : 1;
@@ -730,6 +731,22 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
       const int jobs = 2 * ((dD + 8 * np - 1) / (8 * np));
       if (copies * p.NR * ncol + 2 * 64 <= 512 && jobs <= TS_MAX_JOBS) {
         p.stack = 1; p.np = np; p.Ncol = ncol; p.nacc = p.NR;
+      }
+    }
+    // With the A operand in shared memory the tensor memory holds accumulators only, so the two-plane stack also fits
+    // when NR * ncol <= 512 (config 2 pair 2: 3 groups x 160 columns; 24 N160 MMAs per K-row instead of 72 N48).
+    const char* as_env = getenv("AEFFT_TS_ASMEM");
+    if (!p.stack && allow && win.Nl <= 6 && np_plain == 2 && !(as_env && as_env[0] == '0')) {
+      const int ncol = 32 * win.Nl, jobs = 2 * ((dD + 15) / 16);
+      const int halo = win.Nl - 1, PJ = (Ny + halo <= 64) ? 64 : 128;
+      // shared memory of that configuration at the natural strip pitch (same formulas as the layout search below)
+      const size_t sbp = ((size_t)(PJ + 8) * 32 * 2 + 1023) & ~(size_t)1023;
+      const size_t need = (size_t)2 * dM * PJ * 4 + 2 * ((size_t)(PJ / 8) * (2 * p.RS) * dM * 16) +
+                          (size_t)TS_NSF * 2 * (((size_t)16 * (PJ + 4) * 4 + 127) & ~(size_t)127) +
+                          (size_t)((p.NR - 1) * p.RS + 3) * sbp + 4096;
+      if (p.NR * ncol <= 512 && jobs <= TS_MAX_JOBS && need <= 225 * 1024 - 1024) {
+        p.stack = 1; p.np = 2; p.Ncol = ncol; p.nacc = p.NR;
+        stack_needs_asmem = true;
       }
     }
   }
@@ -750,8 +767,9 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   const int Rmax = (p.NR - 1) * p.RS;
   p.by_chunk = (p.NR == 1 && TS_NI * p.nacc * p.Ncol + 2 * 64 <= 512) ? 1 : 0;
   p.Acol0 = (p.by_chunk ? TS_NI : 1) * p.nacc * p.Ncol;
-  p.NA = (512 - p.Acol0) / 64;
+  p.NA = (512 - p.Acol0) / 64;  // TMEM A chunks (unused with the shared-memory A form)
   if (p.NA > 4) p.NA = 4;
+  if (p.NA < 0) p.NA = 0;
   p.NSB = Rmax + 3;
   if (p.NSB > TS_MAXRING) return AEFFT_ERR_UNSUPPORTED;
   const size_t budget = 225 * 1024 - 1024;
@@ -762,7 +780,7 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   // several groups the kernel is MMA bound and an SS MMA (4 KB of A per MMA over the 128 B/clk operand path, ~43 cycles)
   // is no faster than the TS MMA (~50-64 cycles), while the larger ring forces 64-pixel strips (pair 1: 0.71 vs 0.47 ms).
   const char* as_env = getenv("AEFFT_TS_ASMEM");
-  const bool want_asmem = as_env ? as_env[0] != '0' : p.NR == 1;
+  const bool want_asmem = stack_needs_asmem || (as_env ? as_env[0] != '0' : p.NR == 1);
   const bool narrow_ok = as_env && as_env[0] == '2';  // also try 64-pixel strips for the shared-memory ring (experiments)
   for (int as = want_asmem ? 1 : 0; as >= 0 && p.asmem < 0; as--) {
     const int PJ_nat = (Ny + halo <= 64) ? 64 : 128;
@@ -804,7 +822,7 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
       }
     }
   }
-  if (p.asmem < 0) return AEFFT_ERR_UNSUPPORTED;
+  if (p.asmem < 0 || (stack_needs_asmem && p.asmem != 1)) return AEFFT_ERR_UNSUPPORTED;
   if (p.asmem) p.ub_pitch = 0;
   p.off_u = 0;
   p.off_s = (uint32_t)(((size_t)p.NU * p.u_slot_bytes + 1023) & ~(size_t)1023);
