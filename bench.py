@@ -128,6 +128,20 @@ def cpu_reference_sample(w, budget_s, repeats=1):
     return dict(value=1.0 / per_frame, seconds=t, sample=desc, kind=kind, cores=1, q=q)
 
 
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture of
+    this command (profiles/traffic.json, written from the .ncu-rep next to the summary it cites); None when no capture of
+    that kernel is committed.  Compare with roofline.algorithmic_bytes_per_launch: traffic well above it = wasted re-reads."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tab = json.load(fh).get(workload, {})
+    except (OSError, ValueError):
+        return None
+    key = "wgrad_ts" if kernel.startswith("wgrad_ts") else "conv_rs" if kernel.endswith("_rs") else kernel
+    rec = tab.get(key)
+    return float(rec["dram_bytes_per_launch"]) if rec else None
+
+
 def ref_cuda_sample():
     """The reference's own CUDA kernels on this box (reported baseline): tools/ref_cuda_sample.py in a subprocess, so
     that a fault inside the reference cannot take the bench down.  None-like dict on failure."""
@@ -584,7 +598,7 @@ def run_ours(args, w, rank, world, local_rank):
                 roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"]}
             if roof["bound"] == "tensor":
                 roof.update({"mma_passes": passes, "pipe_frac": roof["frac"] * passes})
-            roof.update({"traffic": None, "kernel": top["name"], "avg_launch_ms": per_ms, "share_of_step": top["ms"] / ms_total,
+            roof.update({"traffic": ncu_traffic(args.workload, top["name"]), "kernel": top["name"], "avg_launch_ms": per_ms, "share_of_step": top["ms"] / ms_total,
                          "peak_source": pk["source"] + (", sustained bf16" if roof["bound"] == "tensor" else ""),
                          "algorithmic_flops_per_launch": fl_l, "algorithmic_bytes_per_launch": by_l})
         cfg = config_dict(w, args, world)
