@@ -19,6 +19,11 @@
 //     STREAM through rings (TMA -> fp32 rows -> converters -> TMEM / bf16 planes), so the halo is paid once per band.
 //   * fp32 parity: bf16 hi/lo split of both operands, products hi*hi + hi*lo + lo*hi (BF16X3), fp32 TMEM accumulators
 //     kept for ALL items of a CTA; per-CTA partials are reduced in fixed order (deterministic).
+//   * Two homes for A, chosen per layer shape (template parameter ASMEM): tensor memory as above, or a DESCENDING
+//     shared-memory ring of converted rows [hi|lo][8-px chunk][position][channel][8 px] whose RS consecutive positions are
+//     the M = 128 block of an SS MMA (row replicas = descriptor arithmetic; no replication stage, no TMEM A ring).  Two
+//     forms of B: separate hi / lo planes (3 MMAs of N = 48 per plane) or one stacked swizzled plane [S_hi | S_lo]
+//     (2 MMAs of N = 16 * np * NL).  launch_wgrad_ts documents which shape takes which and the measurements behind it.
 // Roles (512 threads): warp 0 TMA producer, warps 2-3 S converters (+ sum e, e^2), warps 4-11 U converters (+ sum U),
 // warps 12-15 MMA issuers, warps 4-7 epilogue.
 #include <cstdio>
