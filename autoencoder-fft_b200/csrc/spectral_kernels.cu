@@ -25,37 +25,47 @@ __device__ __forceinline__ void cfma_conj(float2& acc, float2 a, float2 b) {  //
 // ------------------------------------------------------------------------------------------------ spectral pooling
 // resize (:87-157): scale>1 crops the half spectrum around zero frequency, scale<0 embeds it into a zeroed larger
 // one; the Nyquist column/row of the source lands on the Nyquist of the target; no amplitude rescale.
-__global__ void spec_resize_kernel(const float2* __restrict__ in, float2* __restrict__ out, long long planes, int Nx,
-                                   int Ny, int Nxs, int Nys) {
+// One warp-pair (64 threads) per target row, 4 rows per CTA; the row / plane decomposition is done once per row (no
+// per-element 64-bit division) and every thread keeps several independent 8-byte loads in flight.
+constexpr int RSZ_ROWS = 4;
+__global__ void __launch_bounds__(64 * RSZ_ROWS) spec_resize_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                                                                    long long rows, int Nx, int Ny, int Nxs, int Nys) {
   const int Nyr = Ny / 2 + 1, Nyrs = Nys / 2 + 1;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= planes * Nxs * Nyrs) return;
-  const int j = idx % Nyrs;
-  const int i = (idx / Nyrs) % Nxs;
-  const long long d = idx / ((long long)Nyrs * Nxs);
-  const float2* src = in + d * (long long)Nx * Nyr;
-  float2 v = make_float2(0.f, 0.f);
+  const long long row = (long long)blockIdx.x * RSZ_ROWS + (threadIdx.x >> 6);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 63;
+  const long long d = row / Nxs;
+  const int i = (int)(row - d * Nxs);
+  float2* dst = out + row * Nyrs;
+  int si = -1;
   if (Nxs <= Nx) {
-    const int si = i < Nxs / 2 ? i : (i == Nxs / 2 ? Nx / 2 : i + Nx - Nxs);
-    const int sj = j < Nyrs - 1 ? j : Nyr - 1;
-    v = src[(long long)si * Nyr + sj];
+    si = i < Nxs / 2 ? i : (i == Nxs / 2 ? Nx / 2 : i + Nx - Nxs);
   } else {
-    int si = -1;
     if (i < Nx / 2) si = i;
     else if (i > Nxs - Nx / 2) si = i - Nxs + Nx;
     else if (i == Nxs / 2) si = Nx / 2;
-    int sj = -1;
-    if (j == Nyrs - 1) sj = Nyr - 1;      // (the reference tests j<Nyr-1 first; j==Nyrs-1 never satisfies it when upsampling)
-    else if (j < Nyr - 1) sj = j;
-    if (si >= 0 && sj >= 0) v = src[(long long)si * Nyr + sj];
   }
-  out[idx] = v;
+  if (si < 0) {  // a row of the zero band of an embedded spectrum
+    for (int j = lane; j < Nyrs; j += 64) dst[j] = make_float2(0.f, 0.f);
+    return;
+  }
+  const float2* src = in + (d * Nx + si) * (long long)Nyr;
+  // columns: cropping keeps j < Nyrs-1 and puts the source Nyquist column on the target's; embedding copies j < Nyr-1,
+  // zero-fills, and puts the source Nyquist on the target's (the reference tests j<Nyr-1 first; j==Nyrs-1 never
+  // satisfies it when upsampling)
+  const int ncopy = (Nxs <= Nx ? Nyrs : Nyr) - 1;
+#pragma unroll 4
+  for (int j = lane; j < Nyrs - 1; j += 64) dst[j] = j < ncopy ? __ldg(src + j) : make_float2(0.f, 0.f);
+  if (lane == 0) dst[Nyrs - 1] = __ldg(src + Nyr - 1);
 }
 
 int launch_spec_resize(aefft_ctx* ctx, int64_t planes, int Nx, int Ny, int Nxs, int Nys, const float2* in, float2* out) {
   const long long total = (long long)planes * Nxs * (Nys / 2 + 1);
+  const long long rows = (long long)planes * Nxs;
+  if ((rows + RSZ_ROWS - 1) / RSZ_ROWS > 0x7fffffffLL) return AEFFT_ERR_UNSUPPORTED;
   ProfScope prof(ctx, "spec_resize", 0.0, 8.0 * (total + (double)planes * (Nxs <= Nx ? Nxs : Nx) * (Nys / 2 + 1)));
-  spec_resize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(in, out, planes, Nx, Ny, Nxs, Nys);
+  spec_resize_kernel<<<(unsigned)((rows + RSZ_ROWS - 1) / RSZ_ROWS), 64 * RSZ_ROWS, 0, ctx->stream>>>(in, out, rows, Nx, Ny, Nxs,
+                                                                                                  Nys);
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
   return AEFFT_OK;
