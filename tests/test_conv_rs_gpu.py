@@ -52,6 +52,32 @@ def test_conv_rs_forward_vs_oracle(tc, dims):
         assert O.rel_l2(got[n], O.conv_gpu(x[n], c, b)) < 3e-5, n
 
 
+FORMS = [{"AEFFT_RS_ONE": "1"}, {"AEFFT_RS_TWO": "1"}, {"AEFFT_RS_NO_TAPPACK": "1"}, {"AEFFT_RS_STACK2": "1"},
+         {"AEFFT_RS_ONE": "1", "AEFFT_RS_STACK2": "1"}]
+
+
+@pytest.mark.parametrize("env", FORMS, ids=lambda e: "+".join(sorted(e)))
+@pytest.mark.parametrize("dims", [SHAPES[0], SHAPES[1], SHAPES[2], SHAPES[4], SHAPES[10]])
+def test_conv_rs_forced_forms_vs_oracle(tc, dims, env, monkeypatch):
+    """The kernel picks CTAs per SM, K packing and the B operand form per layer; every alternative form is forced here."""
+    for k in ("AEFFT_RS_ONE", "AEFFT_RS_TWO", "AEFFT_RS_NO_TAPPACK", "AEFFT_RS_STACK2"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    dM, dD, Nk, Nl, Nx, Ny, B = dims
+    rng = np.random.default_rng(44)
+    x = np.floor(rng.random((B, dD, Nx, Ny)) * 256).astype(np.float32)
+    c = ((rng.random((dM, dD, Nk, Nl)) * 2 - 1) * 0.2).astype(np.float32)
+    b = (rng.random(dM) * 2 - 1).astype(np.float32)
+    tc.profile_enable(True)
+    got = tc.conv_fwd(x, c, b)
+    names = [r["name"] for r in tc.profile_records()]
+    tc.profile_enable(False)
+    assert names == ["conv_fwd_rs"], f"row-streaming kernel not used: {names}"
+    for n in range(B):
+        assert O.rel_l2(got[n], O.conv_gpu(x[n], c, b)) < 3e-5, n
+
+
 def test_conv_rs_is_deterministic(tc):
     dM, dD, Nk, Nl, Nx, Ny, B = 32, 16, 5, 5, 64, 124, 4
     rng = np.random.default_rng(42)
