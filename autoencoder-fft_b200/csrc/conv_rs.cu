@@ -54,6 +54,7 @@ struct ConvRsParams {
   uint32_t w_bytes, seg_bytes, src_bytes, x_slot_bytes, sb_pitch;
   uint32_t off_w, off_x, off_sb;
   long long* dbg;
+  int skip;  // instrumented build only (AEFFT_RS_DEBUG=1 AEFFT_RS_SKIP=mask): knock out 1 converter work, 2 MMAs, 4 epilogue stores
 };
 
 __global__ void conv_rs_weight_prep_kernel(const float* __restrict__ w, long long w_so, long long w_sc, int C, int O, int Oj,
@@ -170,17 +171,28 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
         const int nrows = min(p.BR, p.Nx - i0);
         const int n_in = nrows + NK - 1;
         const int nseg = min(G, p.n_sub - ug * G);
+        // per item: the (column, plane) coordinates of the one or two strips of the M-block; per row only the wait, the
+        // transaction count and the TMA issues remain on this single thread's path (it is the slowest role of the
+        // pipeline skeleton: 780 cycles per row with the divisions inside the row loop)
+        int cj[2], cb[2];
+        for (int g = 0; g < 2; g++) {
+          const int u = ug * G + (g < nseg ? g : 0);
+          const int b = u / p.strips;
+          cj[g] = (u - b * p.strips) * p.TJ + cs_off;
+          cb[g] = b * p.C;
+        }
+        const uint32_t tx = seg_tx * nseg * (p.has_x1 ? 2 : 1);
+        const int row0 = i0 + p.ai0;
         for (int k = 0; k < n_in; k++) {
           wait_t<DBG, true>(&s_empty[ss.slot], ss.phase ^ 1, wA);
           unsigned char* dst = x_ring + (size_t)ss.slot * p.x_slot_bytes;
-          mbar_expect_tx(&s_full[ss.slot], seg_tx * nseg * (p.has_x1 ? 2 : 1));
-          for (int g = 0; g < nseg; g++) {
-            const int u = ug * G + g;
-            const int b = u / p.strips, j0 = (u - b * p.strips) * p.TJ;
-            tma_load_3d(dst + (size_t)g * p.seg_bytes, &p.x0_map, j0 + cs_off, i0 + p.ai0 + k, b * p.C, &s_full[ss.slot]);
+          mbar_expect_tx(&s_full[ss.slot], tx);
+          tma_load_3d(dst, &p.x0_map, cj[0], row0 + k, cb[0], &s_full[ss.slot]);
+          if (p.has_x1) tma_load_3d(dst + p.src_bytes, &p.x1_map, cj[0], row0 + k, cb[0], &s_full[ss.slot]);
+          if (nseg > 1) {
+            tma_load_3d(dst + p.seg_bytes, &p.x0_map, cj[1], row0 + k, cb[1], &s_full[ss.slot]);
             if (p.has_x1)
-              tma_load_3d(dst + p.src_bytes + (size_t)g * p.seg_bytes, &p.x1_map, j0 + cs_off, i0 + p.ai0 + k, b * p.C,
-                          &s_full[ss.slot]);
+              tma_load_3d(dst + p.src_bytes + p.seg_bytes, &p.x1_map, cj[1], row0 + k, cb[1], &s_full[ss.slot]);
           }
           ss.next();
         }
@@ -226,7 +238,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
         // accumulator column still receives its MMAs in (K stage, window column, pass) order.
         const int tk_lo = max(0, k - nrows + 1), tk_hi = min(NK - 1, k);
         const uint32_t a_row16 = (sb_base + (uint32_t)rx.slot * pitch) >> 4;
-        if (elect_one()) {
+        if (elect_one() && !(DBG && (p.skip & 2))) {
           int rem = tk_hi - tk_lo + 1, slot = fslot;
           uint32_t n0 = (uint32_t)((NK - 1 - tk_hi) * CW);
 #pragma unroll 1
@@ -284,7 +296,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
         wait_t<DBG, true>(&s_full[ss.slot], ss.phase, wA);
         wait_t<DBG, true>(&xb_empty[sb.slot], sb.phase ^ 1, wB);
         const unsigned char* xs = x_ring + (size_t)ss.slot * p.x_slot_bytes;
-        for (int idx = t; idx < n_it; idx += NT) {
+        for (int idx = t; idx < ((DBG && (p.skip & 1)) ? 0 : n_it); idx += NT) {
           const int pl = idx >> 7, px = idx & 127;
           const int seg = px / PJs, c = px - seg * PJs;
           const float* s0 = reinterpret_cast<const float*>(xs + (size_t)seg * p.seg_bytes) + c + d_off;
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
 #pragma unroll
             for (int e = 0; e < 16; e++) v[e] += u[e];
           }
-          if (lane_ok) {
+          if (lane_ok && !(DBG && (p.skip & 4))) {
             // one coalesced 512-byte store per output channel; the channel stride is warp-uniform
             const int nv = n_o - c0;  // live channels of this chunk (warp-uniform)
             float* q = orow + (size_t)c0 * plane_u;
@@ -526,6 +538,7 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
   p.wprep = reinterpret_cast<const uint4*>(wprep);
   const bool debug = getenv("AEFFT_RS_DEBUG") != nullptr;
   p.dbg = nullptr;
+  p.skip = (debug && getenv("AEFFT_RS_SKIP")) ? atoi(getenv("AEFFT_RS_SKIP")) : 0;
   const size_t n_dbg = (size_t)cpj * p.n_jobs * 12 * 4;
   if (debug) {
     AE_TRY(ctx->getT("rs_dbg", n_dbg, &p.dbg));
