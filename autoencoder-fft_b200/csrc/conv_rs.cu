@@ -50,6 +50,8 @@ struct ConvRsParams {
   int n_sub, items, cpj;
   int KS, NP, kpack, NLg, Ntot, Rr, NSB, NSF, passes;
   int tmem_cols;   // 512 / 256 / 128 columns for 1 / 2 / 3 CTAs per SM
+  int npack;       // few outputs (O * NL <= 16): N = (window row, window column, output), the epilogue sums the columns
+  uint32_t off_xch;
   int stack2, CW;  // stack2: B rows = [W_hi | W_lo] per window row (2 MMAs instead of 3); CW = accumulator columns per output row
   uint32_t w_bytes, seg_bytes, src_bytes, x_slot_bytes, sb_pitch;
   uint32_t off_w, off_x, off_sb;
@@ -59,7 +61,7 @@ struct ConvRsParams {
 
 __global__ void conv_rs_weight_prep_kernel(const float* __restrict__ w, long long w_so, long long w_sc, int C, int O, int Oj,
                                            int O_pad, int NK, int NL, int NLg, int flip, int KS, int kpack, int n_jobs,
-                                           int stack2, __nv_bfloat16* __restrict__ wprep) {
+                                           int stack2, int npack, __nv_bfloat16* __restrict__ wprep) {
   const int Ntot = NK * O_pad;
   const long long per_part = (long long)NLg * 2 * Ntot * 8;
   const long long per_job = (long long)KS * 2 * per_part;
@@ -72,10 +74,14 @@ __global__ void conv_rs_weight_prep_kernel(const float* __restrict__ w, long lon
     const int tlg = (int)(r % NLg); r /= NLg;
     const int ks = (int)(r % KS); r /= KS;
     const int job = (int)r;
-    const int tk = NK - 1 - n / O_pad, o = n % O_pad;
+    const int tk = NK - 1 - n / O_pad;
+    // N index inside the window row: output channel, or (window column, output) packed when npack (the A operand is then
+    // not advanced per window column; the epilogue adds the NL column groups with their pixel shifts)
+    const int q = n % O_pad;
+    const int o = npack ? (q < O * NL ? q % O : O_pad) : q;
     // K index of this element: channel block (kpack 0), tap pair x 8 channels (kpack 1), or (tap, channel) packed (kpack 2)
     const int kk = kchunk * 8 + e;
-    const int tl = kpack == 2 ? (kk < C * NL ? kk / C : NL) : kpack ? 2 * tlg + kchunk : tlg;
+    const int tl = npack ? (q < O * NL ? q / O : NL) : kpack == 2 ? (kk < C * NL ? kk / C : NL) : kpack ? 2 * tlg + kchunk : tlg;
     const int c = kpack == 2 ? kk % C : kpack ? e : ks * 16 + kchunk * 8 + e;
     const int k = flip ? NK - 1 - tk : tk, l = flip ? NL - 1 - tl : tl;
     const int og = job * Oj + o;
@@ -372,7 +378,26 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
         wait_t<DBG, true>(&acc_full[slot], phase, wA);
         fence_after_sync();
         float* orow = obase + (long long)rho * p.Ny;
-        for (int c0 = 0; c0 < p.O_pad; c0 += 16) {
+        if (p.npack) {
+          // the 16 accumulator columns of this lane are (window column tl, output o) partial sums of INPUT pixel `lane`:
+          // out[o](j) = bias + sum_tl column[tl * O + o] of lane j + tl.  Exchange through shared memory (double
+          // buffered by row parity, one named barrier of the four epilogue warps per row).
+          float v[16];
+          tmem_ld16(t_lane + (uint32_t)(slot * p.CW), v);
+          tmem_st16(t_lane + (uint32_t)(slot * p.CW), z);
+          float* xch = reinterpret_cast<float*>(smem + p.off_xch) + (rho & 1) * (16 * 132);
+#pragma unroll
+          for (int e = 0; e < 16; e++) xch[e * 132 + lg] = v[e];
+          asm volatile("bar.sync 2, 128;" ::: "memory");
+          if (lane_ok && !(DBG && (p.skip & 4))) {
+            for (int o = 0; o < n_o; o++) {
+              float acc = bias_s[o];
+              for (int tl = 0; tl < p.NL; tl++) acc += xch[(tl * p.O + o) * 132 + lg + tl];
+              orow[(size_t)o * plane_u] = acc;
+            }
+          }
+        }
+        for (int c0 = 0; c0 < (p.npack ? 0 : p.O_pad); c0 += 16) {
           float v[16];
           tmem_ld16(t_lane + (uint32_t)(slot * p.CW + c0), v);
           tmem_st16(t_lane + (uint32_t)(slot * p.CW + c0), z);
@@ -440,6 +465,12 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
   p.KS = p.kpack ? 1 : (C + 15) / 16;
   p.NP = p.kpack == 1 ? 1 : 2 * p.KS;
   p.NLg = p.kpack == 2 ? 1 : p.kpack ? (win.Nl + 1) / 2 : win.Nl;
+  // Few outputs (the 3-channel reconstruction layer): N = (window row, window column, output) -- NL * O <= 16 columns per
+  // output row instead of 16 padded output channels -- so ONE MMA triple per K stage serves all window columns; the
+  // epilogue adds the NL column groups of neighbouring lanes (pixel shifts) through shared memory.
+  p.npack = (p.kpack == 0 && O * win.Nl <= 16 && win.lo == 0 && !getenv("AEFFT_RS_NO_NPACK")) ? 1 : 0;
+  if (p.npack) p.NLg = 1;
+  const size_t xch_bytes = p.npack ? (size_t)2 * 16 * 132 * sizeof(float) : 0;
   const int halo = win.Nl - 1;
   p.PJs = (Ny + halo <= 64) ? 64 : 128;
   p.G = 128 / p.PJs;
@@ -472,14 +503,14 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
         const int O_pad = Oj;
         // [W_hi | W_lo] stacking (2 MMAs of 2N instead of 3 of N) measured no faster on B200 (the N = 80 MMAs are not purely
         // A-read bound): opt-in for experiments only
-        const int stack2 = (getenv("AEFFT_RS_STACK2") && passes == 3 && 2 * win.Nk * O_pad <= 256) ? 1 : 0;
+        const int stack2 = (getenv("AEFFT_RS_STACK2") && !p.npack && passes == 3 && 2 * win.Nk * O_pad <= 256) ? 1 : 0;
         const int CW = stack2 ? 2 * O_pad : O_pad;
         const int Rr = cols / CW > RS_MAXACC ? RS_MAXACC : cols / CW;
         if (Rr < win.Nk + (two ? 3 : 1)) continue;
         const size_t w_bytes = (size_t)p.KS * 2 * p.NLg * 2 * (win.Nk * O_pad) * 16;
         for (int NSB = 4; NSB >= (two ? 3 : 2) && !found; NSB--) {
           const size_t sb_bytes = (size_t)2 * p.NP * NSB * p.sb_pitch;
-          if (w_bytes + x_bytes + sb_bytes + 3 * 1024 <= budget) {
+          if (w_bytes + x_bytes + sb_bytes + xch_bytes + 3 * 1024 <= budget) {
             p.Oj = Oj; p.O_pad = O_pad; p.Rr = Rr; p.NSB = NSB; p.NSF = NSF; p.w_bytes = (uint32_t)w_bytes;
             p.stack2 = stack2; p.CW = CW;
             p.n_jobs = (O + Oj - 1) / Oj;
@@ -496,7 +527,8 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
   p.off_w = 0;
   p.off_x = (p.w_bytes + 1023) & ~1023u;
   p.off_sb = (uint32_t)((p.off_x + x_bytes + 1023) & ~(size_t)1023);
-  const size_t smem = p.off_sb + (size_t)2 * p.NP * p.NSB * p.sb_pitch + 1024;
+  p.off_xch = (uint32_t)((p.off_sb + (size_t)2 * p.NP * p.NSB * p.sb_pitch + 1023) & ~(size_t)1023);
+  const size_t smem = p.off_xch + xch_bytes + 1024;
   // work split
   int cpj = per_sm * ctx->sm_count / p.n_jobs;
   if (cpj < 1) cpj = 1;
@@ -531,7 +563,7 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
     const long long total = w_elems / 2;
     const unsigned blocks = (unsigned)((total + 255) / 256 > 1024 ? 1024 : (total + 255) / 256);
     conv_rs_weight_prep_kernel<<<blocks, 256, 0, ctx->stream>>>(w, w_so, w_sc, C, O, p.Oj, p.O_pad, win.Nk, win.Nl, p.NLg,
-                                                               win.flip, p.KS, p.kpack, p.n_jobs, p.stack2,
+                                                               win.flip, p.KS, p.kpack, p.n_jobs, p.stack2, p.npack,
                                                                reinterpret_cast<__nv_bfloat16*>(wprep));
     ctx->launches++;
   }
@@ -573,8 +605,8 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
         for (int q = 0; q < 4; q++) acc[r][q] += (double)h[((size_t)c * 12 + wv) * 4 + q];
         cnt[r]++;
       }
-    fprintf(stderr, "[conv_rs] C=%d O=%d %dx%d B=%lld PJs=%d G=%d Oj=%d jobs=%d cpj=%d bands=%d BR=%d Rr=%d NSB=%d KS=%d kpack=%d smem=%zu tmem=%d\n",
-            C, O, Nx, Ny, (long long)B, p.PJs, p.G, p.Oj, p.n_jobs, cpj, p.bands, p.BR, p.Rr, p.NSB, p.KS, p.kpack, smem, p.tmem_cols);
+    fprintf(stderr, "[conv_rs] C=%d O=%d %dx%d B=%lld PJs=%d G=%d Oj=%d jobs=%d cpj=%d bands=%d BR=%d Rr=%d NSB=%d KS=%d kpack=%d npack=%d smem=%zu tmem=%d\n",
+            C, O, Nx, Ny, (long long)B, p.PJs, p.G, p.Oj, p.n_jobs, cpj, p.bands, p.BR, p.Rr, p.NSB, p.KS, p.kpack, p.npack, smem, p.tmem_cols);
     for (int r = 0; r < 4; r++)
       fprintf(stderr, "[conv_rs]   %-30s waitA %9.0f  waitB %9.0f  total %9.0f  mma-issue %9.0f cycles\n", role[r],
               acc[r][0] / cnt[r], acc[r][1] / cnt[r], acc[r][2] / cnt[r], acc[r][3] / cnt[r]);

@@ -32,6 +32,8 @@ SHAPES = [
     (8, 1, 5, 5, 64, 48, 1),       # BASELINE config 1 shape class (D = 1)
     (16, 3, 5, 5, 9, 8, 1),        # frame smaller than the window halo
     (16, 3, 5, 5, 320, 240, 2),    # config 2, pair 0
+    (3, 16, 5, 5, 320, 240, 2),    # config 2, pair 0 decoder: (window column, output) packed N, column sums in the epilogue
+    (2, 32, 7, 7, 45, 136, 3),     # the same form with two K stages, 7x7 window (14 of 16 columns), two strips
     (32, 16, 5, 5, 160, 120, 2),   # config 2, pair 1
 ]
 
@@ -53,6 +55,7 @@ def test_conv_rs_forward_vs_oracle(tc, dims):
 
 
 FORMS = [{"AEFFT_RS_ONE": "1"}, {"AEFFT_RS_TWO": "1"}, {"AEFFT_RS_NO_TAPPACK": "1"}, {"AEFFT_RS_STACK2": "1"},
+         {"AEFFT_RS_NO_NPACK": "1"}, {"AEFFT_RS_ONE": "1", "AEFFT_RS_NO_NPACK": "1"},
          {"AEFFT_RS_ONE": "1", "AEFFT_RS_STACK2": "1"}]
 
 
@@ -60,7 +63,7 @@ FORMS = [{"AEFFT_RS_ONE": "1"}, {"AEFFT_RS_TWO": "1"}, {"AEFFT_RS_NO_TAPPACK": "
 @pytest.mark.parametrize("dims", [SHAPES[0], SHAPES[1], SHAPES[2], SHAPES[4], SHAPES[10]])
 def test_conv_rs_forced_forms_vs_oracle(tc, dims, env, monkeypatch):
     """The kernel picks CTAs per SM, K packing and the B operand form per layer; every alternative form is forced here."""
-    for k in ("AEFFT_RS_ONE", "AEFFT_RS_TWO", "AEFFT_RS_NO_TAPPACK", "AEFFT_RS_STACK2"):
+    for k in ("AEFFT_RS_ONE", "AEFFT_RS_TWO", "AEFFT_RS_NO_TAPPACK", "AEFFT_RS_STACK2", "AEFFT_RS_NO_NPACK"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
