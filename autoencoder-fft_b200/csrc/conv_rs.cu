@@ -49,6 +49,7 @@ struct ConvRsParams {
   int PJs, G, TJ, strips, bands, BR;
   int n_sub, items, cpj;
   int KS, NP, kpack, NLg, Ntot, Rr, NSB, NSF, passes;
+  int RU, NSBR;    // input rows per pipeline unit (one barrier round trip moves RU rows), rows of the bf16 ring = NSB * RU
   int tmem_cols;   // 512 / 256 / 128 columns for 1 / 2 / 3 CTAs per SM
   int npack;       // few outputs (O * NL <= 16): N = (window row, window column, output), the epilogue sums the columns
   uint32_t off_xch;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
     const uint4* src = p.wprep + (size_t)job * (p.w_bytes / 16);
     uint4* dst = reinterpret_cast<uint4*>(w_sm);
     for (uint32_t i = tid; i < p.w_bytes / 16; i += RS_THREADS) dst[i] = __ldg(src + i);
-    const uint32_t n16 = (uint32_t)(2 * p.NP * p.NSB) * p.sb_pitch / 16;
+    const uint32_t n16 = (uint32_t)(2 * p.NP * p.NSBR) * p.sb_pitch / 16;
     uint4* z = reinterpret_cast<uint4*>(sb_ring);
     for (uint32_t i = tid; i < n16; i += RS_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     if (tid < 16) voff_s[tid] = tid < p.C * p.NL ? (tid % p.C) * (p.PJs + 4) + tid / p.C : -1;
@@ -189,16 +190,20 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
         }
         const uint32_t tx = seg_tx * nseg * (p.has_x1 ? 2 : 1);
         const int row0 = i0 + p.ai0;
-        for (int k = 0; k < n_in; k++) {
+        for (int k0 = 0; k0 < n_in; k0 += p.RU) {
+          const int nr = min(p.RU, n_in - k0);  // rows of this unit
           wait_t<DBG, true>(&s_empty[ss.slot], ss.phase ^ 1, wA);
-          unsigned char* dst = x_ring + (size_t)ss.slot * p.x_slot_bytes;
-          mbar_expect_tx(&s_full[ss.slot], tx);
-          tma_load_3d(dst, &p.x0_map, cj[0], row0 + k, cb[0], &s_full[ss.slot]);
-          if (p.has_x1) tma_load_3d(dst + p.src_bytes, &p.x1_map, cj[0], row0 + k, cb[0], &s_full[ss.slot]);
-          if (nseg > 1) {
-            tma_load_3d(dst + p.seg_bytes, &p.x0_map, cj[1], row0 + k, cb[1], &s_full[ss.slot]);
-            if (p.has_x1)
-              tma_load_3d(dst + p.src_bytes + p.seg_bytes, &p.x1_map, cj[1], row0 + k, cb[1], &s_full[ss.slot]);
+          mbar_expect_tx(&s_full[ss.slot], tx * nr);
+          for (int r = 0; r < nr; r++) {
+            unsigned char* dst = x_ring + (size_t)(ss.slot * p.RU + r) * p.x_slot_bytes;
+            const int k = k0 + r;
+            tma_load_3d(dst, &p.x0_map, cj[0], row0 + k, cb[0], &s_full[ss.slot]);
+            if (p.has_x1) tma_load_3d(dst + p.src_bytes, &p.x1_map, cj[0], row0 + k, cb[0], &s_full[ss.slot]);
+            if (nseg > 1) {
+              tma_load_3d(dst + p.seg_bytes, &p.x0_map, cj[1], row0 + k, cb[1], &s_full[ss.slot]);
+              if (p.has_x1)
+                tma_load_3d(dst + p.src_bytes + p.seg_bytes, &p.x1_map, cj[1], row0 + k, cb[1], &s_full[ss.slot]);
+            }
           }
           ss.next();
         }
@@ -208,16 +213,16 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
     // ============================================================ MMA issuer (whole warp runs the loops, one lane issues)
     const uint32_t sb_base = smem_u32(sb_ring), w_base = smem_u32(w_sm);
     const uint32_t pitch = p.sb_pitch;
-    const int NSB = p.NSB, NP = p.NP, KS = p.KS, NLg = p.NLg, Rr = p.Rr, CW = p.CW;
+    const int NSB = p.NSB, NSBR = p.NSBR, NP = p.NP, KS = p.KS, NLg = p.NLg, Rr = p.Rr, CW = p.CW;
     const bool stack2 = p.stack2 != 0;
     const int Ntot = stack2 ? 2 * p.Ntot : p.Ntot;  // B rows per K chunk
-    const uint32_t a_lbo = p.kpack == 1 ? 16u : (uint32_t)NSB * pitch;
+    const uint32_t a_lbo = p.kpack == 1 ? 16u : (uint32_t)NSBR * pitch;
     const uint64_t a_desc0 = make_desc(0, a_lbo, 128), b_desc0 = make_desc(0, (uint32_t)Ntot * 16, 128);
-    const uint32_t part_off16 = ((uint32_t)(NP * NSB) * pitch) >> 4;               // A: hi -> lo part
+    const uint32_t part_off16 = ((uint32_t)(NP * NSBR) * pitch) >> 4;               // A: hi -> lo part
     const uint32_t wpart_off16 = (uint32_t)(NLg * 2 * Ntot);                       // W: hi -> lo part (16-byte units; !stack2)
     const bool three = p.passes == 3;
     const int maxchunks = 256 / CW;
-    const uint32_t a_ks_step16 = p.kpack == 1 ? 0u : (((uint32_t)(2 * NSB) * pitch) >> 4);
+    const uint32_t a_ks_step16 = p.kpack == 1 ? 0u : (((uint32_t)(2 * NSBR) * pitch) >> 4);
     const uint32_t a_tl_step16 = p.kpack == 1 ? 2u : 1u;
     const uint32_t w_ks_step16 = (uint32_t)((stack2 ? 1 : 2) * NLg * 2 * Ntot), w_tl_step16 = (uint32_t)(2 * Ntot);
     Ring rx(NSB);
@@ -229,8 +234,11 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
       const int nrows = min(p.BR, p.Nx - i0);
       const int n_in = nrows + NK - 1;
       int fslot = gro;
-      for (int k = 0; k < n_in; k++) {
-        wait_t<DBG, true>(&xb_full[rx.slot], rx.phase, wA);
+      for (int k0 = 0; k0 < n_in; k0 += p.RU) {
+       // one barrier round trip per unit of RU input rows
+       wait_t<DBG, true>(&xb_full[rx.slot], rx.phase, wA);
+       for (int r = 0; r < p.RU && k0 + r < n_in; r++) {
+        const int k = k0 + r;
         if (k < nrows) {
           // the accumulator slot of the newest output row (rho = k) must have been drained and zeroed
           wait_t<DBG, true>(&acc_empty[rn.slot], rn.phase ^ 1, wB);
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
         // stack, advanced as rows complete.  One elected lane walks pieces and descriptors with constant increments; every
         // accumulator column still receives its MMAs in (K stage, window column, pass) order.
         const int tk_lo = max(0, k - nrows + 1), tk_hi = min(NK - 1, k);
-        const uint32_t a_row16 = (sb_base + (uint32_t)rx.slot * pitch) >> 4;
+        const uint32_t a_row16 = (sb_base + (uint32_t)(rx.slot * p.RU + r) * pitch) >> 4;
         if (elect_one() && !(DBG && (p.skip & 2))) {
           int rem = tk_hi - tk_lo + 1, slot = fslot;
           uint32_t n0 = (uint32_t)((NK - 1 - tk_hi) * CW);
@@ -277,12 +285,11 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
         __syncwarp();
         if (DBG) wC += clock64() - t_m0;
         const bool row_done = k >= NK - 1;  // this input row completes output row k - NK + 1, the oldest of the stack
-        if (elect_one()) {
-          commit(&xb_empty[rx.slot]);
-          if (row_done) commit(&acc_full[fslot]);
-        }
+        if (row_done && elect_one()) commit(&acc_full[fslot]);
         if (row_done && ++fslot == Rr) fslot = 0;
-        rx.next();
+       }
+       if (elect_one()) commit(&xb_empty[rx.slot]);
+       rx.next();
       }
       gro = rn.slot;
     }
@@ -298,11 +305,14 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
       const int nrows = min(p.BR, p.Nx - i0);
       const int n_in = nrows + NK - 1;
       const int nseg = min(G, p.n_sub - ug * G);
-      for (int k = 0; k < n_in; k++) {
+      for (int k0 = 0; k0 < n_in; k0 += p.RU) {
+        const int nr = min(p.RU, n_in - k0);  // rows of this unit: their (row, plane, pixel) items share the threads
         wait_t<DBG, true>(&s_full[ss.slot], ss.phase, wA);
         wait_t<DBG, true>(&xb_empty[sb.slot], sb.phase ^ 1, wB);
-        const unsigned char* xs = x_ring + (size_t)ss.slot * p.x_slot_bytes;
-        for (int idx = t; idx < ((DBG && (p.skip & 1)) ? 0 : n_it); idx += NT) {
+        for (int it = t; it < ((DBG && (p.skip & 1)) ? 0 : nr * n_it); it += NT) {
+          const int r = it >= n_it ? 1 : 0, idx = it - r * n_it;  // RU <= 2
+          const unsigned char* xs = x_ring + (size_t)(ss.slot * p.RU + r) * p.x_slot_bytes;
+          const int rslot = sb.slot * p.RU + r;  // row of the bf16 ring
           const int pl = idx >> 7, px = idx & 127;
           const int seg = px / PJs, c = px - seg * PJs;
           const float* s0 = reinterpret_cast<const float*>(xs + (size_t)seg * p.seg_bytes) + c + d_off;
@@ -337,9 +347,9 @@ __global__ void __launch_bounds__(RS_THREADS, 3) conv_rs_kernel(const __grid_con
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; e++) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-          unsigned char* dst = sb_ring + ((size_t)(pl * p.NSB) + sb.slot) * p.sb_pitch + (size_t)px * 16;
+          unsigned char* dst = sb_ring + ((size_t)(pl * p.NSBR) + rslot) * p.sb_pitch + (size_t)px * 16;
           *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(dst + (size_t)(p.NP * p.NSB) * p.sb_pitch) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(dst + (size_t)(p.NP * p.NSBR) * p.sb_pitch) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         fence_proxy_async();
         __syncwarp();
@@ -490,14 +500,17 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
   int found = 0;
   p.tmem_cols = 512;
   int per_sm = 1;
+  // rows per pipeline unit: the bare pipeline (one barrier round trip per row through four roles) is ~40 % of the kernel
+  const int ru_max = (getenv("AEFFT_RS_RU") && atoi(getenv("AEFFT_RS_RU")) == 1) ? 1 : 2;
   const int max_per_sm = getenv("AEFFT_RS_ONE") ? 1 : getenv("AEFFT_RS_TWO") ? 2 : 3;
   for (int ncta = max_per_sm; ncta >= 1 && !found; ncta--) {
     const bool two = ncta > 1;
     const size_t budget = ncta == 3 ? 74 * 1024 : ncta == 2 ? 112 * 1024 : 225 * 1024 - 1024;
     const int cols = 512 >> (ncta == 3 ? 2 : ncta - 1);
-    // preference order: double-buffered fp32 staging, few output jobs, deep bf16 ring
+    // preference order: double-buffered fp32 staging, few output jobs, deep bf16 ring (one row per unit; see below)
+    const int RU = 1;
     for (int NSF = RS_NSF; NSF >= (two ? RS_NSF : 1) && !found; NSF--) {
-      x_bytes = (size_t)NSF * p.x_slot_bytes;
+      x_bytes = (size_t)NSF * RU * p.x_slot_bytes;
       for (int split = 1; split <= (two ? 1 : 8) && !found; split++) {
         const int Oj = ((O + split - 1) / split + 15) / 16 * 16;
         const int O_pad = Oj;
@@ -509,9 +522,10 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
         if (Rr < win.Nk + (two ? 3 : 1)) continue;
         const size_t w_bytes = (size_t)p.KS * 2 * p.NLg * 2 * (win.Nk * O_pad) * 16;
         for (int NSB = 4; NSB >= (two ? 3 : 2) && !found; NSB--) {
-          const size_t sb_bytes = (size_t)2 * p.NP * NSB * p.sb_pitch;
+          const size_t sb_bytes = (size_t)2 * p.NP * NSB * RU * p.sb_pitch;
           if (w_bytes + x_bytes + sb_bytes + xch_bytes + 3 * 1024 <= budget) {
             p.Oj = Oj; p.O_pad = O_pad; p.Rr = Rr; p.NSB = NSB; p.NSF = NSF; p.w_bytes = (uint32_t)w_bytes;
+            p.RU = RU; p.NSBR = NSB * RU;
             p.stack2 = stack2; p.CW = CW;
             p.n_jobs = (O + Oj - 1) / Oj;
             p.tmem_cols = cols;
@@ -523,11 +537,21 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
     }
   }
   if (!found || p.n_jobs > 16) return AEFFT_ERR_UNSUPPORTED;
+  // Two input rows per pipeline unit when the SAME configuration (CTAs per SM, output jobs) still fits with double
+  // buffered staging and a bf16 ring at least 3 units deep: it halves the barrier round trips of producer, converters
+  // and issuer (3->16 data gradient 0.177 -> 0.155 ms).  Never at the price of more output jobs or fewer CTAs per SM.
+  if (ru_max >= 2 && p.NSF == RS_NSF) {
+    const size_t budget = per_sm == 3 ? 74 * 1024 : per_sm == 2 ? 112 * 1024 : 225 * 1024 - 1024;
+    for (int NSB = p.NSB; NSB >= 3 && p.RU == 1; NSB--) {
+      const size_t need = p.w_bytes + (size_t)RS_NSF * 2 * p.x_slot_bytes + (size_t)2 * p.NP * NSB * 2 * p.sb_pitch + xch_bytes + 3 * 1024;
+      if (need <= budget) { p.RU = 2; p.NSB = NSB; p.NSBR = 2 * NSB; x_bytes = (size_t)RS_NSF * 2 * p.x_slot_bytes; }
+    }
+  }
   p.Ntot = win.Nk * p.O_pad;
   p.off_w = 0;
   p.off_x = (p.w_bytes + 1023) & ~1023u;
   p.off_sb = (uint32_t)((p.off_x + x_bytes + 1023) & ~(size_t)1023);
-  p.off_xch = (uint32_t)((p.off_sb + (size_t)2 * p.NP * p.NSB * p.sb_pitch + 1023) & ~(size_t)1023);
+  p.off_xch = (uint32_t)((p.off_sb + (size_t)2 * p.NP * p.NSBR * p.sb_pitch + 1023) & ~(size_t)1023);
   const size_t smem = p.off_xch + xch_bytes + 1024;
   // work split
   int cpj = per_sm * ctx->sm_count / p.n_jobs;
@@ -605,8 +629,8 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
         for (int q = 0; q < 4; q++) acc[r][q] += (double)h[((size_t)c * 12 + wv) * 4 + q];
         cnt[r]++;
       }
-    fprintf(stderr, "[conv_rs] C=%d O=%d %dx%d B=%lld PJs=%d G=%d Oj=%d jobs=%d cpj=%d bands=%d BR=%d Rr=%d NSB=%d KS=%d kpack=%d npack=%d smem=%zu tmem=%d\n",
-            C, O, Nx, Ny, (long long)B, p.PJs, p.G, p.Oj, p.n_jobs, cpj, p.bands, p.BR, p.Rr, p.NSB, p.KS, p.kpack, p.npack, smem, p.tmem_cols);
+    fprintf(stderr, "[conv_rs] C=%d O=%d %dx%d B=%lld PJs=%d G=%d Oj=%d jobs=%d cpj=%d bands=%d BR=%d Rr=%d RU=%d NSB=%d KS=%d kpack=%d npack=%d smem=%zu tmem=%d\n",
+            C, O, Nx, Ny, (long long)B, p.PJs, p.G, p.Oj, p.n_jobs, cpj, p.bands, p.BR, p.Rr, p.RU, p.NSB, p.KS, p.kpack, p.npack, smem, p.tmem_cols);
     for (int r = 0; r < 4; r++)
       fprintf(stderr, "[conv_rs]   %-30s waitA %9.0f  waitB %9.0f  total %9.0f  mma-issue %9.0f cycles\n", role[r],
               acc[r][0] / cnt[r], acc[r][1] / cnt[r], acc[r][2] / cnt[r], acc[r][3] / cnt[r]);

@@ -55,7 +55,7 @@ def test_conv_rs_forward_vs_oracle(tc, dims):
 
 
 FORMS = [{"AEFFT_RS_ONE": "1"}, {"AEFFT_RS_TWO": "1"}, {"AEFFT_RS_NO_TAPPACK": "1"}, {"AEFFT_RS_STACK2": "1"},
-         {"AEFFT_RS_NO_NPACK": "1"}, {"AEFFT_RS_ONE": "1", "AEFFT_RS_NO_NPACK": "1"},
+         {"AEFFT_RS_NO_NPACK": "1"}, {"AEFFT_RS_ONE": "1", "AEFFT_RS_NO_NPACK": "1"}, {"AEFFT_RS_RU": "1"},
          {"AEFFT_RS_ONE": "1", "AEFFT_RS_STACK2": "1"}]
 
 
@@ -63,7 +63,7 @@ FORMS = [{"AEFFT_RS_ONE": "1"}, {"AEFFT_RS_TWO": "1"}, {"AEFFT_RS_NO_TAPPACK": "
 @pytest.mark.parametrize("dims", [SHAPES[0], SHAPES[1], SHAPES[2], SHAPES[4], SHAPES[10]])
 def test_conv_rs_forced_forms_vs_oracle(tc, dims, env, monkeypatch):
     """The kernel picks CTAs per SM, K packing and the B operand form per layer; every alternative form is forced here."""
-    for k in ("AEFFT_RS_ONE", "AEFFT_RS_TWO", "AEFFT_RS_NO_TAPPACK", "AEFFT_RS_STACK2", "AEFFT_RS_NO_NPACK"):
+    for k in ("AEFFT_RS_ONE", "AEFFT_RS_TWO", "AEFFT_RS_NO_TAPPACK", "AEFFT_RS_STACK2", "AEFFT_RS_NO_NPACK", "AEFFT_RS_RU"):
         monkeypatch.delenv(k, raising=False)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
