@@ -606,46 +606,54 @@ constexpr int PD_MAXT = 8;  // taps per axis
 // Both kernels are instantiated for the tap counts the reference's parameter file can produce (3, 5, 7 per axis) plus a
 // generic 8 x 8 variant; index arithmetic is 32-bit (bins per image < 2^31).
 
-// 256 threads = TW columns x (256/TW) rows of one image's (slab of the) half spectrum: grid (col tiles, row tiles, n_img)
+// 128 threads = 128 columns of one image's (slab of the) half spectrum, 16 rows per CTA: grid (col tiles, row tiles, n_img)
 template <int NK, int NL>
-__global__ void __launch_bounds__(256) kernel_spectrum_direct_kernel(const float* __restrict__ taps, float2* __restrict__ spec,
+__global__ void __launch_bounds__(128) kernel_spectrum_direct_kernel(const float* __restrict__ taps, float2* __restrict__ spec,
                                                                       int Nx, int Ny, int Nk, int Nl,
                                                                       const float2* __restrict__ twx,
                                                                       const float2* __restrict__ twy, int col0, int Nyr,
-                                                                      int log2tw) {
-  // (col0, Nyr): the slab of spectrum columns [col0, col0 + Nyr) this device owns (whole half spectrum: 0, Ny/2+1)
+                                                                      int rows_per_cta) {
+  // (col0, Nyr): the slab of spectrum columns [col0, col0 + Nyr) this device owns (whole half spectrum: 0, Ny/2+1).
+  // One thread per spectrum column: the column factor t[k] = sum_l c[k][l] Ey[l](wy) is formed once, every row then costs
+  // NK complex multiply-adds with the (warp-uniform) row factors Ex[k](wx) instead of NK * NL + NK.
   __shared__ float c[PD_MAXT * PD_MAXT];
   const int nk = NK ? NK : Nk, nl = NL ? NL : Nl;
   const unsigned n = blockIdx.z;
   if (threadIdx.x < nk * nl) c[threadIdx.x] = taps[(size_t)n * nk * nl + threadIdx.x];
   __syncthreads();
-  const int tw = 1 << log2tw;
-  const int wl = blockIdx.x * tw + (threadIdx.x & (tw - 1));
-  const int wx = blockIdx.y * (256 >> log2tw) + (threadIdx.x >> log2tw);
-  if (wl >= Nyr || wx >= Nx) return;
+  const int wl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wl >= Nyr) return;
   const int wy = col0 + wl;
-  float2 ey[NL ? NL : PD_MAXT];
+  float2 t[NK ? NK : PD_MAXT];
 #pragma unroll
-  for (int l = 0; l < (NL ? NL : PD_MAXT); l++)
-    if (l < nl) ey[l] = __ldg(twy + ((wy * ((l - nl / 2) & (Ny - 1))) & (Ny - 1)));
-  float2 acc = make_float2(0.f, 0.f);
+  for (int k = 0; k < (NK ? NK : PD_MAXT); k++) t[k] = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int k = 0; k < (NK ? NK : PD_MAXT); k++) {
-    if (k < nk) {
-      const float2 ex = __ldg(twx + ((wx * ((k - nk / 2) & (Nx - 1))) & (Nx - 1)));
-      float2 t = make_float2(0.f, 0.f);  // sum_l c[k][l] Ey[l]
+  for (int l = 0; l < (NL ? NL : PD_MAXT); l++) {
+    if (l < nl) {
+      const float2 ey = __ldg(twy + ((wy * ((l - nl / 2) & (Ny - 1))) & (Ny - 1)));
 #pragma unroll
-      for (int l = 0; l < (NL ? NL : PD_MAXT); l++) {
-        if (l < nl) {
+      for (int k = 0; k < (NK ? NK : PD_MAXT); k++) {
+        if (k < nk) {
           const float cv = c[k * nl + l];
-          t.x = fmaf(cv, ey[l].x, t.x);
-          t.y = fmaf(cv, ey[l].y, t.y);
+          t[k].x = fmaf(cv, ey.x, t[k].x);
+          t[k].y = fmaf(cv, ey.y, t[k].y);
         }
       }
-      cfma(acc, ex, t);
     }
   }
-  spec[((size_t)n * Nx + wx) * Nyr + wl] = acc;
+  const int wx0 = blockIdx.y * rows_per_cta, wx1 = min(Nx, wx0 + rows_per_cta);
+  float2* o = spec + ((size_t)n * Nx + wx0) * Nyr + wl;
+  for (int wx = wx0; wx < wx1; wx++, o += Nyr) {
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < (NK ? NK : PD_MAXT); k++) {
+      if (k < nk) {
+        const float2 ex = __ldg(twx + ((wx * ((k - nk / 2) & (Nx - 1))) & (Nx - 1)));  // warp-uniform address
+        cfma(acc, ex, t[k]);
+      }
+    }
+    *o = acc;
+  }
 }
 
 int launch_kernel_spectrum_direct(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl, const float* taps,
@@ -657,14 +665,12 @@ int launch_kernel_spectrum_direct(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny,
   const int Nyr = ncols > 0 ? ncols : Ny / 2 + 1;
   const long long S = (long long)Nx * Nyr;
   ProfScope prof(ctx, "kernel_spectrum", 8.0 * n_img * S * (Nk + Nk * Nl / 4.0), 8.0 * n_img * S);
-  int log2tw = 8;
-  while (log2tw > 3 && (1 << (log2tw - 1)) >= Nyr) log2tw--;
-  const int threads = 256, tw = 1 << log2tw, rows = 256 >> log2tw;
-  dim3 grid((Nyr + tw - 1) / tw, (Nx + rows - 1) / rows, (unsigned)n_img);
-  if (Nk == 5 && Nl == 5) kernel_spectrum_direct_kernel<5, 5><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr, log2tw);
-  else if (Nk == 3 && Nl == 3) kernel_spectrum_direct_kernel<3, 3><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr, log2tw);
-  else if (Nk == 7 && Nl == 7) kernel_spectrum_direct_kernel<7, 7><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr, log2tw);
-  else kernel_spectrum_direct_kernel<0, 0><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr, log2tw);
+  const int threads = 128, rows = 16;
+  dim3 grid((Nyr + threads - 1) / threads, (Nx + rows - 1) / rows, (unsigned)n_img);
+  if (Nk == 5 && Nl == 5) kernel_spectrum_direct_kernel<5, 5><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr, rows);
+  else if (Nk == 3 && Nl == 3) kernel_spectrum_direct_kernel<3, 3><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr, rows);
+  else if (Nk == 7 && Nl == 7) kernel_spectrum_direct_kernel<7, 7><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr, rows);
+  else kernel_spectrum_direct_kernel<0, 0><<<grid, threads, 0, ctx->stream>>>(taps, spec, Nx, Ny, Nk, Nl, twx, twy, col0, Nyr, rows);
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
   return AEFFT_OK;
@@ -674,7 +680,7 @@ int launch_kernel_spectrum_direct(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny,
 // order: per-thread sums over the rows, warp shuffles, shared memory), a second tiny kernel adds the splits --
 // deterministic.  A thread owns one column wy (its Ey factors stay in registers) and walks down the rows.
 template <int NK, int NL>
-__global__ void __launch_bounds__(256) spectrum_to_taps_kernel(const float2* __restrict__ spec, float* __restrict__ part, int Nx,
+__global__ void __launch_bounds__(768) spectrum_to_taps_kernel(const float2* __restrict__ spec, float* __restrict__ part, int Nx,
                                                                 int Ny, int Nk, int Nl, const float2* __restrict__ twx,
                                                                 const float2* __restrict__ twy, int col0, int Nyr) {
   constexpr int TK = NK ? NK : PD_MAXT, TL = NL ? NL : PD_MAXT;
@@ -686,32 +692,37 @@ __global__ void __launch_bounds__(256) spectrum_to_taps_kernel(const float2* __r
   float g[TK * TL];
 #pragma unroll
   for (int t = 0; t < TK * TL; t++) g[t] = 0.f;
+  // g[k][l] = sum over bins of h * Re( v * conj(Ex[k](wx)) * conj(Ey[l](wy)) ).  Ey depends on the column only, so the
+  // row sum b[k] = sum_wx v * conj(Ex[k]) (NK complex MACs per bin) is taken first and the NL column factors are applied
+  // once per column -- NK instead of NK * NL + NL multiply-adds per bin.
   for (int wl = threadIdx.x; wl < Nyr; wl += blockDim.x) {
     const int wy = col0 + wl;
     const float h = (wy == 0 || wy == Ny / 2) ? 1.f : 2.f;
-    float2 ey[TL];
+    float2 b[TK];
 #pragma unroll
-    for (int l = 0; l < TL; l++)
-      if (l < nl) ey[l] = __ldg(twy + ((wy * ((l - nl / 2) & (Ny - 1))) & (Ny - 1)));
+    for (int k = 0; k < TK; k++) b[k] = make_float2(0.f, 0.f);
     for (int wx = r_lo; wx < r_hi; wx++) {
-      float2 v = z[(size_t)wx * Nyr + wl];
-      v.x *= h; v.y *= h;
-      float2 a[TL];  // v * conj(Ey[l])
-#pragma unroll
-      for (int l = 0; l < TL; l++)
-        if (l < nl) a[l] = make_float2(v.x * ey[l].x + v.y * ey[l].y, v.y * ey[l].x - v.x * ey[l].y);
+      const float2 v = z[(size_t)wx * Nyr + wl];
 #pragma unroll
       for (int k = 0; k < TK; k++) {
         if (k < nk) {
-          const float2 e = __ldg(twx + ((wx * ((k - nk / 2) & (Nx - 1))) & (Nx - 1)));
-#pragma unroll
-          for (int l = 0; l < TL; l++)
-            if (l < nl) g[k * TL + l] += a[l].x * e.x + a[l].y * e.y;  // Re(a * conj(e))
+          const float2 e = __ldg(twx + ((wx * ((k - nk / 2) & (Nx - 1))) & (Nx - 1)));  // warp-uniform address
+          b[k].x = fmaf(v.x, e.x, fmaf(v.y, e.y, b[k].x));   // v * conj(e)
+          b[k].y = fmaf(v.y, e.x, fmaf(-v.x, e.y, b[k].y));
         }
       }
     }
+#pragma unroll
+    for (int l = 0; l < TL; l++) {
+      if (l < nl) {
+        const float2 ey = __ldg(twy + ((wy * ((l - nl / 2) & (Ny - 1))) & (Ny - 1)));
+#pragma unroll
+        for (int k = 0; k < TK; k++)
+          if (k < nk) g[k * TL + l] = fmaf(h, b[k].x * ey.x + b[k].y * ey.y, g[k * TL + l]);  // h * Re(b * conj(ey))
+      }
+    }
   }
-  __shared__ float red[8][TK * TL];
+  __shared__ float red[24][TK * TL];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
   for (int t = 0; t < TK * TL; t++) {
@@ -751,7 +762,10 @@ int launch_spectrum_to_taps(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int N
   int nsplit = (int)((4LL * ctx->sm_count + n_img - 1) / n_img);
   if (nsplit > Nx / 8) nsplit = Nx / 8;
   if (nsplit < 1) nsplit = 1;
-  const int threads = Nyr > 128 ? 256 : (Nyr > 64 ? 128 : 64);
+  // Half spectra have 2^k + 1 columns and a thread owns a column: size the CTA so that the columns need as few passes as
+  // possible (257 columns -> 288 threads, 513 -> 544) instead of a second pass for the Nyquist column alone.
+  const int passes = (Nyr + 767) / 768;
+  const int threads = (((Nyr + passes - 1) / passes) + 31) / 32 * 32;
   float* part;
   AE_TRY(ctx->getT("s2t_part", (size_t)n_img * nsplit * Nk * Nl, &part));
   {
