@@ -545,15 +545,16 @@ __global__ void __launch_bounds__(256) fft_rows_r2c_s(const float* __restrict__ 
   stockham_middle<-1, LOG2N, C::LOG2RP, 1, LR0, false>(src, tw, rs);
   __syncthreads();
   float2* o = out + img * (long long)Nx * Nyr;
-  for (int r = 0; r < RP; r++) {
+  // the RP row pairs of the CTA as ONE index space: a half spectrum has 2^k + 1 columns, so a per-row loop would spend a
+  // whole extra pass on the Nyquist column of every row
+  for (int idx = threadIdx.x; idx < RP * Nyr; idx += blockDim.x) {
+    const int r = idx / Nyr, k = idx - r * Nyr;  // Nyr is a compile-time constant
     const int row = 2 * (rp0 + r);
     if (row >= Nx) break;
-    for (int k = threadIdx.x; k < Nyr; k += blockDim.x) {
-      const float2 z1 = src[rs.addr(r, k)];
-      const float2 z2 = src[rs.addr(r, (Ny - k) & (Ny - 1))];
-      o[(long long)row * Nyr + k] = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
-      o[(long long)(row + 1) * Nyr + k] = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
-    }
+    const float2 z1 = src[rs.addr(r, k)];
+    const float2 z2 = src[rs.addr(r, (Ny - k) & (Ny - 1))];
+    o[(long long)row * Nyr + k] = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+    o[(long long)(row + 1) * Nyr + k] = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
   }
 }
 
