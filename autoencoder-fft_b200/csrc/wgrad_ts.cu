@@ -24,7 +24,7 @@
 //     the M = 128 block of an SS MMA (row replicas = descriptor arithmetic; no replication stage, no TMEM A ring).  Two
 //     forms of B: separate hi / lo planes (3 MMAs of N = 48 per plane) or one stacked swizzled plane [S_hi | S_lo]
 //     (2 MMAs of N = 16 * np * NL).  launch_wgrad_ts documents which shape takes which and the measurements behind it.
-// Roles (512 threads): warp 0 TMA producer, warps 2-3 S converters (+ sum e, e^2), warps 4-11 U converters (+ sum U),
+// Roles (512 threads): warps 0 / 1 TMA producers of the S / U rows, warps 2-3 S converters (+ sum e, e^2), warps 4-11 U converters (+ sum U),
 // warps 12-15 MMA issuers, warps 4-7 epilogue.
 #include <cstdio>
 #include <cstdlib>
@@ -78,6 +78,7 @@ struct WgradTsParams {
   int asmem, NUB, NUBT;      // ring positions, positions incl. the mirror of the first RS-1 (NUBT = NUB + RS - 1)
   uint32_t a_lbo, a_part;    // bytes between 8-pixel chunks (K core matrices), bytes between the hi and lo parts
   long long* dbg;  // AEFFT_TS_DEBUG: [cta][warp][8] cycles (wait A, wait B, total, work, work 2)
+  int skip;        // instrumented build only (AEFFT_TS_SKIP=mask): knock out 1 the S conversion, 2 the MMAs, 4 the U conversion
 };
 
 // S converter, one row: fp32 [channel][PJ + 4] (TMA box, halo origin at d_off) -> bf16 hi / lo rows [pixel][8 channels] of
@@ -210,14 +211,15 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
   const int n_items = (int)p.items, cpj = p.cpj;
 
   if (warp == 0) {
-    // ============================================================ TMA producer
+    // ============================================================ TMA producer of the S rows (one lane).  The U rows have
+    // their own producer (warp 1): one thread issuing both streams needed ~880 cycles per K-row (1-2 S boxes + PJ/32 U
+    // boxes + two waits) and was the slowest role of the bare pipeline; two threads also decouple the two streams.
     if (lane == 0) {
-      tma_prefetch_desc(&J.u_map);
       tma_prefetch_desc(&J.s0_map);
       if (J.has_s1) tma_prefetch_desc(&J.s1_map);
       const int cs_off = J.oj & ~3;  // aligned start column offset (the hardware needs 16-byte aligned inner coordinates)
       const uint32_t s_bytes = (uint32_t)(J.has_s1 ? 2 : 1) * J.nch * (p.PJ + 4) * 4;
-      Ring su(p.NU), ss(TS_NSF);
+      Ring ss(TS_NSF);
       for (int item = cta; item < n_items; item += cpj) {
         const int b = item / items_per_frame;
         const int rem = item - b * items_per_frame;
@@ -225,25 +227,37 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
         const int j0 = strip * p.TJ, i0 = (rem - strip * p.bands) * p.BR;
         const int nrows = min(p.BR, p.Nx - i0);
         const int n_srows = nrows + p.RS - 1 + Rmax;
+        const int col = j0 + cs_off, row0 = i0 + J.oi, plane = b * p.dD + J.ch0;
         for (int k = 0; k < n_srows; k++) {
-          {
-            wait_t<DBG>(&s_empty[ss.slot], ss.phase ^ 1, wA);
-            unsigned char* dst = s_ring + (size_t)ss.slot * p.s_slot_bytes;
-            mbar_expect_tx(&s_full[ss.slot], s_bytes);
-            tma_load_3d(dst, &J.s0_map, j0 + cs_off, i0 + J.oi + k, b * p.dD + J.ch0, &s_full[ss.slot]);
-            if (J.has_s1)
-              tma_load_3d(dst + p.s_src_bytes, &J.s1_map, j0 + cs_off, i0 + J.oi + k, b * p.dD + J.ch0, &s_full[ss.slot]);
-            ss.next();
-          }
-          const int ru = k - Rmax;
-          if (ru >= 0 && ru < nrows) {
-            wait_t<DBG>(&u_empty[su.slot], su.phase ^ 1, wB);
-            unsigned char* dst = u_ring + (size_t)su.slot * p.u_slot_bytes;
-            mbar_expect_tx(&u_full[su.slot], p.u_slot_bytes);
-            for (int sub = 0; sub < p.PJ / 32; sub++)
-              tma_load_3d(dst + (size_t)sub * CU * 128, &J.u_map, j0 + sub * 32, i0 + ru, b * CU, &u_full[su.slot]);
-            su.next();
-          }
+          wait_t<DBG>(&s_empty[ss.slot], ss.phase ^ 1, wA);
+          unsigned char* dst = s_ring + (size_t)ss.slot * p.s_slot_bytes;
+          mbar_expect_tx(&s_full[ss.slot], s_bytes);
+          tma_load_3d(dst, &J.s0_map, col, row0 + k, plane, &s_full[ss.slot]);
+          if (J.has_s1) tma_load_3d(dst + p.s_src_bytes, &J.s1_map, col, row0 + k, plane, &s_full[ss.slot]);
+          ss.next();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ TMA producer of the U rows (one lane)
+    if (lane == 0) {
+      tma_prefetch_desc(&J.u_map);
+      Ring su(p.NU);
+      const int n_sub = p.PJ / 32;
+      for (int item = cta; item < n_items; item += cpj) {
+        const int b = item / items_per_frame;
+        const int rem = item - b * items_per_frame;
+        const int strip = rem / p.bands;
+        const int j0 = strip * p.TJ, i0 = (rem - strip * p.bands) * p.BR;
+        const int nrows = min(p.BR, p.Nx - i0);
+        const int plane = b * CU;
+        for (int ru = 0; ru < nrows; ru++) {
+          wait_t<DBG>(&u_empty[su.slot], su.phase ^ 1, wB);
+          unsigned char* dst = u_ring + (size_t)su.slot * p.u_slot_bytes;
+          mbar_expect_tx(&u_full[su.slot], p.u_slot_bytes);
+          for (int sub = 0; sub < n_sub; sub++)
+            tma_load_3d(dst + (size_t)sub * CU * 128, &J.u_map, j0 + sub * 32, i0 + ru, plane, &u_full[su.slot]);
+          su.next();
         }
       }
     }
@@ -307,7 +321,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
           if (mine) {
             fence_after_sync();
             const long long t_m0 = DBG ? clock64() : 0;
-            if (elect_one()) {
+            if (elect_one() && !(DBG && (p.skip & 2))) {
               // one lane walks the (K-step, window-row group, plane) nest; operands advance by constant increments
               const uint32_t pl_step16 = (uint32_t)NSB * pitch16;
               // A operand: TMEM chunk columns, or the shared-memory descriptor of rows upos .. upos+RS-1, 8-px chunk 8h
@@ -385,8 +399,6 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
       sb_row = 0;
     }
     if (elect_one()) commit(&done_bar);
-  } else if (warp == 1) {
-    // spare warp
   } else if (warp < 4) {
     // ============================================================ S converters (64 threads)
     const int t = tid - 64;
@@ -411,7 +423,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
         const float* s1 = reinterpret_cast<const float*>(s_ring + (size_t)ss.slot * p.s_slot_bytes + p.s_src_bytes);
         const bool own_row = is_gf && (k + oi >= 0) && (k + oi < nrows);
         const long long t_c0 = DBG ? clock64() : 0;
-        if (PJ == 128)
+        if (DBG && (p.skip & 1)) {
+        } else if (PJ == 128)
           s_convert_row<128>(s0, s1, t, p.np, nch, has_s1, own_row, oj, TJ, d_off, fs, fq, sb_ring, sb.slot, p.NSB, p.sb_pitch,
                              lo_part, p.stack != 0);
         else
@@ -484,7 +497,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
           wait_t<DBG>(&ub_empty[upos], mirror ? uph : uph ^ 1, wB);
           const long long t_c0 = DBG ? clock64() : 0;
           const unsigned char* urow = u_ring + (size_t)ru_ring2.slot * p.u_slot_bytes;
-          for (int unit = t256; unit < n_units; unit += 256) {
+          for (int unit = t256; unit < ((DBG && (p.skip & 4)) ? 0 : n_units); unit += 256) {
             const int kc = unit >> cu_shift, mm = unit & (CU - 1);
             uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
             if (real) {
@@ -537,7 +550,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1) wgrad_ts_kernel(const __grid_co
             const long long t_c0 = DBG ? clock64() : 0;
             const unsigned char* urow = u_ring + (size_t)ru_ring.slot * p.u_slot_bytes;
             unsigned char* dst_hi = ub + (size_t)(r & (RS - 1)) * 2 * ub_part;
-            for (int unit = t256; unit < n_units; unit += 256) {
+            for (int unit = t256; unit < ((DBG && (p.skip & 4)) ? 0 : n_units); unit += 256) {
               const int mm = unit >> upm_shift, u8 = unit & (units_per_m - 1);
               const int px0 = u8 * 8, sub = px0 >> 5, g0 = (px0 & 31) >> 2;
               const unsigned char* src = urow + (size_t)sub * CU * 128 + (size_t)mm * 128;
@@ -881,6 +894,7 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   }
   const bool debug = getenv("AEFFT_TS_DEBUG") != nullptr;
   p.dbg = nullptr;
+  p.skip = (debug && getenv("AEFFT_TS_SKIP")) ? atoi(getenv("AEFFT_TS_SKIP")) : 0;
   const size_t n_dbg = (size_t)cpj * p.n_jobs * 16 * 8;
   if (debug) {
     AE_TRY(ctx->getT("wgts_dbg", n_dbg, &p.dbg));
