@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import oracle_np as O
-from conftest import GOLDEN
+from conftest import GOLDEN, ROOT
 
 G = np.load(os.path.join(GOLDEN, "cpu_golden.npz"))
 
@@ -153,6 +153,36 @@ def test_product_saveload_conv_is_byte_exact(tmp_path):
     assert np.array_equal(c2, c) and np.array_equal(b2, b)
     with pytest.raises(A.AefftError):  # unlike the reference (silent zeros, N5) a missing file is an error
         A.saveload_conv(tmp_path, c2, b2, 2, 7, 1, 0)
+
+
+def test_weight_file_tool_round_trips_with_the_library(tmp_path):
+    """tools/weights.py (analysis-side reader / writer of the reference's weight files) against aefft_saveload_conv."""
+    import sys
+
+    import aefft_ctypes as A
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import weights as W
+
+    c, b = np.ascontiguousarray(G["conv_a_c"]), np.ascontiguousarray(G["conv_a_b"])
+    A.saveload_conv(tmp_path, c, b, 2, 3, 1, 1)  # written by the library ...
+    (name,) = os.listdir(tmp_path)
+    meta = W.parse_name(name)
+    assert (meta["L"], meta["io"], meta["scale"]) == (3, 1, 2) and (meta["dM"], meta["dD"], meta["Nk"], meta["Nl"]) == c.shape
+    c2, b2, _ = W.read_conv(tmp_path / name)  # ... read by the tool
+    assert np.array_equal(c2, c) and np.array_equal(b2, b)
+    other = tmp_path / "w2"
+    other.mkdir()
+    path = W.write_conv(other, c, b, 2, 3, 1)  # written by the tool: same name, same bytes ...
+    assert os.path.basename(path) == name and open(path, "rb").read() == (tmp_path / name).read_bytes()
+    c3, b3 = np.zeros_like(c), np.zeros_like(b)
+    A.saveload_conv(other, c3, b3, 2, 3, 1, 0)  # ... read back by the library
+    assert np.array_equal(c3, c) and np.array_equal(b3, b)
+    with open(path, "ab") as fh:
+        fh.write(b"\0\0\0\0")
+    with pytest.raises(ValueError):
+        W.read_conv(path)  # size and name disagree
+    assert W.main(["weights.py", str(tmp_path)]) == 0
 
 
 def test_product_load_param(tmp_path):
