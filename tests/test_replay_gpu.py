@@ -73,9 +73,17 @@ def replica(ctx, tmp):
     return out
 
 
-def test_replay_driver_matches_the_same_calls_through_ctypes(ctx, tmp_path):
+def driver_exe():
+    """The driver binary of the Makefile; rebuilt from its single source if the tree came without it."""
     exe = os.path.join(PKG, "aefft_replay")
-    assert os.path.exists(exe), "aefft_replay not built (make -C autoencoder-fft_b200)"
+    if not os.path.exists(exe):
+        subprocess.run(["g++", "-O2", "-std=c++11", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                        os.path.join(PKG, "tools", "aefft_replay.cpp"), "-L", PKG, "-laefft", f"-Wl,-rpath,{PKG}"], check=True)
+    return exe
+
+
+def test_replay_driver_matches_the_same_calls_through_ctypes(ctx, tmp_path):
+    exe = driver_exe()
     (tmp_path / "New_Layer_Param.txt").write_text(PARAM)
     (tmp_path / "weights").mkdir()
     run = subprocess.run([exe, "--frames", str(B), "--size", f"{NX}x{NY}", "--channels", str(D), "--seed", "1234", "--param",
@@ -98,7 +106,7 @@ def test_replay_driver_matches_the_same_calls_through_ctypes(ctx, tmp_path):
 
 
 def test_replay_driver_reports_errors(tmp_path):
-    exe = os.path.join(PKG, "aefft_replay")
+    exe = driver_exe()
     run = subprocess.run([exe, "--size", "32x32", "--param", str(tmp_path / "missing.txt"), "--script", "n"],
                          capture_output=True, text=True, timeout=120)
     assert run.returncode == 1 and "aefft_replay" in run.stderr
