@@ -55,10 +55,9 @@ __global__ void __launch_bounds__((AB / 8) * XB * NK * WTI) wgrad_kernel(WgradPa
   constexpr int XCP = XCP0 + ((8 - XCP0 % 32) + 32) % 32;  // channel pitch == 8 (mod 32): spreads (x,tk) over banks
   constexpr int XV = (4 + NL - 1 + 3) / 4;
   constexpr int A_FLOATS = AB * WTI * WTJ;
-  constexpr int X_FLOATS = XB * XCP;
   extern __shared__ __align__(16) float smem[];
   float* as = smem;             // [AB][WTI][WTJ]
-  float* xs = smem + A_FLOATS;  // [XB][XCP] rows of PJ
+  float* xs = smem + A_FLOATS;  // [XB][XCP] rows of PJ (XB * XCP floats)
 
   const int tid = threadIdx.x;
   const int g = tid / NT, task = tid % NT;
