@@ -85,16 +85,18 @@ __global__ void pool_down2_kernel(const float4* __restrict__ in, float4* __restr
   o.w = red(a1.z, a1.w, b1.z, b1.w);
   out[n] = o;
 }
-// up: one thread = 4 input pixels of one row -> 2 output rows x 8 pixels
-__global__ void pool_up2_kernel(const float4* __restrict__ in, float4* __restrict__ out, unsigned total, int Nx, int w4) {
+// up: one thread = 2 input pixels of one row -> 2 output rows x 4 pixels: every store instruction of a warp then writes
+// 512 contiguous bytes (full 32-byte sectors); with 4 input pixels per thread the two 16-byte halves of a sector came
+// from two different store instructions.
+__global__ void pool_up2_kernel(const float2* __restrict__ in, float4* __restrict__ out, unsigned total, int Nx, int w2) {
   const unsigned n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= total) return;
-  const unsigned q = n % (unsigned)w4, r = n / (unsigned)w4;  // r = plane * Nx + i
-  const float4 v = __ldg(in + n);
-  const float4 lo = make_float4(v.x, v.x, v.y, v.y), hi = make_float4(v.z, v.z, v.w, v.w);
-  const size_t dst = (size_t)r * 4 * w4 + 2 * q;  // output row 2*(plane*Nx+i), 2*w4 float4 per output row
-  out[dst] = lo; out[dst + 1] = hi;
-  out[dst + 2 * w4] = lo; out[dst + 2 * w4 + 1] = hi;
+  const unsigned q = n % (unsigned)w2, r = n / (unsigned)w2;  // r = plane * Nx + i
+  const float2 v = __ldg(in + n);
+  const float4 o = make_float4(v.x, v.x, v.y, v.y);
+  const size_t dst = (size_t)r * 2 * w2 + q;  // output row 2*(plane*Nx+i), w2 float4 per output row
+  out[dst] = o;
+  out[dst + w2] = o;
 }
 
 int launch_pool(aefft_ctx* ctx, int64_t B, int D, int Nx, int Ny, int oNx, int oNy, int scale, const float* in,
@@ -109,10 +111,10 @@ int launch_pool(aefft_ctx* ctx, int64_t B, int D, int Nx, int Ny, int oNx, int o
     const unsigned n4 = (unsigned)(total / 4);
     pool_down2_kernel<<<(n4 + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(in),
                                                                 reinterpret_cast<float4*>(out), n4, oNx, oNy / 4, Ny / 4);
-  } else if (scale == -2 && al16 && oNx == 2 * Nx && oNy == 2 * Ny && Ny % 4 == 0 && total / 16 < 0xffffffffLL) {
-    const unsigned n4 = (unsigned)(planes * Nx * (Ny / 4));
-    pool_up2_kernel<<<(n4 + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(in),
-                                                              reinterpret_cast<float4*>(out), n4, Nx, Ny / 4);
+  } else if (scale == -2 && al16 && oNx == 2 * Nx && oNy == 2 * Ny && Ny % 4 == 0 && total / 4 < 0xffffffffLL) {
+    const unsigned n2 = (unsigned)(planes * Nx * (Ny / 2));
+    pool_up2_kernel<<<(n2 + 255) / 256, 256, 0, ctx->stream>>>(reinterpret_cast<const float2*>(in),
+                                                              reinterpret_cast<float4*>(out), n2, Nx, Ny / 2);
   } else if (scale > 0) {
     pool_down_kernel<<<blocks, 256, 0, ctx->stream>>>(in, out, planes, Nx, Ny, oNx, oNy, scale);
   } else {
