@@ -17,6 +17,13 @@
 //     zeroed accumulator slot back.  All MMAs accumulate; the halo is paid once per band.
 // fp32 parity: BF16X3 (A_hi W_hi + A_hi W_lo + A_lo W_hi, fp32 accumulation) as in conv_tc.cu.
 // Roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-7 converters, warps 8-11 epilogue.
+// Per layer shape launch_conv_rs also picks (each choice is documented where it is made, and forced in the tests):
+//   * 1, 2 or 3 CTAs per SM (512 / 256 / 128 TMEM columns, a share of the shared memory each);
+//   * the K packing: 16 channels, two window columns x 8 channels (C <= 8), or (window column, channel) when a whole
+//     window row fits in K = 16 (the 3-channel input layer: one MMA triple per input row);
+//   * the N packing: output channels padded to 16 per window row, or (window column, output) for few-output layers (the
+//     3-channel reconstruction layer), whose column groups the epilogue adds across lanes through shared memory;
+//   * one or two input rows per pipeline unit (barrier round trip of producer, converters and issuer).
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
