@@ -24,6 +24,15 @@ void set_error(const char* fmt, ...) {
 
 using namespace aefft;
 
+int aefft_ctx::ensure_dyn_smem(const void* func, size_t bytes) {
+  size_t& have = dyn_smem[func];
+  if (bytes > have) {
+    AE_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+  return AEFFT_OK;
+}
+
 int aefft_ctx::get(const char* name, size_t bytes, void** out) {
   Scratch& s = scratch[name];
   if (s.cap < bytes) {
@@ -95,6 +104,7 @@ struct Stage {
     float* d;
     AE_TRY(ctx->getT(name, count, &d));
     if (upload) AE_CUDA(cudaMemcpyAsync(d, p, count * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    AE_ARG(n_out < (int)(sizeof(outs) / sizeof(outs[0])));
     outs[n_out++] = {p, d, count * sizeof(float)};
     *dev = d;
     return AEFFT_OK;
@@ -473,14 +483,20 @@ int aefft_backprop_coord(aefft_ctx* ctx, int loc, int mode, int quirks, int64_t 
   AE_TRY(st.inout("bp_b", b, dM, &d_b));
   AE_TRY(st.inout("bp_f", f, nC, &d_f));
   AE_TRY(st.inout("bp_p", p, dD, &d_p));
-  AE_TRY(st.inout("bp_dc", dc, nC, &d_dc));
-  AE_TRY(st.inout("bp_db", db, dM, &d_db));
-  AE_TRY(st.inout("bp_df", df, nC, &d_df));
-  AE_TRY(st.inout("bp_dp", dp, dD, &d_dp));
-  AE_TRY(st.inout("bp_ddc", ddc, nC, &d_ddc, false));
-  AE_TRY(st.inout("bp_ddb", ddb, dM, &d_ddb, false));
-  AE_TRY(st.inout("bp_ddf", ddf, nC, &d_ddf, mode == AEFFT_MODE_CUDA_REF_SYM));  // untouched in the tied path
-  AE_TRY(st.inout("bp_ddp", ddp, dD, &d_ddp, false));
+  // momentum (dc..dp) and last-gradient (ddc..ddp) buffers exist only in the CUDA modes (backproplib.cu:387-412); the CPU
+  // path (netlib.cpp:437-444) has neither, so they are neither staged nor written back there
+  const bool cuda_mode = mode != AEFFT_MODE_CPU_REF;
+  d_dc = d_db = d_df = d_dp = d_ddc = d_ddb = d_ddf = d_ddp = nullptr;
+  if (cuda_mode || loc == AEFFT_DEVICE) {
+    AE_TRY(st.inout("bp_dc", dc, nC, &d_dc));
+    AE_TRY(st.inout("bp_db", db, dM, &d_db));
+    AE_TRY(st.inout("bp_df", df, nC, &d_df));
+    AE_TRY(st.inout("bp_dp", dp, dD, &d_dp));
+    AE_TRY(st.inout("bp_ddc", ddc, nC, &d_ddc, false));
+    AE_TRY(st.inout("bp_ddb", ddb, dM, &d_ddb, false));
+    AE_TRY(st.inout("bp_ddf", ddf, nC, &d_ddf, mode == AEFFT_MODE_CUDA_REF_SYM));  // untouched in the tied path
+    AE_TRY(st.inout("bp_ddp", ddp, dD, &d_ddp, false));
+  }
   float* gbuf;
   AE_TRY(ctx->getT("bp_gbuf", (size_t)gbuf_len(mode, dD, dM, Nk, Nl), &gbuf));
   float* mse_dev;

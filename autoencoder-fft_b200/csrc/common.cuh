@@ -68,6 +68,10 @@ struct aefft_ctx {
   cudaEvent_t get_event();
   std::map<std::string, aefft::Scratch> scratch;
   std::map<std::string, aefft::Scratch> pinned;
+  // cudaFuncAttributeMaxDynamicSharedMemorySize already raised on THIS ctx's device, per kernel function (the attribute
+  // is per device: a process-wide "already set" flag would leave the kernels of a second device at the 48 KB default)
+  std::map<const void*, size_t> dyn_smem;
+  int ensure_dyn_smem(const void* func, size_t bytes);
 
   int get(const char* name, size_t bytes, void** out);         // device scratch
   int get_pinned(const char* name, size_t bytes, void** out);  // pinned host staging

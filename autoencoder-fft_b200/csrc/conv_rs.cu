@@ -607,12 +607,8 @@ int launch_conv_rs(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
     AE_TRY(ctx->getT("rs_dbg", n_dbg, &p.dbg));
     AE_CUDA(cudaMemsetAsync(p.dbg, 0, n_dbg * sizeof(long long), ctx->stream));
   }
-  static size_t attr = 0;
-  if (smem > attr) {
-    AE_CUDA(cudaFuncSetAttribute(conv_rs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AE_CUDA(cudaFuncSetAttribute(conv_rs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  AE_TRY(ctx->ensure_dyn_smem((const void*)conv_rs_kernel<false>, smem));
+  AE_TRY(ctx->ensure_dyn_smem((const void*)conv_rs_kernel<true>, smem));
   {
     const double px = (double)B * Nx * Ny;
     ProfScope prof(ctx, win.flip ? "conv_fwd_rs" : "conv_dgrad_rs", 2.0 * px * C * O * win.Nk * win.Nl,

@@ -282,11 +282,7 @@ int launch_conv_tc(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O, i
     ctx->launches++;
   }
   p.wprep = reinterpret_cast<const uint4*>(wprep);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    AE_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_smem = 227 * 1024;
-  }
+  AE_TRY(ctx->ensure_dyn_smem((const void*)conv_tc_kernel, 227 * 1024));
   const double px = (double)B * Nx * Ny;
   ProfScope prof(ctx, win.flip ? "conv_fwd_tc" : "conv_dgrad_tc", 2.0 * px * C * O * p.T,
                  4.0 * (px * C * (src1 ? 2 : 1) + px * O + (double)C * O * p.T));

@@ -254,11 +254,7 @@ int launch_conv_tc_ws(aefft_ctx* ctx, const Window& win, int64_t B, int C, int O
   AE_TRY(ctx->get(win.flip ? "tc_wprep_f" : "tc_wprep_t", (size_t)total * 2 * sizeof(__nv_bfloat16), &wprep));
   conv_weight_prep(ctx, w, w_so, w_sc, C, O, N, win.Nk, win.Nl, win.flip, KS, kpack, wprep, total);
   p.wprep = reinterpret_cast<const uint4*>(wprep);
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    AE_CUDA(cudaFuncSetAttribute(conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  AE_TRY(ctx->ensure_dyn_smem((const void*)conv_tc_ws_kernel, smem));
   const double px = (double)B * Nx * Ny;
   ProfScope prof(ctx, win.flip ? "conv_fwd_tc" : "conv_dgrad_tc", 2.0 * px * C * O * win.Nk * win.Nl,
                  4.0 * (px * C * (src1 ? 2 : 1) + px * O + (double)C * O * win.Nk * win.Nl));

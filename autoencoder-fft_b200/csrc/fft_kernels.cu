@@ -671,16 +671,14 @@ static int run_rows_r2c(aefft_ctx* ctx, int64_t batch, int Nx, const float* in, 
                         long long fstride) {
   if (!getenv("AEFFT_FFT_V1")) {
     using S = SRowCfg<LOG2N>;
-    static bool attr_s = false;
-    if (!attr_s) { AE_CUDA(cudaFuncSetAttribute(fft_rows_r2c_s<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem)); attr_s = true; }
+    AE_TRY(ctx->ensure_dyn_smem((const void*)fft_rows_r2c_s<LOG2N>, S::smem));
     dim3 grid_s((Nx / 2 + S::RP - 1) / S::RP, (unsigned)batch);
     fft_rows_r2c_s<LOG2N><<<grid_s, 256, S::smem, ctx->stream>>>(in, out, Nx, tw, ch, fstride);
     return AEFFT_OK;
   }
   if (fstride != (long long)ch * Nx * (1 << LOG2N)) return AEFFT_ERR_UNSUPPORTED;
   using C = RowCfg<LOG2N>;
-  static bool attr = false;
-  if (!attr) { AE_CUDA(cudaFuncSetAttribute(fft_rows_r2c_t<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem)); attr = true; }
+  AE_TRY(ctx->ensure_dyn_smem((const void*)fft_rows_r2c_t<LOG2N>, C::smem));
   dim3 grid((Nx / 2 + C::RP - 1) / C::RP, (unsigned)batch);
   fft_rows_r2c_t<LOG2N><<<grid, 256, C::smem, ctx->stream>>>(in, out, Nx, tw);
   return AEFFT_OK;
@@ -690,16 +688,14 @@ static int run_rows_c2r(aefft_ctx* ctx, int64_t batch, int Nx, const float2* in,
                         int ch, long long fstride) {
   if (!getenv("AEFFT_FFT_V1")) {
     using S = SRowCfg<LOG2N>;
-    static bool attr_s = false;
-    if (!attr_s) { AE_CUDA(cudaFuncSetAttribute(fft_rows_c2r_s<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem)); attr_s = true; }
+    AE_TRY(ctx->ensure_dyn_smem((const void*)fft_rows_c2r_s<LOG2N>, S::smem));
     dim3 grid_s((Nx / 2 + S::RP - 1) / S::RP, (unsigned)batch);
     fft_rows_c2r_s<LOG2N><<<grid_s, 256, S::smem, ctx->stream>>>(in, out, Nx, tw, scale, ch, fstride);
     return AEFFT_OK;
   }
   if (fstride != (long long)ch * Nx * (1 << LOG2N)) return AEFFT_ERR_UNSUPPORTED;
   using C = RowCfg<LOG2N>;
-  static bool attr = false;
-  if (!attr) { AE_CUDA(cudaFuncSetAttribute(fft_rows_c2r_t<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem)); attr = true; }
+  AE_TRY(ctx->ensure_dyn_smem((const void*)fft_rows_c2r_t<LOG2N>, C::smem));
   dim3 grid((Nx / 2 + C::RP - 1) / C::RP, (unsigned)batch);
   fft_rows_c2r_t<LOG2N><<<grid, 256, C::smem, ctx->stream>>>(in, out, Nx, tw, scale);
   return AEFFT_OK;
@@ -709,15 +705,13 @@ static int run_cols(aefft_ctx* ctx, int64_t batch, int W, const float2* in, floa
   if (!getenv("AEFFT_FFT_V1")) {
     // in place is fine: a CTA owns its CT columns, reads all of them in the first pass and writes them in the last
     using S = SColCfg<LOG2N>;
-    static bool attr_s = false;
-    if (!attr_s) { AE_CUDA(cudaFuncSetAttribute(fft_cols_s<DIR, LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem)); attr_s = true; }
+    AE_TRY(ctx->ensure_dyn_smem((const void*)fft_cols_s<DIR, LOG2N>, S::smem));
     dim3 grid_s((W + S::CT - 1) / S::CT, (unsigned)batch);
     fft_cols_s<DIR, LOG2N><<<grid_s, 256, S::smem, ctx->stream>>>(in, out, W, tw);
     return AEFFT_OK;
   }
   using C = ColCfg<LOG2N>;
-  static bool attr = false;
-  if (!attr) { AE_CUDA(cudaFuncSetAttribute(fft_cols_t<DIR, LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem)); attr = true; }
+  AE_TRY(ctx->ensure_dyn_smem((const void*)fft_cols_t<DIR, LOG2N>, C::smem));
   dim3 grid((W + C::CT - 1) / C::CT, (unsigned)batch);
   fft_cols_t<DIR, LOG2N><<<grid, 256, C::smem, ctx->stream>>>(in, out, W, tw);
   return AEFFT_OK;

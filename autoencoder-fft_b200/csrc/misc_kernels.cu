@@ -257,7 +257,7 @@ __global__ void quirk_dF_main_kernel(const float* __restrict__ out, const float*
 __global__ void quirk_dF_stale_kernel(const float* __restrict__ out, const float* __restrict__ in,
                                       const float* __restrict__ hin, float* __restrict__ gF, long long B, int dD,
                                       int dM, int Nx, int Ny, int Nk, int Nl, int bi, int bj, int c3, int n_border,
-                                      const int* __restrict__ border) {
+                                      int ilo, int ihi, int jlo, int jhi) {
   long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = n < B * n_border;
   const long long plane = (long long)Nx * Ny;
@@ -265,10 +265,23 @@ __global__ void quirk_dF_stale_kernel(const float* __restrict__ out, const float
   long long b = 0;
   int i = 0, j = 0;
   if (active) {
+    // border pixel q of the frame, enumerated without a list: full rows i < ilo, then the column bands j < jlo / j >= jhi
+    // of the rows [ilo, ihi), then full rows i >= ihi (the host passes ilo == ihi == Nx / jlo == jhi == Ny when every
+    // row / column is excluded by some tap)
     b = n / n_border;
-    int pix = border[n % n_border];
-    i = pix / Ny;
-    j = pix % Ny;
+    int q = (int)(n % n_border);
+    const int n_top = ilo * Ny, per_mid = jlo + (Ny - jhi), n_mid = (ihi - ilo) * per_mid;
+    if (q < n_top) {
+      i = q / Ny; j = q - i * Ny;
+    } else if (q < n_top + n_mid) {
+      q -= n_top;
+      const int r = q / per_mid, t = q - r * per_mid;
+      i = ilo + r; j = t < jlo ? t : jhi + (t - jlo);
+    } else {
+      q -= n_top + n_mid;
+      const int r = q / Ny;
+      i = ihi + r; j = q - r * Ny;
+    }
   }
   float last = 0.f;
   const int lane = threadIdx.x & 31;
@@ -309,26 +322,23 @@ int launch_quirk_dF(aefft_ctx* ctx, int quirks, int64_t B, int dD, int dM, int N
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
   if (quirks & AEFFT_QUIRK_C4) {
-    // border pixel list (host-built, tiny): pixels excluded by the mask of at least one tap
-    std::vector<int> border;
-    const int ilo = bi + Nk - 1 > 0 ? bi + Nk - 1 : 0;    // i < ilo is excluded by the largest ik
-    const int ihi = bi < 0 ? Nx + bi : Nx;                // i >= ihi is excluded by the smallest ik
-    const int jlo = bj + Nl - 1 > 0 ? bj + Nl - 1 : 0;
-    const int jhi = bj < 0 ? Ny + bj : Ny;
-    for (int i = 0; i < Nx; i++)
-      for (int j = 0; j < Ny; j++)
-        if (i < ilo || i >= ihi || j < jlo || j >= jhi) border.push_back(i * Ny + j);
-    const int nb = (int)border.size();
+    // border pixels = those excluded by the mask of at least one tap; the kernel enumerates them from the four bounds
+    // (no host-built list: a pinned staging buffer rewritten per pair raced with the previous pair's async copy)
+    int ilo = bi + Nk - 1 > 0 ? bi + Nk - 1 : 0;    // i < ilo is excluded by the largest ik
+    int ihi = bi < 0 ? Nx + bi : Nx;                // i >= ihi is excluded by the smallest ik
+    int jlo = bj + Nl - 1 > 0 ? bj + Nl - 1 : 0;
+    int jhi = bj < 0 ? Ny + bj : Ny;
+    if (ilo > Nx) ilo = Nx;
+    if (jlo > Ny) jlo = Ny;
+    if (ihi <= ilo) ilo = ihi = Nx;                 // every row is a border row
+    if (jhi <= jlo) jlo = jhi = Ny;                 // every column is a border column
+    const long long nb = (long long)ilo * Ny + (long long)(ihi - ilo) * (jlo + Ny - jhi) + (long long)(Nx - ihi) * Ny;
     if (nb > 0) {
-      int* dev = nullptr;
-      AE_TRY(ctx->getT("quirk_border", (size_t)nb, &dev));
-      void* pin = nullptr;
-      AE_TRY(ctx->get_pinned("quirk_border_h", (size_t)nb * sizeof(int), &pin));
-      memcpy(pin, border.data(), (size_t)nb * sizeof(int));
-      AE_CUDA(cudaMemcpyAsync(dev, pin, (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+      AE_ARG(nb <= 0x7fffffffLL);
       long long total = (long long)B * nb;
       quirk_dF_stale_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(out, in, hin, gF, B, dD, dM, Nx,
-                                                                                    Ny, Nk, Nl, bi, bj, c3, nb, dev);
+                                                                                    Ny, Nk, Nl, bi, bj, c3, (int)nb, ilo,
+                                                                                    ihi, jlo, jhi);
       ctx->launches++;
       AE_CUDA(cudaGetLastError());
     }

@@ -102,6 +102,14 @@ int aefft_net_create(aefft_ctx* ctx, aefft_net** out, int D, int Nx, int Ny, int
   return AEFFT_OK;
 }
 
+// The reference zero-initialises its momentum / last-gradient vectors THROUGH Init_conv(..., 0) (autoencoder.cpp:103-107 at
+// start-up, and in the 'n', 'z', 'x', 'd' handlers :288-292, :424-428, :447-451), which still draws one rand() per element.
+// Burning the same number of draws keeps every later Init_conv on the reference's rand() stream for a given srand seed.
+static void burn_zero_init_draws(int dM, int dD, int Nk, int Nl) {
+  const long long nC = (long long)dM * dD * Nk * Nl;
+  for (long long i = 0; i < 2 * (nC + dM) + 2 * (nC + dD); i++) (void)rand();
+}
+
 int aefft_net_destroy(aefft_net* net) {
   if (!net) return AEFFT_OK;
   cudaSetDevice(net->ctx->device);
@@ -128,28 +136,42 @@ int aefft_net_add_layer(aefft_net* net, int dM, int Lk, int Ll, int scal, float 
   AE_ARG(dNx / scal > 0 && dNy / scal > 0);
   LayerL Pin{dD, dNx / scal, dNy / scal, nullptr}, hC{dM, dNx / scal, dNy / scal, nullptr},
       PhC{dD, dNx / scal, dNy / scal, nullptr}, outn{dD, dNx, dNy, nullptr};
-  AE_TRY(alloc_layer(net, Pin)); AE_TRY(alloc_layer(net, hC)); AE_TRY(alloc_layer(net, PhC)); AE_TRY(alloc_layer(net, outn));
+  const size_t nC = (size_t)dM * dD * Nk * Nl;
+  // draw the weights first (host only), then allocate EVERYTHING, and only then commit to the net's vectors: a failed
+  // allocation frees what this call allocated and leaves layers / convs / pairs exactly as they were
+  std::vector<float> c(nC), b(dM), f(nC), p(dD);
+  AE_TRY(aefft_init_conv(c.data(), b.data(), dM, dD, Nk, Nl, rmax));
+  AE_TRY(aefft_init_conv(f.data(), p.data(), dD, dM, Nk, Nl, rmax));
+  burn_zero_init_draws(dM, dD, Nk, Nl);  // Init_conv(dc/df/ddc/ddf, ..., 0) (:103-107, :424-428)
+  ConvL enc{dM, dD, Nk, Nl, scal}, dec{dD, dM, Nk, Nl, -scal};
+  PairState st;
+  auto build = [&]() -> int {
+    AE_TRY(alloc_layer(net, Pin)); AE_TRY(alloc_layer(net, hC)); AE_TRY(alloc_layer(net, PhC)); AE_TRY(alloc_layer(net, outn));
+    AE_TRY(dev_alloc(&enc.c, nC)); AE_TRY(dev_alloc(&enc.b, dM));
+    AE_TRY(dev_alloc(&dec.c, nC)); AE_TRY(dev_alloc(&dec.b, dD));
+    AE_TRY(upload(ctx, enc.c, c.data(), nC)); AE_TRY(upload(ctx, enc.b, b.data(), dM));
+    AE_TRY(upload(ctx, dec.c, f.data(), nC)); AE_TRY(upload(ctx, dec.b, p.data(), dD));
+    AE_TRY(alloc_pair_state(net, st, dM, dD, Nk, Nl));
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
+    return AEFFT_OK;
+  };
+  const int rc = build();
+  if (rc != AEFFT_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    dev_free(Pin.p); dev_free(hC.p); dev_free(PhC.p); dev_free(outn.p);
+    dev_free(enc.c); dev_free(enc.b); dev_free(dec.c); dev_free(dec.b);
+    free_pair_state(st);
+    return rc;
+  }
   if (net->layers.size() == 1) {
     // first pair: layers = in, Pin, hC, PhC, out (:108-112)
     net->layers.push_back(Pin); net->layers.push_back(hC); net->layers.push_back(PhC); net->layers.push_back(outn);
   } else {
     net->layers.insert(net->layers.begin() + n + 1, {Pin, hC, PhC, outn});
   }
-  const size_t nC = (size_t)dM * dD * Nk * Nl;
-  std::vector<float> c(nC), b(dM), f(nC), p(dD);
-  AE_TRY(aefft_init_conv(c.data(), b.data(), dM, dD, Nk, Nl, rmax));
-  AE_TRY(aefft_init_conv(f.data(), p.data(), dD, dM, Nk, Nl, rmax));
-  ConvL enc{dM, dD, Nk, Nl, scal}, dec{dD, dM, Nk, Nl, -scal};
-  AE_TRY(dev_alloc(&enc.c, nC)); AE_TRY(dev_alloc(&enc.b, dM));
-  AE_TRY(dev_alloc(&dec.c, nC)); AE_TRY(dev_alloc(&dec.b, dD));
-  AE_TRY(upload(ctx, enc.c, c.data(), nC)); AE_TRY(upload(ctx, enc.b, b.data(), dM));
-  AE_TRY(upload(ctx, dec.c, f.data(), nC)); AE_TRY(upload(ctx, dec.b, p.data(), dD));
   const int mid = (int)net->convs.size() / 2;
   net->convs.insert(net->convs.begin() + mid, {enc, dec});
-  PairState st;
-  AE_TRY(alloc_pair_state(net, st, dM, dD, Nk, Nl));
   net->pairs.push_back(st);  // innermost pair has the highest index
-  AE_CUDA(cudaStreamSynchronize(ctx->stream));
   return AEFFT_OK;
 }
 
@@ -231,6 +253,7 @@ int aefft_net_reset_momentum(aefft_net* net, int n_l) {
   PairState& s = net->pairs[n_l];
   const size_t nC = (size_t)e.dM * e.dD * e.Nk * e.Nl;
   AE_CUDA(cudaSetDevice(net->ctx->device));
+  burn_zero_init_draws(e.dM, e.dD, e.Nk, e.Nl);  // the reference zeroes through Init_conv(..., 0) (:288-292, :447-451)
   AE_TRY(dev_zero(net->ctx, s.dc, nC)); AE_TRY(dev_zero(net->ctx, s.df, nC));
   AE_TRY(dev_zero(net->ctx, s.ddc, nC)); AE_TRY(dev_zero(net->ctx, s.ddf, nC));
   AE_TRY(dev_zero(net->ctx, s.db, e.dM)); AE_TRY(dev_zero(net->ctx, s.ddb, e.dM));
@@ -294,6 +317,7 @@ int aefft_net_set_frames_u8(aefft_net* net, int loc, const unsigned char* images
   image_to_spin_kernel<<<grid, 256, 0, ctx->stream>>>(dev, L0.p, L0.D, L0.Nx, L0.Ny);
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
+  if (loc == AEFFT_HOST) AE_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller may reuse `images` on return
   return AEFFT_OK;
 }
 
@@ -304,9 +328,13 @@ int aefft_net_forward(aefft_net* net, int loc, const float* frames) {
   AE_CUDA(cudaSetDevice(ctx->device));
   LayerL& L0 = net->layers[0];
   const size_t n0 = (size_t)net->B * L0.D * L0.Nx * L0.Ny;
-  if (frames && frames != L0.p)
+  if (frames && frames != L0.p) {
     AE_CUDA(cudaMemcpyAsync(L0.p, frames, n0 * sizeof(float),
                             loc == AEFFT_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+    // host frames: return only once they have been consumed (a pinned buffer would otherwise still be in flight and the
+    // caller's refill for the next step would corrupt this one); device frames stay asynchronous on the ctx stream
+    if (loc == AEFFT_HOST) AE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   const int N = (int)net->convs.size();
   for (int n = 0; n < N; n++) {
     const ConvL& c = net->convs[n];

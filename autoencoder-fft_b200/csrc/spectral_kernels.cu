@@ -382,11 +382,7 @@ __global__ void __launch_bounds__(ST_THREADS, 2) spec_tiled2_kernel(TiledParams 
 template <int CONJP, int CONJQ, int HASP1, int HASQ1>
 static int run_spec_tiled2(aefft_ctx* ctx, const TiledParams& p, dim3 grid) {
   const size_t smem = (size_t)2 * (2 + HASP1 + HASQ1) * ST_R * ST_I * ST_BINS * sizeof(float2);
-  static bool attr = false;
-  if (!attr) {
-    AE_CUDA(cudaFuncSetAttribute(spec_tiled2_kernel<CONJP, CONJQ, HASP1, HASQ1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  AE_TRY(ctx->ensure_dyn_smem((const void*)spec_tiled2_kernel<CONJP, CONJQ, HASP1, HASQ1>, smem));
   spec_tiled2_kernel<CONJP, CONJQ, HASP1, HASQ1><<<grid, ST_THREADS, smem, ctx->stream>>>(p);
   return AEFFT_OK;
 }
@@ -420,7 +416,7 @@ int launch_spec_contract(aefft_ctx* ctx, int64_t B, int C, int O, int64_t S, con
     // i = output channel (P = W), j = frame (Q = in), r = input channel
     TiledParams t{W, nullptr, in0, in1, nullptr, bias, out, w_so, w_sc, (long long)C * S, S, S, (long long)O * S, S,
                   O, (int)B, C, conjW, 0, 1.f, in_scale, 1.f, bias_scale, 0.f};
-    ProfScope prof(ctx, "spec_contract", 8.0 * B * C * O * S, 8.0 * S * ((double)B * C * (in1 ? 2 : 1) + (double)B * O + (double)C * O));
+    ProfScope prof(ctx, "spec_contract_tiled", 8.0 * B * C * O * S, 8.0 * S * ((double)B * C * (in1 ? 2 : 1) + (double)B * O + (double)C * O));
     return launch_spec_tiled(ctx, t);
   }
   // register tile per thread (one bin): 8 outputs x 8 frames when both extents allow it (16 loads feed 64 complex FMAs
@@ -507,7 +503,7 @@ int launch_spec_outer(aefft_ctx* ctx, int64_t B, int nA, int nC, int64_t S, cons
     // i = a (P = A), j = c (Q = Bm, conjugated, + bias at DC), r = frame
     TiledParams t{A0, A1, Bm, nullptr, bm_bias, nullptr, out, S, (long long)nA * S, S, (long long)nC * S, (long long)nC * S, S, S,
                   nA, nC, (int)B, 0, 1, 1.f, bm_alpha, scale, 0.f, bm_bias_scale};
-    ProfScope prof(ctx, "spec_outer", 8.0 * B * nA * nC * S, 8.0 * S * ((double)B * nA * (A1 ? 2 : 1) + (double)B * nC + (double)nA * nC));
+    ProfScope prof(ctx, "spec_outer_tiled", 8.0 * B * nA * nC * S, 8.0 * S * ((double)B * nA * (A1 ? 2 : 1) + (double)B * nC + (double)nA * nC));
     return launch_spec_tiled(ctx, t);
   }
   OuterParams p{A0, A1, Bm, bm_bias, out, S, (int)B, nA, nC, bm_alpha, bm_bias_scale, scale};

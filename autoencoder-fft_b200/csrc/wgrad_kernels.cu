@@ -271,11 +271,7 @@ static int run_wgrad(aefft_ctx* ctx, WgradParams& p, float* G, float* sumA, floa
   AE_TRY(ctx->getT("wgrad_part_sq", (size_t)n_sq, &part_sq));
   p.part = part; p.part_sum = part_sum; p.part_sq = part_sq;
   auto kern = wgrad_kernel<NK, NL, AB, XB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  AE_TRY(ctx->ensure_dyn_smem((const void*)kern, smem));
   dim3 grid(p.n_chunks, nAB * p.nXB);
   {
     const double px = (double)p.n_tiles / ((double)p.tiles_i * p.tiles_j) * p.Nx * p.Ny;  // B * Nx * Ny

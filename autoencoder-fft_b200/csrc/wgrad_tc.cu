@@ -335,11 +335,7 @@ int launch_wgrad_tc(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
   float* part;
   AE_TRY(ctx->getT("wgtc_part", (size_t)cpj * p.n_out, &part));
   p.part = part;
-  static size_t attr = 0;
-  if (smem > attr) {
-    AE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  AE_TRY(ctx->ensure_dyn_smem((const void*)wgrad_tc_kernel, smem));
   {
     const double px = (double)B * Nx * Ny;
     ProfScope prof(ctx, "wgrad_tc", 2.0 * 2.0 * px * dM * dD * T, 4.0 * px * (3.0 * dD + 2.0 * dM));

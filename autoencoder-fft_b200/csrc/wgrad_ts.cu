@@ -900,14 +900,10 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
     AE_TRY(ctx->getT("wgts_dbg", n_dbg, &p.dbg));
     AE_CUDA(cudaMemsetAsync(p.dbg, 0, n_dbg * sizeof(long long), ctx->stream));
   }
-  static size_t attr = 0;
-  if (smem > attr) {
-    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    AE_CUDA(cudaFuncSetAttribute(wgrad_ts_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  AE_TRY(ctx->ensure_dyn_smem((const void*)wgrad_ts_kernel<false, false>, smem));
+  AE_TRY(ctx->ensure_dyn_smem((const void*)wgrad_ts_kernel<true, false>, smem));
+  AE_TRY(ctx->ensure_dyn_smem((const void*)wgrad_ts_kernel<false, true>, smem));
+  AE_TRY(ctx->ensure_dyn_smem((const void*)wgrad_ts_kernel<true, true>, smem));
   {
     const double px = (double)B * Nx * Ny;
     ProfScope prof(ctx, "wgrad_ts", 2.0 * 2.0 * px * dM * dD * T, 4.0 * px * (3.0 * dD + 2.0 * dM));

@@ -234,7 +234,11 @@ int aefft_net_reset_momentum(aefft_net* net, int n_l);
 int aefft_net_num_layers(const aefft_net* net);
 /* layer l (0..2*convs) dims and device pointer ([B][D][Nx][Ny]) */
 int aefft_net_layer(aefft_net* net, int l, int* D, int* Nx, int* Ny, float** dev_ptr);
-/* forward, coordinate space (autoencoder.cpp:135-150): frames = layer 0 ([B][D][Nx][Ny], per `loc`) */
+/* forward, coordinate space (autoencoder.cpp:135-150): frames = layer 0 ([B][D][Nx][Ny], per `loc`).
+ * Asynchrony contract of aefft_net_forward / aefft_net_step / aefft_net_set_frames_u8: with loc == AEFFT_HOST the call
+ * returns after the caller's buffer has been copied (it may be refilled at once); with loc == AEFFT_DEVICE everything is
+ * queued on the ctx stream and the device buffer must stay untouched until that work has run (aefft_sync, or order your
+ * own work on aefft_stream()).  The compute itself is asynchronous in both cases unless an mse pointer is passed. */
 int aefft_net_forward(aefft_net* net, int loc, const float* frames);
 /* ImageToSpin_C (netlib.cpp:37-50) on the device: B interleaved 8-bit images [B][rows = Ny][cols = Nx][D] (a cv::Mat's
  * data for D = 3: B,G,R bytes) become layer 0, spin[d][i][j] = (float)img(row j, col i)[d] -- raw 0..255, not

@@ -292,6 +292,8 @@ def test_net_step_matches_composed_oracle(ctx):
     rng = O.GlibcRand(1234)
     c0, b0 = O.init_conv(rng, 4, 3, 5, 5, 0.3)
     f0, p0 = O.init_conv(rng, 3, 4, 5, 5, 0.3)
+    for shp in ((4, 3), (3, 4), (4, 3), (3, 4)):  # Init_conv(dc/df/ddc/ddf, ..., 0) still draws (autoencoder.cpp:103-107)
+        O.init_conv(rng, shp[0], shp[1], 5, 5, 0.0)
     c1, b1 = O.init_conv(rng, 6, 4, 5, 5, 0.3)
     f1, p1 = O.init_conv(rng, 4, 6, 5, 5, 0.3)
     net_c, net_b, scale = [c0, c1, f1, f0], [b0, b1, p1, p0], [2, 2, -2, -2]
@@ -366,3 +368,126 @@ def test_image_to_spin_u8_bit_exact(ctx):
         net.close()
     want = img.transpose(0, 3, 2, 1).astype(np.float32)
     assert np.array_equal(got, want)
+
+
+def test_net_step_cuda_ref_quirks_two_pairs(ctx):
+    """aefft_net_step in CUDA_REF mode with all quirks on, two square pairs of DIFFERENT resolution trained back to back
+    without a host sync in between (the stale-border kernel of pair 0 must not see pair 1's border geometry), against
+    the oracle's backprop_gpu per pair."""
+    import ctypes
+
+    ctypes.CDLL("libc.so.6").srand(77)
+    B, D, Nx, Ny = 2, 3, 32, 32
+    net = A.Net(ctx, D, Nx, Ny, B)
+    try:
+        net.add_layer(5, 1, 1, 2, 0.3)
+        net.add_layer(4, 1, 1, 2, 0.3)
+        convs = [net.get_conv(n) for n in range(4)]
+        net_c, net_b, scale = [c for c, _ in convs], [b for _, b in convs], [2, 2, -2, -2]
+        x = O.synth_frames(77, B, D, Nx, Ny)
+        net.step(x, A.MODE_CUDA_REF, quirks=A.QUIRKS_ALL)  # no mse pointer: nothing synchronises between the pairs
+        ctx.sync()
+        layers = oracle_forward(x, net_c, net_b, scale)
+        for n_l, (i, h, o) in enumerate([(1, 2, 7), (3, 4, 5)]):
+            c, b = convs[n_l]
+            f, p = convs[3 - n_l]
+            z = lambda a: np.zeros_like(a)
+            want = O.backprop_gpu(layers[i], layers[o], layers[h], c, b, f, p, z(c), z(b), z(f), z(p), z(c), z(b), z(f),
+                                  z(p), 0.2, 0.9, quirks=True)
+            gc, gb = net.get_conv(n_l)
+            gf, gp = net.get_conv(3 - n_l)
+            check_weights(dict(c=gc, b=gb, f=gf, p=gp), want, dict(c=c, b=b, f=f, p=p))
+    finally:
+        net.close()
+
+
+def test_ten_steps_bf16x3_vs_oracle(ctx):
+    """north_star gate: updated weights and reconstructions after N steps.  10 steps of the symmetric-weights net step on
+    a 3-pair stack (3->8->16->32, the c2 shape class at reduced size) in the DEFAULT tensor-core precision (BF16X3),
+    seeded Init_conv weights (rmax 0.3), rate 0.05 (at the app's 0.2 this stack diverges within 8 steps, in
+    the oracle as well), synthetic frames; the oracle replays forward + backprop_gpu_cc per pair in fp64."""
+    import ctypes
+
+    ctypes.CDLL("libc.so.6").srand(1234)
+    B, D, Nx, Ny, widths, steps = 4, 3, 64, 48, [8, 16, 32], 10
+    prec = ctx.precision
+    ctx.set_precision(A.PRECISION_BF16X3)
+    net = A.Net(ctx, D, Nx, Ny, B)
+    try:
+        for m in widths:
+            net.add_layer(m, 1, 1, 2, 0.3)
+        P = len(widths)
+        for n in range(P):
+            net.set_symmetric(n)
+        convs = [net.get_conv(n) for n in range(2 * P)]
+        start_c = [c.copy() for c, _ in convs]
+        net_c = [c.astype(np.float64) for c, _ in convs]
+        net_b = [b.astype(np.float64) for _, b in convs]
+        scale = [2] * P + [-2] * P
+        mom = [dict(dc=np.zeros_like(net_c[n]), db=np.zeros_like(net_b[n]), df=np.zeros_like(net_c[2 * P - 1 - n]),
+                    dp=np.zeros_like(net_b[2 * P - 1 - n])) for n in range(P)]
+        ctx.profile_enable(True)
+        for s in range(steps):
+            x = O.synth_frames(1234, B, D, Nx, Ny, b0=s * B)  # new frames every step
+            net.step(x, A.MODE_CUDA_REF_SYM, delmax=0.05, alpha=0.9)
+            layers = oracle_forward(x, net_c, net_b, scale)
+            for n in range(P):
+                i, h, o = 2 * n + 1, 2 * n + 2, len(layers) - 2 - 2 * n
+                st = mom[n]
+                zc, zb, zf, zp = (np.zeros_like(t) for t in (st["dc"], st["db"], st["df"], st["dp"]))
+                w = O.backprop_gpu_cc(layers[i], layers[o], layers[h], net_c[n], net_b[n], net_c[2 * P - 1 - n],
+                                      net_b[2 * P - 1 - n], st["dc"], st["db"], st["df"], st["dp"], zc, zb, zf, zp, 0.05, 0.9)
+                net_c[n], net_b[n], net_c[2 * P - 1 - n], net_b[2 * P - 1 - n] = w["c"], w["b"], w["f"], w["p"]
+                mom[n] = dict(dc=w["dc"], db=w["db"], df=w["df"], dp=w["dp"])
+        names = {r["name"] for r in ctx.profile_records()}
+        ctx.profile_enable(False)
+        assert "wgrad_ts" in names or any(n.startswith("wgrad_t") for n in names), names
+        ctx.sync()
+        for n in range(2 * P):
+            gc, gb = net.get_conv(n)
+            assert O.rel_l2(gc, net_c[n]) < 1e-4, ("c", n, O.rel_l2(gc, net_c[n]))
+            assert O.rel_l2(gb, net_b[n]) < 1e-4, ("b", n, O.rel_l2(gb, net_b[n]))
+            # accumulated update over the 10 steps (weights), 1e-3
+            assert O.rel_l2(gc.astype(np.float64) - start_c[n], net_c[n] - start_c[n]) < 1e-3, ("dc", n)
+        # reconstructions of a fresh batch with the trained weights
+        x = O.synth_frames(1234, B, D, Nx, Ny, b0=steps * B)
+        net.forward(x)
+        want = oracle_forward(x, net_c, net_b, scale)
+        assert O.rel_l2(net.layer(2 * 2 * P), want[-1]) < 1e-4
+    finally:
+        ctx.set_precision(prec)
+        net.close()
+
+
+@pytest.mark.parametrize("dims", [(16, 3, 5, 5, 240, 240), (32, 16, 5, 5, 120, 120), (64, 32, 5, 5, 60, 60)])
+def test_config2_square_twin_vs_live_reference(ctx, ref, dims):
+    """the compiled backprop_gpu_cc is only defined on square frames (quirk C2), so every pair of
+    config 2 gets a square twin with its channel widths (16x3 @ 240^2, 32x16 @ 120^2, 64x32 @ 60^2, one frame) and the
+    streaming tensor-core kernels (default BF16X3 precision) are compared with the UNMODIFIED reference run live."""
+    if ref is None:
+        pytest.skip("libref.so not present")
+    dM, dD, Nk, Nl, Nx, Ny = dims
+    rng = np.random.default_rng(dM)
+    inp = np.floor(rng.random((dD, Nx, Ny)) * 256).astype(np.float32)
+    c = ((rng.random((dM, dD, Nk, Nl)) * 2 - 1) * (1.0 / dD)).astype(np.float32)
+    b = (rng.random(dM) * 2 - 1).astype(np.float32)
+    p = (rng.random(dD) * 2 - 1).astype(np.float32)
+    f = np.ascontiguousarray(np.swapaxes(c, 0, 1))
+    hin = ref.conv_gpu(inp, c, b)
+    out = ref.conv_gpu(hin, f, p)
+    cs = dict(inp=inp, hin=hin, out=out, c=c, b=b, f=f, p=p)
+    st = zeros_state(cs)
+    names = "c b f p dc db df dp ddc ddb ddf ddp".split()
+    want = ref.backprop_gpu(1, inp, out, hin, *[dict(cs, **st)[k] for k in names], 0.2, 0.9, 1)
+    prec = ctx.precision
+    ctx.set_precision(A.PRECISION_BF16X3)
+    try:
+        assert O.rel_l2(ctx.conv_fwd(inp, c, b), hin) < 1e-4
+        ctx.profile_enable(True)
+        got = run_product(ctx, A.MODE_CUDA_REF_SYM, cs, st)
+        kernels = {r["name"] for r in ctx.profile_records()}
+        ctx.profile_enable(False)
+    finally:
+        ctx.set_precision(prec)
+    assert any(k.startswith("wgrad_t") for k in kernels), kernels  # a tensor-core weight-gradient kernel ran
+    check_weights(got, want, cs)

@@ -304,3 +304,96 @@ def test_multiobjective_tiled_kernel_vs_oracle(ctx):
     assert np.allclose(trace, want["mse"], rtol=2e-4), (trace, want["mse"])
     for k in "cfbp":
         assert O.rel_l2(w[k], want[k]) < 1e-4, k
+
+
+# ---- the kernels the c3 / c4 benchmarks actually run: B >= 8 and >= 8 channels take the shared-memory tiled contraction
+# (forward conv_k, G, dC, dF forms).  Channel shapes are those of the c3 pairs 1 and 2 (16->32, 32->64) and a c4-like
+# wide pair; resolutions are what the fp64 numpy oracle finishes in seconds.
+def _names(ctx):
+    return {r["name"] for r in ctx.profile_records()}
+
+
+@pytest.mark.parametrize("dims,B,maxdiff", [((32, 16, 5, 5, 32, 32), 8, 0), ((64, 32, 5, 5, 16, 16), 8, 0),
+                                            ((16, 8, 5, 5, 32, 16), 12, 0), ((16, 8, 3, 3, 16, 32), 9, 1)])
+def test_backprop_fft_tiled_kernels_vs_oracle(ctx, dims, B, maxdiff):
+    cs = fft_case(21, *dims, B=B, wscale=0.1)
+    n_iter = 3
+    w = {k: cs[k].copy() for k in "cfbp"}
+    ctx.profile_enable(True)
+    trace = ctx.backprop_fft(cs["inp"], cs["inp"], cs["out"], w["c"], w["f"], w["b"], w["p"], 0.2, maxdiff, n_iter)
+    names = _names(ctx)
+    ctx.profile_enable(False)
+    assert names & {"spec_contract_tiled", "spec_contract_tc"}, names   # not the small-shape register-tile kernels
+    assert names & {"spec_outer_tiled", "spec_outer_tc"}, names
+    assert "spec_contract" not in names and "spec_outer" not in names, names
+    want = O.backprop_fft(cs["inp"], cs["inp"], cs["out"], cs["c"], cs["f"], cs["b"], cs["p"], 0.2, maxdiff, n_iter)
+    assert np.allclose(trace, want["mse"], rtol=2e-4), (trace, want["mse"])
+    for k in "cfbp":
+        assert O.rel_l2(w[k], want[k]) < 1e-4, k
+        assert O.rel_l2(w[k].astype(np.float64) - cs[k], want[k] - cs[k]) < 2e-3, k
+
+
+def test_backprop_fft_expout_differs_tiled(ctx):
+    """expout != in (the library API allows it; the app passes the same array): the G / dF forms then subtract a
+    different target spectrum than the one they correlate with."""
+    dims = (16, 8, 5, 5, 16, 16)
+    cs = fft_case(23, *dims, B=8, wscale=0.1)
+    rng = np.random.default_rng(24)
+    tgt = np.floor(rng.random(cs["inp"].shape) * 256).astype(np.float32)
+    w = {k: cs[k].copy() for k in "cfbp"}
+    trace = ctx.backprop_fft(cs["inp"], tgt, cs["out"], w["c"], w["f"], w["b"], w["p"], 0.2, 0, 2)
+    want = O.backprop_fft(cs["inp"], tgt, cs["out"], cs["c"], cs["f"], cs["b"], cs["p"], 0.2, 0, 2)
+    assert np.allclose(trace, want["mse"], rtol=2e-4)
+    for k in "cfbp":
+        assert O.rel_l2(w[k], want[k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("cfg", [(3, 32, 32, [16, 32], [2, 2], 8), (3, 64, 32, [8, 16, 32], [2, 2, 1], 10)])
+def test_autoenc_fft_batched_tiled_vs_oracle(ctx, cfg):
+    """Forward of the whole stack on B >= 8 frames with the c3 widths: conv_k runs in the tiled kernel."""
+    D, Nx, Ny, widths, scales, B = cfg
+    rng = np.random.default_rng(31)
+    net_c, net_b, scale, shapes = build_net(rng, D, Nx, Ny, widths, scales, wscale=0.1)
+    x = np.floor(rng.random((B, D, Nx, Ny)) * 256).astype(np.float32)
+    ctx.profile_enable(True)
+    layers, spectra = ctx.autoenc_fft(x, net_c, net_b, scale, shapes, None, 1)
+    names = _names(ctx)
+    ctx.profile_enable(False)
+    assert names & {"spec_contract_tiled", "spec_contract_tc"}, names
+    for n in range(B):
+        want, _ = O.autoenc_fft(x[n], net_c, net_b, scale, None, 1)
+        for l in range(len(shapes)):
+            assert O.rel_l2(layers[l][n], want[l]) < 2e-5, (n, l)
+
+
+def test_fft_batched_vs_live_reference_per_frame(ctx, ref):
+    """The reference is strictly one frame per call: (a) the batched forward of 8 frames equals 8 calls of the compiled
+    autoenc_fft; (b) 8 copies of ONE frame make the batch-mean gradient equal that frame's gradient, so the batched
+    100-iteration backprop_fft (tiled kernels, frames = reduction dimension) must reproduce the compiled backprop_fft
+    of that frame (smooth regime: small rate, as the g5 / n5 goldens)."""
+    if ref is None:
+        pytest.skip("libref.so not present")
+    rng = np.random.default_rng(41)
+    net_c, net_b, scale, shapes = build_net(rng, 3, 32, 32, [8, 16], [2, 2], wscale=0.1)
+    x = np.floor(rng.random((8, 3, 32, 32)) * 256).astype(np.float32)
+    got, _ = ctx.autoenc_fft(x, net_c, net_b, scale, shapes, None, 0)
+    for n in range(8):
+        want, _ = ref.autoenc_fft(x[n], net_c, net_b, scale, shapes, None, 0)
+        assert O.rel_l2(got[-1][n], want[-1]) < 1e-4, n
+    dims = (16, 8, 5, 5, 16, 16)
+    dM, dD, Nk, Nl, Nx, Ny = dims
+    cs = fft_case(43, *dims, wscale=0.1)
+    cf = np.ascontiguousarray(ctx.kernel_spectrum(cs["c"], Nx, Ny))
+    ff = np.ascontiguousarray(ctx.kernel_spectrum(cs["f"], Nx, Ny))
+    del0 = 0.002
+    want = ref.backprop_fft(cs["inp"], cs["inp"], cs["out"], cf, cs["c"], ff, cs["f"], cs["b"], cs["p"], del0, 0)
+    rep = lambda a: np.ascontiguousarray(np.broadcast_to(a, (8,) + a.shape))
+    w = {k: cs[k].copy() for k in "cfbp"}
+    ctx.profile_enable(True)
+    ctx.backprop_fft(rep(cs["inp"]), rep(cs["inp"]), rep(cs["out"]), w["c"], w["f"], w["b"], w["p"], del0, 0, 100)
+    names = _names(ctx)
+    ctx.profile_enable(False)
+    assert names & {"spec_outer_tiled", "spec_outer_tc"}, names
+    for k in "cfbp":
+        assert O.rel_l2(w[k], want[k]) < 1e-4, k
+        assert O.rel_l2(w[k].astype(np.float64) - cs[k], want[k].astype(np.float64) - cs[k]) < 5e-3, k
