@@ -169,6 +169,23 @@ class Ctx:
         """Frequency-bin sharding of backprop_fft (aefft_set_bin_shard); the gradient hook must then SUM over devices."""
         _chk(lib().aefft_set_bin_shard(self.h, int(rank), int(world)))
 
+    # ---------------------------------------------------------------- multi-GPU (the engine's own NCCL communicator)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _chk(lib().aefft_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, id_bytes: bytes, rank: int, world: int):
+        assert len(id_bytes) == 128
+        _chk(lib().aefft_comm_init(self.h, C.c_char_p(id_bytes), int(rank), int(world)))
+
+    def comm_destroy(self):
+        _chk(lib().aefft_comm_destroy(self.h))
+
+    def comm_allreduce(self, dev_ptr: int, n: int, op: int = 0):
+        _chk(lib().aefft_comm_allreduce(self.h, C.c_void_p(dev_ptr), C.c_int64(n), int(op)))
+
     def profile_enable(self, on: bool):
         """Bracket every kernel launch of this ctx with a CUDA event pair (aefft_profile_enable)."""
         _chk(lib().aefft_profile_enable(self.h, 1 if on else 0))
@@ -449,6 +466,14 @@ class Net:
         _chk(lib().aefft_net_pair_update(self.h, n_l, mode, C.c_int64(B_global), C.c_float(delmax), C.c_float(alpha),
                                          C.byref(mse) if want_mse else None))
         return float(mse.value)
+
+    def fused_layout(self, mode):
+        """(offsets per pair, total floats) of the fused raw gradient block a data-parallel step all-reduces once."""
+        P = self.num_pairs
+        off = (C.c_int64 * P)()
+        tot = C.c_int64()
+        _chk(lib().aefft_net_fused_layout(self.h, mode, off, C.byref(tot)))
+        return [int(v) for v in off], int(tot.value)
 
     def set_frames_u8(self, images, loc=HOST):
         """ImageToSpin_C on the device: images uint8 [B][Ny][Nx][D] (numpy array, or a raw address with loc)."""

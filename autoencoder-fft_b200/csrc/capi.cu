@@ -283,6 +283,7 @@ int aefft_destroy(aefft_ctx* ctx) {
   if (!ctx) return AEFFT_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) aefft_comm_destroy(ctx);
   for (auto& kv : ctx->scratch)
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : ctx->pinned)

@@ -63,6 +63,8 @@ struct aefft_ctx {
   int shard_rank = 0, shard_world = 1;  // frequency-bin sharding of aefft_backprop_fft (aefft_set_bin_shard)
   aefft_gradient_hook_fn grad_hook = nullptr;  // data-parallel momentum-space training (aefft_set_gradient_hook)
   void* grad_hook_user = nullptr;
+  void* comm = nullptr;                 // ncclComm_t of this rank (aefft_comm_init); collectives run on `stream`
+  int comm_rank = 0, comm_world = 1;
   std::vector<aefft::ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;
   cudaEvent_t get_event();
@@ -261,6 +263,12 @@ int launch_gradient_diff(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, const f
 int launch_axpby(aefft_ctx* ctx, float* y, const float* x, float a, float b, long long n);
 int launch_spec_mse(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx, int Ny, const float2* Xt, const float2* O, float* out,
                     int col0 = 0, int ncols = 0);
+
+// ---- collectives inside the engine (comm.cu): NCCL on the ctx stream; op 0 = sum, 1 = average over the ranks
+int comm_allreduce(aefft_ctx* ctx, float* dev, int64_t n_floats, int op);
+// slab exchange of a bin-sharded transform: rank r sends send + r'*chunk floats to every r' and receives into
+// recv + r'*chunk (ncclSend/ncclRecv group = all-to-all over NVSwitch)
+int comm_alltoall(aefft_ctx* ctx, const float* send, float* recv, int64_t chunk_floats);
 
 // ---- host orchestration shared by capi.cu and net.cu ------------------------------------------------
 int64_t gbuf_len(int mode, int dD, int dM, int Nk, int Nl);

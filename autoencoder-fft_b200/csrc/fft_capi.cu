@@ -304,7 +304,10 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
   const bool sharded = world > 1;
   if (sharded) {
     AE_ARG(ncols > 0 && !cfreq && !ffreq && loc == AEFFT_DEVICE);
-    if (!ctx->grad_hook) { set_error("bin-sharded aefft_backprop_fft needs a gradient hook (sum over devices)"); return AEFFT_ERR_ARG; }
+    if (!ctx->grad_hook && ctx->comm_world <= 1) {
+      set_error("bin-sharded aefft_backprop_fft needs a communicator (aefft_comm_init) or a gradient hook (sum over devices)");
+      return AEFFT_ERR_ARG;
+    }
   }
   const bool own_dc = col0 == 0;  // the DC bin (biases, db/dp) lives on the device that owns column 0
   const int64_t S = (int64_t)Nx * ncols;
@@ -365,7 +368,13 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
   if (ffreq) AE_CUDA(cudaMemcpyAsync(q.F, ffreq, nKS * sizeof(float2), k_in, st));
   else AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F, col0, ncols));
   const float norm = (float)Nx * (float)Ny;
+  // Reduction of the raw kernel-space block over the devices, before the non-linear clip: the engine's own NCCL
+  // all-reduce when the ctx has a communicator (average for data-parallel frames, sum for bin-sharded partial blocks),
+  // else the caller's hook.  The mse values feed nothing inside the loop, so their partials stay local until the end of
+  // the call and are reduced ONCE as a whole trace -- one collective per iteration instead of three.
+  const bool use_comm = ctx->comm_world > 1;
   auto reduce_over_devices = [&](float* block, int64_t n) -> int {
+    if (use_comm) return comm_allreduce(ctx, block, n, sharded ? 0 : 1);
     if (ctx->grad_hook && ctx->grad_hook(ctx->grad_hook_user, block, n) != 0) {
       set_error("aefft_backprop_fft: gradient hook failed");
       return AEFFT_ERR_ARG;
@@ -375,7 +384,7 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
   const float* bias_b = own_dc ? db_w : nullptr;
   const float* bias_p = own_dc ? dp_w : nullptr;
   AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse, col0, ncols));  // "mse fft:" (:1440)
-  if (sharded) AE_TRY(reduce_over_devices(q.mse, 1));
+  if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse, 1));
   // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1)
   AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, bias_b, norm, q.H));
   const float del = 0.1f * del0;                                        // :1445
@@ -410,8 +419,9 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
     AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, bias_b, norm, q.H));
     AE_TRY(launch_spec_contract(ctx, B, dM, dD, S, q.H, nullptr, q.F, (int64_t)dM * S, S, 0, 1.f / (float)dD, bias_p, norm, q.O));
     AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse + n + 1, col0, ncols));
-    if (sharded) AE_TRY(reduce_over_devices(q.mse + n + 1, 1));
+    if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse + n + 1, 1));
   }
+  if (use_comm) AE_TRY(comm_allreduce(ctx, q.mse, (int64_t)n_iter + 1, sharded ? 0 : 1));
   // store_cfreq (:1484-1485) and export_cfreq (:1487-1488: c,f re-derived from the spectra: C2R/(NxNy) + kernel_invpad)
   if (cfreq) AE_CUDA(cudaMemcpyAsync(cfreq, q.C, nKS * sizeof(float2), k_out, st));
   if (ffreq) AE_CUDA(cudaMemcpyAsync(ffreq, q.F, nKS * sizeof(float2), k_out, st));

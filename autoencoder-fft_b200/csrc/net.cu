@@ -24,7 +24,7 @@ struct LayerL {
 struct PairState {
   float *dc = nullptr, *db = nullptr, *df = nullptr, *dp = nullptr;
   float *ddc = nullptr, *ddb = nullptr, *ddf = nullptr, *ddp = nullptr;
-  float* gbuf = nullptr;
+  float* gbuf = nullptr;  // view into aefft_net::gall (the fused gradient block of all pairs), valid for gbuf_mode
   int64_t gbuf_len = 0;
   int gbuf_mode = -1;
 };
@@ -38,6 +38,11 @@ struct aefft_net {
   std::vector<ConvL> convs;     // encoder convs 0..P-1, decoder convs P..2P-1 (pair n: convs n and N-1-n)
   std::vector<PairState> pairs; // index = pair
   float* mse_dev = nullptr;     // [64]
+  // Raw gradient blocks of ALL pairs in one contiguous buffer [pair 0 | pair 1 | ...] (layout of `gall_mode`): a
+  // data-parallel step all-reduces it ONCE (the pairs are independent given the forward's activations).
+  float* gall = nullptr;
+  int64_t gall_len = 0, gall_cap = 0;
+  int gall_mode = -1;
 };
 
 namespace {
@@ -73,8 +78,37 @@ int alloc_pair_state(aefft_net* net, PairState& s, int dM, int dD, int Nk, int N
 void free_pair_state(PairState& s) {
   dev_free(s.dc); dev_free(s.db); dev_free(s.df); dev_free(s.dp);
   dev_free(s.ddc); dev_free(s.ddb); dev_free(s.ddf); dev_free(s.ddp);
-  dev_free(s.gbuf);
+  s.gbuf = nullptr;  // a view, owned by the net
   s.gbuf_len = 0; s.gbuf_mode = -1;
+}
+
+// (re)build the fused gradient block for `mode`: every pair's gbuf becomes a view at its offset
+int ensure_fused(aefft_net* net, int mode) {
+  if (net->gall_mode == mode) return AEFFT_OK;
+  int64_t total = 0;
+  const int P = (int)net->pairs.size();
+  for (int n = 0; n < P; n++) {
+    const ConvL& e = net->convs[n];
+    total += aefft::gbuf_len(mode, e.dD, e.dM, e.Nk, e.Nl);
+  }
+  if (total > net->gall_cap) {
+    AE_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    dev_free(net->gall);
+    AE_TRY(dev_alloc(&net->gall, (size_t)total));
+    net->gall_cap = total;
+  }
+  int64_t off = 0;
+  for (int n = 0; n < P; n++) {
+    const ConvL& e = net->convs[n];
+    PairState& s = net->pairs[n];
+    s.gbuf = net->gall + off;
+    s.gbuf_len = aefft::gbuf_len(mode, e.dD, e.dM, e.Nk, e.Nl);
+    s.gbuf_mode = -1;  // nothing computed yet in this layout
+    off += s.gbuf_len;
+  }
+  net->gall_len = total;
+  net->gall_mode = mode;
+  return AEFFT_OK;
 }
 
 int upload(aefft_ctx* ctx, float* dst, const float* src, size_t n) {
@@ -118,6 +152,7 @@ int aefft_net_destroy(aefft_net* net) {
   for (auto& c : net->convs) { dev_free(c.c); dev_free(c.b); }
   for (auto& s : net->pairs) free_pair_state(s);
   dev_free(net->mse_dev);
+  dev_free(net->gall);
   delete net;
   return AEFFT_OK;
 }
@@ -172,6 +207,7 @@ int aefft_net_add_layer(aefft_net* net, int dM, int Lk, int Ll, int scal, float 
   const int mid = (int)net->convs.size() / 2;
   net->convs.insert(net->convs.begin() + mid, {enc, dec});
   net->pairs.push_back(st);  // innermost pair has the highest index
+  net->gall_mode = -1;       // the fused gradient block is laid out again on the next gradient call
   return AEFFT_OK;
 }
 
@@ -189,6 +225,7 @@ int aefft_net_delete_layer(aefft_net* net) {
   net->layers.erase(net->layers.begin() + n - 1, net->layers.begin() + n + 3);
   free_pair_state(net->pairs.back());
   net->pairs.pop_back();
+  net->gall_mode = -1;
   return AEFFT_OK;
 }
 
@@ -372,14 +409,9 @@ int aefft_net_pair_gradients(aefft_net* net, int n_l, int mode, int quirks, floa
   AE_TRY(pair_views(net, n_l, &enc, &dec, &in, &hin, &out));
   aefft_ctx* ctx = net->ctx;
   AE_CUDA(cudaSetDevice(ctx->device));
+  AE_TRY(ensure_fused(net, mode));
   PairState& s = net->pairs[n_l];
-  const int64_t len = gbuf_len(mode, enc->dD, enc->dM, enc->Nk, enc->Nl);
-  if (s.gbuf_len < len) {
-    AE_CUDA(cudaStreamSynchronize(ctx->stream));
-    dev_free(s.gbuf);
-    AE_TRY(dev_alloc(&s.gbuf, (size_t)len));
-    s.gbuf_len = len;
-  }
+  const int64_t len = s.gbuf_len;
   s.gbuf_mode = mode;
   AE_TRY(coord_gradients_dev(ctx, mode, quirks, net->B, enc->dD, enc->dM, in->Nx, in->Ny, enc->Nk, enc->Nl, in->p, out->p,
                              hin->p, dec->c, s.gbuf));
@@ -417,17 +449,36 @@ int aefft_net_train_pair(aefft_net* net, int n_l, int mode, int quirks, float de
 int aefft_net_step(aefft_net* net, int loc, const float* frames, int mode, int quirks, float delmax, float alpha,
                    float* mse) {
   AE_ARG(net);
+  aefft_ctx* ctx = net->ctx;
   AE_TRY(aefft_net_forward(net, loc, frames));
   const int P = (int)net->pairs.size();
-  for (int n = 0; n < P; n++) {
-    AE_TRY(aefft_net_pair_gradients(net, n, mode, quirks, nullptr, nullptr));
-    AE_TRY(aefft_net_pair_update(net, n, mode, net->B, delmax, alpha, nullptr));
+  if (ctx->comm_world > 1) {
+    // data-parallel frames (aefft_comm_init): raw gradient blocks of every pair, ONE all-reduce(sum) of the fused block
+    // on the ctx stream, then the identical clipped-momentum update everywhere.  The sum precedes the non-linear clip.
+    for (int n = 0; n < P; n++) AE_TRY(aefft_net_pair_gradients(net, n, mode, quirks, nullptr, nullptr));
+    AE_TRY(comm_allreduce(ctx, net->gall, net->gall_len, 0));
+    for (int n = 0; n < P; n++) AE_TRY(aefft_net_pair_update(net, n, mode, net->B * ctx->comm_world, delmax, alpha, nullptr));
+  } else {
+    for (int n = 0; n < P; n++) {
+      AE_TRY(aefft_net_pair_gradients(net, n, mode, quirks, nullptr, nullptr));
+      AE_TRY(aefft_net_pair_update(net, n, mode, net->B, delmax, alpha, nullptr));
+    }
   }
   if (mse) {
-    AE_CUDA(cudaMemcpyAsync(mse, net->mse_dev, sizeof(float) * (P < 64 ? P : 64), cudaMemcpyDeviceToHost,
-                            net->ctx->stream));
-    AE_CUDA(cudaStreamSynchronize(net->ctx->stream));
+    AE_CUDA(cudaMemcpyAsync(mse, net->mse_dev, sizeof(float) * (P < 64 ? P : 64), cudaMemcpyDeviceToHost, ctx->stream));
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  return AEFFT_OK;
+}
+
+// Layout of the fused gradient block for `mode`: offsets[n] = first float of pair n, *total = length (floats).
+int aefft_net_fused_layout(aefft_net* net, int mode, int64_t* offsets, int64_t* total) {
+  AE_ARG(net);
+  AE_CUDA(cudaSetDevice(net->ctx->device));
+  AE_TRY(ensure_fused(net, mode));
+  if (offsets)
+    for (size_t n = 0; n < net->pairs.size(); n++) offsets[n] = net->pairs[n].gbuf - net->gall;
+  if (total) *total = net->gall_len;
   return AEFFT_OK;
 }
 

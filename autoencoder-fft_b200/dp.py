@@ -1,8 +1,14 @@
-"""Data-parallel plumbing shared by bench.py and the gloo tests: which frames a rank owns and the one collective of a
-training step.  The reference has no multi-GPU path; this is the engine's extension (DESIGN.md "Multi-GPU"):
-every rank computes the RAW (un-normalised, un-clipped) gradient block of its own frames, ONE all-reduce(sum) of that
-small fp32 block per layer pair, then the identical clip + momentum update on every rank (weights stay replicated, no
-broadcast).  The reduction must precede the clip g/max(10,|g|), which is non-linear."""
+"""Host-side sharding plan of the multi-GPU paths (one process per GPU), shared by bench.py and the CPU (gloo) tests.
+
+The reference has no multi-GPU path; the engine adds two splits (DESIGN.md "Multi-GPU"):
+  * data-parallel frames: rank r owns frames [r*B, (r+1)*B) of the global batch; the raw (un-normalised, un-clipped)
+    gradient blocks of ALL layer pairs form one fused fp32 buffer that is all-reduced (sum) ONCE per step, then every rank
+    applies the identical clip + momentum update (weights stay replicated, no broadcast).  The reduction must precede the
+    clip g/max(10,|g|), which is non-linear.  The collective itself is issued by the engine (csrc/comm.cu, NCCL on the
+    ctx stream); the functions below only say WHO owns WHAT, so that the plan can be tested without a GPU.
+  * frequency-bin sharding: rank r owns the spectrum columns bin_slab(r) of every image, and rows row_slab(r) of every
+    frame for the row pass of the slab-decomposed 2-D transform (rows -> all-to-all -> columns).
+"""
 from __future__ import annotations
 
 
@@ -11,13 +17,26 @@ def frame_range(rank: int, world: int, batch_per_rank: int):
     return rank * batch_per_rank, batch_per_rank
 
 
-def allreduce_gradient_block(gbuf, world: int):
-    """Sum the raw gradient block over ranks in place (NCCL on GPUs, gloo in the CPU tests)."""
-    if world > 1:
-        import torch.distributed as dist
+def gbuf_len(mode: int, dD: int, dM: int, Nk: int, Nl: int) -> int:
+    """Length (floats) of one pair's raw gradient block; mirrors aefft_coord_gbuf_len (csrc/capi.cu gbuf_len).
+    mode 0 = CPU_REF: [R (dD*T)^2 | Bm dD*T | GF dD*dM*T | GP dD | SQ 1]; modes 1, 2 = CUDA_REF(_SYM):
+    [GC dM*dD*T | GF dD*dM*T | GB dM | GP dD | SQ 1]."""
+    T = Nk * Nl
+    nC = dM * dD * T
+    if mode == 0:
+        S = dD * T
+        return S * S + S + nC + dD + 1
+    return 2 * nC + dM + dD + 1
 
-        dist.all_reduce(gbuf, op=dist.ReduceOp.SUM)
-    return gbuf
+
+def fused_block_layout(pairs, mode: int):
+    """pairs: [(dD, dM, Nk, Nl)] in pair order.  Returns (offsets, total) of the fused gradient buffer
+    [pair 0 | pair 1 | ...] -- the same layout as aefft_net_fused_layout."""
+    offs, total = [], 0
+    for dD, dM, Nk, Nl in pairs:
+        offs.append(total)
+        total += gbuf_len(mode, dD, dM, Nk, Nl)
+    return offs, total
 
 
 def bin_slab(rank: int, world: int, Ny: int):
@@ -28,10 +47,7 @@ def bin_slab(rank: int, world: int, Ny: int):
     return c0, (rank + 1) * nyr // world - c0
 
 
-def allreduce_partial_block(block, world: int):
-    """Bin-sharded devices hold PARTIAL sums (over their spectrum columns) of the gradient block and of the mse: add them."""
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.all_reduce(block, op=dist.ReduceOp.SUM)
-    return block
+def row_slab(rank: int, world: int, Nx: int):
+    """(first row, row count) of every frame that `rank` row-transforms in the slab-decomposed 2-D R2C."""
+    r0 = rank * Nx // world
+    return r0, (rank + 1) * Nx // world - r0

@@ -92,6 +92,26 @@ int aefft_free(aefft_ctx* ctx, void* dev_ptr);
 /* kind: 0 host->device, 1 device->host, 2 device->device; ordered on the ctx stream, synchronous on return. */
 int aefft_memcpy(aefft_ctx* ctx, void* dst, const void* src, int64_t bytes, int kind);
 
+/* ------------------------------------------------------------------ multi-GPU (one process / ctx per GPU)
+ * The reference has no multi-GPU path.  aefft_comm_init gives a ctx an NCCL communicator (NVLink /
+ * NVSwitch); afterwards the engine itself issues the collectives on the ctx stream:
+ *   - aefft_net_step: the raw gradient blocks of ALL pairs are all-reduced (sum) as ONE fused buffer, then every rank
+ *     applies the identical clipped-momentum update with B_global = B * world (weights stay replicated);
+ *   - aefft_backprop_fft (data-parallel frames): one all-reduce(avg) of the kernel-space block [dck|dfk|db|dp] per
+ *     iteration, the mse trace is averaged once at the end of the call;
+ *   - aefft_backprop_fft under aefft_set_bin_shard: all-reduce(sum) of the partial block per iteration, the partial
+ *     mse trace is summed once at the end.
+ * The reduction always precedes the non-linear clip g/max(10,|g|).  Bootstrap: rank 0 calls aefft_comm_unique_id and
+ * hands the AEFFT_COMM_ID_BYTES bytes to the other ranks by any means (file, socket, MPI, torch.distributed). */
+#define AEFFT_COMM_ID_BYTES 128
+int aefft_comm_unique_id(void* id_bytes);
+int aefft_comm_init(aefft_ctx* ctx, const void* id_bytes, int rank, int world);
+int aefft_comm_destroy(aefft_ctx* ctx);
+int aefft_comm_rank(const aefft_ctx* ctx);
+int aefft_comm_world(const aefft_ctx* ctx);
+/* all-reduce of a device buffer on the ctx stream; op 0 = sum, 1 = average.  No-op for world == 1. */
+int aefft_comm_allreduce(aefft_ctx* ctx, float* dev, int64_t n_floats, int op);
+
 /* ------------------------------------------------------------------ forward, coordinate space */
 
 /* Conv_gpu (backproplib.cu:114-182) / Conv (netlib.cpp:318-358), per `convention`.
@@ -251,7 +271,11 @@ int aefft_net_train_pair(aefft_net* net, int n_l, int mode, int quirks, float de
  * data-parallel split (all-reduce the buffer in between). */
 int aefft_net_pair_gradients(aefft_net* net, int n_l, int mode, int quirks, float** gbuf_dev, int64_t* gbuf_len);
 int aefft_net_pair_update(aefft_net* net, int n_l, int mode, int64_t B_global, float delmax, float alpha, float* mse);
-/* one whole training step: forward + train every pair once (order 0..pairs-1). mse[pairs] host or NULL. */
+/* Offsets (floats) of every pair's raw gradient block inside the net's fused gradient buffer for `mode`, and its total
+ * length: the buffer a data-parallel step all-reduces once (offsets may be NULL). */
+int aefft_net_fused_layout(aefft_net* net, int mode, int64_t* offsets, int64_t* total);
+/* one whole training step: forward + train every pair once (order 0..pairs-1). mse[pairs] host or NULL.
+ * With a communicator (aefft_comm_init, world > 1): gradients of all pairs -> ONE all-reduce -> updates. */
 int aefft_net_step(aefft_net* net, int loc, const float* frames, int mode, int quirks, float delmax, float alpha,
                    float* mse);
 

@@ -1,7 +1,8 @@
-"""CPU test of the multi-rank path (world_size 2, gloo): rank r computes the oracle's raw gradient sums of ITS frames
-(dp.frame_range), the block is all-reduced (dp.allreduce_gradient_block), every rank applies the same clipped-momentum
-update -> identical weights on both ranks, equal to the single-process full-batch step.  Also shows why the reduction
-must come before the clip."""
+"""CPU test of the multi-rank plan (world_size 2, gloo): rank r computes the oracle's raw gradient sums of ITS frames
+(dp.frame_range) for TWO layer pairs into one fused block (dp.fused_block_layout, the layout aefft_net_step all-reduces
+once per step), ONE all-reduce(sum), every rank applies the same clipped-momentum update -> identical weights on both
+ranks, equal to the single-process full-batch step.  Also shows why the reduction must come before the clip, and that
+the bin / row slabs of the sharded transform partition their axes."""
 import os
 import sys
 
@@ -44,6 +45,22 @@ def _raw_sums(inp, out, hin, c, f):
     return acc
 
 
+def _case2():
+    """A second, wider pair (the fused block carries every pair of the net)."""
+    import oracle_np as O
+
+    rng = np.random.default_rng(1)
+    B, dD, dM, Nk, Nl, Nx, Ny = 4, 3, 4, 3, 3, 6, 6
+    inp = O.synth_frames(99, B, dD, Nx, Ny)
+    c = ((rng.random((dM, dD, Nk, Nl)) * 2 - 1) * 0.2).astype(np.float32)
+    f = np.ascontiguousarray(np.swapaxes(c, 0, 1))
+    b = (rng.random(dM) * 2 - 1).astype(np.float32)
+    p = (rng.random(dD) * 2 - 1).astype(np.float32)
+    hin = O.conv_gpu(inp, c, b).astype(np.float32)
+    out = O.conv_gpu(hin, f, p).astype(np.float32)
+    return inp, out, hin, c, b, f, p
+
+
 def _worker(rank, world, port, ret):
     import dp
     import oracle_np as O
@@ -51,16 +68,24 @@ def _worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    inp, out, hin, c, b, f, p = _case()
-    b0, n = dp.frame_range(rank, world, inp.shape[0] // world)
-    sl = slice(b0, b0 + n)
-    g = torch.from_numpy(_raw_sums(inp[sl], out[sl], hin[sl], c, f))
-    dp.allreduce_gradient_block(g, world)
-    g = g.numpy() / inp.shape[0]  # mean over the GLOBAL batch
-    nC = c.size
-    c2, _ = O.momentum_update(c, np.zeros_like(c), g[:nC].reshape(c.shape), 0.2, 0.9)
-    b2, _ = O.momentum_update(b, np.zeros_like(b), g[nC:nC + b.size], 0.2, 0.9)
-    ret[rank] = (c2, b2)
+    cases = [_case(), _case2()]
+    shapes = [(cs[3].shape[1], cs[3].shape[0], cs[3].shape[2], cs[3].shape[3]) for cs in cases]  # (dD, dM, Nk, Nl)
+    offs, total = dp.fused_block_layout(shapes, 2)
+    fused = torch.zeros(total, dtype=torch.float64)
+    for (inp, out, hin, c, b, f, p), off in zip(cases, offs):
+        b0, n = dp.frame_range(rank, world, inp.shape[0] // world)
+        sl = slice(b0, b0 + n)
+        v = _raw_sums(inp[sl], out[sl], hin[sl], c, f)   # combined form [g | gB | gP | sq]
+        fused[off:off + len(v)] = torch.from_numpy(v)
+    dist.all_reduce(fused, op=dist.ReduceOp.SUM)          # the ONE collective of the step
+    res = []
+    for (inp, out, hin, c, b, f, p), off in zip(cases, offs):
+        g = fused[off:].numpy() / inp.shape[0]            # mean over the GLOBAL batch
+        nC = c.size
+        c2, _ = O.momentum_update(c, np.zeros_like(c), g[:nC].reshape(c.shape), 0.2, 0.9)
+        b2, _ = O.momentum_update(b, np.zeros_like(b), g[nC:nC + b.size], 0.2, 0.9)
+        res.append((c2, b2))
+    ret[rank] = res
     dist.destroy_process_group()
 
 
@@ -71,13 +96,25 @@ def test_two_rank_step_equals_full_batch():
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    inp, out, hin, c, b, f, p = _case()
     z = lambda a: np.zeros_like(a)
-    want = O.backprop_gpu_cc(inp, out, hin, c, b, f, p, z(c), z(b), z(f), z(p), z(c), z(b), z(f), z(p), 0.2, 0.9)
-    for r in range(world):
-        c2, b2 = ret[r]
-        assert O.rel_l2(c2, want["c"]) < 1e-12 and O.rel_l2(b2, want["b"]) < 1e-12
-    assert np.array_equal(ret[0][0], ret[1][0])  # replicas stay bit-identical without any broadcast
+    for k, (inp, out, hin, c, b, f, p) in enumerate([_case(), _case2()]):
+        want = O.backprop_gpu_cc(inp, out, hin, c, b, f, p, z(c), z(b), z(f), z(p), z(c), z(b), z(f), z(p), 0.2, 0.9)
+        for r in range(world):
+            c2, b2 = ret[r][k]
+            assert O.rel_l2(c2, want["c"]) < 1e-12 and O.rel_l2(b2, want["b"]) < 1e-12
+        assert np.array_equal(ret[0][k][0], ret[1][k][0])  # replicas stay bit-identical without any broadcast
+
+
+def test_fused_layout_matches_the_engine_formula():
+    """dp.gbuf_len restates aefft_coord_gbuf_len (exported by libaefft.so; a host-only function)."""
+    import aefft_ctypes as A
+    import dp
+
+    for mode in (0, 1, 2):
+        for dD, dM, Nk, Nl in [(3, 16, 5, 5), (16, 32, 5, 5), (32, 64, 3, 7), (1, 8, 5, 5)]:
+            assert dp.gbuf_len(mode, dD, dM, Nk, Nl) == A.lib().aefft_coord_gbuf_len(mode, dD, dM, Nk, Nl)
+    offs, total = dp.fused_block_layout([(3, 16, 5, 5), (16, 32, 5, 5), (32, 64, 5, 5)], 2)
+    assert offs == [0, 2420, 2420 + 25649] and total == 2420 + 25649 + 102497
 
 
 def test_clip_is_nonlinear_so_reduce_raw_gradients():
@@ -95,6 +132,17 @@ def test_frame_range_partitions_the_global_batch():
 
 
 # ---------------------------------------------------------------------------------------------- frequency-bin sharding
+def test_row_slabs_partition_the_rows():
+    import dp
+
+    for Nx in (8, 64, 2048):
+        for world in (1, 2, 3, 8):
+            slabs = [dp.row_slab(r, world, Nx) for r in range(world)]
+            assert slabs[0][0] == 0 and sum(n for _, n in slabs) == Nx
+            for (r0, n), (r1, _) in zip(slabs, slabs[1:]):
+                assert r0 + n == r1
+
+
 def test_bin_slabs_partition_the_half_spectrum():
     import dp
 
@@ -135,7 +183,7 @@ def _shard_worker(rank, world, port, ret):
     Z = np.fft.rfft2(img)  # every rank holds the same frames; it keeps only its slab of columns
     c0, n = dp.bin_slab(rank, world, Ny)
     part = torch.from_numpy(_pruned_taps_partial(Z, Ny, Nk, Nl, c0, n))
-    dp.allreduce_partial_block(part, world)
+    dist.all_reduce(part, op=dist.ReduceOp.SUM)  # bin-sharded devices hold PARTIAL sums of the gradient block: add them
     ret[rank] = part.numpy()
     dist.destroy_process_group()
 

@@ -13,7 +13,62 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import ref_lib  # noqa: E402
 
 
+def fft_main():
+    """`--fft`: the reference's momentum-space path (fft_backproplib.cu + cuFFT, rebuilt for sm_100) at the BASELINE
+    config-3 shapes, one frame: autoenc_fft of the whole 3-pair stack at 1024x1024 (fft_l = 1, as training needs) and one
+    backprop_fft call (its hard-coded 100 iterations) per pair at the pair's resolution; a bench step is the forward plus
+    ONE iteration per pair, so seconds_per_frame_step = t(autoenc_fft) + sum_pairs t(backprop_fft) / 100."""
+    if not ref_lib.available():
+        print(json.dumps({"unavailable": "oracle/_ref/libref.so not built"}))
+        return
+    rng = np.random.default_rng(0)
+    size = int(os.environ.get("AEFFT_REF_FFT_SIZE", "1024"))
+    widths, D = [16, 32, 64], 3
+    encs, d, nx = [], D, size
+    shapes = [(D, size, size)]
+    for m in widths:
+        c = ((rng.random((m, d, 5, 5)) * 2 - 1) * 0.3).astype(np.float32)
+        encs.append((c, np.zeros(m, np.float32), np.ascontiguousarray(np.swapaxes(c, 0, 1)), np.zeros(d, np.float32), d, nx))
+        nx //= 2
+        shapes += [(d, nx, nx), (m, nx, nx)]
+        d = m
+    for (c, b, f, p, d0, nx0) in reversed(encs):
+        shapes += [(d0, nx0 // 2, nx0 // 2), (d0, nx0, nx0)]
+    net_c = [e[0] for e in encs] + [e[2] for e in reversed(encs)]
+    net_b = [e[1] for e in encs] + [e[3] for e in reversed(encs)]
+    scale = [2, 2, 2, -2, -2, -2]
+    x = np.floor(rng.random((D, size, size)) * 256).astype(np.float32)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)  # the reference prints "mse ..." lines
+    try:
+        ref_lib.autoenc_fft(x, net_c, net_b, scale, shapes, None, 1)  # pays CUDA context / cuFFT module load
+        t0 = time.perf_counter()
+        layers, cfs = ref_lib.autoenc_fft(x, net_c, net_b, scale, shapes, None, 1)
+        t_fwd = time.perf_counter() - t0
+        parts, t_bp = [], 0.0
+        P = len(encs)
+        for n in range(P):
+            c, b, f, p, d0, nx0 = encs[n]
+            inp, out = layers[2 * n + 1], layers[len(layers) - 2 - 2 * n]
+            t0 = time.perf_counter()
+            ref_lib.backprop_fft(inp, inp, out, cfs[n], c, cfs[2 * P - 1 - n], f, b, p, 0.2, 0)
+            dt = time.perf_counter() - t0
+            parts.append({"pair": f"{d0}->{c.shape[0]} @ {inp.shape[-2]}x{inp.shape[-1]}", "seconds_100_iterations": dt})
+            t_bp += dt / 100.0
+    finally:
+        os.dup2(saved, 1)
+    total = t_fwd + t_bp
+    print(json.dumps({"value": 1.0 / total, "unit": "frames/s", "seconds_per_frame_step": total, "autoenc_fft_seconds": t_fwd,
+                      "pairs": parts,
+                      "what": f"reference CUDA momentum path (fft_backproplib.cu + cuFFT rebuilt for sm_100, nvcc 12.9) at {size}x{size}, "
+                              "1 frame: autoenc_fft (fft_l=1) + one backprop_fft call per pair / its 100 iterations, through the "
+                              "nested-vector API incl. its per-call packing, H2D/D2H, plan creation and mallocs"}))
+
+
 def main():
+    if "--fft" in sys.argv:
+        return fft_main()
     if not ref_lib.available():
         print(json.dumps({"unavailable": "oracle/_ref/libref.so not built"}))
         return
