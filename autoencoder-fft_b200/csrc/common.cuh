@@ -264,6 +264,25 @@ int launch_axpby(aefft_ctx* ctx, float* y, const float* x, float a, float b, lon
 int launch_spec_mse(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx, int Ny, const float2* Xt, const float2* O, float* out,
                     int col0 = 0, int ncols = 0);
 
+// ---- momentum-space contractions on the tensor cores (spec_tc.cu): bin-major [bin][row][col] fp32 operands, interleaved
+// complex rows, embedded weight blocks [[Wr, -Wi], [Wi, Wr]]; see the header of spec_tc.cu
+bool spec_tc_eligible(int dD, int dM, int Nk, int Nl);
+// [R][S] complex (bins fastest) -> [S][R] complex, optionally in0 - in1
+int launch_to_binmajor(aefft_ctx* ctx, long long R, long long S, const float2* in0, const float2* in1, float2* out);
+// emb[w][2r+a][2c+b] for the R x C kernels `taps` [R][C][Nk][Nl] on the slab [col0, col0+ncols) (ncols <= 0: whole half spectrum)
+int launch_kernel_spectrum_emb(aefft_ctx* ctx, int R, int C, int Nk, int Nl, int Nx, int Ny, int col0, int ncols, const float* taps,
+                               float* emb);
+int launch_binmajor_to_taps(aefft_ctx* ctx, int R, int C, int transpose, int Nk, int Nl, int Nx, int Ny, int col0, int ncols,
+                            const float2* z, float* taps, float scale);
+int launch_tc_forward(aefft_ctx* ctx, long long S, int B, int C, int O, const float* in, const float* Wemb, float scale,
+                      const float* bias, float bias_scale, const float* sub, float* out, float* mse_out, double mse_scale, int ncols,
+                      int col0, int Ny);
+int launch_tc_adjoint(aefft_ctx* ctx, long long S, int B, int dD, int dM, const float* E, const float* Femb, float* G);
+int launch_tc_outer(aefft_ctx* ctx, long long S, int B, int nP, int nQ, const float* P, const float* Q, float scale, int conj_out,
+                    float* out);
+int launch_tc_dc_terms(aefft_ctx* ctx, int B, int dM, int dD, const float* G, const float* E, const float* bias_b, float* dFt,
+                       float* db, float* dp, float gs, float fs, float corr_scale);
+
 // ---- collectives inside the engine (comm.cu): NCCL on the ctx stream; op 0 = sum, 1 = average over the ranks
 int comm_allreduce(aefft_ctx* ctx, float* dev, int64_t n_floats, int op);
 // slab exchange of a bin-sharded transform: rank r sends send + r'*chunk floats to every r' and receives into

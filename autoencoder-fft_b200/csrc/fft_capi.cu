@@ -385,11 +385,70 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
   const float* bias_p = own_dc ? dp_w : nullptr;
   AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse, col0, ncols));  // "mse fft:" (:1440)
   if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse, 1));
-  // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1)
-  AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, bias_b, norm, q.H));
   const float del = 0.1f * del0;                                        // :1445
   const double Norm = (double)norm * 2.0 * dM * dD * (double)Nx * Ny;   // :399
   const float gscale = (float)(1.0 / (Norm * (double)B));
+  // Tensor-core path (spec_tc.cu): pairs with >= 8 channels on both sides run the five per-bin contractions of an
+  // iteration as real GEMMs on tcgen05 over bin-major operands; the frame spectra are transposed once per call, the
+  // kernel spectra are generated directly in the embedded bin-major form, the kernel-space gradients are reduced from
+  // the bin-major gradient spectra.  Callers that pass spectra caches (cfreq / ffreq) keep the bins-fastest path, whose
+  // first iteration consumes those caches as they are.
+  const bool use_tc = spec_tc_eligible(dD, dM, Nk, Nl) && !cfreq && !ffreq && n_iter > 0;
+  if (use_tc) {
+    float *Xb, *Xtb, *Eb, *Hb, *Gb, *Cemb, *Femb, *dCt, *dFt;
+    AE_TRY(ctx->getT("tc_Xb", 2 * nXs, &Xb));
+    AE_TRY(ctx->getT("tc_Eb", 2 * nXs, &Eb));
+    AE_TRY(ctx->getT("tc_Hb", 2 * nHs, &Hb));
+    AE_TRY(ctx->getT("tc_Gb", 2 * nHs, &Gb));
+    AE_TRY(ctx->getT("tc_Cemb", 4 * nKS, &Cemb));
+    AE_TRY(ctx->getT("tc_Femb", 4 * nKS, &Femb));
+    AE_TRY(ctx->getT("tc_dCt", 2 * nKS, &dCt));
+    AE_TRY(ctx->getT("tc_dFt", 2 * nKS, &dFt));
+    AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, q.X, nullptr, (float2*)Xb));
+    Xtb = Xb;
+    if (Xt != q.X) {
+      AE_TRY(ctx->getT("tc_Xtb", 2 * nXs, &Xtb));
+      AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, Xt, nullptr, (float2*)Xtb));
+    }
+    AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, q.O, Xt, (float2*)Eb));  // E = O - Xt of the caller's `out`
+    AE_TRY(launch_kernel_spectrum_emb(ctx, dM, dD, Nk, Nl, Nx, Ny, col0, ncols, dc_w, Cemb));
+    AE_TRY(launch_kernel_spectrum_emb(ctx, dD, dM, Nk, Nl, Nx, Ny, col0, ncols, df_w, Femb));
+    // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1)
+    AE_TRY(launch_tc_forward(ctx, S, (int)B, dD, dM, Xb, Cemb, 1.f / (float)dM, bias_b, norm, nullptr, Hb, nullptr, 0.0, 0, 0, 0));
+    const double mse_scale = 1.0 / ((double)dD * Nx * Ny) / (2.0 * dM * Nx * Ny) / (double)B;
+    for (int n = 0; n < n_iter; n++) {
+      AE_TRY(launch_tc_adjoint(ctx, S, (int)B, dD, dM, Eb, Femb, Gb));                               // G = E conj(F)
+      AE_TRY(launch_tc_outer(ctx, S, (int)B, dM, dD, Gb, Xb, gscale, 0, dCt));                       // dC[m][d] = G conj(X)
+      AE_TRY(launch_tc_outer(ctx, S, (int)B, dM, dD, Hb, Eb, gscale * (float)dM, 1, dFt));           // dF[d][m] = E conj(dM H) at [m][d]
+      if (own_dc)
+        AE_TRY(launch_tc_dc_terms(ctx, (int)B, dM, dD, Gb, Eb, bias_b, dFt, q.db, q.dp, (float)((double)norm / (Norm * (double)B)),
+                                  gscale, -(float)(dM - 1) * norm));
+      else AE_CUDA(cudaMemsetAsync(q.db, 0, (size_t)(dM + dD) * sizeof(float), st));
+      AE_TRY(launch_binmajor_to_taps(ctx, dM, dD, 0, Nk, Nl, Nx, Ny, col0, ncols, (const float2*)dCt, q.taps, 1.f));
+      AE_TRY(launch_binmajor_to_taps(ctx, dM, dD, 1, Nk, Nl, Nx, Ny, col0, ncols, (const float2*)dFt, q.taps + nC, 1.f));
+      const bool fold_div = sharded && maxdiff;
+      if (fold_div) {
+        AE_TRY(launch_gradient_diff(ctx, dM, dD, Nk, Nl, dc_w, df_w, db_w, dp_w, q.div, srank, world));
+        AE_TRY(launch_axpby(ctx, q.taps, q.div, 1.f, -10.f, (long long)(2 * nC + dM + dD)));
+      }
+      AE_TRY(reduce_over_devices(q.taps, (int64_t)(2 * nC + dM + dD)));
+      AE_TRY(launch_fft_update(ctx, dM, dD, Nk, Nl, dc_w, df_w, db_w, dp_w, q.taps, q.taps + nC, q.db, q.dp, q.Dc, q.Df, q.Db,
+                               q.Dp, del, fold_div ? 0 : maxdiff, q.div));
+      AE_TRY(launch_kernel_spectrum_emb(ctx, dM, dD, Nk, Nl, Nx, Ny, col0, ncols, dc_w, Cemb));
+      AE_TRY(launch_kernel_spectrum_emb(ctx, dD, dM, Nk, Nl, Nx, Ny, col0, ncols, df_w, Femb));
+      AE_TRY(launch_tc_forward(ctx, S, (int)B, dD, dM, Xb, Cemb, 1.f / (float)dM, bias_b, norm, nullptr, Hb, nullptr, 0.0, 0, 0, 0));
+      // re-forward O = conv(H; F, p), kept as E = O - Xt, and its mse (:1460-1463)
+      AE_TRY(launch_tc_forward(ctx, S, (int)B, dM, dD, Hb, Femb, 1.f / (float)dD, bias_p, norm, Xtb, Eb, q.mse + n + 1, mse_scale,
+                               ncols, col0, Ny));
+      if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse + n + 1, 1));
+    }
+    if (!sharded) {  // the bins-fastest spectra of the trained kernels, for the export below
+      AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C, col0, ncols));
+      AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F, col0, ncols));
+    }
+  } else {
+  // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1)
+  AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, bias_b, norm, q.H));
   for (int n = 0; n < n_iter; n++) {
     // G[m] = sum_d1 (O - Xt)[d1] conj(F[d1][m])
     AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.O, Xt, q.F, S, (int64_t)dM * S, 1, 1.f, nullptr, 0.f, q.G));
@@ -421,6 +480,7 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
     AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse + n + 1, col0, ncols));
     if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse + n + 1, 1));
   }
+  }  // !use_tc
   if (use_comm) AE_TRY(comm_allreduce(ctx, q.mse, (int64_t)n_iter + 1, sharded ? 0 : 1));
   // store_cfreq (:1484-1485) and export_cfreq (:1487-1488: c,f re-derived from the spectra: C2R/(NxNy) + kernel_invpad)
   if (cfreq) AE_CUDA(cudaMemcpyAsync(cfreq, q.C, nKS * sizeof(float2), k_out, st));

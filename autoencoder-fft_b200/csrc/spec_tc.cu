@@ -1,0 +1,663 @@
+// Momentum-space per-bin channel contractions on the tensor cores (tcgen05, kind::tf32, 3xTF32 split).
+//
+// Replaces conv_k (fft_backproplib.cu:162-189) and the contractions inside gradient_k_io (:395-475) for layer pairs
+// with >= 8 channels on both sides.  Per frequency bin w the reference computes small COMPLEX matrix products over the
+// channels (forward, G) or over the frames (dC, dF -- this engine's batch extension); here every bin is one REAL GEMM
+//     D_w [M x N] = A_w [M x K] * B_w [N x K]^T
+// on interleaved (re, im) data: a complex row (x_0, x_1, ...) is the real row (Re x_0, Im x_0, Re x_1, ...), and a
+// complex weight matrix W [r][c] is stored "embedded" as the real 2r x 2c matrix [[Wr, -Wi], [Wi, Wr]] so that
+// interleaved in -> interleaved out with exactly 4 real multiplies per complex multiply (no wasted tensor work).
+//
+// Data layout: everything the tensor path touches is BIN-MAJOR, [bin][row][col] fp32 with `col` contiguous:
+//   X~, E~ [S][B][2 dD]   H~, G~ [S][B][2 dM]   Cemb [S][2 dM][2 dD]   Femb [S][2 dD][2 dM]   dC, dF^T [S][dM][dD][2]
+// so one bin's operand is one contiguous block and TMA lands it directly in the UMMA canonical layout:
+//   K-major operand  (rows = M/N index, K contiguous): box {32 floats, rows}, SWIZZLE_128B   -> UMMA SWIZZLE_128B
+//   MN-major operand (rows = K index, M/N contiguous): boxes {32 floats, 32 rows}, SWIZZLE_128B_ATOM_32B
+//                                                      -> UMMA SWIZZLE_128B_BASE32B (the only transposed tf32 layout)
+// (descriptor strides measured with tools/probe_tf32.cu).  The same Femb block serves O = H F^T as a K-major operand and
+// G = E conj(F) as an MN-major one; the frame-reduced outer products read G~, H~, X~, E~ as MN-major operands (frames = K).
+//
+// fp32-grade results from tf32 products: x = hi + lo with hi = x & 0xffffe000 (exactly a tf32 number), lo = x - hi (exact in
+// fp32); D += hi*hi + hi*lo + lo*hi in the fp32 TMEM accumulator: 1e-6 relative against fp64 (probe), the same budget as
+// the BF16X3 split of the coordinate-space kernels.  The split is elementwise and position preserving: the splitter warps
+// rewrite the TMA-landed tile in place (hi) and into a twin buffer (lo) without caring about the swizzle.
+//
+// Kernel: persistent, one CTA per SM, warp specialised: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
+// (TMEM -> registers -> global), warps 6-9 splitters.  Unit of the smem ring = one bin x one 32-wide K block
+// (A 16 KB + B NT*128 B, twice for hi/lo); TMEM holds two accumulators so the epilogue of bin i overlaps the MMAs of i+1.
+// Bound: HBM (per bin a 128 x 128 x 64 product is ~0.8 us of tensor time but 128+ KB of traffic).
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "pipe.cuh"
+#include "tma.cuh"
+
+namespace aefft {
+
+namespace {
+
+using namespace umma;
+
+constexpr int TC_THREADS = 320;
+constexpr int TC_MAX_STAGES = 5;
+enum { EPI_STORE = 0, EPI_OUTER = 1 };
+
+struct TcParams {
+  CUtensorMap amap, bmap;
+  int a_mn, b_mn;        // 0: K-major, 1: MN-major
+  int Mtot, Ntot;        // extents of D per bin
+  int n_mt, n_nt, n_kb;  // tiles: M 128, N NT, K 32
+  int NT;
+  long long n_items;     // bins * n_mt * n_nt
+  int stages;
+  uint32_t stage_bytes;
+  int epi;
+  float scale;
+  const float* bias;     // EPI_STORE: + bias[n / 2] * bias_scale on even columns n (real parts) of bin 0
+  float bias_scale;
+  const float* sub;      // EPI_STORE: - sub[bin][row][n]
+  float* out;
+  int conj_out;          // EPI_OUTER: negate the imaginary parts
+  double* sq_part;       // EPI_STORE: per-warp sums of hw(bin) * out^2 ([grid][4]) or nullptr
+  int ncols, col0, Ny;   // Hermitian weight of bin w: column col0 + w % ncols in {0, Ny/2} -> 1, else 2
+};
+
+__device__ __forceinline__ uint64_t desc_k(uint32_t addr) {  // K-major, SWIZZLE_128B: SBO = 8 rows x 128 B
+  return make_desc(addr, 16, 1024) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr) {  // MN-major, SWIZZLE_128B_BASE32B: 32-wide blocks 4096 B apart
+  return make_desc(addr, 4096, 512) | ((uint64_t)1 << 61);    // (32 K rows x 128 B), 4-row K groups 512 B apart
+}
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d),
+      "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) spec_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full[TC_MAX_STAGES], ready[TC_MAX_STAGES], empty[TC_MAX_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  uint32_t tcols = 32;
+  while ((int)tcols < 2 * p.NT) tcols <<= 1;
+  if (warp == 0) tmem_alloc(&tmem_slot, tcols);
+  if (tid == 32) {
+    for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    fence_mbar_init();
+  }
+  if (tid == 0) { tma::tma_prefetch_desc(&p.amap); tma::tma_prefetch_desc(&p.bmap); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = tmem_slot;
+  const int per_bin = p.n_mt * p.n_nt;
+  const uint32_t a_lo = 16384, b_hi = 32768, b_lo = 32768 + (uint32_t)p.NT * 128;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      Ring r(p.stages);
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const long long w = item / per_bin;
+        const int rem = (int)(item - w * per_bin), mt = rem / p.n_nt, nt = rem - mt * p.n_nt;
+        int a_blocks = (p.Mtot - mt * 128 + 31) / 32;
+        if (a_blocks > 4) a_blocks = 4;
+        const uint32_t bytes = (p.a_mn ? (uint32_t)a_blocks * 4096u : 16384u) + (uint32_t)p.NT * 128u;
+        for (int kb = 0; kb < p.n_kb; kb++) {
+          mbar_wait_role<false>(&empty[r.slot], r.phase ^ 1);
+          uint8_t* st = smem + (size_t)r.slot * p.stage_bytes;
+          tma::mbar_expect_tx(&full[r.slot], bytes);
+          if (!p.a_mn) {
+            tma::tma_load_3d(st, &p.amap, kb * 32, mt * 128, (int)w, &full[r.slot]);
+          } else {
+            for (int j = 0; j < a_blocks; j++) tma::tma_load_3d(st + j * 4096, &p.amap, mt * 128 + j * 32, kb * 32, (int)w, &full[r.slot]);
+          }
+          if (!p.b_mn) {
+            tma::tma_load_3d(st + b_hi, &p.bmap, kb * 32, nt * p.NT, (int)w, &full[r.slot]);
+          } else {
+            for (int j = 0; j < p.NT / 32; j++)
+              tma::tma_load_3d(st + b_hi + j * 4096, &p.bmap, nt * p.NT + j * 32, kb * 32, (int)w, &full[r.slot]);
+          }
+          r.next();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      Ring r(p.stages);
+      const uint32_t idesc = idesc_tf32(128, p.NT, p.a_mn, p.b_mn);
+      const uint32_t a_step = p.a_mn ? 1024u : 32u, b_step = p.b_mn ? 1024u : 32u;
+      int it = 0;
+      for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x, it++) {
+        const int a = it & 1;
+        mbar_wait_role<false>(&acc_empty[a], ((it >> 1) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t d = tb + (uint32_t)(a * p.NT);
+        uint32_t acc = 0;
+        for (int kb = 0; kb < p.n_kb; kb++) {
+          mbar_wait_role<false>(&ready[r.slot], r.phase);
+          fence_after_sync();
+          const uint32_t st = smem_u32(smem + (size_t)r.slot * p.stage_bytes);
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {
+            const uint32_t ao = st + ks * a_step, bo = st + b_hi + ks * b_step;
+            const uint64_t ah = p.a_mn ? desc_mn(ao) : desc_k(ao), al = p.a_mn ? desc_mn(ao + a_lo) : desc_k(ao + a_lo);
+            const uint64_t bh = p.b_mn ? desc_mn(bo) : desc_k(bo);
+            const uint64_t bl = p.b_mn ? desc_mn(bo + (b_lo - b_hi)) : desc_k(bo + (b_lo - b_hi));
+            mma_tf32(d, ah, bh, idesc, acc);
+            mma_tf32(d, ah, bl, idesc, 1);
+            mma_tf32(d, al, bh, idesc, 1);
+            acc = 1;
+          }
+          commit(&empty[r.slot]);  // the stage may be refilled once these MMAs have read it
+          r.next();
+        }
+        commit(&acc_full[a]);
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------------------------------ epilogue
+    const int q = warp & 3;  // TMEM lanes 32q .. 32q+31 belong to this warp
+    double sq = 0.0;
+    int it = 0;
+    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x, it++) {
+      const long long w = item / per_bin;
+      const int rem = (int)(item - w * per_bin), mt = rem / p.n_nt, nt = rem - mt * p.n_nt;
+      const int a = it & 1;
+      mbar_wait_role<false>(&acc_full[a], (it >> 1) & 1);
+      fence_after_sync();
+      const int row = mt * 128 + q * 32 + lane;
+      const uint32_t taddr = tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.NT);
+      if (p.epi == EPI_STORE) {
+        const bool row_ok = row < p.Mtot;
+        const long long base = (w * p.Mtot + row) * (long long)p.Ntot + (long long)nt * p.NT;
+        float hw = 2.f;
+        if (p.sq_part) {
+          const int wy = p.col0 + (int)(w % p.ncols);
+          if (wy == 0 || wy == p.Ny / 2) hw = 1.f;
+        }
+        float part = 0.f;
+        for (int c0 = 0; c0 < p.NT; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          const int n0 = nt * p.NT + c0;
+          if (!row_ok || n0 >= p.Ntot) continue;
+#pragma unroll
+          for (int e = 0; e < 16; e++) v[e] *= p.scale;
+          if (w == 0 && p.bias) {
+#pragma unroll
+            for (int e = 0; e < 16; e += 2) v[e] = fmaf(__ldg(p.bias + (n0 + e) / 2), p.bias_scale, v[e]);
+          }
+          if (p.sub) {
+            const float4* s4 = reinterpret_cast<const float4*>(p.sub + base + c0);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const float4 s = __ldg(s4 + e);
+              v[4 * e] -= s.x; v[4 * e + 1] -= s.y; v[4 * e + 2] -= s.z; v[4 * e + 3] -= s.w;
+            }
+          }
+          if (p.sq_part) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) part = fmaf(v[e], v[e], part);
+          }
+          float4* o4 = reinterpret_cast<float4*>(p.out + base + c0);
+#pragma unroll
+          for (int e = 0; e < 4; e++) o4[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+        }
+        sq += (double)(part * hw);
+      } else {
+        // frame-reduced outer product of two interleaved complex operands: lane pair (2m, 2m+1) holds the four real sums
+        // of row m; re = D[mr][dr] + D[mi][di], im = D[mi][dr] - D[mr][di]  (conj_out flips im)
+        const int Mh = p.Mtot >> 1, Nh = p.Ntot >> 1;
+        const int m = row >> 1;
+        const bool odd = lane & 1;
+        for (int c0 = 0; c0 < p.NT; c0 += 16) {
+          float v[16];
+          tmem_ld16(taddr + c0, v);
+          const int n0 = nt * p.NT + c0;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const float pa = v[2 * i], pb = __shfl_xor_sync(0xffffffffu, v[2 * i + 1], 1);
+            float r = odd ? pa - pb : pa + pb;
+            if (odd && p.conj_out) r = -r;
+            const int d = (n0 >> 1) + i;
+            if (m < Mh && d < Nh) p.out[((w * Mh + m) * (long long)Nh + d) * 2 + (odd ? 1 : 0)] = r * p.scale;
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tma::mbar_arrive(&acc_empty[a]);
+    }
+    if (p.sq_part) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sq += __shfl_down_sync(0xffffffffu, sq, o);
+      if (lane == 0) p.sq_part[(size_t)blockIdx.x * 4 + q] = sq;
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------ splitters
+    const int t = tid - 6 * 32;  // 0..127
+    Ring r(p.stages);
+    const int nb4 = p.NT * 8;    // float4 per B panel
+    for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      int na4 = 1024;
+      if (p.a_mn) {
+        const long long w = item / per_bin;
+        const int mt = (int)(item - w * per_bin) / p.n_nt;
+        int a_blocks = (p.Mtot - mt * 128 + 31) / 32;
+        na4 = (a_blocks > 4 ? 4 : a_blocks) * 256;
+      }
+      for (int kb = 0; kb < p.n_kb; kb++) {
+        mbar_wait_role<false>(&full[r.slot], r.phase);
+        uint8_t* st = smem + (size_t)r.slot * p.stage_bytes;
+        uint4* ah = reinterpret_cast<uint4*>(st);
+        float4* al = reinterpret_cast<float4*>(st + a_lo);
+        uint4* bh = reinterpret_cast<uint4*>(st + b_hi);
+        float4* bl = reinterpret_cast<float4*>(st + b_lo);
+        auto split = [](uint4* hi, float4* lo, int i) {
+          uint4 u = hi[i];
+          const float4 x = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+          u.x &= 0xffffe000u; u.y &= 0xffffe000u; u.z &= 0xffffe000u; u.w &= 0xffffe000u;
+          hi[i] = u;
+          lo[i] = make_float4(x.x - __uint_as_float(u.x), x.y - __uint_as_float(u.y), x.z - __uint_as_float(u.z),
+                              x.w - __uint_as_float(u.w));
+        };
+#pragma unroll 4
+        for (int i = t; i < na4; i += 128) split(ah, al, i);
+#pragma unroll 4
+        for (int i = t; i < nb4; i += 128) split(bh, bl, i);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tma::mbar_arrive(&ready[r.slot]);
+        r.next();
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, tcols);
+}
+
+__global__ void sq_final_kernel(const double* __restrict__ part, int n, double scale, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)(red[0] * scale);
+}
+
+// ---- [R][S] complex (bins fastest) -> [S][R] complex (bin-major), optionally minus a second source: 32 x 32 tiles
+__global__ void __launch_bounds__(256) to_binmajor_kernel(const float2* __restrict__ in0, const float2* __restrict__ in1,
+                                                          float2* __restrict__ out, long long R, long long S) {
+  __shared__ float2 tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long s0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const long long r = r0 + ty + 8 * k, s = s0 + tx;
+    float2 v = make_float2(0.f, 0.f);
+    if (r < R && s < S) {
+      v = __ldg(in0 + r * S + s);
+      if (in1) { const float2 u = __ldg(in1 + r * S + s); v.x -= u.x; v.y -= u.y; }
+    }
+    tile[ty + 8 * k][tx] = v;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const long long s = s0 + ty + 8 * k, r = r0 + tx;
+    if (r < R && s < S) out[s * R + r] = tile[tx][ty + 8 * k];
+  }
+}
+
+// ---- embedded kernel spectra, bin-major: emb[w][2r+a][2c+b] from the taps of the R x C kernels (pruned 25-tap DFT)
+constexpr int KE_BINS = 8, KE_MAXT = 64;
+__global__ void __launch_bounds__(256) kernel_spectrum_emb_kernel(const float* __restrict__ taps, float* __restrict__ emb, int R,
+                                                                  int C, int Nk, int Nl, int Nx, int Ny, int ncols, int col0,
+                                                                  long long S, const float2* __restrict__ twx,
+                                                                  const float2* __restrict__ twy) {
+  __shared__ float2 ph[KE_BINS][KE_MAXT];
+  const int T = Nk * Nl;
+  const long long w0 = (long long)blockIdx.x * KE_BINS;
+  for (int i = threadIdx.x; i < KE_BINS * T; i += blockDim.x) {
+    const int bi = i / T, t = i - bi * T, k = t / Nl, l = t - k * Nl;
+    const long long w = w0 + bi;
+    float2 v = make_float2(0.f, 0.f);
+    if (w < S) {
+      const int wx = (int)(w / ncols), wy = col0 + (int)(w - (long long)wx * ncols);
+      const float2 ex = twx[(wx * ((k - Nk / 2) & (Nx - 1))) & (Nx - 1)];
+      const float2 ey = twy[(wy * ((l - Nl / 2) & (Ny - 1))) & (Ny - 1)];
+      v = make_float2(ex.x * ey.x - ex.y * ey.y, ex.x * ey.y + ex.y * ey.x);
+    }
+    ph[bi][t] = v;
+  }
+  __syncthreads();
+  const int e = blockIdx.y * blockDim.x + threadIdx.x;
+  if (e >= R * C) return;
+  const int r = e / C, c = e - r * C;
+  float tp[KE_MAXT];
+#pragma unroll 1
+  for (int t = 0; t < T; t++) tp[t] = taps[(size_t)e * T + t];
+  for (int bi = 0; bi < KE_BINS; bi++) {
+    const long long w = w0 + bi;
+    if (w >= S) break;
+    float vr = 0.f, vi = 0.f;
+    for (int t = 0; t < T; t++) { vr = fmaf(tp[t], ph[bi][t].x, vr); vi = fmaf(tp[t], ph[bi][t].y, vi); }
+    float* o = emb + ((w * 2 * R + 2 * r) * 2 * (long long)C + 2 * c);
+    *reinterpret_cast<float2*>(o) = make_float2(vr, -vi);
+    *reinterpret_cast<float2*>(o + 2 * C) = make_float2(vi, vr);
+  }
+}
+// fixed-size tap registers (the generic kernel above spills for T = 25: tp[] is indexed in a runtime loop)
+template <int T>
+__global__ void __launch_bounds__(256) kernel_spectrum_emb_kernel_t(const float* __restrict__ taps, float* __restrict__ emb, int R,
+                                                                    int C, int Nk, int Nl, int Nx, int Ny, int ncols, int col0,
+                                                                    long long S, const float2* __restrict__ twx,
+                                                                    const float2* __restrict__ twy) {
+  __shared__ float2 ph[KE_BINS][T];
+  const long long w0 = (long long)blockIdx.x * KE_BINS;
+  for (int i = threadIdx.x; i < KE_BINS * T; i += blockDim.x) {
+    const int bi = i / T, t = i - bi * T, k = t / Nl, l = t - k * Nl;
+    const long long w = w0 + bi;
+    float2 v = make_float2(0.f, 0.f);
+    if (w < S) {
+      const int wx = (int)(w / ncols), wy = col0 + (int)(w - (long long)wx * ncols);
+      const float2 ex = twx[(wx * ((k - Nk / 2) & (Nx - 1))) & (Nx - 1)];
+      const float2 ey = twy[(wy * ((l - Nl / 2) & (Ny - 1))) & (Ny - 1)];
+      v = make_float2(ex.x * ey.x - ex.y * ey.y, ex.x * ey.y + ex.y * ey.x);
+    }
+    ph[bi][t] = v;
+  }
+  __syncthreads();
+  const int e = blockIdx.y * blockDim.x + threadIdx.x;
+  if (e >= R * C) return;
+  const int r = e / C, c = e - r * C;
+  float tp[T];
+#pragma unroll
+  for (int t = 0; t < T; t++) tp[t] = __ldg(taps + (size_t)e * T + t);
+#pragma unroll 2
+  for (int bi = 0; bi < KE_BINS; bi++) {
+    const long long w = w0 + bi;
+    if (w >= S) break;
+    float vr = 0.f, vi = 0.f;
+#pragma unroll
+    for (int t = 0; t < T; t++) { vr = fmaf(tp[t], ph[bi][t].x, vr); vi = fmaf(tp[t], ph[bi][t].y, vi); }
+    float* o = emb + ((w * 2 * R + 2 * r) * 2 * (long long)C + 2 * c);
+    *reinterpret_cast<float2*>(o) = make_float2(vr, -vi);
+    *reinterpret_cast<float2*>(o + 2 * C) = make_float2(vi, vr);
+  }
+}
+
+// ---- kernel-space gradients from bin-major gradient spectra: part[(n*nsplit + sp)*T + t] = sum over the bins of split sp of
+//      h(wy) Re( z[w][e] conj(Ex[k](wx) Ey[l](wy)) ),  n = e or its transpose (the dF^T block holds dF[d][m] at [m][d])
+constexpr int BT_BINS = 16;
+template <int T>
+__global__ void __launch_bounds__(128) binmajor_to_taps_kernel(const float2* __restrict__ z, float* __restrict__ part, int E, int R,
+                                                               int C, int transpose, int Nk, int Nl, int Nx, int Ny, int ncols,
+                                                               int col0, long long S, const float2* __restrict__ twx,
+                                                               const float2* __restrict__ twy) {
+  __shared__ float2 ph[BT_BINS][T];
+  const int nsplit = gridDim.y, sp = blockIdx.y;
+  const long long w_lo = S * sp / nsplit, w_hi = S * (sp + 1) / nsplit;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  float g[T];
+#pragma unroll
+  for (int t = 0; t < T; t++) g[t] = 0.f;
+  for (long long wb = w_lo; wb < w_hi; wb += BT_BINS) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < BT_BINS * T; i += blockDim.x) {
+      const int bi = i / T, t = i - bi * T, k = t / Nl, l = t - k * Nl;
+      const long long w = wb + bi;
+      float2 v = make_float2(0.f, 0.f);
+      if (w < w_hi) {
+        const int wx = (int)(w / ncols), wy = col0 + (int)(w - (long long)wx * ncols);
+        const float h = (wy == 0 || wy == Ny / 2) ? 1.f : 2.f;
+        const float2 ex = twx[(wx * ((k - Nk / 2) & (Nx - 1))) & (Nx - 1)];
+        const float2 ey = twy[(wy * ((l - Nl / 2) & (Ny - 1))) & (Ny - 1)];
+        v = make_float2(h * (ex.x * ey.x - ex.y * ey.y), h * (ex.x * ey.y + ex.y * ey.x));
+      }
+      ph[bi][t] = v;
+    }
+    __syncthreads();
+    if (e < E) {
+#pragma unroll 2
+      for (int bi = 0; bi < BT_BINS; bi++) {
+        const long long w = wb + bi;
+        if (w >= w_hi) break;
+        const float2 v = __ldg(z + w * E + e);
+#pragma unroll
+        for (int t = 0; t < T; t++) g[t] = fmaf(v.x, ph[bi][t].x, fmaf(v.y, ph[bi][t].y, g[t]));
+      }
+    }
+  }
+  if (e < E) {
+    int n = e;
+    if (transpose) { const int r = e / C, c = e - r * C; n = c * R + r; }
+#pragma unroll
+    for (int t = 0; t < T; t++) part[((size_t)n * nsplit + sp) * T + t] = g[t];
+  }
+}
+__global__ void taps_final_kernel(const float* __restrict__ part, float* __restrict__ taps, long long total, int nsplit, int T,
+                                  float scale) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long n = idx / T;
+  const int t = (int)(idx - n * T);
+  double s = 0.0;
+  for (int sp = 0; sp < nsplit; sp++) s += (double)part[(n * nsplit + sp) * T + t];
+  taps[idx] = (float)(s * (double)scale);
+}
+
+// ---- DC-bin terms of gradient_k_io (:447-473) on bin-major data (bin 0 = the first block):
+//   db[m] = gs * sum_b Re G[b][m](0);  dp[d] = gs * sum_b Re E[b][d](0);
+//   dF^T[0][m][d] += fs * corr[m] * sum_b E[b][d](0)   (H-hat's bias correction, quirk F1; corr real)
+__global__ void dc_terms_kernel(const float* __restrict__ G, const float* __restrict__ E, const float* __restrict__ bias_b,
+                                float* __restrict__ dFt, float* __restrict__ db, float* __restrict__ dp, int B, int dM, int dD,
+                                float gs, float fs, float corr_scale) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < dM) {
+    double s = 0.0;
+    for (int b = 0; b < B; b++) s += (double)G[(size_t)b * 2 * dM + 2 * n];
+    db[n] = (float)(s * (double)gs);
+  } else if (n < dM + dD) {
+    const int d = n - dM;
+    double sr = 0.0, si = 0.0;
+    for (int b = 0; b < B; b++) { sr += (double)E[(size_t)b * 2 * dD + 2 * d]; si += (double)E[(size_t)b * 2 * dD + 2 * d + 1]; }
+    dp[d] = (float)(sr * (double)gs);
+    if (bias_b)
+      for (int m = 0; m < dM; m++) {
+        const double corr = (double)bias_b[m] * (double)corr_scale * (double)fs;
+        dFt[((size_t)m * dD + d) * 2] += (float)(corr * sr);
+        dFt[((size_t)m * dD + d) * 2 + 1] += (float)(corr * si);
+      }
+  }
+}
+
+struct TcOperand {
+  const float* base;
+  int rows, cols;  // memory [S][rows][cols]
+  int mn;          // 0: rows = M/N index, cols = K (K-major); 1: rows = K, cols = M/N index (MN-major)
+};
+
+int launch_bgemm(aefft_ctx* ctx, const char* name, long long S, const TcOperand& A, const TcOperand& B, int Mtot, int Ntot,
+                 int Ktot, int epi, float scale, const float* bias, float bias_scale, const float* sub, float* out, int conj_out,
+                 float* sq_out, double sq_scale, int ncols, int col0, int Ny, double alg_bytes) {
+  AE_ARG(S > 0 && S < (1LL << 31) && Mtot > 0 && Ntot > 0 && Ktot > 0 && Ntot % 16 == 0 && Mtot % 2 == 0);
+  AE_ARG((A.mn ? A.cols : A.rows) == Mtot && (A.mn ? A.rows : A.cols) == Ktot);
+  AE_ARG((B.mn ? B.cols : B.rows) == Ntot && (B.mn ? B.rows : B.cols) == Ktot);
+  AE_ARG(A.cols % 4 == 0 && B.cols % 4 == 0);
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.a_mn = A.mn; p.b_mn = B.mn; p.Mtot = Mtot; p.Ntot = Ntot;
+  int NT = Ntot <= 256 ? Ntot : 256;
+  if (B.mn) NT = (NT + 31) / 32 * 32;
+  p.NT = NT;
+  p.n_mt = (Mtot + 127) / 128; p.n_nt = (Ntot + NT - 1) / NT; p.n_kb = (Ktot + 31) / 32;
+  p.n_items = S * p.n_mt * p.n_nt;
+  p.stage_bytes = 32768u + 2u * (uint32_t)NT * 128u;
+  p.stages = (int)((227u * 1024u - 2048u) / p.stage_bytes);
+  if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  AE_ARG(p.stages >= 2);
+  p.epi = epi; p.scale = scale; p.bias = bias; p.bias_scale = bias_scale; p.sub = sub; p.out = out; p.conj_out = conj_out;
+  p.ncols = ncols > 0 ? ncols : 1; p.col0 = col0; p.Ny = Ny;
+  int rc = A.mn ? tma::make_tmap_3d_f32(&p.amap, A.base, A.cols, A.rows, S, 32, 32, 1, 2)
+                : tma::make_tmap_3d_f32(&p.amap, A.base, A.cols, A.rows, S, 32, 128, 1, 1);
+  if (rc == 0)
+    rc = B.mn ? tma::make_tmap_3d_f32(&p.bmap, B.base, B.cols, B.rows, S, 32, 32, 1, 2)
+              : tma::make_tmap_3d_f32(&p.bmap, B.base, B.cols, B.rows, S, 32, NT, 1, 1);
+  if (rc != 0) { set_error("spec_tc: cuTensorMapEncodeTiled failed (%d)", rc); return AEFFT_ERR_CUDA; }
+  const long long grid = p.n_items < ctx->sm_count ? p.n_items : ctx->sm_count;
+  double* part = nullptr;
+  if (sq_out) {
+    AE_TRY(ctx->getT("tc_sq_part", (size_t)grid * 4, &part));
+    p.sq_part = part;
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  AE_TRY(ctx->ensure_dyn_smem((const void*)spec_tc_kernel, smem));
+  {
+    ProfScope prof(ctx, name, 2.0 * (double)S * Mtot * Ntot * Ktot, alg_bytes);
+    spec_tc_kernel<<<(unsigned)grid, TC_THREADS, smem, ctx->stream>>>(p);
+    ctx->launches++;
+  }
+  AE_CUDA(cudaGetLastError());
+  if (sq_out) {
+    sq_final_kernel<<<1, 256, 0, ctx->stream>>>(part, (int)grid * 4, sq_scale, sq_out);
+    ctx->launches++;
+    AE_CUDA(cudaGetLastError());
+  }
+  return AEFFT_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ public (engine-internal)
+
+bool spec_tc_eligible(int dD, int dM, int Nk, int Nl) {
+  return dD % 8 == 0 && dM % 8 == 0 && dD >= 8 && dM >= 8 && Nk * Nl <= KE_MAXT && !getenv("AEFFT_NO_SPEC_TC");
+}
+
+int launch_to_binmajor(aefft_ctx* ctx, long long R, long long S, const float2* in0, const float2* in1, float2* out) {
+  dim3 grid((unsigned)((S + 31) / 32), (unsigned)((R + 31) / 32));
+  AE_ARG(grid.y <= 65535);
+  ProfScope prof(ctx, "spec_to_binmajor", 0.0, 8.0 * R * S * (in1 ? 3 : 2));
+  to_binmajor_kernel<<<grid, 256, 0, ctx->stream>>>(in0, in1, out, R, S);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+int launch_kernel_spectrum_emb(aefft_ctx* ctx, int R, int C, int Nk, int Nl, int Nx, int Ny, int col0, int ncols, const float* taps,
+                               float* emb) {
+  const float2 *twx, *twy;
+  AE_TRY(get_twiddles(ctx, Nx, &twx));
+  AE_TRY(get_twiddles(ctx, Ny, &twy));
+  if (ncols <= 0) { ncols = Ny / 2 + 1; col0 = 0; }
+  const long long S = (long long)Nx * ncols;
+  const int T = Nk * Nl;
+  AE_ARG(T <= KE_MAXT);
+  dim3 grid((unsigned)((S + KE_BINS - 1) / KE_BINS), (unsigned)((R * C + 255) / 256));
+  ProfScope prof(ctx, "kernel_spectrum_emb", 4.0 * S * R * C * T, 16.0 * S * R * C);
+  if (T == 25) kernel_spectrum_emb_kernel_t<25><<<grid, 256, 0, ctx->stream>>>(taps, emb, R, C, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
+  else if (T == 9) kernel_spectrum_emb_kernel_t<9><<<grid, 256, 0, ctx->stream>>>(taps, emb, R, C, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
+  else if (T == 49) kernel_spectrum_emb_kernel_t<49><<<grid, 256, 0, ctx->stream>>>(taps, emb, R, C, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
+  else kernel_spectrum_emb_kernel<<<grid, 256, 0, ctx->stream>>>(taps, emb, R, C, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// taps[n][k][l] = scale * (pruned inverse DFT of the bin-major spectra z [S][R*C] complex), n = (r, c) or (c, r) when transposed
+int launch_binmajor_to_taps(aefft_ctx* ctx, int R, int C, int transpose, int Nk, int Nl, int Nx, int Ny, int col0, int ncols,
+                            const float2* z, float* taps, float scale) {
+  const float2 *twx, *twy;
+  AE_TRY(get_twiddles(ctx, Nx, &twx));
+  AE_TRY(get_twiddles(ctx, Ny, &twy));
+  if (ncols <= 0) { ncols = Ny / 2 + 1; col0 = 0; }
+  const long long S = (long long)Nx * ncols;
+  const int T = Nk * Nl, E = R * C;
+  AE_ARG(T == 25 || T == 9 || T == 49);
+  const int etiles = (E + 127) / 128;
+  long long nsplit = (4LL * ctx->sm_count + etiles - 1) / etiles;
+  if (nsplit > S / BT_BINS) nsplit = S / BT_BINS;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > 65535) nsplit = 65535;
+  float* part;
+  AE_TRY(ctx->getT("tc_taps_part", (size_t)E * nsplit * T, &part));
+  dim3 grid(etiles, (unsigned)nsplit);
+  {
+    ProfScope prof(ctx, "binmajor_to_taps", 4.0 * S * E * T, 8.0 * S * E);
+    if (T == 25) binmajor_to_taps_kernel<25><<<grid, 128, 0, ctx->stream>>>(z, part, E, R, C, transpose, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
+    else if (T == 9) binmajor_to_taps_kernel<9><<<grid, 128, 0, ctx->stream>>>(z, part, E, R, C, transpose, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
+    else binmajor_to_taps_kernel<49><<<grid, 128, 0, ctx->stream>>>(z, part, E, R, C, transpose, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
+  }
+  const long long total = (long long)E * T;
+  taps_final_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(part, taps, total, (int)nsplit, T, scale);
+  ctx->launches += 2;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// forward contraction (conv_k): out~[S][B][2 O] = scale * in~[S][B][2 C] . Wemb[S][2 O][2 C]^T  (+ bias[o] * bias_scale at bin 0)
+//   minus `sub` when given (E = O - Xt), and then *mse_out = mse_scale * sum_bins hw * |out|^2 (Hermitian weights)
+int launch_tc_forward(aefft_ctx* ctx, long long S, int B, int C, int O, const float* in, const float* Wemb, float scale,
+                      const float* bias, float bias_scale, const float* sub, float* out, float* mse_out, double mse_scale, int ncols,
+                      int col0, int Ny) {
+  TcOperand A{in, B, 2 * C, 0}, W{Wemb, 2 * O, 2 * C, 0};
+  const double bytes = 4.0 * S * (2.0 * B * C * (sub ? 1 : 1) + 2.0 * B * O * (sub ? 2 : 1) + 4.0 * O * C);
+  return launch_bgemm(ctx, "spec_contract_tc", S, A, W, B, 2 * O, 2 * C, EPI_STORE, scale, bias, bias_scale, sub, out, 0, mse_out,
+                      mse_scale, ncols, col0, Ny, bytes);
+}
+// G~[S][B][2 dM] = E~[S][B][2 dD] . conj(F): the Femb[S][2 dD][2 dM] block of O = H F^T read as an MN-major operand
+int launch_tc_adjoint(aefft_ctx* ctx, long long S, int B, int dD, int dM, const float* E, const float* Femb, float* G) {
+  TcOperand A{E, B, 2 * dD, 0}, W{Femb, 2 * dD, 2 * dM, 1};
+  const double bytes = 4.0 * S * (2.0 * B * dD + 2.0 * B * dM + 4.0 * dD * dM);
+  return launch_bgemm(ctx, "spec_contract_tc", S, A, W, B, 2 * dM, 2 * dD, EPI_STORE, 1.f, nullptr, 0.f, nullptr, G, 0, nullptr, 0.0,
+                      0, 0, 0, bytes);
+}
+// out[S][nP][nQ][2] = scale * sum_b P~[b][p] conj(Q~[b][q])   (conj_out: the conjugate of that), P~ [S][B][2 nP], Q~ [S][B][2 nQ]
+int launch_tc_outer(aefft_ctx* ctx, long long S, int B, int nP, int nQ, const float* P, const float* Q, float scale, int conj_out,
+                    float* out) {
+  TcOperand A{P, B, 2 * nP, 1}, Bq{Q, B, 2 * nQ, 1};
+  const double bytes = 4.0 * S * (2.0 * B * nP + 2.0 * B * nQ + 2.0 * nP * nQ);
+  return launch_bgemm(ctx, "spec_outer_tc", S, A, Bq, 2 * nP, 2 * nQ, B, EPI_OUTER, scale, nullptr, 0.f, nullptr, out, conj_out,
+                      nullptr, 0.0, 0, 0, 0, bytes);
+}
+
+int launch_tc_dc_terms(aefft_ctx* ctx, int B, int dM, int dD, const float* G, const float* E, const float* bias_b, float* dFt,
+                       float* db, float* dp, float gs, float fs, float corr_scale) {
+  dc_terms_kernel<<<(dM + dD + 127) / 128, 128, 0, ctx->stream>>>(G, E, bias_b, dFt, db, dp, B, dM, dD, gs, fs, corr_scale);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+}  // namespace aefft
+
+// Diagnostic entry (tests/test_spec_tc_gpu.py): one batched-over-bins real GEMM of the tensor path on device buffers.
+extern "C" int aefft_spec_bin_gemm(aefft_ctx* ctx, int64_t S, const float* a, int a_rows, int a_cols, int a_mn, const float* b,
+                                   int b_rows, int b_cols, int b_mn, int M, int N, int K, int outer, int conj_out, float scale,
+                                   float* out) {
+  using namespace aefft;
+  AE_ARG(ctx && a && b && out);
+  AE_CUDA(cudaSetDevice(ctx->device));
+  TcOperand A{a, a_rows, a_cols, a_mn}, B{b, b_rows, b_cols, b_mn};
+  return launch_bgemm(ctx, outer ? "spec_outer_tc" : "spec_contract_tc", S, A, B, M, N, K, outer ? EPI_OUTER : EPI_STORE, scale, nullptr,
+                      0.f, nullptr, out, conj_out, nullptr, 0.0, 0, 0, 0, 0.0);
+}

@@ -28,10 +28,13 @@ inline EncodeTiledFn encode_fn() {
   }
   return fn;
 }
-// swizzle128: inner box extent must be 32 floats (128 bytes); 16-byte chunk c of inner row r lands at chunk c ^ (r & 7)
-// (r = linear row index b1*i2 + i1 of the box; destination 1024-byte aligned).
+// swizzle (inner box extent must then be 32 floats = 128 bytes, destination 1024-byte aligned):
+//   1 = SWIZZLE_128B: 16-byte chunk c of inner row r lands at chunk c ^ (r & 7) (r = linear row index b1*i2 + i1 of the box);
+//   2 = SWIZZLE_128B_ATOM_32B: 32-byte chunk c of row r lands at chunk c ^ (r & 3) -- the only layout tcgen05.mma accepts
+//       for MN-major (transposed) tf32 operands (UMMA layout type SWIZZLE_128B_BASE32B).
 inline int make_tmap_3d_f32(CUtensorMap* tm, const float* base, uint64_t n0, uint64_t n1, uint64_t n2, uint32_t b0,
-                            uint32_t b1, uint32_t b2, bool swizzle128 = false) {
+                            uint32_t b1, uint32_t b2, int swizzle = 0) {
+  const bool swizzle128 = swizzle != 0;
   EncodeTiledFn fn = encode_fn();
   if (!fn) return -1;
   if (((uintptr_t)base & 15) || (n0 * 4) % 16 || (b0 * 4) % 16 || b0 > 256 || b1 > 256 || b2 > 256) return -2;
@@ -41,7 +44,8 @@ inline int make_tmap_3d_f32(CUtensorMap* tm, const float* base, uint64_t n0, uin
   cuuint32_t box[3] = {b0, b1, b2};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 

@@ -206,6 +206,14 @@ int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int N
                        const float* in, const float* expout, const float* out, float* cfreq, float* c, float* ffreq,
                        float* f, float* b, float* p, float del0, int maxdiff, int n_iter, float* mse_trace);
 
+/* Diagnostic (tests only, like aefft_profile_*): ONE batched-over-bins real GEMM of the tensor-core momentum path
+ * (csrc/spec_tc.cu, tcgen05 kind::tf32 with the 3xTF32 split): D_w[M][N] = A_w . B_w^T for S bins on device buffers
+ * [S][rows][cols]; *_mn = 0: rows index M / N and cols index K, 1: rows index K.  outer != 0 applies the complex-pair
+ * epilogue of the frame-reduced outer products (out [S][M/2][N/2][2]).  It is the per-bin "complex batched GEMM" that
+ * replaces conv_k (fft_backproplib.cu:162-189) and the contractions of gradient_k_io (:395-475). */
+int aefft_spec_bin_gemm(aefft_ctx* ctx, int64_t S, const float* a, int a_rows, int a_cols, int a_mn, const float* b, int b_rows,
+                        int b_cols, int b_mn, int M, int N, int K, int outer, int conj_out, float scale, float* out);
+
 /* backprop_fft on layers stored per frame with stride `frame_stride` floats (the layer block aefft_autoenc_fft writes);
  * device pointers, expout = in (autoencoder.cpp:194), spectra derived from c,f. */
 int aefft_backprop_fft_strided(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl, const float* in,
