@@ -499,7 +499,7 @@ struct TcOperand {
 int launch_bgemm(aefft_ctx* ctx, const char* name, long long S, const TcOperand& A, const TcOperand& B, int Mtot, int Ntot,
                  int Ktot, int epi, float scale, const float* bias, float bias_scale, const float* sub, float* out, int conj_out,
                  float* sq_out, double sq_scale, int ncols, int col0, int Ny, double alg_bytes) {
-  AE_ARG(S > 0 && S < (1LL << 31) && Mtot > 0 && Ntot > 0 && Ktot > 0 && Ntot % 16 == 0 && Mtot % 2 == 0);
+  AE_ARG(S > 0 && S < (1LL << 31) && Mtot > 0 && Ntot > 0 && Ktot > 0 && Ntot % 16 == 0 && (epi != EPI_OUTER || Mtot % 2 == 0));
   AE_ARG((A.mn ? A.cols : A.rows) == Mtot && (A.mn ? A.rows : A.cols) == Ktot);
   AE_ARG((B.mn ? B.cols : B.rows) == Ntot && (B.mn ? B.rows : B.cols) == Ktot);
   AE_ARG(A.cols % 4 == 0 && B.cols % 4 == 0);

@@ -682,6 +682,8 @@ def synth_frames(seed: int, B: int, D: int, Nx: int, Ny: int, b0: int = 0) -> np
 
 
 def rel_l2(a, b) -> float:
-    a, b = np.asarray(a, F64).ravel(), np.asarray(b, F64).ravel()
+    a, b = np.asarray(a), np.asarray(b)
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else F64  # never drop an imaginary part silently
+    a, b = a.astype(dt).ravel(), b.astype(dt).ravel()
     d = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / (d if d > 0 else 1.0))
