@@ -467,6 +467,25 @@ class Net:
                                          C.byref(mse) if want_mse else None))
         return float(mse.value)
 
+    # ---------------------------------------------------------------- momentum space on the resident net
+    def fft_forward(self, frames, fft_l=1, loc=HOST):
+        _chk(lib().aefft_net_fft_forward(self.h, loc, _ptr(frames), int(fft_l)))
+
+    def fft_step(self, frames, del0=0.2, maxdiff=0, n_iter=1, fft_l=0, loc=HOST, want_mse=True):
+        """Returns the mse traces [pairs][n_iter+1] (or None)."""
+        trace = np.zeros((self.num_pairs, n_iter + 1), np.float32) if want_mse else None
+        _chk(lib().aefft_net_fft_step(self.h, loc, _ptr(frames), C.c_float(del0), int(maxdiff), int(n_iter), int(fft_l),
+                                      _ptr(trace)))
+        return trace
+
+    def get_cfreq(self, n):
+        dM, dD, Nk, Nl, _ = self.conv_dims(n)
+        N = 2 * self.num_pairs
+        _, Nx, Ny, _ = self.layer_info(2 * n + 1 if n < N // 2 else 2 * n)
+        out = np.empty((dM, dD, Nx, Ny // 2 + 1, 2), np.float32)
+        _chk(lib().aefft_net_get_cfreq(self.h, n, _ptr(out), C.c_int64(out.size)))
+        return out
+
     def fused_layout(self, mode):
         """(offsets per pair, total floats) of the fused raw gradient block a data-parallel step all-reduces once."""
         P = self.num_pairs

@@ -283,6 +283,29 @@ int launch_tc_outer(aefft_ctx* ctx, long long S, int B, int nP, int nQ, const fl
 int launch_tc_dc_terms(aefft_ctx* ctx, int B, int dM, int dD, const float* G, const float* E, const float* bias_b, float* dFt,
                        float* db, float* dp, float gs, float fs, float corr_scale);
 
+// E~ = O~ - X~ on bin-major spectra [S][rowlen] and *mse_out = mse_scale * sum_bins hw(bin) |E|^2 (mse_out may be null)
+int launch_bm_sub_mse(aefft_ctx* ctx, long long S, long long rowlen, const float* O, const float* X, float* E, float* mse_out,
+                      double mse_scale, int ncols, int col0, int Ny);
+// bin-major spectral pooling (resize, fft_backproplib.cu:87-157, on [bin][rowlen] data): whole rows are gathered
+int launch_bm_resize(aefft_ctx* ctx, long long rowlen, int Nx, int Ny, int Nxs, int Nys, const float* in, float* out);
+
+// backprop_fft (fft_backproplib.cu:1381-1511) on one of three input forms (fft_capi.cu)
+struct FftTrainInputs {
+  const float *in = nullptr, *expout = nullptr, *out = nullptr;  // real-space frames [B][dD][Nx][Ny] (per `loc`) ...
+  int64_t fstride = 0;                                           // ... or per-frame blocks `fstride` floats apart (device)
+  const float2 *Xs = nullptr, *Os = nullptr;   // device spectra, bins-fastest [B][dD][Nx][Nyr]  (expout = in)
+  const float *Xbm = nullptr, *Obm = nullptr;  // device spectra, bin-major [bin][B][2 dD]         (expout = in)
+  bool resident = false;      // c,f,b,p are the device-resident masters: no export through the spectra, and no stream
+                              // synchronisation unless a host trace is requested
+  float* trace_dev = nullptr; // device destination of the mse trace (n_iter + 1 floats), optional
+};
+int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl, const FftTrainInputs& inp,
+                     float* cfreq, float* c, float* ffreq, float* f, float* b, float* p, float del0, int maxdiff, int n_iter,
+                     float* mse_trace);
+// kernel spectra [n_img][Nx][Nyr] (bins fastest) from taps, on a column slab when ncols > 0 (fft_capi.cu)
+int kernel_spectrum_dev(aefft_ctx* ctx, int64_t n_img, int Nk, int Nl, int Nx, int Ny, const float* taps, float* img, float2* spec,
+                        int col0 = 0, int ncols = 0);
+
 // ---- collectives inside the engine (comm.cu): NCCL on the ctx stream; op 0 = sum, 1 = average over the ranks
 int comm_allreduce(aefft_ctx* ctx, float* dev, int64_t n_floats, int op);
 // slab exchange of a bin-sharded transform: rank r sends send + r'*chunk floats to every r' and receives into

@@ -15,8 +15,8 @@ static bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 // C = R2C(pad(c)) for n_img kernels (StoreLoad_cfreq first-time branch, fft_backproplib.cu:1148-1157; backprop :1274-1282)
 // Evaluated directly from the Nk x Nl taps (pruned DFT): mathematically the same spectrum, no padded image, one write.
 // Batches above the grid limit and taps beyond the pruned kernel's envelope go through pad_k + R2C.
-static int kernel_spectrum_dev(aefft_ctx* ctx, int64_t n_img, int Nk, int Nl, int Nx, int Ny, const float* taps, float* img,
-                               float2* spec, int col0 = 0, int ncols = 0) {
+int kernel_spectrum_dev(aefft_ctx* ctx, int64_t n_img, int Nk, int Nl, int Nx, int Ny, const float* taps, float* img, float2* spec,
+                        int col0, int ncols) {
   const bool slab = ncols > 0 && ncols != Ny / 2 + 1;
   if (Nk <= 8 && Nl <= 8 && (slab || !getenv("AEFFT_NO_PRUNED_DFT"))) {
     const int64_t S = (int64_t)Nx * (ncols > 0 ? ncols : Ny / 2 + 1);
@@ -285,13 +285,22 @@ int aefft_autoenc_fft(aefft_ctx* ctx, int loc, int64_t B, int n_conv, const int*
   return AEFFT_OK;
 }
 
-// backprop_fft (fft_backproplib.cu:1381-1511).
-// in_fstride != 0 (device pointers only): frame n of in / expout / out starts at ptr + n*in_fstride (per-frame layer blocks)
-static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl,
-                             const float* in, const float* expout, const float* out, int64_t in_fstride, float* cfreq,
-                             float* c, float* ffreq, float* f, float* b, float* p, float del0, int maxdiff, int n_iter,
-                             float* mse_trace) {
-  AE_ARG(ctx && in && expout && out && c && f && b && p);
+}  // extern "C"
+
+// backprop_fft (fft_backproplib.cu:1381-1511) on real-space frames (transformed here, as the reference does) or on spectra
+// that already live in HBM (the device-resident net keeps every layer's spectrum: net_fft.cu).
+namespace aefft {
+int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl, const FftTrainInputs& inp,
+                     float* cfreq, float* c, float* ffreq, float* f, float* b, float* p, float del0, int maxdiff, int n_iter,
+                     float* mse_trace) {
+  const float *in = inp.in, *expout = inp.expout, *out = inp.out;
+  const int64_t in_fstride = inp.fstride;
+  const bool have_real = in != nullptr, have_ff = inp.Xs != nullptr, have_bm = inp.Xbm != nullptr;
+  AE_ARG(ctx && c && f && b && p && (int)have_real + (int)have_ff + (int)have_bm == 1);
+  AE_ARG(!have_real || (expout && out));
+  AE_ARG(!have_ff || inp.Os);
+  AE_ARG(!have_bm || (inp.Obm && spec_tc_eligible(dD, dM, Nk, Nl) && !cfreq && !ffreq && n_iter > 0));
+  AE_ARG(have_real || loc == AEFFT_DEVICE);
   AE_ARG(B > 0 && dD > 0 && dM > 0 && pow2(Nx) && pow2(Ny) && Nk <= Nx && Nl <= Ny && n_iter >= 0);
   AE_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
@@ -317,17 +326,26 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
   const cudaMemcpyKind k_out = loc == AEFFT_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   FftPairBufs q;
   float *real, *wts;  // wts = [c | f | b | p]
-  AE_TRY(ctx->getT("bpf_X", nXs, &q.X));
-  AE_TRY(ctx->getT("bpf_Xt", nXs, &q.Xt));
-  AE_TRY(ctx->getT("bpf_O", nXs, &q.O));
-  AE_TRY(ctx->getT("bpf_H", nHs, &q.H));
-  AE_TRY(ctx->getT("bpf_G", nHs, &q.G));
-  AE_TRY(ctx->getT("bpf_C", nKS, &q.C));
-  AE_TRY(ctx->getT("bpf_F", nKS, &q.F));
-  AE_TRY(ctx->getT("bpf_dCF", 2 * nKS, &q.dCF));
-  AE_TRY(ctx->getT("bpf_work", 2 * nKS > nXs ? 2 * nKS : nXs, &q.work));
-  AE_TRY(ctx->getT("bpf_img", 2 * (size_t)dM * dD * P, &q.img));
-  AE_TRY(ctx->getT("bpf_real", (size_t)B * dD * P, &real));
+  const bool use_tc = spec_tc_eligible(dD, dM, Nk, Nl) && !cfreq && !ffreq && n_iter > 0;
+  q.X = q.Xt = q.O = q.H = q.G = q.C = q.F = q.dCF = q.work = nullptr;
+  q.img = real = nullptr;
+  if (have_real) {
+    AE_TRY(ctx->getT("bpf_X", nXs, &q.X));
+    AE_TRY(ctx->getT("bpf_Xt", nXs, &q.Xt));
+    AE_TRY(ctx->getT("bpf_O", nXs, &q.O));
+    if (loc == AEFFT_HOST) AE_TRY(ctx->getT("bpf_real", (size_t)B * dD * P, &real));
+  }
+  if (!use_tc) {  // the bins-fastest CUDA-core path keeps H, G and the gradient spectra
+    AE_TRY(ctx->getT("bpf_H", nHs, &q.H));
+    AE_TRY(ctx->getT("bpf_G", nHs, &q.G));
+    AE_TRY(ctx->getT("bpf_dCF", 2 * nKS, &q.dCF));
+  }
+  if (!use_tc || !inp.resident) {
+    AE_TRY(ctx->getT("bpf_C", nKS, &q.C));
+    AE_TRY(ctx->getT("bpf_F", nKS, &q.F));
+    AE_TRY(ctx->getT("bpf_work", 2 * nKS > nXs ? 2 * nKS : nXs, &q.work));
+    AE_TRY(ctx->getT("bpf_img", 2 * (size_t)dM * dD * P, &q.img));
+  }
   AE_TRY(ctx->getT("bpf_taps", 2 * nC + dM + dD, &q.taps));  // raw gradient block [dck | dfk | db | dp]
   AE_TRY(ctx->getT("bpf_wts", 2 * nC + dM + dD, &wts));
   float* small;
@@ -355,18 +373,30 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
     if (sharded) AE_TRY(launch_spec_slab(ctx, B * dD, Nx, Ny, tgt, dst, col0, ncols));
     return AEFFT_OK;
   };
-  AE_TRY(load_fft(in, q.X));
-  const float2* Xt = q.X;
-  if (expout != in) {
-    AE_TRY(load_fft(expout, q.Xt));
-    Xt = q.Xt;
+  const float2* Xt = nullptr;
+  if (have_real) {
+    AE_TRY(load_fft(in, q.X));
+    Xt = q.X;
+    if (expout != in) {
+      AE_TRY(load_fft(expout, q.Xt));
+      Xt = q.Xt;
+    }
+    AE_TRY(load_fft(out, q.O));
+  } else if (have_ff) {
+    AE_ARG(!sharded);
+    q.X = const_cast<float2*>(inp.Xs);  // read only below
+    q.O = const_cast<float2*>(inp.Os);
+    Xt = q.X;
+  } else {
+    AE_ARG(!sharded);
   }
-  AE_TRY(load_fft(out, q.O));
   // kernel spectra: the caller's cache (load_cfreq :1434-1435) or derived from c,f
-  if (cfreq) AE_CUDA(cudaMemcpyAsync(q.C, cfreq, nKS * sizeof(float2), k_in, st));
-  else AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C, col0, ncols));
-  if (ffreq) AE_CUDA(cudaMemcpyAsync(q.F, ffreq, nKS * sizeof(float2), k_in, st));
-  else AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F, col0, ncols));
+  if (!use_tc) {
+    if (cfreq) AE_CUDA(cudaMemcpyAsync(q.C, cfreq, nKS * sizeof(float2), k_in, st));
+    else AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C, col0, ncols));
+    if (ffreq) AE_CUDA(cudaMemcpyAsync(q.F, ffreq, nKS * sizeof(float2), k_in, st));
+    else AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F, col0, ncols));
+  }
   const float norm = (float)Nx * (float)Ny;
   // Reduction of the raw kernel-space block over the devices, before the non-linear clip: the engine's own NCCL
   // all-reduce when the ctx has a communicator (average for data-parallel frames, sum for bin-sharded partial blocks),
@@ -383,8 +413,11 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
   };
   const float* bias_b = own_dc ? db_w : nullptr;
   const float* bias_p = own_dc ? dp_w : nullptr;
-  AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse, col0, ncols));  // "mse fft:" (:1440)
-  if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse, 1));
+  const double mse_scale = 1.0 / ((double)dD * Nx * Ny) / (2.0 * dM * Nx * Ny) / (double)B;
+  if (!have_bm) {
+    AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse, col0, ncols));  // "mse fft:" (:1440)
+    if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse, 1));
+  }
   const float del = 0.1f * del0;                                        // :1445
   const double Norm = (double)norm * 2.0 * dM * dD * (double)Nx * Ny;   // :399
   const float gscale = (float)(1.0 / (Norm * (double)B));
@@ -393,10 +426,9 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
   // kernel spectra are generated directly in the embedded bin-major form, the kernel-space gradients are reduced from
   // the bin-major gradient spectra.  Callers that pass spectra caches (cfreq / ffreq) keep the bins-fastest path, whose
   // first iteration consumes those caches as they are.
-  const bool use_tc = spec_tc_eligible(dD, dM, Nk, Nl) && !cfreq && !ffreq && n_iter > 0;
   if (use_tc) {
-    float *Xb, *Xtb, *Eb, *Hb, *Gb, *Cemb, *Femb, *dCt, *dFt;
-    AE_TRY(ctx->getT("tc_Xb", 2 * nXs, &Xb));
+    float *Xb = nullptr, *Xtb, *Eb, *Hb, *Gb, *Cemb, *Femb, *dCt, *dFt;
+    if (!have_bm) AE_TRY(ctx->getT("tc_Xb", 2 * nXs, &Xb));
     AE_TRY(ctx->getT("tc_Eb", 2 * nXs, &Eb));
     AE_TRY(ctx->getT("tc_Hb", 2 * nHs, &Hb));
     AE_TRY(ctx->getT("tc_Gb", 2 * nHs, &Gb));
@@ -404,18 +436,24 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
     AE_TRY(ctx->getT("tc_Femb", 4 * nKS, &Femb));
     AE_TRY(ctx->getT("tc_dCt", 2 * nKS, &dCt));
     AE_TRY(ctx->getT("tc_dFt", 2 * nKS, &dFt));
-    AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, q.X, nullptr, (float2*)Xb));
-    Xtb = Xb;
-    if (Xt != q.X) {
-      AE_TRY(ctx->getT("tc_Xtb", 2 * nXs, &Xtb));
-      AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, Xt, nullptr, (float2*)Xtb));
+    if (have_bm) {
+      // the layer spectra are bin-major already: E = O - X and the "mse fft:" value in one pass
+      Xb = const_cast<float*>(inp.Xbm);
+      Xtb = Xb;
+      AE_TRY(launch_bm_sub_mse(ctx, S, (long long)B * 2 * dD, inp.Obm, inp.Xbm, Eb, q.mse, mse_scale, ncols, col0, Ny));
+    } else {
+      AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, q.X, nullptr, (float2*)Xb));
+      Xtb = Xb;
+      if (Xt != q.X) {
+        AE_TRY(ctx->getT("tc_Xtb", 2 * nXs, &Xtb));
+        AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, Xt, nullptr, (float2*)Xtb));
+      }
+      AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, q.O, Xt, (float2*)Eb));  // E = O - Xt of the caller's `out`
     }
-    AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, q.O, Xt, (float2*)Eb));  // E = O - Xt of the caller's `out`
     AE_TRY(launch_kernel_spectrum_emb(ctx, dM, dD, Nk, Nl, Nx, Ny, col0, ncols, dc_w, Cemb));
     AE_TRY(launch_kernel_spectrum_emb(ctx, dD, dM, Nk, Nl, Nx, Ny, col0, ncols, df_w, Femb));
     // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1)
     AE_TRY(launch_tc_forward(ctx, S, (int)B, dD, dM, Xb, Cemb, 1.f / (float)dM, bias_b, norm, nullptr, Hb, nullptr, 0.0, 0, 0, 0));
-    const double mse_scale = 1.0 / ((double)dD * Nx * Ny) / (2.0 * dM * Nx * Ny) / (double)B;
     for (int n = 0; n < n_iter; n++) {
       AE_TRY(launch_tc_adjoint(ctx, S, (int)B, dD, dM, Eb, Femb, Gb));                               // G = E conj(F)
       AE_TRY(launch_tc_outer(ctx, S, (int)B, dM, dD, Gb, Xb, gscale, 0, dCt));                       // dC[m][d] = G conj(X)
@@ -442,7 +480,7 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
                                ncols, col0, Ny));
       if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse + n + 1, 1));
     }
-    if (!sharded) {  // the bins-fastest spectra of the trained kernels, for the export below
+    if (!sharded && !inp.resident) {  // the bins-fastest spectra of the trained kernels, for the export below
       AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C, col0, ncols));
       AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F, col0, ncols));
     }
@@ -485,8 +523,9 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
   // store_cfreq (:1484-1485) and export_cfreq (:1487-1488: c,f re-derived from the spectra: C2R/(NxNy) + kernel_invpad)
   if (cfreq) AE_CUDA(cudaMemcpyAsync(cfreq, q.C, nKS * sizeof(float2), k_out, st));
   if (ffreq) AE_CUDA(cudaMemcpyAsync(ffreq, q.F, nKS * sizeof(float2), k_out, st));
-  if (sharded) {
-    // the kernels in tap space are the master copy (identical on every device); no device holds a whole spectrum
+  if (sharded || inp.resident) {
+    // the kernels in tap space are the master copy (identical on every device / resident in the net); no round trip
+    // through the spectra (which is the identity up to fp32 rounding)
     AE_CUDA(cudaMemcpyAsync(q.taps, wts, 2 * nC * sizeof(float), cudaMemcpyDeviceToDevice, st));
   } else {
     AE_TRY(spectrum_taps_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.C, q.work, q.img, q.taps, 1.f / norm));
@@ -497,17 +536,24 @@ static int backprop_fft_core(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM,
   AE_CUDA(cudaMemcpyAsync(f, q.taps + nC, nC * sizeof(float), k_out, st));
   AE_CUDA(cudaMemcpyAsync(b, db_w, dM * sizeof(float), k_out, st));
   AE_CUDA(cudaMemcpyAsync(p, dp_w, dD * sizeof(float), k_out, st));
+  if (inp.trace_dev)
+    AE_CUDA(cudaMemcpyAsync(inp.trace_dev, q.mse, ((size_t)n_iter + 1) * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (mse_trace)
     AE_CUDA(cudaMemcpyAsync(mse_trace, q.mse, ((size_t)n_iter + 1) * sizeof(float), cudaMemcpyDeviceToHost, st));
-  AE_CUDA(cudaStreamSynchronize(st));
+  if (mse_trace || !inp.resident) AE_CUDA(cudaStreamSynchronize(st));
   return AEFFT_OK;
 }
+}  // namespace aefft
+
+extern "C" {
 
 int aefft_backprop_fft(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl,
                        const float* in, const float* expout, const float* out, float* cfreq, float* c, float* ffreq,
                        float* f, float* b, float* p, float del0, int maxdiff, int n_iter, float* mse_trace) {
-  return backprop_fft_core(ctx, loc, B, dD, dM, Nx, Ny, Nk, Nl, in, expout, out, 0, cfreq, c, ffreq, f, b, p, del0, maxdiff,
-                           n_iter, mse_trace);
+  AE_ARG(in && expout && out);
+  FftTrainInputs inp;
+  inp.in = in; inp.expout = expout; inp.out = out;
+  return backprop_fft_run(ctx, loc, B, dD, dM, Nx, Ny, Nk, Nl, inp, cfreq, c, ffreq, f, b, p, del0, maxdiff, n_iter, mse_trace);
 }
 
 }  // extern "C"
@@ -524,8 +570,12 @@ int aefft_backprop_fft_strided(aefft_ctx* ctx, int64_t B, int dD, int dM, int Nx
   AE_CUDA(cudaSetDevice(ctx->device));
   // transform the frames where they lie when the row kernels can address the per-frame blocks, else gather
   if (Ny >= 8 && Ny <= 4096 && !getenv("AEFFT_FFT_V1"))
-    return backprop_fft_core(ctx, AEFFT_DEVICE, B, dD, dM, Nx, Ny, Nk, Nl, in, in, out, frame_stride, nullptr, c, nullptr, f, b, p,
-                             del0, maxdiff, n_iter, mse_trace);
+  {
+    FftTrainInputs inp;
+    inp.in = in; inp.expout = in; inp.out = out; inp.fstride = frame_stride;
+    return backprop_fft_run(ctx, AEFFT_DEVICE, B, dD, dM, Nx, Ny, Nk, Nl, inp, nullptr, c, nullptr, f, b, p, del0, maxdiff, n_iter,
+                            mse_trace);
+  }
   const size_t w = (size_t)dD * Nx * Ny * sizeof(float);
   float *gin, *gout;
   AE_TRY(ctx->getT("bpfs_in", (size_t)B * dD * Nx * Ny, &gin));

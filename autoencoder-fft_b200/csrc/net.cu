@@ -8,42 +8,7 @@
 
 using namespace aefft;
 
-namespace {
-
-struct ConvL {
-  int dM, dD, Nk, Nl, scale;
-  float *c = nullptr, *b = nullptr;  // device
-};
-struct LayerL {
-  int D, Nx, Ny;
-  float* p = nullptr;  // [B][D][Nx][Ny]
-};
-// per-pair momentum / last-gradient state.  The reference shares ONE set (dc,db,df,dp,ddc,..) between all pairs and
-// zeroes it whenever the active pair changes (autoencoder.cpp:288-292, 412-417, 447-452); here each pair owns its set
-// (aefft_net_reset_momentum reproduces the zeroing).
-struct PairState {
-  float *dc = nullptr, *db = nullptr, *df = nullptr, *dp = nullptr;
-  float *ddc = nullptr, *ddb = nullptr, *ddf = nullptr, *ddp = nullptr;
-  float* gbuf = nullptr;  // view into aefft_net::gall (the fused gradient block of all pairs), valid for gbuf_mode
-  int64_t gbuf_len = 0;
-  int gbuf_mode = -1;
-};
-
-}  // namespace
-
-struct aefft_net {
-  aefft_ctx* ctx;
-  int64_t B;
-  std::vector<LayerL> layers;   // 2*convs+1
-  std::vector<ConvL> convs;     // encoder convs 0..P-1, decoder convs P..2P-1 (pair n: convs n and N-1-n)
-  std::vector<PairState> pairs; // index = pair
-  float* mse_dev = nullptr;     // [64]
-  // Raw gradient blocks of ALL pairs in one contiguous buffer [pair 0 | pair 1 | ...] (layout of `gall_mode`): a
-  // data-parallel step all-reduces it ONCE (the pairs are independent given the forward's activations).
-  float* gall = nullptr;
-  int64_t gall_len = 0, gall_cap = 0;
-  int gall_mode = -1;
-};
+#include "net.cuh"
 
 namespace {
 
@@ -153,6 +118,7 @@ int aefft_net_destroy(aefft_net* net) {
   for (auto& s : net->pairs) free_pair_state(s);
   dev_free(net->mse_dev);
   dev_free(net->gall);
+  net_fft_release(net);
   delete net;
   return AEFFT_OK;
 }
@@ -208,6 +174,7 @@ int aefft_net_add_layer(aefft_net* net, int dM, int Lk, int Ll, int scal, float 
   net->convs.insert(net->convs.begin() + mid, {enc, dec});
   net->pairs.push_back(st);  // innermost pair has the highest index
   net->gall_mode = -1;       // the fused gradient block is laid out again on the next gradient call
+  net_fft_release(net);      // layer spectra are re-planned for the new topology (the reference clears net_cfreq, :429)
   return AEFFT_OK;
 }
 
@@ -226,6 +193,7 @@ int aefft_net_delete_layer(aefft_net* net) {
   free_pair_state(net->pairs.back());
   net->pairs.pop_back();
   net->gall_mode = -1;
+  net_fft_release(net);  // (:454)
   return AEFFT_OK;
 }
 

@@ -1,0 +1,243 @@
+// Momentum (FFT) space on the device-resident net: forward of the whole stack and training of every pair with the
+// activations kept as SPECTRA in HBM.
+//
+// Reference flow (autoencoder.cpp:131-133, 190-196): autoenc_fft transforms the frame, keeps the activations in frequency
+// space across the stack, and -- with fft_l = 1, which training presupposes -- inverse-transforms
+// EVERY layer; backprop_fft then forward-transforms the pair's in / out layers again (fft_backproplib.cu:1430-1432) and
+// uploads the kernel spectra from the host cache net_cfreq (51-136 MB per layer per frame at config 3, :1434-1435).
+// Here the forward keeps every layer's spectrum, the pair training consumes those spectra directly (a C2R followed by an
+// R2C is the identity up to fp32 rounding), real-space layers are materialised only where the caller wants to look at
+// them (fft_l), and net_cfreq is a lazily computed VIEW of the device-resident kernels (aefft_net_get_cfreq) instead of a
+// host cache that has to be kept in sync.
+//
+// Layout per resolution level: pairs whose channel counts allow the tensor-core contraction (spec_tc.cu) keep their four
+// layers bin-major [bin][frame][2 ch]; the others (3-channel image side) keep the reference's [frame][ch][Nx][Nyr].
+// Level changes (spectral pooling, resize :87-157) convert where the two sides differ.
+#include <cstdio>
+
+#include "net.cuh"
+
+using namespace aefft;
+
+namespace aefft {
+
+void net_fft_release(aefft_net* net) {
+  if (!net) return;
+  if (!net->spec.empty() || net->fft_trace) {
+    cudaSetDevice(net->ctx->device);
+    cudaStreamSynchronize(net->ctx->stream);
+  }
+  for (auto& s : net->spec)
+    if (s.p) cudaFree(s.p);
+  net->spec.clear();
+  if (net->fft_trace) cudaFree(net->fft_trace);
+  net->fft_trace = nullptr;
+  net->fft_trace_cap = 0;
+}
+
+}  // namespace aefft
+
+namespace {
+
+bool pow2i(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+// resolution level of layer l (-1: frame resolution): level n holds layers 2n+1, 2n+2, 2N-2-2n, 2N-1-2n
+int level_of(int l, int N) {
+  if (l == 0 || l == 2 * N) return -1;
+  const int m = l <= N ? l : 2 * N - l;  // N = 2P: layers 1..2P on the way down, mirrored on the way up
+  return (m - 1) / 2;
+}
+
+bool pair_tc(const aefft_net* net, int n) {
+  const ConvL& e = net->convs[n];
+  return spec_tc_eligible(e.dD, e.dM, e.Nk, e.Nl);
+}
+
+size_t spec_floats(const aefft_net* net, int l) {
+  const LayerL& L = net->layers[l];
+  return (size_t)net->B * L.D * L.Nx * (L.Ny / 2 + 1) * 2;
+}
+
+int plan(aefft_net* net) {
+  const int nl = (int)net->layers.size(), N = (int)net->convs.size();
+  if ((int)net->spec.size() == nl) return AEFFT_OK;
+  net_fft_release(net);
+  AE_ARG(N >= 2);
+  for (int l = 0; l < nl; l++) AE_ARG(pow2i(net->layers[l].Nx) && pow2i(net->layers[l].Ny));
+  net->spec.resize(nl);
+  for (int l = 0; l < nl; l++) {
+    const int lev = level_of(l, N);
+    net->spec[l].bin_major = lev >= 0 && pair_tc(net, lev);
+    AE_CUDA(cudaMalloc((void**)&net->spec[l].p, spec_floats(net, l) * sizeof(float)));
+  }
+  return AEFFT_OK;
+}
+
+// spectrum of layer ls -> spectrum of layer ld across a level change (spectral pooling by `scale`, possibly a layout change)
+int move_spec(aefft_net* net, int ls, int ld) {
+  aefft_ctx* ctx = net->ctx;
+  const LayerL &A = net->layers[ls], &Z = net->layers[ld];
+  AE_ARG(A.D == Z.D);
+  const SpecL &sa = net->spec[ls], &sz = net->spec[ld];
+  const long long B = net->B, R = B * A.D;
+  const long long Sa = (long long)A.Nx * (A.Ny / 2 + 1), Sz = (long long)Z.Nx * (Z.Ny / 2 + 1);
+  const bool same_res = A.Nx == Z.Nx && A.Ny == Z.Ny;
+  if (sa.bin_major == sz.bin_major) {
+    if (same_res) {
+      AE_CUDA(cudaMemcpyAsync(sz.p, sa.p, spec_floats(net, ls) * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+      return AEFFT_OK;
+    }
+    if (sa.bin_major) return launch_bm_resize(ctx, 2 * R, A.Nx, A.Ny, Z.Nx, Z.Ny, sa.p, sz.p);
+    return launch_spec_resize(ctx, R, A.Nx, A.Ny, Z.Nx, Z.Ny, (const float2*)sa.p, (float2*)sz.p);
+  }
+  float* tmp;
+  if (!sa.bin_major) {  // bins-fastest -> bin-major: pool in the source layout, then transpose
+    if (same_res) return launch_to_binmajor(ctx, R, Sa, (const float2*)sa.p, nullptr, (float2*)sz.p);
+    AE_TRY(ctx->getT("nf_tmp", (size_t)R * Sz * 2, &tmp));
+    AE_TRY(launch_spec_resize(ctx, R, A.Nx, A.Ny, Z.Nx, Z.Ny, (const float2*)sa.p, (float2*)tmp));
+    return launch_to_binmajor(ctx, R, Sz, (const float2*)tmp, nullptr, (float2*)sz.p);
+  }
+  // bin-major -> bins-fastest: transpose ([S][R] -> [R][S] is the same kernel with the roles swapped), then pool
+  if (same_res) return launch_to_binmajor(ctx, Sa, R, (const float2*)sa.p, nullptr, (float2*)sz.p);
+  AE_TRY(ctx->getT("nf_tmp", (size_t)R * Sa * 2, &tmp));
+  AE_TRY(launch_to_binmajor(ctx, Sa, R, (const float2*)sa.p, nullptr, (float2*)tmp));
+  return launch_spec_resize(ctx, R, A.Nx, A.Ny, Z.Nx, Z.Ny, (const float2*)tmp, (float2*)sz.p);
+}
+
+// conv_k (:162-189) of conv n: spectrum of layer li -> spectrum of layer lo (same level, same layout)
+int conv_spec(aefft_net* net, int n, int li, int lo) {
+  aefft_ctx* ctx = net->ctx;
+  const ConvL& c = net->convs[n];
+  const LayerL &A = net->layers[li], &Z = net->layers[lo];
+  AE_ARG(A.D == c.dD && Z.D == c.dM && A.Nx == Z.Nx && A.Ny == Z.Ny && net->spec[li].bin_major == net->spec[lo].bin_major);
+  AE_ARG(c.Nk <= A.Nx && c.Nl <= A.Ny);
+  const long long S = (long long)A.Nx * (A.Ny / 2 + 1);
+  const float norm = (float)A.Nx * (float)A.Ny;
+  if (net->spec[li].bin_major) {
+    float* emb;
+    AE_TRY(ctx->getT("nf_emb", (size_t)4 * c.dM * c.dD * S, &emb));
+    AE_TRY(launch_kernel_spectrum_emb(ctx, c.dM, c.dD, c.Nk, c.Nl, A.Nx, A.Ny, 0, 0, c.c, emb));
+    return launch_tc_forward(ctx, S, (int)net->B, c.dD, c.dM, net->spec[li].p, emb, 1.f / (float)c.dM, c.b, norm, nullptr,
+                             net->spec[lo].p, nullptr, 0.0, 0, 0, 0);
+  }
+  float2* kspec;
+  float* kimg;
+  AE_TRY(ctx->getT("nf_kspec", (size_t)c.dM * c.dD * S, &kspec));
+  AE_TRY(ctx->getT("nf_kimg", (size_t)c.dM * c.dD * A.Nx * A.Ny, &kimg));
+  AE_TRY(kernel_spectrum_dev(ctx, (int64_t)c.dM * c.dD, c.Nk, c.Nl, A.Nx, A.Ny, c.c, kimg, kspec));
+  return launch_spec_contract(ctx, net->B, c.dD, c.dM, S, (const float2*)net->spec[li].p, nullptr, kspec, (int64_t)c.dD * S, S, 0,
+                              1.f / (float)c.dM, c.b, norm, (float2*)net->spec[lo].p);
+}
+
+// fft_inv (:806-864): spectrum of layer l -> real layer l, scaled by 1/(Nx Ny)
+int materialise(aefft_net* net, int l) {
+  aefft_ctx* ctx = net->ctx;
+  const LayerL& L = net->layers[l];
+  const long long R = net->B * L.D, S = (long long)L.Nx * (L.Ny / 2 + 1);
+  const float2* spec = (const float2*)net->spec[l].p;
+  float2* work;
+  AE_TRY(ctx->getT("nf_work", (size_t)R * S, &work));
+  if (net->spec[l].bin_major) {
+    float2* ff;
+    AE_TRY(ctx->getT("nf_ff", (size_t)R * S, &ff));
+    AE_TRY(launch_to_binmajor(ctx, S, R, spec, nullptr, ff));
+    spec = ff;
+  }
+  return launch_fft_c2r(ctx, R, L.Nx, L.Ny, spec, work, L.p, 1.f / ((float)L.Nx * (float)L.Ny));
+}
+
+int forward(aefft_net* net, int loc, const float* frames, int fft_l) {
+  aefft_ctx* ctx = net->ctx;
+  AE_CUDA(cudaSetDevice(ctx->device));
+  AE_TRY(plan(net));
+  const int N = (int)net->convs.size();
+  LayerL& L0 = net->layers[0];
+  const size_t n0 = (size_t)net->B * L0.D * L0.Nx * L0.Ny;
+  if (frames && frames != L0.p) {
+    AE_CUDA(cudaMemcpyAsync(L0.p, frames, n0 * sizeof(float),
+                            loc == AEFFT_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
+    if (loc == AEFFT_HOST) AE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  AE_TRY(launch_fft_r2c(ctx, net->B * L0.D, L0.Nx, L0.Ny, L0.p, (float2*)net->spec[0].p));  // fft() :764-801
+  for (int n = 0; n < N; n++) {
+    if (n < N / 2) {
+      AE_TRY(move_spec(net, 2 * n, 2 * n + 1));        // pool_fft :1346
+      if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 1));
+      AE_TRY(conv_spec(net, n, 2 * n + 1, 2 * n + 2));  // conv_fft :1356
+      if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 2));
+    } else {
+      AE_TRY(conv_spec(net, n, 2 * n, 2 * n + 1));
+      if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 1));
+      AE_TRY(move_spec(net, 2 * n + 1, 2 * n + 2));     // pool_fft :1360
+      if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 2));
+    }
+  }
+  if (fft_l == 0) AE_TRY(materialise(net, 2 * N));       // fft_inv of the last layer only (:1373)
+  return AEFFT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int aefft_net_fft_forward(aefft_net* net, int loc, const float* frames, int fft_l) {
+  AE_ARG(net && net->convs.size() >= 2);
+  return forward(net, loc, frames, fft_l);
+}
+
+int aefft_net_fft_step(aefft_net* net, int loc, const float* frames, float del0, int maxdiff, int n_iter, int fft_l,
+                       float* mse) {
+  AE_ARG(net && net->convs.size() >= 2 && n_iter >= 1);
+  aefft_ctx* ctx = net->ctx;
+  AE_TRY(forward(net, loc, frames, fft_l));
+  const int N = (int)net->convs.size(), P = N / 2;
+  const int64_t tlen = (int64_t)P * (n_iter + 1);
+  if (net->fft_trace_cap < tlen) {
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (net->fft_trace) cudaFree(net->fft_trace);
+    net->fft_trace = nullptr;
+    AE_CUDA(cudaMalloc((void**)&net->fft_trace, (size_t)tlen * sizeof(float)));
+    net->fft_trace_cap = tlen;
+  }
+  for (int n = 0; n < P; n++) {
+    // pair n: in = layers[2n+1], out = layers[size-2-2n], c = net_c[n], f = net_c[N-1-n] (autoencoder.cpp:161-196)
+    const ConvL &e = net->convs[n], &d = net->convs[N - 1 - n];
+    const int li = 2 * n + 1, lo = 2 * N - 1 - 2 * n;
+    const LayerL& L = net->layers[li];
+    FftTrainInputs inp;
+    if (net->spec[li].bin_major) { inp.Xbm = net->spec[li].p; inp.Obm = net->spec[lo].p; }
+    else { inp.Xs = (const float2*)net->spec[li].p; inp.Os = (const float2*)net->spec[lo].p; }
+    inp.resident = true;
+    inp.trace_dev = net->fft_trace + (size_t)n * (n_iter + 1);
+    AE_TRY(backprop_fft_run(ctx, AEFFT_DEVICE, net->B, e.dD, e.dM, L.Nx, L.Ny, e.Nk, e.Nl, inp, nullptr, e.c, nullptr, d.c, e.b, d.b,
+                            del0, maxdiff, n_iter, nullptr));
+  }
+  if (mse) {
+    AE_CUDA(cudaMemcpyAsync(mse, net->fft_trace, (size_t)tlen * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return AEFFT_OK;
+}
+
+// net_cfreq[n] as a view of the device-resident kernels: R2C(kernel_pad(net_c[n])) at the resolution conv n runs at, in the
+// reference's interleaved wire format (store_cfreq :1117-1127).  n_floats must equal 2*dM*dD*Nx*(Ny/2+1).
+int aefft_net_get_cfreq(aefft_net* net, int n, float* cfreq, int64_t n_floats) {
+  AE_ARG(net && cfreq && n >= 0 && n < (int)net->convs.size());
+  aefft_ctx* ctx = net->ctx;
+  AE_CUDA(cudaSetDevice(ctx->device));
+  const int N = (int)net->convs.size();
+  const ConvL& c = net->convs[n];
+  const LayerL& L = net->layers[n < N / 2 ? 2 * n + 1 : 2 * n];
+  const size_t S = (size_t)L.Nx * (L.Ny / 2 + 1), want = 2 * (size_t)c.dM * c.dD * S;
+  AE_ARG((size_t)n_floats == want && pow2i(L.Nx) && pow2i(L.Ny));
+  float2* kspec;
+  float* kimg;
+  AE_TRY(ctx->getT("nf_kspec", (size_t)c.dM * c.dD * S, &kspec));
+  AE_TRY(ctx->getT("nf_kimg", (size_t)c.dM * c.dD * L.Nx * L.Ny, &kimg));
+  AE_TRY(kernel_spectrum_dev(ctx, (int64_t)c.dM * c.dD, c.Nk, c.Nl, L.Nx, L.Ny, c.c, kimg, kspec));
+  AE_CUDA(cudaMemcpyAsync(cfreq, kspec, want * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  AE_CUDA(cudaStreamSynchronize(ctx->stream));
+  return AEFFT_OK;
+}
+
+}  // extern "C"

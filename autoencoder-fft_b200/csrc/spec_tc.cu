@@ -640,6 +640,90 @@ int launch_tc_outer(aefft_ctx* ctx, long long S, int B, int nP, int nQ, const fl
                       nullptr, 0.0, 0, 0, 0, bytes);
 }
 
+// ---- E = O - X on bin-major spectra, with the Hermitian-weighted sum of |E|^2 (calc_mse, fft_backproplib.cu:480-498)
+__global__ void __launch_bounds__(256) bm_sub_mse_kernel(const float4* __restrict__ O, const float4* __restrict__ X, float4* __restrict__ E,
+                                                         long long S, long long row4, int ncols, int col0, int Ny,
+                                                         double* __restrict__ part) {
+  double s = 0.0;
+  for (long long w = blockIdx.x; w < S; w += gridDim.x) {
+    const int wy = col0 + (int)(w % ncols);
+    const float hw = (wy == 0 || wy == Ny / 2) ? 1.f : 2.f;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < row4; i += blockDim.x) {
+      const float4 o = __ldg(O + w * row4 + i), x = __ldg(X + w * row4 + i);
+      const float4 e = make_float4(o.x - x.x, o.y - x.y, o.z - x.z, o.w - x.w);
+      E[w * row4 + i] = e;
+      acc += (e.x * e.x + e.y * e.y) + (e.z * e.z + e.w * e.w);
+    }
+    s += (double)(acc * hw);
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+
+int launch_bm_sub_mse(aefft_ctx* ctx, long long S, long long rowlen, const float* O, const float* X, float* E, float* mse_out,
+                      double mse_scale, int ncols, int col0, int Ny) {
+  AE_ARG(rowlen % 4 == 0 && S > 0);
+  if (ncols <= 0) { ncols = Ny / 2 + 1; col0 = 0; }
+  const int grid = (int)(S < 8LL * ctx->sm_count ? S : 8LL * ctx->sm_count);
+  double* part;
+  AE_TRY(ctx->getT("tc_sq_part", (size_t)(grid > 4 * ctx->sm_count ? grid : 4 * ctx->sm_count), &part));
+  {
+    ProfScope prof(ctx, "spec_bm_sub_mse", 0.0, 12.0 * S * rowlen);
+    bm_sub_mse_kernel<<<grid, 256, 0, ctx->stream>>>((const float4*)O, (const float4*)X, (float4*)E, S, rowlen / 4, ncols, col0, Ny, part);
+    ctx->launches++;
+  }
+  if (mse_out) {
+    sq_final_kernel<<<1, 256, 0, ctx->stream>>>(part, grid, mse_scale, mse_out);
+    ctx->launches++;
+  }
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// ---- spectral pooling on bin-major data: target bin (i, j) <- source bin (si, sj) or zero; same index map as spec_resize_kernel
+__global__ void __launch_bounds__(256) bm_resize_kernel(const float4* __restrict__ in, float4* __restrict__ out, long long row4, int Nx,
+                                                        int Ny, int Nxs, int Nys) {
+  const int Nyr = Ny / 2 + 1, Nyrs = Nys / 2 + 1;
+  const long long w = blockIdx.x;
+  const int i = (int)(w / Nyrs), j = (int)(w - (long long)i * Nyrs);
+  int si = -1, sj = -1;
+  if (Nxs <= Nx) {
+    si = i < Nxs / 2 ? i : (i == Nxs / 2 ? Nx / 2 : i + Nx - Nxs);
+    sj = j < Nyrs - 1 ? j : Nyr - 1;
+  } else {
+    if (i < Nx / 2) si = i;
+    else if (i > Nxs - Nx / 2) si = i - Nxs + Nx;
+    else if (i == Nxs / 2) si = Nx / 2;
+    if (j < Nyr - 1) sj = j;
+    else if (j == Nyrs - 1) sj = Nyr - 1;
+  }
+  float4* o = out + w * row4;
+  if (si < 0 || sj < 0) {
+    for (long long t = threadIdx.x; t < row4; t += blockDim.x) o[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const float4* s = in + ((long long)si * Nyr + sj) * row4;
+  for (long long t = threadIdx.x; t < row4; t += blockDim.x) o[t] = __ldg(s + t);
+}
+
+int launch_bm_resize(aefft_ctx* ctx, long long rowlen, int Nx, int Ny, int Nxs, int Nys, const float* in, float* out) {
+  AE_ARG(rowlen % 4 == 0);
+  const long long bins = (long long)Nxs * (Nys / 2 + 1);
+  const long long src_bins = (long long)(Nxs <= Nx ? Nxs : Nx) * ((Nxs <= Nx ? Nys : Ny) / 2 + 1);
+  ProfScope prof(ctx, "spec_resize_bm", 0.0, 4.0 * rowlen * (bins + src_bins));
+  bm_resize_kernel<<<(unsigned)bins, 256, 0, ctx->stream>>>((const float4*)in, (float4*)out, rowlen / 4, Nx, Ny, Nxs, Nys);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
 int launch_tc_dc_terms(aefft_ctx* ctx, int B, int dM, int dD, const float* G, const float* E, const float* bias_b, float* dFt,
                        float* db, float* dp, float gs, float fs, float corr_scale) {
   dc_terms_kernel<<<(dM + dD + 127) / 128, 128, 0, ctx->stream>>>(G, E, bias_b, dFt, db, dp, B, dM, dD, gs, fs, corr_scale);

@@ -279,6 +279,22 @@ int aefft_net_train_pair(aefft_net* net, int n_l, int mode, int quirks, float de
  * data-parallel split (all-reduce the buffer in between). */
 int aefft_net_pair_gradients(aefft_net* net, int n_l, int mode, int quirks, float** gbuf_dev, int64_t* gbuf_len);
 int aefft_net_pair_update(aefft_net* net, int n_l, int mode, int64_t B_global, float delmax, float alpha, float* mse);
+/* ---- momentum (FFT) space on the resident net (autoencoder.cpp:131-133 forward with fft == 1, :190-196 training).
+ * The forward keeps EVERY layer's spectrum in HBM; real-space layers (aefft_net_layer) are written per fft_l:
+ * 1 = every layer (the reference's display mode, fft_backproplib.cu:1347-1361), 0 = the last layer only (:1373),
+ * -1 = none.  aefft_net_fft_step = that forward + n_iter iterations of backprop_fft (:1381-1511; the reference runs 100,
+ * lr 0.1*del0, alpha 0.9, momentum zeroed per call) for EVERY pair, consuming the pair's in / out spectra directly -- the
+ * reference inverse-transforms the layers and backprop_fft transforms them again, a round trip that is the identity up to
+ * fp32 rounding.  mse: host [pairs][n_iter+1] (the "mse fft:" / "n: .. mse:" values) or NULL (then nothing synchronises).
+ * With a communicator (aefft_comm_init) the kernel-space gradient block of every iteration is averaged over the ranks. */
+int aefft_net_fft_forward(aefft_net* net, int loc, const float* frames, int fft_l);
+int aefft_net_fft_step(aefft_net* net, int loc, const float* frames, float del0, int maxdiff, int n_iter, int fft_l,
+                       float* mse);
+/* net_cfreq[n] (fft_backproplib.cu:1146-1161) as a lazily computed VIEW of the device-resident kernels of conv n:
+ * the interleaved wire-format spectrum [dM][dD][Nx][Ny/2+1][2] at the resolution conv n runs at, n_floats = its length.
+ * The reference keeps this as a host cache that is uploaded (51-136 MB per layer) on every frame. */
+int aefft_net_get_cfreq(aefft_net* net, int n, float* cfreq, int64_t n_floats);
+
 /* Offsets (floats) of every pair's raw gradient block inside the net's fused gradient buffer for `mode`, and its total
  * length: the buffer a data-parallel step all-reduces once (offsets may be NULL). */
 int aefft_net_fused_layout(aefft_net* net, int mode, int64_t* offsets, int64_t* total);

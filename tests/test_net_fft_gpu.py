@@ -1,0 +1,121 @@
+"""GPU parity tests of the momentum-space mode of the device-resident net (csrc/net_fft.cu): the forward that keeps every
+layer's spectrum, the training step that consumes those spectra, and net_cfreq as a view of the resident kernels --
+against the fp64 oracle (autoenc_fft + backprop_fft per pair, fft_backproplib.cu:1331-1511) and against this engine's
+reference-shaped C-ABI path (aefft_autoenc_fft with fft_l = 1, then aefft_backprop_fft on the real-space layers), which
+the other test files pin against the compiled reference.  Tolerances: layers 2e-5, weights 1e-4 / updates 2e-3 vs the
+oracle (north_star), 2e-5 between the two engine paths (they differ by one C2R/R2C round trip in fp32)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import aefft_ctypes as A
+import oracle_np as O
+
+pytestmark = pytest.mark.gpu
+
+
+def make_net(ctx, D, Nx, Ny, widths, pools, B, rmax=0.1, seed=4321):
+    ctypes.CDLL("libc.so.6").srand(seed)
+    net = A.Net(ctx, D, Nx, Ny, B)
+    for m, s in zip(widths, pools):
+        net.add_layer(m, 1, 1, s, rmax)
+    N = 2 * net.num_pairs
+    convs = [net.get_conv(n) for n in range(N)]
+    net_c, net_b = [c for c, _ in convs], [b for _, b in convs]
+    scale = [net.conv_dims(n)[4] for n in range(N)]
+    shapes = [net.layer_info(l)[:3] for l in range(net.num_layers)]
+    return net, net_c, net_b, scale, shapes
+
+
+CASES = [
+    (3, 32, 32, [4, 5], [2, 2], 2),          # no tensor-core pair: the reference's bins-fastest layout throughout
+    (3, 64, 64, [8, 16], [2, 2], 5),         # pair 0 CUDA cores, pair 1 tensor cores (layout change at the pooling)
+    (8, 32, 64, [16, 8], [2, 1], 9),         # both pairs tensor cores, pool 1 between them, rectangular
+    (3, 64, 32, [8, 16, 32], [2, 2, 2], 8),  # the c3 stack at reduced size
+]
+
+
+@pytest.mark.parametrize("cfg", CASES)
+def test_net_fft_forward_vs_oracle_and_capi(ctx, cfg):
+    D, Nx, Ny, widths, pools, B = cfg
+    net, net_c, net_b, scale, shapes = make_net(ctx, D, Nx, Ny, widths, pools, B)
+    try:
+        x = O.synth_frames(7, B, D, Nx, Ny)
+        net.fft_forward(x, fft_l=1)
+        ctx.sync()
+        got = [net.layer(l) for l in range(net.num_layers)]
+        capi, spectra = ctx.autoenc_fft(x, net_c, net_b, scale, shapes, None, 1)
+        for n in range(B):
+            want, _ = O.autoenc_fft(x[n], net_c, net_b, scale, None, 1)
+            for l in range(len(shapes)):
+                assert O.rel_l2(got[l][n], want[l]) < 2e-5, (n, l)
+        for l in range(len(shapes)):
+            assert O.rel_l2(got[l], capi[l]) < 2e-5, l
+        # fft_l = 0 writes the last layer only
+        net.fft_forward(x * 0.5, fft_l=0)
+        ctx.sync()
+        assert O.rel_l2(net.layer(len(shapes) - 1), 0.5 * got[-1] + 0.5 * O.autoenc_fft(np.zeros_like(x[0]), net_c, net_b, scale, None, 0)[0][-1]) < 1e-4
+        assert np.array_equal(net.layer(1), got[1])
+        # net_cfreq as a view of the resident kernels
+        for n in range(len(net_c)):
+            assert O.rel_l2(net.get_cfreq(n).ravel(), spectra[n]) < 1e-5, n
+    finally:
+        net.close()
+
+
+@pytest.mark.parametrize("cfg", CASES)
+@pytest.mark.parametrize("maxdiff", [0, 1])
+def test_net_fft_step_vs_oracle_and_capi(ctx, cfg, maxdiff):
+    D, Nx, Ny, widths, pools, B = cfg
+    if maxdiff and max(widths) > 16:
+        pytest.skip("the oracle's multiobjective term is a python loop over kernel pairs")
+    n_iter = 2
+    net, net_c, net_b, scale, shapes = make_net(ctx, D, Nx, Ny, widths, pools, B)
+    try:
+        P, N = len(widths), 2 * len(widths)
+        x = O.synth_frames(11, B, D, Nx, Ny)
+        traces = net.fft_step(x, del0=0.2, maxdiff=maxdiff, n_iter=n_iter, fft_l=0)
+        trained = [net.get_conv(n) for n in range(N)]
+        # reference-shaped path of this engine: layers in real space, then backprop_fft per pair
+        layers, _ = ctx.autoenc_fft(x, net_c, net_b, scale, shapes, None, 1)
+        for n in range(P):
+            c, f, b, p = (net_c[n].copy(), net_c[N - 1 - n].copy(), net_b[n].copy(), net_b[N - 1 - n].copy())
+            li, lo = 2 * n + 1, 2 * N - 1 - 2 * n
+            tr = ctx.backprop_fft(layers[li], layers[li], layers[lo], c, f, b, p, 0.2, maxdiff, n_iter)
+            assert np.allclose(traces[n], tr, rtol=1e-4), (n, traces[n], tr)
+            for got, want, base in ((trained[n][0], c, net_c[n]), (trained[N - 1 - n][0], f, net_c[N - 1 - n]),
+                                    (trained[n][1], b, net_b[n]), (trained[N - 1 - n][1], p, net_b[N - 1 - n])):
+                assert O.rel_l2(got, want) < 2e-5, n
+                assert O.rel_l2(got.astype(np.float64) - base, want.astype(np.float64) - base) < 1e-3, n
+        # fp64 oracle, batched: forward per frame, then backprop_fft on the stacked layers
+        olayers = [O.autoenc_fft(x[k], net_c, net_b, scale, None, 1)[0] for k in range(B)]
+        for n in range(P):
+            li, lo = 2 * n + 1, 2 * N - 1 - 2 * n
+            inp = np.stack([olayers[k][li] for k in range(B)])
+            out = np.stack([olayers[k][lo] for k in range(B)])
+            want = O.backprop_fft(inp, inp, out, net_c[n], net_c[N - 1 - n], net_b[n], net_b[N - 1 - n], 0.2, maxdiff, n_iter)
+            assert np.allclose(traces[n], want["mse"], rtol=2e-4), (n, traces[n], want["mse"])
+            for got, key, base in ((trained[n][0], "c", net_c[n]), (trained[N - 1 - n][0], "f", net_c[N - 1 - n]),
+                                   (trained[n][1], "b", net_b[n]), (trained[N - 1 - n][1], "p", net_b[N - 1 - n])):
+                assert O.rel_l2(got, want[key]) < 1e-4, (n, key)
+                assert O.rel_l2(got.astype(np.float64) - base, want[key] - base) < 2e-3, (n, key)
+    finally:
+        net.close()
+
+
+def test_net_fft_step_uses_tensor_cores_and_no_layer_transforms(ctx):
+    """At the c3 channel widths the step runs the tcgen05 contraction for pairs 1 and 2 and transforms only the frames
+    (one R2C) and the reconstruction (one C2R): no per-layer C2R/R2C round trips."""
+    net, *_ = make_net(ctx, 3, 64, 64, [16, 32, 64], [2, 2, 2], 8)
+    try:
+        x = O.synth_frames(3, 8, 3, 64, 64)
+        net.fft_step(x, n_iter=1, fft_l=0, want_mse=False)  # plans / allocates
+        ctx.profile_enable(True)
+        net.fft_step(x, n_iter=1, fft_l=0, want_mse=False)
+        rec = {r["name"]: r["launches"] for r in ctx.profile_records()}
+        ctx.profile_enable(False)
+        assert rec.get("spec_contract_tc", 0) >= 12 and rec.get("spec_outer_tc", 0) == 4, rec
+        assert rec.get("fft_rows_r2c", 0) == 1 and rec.get("fft_rows_c2r", 0) == 1, rec
+    finally:
+        net.close()
