@@ -481,8 +481,52 @@ class CoordWorkload:
         self.net.close()
 
 
+class FftNetWorkload:
+    """c3: momentum-space training on the device-resident net (aefft_net_fft_step): one R2C of the frames, forward of the
+    whole stack with every layer's spectrum kept in HBM, ONE iteration of backprop_fft's loop for every pair directly on
+    those spectra (the survey's definition of an FFT-space training step), one C2R of the reconstruction (fft_l = 0)."""
+
+    def __init__(self, A, ctx, w, batch, rank, world, dev, torch):
+        self.A, self.ctx, self.w, self.world, self.torch = A, ctx, w, world, torch
+        B = self.B = batch
+        ctypes.CDLL("libc.so.6").srand(SEED)
+        self.net = net = A.Net(ctx, w["D"], w["Nx"], w["Ny"], B)
+        for m in w["widths"]:
+            net.add_layer(m, w["Lk"], w["Ll"], w["pool"], w["rmax"] / 10.0)
+        self.P = net.num_pairs
+        for n in range(self.P):
+            net.set_symmetric(n)
+        self.n_iter, self.maxdiff = int(w.get("n_iter", 1)), int(w.get("maxdiff", 0))
+        _, _, _, self.l0 = net.layer_info(0)
+        self.n0 = B * w["D"] * w["Nx"] * w["Ny"]
+        ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=rank * B, out=self.l0, loc=A.DEVICE)
+        host = torch.empty(self.n0, dtype=torch.float32).pin_memory()
+        ctx.memcpy(host.data_ptr(), self.l0, self.n0 * 4, 1)
+        self.f32 = Staging(torch, dev, host)
+        self.h2d_bytes, self.d2h_bytes = self.n0 * 4, 4 * self.P * (self.n_iter + 1)
+        self.has_u8 = False
+
+    def step_resident(self):
+        self.net.fft_step(None, DELMAX, self.maxdiff, self.n_iter, fft_l=0, loc=self.A.DEVICE, want_mse=False)
+
+    def e2e_begin(self):
+        self.f32.begin()
+
+    def step_e2e(self):
+        slot, buf = self.f32.acquire()
+        self.net.fft_step(buf, DELMAX, self.maxdiff, self.n_iter, fft_l=0, loc=self.A.DEVICE, want_mse=True)  # syncs (mse D2H)
+        self.f32.release(slot)
+
+    def describe_e2e(self):
+        return ("pinned host frames -> double-buffered device staging on a copy stream (upload of step k+1 overlaps step k) -> "
+                "aefft_net_fft_step(AEFFT_DEVICE), mse traces of all pairs read back every step")
+
+    def close(self):
+        self.net.close()
+
+
 class FftWorkload:
-    """c3 / c4: momentum-space training.  One step = autoenc_fft forward of the whole stack (all layers materialised, as
+    """c3 (reference-shaped C-ABI path) / c4: momentum-space training.  One step = autoenc_fft forward of the whole stack (all layers materialised, as
     the reference needs them for training) + n_iter iterations of backprop_fft's loop for every pair (c3: ONE,
     the survey's definition of an FFT-space training step), on B frames, through the C ABI with device pointers."""
 
@@ -638,7 +682,9 @@ def measure(env, name, w, batch, steps, warmup, precision):
             ident.copy_(torch.frombuffer(bytearray(A.Ctx.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(ident, 0)
         ctx.comm_init(bytes(ident.cpu().numpy().tobytes()), rank, world)
-    wl = (CoordWorkload if w["space"] == "coordinate" else FftWorkload)(A, ctx, w, batch, rank, world, dev, torch)
+    cls = CoordWorkload if w["space"] == "coordinate" else FftWorkload if (w.get("shard") == "bins" or env.get("fft_capi")) \
+        else FftNetWorkload
+    wl = cls(A, ctx, w, batch, rank, world, dev, torch)
     small = batch * w["Nx"] * w["Ny"] * w["D"] * 4 <= 2e8  # working set may sit in the 126 MB L2: flush between iterations
     flush = torch.empty(64 << 20, dtype=torch.float32, device=dev) if small else None
 
@@ -723,6 +769,7 @@ def measure(env, name, w, batch, steps, warmup, precision):
                 "d2h_bytes_per_step": wl.d2h_bytes, "ms_per_step": e2e_u8_ms / steps,
                 "note": "same step, frames uploaded as interleaved 8-bit images (what the reference's camera delivers) and "
                         "converted on the device (aefft_net_set_frames_u8 = ImageToSpin_C); `e2e` above uploads fp32 frames"},
+            "path": cls.__name__ + ": " + " ".join((cls.__doc__ or "").split())[:400],
             "gpu_launches": int(launches) * world,
             "collectives_per_step": (0 if world == 1 else 1 if w["space"] == "coordinate" else
                                      len(w["widths"]) * (int(w.get("n_iter", 1)) + 1)),
@@ -753,7 +800,8 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
-    env = dict(torch=torch, dist=dist, A=A, rank=rank, world=world, dev=dev, local_rank=local_rank, stream=stream)
+    env = dict(torch=torch, dist=dist, A=A, rank=rank, world=world, dev=dev, local_rank=local_rank, stream=stream,
+               fft_capi=args.fft_capi)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()  # started before the warm-up so that samples exist for short timed regions
@@ -772,6 +820,18 @@ def run_ours(args, rank, world, local_rank):
                                     args.warmup, args.precision)
             except Exception as e:  # a failing side workload must not take the headline down
                 extra[nm] = {"error": repr(e)[:300]}
+    if not args.only and args.workload == "c2" and not args.size and not args.fft_capi:
+        # the same c3 step through the reference-shaped C-ABI calls (aefft_autoenc_fft with fft_l = 1, then
+        # aefft_backprop_fft on the real-space layers, i.e. with the per-layer C2R / R2C round trips the reference makes)
+        try:
+            env2 = dict(env, fft_capi=True)
+            ww = dict(WORKLOADS["c3"])
+            r = measure(env2, "c3", ww, ww["batch"], max(2, min(args.steps, 5)), args.warmup, args.precision)
+            if rank == 0 and isinstance(extra.get("c3"), dict) and "error" not in extra["c3"]:
+                extra["c3"]["capi_path"] = {k: r[k] for k in ("value", "unit", "ms_per_step", "e2e", "path", "gpu_launches")}
+        except Exception as e:
+            if rank == 0 and isinstance(extra.get("c3"), dict):
+                extra["c3"]["capi_path"] = {"error": repr(e)[:300]}
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         line["clocks"] = clocks
@@ -807,6 +867,9 @@ def main():
     ap.add_argument("--size", type=int, default=None, help="square frames of this edge instead of the workload's (sweeps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--fft-capi", action="store_true",
+                    help="c3 through the reference-shaped C-ABI calls (autoenc_fft fft_l=1 + backprop_fft on real-space layers) "
+                         "instead of the resident net's aefft_net_fft_step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

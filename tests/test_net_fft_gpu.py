@@ -32,7 +32,7 @@ CASES = [
     (3, 32, 32, [4, 5], [2, 2], 2),          # no tensor-core pair: the reference's bins-fastest layout throughout
     (3, 64, 64, [8, 16], [2, 2], 5),         # pair 0 CUDA cores, pair 1 tensor cores (layout change at the pooling)
     (8, 32, 64, [16, 8], [2, 1], 9),         # both pairs tensor cores, pool 1 between them, rectangular
-    (3, 64, 32, [8, 16, 32], [2, 2, 2], 8),  # the c3 stack at reduced size
+    (3, 64, 128, [8, 16, 32], [2, 2, 2], 8), # the c3 stack at reduced size
 ]
 
 
@@ -79,6 +79,7 @@ def test_net_fft_step_vs_oracle_and_capi(ctx, cfg, maxdiff):
         trained = [net.get_conv(n) for n in range(N)]
         # reference-shaped path of this engine: layers in real space, then backprop_fft per pair
         layers, _ = ctx.autoenc_fft(x, net_c, net_b, scale, shapes, None, 1)
+        layers = [np.ascontiguousarray(t) for t in layers]
         for n in range(P):
             c, f, b, p = (net_c[n].copy(), net_c[N - 1 - n].copy(), net_b[n].copy(), net_b[N - 1 - n].copy())
             li, lo = 2 * n + 1, 2 * N - 1 - 2 * n
