@@ -283,6 +283,15 @@ int launch_tc_outer(aefft_ctx* ctx, long long S, int B, int nP, int nQ, const fl
 int launch_tc_dc_terms(aefft_ctx* ctx, int B, int dM, int dD, const float* G, const float* E, const float* bias_b, float* dFt,
                        float* db, float* dp, float gs, float fs, float corr_scale);
 
+// ---- fused iteration for pairs with <= 4 input channels (spec_small.cu), bins-fastest spectra
+bool spec_small_eligible(int dD, int dM);
+int launch_small_grad(aefft_ctx* ctx, int64_t B, int dD, int dM, int64_t S, const float2* X, const float2* Xt, const float2* O,
+                      const float2* C, const float2* F, const float* bias_b, const float* bias_p, float norm, float gscale,
+                      float dbscale, float2* dC, float2* dF, float* db, float* dp);
+int launch_small_mse(aefft_ctx* ctx, int64_t B, int dD, int dM, int64_t S, const float2* X, const float2* Xt, const float2* C,
+                     const float2* F, const float* bias_b, const float* bias_p, float norm, float* mse_out, double mse_scale,
+                     int ncols, int col0, int Ny);
+
 // E~ = O~ - X~ on bin-major spectra [S][rowlen] and *mse_out = mse_scale * sum_bins hw(bin) |E|^2 (mse_out may be null)
 int launch_bm_sub_mse(aefft_ctx* ctx, long long S, long long rowlen, const float* O, const float* X, float* E, float* mse_out,
                       double mse_scale, int ncols, int col0, int Ny);

@@ -335,9 +335,13 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
     AE_TRY(ctx->getT("bpf_O", nXs, &q.O));
     if (loc == AEFFT_HOST) AE_TRY(ctx->getT("bpf_real", (size_t)B * dD * P, &real));
   }
-  if (!use_tc) {  // the bins-fastest CUDA-core path keeps H, G and the gradient spectra
-    AE_TRY(ctx->getT("bpf_H", nHs, &q.H));
-    AE_TRY(ctx->getT("bpf_G", nHs, &q.G));
+  // <= 4 input channels (the image side): one fused kernel per iteration, H / G / E never touch HBM (spec_small.cu)
+  const bool use_small = !use_tc && spec_small_eligible(dD, dM) && n_iter > 0;
+  if (!use_tc) {  // the bins-fastest CUDA-core path keeps the gradient spectra, and H, G unless fused
+    if (!use_small) {
+      AE_TRY(ctx->getT("bpf_H", nHs, &q.H));
+      AE_TRY(ctx->getT("bpf_G", nHs, &q.G));
+    }
     AE_TRY(ctx->getT("bpf_dCF", 2 * nKS, &q.dCF));
   }
   if (!use_tc || !inp.resident) {
@@ -386,6 +390,10 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
     AE_ARG(!sharded);
     q.X = const_cast<float2*>(inp.Xs);  // read only below
     q.O = const_cast<float2*>(inp.Os);
+    if (!use_tc && !use_small && n_iter > 0) {  // the generic loop rewrites O in place: work on a copy of the layer spectrum
+      AE_TRY(ctx->getT("bpf_O", nXs, &q.O));
+      AE_CUDA(cudaMemcpyAsync(q.O, inp.Os, nXs * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+    }
     Xt = q.X;
   } else {
     AE_ARG(!sharded);
@@ -486,8 +494,16 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
     }
   } else {
   // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1)
-  AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, bias_b, norm, q.H));
+  if (!use_small)
+    AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, bias_b, norm, q.H));
   for (int n = 0; n < n_iter; n++) {
+    if (use_small) {
+      // fused: H-hat, E, G formed per (bin, frame) in registers; the first iteration takes the caller's O, later ones
+      // recompute O = conv(conv(X; C, b); F, p) from the updated kernels (what :1460-1461 left in freq_out)
+      if (!own_dc) AE_CUDA(cudaMemsetAsync(q.db, 0, (size_t)(dM + dD) * sizeof(float), st));
+      AE_TRY(launch_small_grad(ctx, B, dD, dM, S, q.X, Xt, n == 0 ? q.O : nullptr, q.C, q.F, bias_b, bias_p, norm, gscale,
+                               (float)((double)norm / (Norm * (double)B)), q.dCF, q.dCF + nKS, q.db, q.dp));
+    } else {
     // G[m] = sum_d1 (O - Xt)[d1] conj(F[d1][m])
     AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.O, Xt, q.F, S, (int64_t)dM * S, 1, 1.f, nullptr, 0.f, q.G));
     // dC[m][d] = G[m] conj(X[d]) / Norm ; dF[d][m] = E[d] conj(H-hat[m]) / Norm, averaged over frames
@@ -495,6 +511,7 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
     AE_TRY(launch_spec_outer(ctx, B, dD, dM, S, q.O, Xt, q.H, (float)dM, bias_b, -(float)(dM - 1) * norm, gscale, q.dCF + nKS));
     if (own_dc) AE_TRY(launch_spec_dc_sums(ctx, B, dM, dD, S, q.G, q.O, Xt, q.db, q.dp, (float)((double)norm / (Norm * (double)B))));
     else AE_CUDA(cudaMemsetAsync(q.db, 0, (size_t)(dM + dD) * sizeof(float), st));
+    }
     // kernel-space gradients: C2R (unnormalised) + shrink_k (:1219-1226)
     AE_TRY(spectrum_taps_dev(ctx, 2 * (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.dCF, q.work, q.img, q.taps, 1.f, col0, ncols));
     // bin-sharded devices also split the kernel-space multiobjective term: each folds its share into its partial block,
@@ -513,9 +530,13 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
     AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C, col0, ncols));
     AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F, col0, ncols));
     // re-forward (:1460-1461) and mse (:1463)
+    if (use_small) {
+      AE_TRY(launch_small_mse(ctx, B, dD, dM, S, q.X, Xt, q.C, q.F, bias_b, bias_p, norm, q.mse + n + 1, mse_scale, ncols, col0, Ny));
+    } else {
     AE_TRY(launch_spec_contract(ctx, B, dD, dM, S, q.X, nullptr, q.C, (int64_t)dD * S, S, 0, 1.f / (float)dM, bias_b, norm, q.H));
     AE_TRY(launch_spec_contract(ctx, B, dM, dD, S, q.H, nullptr, q.F, (int64_t)dM * S, S, 0, 1.f / (float)dD, bias_p, norm, q.O));
     AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse + n + 1, col0, ncols));
+    }
     if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse + n + 1, 1));
   }
   }  // !use_tc

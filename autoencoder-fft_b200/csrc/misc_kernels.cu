@@ -255,7 +255,7 @@ __global__ void quirk_dF_main_kernel(const float* __restrict__ out, const float*
 // order (m; d; k; l), carrying the value last written at its pixel, and adds it to every launch whose mask excludes
 // the pixel.  Border pixels = those excluded by at least one tap's mask.
 __global__ void quirk_dF_stale_kernel(const float* __restrict__ out, const float* __restrict__ in,
-                                      const float* __restrict__ hin, float* __restrict__ gF, long long B, int dD,
+                                      const float* __restrict__ hin, double* __restrict__ acc, long long B, int dD,
                                       int dM, int Nx, int Ny, int Nk, int Nl, int bi, int bj, int c3, int n_border,
                                       int ilo, int ihi, int jlo, int jhi) {
   long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,9 +308,16 @@ __global__ void quirk_dF_stale_kernel(const float* __restrict__ out, const float
           }
 #pragma unroll
           for (int sft = 16; sft > 0; sft >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, sft);
-          if (lane == 0 && contrib != 0.f) atomicAdd(gF + (((long long)d * dM + m) * Nk + k) * Nl + l, contrib);
+          // fp64 accumulator: the order in which the warps arrive changes the sum by ~1e-16 relative, far below the fp32
+          // rounding of the result (float atomics made the last bit of gF depend on the block schedule)
+          if (lane == 0 && contrib != 0.f) atomicAdd(acc + (((long long)d * dM + m) * Nk + k) * Nl + l, (double)contrib);
         }
     }
+}
+
+__global__ void quirk_dF_fold_kernel(const double* __restrict__ acc, float* __restrict__ gF, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) gF[i] = (float)((double)gF[i] + acc[i]);
 }
 
 int launch_quirk_dF(aefft_ctx* ctx, int quirks, int64_t B, int dD, int dM, int Nx, int Ny, int Nk, int Nl,
@@ -336,10 +343,15 @@ int launch_quirk_dF(aefft_ctx* ctx, int quirks, int64_t B, int dD, int dM, int N
     if (nb > 0) {
       AE_ARG(nb <= 0x7fffffffLL);
       long long total = (long long)B * nb;
-      quirk_dF_stale_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(out, in, hin, gF, B, dD, dM, Nx,
+      const int nG = dD * dM * Nk * Nl;
+      double* acc;
+      AE_TRY(ctx->getT("quirk_acc", (size_t)nG, &acc));
+      AE_CUDA(cudaMemsetAsync(acc, 0, (size_t)nG * sizeof(double), ctx->stream));
+      quirk_dF_stale_kernel<<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(out, in, hin, acc, B, dD, dM, Nx,
                                                                                     Ny, Nk, Nl, bi, bj, c3, (int)nb, ilo,
                                                                                     ihi, jlo, jhi);
-      ctx->launches++;
+      quirk_dF_fold_kernel<<<(nG + 255) / 256, 256, 0, ctx->stream>>>(acc, gF, nG);
+      ctx->launches += 2;
       AE_CUDA(cudaGetLastError());
     }
   }

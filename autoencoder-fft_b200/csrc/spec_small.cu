@@ -1,0 +1,305 @@
+// Momentum-space training iteration for layer pairs with FEW input channels (the 3-channel image side: dD <= 4), fused.
+//
+// The reference's gradient_k_io (fft_backproplib.cu:395-475) is one thread per (m, d, bin) that recomputes G and H-hat
+// for every d; the engine's generic path splits it into contractions that each stream a [frames][dM][bins] tensor
+// through HBM (H, G written and read back: ~13 GB per iteration for 3 -> 16 channels at 512^2, 128 frames).  With 3 input
+// channels everything a (bin, frame) needs fits in registers, so ONE kernel reads X (and the caller's O on the first
+// iteration), forms H-hat, E, G on the fly and accumulates the frame-reduced outer products dC, dF in registers:
+// HBM traffic = X + O + the gradient spectra (~1 GB).  A second kernel does the post-update re-forward + mse
+// (conv_k twice + calc_mse, :1460-1463) without writing H or O at all.  Later iterations recompute O = F.H from X.
+//
+// Thread mapping: 4 consecutive lanes share a bin, each owns 4 hidden channels m (its rows of C, columns of F, and
+// the matching 4 x dD blocks of dC / dF); sums over m (the decoder output O) are butterfly-reduced inside the lane group.
+// Spectra are the reference layout [frame][channel][bins] / [m][d][bins], bins fastest (coalesced 8-byte accesses).
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace aefft {
+
+namespace {
+
+__device__ __forceinline__ void cmac(float2& acc, float2 a, float2 b) {  // acc += a*b
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(-a.y, b.y, acc.x);
+  acc.y = fmaf(a.x, b.y, acc.y); acc.y = fmaf(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ void cmac_conj(float2& acc, float2 a, float2 b) {  // acc += a*conj(b)
+  acc.x = fmaf(a.x, b.x, acc.x); acc.x = fmaf(a.y, b.y, acc.x);
+  acc.y = fmaf(a.y, b.x, acc.y); acc.y = fmaf(-a.x, b.y, acc.y);
+}
+
+struct SmallParams {
+  const float2 *X, *Xt, *O;  // [B][dD][S]; O == nullptr: recompute O = conv(conv(X; C, b); F, p)
+  const float2 *C, *F;       // [dM][dD][S], [dD][dM][S]
+  const float *bias_b, *bias_p;  // applied at bin 0 (nullptr on devices that do not own the DC column)
+  float2 *dC, *dF;           // [dM][dD][S], [dD][dM][S]
+  float *db, *dp;            // written by the threads of bin 0 (when bias_b != nullptr, i.e. the DC owner)
+  double* part;              // mse kernel: per-block partial sums
+  long long S;
+  int B, dM, ncols, col0, Ny;
+  float norm, gscale, dbscale;
+};
+
+template <int DD, int LG, bool HAS_O>
+__global__ void __launch_bounds__(128) small_grad_kernel(SmallParams p) {
+  // LG = lanes per bin = dM / 4
+  const int tid = threadIdx.x;
+  const int mq = tid % LG;
+  const long long w = (long long)blockIdx.x * (128 / LG) + tid / LG;
+  const bool live = w < p.S;
+  const long long wc = live ? w : 0;
+  const int dM = p.dM;
+  const float inv_dM = 1.f / (float)dM, inv_dD = 1.f / (float)DD;
+  float2 Cq[4][DD], Fq[DD][4], dCq[4][DD], dFq[DD][4];
+  float bb[4], bp[DD];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int m = 4 * mq + a;
+#pragma unroll
+    for (int d = 0; d < DD; d++) {
+      Cq[a][d] = __ldg(p.C + ((long long)m * DD + d) * p.S + wc);
+      Fq[d][a] = __ldg(p.F + ((long long)d * dM + m) * p.S + wc);
+      dCq[a][d] = make_float2(0.f, 0.f);
+      dFq[d][a] = make_float2(0.f, 0.f);
+    }
+    bb[a] = (wc == 0 && p.bias_b) ? p.bias_b[m] * p.norm : 0.f;
+  }
+#pragma unroll
+  for (int d = 0; d < DD; d++) bp[d] = (wc == 0 && p.bias_p) ? p.bias_p[d] * p.norm : 0.f;
+  float gsum[4] = {0.f, 0.f, 0.f, 0.f}, esum[DD];
+#pragma unroll
+  for (int d = 0; d < DD; d++) esum[d] = 0.f;
+  const long long fs = (long long)DD * p.S;
+  for (int b = 0; b < p.B; b++) {
+    float2 x[DD], e[DD], hh[4];
+#pragma unroll
+    for (int d = 0; d < DD; d++) x[d] = __ldg(p.X + b * fs + d * p.S + wc);
+    // H-hat[m] = sum_d C[m][d] X[d] + b[m] Nx Ny at DC  (no /dM: quirk F1);  H = (H-hat - bias)/dM + bias
+    if (!HAS_O) {
+#pragma unroll
+      for (int d = 0; d < DD; d++) e[d] = make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int d = 0; d < DD; d++) cmac(s, Cq[a][d], x[d]);
+      hh[a] = make_float2(s.x + bb[a], s.y);
+      if (!HAS_O) {  // this lane's share of the decoder output O = sum_m F[d][m] H[m] (reduced over the lane group below)
+        const float2 h = make_float2(fmaf(s.x, inv_dM, bb[a]), s.y * inv_dM);
+#pragma unroll
+        for (int d = 0; d < DD; d++) cmac(e[d], Fq[d][a], h);
+      }
+    }
+    if (HAS_O) {
+#pragma unroll
+      for (int d = 0; d < DD; d++) {
+        const float2 o = __ldg(p.O + b * fs + d * p.S + wc), t = __ldg(p.Xt + b * fs + d * p.S + wc);
+        e[d] = make_float2(o.x - t.x, o.y - t.y);
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < DD; d++) {
+#pragma unroll
+        for (int o = 1; o < LG; o <<= 1) {
+          e[d].x += __shfl_xor_sync(0xffffffffu, e[d].x, o);
+          e[d].y += __shfl_xor_sync(0xffffffffu, e[d].y, o);
+        }
+        const float2 t = __ldg(p.Xt + b * fs + d * p.S + wc);
+        e[d] = make_float2(fmaf(e[d].x, inv_dD, bp[d]) - t.x, e[d].y * inv_dD - t.y);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      float2 g = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int d = 0; d < DD; d++) cmac_conj(g, e[d], Fq[d][a]);
+      gsum[a] += g.x;
+#pragma unroll
+      for (int d = 0; d < DD; d++) {
+        cmac_conj(dCq[a][d], g, x[d]);
+        cmac_conj(dFq[d][a], e[d], hh[a]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < DD; d++) esum[d] += e[d].x;
+  }
+  if (!live) return;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int m = 4 * mq + a;
+#pragma unroll
+    for (int d = 0; d < DD; d++) {
+      p.dC[((long long)m * DD + d) * p.S + w] = make_float2(dCq[a][d].x * p.gscale, dCq[a][d].y * p.gscale);
+      p.dF[((long long)d * dM + m) * p.S + w] = make_float2(dFq[d][a].x * p.gscale, dFq[d][a].y * p.gscale);
+    }
+  }
+  if (w == 0 && p.db) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) p.db[4 * mq + a] = gsum[a] * p.dbscale;
+    if (mq == 0) {
+#pragma unroll
+      for (int d = 0; d < DD; d++) p.dp[d] = esum[d] * p.dbscale;
+    }
+  }
+}
+
+// re-forward + mse: sum over bins and frames of hw(bin) |conv(conv(X; C, b); F, p) - Xt|^2
+template <int DD, int LG>
+__global__ void __launch_bounds__(128) small_mse_kernel(SmallParams p) {
+  const int tid = threadIdx.x;
+  const int mq = tid % LG;
+  const long long w = (long long)blockIdx.x * (128 / LG) + tid / LG;
+  const bool live = w < p.S;
+  const long long wc = live ? w : 0;
+  const int dM = p.dM;
+  const float inv_dM = 1.f / (float)dM, inv_dD = 1.f / (float)DD;
+  float2 Cq[4][DD], Fq[DD][4];
+  float bb[4], bp[DD];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int m = 4 * mq + a;
+#pragma unroll
+    for (int d = 0; d < DD; d++) {
+      Cq[a][d] = __ldg(p.C + ((long long)m * DD + d) * p.S + wc);
+      Fq[d][a] = __ldg(p.F + ((long long)d * dM + m) * p.S + wc);
+    }
+    bb[a] = (wc == 0 && p.bias_b) ? p.bias_b[m] * p.norm : 0.f;
+  }
+#pragma unroll
+  for (int d = 0; d < DD; d++) bp[d] = (wc == 0 && p.bias_p) ? p.bias_p[d] * p.norm : 0.f;
+  const long long fs = (long long)DD * p.S;
+  float acc = 0.f;
+  double tot = 0.0;
+  for (int b = 0; b < p.B; b++) {
+    float2 x[DD], o[DD];
+#pragma unroll
+    for (int d = 0; d < DD; d++) { x[d] = __ldg(p.X + b * fs + d * p.S + wc); o[d] = make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int d = 0; d < DD; d++) cmac(s, Cq[a][d], x[d]);
+      s.x = fmaf(s.x, inv_dM, bb[a]);
+      s.y *= inv_dM;
+#pragma unroll
+      for (int d = 0; d < DD; d++) cmac(o[d], Fq[d][a], s);
+    }
+#pragma unroll
+    for (int d = 0; d < DD; d++) {
+#pragma unroll
+      for (int k = 1; k < LG; k <<= 1) {
+        o[d].x += __shfl_xor_sync(0xffffffffu, o[d].x, k);
+        o[d].y += __shfl_xor_sync(0xffffffffu, o[d].y, k);
+      }
+      const float2 t = __ldg(p.Xt + b * fs + d * p.S + wc);
+      const float ex = fmaf(o[d].x, inv_dD, bp[d]) - t.x, ey = o[d].y * inv_dD - t.y;
+      acc = fmaf(ex, ex, fmaf(ey, ey, acc));
+    }
+    if ((b & 7) == 7) { tot += (double)acc; acc = 0.f; }
+  }
+  tot += (double)acc;
+  const int wy = p.col0 + (int)(wc % p.ncols);
+  const double hw = (wy == 0 || wy == p.Ny / 2) ? 1.0 : 2.0;
+  if (!live || mq != 0) tot = 0.0;
+  tot *= hw;
+  __shared__ double red[128];
+  red[tid] = tot;
+  __syncthreads();
+  for (int h = 64; h > 0; h >>= 1) {
+    if (tid < h) red[tid] += red[tid + h];
+    __syncthreads();
+  }
+  if (tid == 0) p.part[blockIdx.x] = red[0];
+}
+
+__global__ void small_final_kernel(const double* __restrict__ part, long long n, double scale, float* __restrict__ out) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int h = 128; h > 0; h >>= 1) {
+    if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = (float)(red[0] * scale);
+}
+
+template <int DD, int LG>
+int run_grad(aefft_ctx* ctx, const SmallParams& p) {
+  const long long blocks = (p.S + 128 / LG - 1) / (128 / LG);
+  if (p.O) small_grad_kernel<DD, LG, true><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p);
+  else small_grad_kernel<DD, LG, false><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p);
+  return AEFFT_OK;
+}
+template <int DD, int LG>
+int run_mse(aefft_ctx* ctx, const SmallParams& p) {
+  const long long blocks = (p.S + 128 / LG - 1) / (128 / LG);
+  small_mse_kernel<DD, LG><<<(unsigned)blocks, 128, 0, ctx->stream>>>(p);
+  return AEFFT_OK;
+}
+
+#define AEFFT_SMALL_DISPATCH(FN, dD, lg, ...)                                                   \
+  do {                                                                                          \
+    if (dD == 1) { SMALL_LG(FN, 1, lg, __VA_ARGS__); }                                          \
+    else if (dD == 2) { SMALL_LG(FN, 2, lg, __VA_ARGS__); }                                     \
+    else if (dD == 3) { SMALL_LG(FN, 3, lg, __VA_ARGS__); }                                     \
+    else { SMALL_LG(FN, 4, lg, __VA_ARGS__); }                                                  \
+  } while (0)
+#define SMALL_LG(FN, DD, lg, ...)                                                               \
+  switch (lg) {                                                                                 \
+    case 1: FN<DD, 1>(__VA_ARGS__); break;                                                      \
+    case 2: FN<DD, 2>(__VA_ARGS__); break;                                                      \
+    case 4: FN<DD, 4>(__VA_ARGS__); break;                                                      \
+    case 8: FN<DD, 8>(__VA_ARGS__); break;                                                      \
+    default: FN<DD, 16>(__VA_ARGS__); break;                                                    \
+  }
+
+}  // namespace
+
+bool spec_small_eligible(int dD, int dM) {
+  if (getenv("AEFFT_NO_SPEC_SMALL")) return false;
+  const int lg = dM / 4;
+  return dD >= 1 && dD <= 4 && dM % 4 == 0 && (lg == 1 || lg == 2 || lg == 4 || lg == 8 || lg == 16);
+}
+
+// gradient spectra dC [dM][dD][S], dF [dD][dM][S] (scaled by gscale) and the DC-bin bias gradients of one iteration
+int launch_small_grad(aefft_ctx* ctx, int64_t B, int dD, int dM, int64_t S, const float2* X, const float2* Xt, const float2* O,
+                      const float2* C, const float2* F, const float* bias_b, const float* bias_p, float norm, float gscale,
+                      float dbscale, float2* dC, float2* dF, float* db, float* dp) {
+  AE_ARG(spec_small_eligible(dD, dM));
+  SmallParams p{X, Xt, O, C, F, bias_b, bias_p, dC, dF, bias_b ? db : nullptr, dp, nullptr, S, (int)B, dM, 1, 0, 2, norm, gscale,
+                dbscale};
+  const double px = (double)B * S;
+  ProfScope prof(ctx, "spec_small_grad", 8.0 * px * dM * dD * (O ? 4 : 5), 8.0 * (px * dD * (O ? (Xt == X ? 2 : 3) : (Xt == X ? 1 : 2)) + 4.0 * S * dM * dD));
+  AEFFT_SMALL_DISPATCH(run_grad, dD, dM / 4, ctx, p);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// *mse_out = mse_scale * sum hw |conv(conv(X; C, b); F, p) - Xt|^2 over the owned bins and the frames
+int launch_small_mse(aefft_ctx* ctx, int64_t B, int dD, int dM, int64_t S, const float2* X, const float2* Xt, const float2* C,
+                     const float2* F, const float* bias_b, const float* bias_p, float norm, float* mse_out, double mse_scale,
+                     int ncols, int col0, int Ny) {
+  AE_ARG(spec_small_eligible(dD, dM));
+  const int lg = dM / 4;
+  const long long blocks = (S + 128 / lg - 1) / (128 / lg);
+  double* part;
+  AE_TRY(ctx->getT("small_part", (size_t)blocks, &part));
+  SmallParams p{X, Xt, nullptr, C, F, bias_b, bias_p, nullptr, nullptr, nullptr, nullptr, part, S, (int)B, dM,
+                ncols > 0 ? ncols : Ny / 2 + 1, ncols > 0 ? col0 : 0, Ny, norm, 0.f, 0.f};
+  const double px = (double)B * S;
+  {
+    ProfScope prof(ctx, "spec_small_mse", 8.0 * px * dM * dD * 2, 8.0 * (px * dD * (Xt == X ? 1 : 2) + 2.0 * S * dM * dD));
+    AEFFT_SMALL_DISPATCH(run_mse, dD, lg, ctx, p);
+    ctx->launches++;
+  }
+  small_final_kernel<<<1, 256, 0, ctx->stream>>>(part, blocks, mse_scale, mse_out);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+}  // namespace aefft

@@ -397,3 +397,35 @@ def test_fft_batched_vs_live_reference_per_frame(ctx, ref):
     for k in "cfbp":
         assert O.rel_l2(w[k], want[k]) < 1e-4, k
         assert O.rel_l2(w[k].astype(np.float64) - cs[k], want[k].astype(np.float64) - cs[k]) < 5e-3, k
+
+
+@pytest.mark.parametrize("dims,B,maxdiff", [((16, 3, 5, 5, 32, 32), 8, 0), ((8, 2, 3, 3, 16, 32), 3, 1), ((4, 4, 5, 5, 16, 16), 5, 0),
+                                            ((64, 1, 5, 5, 16, 16), 2, 0)])
+def test_backprop_fft_fused_small_channel_path(ctx, dims, B, maxdiff):
+    """Pairs with <= 4 input channels (the 3-channel image side of every net) run one fused kernel per iteration
+    (spec_small.cu): against the fp64 oracle, and against the generic contraction path it replaces; expout != in."""
+    cs = fft_case(61, *dims, B=B, wscale=0.1)
+    rng = np.random.default_rng(62)
+    tgt = (cs["inp"] + np.floor(rng.random(cs["inp"].shape) * 16)).astype(np.float32)
+    runs = {}
+    for tag in ("fused", "generic"):
+        if tag == "generic":
+            os.environ["AEFFT_NO_SPEC_SMALL"] = "1"
+        try:
+            w = {k: cs[k].copy() for k in "cfbp"}
+            ctx.profile_enable(True)
+            trace = ctx.backprop_fft(cs["inp"], tgt, cs["out"], w["c"], w["f"], w["b"], w["p"], 0.2, maxdiff, 3)
+            names = _names(ctx)
+            ctx.profile_enable(False)
+        finally:
+            os.environ.pop("AEFFT_NO_SPEC_SMALL", None)
+        runs[tag] = (w, trace, names)
+    assert {"spec_small_grad", "spec_small_mse"} <= runs["fused"][2], runs["fused"][2]
+    assert "spec_small_grad" not in runs["generic"][2]
+    want = O.backprop_fft(cs["inp"], tgt, cs["out"], cs["c"], cs["f"], cs["b"], cs["p"], 0.2, maxdiff, 3)
+    assert np.allclose(runs["fused"][1], want["mse"], rtol=2e-4), (runs["fused"][1], want["mse"])
+    assert np.allclose(runs["fused"][1], runs["generic"][1], rtol=1e-4)
+    for k in "cfbp":
+        assert O.rel_l2(runs["fused"][0][k], want[k]) < 1e-4, k
+        assert O.rel_l2(runs["fused"][0][k], runs["generic"][0][k]) < 2e-5, k
+        assert O.rel_l2(runs["fused"][0][k].astype(np.float64) - cs[k], want[k] - cs[k]) < 2e-3, k
