@@ -478,6 +478,11 @@ class Net:
                                       _ptr(trace)))
         return trace
 
+    def fft_train_pair(self, n_l, del0=0.2, maxdiff=0, n_iter=100):
+        trace = np.zeros(n_iter + 1, np.float32)
+        _chk(lib().aefft_net_fft_train_pair(self.h, int(n_l), C.c_float(del0), int(maxdiff), int(n_iter), _ptr(trace)))
+        return trace
+
     def get_cfreq(self, n):
         dM, dD, Nk, Nl, _ = self.conv_dims(n)
         N = 2 * self.num_pairs

@@ -407,8 +407,11 @@ int aefft_net_pair_update(aefft_net* net, int n_l, int mode, int64_t B_global, f
 }
 
 int aefft_net_train_pair(aefft_net* net, int n_l, int mode, int quirks, float delmax, float alpha, float* mse) {
-  AE_TRY(aefft_net_pair_gradients(net, n_l, mode, quirks, nullptr, nullptr));
-  return aefft_net_pair_update(net, n_l, mode, net->B, delmax, alpha, mse);
+  float* g = nullptr;
+  int64_t len = 0;
+  AE_TRY(aefft_net_pair_gradients(net, n_l, mode, quirks, &g, &len));
+  AE_TRY(comm_allreduce(net->ctx, g, len, 0));  // data-parallel ranks: sum of the raw blocks (no-op for world == 1)
+  return aefft_net_pair_update(net, n_l, mode, net->B * net->ctx->comm_world, delmax, alpha, mse);
 }
 
 // One whole training step: forward + train every pair once on that forward's activations (order 0..pairs-1).

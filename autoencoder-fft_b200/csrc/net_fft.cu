@@ -185,6 +185,30 @@ int aefft_net_fft_forward(aefft_net* net, int loc, const float* frames, int fft_
   return forward(net, loc, frames, fft_l);
 }
 
+// backprop_fft (:1381-1511) of pair n_l on the spectra the last aefft_net_fft_forward / _step left in HBM
+// (autoencoder.cpp:190-196: in = layers[2n+1], out = layers[size-2-2n], c = net_c[n], f = net_c[N-1-n]).
+static int train_pair_spectra(aefft_net* net, int n, float del0, int maxdiff, int n_iter, float* trace_dev, float* trace_host) {
+  aefft_ctx* ctx = net->ctx;
+  const int N = (int)net->convs.size();
+  AE_ARG((int)net->spec.size() == (int)net->layers.size());  // a forward has planned and filled the spectra
+  const ConvL &e = net->convs[n], &d = net->convs[N - 1 - n];
+  const int li = 2 * n + 1, lo = 2 * N - 1 - 2 * n;
+  const LayerL& L = net->layers[li];
+  FftTrainInputs inp;
+  if (net->spec[li].bin_major) { inp.Xbm = net->spec[li].p; inp.Obm = net->spec[lo].p; }
+  else { inp.Xs = (const float2*)net->spec[li].p; inp.Os = (const float2*)net->spec[lo].p; }
+  inp.resident = true;
+  inp.trace_dev = trace_dev;
+  return backprop_fft_run(ctx, AEFFT_DEVICE, net->B, e.dD, e.dM, L.Nx, L.Ny, e.Nk, e.Nl, inp, nullptr, e.c, nullptr, d.c, e.b, d.b,
+                          del0, maxdiff, n_iter, trace_host);
+}
+
+int aefft_net_fft_train_pair(aefft_net* net, int n_l, float del0, int maxdiff, int n_iter, float* mse_trace) {
+  AE_ARG(net && n_l >= 0 && n_l < (int)net->pairs.size() && n_iter >= 1);
+  AE_CUDA(cudaSetDevice(net->ctx->device));
+  return train_pair_spectra(net, n_l, del0, maxdiff, n_iter, nullptr, mse_trace);
+}
+
 int aefft_net_fft_step(aefft_net* net, int loc, const float* frames, float del0, int maxdiff, int n_iter, int fft_l,
                        float* mse) {
   AE_ARG(net && net->convs.size() >= 2 && n_iter >= 1);
@@ -199,19 +223,8 @@ int aefft_net_fft_step(aefft_net* net, int loc, const float* frames, float del0,
     AE_CUDA(cudaMalloc((void**)&net->fft_trace, (size_t)tlen * sizeof(float)));
     net->fft_trace_cap = tlen;
   }
-  for (int n = 0; n < P; n++) {
-    // pair n: in = layers[2n+1], out = layers[size-2-2n], c = net_c[n], f = net_c[N-1-n] (autoencoder.cpp:161-196)
-    const ConvL &e = net->convs[n], &d = net->convs[N - 1 - n];
-    const int li = 2 * n + 1, lo = 2 * N - 1 - 2 * n;
-    const LayerL& L = net->layers[li];
-    FftTrainInputs inp;
-    if (net->spec[li].bin_major) { inp.Xbm = net->spec[li].p; inp.Obm = net->spec[lo].p; }
-    else { inp.Xs = (const float2*)net->spec[li].p; inp.Os = (const float2*)net->spec[lo].p; }
-    inp.resident = true;
-    inp.trace_dev = net->fft_trace + (size_t)n * (n_iter + 1);
-    AE_TRY(backprop_fft_run(ctx, AEFFT_DEVICE, net->B, e.dD, e.dM, L.Nx, L.Ny, e.Nk, e.Nl, inp, nullptr, e.c, nullptr, d.c, e.b, d.b,
-                            del0, maxdiff, n_iter, nullptr));
-  }
+  for (int n = 0; n < P; n++)
+    AE_TRY(train_pair_spectra(net, n, del0, maxdiff, n_iter, net->fft_trace + (size_t)n * (n_iter + 1), nullptr));
   if (mse) {
     AE_CUDA(cudaMemcpyAsync(mse, net->fft_trace, (size_t)tlen * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     AE_CUDA(cudaStreamSynchronize(ctx->stream));

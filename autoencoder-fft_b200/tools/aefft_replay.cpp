@@ -2,8 +2,13 @@
 // over the C ABI of libaefft: the "caller" side of the drop-in boundary without the webcam / OpenCV window.
 //
 //   aefft_replay [--frames B] [--size NxxNy] [--channels D] [--seed S] [--param FILE] [--weights DIR]
-//                [--precision fp32|bf16x3|bf16] [--del 0.2] [--alpha 0.9] [--quirks 7]
-//                --script "n n t5 z t3 p t2 s d l t1 i"
+//                [--precision fp32|bf16x3|bf16] [--del 0.2] [--alpha 0.9] [--quirks 7] [--fft-iters 100]
+//                [--device K --rank R --world W --id-file PATH]
+//                --script "n n t5 z t3 p t2 s d l t1 i f g t1"
+// --rank/--world/--id-file: data-parallel frames over W processes, one GPU each, WITHOUT any Python: rank 0 writes the
+// NCCL unique id (aefft_comm_unique_id) to PATH, the others read it, every rank calls aefft_comm_init; rank r then
+// trains on frames [it*W*B + r*B, +B) and the engine all-reduces the raw gradient block before every update, so all
+// ranks print the same mse lines as ONE process with --frames W*B.
 // --quirks: bit mask of the reference's backprop_gpu defects to reproduce (aefft.h AEFFT_QUIRK_*).  Default: all of them
 // on square frames (= what the reference computes), none on non-square frames, where the reference indexes out of bounds
 // and the library only offers the intended gradients.
@@ -13,14 +18,19 @@
 //   z / x  next / previous active pair; the shared momentum / last-gradient buffers restart (:279-310)
 //   e  re-draw the weights of the active pair (:311-325)      p  toggle symmetric weights, copying c into f (:331-356)
 //   s / l  save / load the active pair's weight files (:357-382)      i  print the structure (:458-)
+//   f  toggle momentum (FFT) space (:274)      g  toggle fft_l, the inverse transform of every layer (:275)
+//   m  toggle the multiobjective kernel-diversity term (:278)
 //   tK  K iterations of: synthetic frames (SURVEY 8d generator, frame counter advancing) -> forward -> backprop of the
 //       active pair (backprop_gpu, or backprop_gpu_cc when symmetric), one "mse" line each like the reference prints.
+//       In FFT mode: autoenc_fft forward (:131-132) -> backprop_fft of the active pair (:190-196, --fft-iters iterations,
+//       the reference hard-codes 100), printing its "mse fft:" / "n: .. mse:" lines (fft_backproplib.cu:1441, :1464).
 // Every event prints one line; the run ends with "replay ok" and exit code 0, or the library's error text and 1.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
+#include <unistd.h>
 
 #include "aefft.h"
 
@@ -37,7 +47,8 @@ int main(int argc, char** argv) {
   int D = 3, Nx = 640, Ny = 480, precision = AEFFT_PRECISION_BF16X3, quirks = -1;
   unsigned seed = 1234;
   float del = 0.2f, alpha = 0.9f;
-  std::string param = "New_Layer_Param.txt", weights = "./weights", script;
+  std::string param = "New_Layer_Param.txt", weights = "./weights", script, id_file;
+  int device = 0, rank = 0, world = 1, fft_iters = 100;
   for (int a = 1; a < argc; a++) {
     const std::string k = argv[a];
     const char* v = a + 1 < argc ? argv[a + 1] : "";
@@ -51,6 +62,11 @@ int main(int argc, char** argv) {
     else if (k == "--alpha") { alpha = (float)std::atof(v); a++; }
     else if (k == "--script") { script = v; a++; }
     else if (k == "--quirks") { quirks = std::atoi(v); a++; }
+    else if (k == "--device") { device = std::atoi(v); a++; }
+    else if (k == "--rank") { rank = std::atoi(v); a++; }
+    else if (k == "--world") { world = std::atoi(v); a++; }
+    else if (k == "--id-file") { id_file = v; a++; }
+    else if (k == "--fft-iters") { fft_iters = std::atoi(v); a++; }
     else if (k == "--precision") {
       precision = !std::strcmp(v, "fp32") ? AEFFT_PRECISION_FP32 : !std::strcmp(v, "bf16") ? AEFFT_PRECISION_BF16 : AEFFT_PRECISION_BF16X3;
       a++;
@@ -59,11 +75,30 @@ int main(int argc, char** argv) {
   if (quirks < 0) quirks = Nx == Ny ? AEFFT_QUIRKS_ALL : 0;
   aefft_ctx* ctx = nullptr;
   aefft_net* net = nullptr;
-  CHECK(aefft_create(&ctx, 0));
+  CHECK(aefft_create(&ctx, device));
   CHECK(aefft_set_precision(ctx, precision));
+  if (world > 1) {
+    // bootstrap of the engine's NCCL communicator through a file (any channel works: the id is 128 opaque bytes)
+    if (id_file.empty()) { std::fprintf(stderr, "aefft_replay: --world needs --id-file\n"); return 1; }
+    unsigned char id[AEFFT_COMM_ID_BYTES];
+    if (rank == 0) {
+      CHECK(aefft_comm_unique_id(id));
+      const std::string tmp = id_file + ".tmp";
+      FILE* fh = std::fopen(tmp.c_str(), "wb");
+      if (!fh || std::fwrite(id, 1, sizeof(id), fh) != sizeof(id)) { std::fprintf(stderr, "aefft_replay: cannot write %s\n", tmp.c_str()); return 1; }
+      std::fclose(fh);
+      std::rename(tmp.c_str(), id_file.c_str());
+    } else {
+      FILE* fh = nullptr;
+      for (int tries = 0; tries < 600 && !(fh = std::fopen(id_file.c_str(), "rb")); tries++) usleep(100000);
+      if (!fh || std::fread(id, 1, sizeof(id), fh) != sizeof(id)) { std::fprintf(stderr, "aefft_replay: cannot read %s\n", id_file.c_str()); return 1; }
+      std::fclose(fh);
+    }
+    CHECK(aefft_comm_init(ctx, id, rank, world));
+  }
   CHECK(aefft_net_create(ctx, &net, D, Nx, Ny, B));
   std::srand(seed);  // the reference seeds once and draws every Init_conv from the same stream (autoencoder.cpp:100)
-  int n_l = 0, sym = 0;
+  int n_l = 0, sym = 0, fft = 0, fft_l = 0, maxdiff = 0;
   int64_t frame0 = 0;
   // start-up: the reference builds its first pair from the parameter file before the loop (:98-120)
   auto add_layer = [&]() -> int {
@@ -112,6 +147,15 @@ int main(int argc, char** argv) {
       CHECK(aefft_net_set_conv(net, n_l, c.data(), b.data()));
       CHECK(aefft_net_set_conv(net, N - n_l, f.data(), p.data()));
       std::printf("Initialize random convolutional weights\n");
+    } else if (t == "f") {
+      fft = (fft + 1) % 2;
+      std::printf("fft %d\n", fft);
+    } else if (t == "g") {
+      fft_l = (fft_l + 1) % 2;
+      std::printf("fft_l %d\n", fft_l);
+    } else if (t == "m") {
+      maxdiff = (maxdiff + 1) % 2;
+      std::printf("multiobjective %d\n", maxdiff);
     } else if (t == "p") {
       sym = (sym + 1) % 2;
       std::printf("Symmetric weights %d\n", sym);
@@ -141,9 +185,17 @@ int main(int argc, char** argv) {
       int D0, X0, Y0;
       float* layer0 = nullptr;
       CHECK(aefft_net_layer(net, 0, &D0, &X0, &Y0, &layer0));
+      std::vector<float> trace((size_t)fft_iters + 1);
       for (int it = 0; it < K; it++) {
-        CHECK(aefft_synth_frames(ctx, AEFFT_DEVICE, 1234, frame0, B, D0, X0, Y0, layer0));
-        frame0 += B;
+        CHECK(aefft_synth_frames(ctx, AEFFT_DEVICE, 1234, frame0 + (int64_t)rank * B, B, D0, X0, Y0, layer0));
+        frame0 += B * world;
+        if (fft) {
+          CHECK(aefft_net_fft_forward(net, AEFFT_DEVICE, nullptr, fft_l));
+          CHECK(aefft_net_fft_train_pair(net, n_l, del, maxdiff, fft_iters, trace.data()));
+          std::printf("mse fft: %.6g\n", (double)trace[0]);
+          for (int n = 0; n < fft_iters; n++) std::printf("n: %d mse: %.6g\n", n, (double)trace[n + 1]);
+          continue;
+        }
         CHECK(aefft_net_forward(net, AEFFT_DEVICE, nullptr));
         float mse = 0.f;
         CHECK(aefft_net_train_pair(net, n_l, sym ? AEFFT_MODE_CUDA_REF_SYM : AEFFT_MODE_CUDA_REF, quirks, del, alpha, &mse));

@@ -273,7 +273,8 @@ int aefft_net_forward(aefft_net* net, int loc, const float* frames);
  * normalised.  Uploading bytes moves 4x less data over PCIe than float frames; follow with aefft_net_forward /
  * aefft_net_step with frames == NULL (layer 0 already set). */
 int aefft_net_set_frames_u8(aefft_net* net, int loc, const unsigned char* images);
-/* train pair n_l on the activations of the last forward (autoencoder.cpp:158-201, q=1).  *mse host or NULL. */
+/* train pair n_l on the activations of the last forward (autoencoder.cpp:158-201, q=1).  *mse host or NULL.
+ * With a communicator (world > 1) the pair's raw gradient block is all-reduced before the update (B_global = B * world). */
 int aefft_net_train_pair(aefft_net* net, int n_l, int mode, int quirks, float delmax, float alpha, float* mse);
 /* raw gradient block of pair n_l into the net's gradient buffer (device ptr returned), then update: the
  * data-parallel split (all-reduce the buffer in between). */
@@ -290,6 +291,9 @@ int aefft_net_pair_update(aefft_net* net, int n_l, int mode, int64_t B_global, f
 int aefft_net_fft_forward(aefft_net* net, int loc, const float* frames, int fft_l);
 int aefft_net_fft_step(aefft_net* net, int loc, const float* frames, float del0, int maxdiff, int n_iter, int fft_l,
                        float* mse);
+/* backprop_fft of ONE pair (the active pair n_l of autoencoder.cpp:190-196) on the spectra of the last
+ * aefft_net_fft_forward / aefft_net_fft_step; mse_trace: host, n_iter+1 floats, or NULL. */
+int aefft_net_fft_train_pair(aefft_net* net, int n_l, float del0, int maxdiff, int n_iter, float* mse_trace);
 /* net_cfreq[n] (fft_backproplib.cu:1146-1161) as a lazily computed VIEW of the device-resident kernels of conv n:
  * the interleaved wire-format spectrum [dM][dD][Nx][Ny/2+1][2] at the resolution conv n runs at, n_floats = its length.
  * The reference keeps this as a host cache that is uploaded (51-136 MB per layer) on every frame. */

@@ -2,7 +2,9 @@
 application's key-driven state machine -- add / delete layer from New_Layer_Param.txt, layer cycling with momentum
 restart, weight re-draw, symmetric toggle, save / load -- over the C ABI.  The same event sequence is replayed here
 through ctypes on the same library; seeded weights, synthetic frames and kernels are deterministic, so every "mse" line
-must agree to the printed precision."""
+must agree to the printed precision.  Further down the driver's output is checked against the ORACLE (coordinate mode:
+backprop_gpu with its quirks; FFT mode, keys f / g: autoenc_fft + backprop_fft), and two C++-only data-parallel ranks
+against one rank holding all frames."""
 import ctypes
 import os
 import subprocess
@@ -11,6 +13,7 @@ import numpy as np
 import pytest
 
 import aefft_ctypes as A
+import oracle_np as O
 from conftest import ROOT
 
 pytestmark = pytest.mark.gpu
@@ -110,3 +113,119 @@ def test_replay_driver_reports_errors(tmp_path):
     run = subprocess.run([exe, "--size", "32x32", "--param", str(tmp_path / "missing.txt"), "--script", "n"],
                          capture_output=True, text=True, timeout=120)
     assert run.returncode == 1 and "aefft_replay" in run.stderr
+
+
+# ---------------------------------------------------------------------------------------------- against the oracle
+def _run(exe, tmp_path, args, script, timeout=300):
+    (tmp_path / "New_Layer_Param.txt").write_text(PARAM)
+    (tmp_path / "weights").mkdir(exist_ok=True)
+    run = subprocess.run([exe, "--param", str(tmp_path / "New_Layer_Param.txt"), "--weights", str(tmp_path / "weights"), *args,
+                          "--script", script], capture_output=True, text=True, timeout=timeout)
+    assert run.returncode == 0, run.stderr
+    lines = run.stdout.splitlines()
+    assert lines[-1] == "replay ok"
+    return lines
+
+
+def _oracle_net(seed, D, n_pairs):
+    """The weights the driver draws: srand(seed), per pair Init_conv(c,b) then Init_conv(f,p) then the four zero-inits that
+    still consume rand() (autoencoder.cpp:100-107, :412-428), with the parameters of PARAM."""
+    dM, Lk, Ll, scal, rmax = [float(l.split()[1]) for l in PARAM.strip().splitlines()]
+    dM, Nk, Nl, scal = int(dM), 2 * (int(Lk) + 1) + 1, 2 * (int(Ll) + 1) + 1, int(scal)
+    rng = O.GlibcRand(seed)
+    encs, d = [], D
+    for _ in range(n_pairs):
+        c, b = O.init_conv(rng, dM, d, Nk, Nl, rmax)
+        f, p = O.init_conv(rng, d, dM, Nk, Nl, rmax)
+        for a, bb in ((dM, d), (d, dM), (dM, d), (d, dM)):
+            O.init_conv(rng, a, bb, Nk, Nl, 0.0)
+        encs.append((c, b, f, p))
+        d = dM
+    net_c = [e[0] for e in encs] + [e[2] for e in reversed(encs)]
+    net_b = [e[1] for e in encs] + [e[3] for e in reversed(encs)]
+    return net_c, net_b, [scal] * n_pairs + [-scal] * n_pairs
+
+
+def test_replay_coordinate_mse_lines_match_the_oracle(tmp_path):
+    """`n t3` on one square frame: the driver's mse lines are the oracle's backprop_gpu (all quirks, momentum carried) on
+    the oracle's own forward -- not a comparison of the library with itself."""
+    from test_coord_gpu import oracle_forward
+
+    lines = _run(driver_exe(), tmp_path, ["--frames", "1", "--size", "32x32", "--channels", "3", "--seed", "77", "--precision", "fp32"],
+                 "n t3")
+    got = [float(l.split()[1]) for l in lines if l.startswith("mse ")]
+    net_c, net_b, scale = _oracle_net(77, 3, 1)
+    c, b, f, p = net_c[0].astype(np.float64), net_b[0].astype(np.float64), net_c[1].astype(np.float64), net_b[1].astype(np.float64)
+    st = {k: np.zeros_like(v) for k, v in (("dc", c), ("db", b), ("df", f), ("dp", p))}
+    want = []
+    for it in range(3):
+        x = O.synth_frames(1234, 1, 3, 32, 32, b0=it)
+        L = oracle_forward(x, [c, f], [b, p], scale)
+        z = lambda a: np.zeros_like(a)
+        r = O.backprop_gpu(L[1][0], L[3][0], L[2][0], c, b, f, p, st["dc"], st["db"], st["df"], st["dp"], z(c), z(b), z(f), z(p),
+                           0.2, 0.9, quirks=True)
+        c, b, f, p = r["c"], r["b"], r["f"], r["p"]
+        st = {k: r[k] for k in st}
+        want.append(r["mse"])
+    assert len(got) == 3 and np.allclose(got, want, rtol=1e-4), (got, want)
+
+
+def test_replay_fft_mode_matches_the_oracle(tmp_path):
+    """`f g t2`: momentum-space forward + backprop_fft of the active pair; the "mse fft:" / "n: .. mse:" lines are the
+    oracle's (autoenc_fft + backprop_fft, fft_backproplib.cu:1331-1511) for the weights the driver drew."""
+    iters = 6
+    lines = _run(driver_exe(), tmp_path, ["--frames", "2", "--size", "32x32", "--channels", "3", "--seed", "91", "--fft-iters", str(iters),
+                                          "--del", "0.05"], "n f g t2")
+    assert "fft 1" in lines and "fft_l 1" in lines
+    got0 = [float(l.split()[2]) for l in lines if l.startswith("mse fft:")]
+    gotn = [float(l.split()[3]) for l in lines if l.startswith("n: ")]
+    assert len(got0) == 2 and len(gotn) == 2 * iters
+    net_c, net_b, scale = _oracle_net(91, 3, 1)
+    N, n_l = 2, 0
+    want0, wantn = [], []
+    for it in range(2):
+        x = O.synth_frames(1234, 2, 3, 32, 32, b0=2 * it)
+        layers = [O.autoenc_fft(x[k], net_c, net_b, scale, None, 1)[0] for k in range(2)]
+        li, lo = 2 * n_l + 1, 2 * N - 1 - 2 * n_l
+        inp = np.stack([layers[k][li] for k in range(2)])
+        out = np.stack([layers[k][lo] for k in range(2)])
+        r = O.backprop_fft(inp, inp, out, net_c[n_l], net_c[N - 1 - n_l], net_b[n_l], net_b[N - 1 - n_l], 0.05, 0, iters)
+        net_c[n_l], net_c[N - 1 - n_l], net_b[n_l], net_b[N - 1 - n_l] = r["c"], r["f"], r["b"], r["p"]
+        want0.append(r["mse"][0])
+        wantn += list(r["mse"][1:])
+    assert np.allclose(got0, want0, rtol=2e-4), (got0, want0)
+    assert np.allclose(gotn, wantn, rtol=2e-4), (gotn, wantn)
+
+
+def _gpu_count():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True, timeout=30).stdout
+        return sum(1 for l in out.splitlines() if l.startswith("GPU "))
+    except Exception:
+        return 0
+
+
+def test_replay_two_ranks_equal_one_rank_with_twice_the_frames(tmp_path):
+    """C++ only, no Python in the training processes: two aefft_replay ranks (one GPU each, the engine's own NCCL
+    communicator bootstrapped through a file) print the mse lines of one rank that holds both ranks' frames."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    exe = driver_exe()
+    (tmp_path / "New_Layer_Param.txt").write_text(PARAM)
+    (tmp_path / "weights").mkdir()
+    common = ["--size", "48x48", "--channels", "3", "--seed", "5", "--param", str(tmp_path / "New_Layer_Param.txt"), "--weights",
+              str(tmp_path / "weights")]
+    script = "n p t3 z t2 f t1"
+    one = subprocess.run([exe, "--frames", "4", *common, "--fft-iters", "4", "--script", script], capture_output=True, text=True,
+                         timeout=300)
+    assert one.returncode == 0, one.stderr
+    procs = [subprocess.Popen([exe, "--frames", "2", *common, "--fft-iters", "4", "--device", str(r), "--rank", str(r), "--world", "2",
+                               "--id-file", str(tmp_path / "nccl.id"), "--script", script], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se
+    pick = lambda text: [float(l.split()[-1]) for l in text.splitlines() if l.startswith(("mse ", "mse fft:", "n: "))]
+    want, r0, r1 = pick(one.stdout), pick(outs[0][0]), pick(outs[1][0])
+    assert len(want) == 5 + 5 and r0 == r1          # replicas stay identical without any broadcast
+    assert np.allclose(r0, want, rtol=2e-5), (r0, want)
