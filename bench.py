@@ -676,12 +676,21 @@ def measure(env, name, w, batch, steps, warmup, precision):
     stream = env["stream"]
     A._chk(A.lib().aefft_set_stream(ctx.h, ctypes.c_void_p(stream.cuda_stream)))
     if world > 1:
-        # the engine's own communicator: rank 0's NCCL unique id travels through torch.distributed (rendezvous only)
-        ident = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            ident.copy_(torch.frombuffer(bytearray(A.Ctx.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(ident, 0)
-        ctx.comm_init(bytes(ident.cpu().numpy().tobytes()), rank, world)
+        # the engine's own communicator: rank 0's NCCL unique id travels through torch.distributed (rendezvous only).
+        # NCCL prints its version banner to stdout on the first communicator: keep stdout for the one JSON line.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            ident = torch.zeros(128, dtype=torch.uint8, device=dev)
+            if rank == 0:
+                ident.copy_(torch.frombuffer(bytearray(A.Ctx.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(ident, 0)
+            ctx.comm_init(bytes(ident.cpu().numpy().tobytes()), rank, world)
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     cls = CoordWorkload if w["space"] == "coordinate" else FftWorkload if (w.get("shard") == "bins" or env.get("fft_capi")) \
         else FftNetWorkload
     wl = cls(A, ctx, w, batch, rank, world, dev, torch)

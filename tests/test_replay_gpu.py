@@ -213,7 +213,7 @@ def test_replay_two_ranks_equal_one_rank_with_twice_the_frames(tmp_path):
     exe = driver_exe()
     (tmp_path / "New_Layer_Param.txt").write_text(PARAM)
     (tmp_path / "weights").mkdir()
-    common = ["--size", "48x48", "--channels", "3", "--seed", "5", "--param", str(tmp_path / "New_Layer_Param.txt"), "--weights",
+    common = ["--size", "64x64", "--channels", "3", "--seed", "5", "--param", str(tmp_path / "New_Layer_Param.txt"), "--weights",
               str(tmp_path / "weights")]
     script = "n p t3 z t2 f t1"
     one = subprocess.run([exe, "--frames", "4", *common, "--fft-iters", "4", "--script", script], capture_output=True, text=True,
