@@ -88,6 +88,20 @@ int comm_alltoall(aefft_ctx* ctx, const float* send, float* recv, int64_t chunk)
   return AEFFT_OK;
 }
 
+// all-to-all with per-peer counts (floats) and offsets: the frame-sharded -> bin-sharded exchange of spectrum slabs
+int comm_alltoallv(aefft_ctx* ctx, const float* send, const int64_t* scount, const int64_t* soff, float* recv,
+                   const int64_t* rcount, const int64_t* roff) {
+  NcclApi* a = api();
+  AE_ARG(a && ctx->comm && ctx->comm_world > 1);
+  AE_NCCL(a->GroupStart());
+  for (int r = 0; r < ctx->comm_world; r++) {
+    if (scount[r] > 0) AE_NCCL(a->Send(send + soff[r], (size_t)scount[r], ncclFloat, r, (ncclComm_t)ctx->comm, ctx->stream));
+    if (rcount[r] > 0) AE_NCCL(a->Recv(recv + roff[r], (size_t)rcount[r], ncclFloat, r, (ncclComm_t)ctx->comm, ctx->stream));
+  }
+  AE_NCCL(a->GroupEnd());
+  return AEFFT_OK;
+}
+
 }  // namespace aefft
 
 using namespace aefft;

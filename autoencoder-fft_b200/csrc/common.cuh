@@ -302,7 +302,8 @@ int launch_bm_resize(aefft_ctx* ctx, long long rowlen, int Nx, int Ny, int Nxs, 
 struct FftTrainInputs {
   const float *in = nullptr, *expout = nullptr, *out = nullptr;  // real-space frames [B][dD][Nx][Ny] (per `loc`) ...
   int64_t fstride = 0;                                           // ... or per-frame blocks `fstride` floats apart (device)
-  const float2 *Xs = nullptr, *Os = nullptr;   // device spectra, bins-fastest [B][dD][Nx][Nyr]  (expout = in)
+  const float2 *Xs = nullptr, *Os = nullptr;   // device spectra, bins-fastest [B][dD][Nx][Nyr]  (expout = in); under bin
+                                               // sharding: this device's column slab [B][dD][Nx][ncols] of ALL frames
   const float *Xbm = nullptr, *Obm = nullptr;  // device spectra, bin-major [bin][B][2 dD]         (expout = in)
   bool resident = false;      // c,f,b,p are the device-resident masters: no export through the spectra, and no stream
                               // synchronisation unless a host trace is requested
@@ -320,6 +321,8 @@ int comm_allreduce(aefft_ctx* ctx, float* dev, int64_t n_floats, int op);
 // slab exchange of a bin-sharded transform: rank r sends send + r'*chunk floats to every r' and receives into
 // recv + r'*chunk (ncclSend/ncclRecv group = all-to-all over NVSwitch)
 int comm_alltoall(aefft_ctx* ctx, const float* send, float* recv, int64_t chunk_floats);
+int comm_alltoallv(aefft_ctx* ctx, const float* send, const int64_t* scount, const int64_t* soff, float* recv,
+                   const int64_t* rcount, const int64_t* roff);
 
 // ---- host orchestration shared by capi.cu and net.cu ------------------------------------------------
 int64_t gbuf_len(int mode, int dD, int dM, int Nk, int Nl);

@@ -312,7 +312,7 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
   const int col0 = (int)((long long)srank * Nyr / world), ncols = (int)((long long)(srank + 1) * Nyr / world) - col0;
   const bool sharded = world > 1;
   if (sharded) {
-    AE_ARG(ncols > 0 && !cfreq && !ffreq && loc == AEFFT_DEVICE);
+    AE_ARG(ncols > 0 && !cfreq && !ffreq && loc == AEFFT_DEVICE && !have_bm);
     if (!ctx->grad_hook && ctx->comm_world <= 1) {
       set_error("bin-sharded aefft_backprop_fft needs a communicator (aefft_comm_init) or a gradient hook (sum over devices)");
       return AEFFT_ERR_ARG;
@@ -326,7 +326,9 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
   const cudaMemcpyKind k_out = loc == AEFFT_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   FftPairBufs q;
   float *real, *wts;  // wts = [c | f | b | p]
-  const bool use_tc = spec_tc_eligible(dD, dM, Nk, Nl) && !cfreq && !ffreq && n_iter > 0;
+  // (with a handful of frames the per-bin weight blocks dominate the traffic and the embedded form doubles them: the
+  // bins-fastest kernels are faster there; a bin-major caller has made that choice already)
+  const bool use_tc = spec_tc_eligible(dD, dM, Nk, Nl) && !cfreq && !ffreq && n_iter > 0 && (B >= 16 || have_bm);
   q.X = q.Xt = q.O = q.H = q.G = q.C = q.F = q.dCF = q.work = nullptr;
   q.img = real = nullptr;
   if (have_real) {
@@ -387,8 +389,7 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
     }
     AE_TRY(load_fft(out, q.O));
   } else if (have_ff) {
-    AE_ARG(!sharded);
-    q.X = const_cast<float2*>(inp.Xs);  // read only below
+    q.X = const_cast<float2*>(inp.Xs);  // read only below (sharded: the caller exchanged the slabs already)
     q.O = const_cast<float2*>(inp.Os);
     if (!use_tc && !use_small && n_iter > 0) {  // the generic loop rewrites O in place: work on a copy of the layer spectrum
       AE_TRY(ctx->getT("bpf_O", nXs, &q.O));

@@ -14,6 +14,7 @@
 // layers bin-major [bin][frame][2 ch]; the others (3-channel image side) keep the reference's [frame][ch][Nx][Nyr].
 // Level changes (spectral pooling, resize :87-157) convert where the two sides differ.
 #include <cstdio>
+#include <vector>
 
 #include "net.cuh"
 
@@ -50,7 +51,8 @@ int level_of(int l, int N) {
 
 bool pair_tc(const aefft_net* net, int n) {
   const ConvL& e = net->convs[n];
-  return spec_tc_eligible(e.dD, e.dM, e.Nk, e.Nl);
+  // few frames: weight traffic dominates (fft_capi.cu); bin sharding exchanges bins-fastest column slabs
+  return net->B >= 16 && net->ctx->shard_world == 1 && spec_tc_eligible(e.dD, e.dM, e.Nk, e.Nl);
 }
 
 size_t spec_floats(const aefft_net* net, int l) {
@@ -195,10 +197,49 @@ static int train_pair_spectra(aefft_net* net, int n, float del0, int maxdiff, in
   const int li = 2 * n + 1, lo = 2 * N - 1 - 2 * n;
   const LayerL& L = net->layers[li];
   FftTrainInputs inp;
-  if (net->spec[li].bin_major) { inp.Xbm = net->spec[li].p; inp.Obm = net->spec[lo].p; }
-  else { inp.Xs = (const float2*)net->spec[li].p; inp.Os = (const float2*)net->spec[lo].p; }
   inp.resident = true;
   inp.trace_dev = trace_dev;
+  const int W = ctx->shard_world;
+  if (W > 1) {
+    // Frequency-bin sharding (BASELINE config 4).  The forward ran data parallel: this rank holds the FULL spectra of its own
+    // net->B frames.  Training wants the opposite split -- this rank's column slab of ALL W*B frames -- so the pair's in /
+    // out spectra are cut into W column slabs and exchanged (one all-to-all over NVSwitch per spectrum: the transpose step of
+    // a slab-decomposed transform); the received blocks, ordered by source rank, ARE the frame-major slab
+    // [W*B][dD][Nx][ncols] that backprop_fft's sharded form consumes.  Kernels / biases stay replicated: the partial
+    // kernel-space gradient blocks are all-reduced inside backprop_fft_run.
+    AE_ARG(ctx->comm_world == W && ctx->comm_rank == ctx->shard_rank && !net->spec[li].bin_major);
+    const int Nyr = L.Ny / 2 + 1, me = ctx->shard_rank;
+    const int64_t img = net->B * e.dD;  // images per rank
+    std::vector<int64_t> scount(W), soff(W), rcount(W), roff(W);
+    int64_t so = 0;
+    const int my_c0 = (int)((long long)me * Nyr / W), my_nc = (int)((long long)(me + 1) * Nyr / W) - my_c0;
+    for (int r = 0; r < W; r++) {
+      const int c0 = (int)((long long)r * Nyr / W), nc = (int)((long long)(r + 1) * Nyr / W) - c0;
+      scount[r] = 2 * img * L.Nx * nc;  // floats
+      soff[r] = so;
+      so += scount[r];
+      rcount[r] = 2 * img * L.Nx * my_nc;
+      roff[r] = (int64_t)r * rcount[r];
+    }
+    float *send, *rx, *ro;
+    AE_TRY(ctx->getT("nf_a2a_send", (size_t)so, &send));
+    AE_TRY(ctx->getT("nf_a2a_X", (size_t)W * rcount[0], &rx));
+    AE_TRY(ctx->getT("nf_a2a_O", (size_t)W * rcount[0], &ro));
+    for (int which = 0; which < 2; which++) {
+      const float2* full = (const float2*)net->spec[which ? lo : li].p;
+      for (int r = 0; r < W; r++) {
+        const int c0 = (int)((long long)r * Nyr / W), nc = (int)((long long)(r + 1) * Nyr / W) - c0;
+        AE_TRY(launch_spec_slab(ctx, img, L.Nx, L.Ny, full, (float2*)(send + soff[r]), c0, nc));
+      }
+      AE_TRY(comm_alltoallv(ctx, send, scount.data(), soff.data(), which ? ro : rx, rcount.data(), roff.data()));
+    }
+    inp.Xs = (const float2*)rx;
+    inp.Os = (const float2*)ro;
+    return backprop_fft_run(ctx, AEFFT_DEVICE, net->B * W, e.dD, e.dM, L.Nx, L.Ny, e.Nk, e.Nl, inp, nullptr, e.c, nullptr, d.c, e.b,
+                            d.b, del0, maxdiff, n_iter, trace_host);
+  }
+  if (net->spec[li].bin_major) { inp.Xbm = net->spec[li].p; inp.Obm = net->spec[lo].p; }
+  else { inp.Xs = (const float2*)net->spec[li].p; inp.Os = (const float2*)net->spec[lo].p; }
   return backprop_fft_run(ctx, AEFFT_DEVICE, net->B, e.dD, e.dM, L.Nx, L.Ny, e.Nk, e.Nl, inp, nullptr, e.c, nullptr, d.c, e.b, d.b,
                           del0, maxdiff, n_iter, trace_host);
 }

@@ -49,7 +49,7 @@ WORKLOADS = {
     # configs[3]: 5 pairs (widths assumed), multiobjective term, 2048x2048 frames, FREQUENCY-BIN SHARDED:
     # every GPU holds all `batch` frames and owns a slab of spectrum columns (strong scaling); n_iter iterations per
     # backprop_fft call amortise the frame transforms (the reference runs 100 per call)
-    "c4": dict(D=3, Nx=2048, Ny=2048, widths=[16, 32, 64, 128, 256], Lk=1, Ll=1, pool=2, rmax=3.0, batch=4, space="fft",
+    "c4": dict(D=3, Nx=2048, Ny=2048, widths=[16, 32, 64, 128, 256], Lk=1, Ll=1, pool=2, rmax=3.0, batch=32, space="fft",
                shard="bins", n_iter=10, maxdiff=1),
 }
 DELMAX, ALPHA = 0.2, 0.9  # autoencoder.cpp:87-89
@@ -312,7 +312,8 @@ def config_dict(w, args, world, name=None, batch=None):
                     + f"{w['Nx']}x{w['Ny']} frames, batch {batch} per GPU",
         "global_batch": batch * (1 if w.get("shard") == "bins" else world),
         "pairs": [{"dD": d, "dM": m, "Nx": x, "Ny": y} for d, m, x, y in geo],
-        "parallelism": (f"bins{world} (frequency-bin sharded backprop_fft, {w.get('n_iter', 1)} iterations per call)")
+        "parallelism": (f"bins{world} (forward data parallel over {world} x {batch // world if not name or True else batch} frames, all-to-all of the "
+                        f"pairs' spectrum slabs, frequency-bin sharded backprop_fft with {w.get('n_iter', 1)} iterations per call)")
                        if w.get("shard") == "bins" else f"dp{world}",
         "cache": "inputs larger than L2 (frames + activations per step >> 126 MB); no explicit flush" if batch * w["Nx"] * w["Ny"] * w["D"] * 4 > 2e8
                  else "L2 flushed between timed iterations (256 MB scratch write)",
@@ -488,6 +489,14 @@ class FftNetWorkload:
 
     def __init__(self, A, ctx, w, batch, rank, world, dev, torch):
         self.A, self.ctx, self.w, self.world, self.torch = A, ctx, w, world, torch
+        self.shard = w.get("shard") == "bins"
+        if self.shard:
+            # c4: the GLOBAL batch is fixed (strong scaling): every rank forwards batch/world frames, the pairs' spectra are
+            # exchanged into column slabs (all-to-all) and training runs bin sharded (aefft_set_bin_shard)
+            assert batch % world == 0, "c4: the batch must divide over the ranks"
+            batch //= world
+            if world > 1:
+                ctx.set_bin_shard(rank, world)
         B = self.B = batch
         ctypes.CDLL("libc.so.6").srand(SEED)
         self.net = net = A.Net(ctx, w["D"], w["Nx"], w["Ny"], B)
@@ -691,8 +700,7 @@ def measure(env, name, w, batch, steps, warmup, precision):
         finally:
             os.dup2(saved, 1)
             os.close(saved)
-    cls = CoordWorkload if w["space"] == "coordinate" else FftWorkload if (w.get("shard") == "bins" or env.get("fft_capi")) \
-        else FftNetWorkload
+    cls = CoordWorkload if w["space"] == "coordinate" else FftWorkload if env.get("fft_capi") else FftNetWorkload
     wl = cls(A, ctx, w, batch, rank, world, dev, torch)
     small = batch * w["Nx"] * w["Ny"] * w["D"] * 4 <= 2e8  # working set may sit in the 126 MB L2: flush between iterations
     flush = torch.empty(64 << 20, dtype=torch.float32, device=dev) if small else None

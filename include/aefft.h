@@ -196,6 +196,12 @@ int aefft_set_gradient_hook(aefft_ctx* ctx, aefft_gradient_hook_fn fn, void* use
  * over the devices (NCCL all-reduce(sum) on the ctx stream); kernels / biases end identical everywhere.  The one-off
  * frame transform is amortised over the n_iter (reference: 100) iterations of a call.  world == 1 restores the default. */
 int aefft_set_bin_shard(aefft_ctx* ctx, int rank, int world);
+/* On the resident net (aefft_net_fft_step / aefft_net_fft_train_pair) bin sharding needs the ctx's communicator
+ * (aefft_comm_init with the same rank / world) and must be set BEFORE the first momentum-space call on the net.  The net
+ * then holds this rank's share of the frames (global batch = B * world): the forward runs data parallel on them, each
+ * trained pair's in / out spectra are cut into column slabs and exchanged with one all-to-all per spectrum (the transpose
+ * of a slab-decomposed transform, over NVLink / NVSwitch), training runs on this rank's slab of ALL frames, and the partial
+ * kernel-space gradient blocks are all-reduced (sum) -- nothing is replicated except the (tiny) kernels. */
 
 /* backprop_fft (fft_backproplib.cu:1381-1511): n_iter (reference: 100) iterations of spectral gradients ->
  * kernel-space clipped-momentum update (lr 0.1*del0, alpha 0.9, momentum zeroed per call) -> re-forward.

@@ -30,9 +30,9 @@ def make_net(ctx, D, Nx, Ny, widths, pools, B, rmax=0.1, seed=4321):
 
 CASES = [
     (3, 32, 32, [4, 5], [2, 2], 2),          # no tensor-core pair: the reference's bins-fastest layout throughout
-    (3, 64, 64, [8, 16], [2, 2], 5),         # pair 0 CUDA cores, pair 1 tensor cores (layout change at the pooling)
-    (8, 32, 64, [16, 8], [2, 1], 9),         # both pairs tensor cores, pool 1 between them, rectangular
-    (3, 64, 128, [8, 16, 32], [2, 2, 2], 8), # the c3 stack at reduced size
+    (3, 64, 64, [8, 16], [2, 2], 16),        # pair 0 CUDA cores, pair 1 tensor cores (layout change at the pooling)
+    (8, 32, 64, [16, 8], [2, 1], 17),        # both pairs tensor cores, pool 1 between them, rectangular
+    (3, 64, 128, [8, 16, 32], [2, 2, 2], 16), # the c3 stack at reduced size
 ]
 
 
@@ -108,9 +108,9 @@ def test_net_fft_step_vs_oracle_and_capi(ctx, cfg, maxdiff):
 def test_net_fft_step_uses_tensor_cores_and_no_layer_transforms(ctx):
     """At the c3 channel widths the step runs the tcgen05 contraction for pairs 1 and 2 and transforms only the frames
     (one R2C) and the reconstruction (one C2R): no per-layer C2R/R2C round trips."""
-    net, *_ = make_net(ctx, 3, 64, 64, [16, 32, 64], [2, 2, 2], 8)
+    net, *_ = make_net(ctx, 3, 64, 64, [16, 32, 64], [2, 2, 2], 16)
     try:
-        x = O.synth_frames(3, 8, 3, 64, 64)
+        x = O.synth_frames(3, 16, 3, 64, 64)
         net.fft_step(x, n_iter=1, fft_l=0, want_mse=False)  # plans / allocates
         ctx.profile_enable(True)
         net.fft_step(x, n_iter=1, fft_l=0, want_mse=False)
