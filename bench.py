@@ -812,7 +812,17 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else {"numa_node": None, "note": "single process: not bound"}
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout when the first communicator comes up: stdout carries only the JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     # all engine work, the collectives and the timing events share ONE non-default torch stream
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
