@@ -405,6 +405,58 @@ __global__ void __launch_bounds__(256) kernel_spectrum_emb_kernel_t(const float*
   }
 }
 
+// Separable form: spec(wx, wy) = sum_k Ex_k(wx) u_k(wy), u_k(wy) = sum_l taps[k][l] Ey_l(wy).  A thread owns one kernel
+// (r, c), forms the NK column factors once per spectrum column and pays NK complex multiply-adds per bin (20 FMA for
+// 5 taps instead of 50); a CTA covers KS_COLS columns x KS_ROWS rows.
+constexpr int KS_COLS = 4, KS_ROWS = 32;
+template <int NK, int NL>
+__global__ void __launch_bounds__(256) kernel_spectrum_emb_sep_kernel(const float* __restrict__ taps, float* __restrict__ emb, int R,
+                                                                      int C, int Nx, int Ny, int ncols, int col0,
+                                                                      const float2* __restrict__ twx,
+                                                                      const float2* __restrict__ twy) {
+  __shared__ float2 ex[KS_ROWS][NK], ey[KS_COLS][NL];
+  const int wl0 = blockIdx.x * KS_COLS, wx0 = blockIdx.z * KS_ROWS;
+  for (int i = threadIdx.x; i < KS_ROWS * NK; i += blockDim.x) {
+    const int rr = i / NK, k = i - rr * NK, wx = wx0 + rr;
+    ex[rr][k] = wx < Nx ? twx[(wx * ((k - NK / 2) & (Nx - 1))) & (Nx - 1)] : make_float2(0.f, 0.f);
+  }
+  for (int i = threadIdx.x; i < KS_COLS * NL; i += blockDim.x) {
+    const int cc = i / NL, l = i - cc * NL, wy = col0 + wl0 + cc;
+    ey[cc][l] = wl0 + cc < ncols ? twy[(wy * ((l - NL / 2) & (Ny - 1))) & (Ny - 1)] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  const int e = blockIdx.y * blockDim.x + threadIdx.x;
+  if (e >= R * C) return;
+  const int r = e / C, c = e - r * C;
+  float tp[NK * NL];
+#pragma unroll
+  for (int t = 0; t < NK * NL; t++) tp[t] = __ldg(taps + (size_t)e * (NK * NL) + t);
+  const int nrows = min(KS_ROWS, Nx - wx0);
+  for (int cc = 0; cc < KS_COLS && wl0 + cc < ncols; cc++) {
+    float2 u[NK];
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+      float ur = 0.f, ui = 0.f;
+#pragma unroll
+      for (int l = 0; l < NL; l++) { ur = fmaf(tp[k * NL + l], ey[cc][l].x, ur); ui = fmaf(tp[k * NL + l], ey[cc][l].y, ui); }
+      u[k] = make_float2(ur, ui);
+    }
+    for (int rr = 0; rr < nrows; rr++) {
+      float vr = 0.f, vi = 0.f;
+#pragma unroll
+      for (int k = 0; k < NK; k++) {
+        const float2 a = ex[rr][k];
+        vr = fmaf(a.x, u[k].x, fmaf(-a.y, u[k].y, vr));
+        vi = fmaf(a.x, u[k].y, fmaf(a.y, u[k].x, vi));
+      }
+      const long long w = (long long)(wx0 + rr) * ncols + wl0 + cc;
+      float* o = emb + ((w * 2 * R + 2 * r) * 2 * (long long)C + 2 * c);
+      *reinterpret_cast<float2*>(o) = make_float2(vr, -vi);
+      *reinterpret_cast<float2*>(o + 2 * C) = make_float2(vi, vr);
+    }
+  }
+}
+
 // ---- kernel-space gradients from bin-major gradient spectra: part[(n*nsplit + sp)*T + t] = sum over the bins of split sp of
 //      h(wy) Re( z[w][e] conj(Ex[k](wx) Ey[l](wy)) ),  n = e or its transpose (the dF^T block holds dF[d][m] at [m][d])
 constexpr int BT_BINS = 16;
@@ -454,6 +506,58 @@ __global__ void __launch_bounds__(128) binmajor_to_taps_kernel(const float2* __r
     for (int t = 0; t < T; t++) part[((size_t)n * nsplit + sp) * T + t] = g[t];
   }
 }
+// Separable form of the same reduction: Ey_l depends on the column only, so a thread first folds a whole spectrum ROW into
+// NL complex partial sums t[l] = sum_wy h(wy) z conj(Ey_l(wy)) (NL complex multiply-adds per bin instead of NK*NL real
+// pairs) and applies the NK row factors conj(Ex_k(wx)) once per row.  The h-weighted column factors of the slab sit in
+// shared memory.  Splits are over rows.
+template <int NK, int NL>
+__global__ void __launch_bounds__(128) binmajor_to_taps_sep_kernel(const float2* __restrict__ z, float* __restrict__ part, int E,
+                                                                   int R, int C, int transpose, int Nx, int Ny, int ncols, int col0,
+                                                                   const float2* __restrict__ twx,
+                                                                   const float2* __restrict__ twy) {
+  extern __shared__ float2 phy[];  // [ncols][NL]
+  for (int i = threadIdx.x; i < ncols * NL; i += blockDim.x) {
+    const int wl = i / NL, l = i - wl * NL, wy = col0 + wl;
+    const float h = (wy == 0 || wy == Ny / 2) ? 1.f : 2.f;
+    const float2 ey = twy[(wy * ((l - NL / 2) & (Ny - 1))) & (Ny - 1)];
+    phy[i] = make_float2(h * ey.x, h * ey.y);
+  }
+  __syncthreads();
+  const int nsplit = gridDim.y, sp = blockIdx.y;
+  const int r_lo = (int)((long long)Nx * sp / nsplit), r_hi = (int)((long long)Nx * (sp + 1) / nsplit);
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  float g[NK * NL];
+#pragma unroll
+  for (int t = 0; t < NK * NL; t++) g[t] = 0.f;
+  for (int wx = r_lo; wx < r_hi; wx++) {
+    float2 t[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) t[l] = make_float2(0.f, 0.f);
+    const float2* zr = z + (long long)wx * ncols * E + e;
+#pragma unroll 4
+    for (int wl = 0; wl < ncols; wl++) {
+      const float2 v = __ldg(zr + (long long)wl * E);
+#pragma unroll
+      for (int l = 0; l < NL; l++) {  // t[l] += v * conj(phy)
+        const float2 ph = phy[wl * NL + l];
+        t[l].x = fmaf(v.x, ph.x, fmaf(v.y, ph.y, t[l].x));
+        t[l].y = fmaf(v.y, ph.x, fmaf(-v.x, ph.y, t[l].y));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NK; k++) {
+      const float2 ex = __ldg(twx + ((wx * ((k - NK / 2) & (Nx - 1))) & (Nx - 1)));
+#pragma unroll
+      for (int l = 0; l < NL; l++) g[k * NL + l] = fmaf(t[l].x, ex.x, fmaf(t[l].y, ex.y, g[k * NL + l]));  // Re(t conj(ex))
+    }
+  }
+  int n = e;
+  if (transpose) { const int r = e / C, c = e - r * C; n = c * R + r; }
+#pragma unroll
+  for (int t = 0; t < NK * NL; t++) part[((size_t)n * nsplit + sp) * (NK * NL) + t] = g[t];
+}
+
 __global__ void taps_final_kernel(const float* __restrict__ part, float* __restrict__ taps, long long total, int nsplit, int T,
                                   float scale) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -573,8 +677,14 @@ int launch_kernel_spectrum_emb(aefft_ctx* ctx, int R, int C, int Nk, int Nl, int
   const int T = Nk * Nl;
   AE_ARG(T <= KE_MAXT);
   dim3 grid((unsigned)((S + KE_BINS - 1) / KE_BINS), (unsigned)((R * C + 255) / 256));
-  ProfScope prof(ctx, "kernel_spectrum_emb", 4.0 * S * R * C * T, 16.0 * S * R * C);
-  if (T == 25) kernel_spectrum_emb_kernel_t<25><<<grid, 256, 0, ctx->stream>>>(taps, emb, R, C, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
+  const bool sep = Nk == Nl && (Nk == 5 || Nk == 3 || Nk == 7) && !getenv("AEFFT_EMB_NOSEP");
+  ProfScope prof(ctx, "kernel_spectrum_emb", 4.0 * S * R * C * (sep ? 2.0 * Nk : (double)T), 16.0 * S * R * C);
+  if (sep) {
+    dim3 g2((unsigned)((ncols + KS_COLS - 1) / KS_COLS), (unsigned)((R * C + 255) / 256), (unsigned)((Nx + KS_ROWS - 1) / KS_ROWS));
+    if (Nk == 5) kernel_spectrum_emb_sep_kernel<5, 5><<<g2, 256, 0, ctx->stream>>>(taps, emb, R, C, Nx, Ny, ncols, col0, twx, twy);
+    else if (Nk == 3) kernel_spectrum_emb_sep_kernel<3, 3><<<g2, 256, 0, ctx->stream>>>(taps, emb, R, C, Nx, Ny, ncols, col0, twx, twy);
+    else kernel_spectrum_emb_sep_kernel<7, 7><<<g2, 256, 0, ctx->stream>>>(taps, emb, R, C, Nx, Ny, ncols, col0, twx, twy);
+  } else if (T == 25) kernel_spectrum_emb_kernel_t<25><<<grid, 256, 0, ctx->stream>>>(taps, emb, R, C, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
   else if (T == 9) kernel_spectrum_emb_kernel_t<9><<<grid, 256, 0, ctx->stream>>>(taps, emb, R, C, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
   else if (T == 49) kernel_spectrum_emb_kernel_t<49><<<grid, 256, 0, ctx->stream>>>(taps, emb, R, C, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
   else kernel_spectrum_emb_kernel<<<grid, 256, 0, ctx->stream>>>(taps, emb, R, C, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
@@ -595,15 +705,29 @@ int launch_binmajor_to_taps(aefft_ctx* ctx, int R, int C, int transpose, int Nk,
   AE_ARG(T == 25 || T == 9 || T == 49);
   const int etiles = (E + 127) / 128;
   long long nsplit = (4LL * ctx->sm_count + etiles - 1) / etiles;
-  if (nsplit > S / BT_BINS) nsplit = S / BT_BINS;
+  const bool sep = (Nk == Nl) && (Nk == 5 || Nk == 3 || Nk == 7) && !getenv("AEFFT_TAPS_NOSEP");
+  const long long max_split = sep ? Nx : S / BT_BINS;
+  if (nsplit > max_split) nsplit = max_split;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > 65535) nsplit = 65535;
   float* part;
   AE_TRY(ctx->getT("tc_taps_part", (size_t)E * nsplit * T, &part));
   dim3 grid(etiles, (unsigned)nsplit);
   {
-    ProfScope prof(ctx, "binmajor_to_taps", 4.0 * S * E * T, 8.0 * S * E);
-    if (T == 25) binmajor_to_taps_kernel<25><<<grid, 128, 0, ctx->stream>>>(z, part, E, R, C, transpose, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
+    ProfScope prof(ctx, "binmajor_to_taps", 4.0 * S * E * (sep ? 2.0 * Nl : (double)T), 8.0 * S * E);
+    if (sep) {
+      const size_t smem = (size_t)ncols * Nl * sizeof(float2);
+      if (Nk == 5) {
+        AE_TRY(ctx->ensure_dyn_smem((const void*)binmajor_to_taps_sep_kernel<5, 5>, smem));
+        binmajor_to_taps_sep_kernel<5, 5><<<grid, 128, smem, ctx->stream>>>(z, part, E, R, C, transpose, Nx, Ny, ncols, col0, twx, twy);
+      } else if (Nk == 3) {
+        AE_TRY(ctx->ensure_dyn_smem((const void*)binmajor_to_taps_sep_kernel<3, 3>, smem));
+        binmajor_to_taps_sep_kernel<3, 3><<<grid, 128, smem, ctx->stream>>>(z, part, E, R, C, transpose, Nx, Ny, ncols, col0, twx, twy);
+      } else {
+        AE_TRY(ctx->ensure_dyn_smem((const void*)binmajor_to_taps_sep_kernel<7, 7>, smem));
+        binmajor_to_taps_sep_kernel<7, 7><<<grid, 128, smem, ctx->stream>>>(z, part, E, R, C, transpose, Nx, Ny, ncols, col0, twx, twy);
+      }
+    } else if (T == 25) binmajor_to_taps_kernel<25><<<grid, 128, 0, ctx->stream>>>(z, part, E, R, C, transpose, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
     else if (T == 9) binmajor_to_taps_kernel<9><<<grid, 128, 0, ctx->stream>>>(z, part, E, R, C, transpose, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
     else binmajor_to_taps_kernel<49><<<grid, 128, 0, ctx->stream>>>(z, part, E, R, C, transpose, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
   }

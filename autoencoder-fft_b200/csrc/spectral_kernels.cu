@@ -856,38 +856,48 @@ __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* _
                                                                    float* __restrict__ cd, float* __restrict__ fd, int dM, int dD,
                                                                    int tile0) {
   // tile0: first 64-kernel tile of this launch (bin-sharded devices split the rows; the hook adds the results)
+  // The streamed kernels b sit in shared memory padded to T4 float4 per kernel and are read with 16-byte broadcast loads:
+  // with scalar loads the inner loop issued 25 LDS per 77 arithmetic instructions and was bound by the shared-memory
+  // pipe (one wavefront per clock) rather than by the FMA pipes.
+  constexpr int T4 = (T + 3) / 4, TP = 4 * T4;
   const bool isf = blockIdx.y == 1;
   const float* x = isf ? f : c;
   float* xd = isf ? fd : cd;
   const int n2 = isf ? dM : dD;
   const int n = dM * dD;
-  __shared__ float tb[64][T + 1];
+  __shared__ float4 tb[64][T4];
   __shared__ float red[3][64][T + 1];
   const int la = threadIdx.x & 63, grp = threadIdx.x >> 6;
   const int a = (tile0 + blockIdx.x) * 64 + la;
   const bool a_ok = a < n;
   const int a1 = a_ok ? a / n2 : -1, a2 = a_ok ? a - a1 * n2 : -1;
-  float xa[T], swx[T], sw = 0.f;
+  float xa[TP], swx[TP], sw = 0.f;
 #pragma unroll
-  for (int t = 0; t < T; t++) { xa[t] = a_ok ? x[(size_t)a * T + t] : 0.f; swx[t] = 0.f; }
+  for (int t = 0; t < TP; t++) { xa[t] = (a_ok && t < T) ? x[(size_t)a * T + t] : 0.f; swx[t] = 0.f; }
   for (int b0 = 0; b0 < n; b0 += 64) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 64 * T; i += 256) {
-      const int r = i / T, t = i - r * T;
-      tb[r][t] = b0 + r < n ? x[(size_t)(b0 + r) * T + t] : 0.f;
+    for (int i = threadIdx.x; i < 64 * TP; i += 256) {
+      const int r = i / TP, t = i - r * TP;
+      reinterpret_cast<float*>(&tb[r][0])[t] = (b0 + r < n && t < T) ? x[(size_t)(b0 + r) * T + t] : 0.f;
     }
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 2
     for (int j = grp; j < 64; j += 4) {
       const int b = b0 + j;
       const int b1 = b / n2, b2 = b - b1 * n2;
+      float xb[TP];
+#pragma unroll
+      for (int q = 0; q < T4; q++) {
+        const float4 v = tb[j][q];
+        xb[4 * q] = v.x; xb[4 * q + 1] = v.y; xb[4 * q + 2] = v.z; xb[4 * q + 3] = v.w;
+      }
       float d2 = 0.f;
 #pragma unroll
-      for (int t = 0; t < T; t++) { const float e = xa[t] - tb[j][t]; d2 = fmaf(e, e, d2); }
+      for (int t = 0; t < T; t++) { const float e = xa[t] - xb[t]; d2 = fmaf(e, e, d2); }
       const float w = (b < n && b1 != a1 && b2 != a2) ? 1.f / d2 : 0.f;
       sw += w;
 #pragma unroll
-      for (int t = 0; t < T; t++) swx[t] = fmaf(w, tb[j][t], swx[t]);
+      for (int t = 0; t < T; t++) swx[t] = fmaf(w, xb[t], swx[t]);
     }
   }
   // combine the 4 groups (fixed order)
