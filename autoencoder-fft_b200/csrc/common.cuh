@@ -285,6 +285,10 @@ int launch_tc_dc_terms(aefft_ctx* ctx, int B, int dM, int dD, const float* G, co
 
 // ---- fused iteration for pairs with <= 4 input channels (spec_small.cu), bins-fastest spectra
 bool spec_small_eligible(int dD, int dM);
+// forward contraction with the CO x CI weight block of a bin in registers; AEFFT_ERR_UNSUPPORTED when (CI, CO) has no
+// instantiation (W [CO][CI][S], in [B][CI][S], out [B][CO][S])
+int launch_spec_conv_reg(aefft_ctx* ctx, int64_t B, int CI, int CO, int64_t S, const float2* in, const float2* W, const float* bias,
+                         float bias_scale, float in_scale, float2* out);
 int launch_small_grad(aefft_ctx* ctx, int64_t B, int dD, int dM, int64_t S, const float2* X, const float2* Xt, const float2* O,
                       const float2* C, const float2* F, const float* bias_b, const float* bias_p, float norm, float gscale,
                       float dbscale, float2* dC, float2* dF, float* db, float* dp);
@@ -305,6 +309,8 @@ struct FftTrainInputs {
   const float2 *Xs = nullptr, *Os = nullptr;   // device spectra, bins-fastest [B][dD][Nx][Nyr]  (expout = in); under bin
                                                // sharding: this device's column slab [B][dD][Nx][ncols] of ALL frames
   const float *Xbm = nullptr, *Obm = nullptr;  // device spectra, bin-major [bin][B][2 dD]         (expout = in)
+  const float* Hbm = nullptr;                  // optional with Xbm: conv_k(X; c, b) of the CURRENT kernels, bin-major
+                                               // [bin][B][2 dM] (the forward's hidden layer): saves its recomputation
   bool resident = false;      // c,f,b,p are the device-resident masters: no export through the spectra, and no stream
                               // synchronisation unless a host trace is requested
   float* trace_dev = nullptr; // device destination of the mse trace (n_iter + 1 floats), optional

@@ -459,14 +459,20 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
       }
       AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, q.O, Xt, (float2*)Eb));  // E = O - Xt of the caller's `out`
     }
-    AE_TRY(launch_kernel_spectrum_emb(ctx, dM, dD, Nk, Nl, Nx, Ny, col0, ncols, dc_w, Cemb));
     AE_TRY(launch_kernel_spectrum_emb(ctx, dD, dM, Nk, Nl, Nx, Ny, col0, ncols, df_w, Femb));
-    // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1)
-    AE_TRY(launch_tc_forward(ctx, S, (int)B, dD, dM, Xb, Cemb, 1.f / (float)dM, bias_b, norm, nullptr, Hb, nullptr, 0.0, 0, 0, 0));
+    // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1);
+    // the resident net hands over the hidden layer its forward just computed with these very kernels
+    const float* Hcur = inp.Hbm;
+    if (!Hcur) {
+      AE_TRY(launch_kernel_spectrum_emb(ctx, dM, dD, Nk, Nl, Nx, Ny, col0, ncols, dc_w, Cemb));
+      AE_TRY(launch_tc_forward(ctx, S, (int)B, dD, dM, Xb, Cemb, 1.f / (float)dM, bias_b, norm, nullptr, Hb, nullptr, 0.0, 0, 0, 0));
+      Hcur = Hb;
+    }
     for (int n = 0; n < n_iter; n++) {
       AE_TRY(launch_tc_adjoint(ctx, S, (int)B, dD, dM, Eb, Femb, Gb));                               // G = E conj(F)
       AE_TRY(launch_tc_outer(ctx, S, (int)B, dM, dD, Gb, Xb, gscale, 0, dCt));                       // dC[m][d] = G conj(X)
-      AE_TRY(launch_tc_outer(ctx, S, (int)B, dM, dD, Hb, Eb, gscale * (float)dM, 1, dFt));           // dF[d][m] = E conj(dM H) at [m][d]
+      AE_TRY(launch_tc_outer(ctx, S, (int)B, dM, dD, Hcur, Eb, gscale * (float)dM, 1, dFt));         // dF[d][m] = E conj(dM H) at [m][d]
+      Hcur = Hb;  // from now on the re-forward below provides H
       if (own_dc)
         AE_TRY(launch_tc_dc_terms(ctx, (int)B, dM, dD, Gb, Eb, bias_b, dFt, q.db, q.dp, (float)((double)norm / (Norm * (double)B)),
                                   gscale, -(float)(dM - 1) * norm));

@@ -189,7 +189,11 @@ int aefft_net_fft_forward(aefft_net* net, int loc, const float* frames, int fft_
 
 // backprop_fft (:1381-1511) of pair n_l on the spectra the last aefft_net_fft_forward / _step left in HBM
 // (autoencoder.cpp:190-196: in = layers[2n+1], out = layers[size-2-2n], c = net_c[n], f = net_c[N-1-n]).
-static int train_pair_spectra(aefft_net* net, int n, float del0, int maxdiff, int n_iter, float* trace_dev, float* trace_host) {
+// fresh_forward: the hidden-layer spectrum of the last forward was computed with the pair's CURRENT kernels (true inside
+// aefft_net_fft_step, where every pair is trained once right after the forward; a caller of aefft_net_fft_train_pair may
+// train the same pair repeatedly on one forward, so it is recomputed there)
+static int train_pair_spectra(aefft_net* net, int n, float del0, int maxdiff, int n_iter, float* trace_dev, float* trace_host,
+                              bool fresh_forward) {
   aefft_ctx* ctx = net->ctx;
   const int N = (int)net->convs.size();
   AE_ARG((int)net->spec.size() == (int)net->layers.size());  // a forward has planned and filled the spectra
@@ -238,8 +242,10 @@ static int train_pair_spectra(aefft_net* net, int n, float del0, int maxdiff, in
     return backprop_fft_run(ctx, AEFFT_DEVICE, net->B * W, e.dD, e.dM, L.Nx, L.Ny, e.Nk, e.Nl, inp, nullptr, e.c, nullptr, d.c, e.b,
                             d.b, del0, maxdiff, n_iter, trace_host);
   }
-  if (net->spec[li].bin_major) { inp.Xbm = net->spec[li].p; inp.Obm = net->spec[lo].p; }
-  else { inp.Xs = (const float2*)net->spec[li].p; inp.Os = (const float2*)net->spec[lo].p; }
+  if (net->spec[li].bin_major) {
+    inp.Xbm = net->spec[li].p; inp.Obm = net->spec[lo].p;
+    if (fresh_forward) inp.Hbm = net->spec[li + 1].p;  // hin = conv_k(in; c, b) with the kernels as they are now
+  } else { inp.Xs = (const float2*)net->spec[li].p; inp.Os = (const float2*)net->spec[lo].p; }
   return backprop_fft_run(ctx, AEFFT_DEVICE, net->B, e.dD, e.dM, L.Nx, L.Ny, e.Nk, e.Nl, inp, nullptr, e.c, nullptr, d.c, e.b, d.b,
                           del0, maxdiff, n_iter, trace_host);
 }
@@ -247,7 +253,7 @@ static int train_pair_spectra(aefft_net* net, int n, float del0, int maxdiff, in
 int aefft_net_fft_train_pair(aefft_net* net, int n_l, float del0, int maxdiff, int n_iter, float* mse_trace) {
   AE_ARG(net && n_l >= 0 && n_l < (int)net->pairs.size() && n_iter >= 1);
   AE_CUDA(cudaSetDevice(net->ctx->device));
-  return train_pair_spectra(net, n_l, del0, maxdiff, n_iter, nullptr, mse_trace);
+  return train_pair_spectra(net, n_l, del0, maxdiff, n_iter, nullptr, mse_trace, false);
 }
 
 int aefft_net_fft_step(aefft_net* net, int loc, const float* frames, float del0, int maxdiff, int n_iter, int fft_l,
@@ -265,7 +271,7 @@ int aefft_net_fft_step(aefft_net* net, int loc, const float* frames, float del0,
     net->fft_trace_cap = tlen;
   }
   for (int n = 0; n < P; n++)
-    AE_TRY(train_pair_spectra(net, n, del0, maxdiff, n_iter, net->fft_trace + (size_t)n * (n_iter + 1), nullptr));
+    AE_TRY(train_pair_spectra(net, n, del0, maxdiff, n_iter, net->fft_trace + (size_t)n * (n_iter + 1), nullptr, true));
   if (mse) {
     AE_CUDA(cudaMemcpyAsync(mse, net->fft_trace, (size_t)tlen * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     AE_CUDA(cudaStreamSynchronize(ctx->stream));

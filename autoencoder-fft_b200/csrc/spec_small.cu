@@ -258,6 +258,63 @@ int run_mse(aefft_ctx* ctx, const SmallParams& p) {
 
 }  // namespace
 
+// ---- forward contraction (conv_k, :162-189) when CI*CO is small: one thread per bin keeps the whole CO x CI weight block of its
+// bin in registers and walks over a chunk of frames -- every load and store of a warp is one contiguous 256-byte run, the
+// weights are read once per frame chunk.  out[b][o][w] = in_scale * sum_c W[o][c][w] in[b][c][w]  (+ bias[o]*bias_scale at bin 0)
+namespace {
+template <int CI, int CO>
+__global__ void __launch_bounds__(128) conv_reg_kernel(const float2* __restrict__ in, const float2* __restrict__ W,
+                                                       const float* __restrict__ bias, float2* __restrict__ out, long long S, int B,
+                                                       int frames_per_block, float in_scale, float bias_scale) {
+  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= S) return;
+  float2 Wr[CO][CI];
+  float bo[CO];
+#pragma unroll
+  for (int o = 0; o < CO; o++) {
+#pragma unroll
+    for (int c = 0; c < CI; c++) {
+      const float2 v = __ldg(W + ((long long)o * CI + c) * S + w);
+      Wr[o][c] = make_float2(v.x * in_scale, v.y * in_scale);
+    }
+    bo[o] = (w == 0 && bias) ? bias[o] * bias_scale : 0.f;
+  }
+  const int b0 = blockIdx.y * frames_per_block, b1 = min(B, b0 + frames_per_block);
+  for (int b = b0; b < b1; b++) {
+    float2 x[CI];
+#pragma unroll
+    for (int c = 0; c < CI; c++) x[c] = __ldg(in + ((long long)b * CI + c) * S + w);
+#pragma unroll
+    for (int o = 0; o < CO; o++) {
+      float2 acc = make_float2(bo[o], 0.f);
+#pragma unroll
+      for (int c = 0; c < CI; c++) cmac(acc, Wr[o][c], x[c]);
+      out[((long long)b * CO + o) * S + w] = acc;
+    }
+  }
+}
+}  // namespace
+
+int launch_spec_conv_reg(aefft_ctx* ctx, int64_t B, int CI, int CO, int64_t S, const float2* in, const float2* W, const float* bias,
+                         float bias_scale, float in_scale, float2* out) {
+  if (getenv("AEFFT_NO_SPEC_SMALL")) return AEFFT_ERR_UNSUPPORTED;
+  const int fpb = 16;
+  dim3 grid((unsigned)((S + 127) / 128), (unsigned)((B + fpb - 1) / fpb));
+  if (grid.y > 65535) return AEFFT_ERR_UNSUPPORTED;
+#define AEFFT_CONV_REG(ci, co)                                                                                              \
+  if (CI == ci && CO == co) {                                                                                               \
+    ProfScope prof(ctx, "spec_contract_reg", 8.0 * B * CI * CO * S, 8.0 * S * ((double)B * (CI + CO) + (double)CI * CO));   \
+    conv_reg_kernel<ci, co><<<grid, 128, 0, ctx->stream>>>(in, W, bias, out, S, (int)B, fpb, in_scale, bias_scale);         \
+    ctx->launches++;                                                                                                        \
+    AE_CUDA(cudaGetLastError());                                                                                            \
+    return AEFFT_OK;                                                                                                        \
+  }
+  AEFFT_CONV_REG(3, 16) AEFFT_CONV_REG(16, 3) AEFFT_CONV_REG(3, 8) AEFFT_CONV_REG(8, 3) AEFFT_CONV_REG(1, 8) AEFFT_CONV_REG(8, 1)
+  AEFFT_CONV_REG(3, 4) AEFFT_CONV_REG(4, 3) AEFFT_CONV_REG(1, 16) AEFFT_CONV_REG(16, 1)
+#undef AEFFT_CONV_REG
+  return AEFFT_ERR_UNSUPPORTED;
+}
+
 bool spec_small_eligible(int dD, int dM) {
   if (getenv("AEFFT_NO_SPEC_SMALL")) return false;
   const int lg = dM / 4;

@@ -411,6 +411,10 @@ int launch_spec_contract(aefft_ctx* ctx, int64_t B, int C, int O, int64_t S, con
                          const float2* W, int64_t w_so, int64_t w_sc, int conjW, float in_scale, const float* bias,
                          float bias_scale, float2* out) {
   AE_ARG(B > 0 && C > 0 && O > 0 && S > 0);
+  if (!in1 && !conjW && w_so == (int64_t)C * S && w_sc == S) {  // plain conv_k with few channels on one side
+    const int rc = launch_spec_conv_reg(ctx, B, C, O, S, in0, W, bias, bias_scale, in_scale, out);
+    if (rc != AEFFT_ERR_UNSUPPORTED) return rc;
+  }
   ContractParams p{in0, in1, W, bias, out, w_so, w_sc, S, (int)B, C, O, conjW, in_scale, bias_scale};
   if (O >= 8 && B >= 8 && !getenv("AEFFT_NO_SPEC_TILED")) {
     // i = output channel (P = W), j = frame (Q = in), r = input channel

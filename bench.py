@@ -513,18 +513,27 @@ class FftNetWorkload:
         ctx.memcpy(host.data_ptr(), self.l0, self.n0 * 4, 1)
         self.f32 = Staging(torch, dev, host)
         self.h2d_bytes, self.d2h_bytes = self.n0 * 4, 4 * self.P * (self.n_iter + 1)
-        self.has_u8 = False
+        # 8-bit camera frames [B][rows = Ny][cols = Nx][D] (cv::Mat data), converted on the device (ImageToSpin_C)
+        f32 = host.numpy().reshape(B, w["D"], w["Nx"], w["Ny"])
+        host_u8 = torch.from_numpy(np.ascontiguousarray(f32.transpose(0, 3, 2, 1)).astype(np.uint8)).pin_memory()
+        self.u8s = Staging(torch, dev, host_u8)
+        self.u8 = False
+        self.has_u8 = w["D"] <= 4
 
     def step_resident(self):
         self.net.fft_step(None, DELMAX, self.maxdiff, self.n_iter, fft_l=0, loc=self.A.DEVICE, want_mse=False)
 
     def e2e_begin(self):
-        self.f32.begin()
+        (self.u8s if self.u8 else self.f32).begin()
 
     def step_e2e(self):
-        slot, buf = self.f32.acquire()
+        st = self.u8s if self.u8 else self.f32
+        slot, buf = st.acquire()
+        if self.u8:
+            self.net.set_frames_u8(buf.data_ptr(), loc=self.A.DEVICE)
+            buf = None
         self.net.fft_step(buf, DELMAX, self.maxdiff, self.n_iter, fft_l=0, loc=self.A.DEVICE, want_mse=True)  # syncs (mse D2H)
-        self.f32.release(slot)
+        st.release(slot)
 
     def describe_e2e(self):
         return ("pinned host frames -> double-buffered device staging on a copy stream (upload of step k+1 overlaps step k) -> "
