@@ -26,6 +26,12 @@
 // (TMEM -> registers -> global), warps 6-9 splitters.  Unit of the smem ring = one bin x one 32-wide K block
 // (A 16 KB + B NT*128 B, twice for hi/lo); TMEM holds two accumulators so the epilogue of bin i overlaps the MMAs of i+1.
 // Bound: HBM (per bin a 128 x 128 x 64 product is ~0.8 us of tensor time but 128+ KB of traffic).
+// Measured (tools/tc_sweep.py, c3 shapes): 3.9-4.3 TB/s of algorithmic bytes for the forward / adjoint forms and the
+// 64 -> 32 outer product, 2.6 TB/s for the small 32 -> 16 outer product.  Knock-outs (AEFFT_TC_KNOCK): without the global
+// stores the store-heavy forms run at 7.9 TB/s-equivalent (the read stream alone is at the HBM read limit), without the
+// split or the MMAs nothing changes (<10 %); a deeper ring (3 -> 5 stages), an 8-deep accumulator ring with two epilogue
+// groups, 128-byte staged stores and 64-row K units for the outer products were all measured and gave nothing or were
+// slower -- what remains is the mixed read/write stream itself (64 KB in, 64 KB out per bin and SM).
 #include <cstdlib>
 #include <cstring>
 
@@ -61,6 +67,7 @@ struct TcParams {
   int conj_out;          // EPI_OUTER: negate the imaginary parts
   double* sq_part;       // EPI_STORE: per-warp sums of hw(bin) * out^2 ([grid][4]) or nullptr
   int ncols, col0, Ny;   // Hermitian weight of bin w: column col0 + w % ncols in {0, Ny/2} -> 1, else 2
+  int knock;             // development knock-outs (AEFFT_TC_KNOCK bit mask): 1 no global stores, 2 no hi/lo split, 4 no MMAs
 };
 
 __device__ __forceinline__ uint64_t desc_k(uint32_t addr) {  // K-major, SWIZZLE_128B: SBO = 8 rows x 128 B
@@ -156,9 +163,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_tc_kernel(const __grid_con
             const uint64_t ah = p.a_mn ? desc_mn(ao) : desc_k(ao), al = p.a_mn ? desc_mn(ao + a_lo) : desc_k(ao + a_lo);
             const uint64_t bh = p.b_mn ? desc_mn(bo) : desc_k(bo);
             const uint64_t bl = p.b_mn ? desc_mn(bo + (b_lo - b_hi)) : desc_k(bo + (b_lo - b_hi));
-            mma_tf32(d, ah, bh, idesc, acc);
-            mma_tf32(d, ah, bl, idesc, 1);
-            mma_tf32(d, al, bh, idesc, 1);
+            if (!(p.knock & 4)) {
+              mma_tf32(d, ah, bh, idesc, acc);
+              mma_tf32(d, ah, bl, idesc, 1);
+              mma_tf32(d, al, bh, idesc, 1);
+            }
             acc = 1;
           }
           commit(&empty[r.slot]);  // the stage may be refilled once these MMAs have read it
@@ -212,6 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_tc_kernel(const __grid_con
 #pragma unroll
             for (int e = 0; e < 16; e++) part = fmaf(v[e], v[e], part);
           }
+          if (p.knock & 1) continue;
           float4* o4 = reinterpret_cast<float4*>(p.out + base + c0);
 #pragma unroll
           for (int e = 0; e < 4; e++) o4[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
@@ -233,7 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_tc_kernel(const __grid_con
             float r = odd ? pa - pb : pa + pb;
             if (odd && p.conj_out) r = -r;
             const int d = (n0 >> 1) + i;
-            if (m < Mh && d < Nh) p.out[((w * Mh + m) * (long long)Nh + d) * 2 + (odd ? 1 : 0)] = r * p.scale;
+            if (m < Mh && d < Nh && !(p.knock & 1)) p.out[((w * Mh + m) * (long long)Nh + d) * 2 + (odd ? 1 : 0)] = r * p.scale;
           }
         }
       }
@@ -274,10 +284,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_tc_kernel(const __grid_con
           lo[i] = make_float4(x.x - __uint_as_float(u.x), x.y - __uint_as_float(u.y), x.z - __uint_as_float(u.z),
                               x.w - __uint_as_float(u.w));
         };
+        if (!(p.knock & 2)) {
 #pragma unroll 4
-        for (int i = t; i < na4; i += 128) split(ah, al, i);
+          for (int i = t; i < na4; i += 128) split(ah, al, i);
 #pragma unroll 4
-        for (int i = t; i < nb4; i += 128) split(bh, bl, i);
+          for (int i = t; i < nb4; i += 128) split(bh, bl, i);
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) tma::mbar_arrive(&ready[r.slot]);
@@ -618,6 +630,11 @@ int launch_bgemm(aefft_ctx* ctx, const char* name, long long S, const TcOperand&
   p.stage_bytes = 32768u + 2u * (uint32_t)NT * 128u;
   p.stages = (int)((227u * 1024u - 2048u) / p.stage_bytes);
   if (p.stages > TC_MAX_STAGES) p.stages = TC_MAX_STAGES;
+  if (const char* e = getenv("AEFFT_TC_STAGES")) {  // development knobs: cap the ring depth, knock out a role's work
+    const int cap = atoi(e);
+    if (cap >= 2 && cap < p.stages) p.stages = cap;
+  }
+  if (const char* e = getenv("AEFFT_TC_KNOCK")) p.knock = atoi(e);
   AE_ARG(p.stages >= 2);
   p.epi = epi; p.scale = scale; p.bias = bias; p.bias_scale = bias_scale; p.sub = sub; p.out = out; p.conj_out = conj_out;
   p.ncols = ncols > 0 ? ncols : 1; p.col0 = col0; p.Ny = Ny;
