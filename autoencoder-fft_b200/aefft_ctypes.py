@@ -491,6 +491,9 @@ class Net:
         _chk(lib().aefft_net_get_cfreq(self.h, n, _ptr(out), C.c_int64(out.size)))
         return out
 
+    def saveload_momentum(self, directory, n_l, write):
+        _chk(lib().aefft_net_saveload_momentum(self.h, str(directory).encode(), int(n_l), 1 if write else 0))
+
     def fused_layout(self, mode):
         """(offsets per pair, total floats) of the fused raw gradient block a data-parallel step all-reduces once."""
         P = self.num_pairs

@@ -1,7 +1,9 @@
 // Device-resident replay of autoencoder.cpp's state model (:69-120 state, :135-150 forward, :158-201 training
 // dispatch, :384-457 add/delete layer, :343-356 symmetric copy).  The reference keeps layers[], net_c[], net_b[],
 // scale[] as nested host vectors and crosses the PCIe bus twice per conv; here they live in HBM for B frames at once.
+#include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -439,6 +441,54 @@ int aefft_net_step(aefft_net* net, int loc, const float* frames, int mode, int q
     AE_CUDA(cudaMemcpyAsync(mse, net->mse_dev, sizeof(float) * (P < 64 ? P : 64), cudaMemcpyDeviceToHost, ctx->stream));
     AE_CUDA(cudaStreamSynchronize(ctx->stream));
   }
+  return AEFFT_OK;
+}
+
+// Momentum sidecar: the reference's 's' / 'l' keys save the kernels and biases only -- the inertia state
+// dc/db/df/dp and the last gradients ddc/ddb/ddf/ddp (autoencoder.cpp:75-83) are lost, so a reloaded net restarts its
+// momentum from zero.  The sidecar keeps them next to the weight files:
+//   <dir>/C_momentum_{L}_D={dD}_M={dM}_Lk={Lk}_Ll={Ll}.mom = raw little-endian float32
+//   [dc dM*dD*T | db dM | df dD*dM*T | dp dD | ddc | ddb | ddf | ddp]   (T = Nk*Nl; same naming scheme as SaveLoad_conv)
+int aefft_net_saveload_momentum(aefft_net* net, const char* dir, int n_l, int write) {
+  AE_ARG(net && dir && n_l >= 0 && n_l < (int)net->pairs.size());
+  aefft_ctx* ctx = net->ctx;
+  AE_CUDA(cudaSetDevice(ctx->device));
+  const ConvL& e = net->convs[n_l];
+  PairState& st = net->pairs[n_l];
+  const size_t nC = (size_t)e.dM * e.dD * e.Nk * e.Nl;
+  float* parts[8] = {st.dc, st.db, st.df, st.dp, st.ddc, st.ddb, st.ddf, st.ddp};
+  const size_t lens[8] = {nC, (size_t)e.dM, nC, (size_t)e.dD, nC, (size_t)e.dM, nC, (size_t)e.dD};
+  size_t total = 0;
+  for (size_t l : lens) total += l;
+  std::vector<float> host(total + 1);
+  const std::string path = std::string(dir) + "/C_momentum_" + std::to_string(n_l) + "_D=" + std::to_string(e.dD) + "_M=" +
+                           std::to_string(e.dM) + "_Lk=" + std::to_string((e.Nk - 1) / 2 - 1) + "_Ll=" +
+                           std::to_string((e.Nl - 1) / 2 - 1) + ".mom";
+  if (write) {
+    size_t off = 0;
+    for (int i = 0; i < 8; i++) {
+      AE_CUDA(cudaMemcpyAsync(host.data() + off, parts[i], lens[i] * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+      off += lens[i];
+    }
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
+    FILE* fh = fopen(path.c_str(), "wb");
+    if (!fh) { set_error("cannot open %s for writing", path.c_str()); return AEFFT_ERR_IO; }
+    const size_t n = fwrite(host.data(), sizeof(float), total, fh);
+    fclose(fh);
+    if (n != total) { set_error("short write to %s", path.c_str()); return AEFFT_ERR_IO; }
+    return AEFFT_OK;
+  }
+  FILE* fh = fopen(path.c_str(), "rb");
+  if (!fh) { set_error("cannot open %s", path.c_str()); return AEFFT_ERR_IO; }
+  const size_t n = fread(host.data(), sizeof(float), total + 1, fh);  // one past: a longer file is a mismatch too
+  fclose(fh);
+  if (n != total) { set_error("%s: %zu floats, expected %zu", path.c_str(), n, total); return AEFFT_ERR_IO; }
+  size_t off = 0;
+  for (int i = 0; i < 8; i++) {
+    AE_CUDA(cudaMemcpyAsync(parts[i], host.data() + off, lens[i] * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    off += lens[i];
+  }
+  AE_CUDA(cudaStreamSynchronize(ctx->stream));
   return AEFFT_OK;
 }
 

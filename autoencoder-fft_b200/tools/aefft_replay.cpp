@@ -3,7 +3,7 @@
 //
 //   aefft_replay [--frames B] [--size NxxNy] [--channels D] [--seed S] [--param FILE] [--weights DIR]
 //                [--precision fp32|bf16x3|bf16] [--del 0.2] [--alpha 0.9] [--quirks 7] [--fft-iters 100]
-//                [--device K --rank R --world W --id-file PATH]
+//                [--device K --rank R --world W --id-file PATH] [--sidecar]
 //                --script "n n t5 z t3 p t2 s d l t1 i f g t1"
 // --rank/--world/--id-file: data-parallel frames over W processes, one GPU each, WITHOUT any Python: rank 0 writes the
 // NCCL unique id (aefft_comm_unique_id) to PATH, the others read it, every rank calls aefft_comm_init; rank r then
@@ -48,7 +48,7 @@ int main(int argc, char** argv) {
   unsigned seed = 1234;
   float del = 0.2f, alpha = 0.9f;
   std::string param = "New_Layer_Param.txt", weights = "./weights", script, id_file;
-  int device = 0, rank = 0, world = 1, fft_iters = 100;
+  int device = 0, rank = 0, world = 1, fft_iters = 100, sidecar = 0;
   for (int a = 1; a < argc; a++) {
     const std::string k = argv[a];
     const char* v = a + 1 < argc ? argv[a + 1] : "";
@@ -67,6 +67,7 @@ int main(int argc, char** argv) {
     else if (k == "--world") { world = std::atoi(v); a++; }
     else if (k == "--id-file") { id_file = v; a++; }
     else if (k == "--fft-iters") { fft_iters = std::atoi(v); a++; }
+    else if (k == "--sidecar") { sidecar = 1; }
     else if (k == "--precision") {
       precision = !std::strcmp(v, "fp32") ? AEFFT_PRECISION_FP32 : !std::strcmp(v, "bf16") ? AEFFT_PRECISION_BF16 : AEFFT_PRECISION_BF16X3;
       a++;
@@ -171,6 +172,8 @@ int main(int argc, char** argv) {
         CHECK(aefft_saveload_conv(weights.c_str(), c.data(), b.data(), dM, dD, Nk, Nl, sc, n_l, io, write));
         if (!write) CHECK(aefft_net_set_conv(net, n, c.data(), b.data()));
       }
+      // --sidecar: also keep the momentum / last-gradient state the reference drops on save
+      if (sidecar) CHECK(aefft_net_saveload_momentum(net, weights.c_str(), n_l, write));
       std::printf(write ? "Saved convolutional weights\n" : "Loaded convolutional weights\n");
     } else if (t == "i") {
       std::printf("Network structure: %d pair(s), %d layers, active %d, symmetric %d\n", pairs, aefft_net_num_layers(net), n_l, sym);

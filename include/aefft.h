@@ -305,6 +305,11 @@ int aefft_net_fft_train_pair(aefft_net* net, int n_l, float del0, int maxdiff, i
  * The reference keeps this as a host cache that is uploaded (51-136 MB per layer) on every frame. */
 int aefft_net_get_cfreq(aefft_net* net, int n, float* cfreq, int64_t n_floats);
 
+/* Momentum sidecar (the reference's 's'/'l' keys drop this state, autoencoder.cpp:358-383): the inertia and
+ * last-gradient buffers of pair n_l to / from <dir>/C_momentum_{n_l}_D=.._M=.._Lk=.._Ll=...mom, raw float32
+ * [dc | db | df | dp | ddc | ddb | ddf | ddp].  write != 0 saves, 0 loads (AEFFT_ERR_IO on a missing / mismatching file). */
+int aefft_net_saveload_momentum(aefft_net* net, const char* dir, int n_l, int write);
+
 /* Offsets (floats) of every pair's raw gradient block inside the net's fused gradient buffer for `mode`, and its total
  * length: the buffer a data-parallel step all-reduces once (offsets may be NULL). */
 int aefft_net_fused_layout(aefft_net* net, int mode, int64_t* offsets, int64_t* total);

@@ -229,3 +229,55 @@ def test_replay_two_ranks_equal_one_rank_with_twice_the_frames(tmp_path):
     want, r0, r1 = pick(one.stdout), pick(outs[0][0]), pick(outs[1][0])
     assert len(want) == 5 + 5 and r0 == r1          # replicas stay identical without any broadcast
     assert np.allclose(r0, want, rtol=2e-5), (r0, want)
+
+
+def test_momentum_sidecar_makes_a_reload_bit_identical(ctx, tmp_path):
+    """Train 2 steps, save weights + the momentum sidecar, train 2 more steps; a second net that loads both and trains the
+    same 2 steps ends bit-identical -- with the weight files alone (what the reference saves) the momentum restarts from
+    zero and the result differs."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import weights as W
+
+    def fresh():
+        ctypes.CDLL("libc.so.6").srand(3)
+        net = A.Net(ctx, 3, 32, 32, 2)
+        net.add_layer(6, 1, 1, 2, 0.3)
+        return net
+
+    frames = [O.synth_frames(8, 2, 3, 32, 32, b0=2 * k) for k in range(4)]
+    (tmp_path / "w").mkdir()
+    a = fresh()
+    for k in range(2):
+        a.step(frames[k], A.MODE_CUDA_REF)
+    for n, io in ((0, 0), (1, 1)):
+        c, b = a.get_conv(n)
+        A.saveload_conv(tmp_path / "w", c, b, a.conv_dims(n)[4], 0, io, True)
+    a.saveload_momentum(tmp_path / "w", 0, True)
+    for k in range(2, 4):
+        a.step(frames[k], A.MODE_CUDA_REF)
+    want = [a.get_conv(n) for n in range(2)]
+    a.close()
+    mom, meta = W.read_momentum(next((tmp_path / "w").glob("*.mom")))
+    assert meta["dM"] == 6 and mom["dc"].shape == (6, 3, 5, 5) and np.abs(mom["dc"]).max() > 0
+
+    def reload(with_sidecar):
+        net = fresh()
+        for n, io in ((0, 0), (1, 1)):
+            dM, dD, Nk, Nl, sc = net.conv_dims(n)
+            c, b = np.empty((dM, dD, Nk, Nl), np.float32), np.empty(dM, np.float32)
+            A.saveload_conv(tmp_path / "w", c, b, sc, 0, io, False)
+            net.set_conv(n, c, b)
+        if with_sidecar:
+            net.saveload_momentum(tmp_path / "w", 0, False)
+        for k in range(2, 4):
+            net.step(frames[k], A.MODE_CUDA_REF)
+        got = [net.get_conv(n) for n in range(2)]
+        net.close()
+        return got
+
+    got = reload(True)
+    assert all(np.array_equal(g[0], w[0]) and np.array_equal(g[1], w[1]) for g, w in zip(got, want))
+    cold = reload(False)
+    assert not np.array_equal(cold[0][0], want[0][0])

@@ -54,6 +54,30 @@ def write_conv(directory, c, b, scale, L, io):
     return path
 
 
+MOM = re.compile(r"C_momentum_(?P<L>\d+)_D=(?P<dD>\d+)_M=(?P<dM>\d+)_Lk=(?P<Lk>-?\d+)_Ll=(?P<Ll>-?\d+)\.mom$")
+
+
+def read_momentum(path):
+    """The engine's momentum sidecar (aefft_net_saveload_momentum; the reference does not save this state):
+    dict(dc, db, df, dp, ddc, ddb, ddf, ddp) + meta."""
+    m = MOM.search(os.path.basename(str(path)))
+    if not m:
+        raise ValueError(f"not a momentum sidecar name: {path}")
+    meta = {k: int(v) for k, v in m.groupdict().items()}
+    Nk, Nl = 2 * (meta["Lk"] + 1) + 1, 2 * (meta["Ll"] + 1) + 1
+    dM, dD = meta["dM"], meta["dD"]
+    nC = dM * dD * Nk * Nl
+    raw = np.fromfile(str(path), dtype="<f4")
+    if raw.size != 4 * nC + 2 * (dM + dD):
+        raise ValueError(f"{path}: {raw.size} floats, expected {4 * nC + 2 * (dM + dD)}")
+    out, off = {}, 0
+    for name, n, shape in (("dc", nC, (dM, dD, Nk, Nl)), ("db", dM, (dM,)), ("df", nC, (dD, dM, Nk, Nl)), ("dp", dD, (dD,)),
+                           ("ddc", nC, (dM, dD, Nk, Nl)), ("ddb", dM, (dM,)), ("ddf", nC, (dD, dM, Nk, Nl)), ("ddp", dD, (dD,))):
+        out[name] = raw[off:off + n].reshape(shape).copy()
+        off += n
+    return out, meta
+
+
 def main(argv):
     directory = argv[1] if len(argv) > 1 else "./weights"
     names = sorted(n for n in os.listdir(directory) if NAME.search(n))
