@@ -858,7 +858,11 @@ __global__ void gradient_diff_kernel(const float* __restrict__ c, const float* _
 template <int T>
 __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* __restrict__ c, const float* __restrict__ f,
                                                                    float* __restrict__ cd, float* __restrict__ fd, int dM, int dD,
-                                                                   int tile0) {
+                                                                   int tile0, float* __restrict__ part) {
+  // gridDim.z > 1: the streamed kernels b are split into gridDim.z chunks (a bin-sharded device owns few row tiles -- 64 of
+  // 512 at 8 devices -- and one CTA per tile would leave most SMs idle while each CTA walks ALL b); every (tile, chunk) CTA
+  // then writes its partial (sw, swx[T]) to `part` [tensor][chunk][local a][T+1] and gradient_diff_finish_kernel combines
+  // them in chunk order (deterministic).
   // tile0: first 64-kernel tile of this launch (bin-sharded devices split the rows; the hook adds the results)
   // The streamed kernels b sit in shared memory padded to T4 float4 per kernel and are read with 16-byte broadcast loads:
   // with scalar loads the inner loop issued 25 LDS per 77 arithmetic instructions and was bound by the shared-memory
@@ -878,7 +882,9 @@ __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* _
   float xa[TP], swx[TP], sw = 0.f;
 #pragma unroll
   for (int t = 0; t < TP; t++) { xa[t] = (a_ok && t < T) ? x[(size_t)a * T + t] : 0.f; swx[t] = 0.f; }
-  for (int b0 = 0; b0 < n; b0 += 64) {
+  const int nbt = (n + 63) / 64;  // 64-kernel tiles of b
+  const int bt_lo = (int)((long long)nbt * blockIdx.z / gridDim.z), bt_hi = (int)((long long)nbt * (blockIdx.z + 1) / gridDim.z);
+  for (int b0 = bt_lo * 64; b0 < bt_hi * 64; b0 += 64) {
     __syncthreads();
     for (int i = threadIdx.x; i < 64 * TP; i += 256) {
       const int r = i / TP, t = i - r * TP;
@@ -917,9 +923,39 @@ __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* _
       for (int t = 0; t < T; t++) swx[t] += red[g][la][t];
       sw += red[g][la][T];
     }
+    if (gridDim.z == 1) {
 #pragma unroll
-    for (int t = 0; t < T; t++) xd[(size_t)a * T + t] = xa[t] * sw - swx[t];
+      for (int t = 0; t < T; t++) xd[(size_t)a * T + t] = xa[t] * sw - swx[t];
+    } else {
+      float* o = part + ((((size_t)blockIdx.y * gridDim.z + blockIdx.z) * gridDim.x + blockIdx.x) * 64 + la) * (T + 1);
+#pragma unroll
+      for (int t = 0; t < T; t++) o[t] = swx[t];
+      o[T] = sw;
+    }
   }
+}
+template <int T>
+__global__ void gradient_diff_finish_kernel(const float* __restrict__ c, const float* __restrict__ f, float* __restrict__ cd,
+                                            float* __restrict__ fd, const float* __restrict__ part, int n, int tile0, int ntiles,
+                                            int nchunks) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (tensor, local a)
+  if (idx >= 2 * ntiles * 64) return;
+  const int isf = idx / (ntiles * 64), al = idx - isf * ntiles * 64;
+  const int a = tile0 * 64 + al;
+  if (a >= n) return;
+  const float* x = isf ? f : c;
+  float* xd = isf ? fd : cd;
+  float sw = 0.f, swx[T];
+#pragma unroll
+  for (int t = 0; t < T; t++) swx[t] = 0.f;
+  for (int z = 0; z < nchunks; z++) {
+    const float* o = part + ((((size_t)isf * nchunks + z) * ntiles) * 64 + al) * (T + 1);
+#pragma unroll
+    for (int t = 0; t < T; t++) swx[t] += o[t];
+    sw += o[T];
+  }
+#pragma unroll
+  for (int t = 0; t < T; t++) xd[(size_t)a * T + t] = x[(size_t)a * T + t] * sw - swx[t];
 }
 __global__ void gradient_diff_bias_kernel(const float* __restrict__ b, const float* __restrict__ p, float* __restrict__ bd,
                                           float* __restrict__ pd, int dM, int dD) {
@@ -991,10 +1027,28 @@ int launch_gradient_diff(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, const f
     const int tiles = (n + 63) / 64;
     const int t0 = (int)((long long)tiles * rank / world), t1 = (int)((long long)tiles * (rank + 1) / world);
     if (t1 > t0) {
-      dim3 grid(t1 - t0, 2);
-      if (T == 25) gradient_diff_tiled_kernel<25><<<grid, 256, 0, ctx->stream>>>(c, f, cd, fd, dM, dD, t0);
-      else gradient_diff_tiled_kernel<9><<<grid, 256, 0, ctx->stream>>>(c, f, cd, fd, dM, dD, t0);
+      const int nt = t1 - t0;
+      // enough CTAs for ~4 per SM: split the streamed kernels into chunks when this device owns few row tiles
+      int nchunks = (4 * ctx->sm_count + 2 * nt - 1) / (2 * nt);
+      if (nchunks > tiles / 8) nchunks = tiles / 8;  // >= 8 b-tiles (512 kernels) per chunk
+      if (nchunks < 1) nchunks = 1;
+      if (const char* e = getenv("AEFFT_GDIFF_CHUNKS")) {  // tests force the chunked form on small shapes
+        nchunks = atoi(e);
+        if (nchunks > tiles) nchunks = tiles;
+        if (nchunks < 1) nchunks = 1;
+      }
+      float* part = nullptr;
+      if (nchunks > 1) AE_TRY(ctx->getT("gdiff_part", (size_t)2 * nchunks * nt * 64 * (T + 1), &part));
+      dim3 grid(nt, 2, nchunks);
+      if (T == 25) gradient_diff_tiled_kernel<25><<<grid, 256, 0, ctx->stream>>>(c, f, cd, fd, dM, dD, t0, part);
+      else gradient_diff_tiled_kernel<9><<<grid, 256, 0, ctx->stream>>>(c, f, cd, fd, dM, dD, t0, part);
       ctx->launches++;
+      if (nchunks > 1) {
+        const int total = 2 * nt * 64;
+        if (T == 25) gradient_diff_finish_kernel<25><<<(total + 127) / 128, 128, 0, ctx->stream>>>(c, f, cd, fd, part, n, t0, nt, nchunks);
+        else gradient_diff_finish_kernel<9><<<(total + 127) / 128, 128, 0, ctx->stream>>>(c, f, cd, fd, part, n, t0, nt, nchunks);
+        ctx->launches++;
+      }
     }
     if (rank == 0) {
       gradient_diff_bias_kernel<<<(dM + dD + 127) / 128, 128, 0, ctx->stream>>>(b, p, bd, pd, dM, dD);

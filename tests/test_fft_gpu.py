@@ -290,13 +290,21 @@ def test_bin_sharding_two_device_emulation(ctx, dims, maxdiff):
     assert np.isclose(post[0][0] + post[1][0], want_trace[1], rtol=1e-5), (post, want_trace)
 
 
-def test_multiobjective_tiled_kernel_vs_oracle(ctx):
-    """maxdiff=1 with dM*dD >= 256 kernels takes the tiled gradient_diff kernel (fft_backproplib.cu:709-753 semantics)."""
+@pytest.mark.parametrize("chunks", [None, "3"])
+def test_multiobjective_tiled_kernel_vs_oracle(ctx, chunks):
+    """maxdiff=1 with dM*dD >= 256 kernels takes the tiled gradient_diff kernel (fft_backproplib.cu:709-753 semantics);
+    chunks: the form that splits the streamed kernels over several CTAs per row tile (what a bin-sharded device with few
+    row tiles runs), forced here on a small shape."""
     dims = (32, 8, 5, 5, 16, 16)
     cs = fft_case(11, *dims)
     w = {k: cs[k].copy() for k in "cfbp"}
     ctx.profile_enable(True)
-    trace = ctx.backprop_fft(cs["inp"], cs["inp"], cs["out"], w["c"], w["f"], w["b"], w["p"], 0.2, 1, 2)
+    if chunks:
+        os.environ["AEFFT_GDIFF_CHUNKS"] = chunks
+    try:
+        trace = ctx.backprop_fft(cs["inp"], cs["inp"], cs["out"], w["c"], w["f"], w["b"], w["p"], 0.2, 1, 2)
+    finally:
+        os.environ.pop("AEFFT_GDIFF_CHUNKS", None)
     names = [r["name"] for r in ctx.profile_records()]
     ctx.profile_enable(False)
     assert "gradient_diff" in names
