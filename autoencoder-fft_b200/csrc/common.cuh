@@ -233,6 +233,12 @@ int launch_fft_r2c_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const 
                            float2* spec);
 int launch_fft_c2r_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float2* spec, float2* work, float* out, int ch,
                            long long fstride, float scale);
+// transforms fused with the adjacent spectral pooling (AEFFT_ERR_UNSUPPORTED outside the compile-time-length envelope):
+// real [batch][Nx][Ny] -> pooled half spectrum [batch][Nxs][Nys/2+1];  small half spectrum -> real image of its embedding
+int launch_fft_r2c_pooled(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, int Nxs, int Nys, const float* in, float2* tmp,
+                          float2* out);
+int launch_fft_c2r_embedded(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, int Nxs, int Nys, const float2* spec, float2* tmp,
+                            float* out, float scale);
 int launch_spec_resize(aefft_ctx* ctx, int64_t planes, int Nx, int Ny, int Nxs, int Nys, const float2* in, float2* out);
 int launch_spec_contract(aefft_ctx* ctx, int64_t B, int C, int O, int64_t S, const float2* in0, const float2* in1,
                          const float2* W, int64_t w_so, int64_t w_sc, int conjW, float in_scale, const float* bias,

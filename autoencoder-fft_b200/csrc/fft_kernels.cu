@@ -519,9 +519,11 @@ struct ColSeq {   // columns: element n of column c at padi(n)*CT + c; items: c 
   __device__ __forceinline__ int addr(int c, int n) const { return (padi(n) << LOG2CT) + c; }
 };
 
-template <int LOG2N>
+// PRUNE: the caller pools the spectrum right away (spectral pooling keeps the columns k < keep-1 and puts the Nyquist
+// column Ny/2 on column keep-1, resize fft_backproplib.cu:87-157): only those `keep` columns are written, pitch `keep`.
+template <int LOG2N, bool PRUNE = false>
 __global__ void __launch_bounds__(256) fft_rows_r2c_s(const float* __restrict__ in, float2* __restrict__ out, int Nx,
-                                                      const float2* __restrict__ tw, int ch, long long fstride) {
+                                                      const float2* __restrict__ tw, int ch, long long fstride, int keep = 0) {
   using C = SRowCfg<LOG2N>;
   constexpr int Ny = C::N, Nyr = Ny / 2 + 1, SP = C::SP, RP = C::RP, LR0 = Sched<LOG2N>::lr(0);
   extern __shared__ __align__(16) float2 sm[];
@@ -544,6 +546,20 @@ __global__ void __launch_bounds__(256) fft_rows_r2c_s(const float* __restrict__ 
   }
   stockham_middle<-1, LOG2N, C::LOG2RP, 1, LR0, false>(src, tw, rs);
   __syncthreads();
+  if constexpr (PRUNE) {
+    float2* o = out + img * (long long)Nx * keep;
+    for (int idx = threadIdx.x; idx < RP * keep; idx += blockDim.x) {
+      const int r = idx / keep, kk = idx - r * keep;
+      const int k = kk < keep - 1 ? kk : Ny / 2;
+      const int row = 2 * (rp0 + r);
+      if (row >= Nx) break;
+      const float2 z1 = src[rs.addr(r, k)];
+      const float2 z2 = src[rs.addr(r, (Ny - k) & (Ny - 1))];
+      o[(long long)row * keep + kk] = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+      o[(long long)(row + 1) * keep + kk] = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+    }
+    return;
+  }
   float2* o = out + img * (long long)Nx * Nyr;
   // the RP row pairs of the CTA as ONE index space: a half spectrum has 2^k + 1 columns, so a per-row loop would spend a
   // whole extra pass on the Nyquist column of every row
@@ -558,9 +574,12 @@ __global__ void __launch_bounds__(256) fft_rows_r2c_s(const float* __restrict__ 
   }
 }
 
-template <int LOG2N>
+// EMBED: the input is a spectrum that was zero-embedded from a smaller one (spectral up-sampling): only `keep` columns
+// exist (pitch `keep`): k < keep-1, and the Nyquist column Ny/2 at column keep-1; every other column reads as zero.
+template <int LOG2N, bool EMBED = false>
 __global__ void __launch_bounds__(256) fft_rows_c2r_s(const float2* __restrict__ in, float* __restrict__ out, int Nx,
-                                                      const float2* __restrict__ tw, float scale, int ch, long long fstride) {
+                                                      const float2* __restrict__ tw, float scale, int ch, long long fstride,
+                                                      int keep = 0) {
   using C = SRowCfg<LOG2N>;
   constexpr int Ny = C::N, Nyr = Ny / 2 + 1, SP = C::SP, RP = C::RP, LR0 = Sched<LOG2N>::lr(0), NP = C::npass;
   constexpr int LRL = Sched<LOG2N>::lr(NP - 1);
@@ -568,14 +587,20 @@ __global__ void __launch_bounds__(256) fft_rows_c2r_s(const float2* __restrict__
   float2* src = sm;
   const long long img = blockIdx.y;
   const int rp0 = blockIdx.x * RP;
-  const float2* base = in + img * (long long)Nx * Nyr;
+  const int pitch = EMBED ? keep : Nyr;
+  const float2* base = in + img * (long long)Nx * pitch;
   float* obase = out + (img / ch) * fstride + (img % ch) * (long long)Nx * Ny;
   RowSeq rs{SP};
   // Z[n] = A[n] + i B[n] for n <= N/2, conj(A[N-n]) + i conj(B[N-n]) above; imaginary parts of DC / Nyquist ignored
   auto load_z = [&](const float2* ra, bool ok, int n) {
     if (!ok) return make_float2(0.f, 0.f);
     const int m = n <= Ny / 2 ? n : Ny - n;
-    float2 a = __ldg(ra + m), b = __ldg(ra + Nyr + m);
+    int mc = m;
+    if constexpr (EMBED) {
+      if (m == Ny / 2) mc = keep - 1;
+      else if (m >= keep - 1) return make_float2(0.f, 0.f);
+    }
+    float2 a = __ldg(ra + mc), b = __ldg(ra + pitch + mc);
     if (m == 0 || m == Ny / 2) { a.y = 0.f; b.y = 0.f; }
     return n <= Ny / 2 ? make_float2(a.x - b.y, a.y + b.x) : make_float2(a.x + b.y, b.x - a.y);
   };
@@ -588,7 +613,7 @@ __global__ void __launch_bounds__(256) fft_rows_c2r_s(const float2* __restrict__
       const int r = item >> (LOG2N - LR0), j = item & ((1 << (LOG2N - LR0)) - 1);
       const int row = 2 * (rp0 + r);
       const bool ok = row < Nx;
-      const float2* ra = base + (long long)row * Nyr;
+      const float2* ra = base + (long long)row * pitch;
       stockham_item<+1, LOG2N, 0, 0>(j, [&](int n) { return load_z(ra, ok, n); },
                                      [&](int i, float2 v) { if (ok) store_out(row, i, v); }, tw);
     }
@@ -597,7 +622,7 @@ __global__ void __launch_bounds__(256) fft_rows_c2r_s(const float2* __restrict__
       const int r = item >> (LOG2N - LR0), j = item & ((1 << (LOG2N - LR0)) - 1);
       const int row = 2 * (rp0 + r);
       const bool ok = row < Nx;
-      const float2* ra = base + (long long)row * Nyr;
+      const float2* ra = base + (long long)row * pitch;
       float2* d = src;
       stockham_item<+1, LOG2N, 0, 0>(j, [&](int n) { return load_z(ra, ok, n); }, [&](int i, float2 v) { d[rs.addr(r, i)] = v; },
                                      tw);
@@ -624,9 +649,12 @@ struct SColCfg {
   static constexpr size_t smem = (size_t)(N + (N >> 3) + 2) * CT * sizeof(float2);
 };
 
-template <int DIR, int LOG2N>
+// MODE 1 (forward + spectral pooling): only the Nxo rows the crop keeps are stored (i < Nxo/2 -> i, Nx/2 -> Nxo/2,
+// i > Nx - Nxo/2 -> i - (Nx - Nxo)), into an [Nxo][W] image.  MODE 2 (inverse of a zero-embedded spectrum): the input image
+// has Nxo rows, the rows in between read as zero.  MODE 0: plain.
+template <int DIR, int LOG2N, int MODE = 0>
 __global__ void __launch_bounds__(256) fft_cols_s(const float2* __restrict__ in, float2* __restrict__ out, int W,
-                                                  const float2* __restrict__ tw) {
+                                                  const float2* __restrict__ tw, int Nxo = 0) {
   using C = SColCfg<LOG2N>;
   constexpr int Nx = C::N, CT = C::CT, LOG2CT = C::LOG2CT, LR0 = Sched<LOG2N>::lr(0), NP = Sched<LOG2N>::npass;
   constexpr int LRL = Sched<LOG2N>::lr(NP - 1);
@@ -634,16 +662,32 @@ __global__ void __launch_bounds__(256) fft_cols_s(const float2* __restrict__ in,
   float2* src = sm;
   const long long img = blockIdx.y;
   const int c0 = blockIdx.x * CT;
-  const float2* gin = in + img * (long long)Nx * W;
-  float2* gout = out + img * (long long)Nx * W;
+  const float2* gin = in + img * (long long)(MODE == 2 ? Nxo : Nx) * W;
+  float2* gout = out + img * (long long)(MODE == 1 ? Nxo : Nx) * W;
+  // row maps of the spectral pooling (resize :87-157); -1 = dropped / zero
+  auto out_row = [&](int i) {
+    if constexpr (MODE != 1) return i;
+    else return i < Nxo / 2 ? i : (i == Nx / 2 ? Nxo / 2 : (i > Nx - Nxo / 2 ? i - (Nx - Nxo) : -1));
+  };
+  auto in_row = [&](int n) {
+    if constexpr (MODE != 2) return n;
+    else return n < Nxo / 2 ? n : (n == Nx / 2 ? Nxo / 2 : (n > Nx - Nxo / 2 ? n - (Nx - Nxo) : -1));
+  };
+  auto gload = [&](int n, int c, bool ok) {
+    const int r = in_row(n);
+    return (ok && r >= 0) ? __ldg(gin + (long long)r * W + c0 + c) : make_float2(0.f, 0.f);
+  };
+  auto gstore = [&](int i, int c, bool ok, float2 v) {
+    const int r = out_row(i);
+    if (ok && r >= 0) gout[(long long)r * W + c0 + c] = v;
+  };
   ColSeq<LOG2CT> cs;
   if constexpr (NP == 1) {
     for (int item = threadIdx.x; item < (1 << (LOG2N - LR0 + LOG2CT)); item += blockDim.x) {
       const int c = item & (CT - 1), j = item >> LOG2CT;
       const bool ok = c0 + c < W;
       stockham_item<DIR, LOG2N, 0, 0>(
-          j, [&](int n) { return ok ? __ldg(gin + (long long)n * W + c0 + c) : make_float2(0.f, 0.f); },
-          [&](int i, float2 v) { if (ok) gout[(long long)i * W + c0 + c] = v; }, tw);
+          j, [&](int n) { return gload(n, c, ok); }, [&](int i, float2 v) { gstore(i, c, ok, v); }, tw);
     }
   } else {
     for (int item = threadIdx.x; item < (1 << (LOG2N - LR0 + LOG2CT)); item += blockDim.x) {
@@ -651,8 +695,7 @@ __global__ void __launch_bounds__(256) fft_cols_s(const float2* __restrict__ in,
       const bool ok = c0 + c < W;
       float2* d = src;
       stockham_item<DIR, LOG2N, 0, 0>(
-          j, [&](int n) { return ok ? __ldg(gin + (long long)n * W + c0 + c) : make_float2(0.f, 0.f); },
-          [&](int i, float2 v) { d[cs.addr(c, i)] = v; }, tw);
+          j, [&](int n) { return gload(n, c, ok); }, [&](int i, float2 v) { d[cs.addr(c, i)] = v; }, tw);
     }
     stockham_middle<DIR, LOG2N, LOG2CT, 1, LR0, true>(src, tw, cs);
     __syncthreads();
@@ -661,7 +704,7 @@ __global__ void __launch_bounds__(256) fft_cols_s(const float2* __restrict__ in,
       const bool ok = c0 + c < W;
       const float2* s = src;
       stockham_item<DIR, LOG2N, NP - 1, LOG2N - LRL>(j, [&](int n) { return s[cs.addr(c, n)]; },
-                                                     [&](int i, float2 v) { if (ok) gout[(long long)i * W + c0 + c] = v; }, tw);
+                                                     [&](int i, float2 v) { gstore(i, c, ok, v); }, tw);
     }
   }
 }
@@ -826,6 +869,110 @@ int launch_fft_r2c_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const 
     const int rc = cols_fast<-1>(ctx, ilog2(Nx), batch, Nyr, spec, spec, twx);
     if (rc == AEFFT_ERR_UNSUPPORTED) fft_cols_kernel<-1><<<grid, 256, smem, ctx->stream>>>(spec, spec, Nx, Nyr, CT, make_plan(Nx), twx);
     else if (rc != AEFFT_OK) return rc;
+  }
+  ctx->launches += 2;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// ---- transforms fused with the spectral pooling next to them (resize, fft_backproplib.cu:87-157) --------------------------
+// R2C of [batch][Nx][Ny] real images straight into the POOLED half spectrum [batch][Nxs][Nys/2+1] (Nxs <= Nx, Nys <= Ny):
+// the row pass writes only the Nys/2+1 columns the pooling keeps (tmp: batch*Nx*(Nys/2+1) complex), the column pass runs
+// on those columns only and stores only the Nxs kept rows.  Half of the row-pass writes, half of the column pass and the
+// separate resize kernel disappear; the full-resolution spectrum (which nothing else reads) is never formed.
+template <int LY>
+static int rows_r2c_pruned(aefft_ctx* ctx, int64_t batch, int Nx, const float* in, float2* tmp, const float2* tw, int keep) {
+  using S = SRowCfg<LY>;
+  AE_TRY(ctx->ensure_dyn_smem((const void*)fft_rows_r2c_s<LY, true>, S::smem));
+  dim3 grid((Nx / 2 + S::RP - 1) / S::RP, (unsigned)batch);
+  fft_rows_r2c_s<LY, true><<<grid, 256, S::smem, ctx->stream>>>(in, tmp, Nx, tw, 1, (long long)Nx * (1 << LY), keep);
+  return AEFFT_OK;
+}
+template <int DIR, int MODE, int LX>
+static int cols_mode(aefft_ctx* ctx, int64_t batch, int W, const float2* in, float2* out, const float2* tw, int Nxo) {
+  using S = SColCfg<LX>;
+  AE_TRY(ctx->ensure_dyn_smem((const void*)fft_cols_s<DIR, LX, MODE>, S::smem));
+  dim3 grid((W + S::CT - 1) / S::CT, (unsigned)batch);
+  fft_cols_s<DIR, LX, MODE><<<grid, 256, S::smem, ctx->stream>>>(in, out, W, tw, Nxo);
+  return AEFFT_OK;
+}
+template <int LY>
+static int rows_c2r_embed(aefft_ctx* ctx, int64_t batch, int Nx, const float2* tmp, float* out, const float2* tw, float scale,
+                          int keep) {
+  using S = SRowCfg<LY>;
+  AE_TRY(ctx->ensure_dyn_smem((const void*)fft_rows_c2r_s<LY, true>, S::smem));
+  dim3 grid((Nx / 2 + S::RP - 1) / S::RP, (unsigned)batch);
+  fft_rows_c2r_s<LY, true><<<grid, 256, S::smem, ctx->stream>>>(tmp, out, Nx, tw, scale, 1, (long long)Nx * (1 << LY), keep);
+  return AEFFT_OK;
+}
+
+int launch_fft_r2c_pooled(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, int Nxs, int Nys, const float* in, float2* tmp,
+                          float2* out) {
+  AE_ARG(batch > 0 && batch <= 65535 && is_pow2(Nx) && is_pow2(Ny) && is_pow2(Nxs) && is_pow2(Nys));
+  if (getenv("AEFFT_FFT_V1") || getenv("AEFFT_NO_FFT_POOL") || Nxs >= Nx || Nys >= Ny || Nxs < 4 || Nys < 4) return AEFFT_ERR_UNSUPPORTED;
+  const int ly = ilog2(Ny), lx = ilog2(Nx), keep = Nys / 2 + 1;
+  if (ly < 3 || ly > 12 || lx < 3 || lx > 12) return AEFFT_ERR_UNSUPPORTED;
+  const float2 *twx, *twy;
+  AE_TRY(get_twiddles(ctx, Nx, &twx));
+  AE_TRY(get_twiddles(ctx, Ny, &twy));
+  const double px = (double)batch * Nx * Ny, mid = (double)batch * Nx * keep, sp = (double)batch * Nxs * keep;
+  {
+    ProfScope prof(ctx, "fft_rows_r2c", 2.5 * px * log2((double)Ny), 4.0 * px + 8.0 * mid);
+    int rc = AEFFT_ERR_UNSUPPORTED;
+    switch (ly) {
+#define X(L) case L: rc = rows_r2c_pruned<L>(ctx, batch, Nx, in, tmp, twy, keep); break;
+      AEFFT_FOR_LOG2N(X)
+#undef X
+    }
+    AE_TRY(rc);
+  }
+  {
+    ProfScope prof(ctx, "fft_cols", 5.0 * mid * log2((double)Nx), 8.0 * (mid + sp));
+    int rc = AEFFT_ERR_UNSUPPORTED;
+    switch (lx) {
+#define X(L) case L: rc = cols_mode<-1, 1, L>(ctx, batch, keep, tmp, out, twx, Nxs); break;
+      AEFFT_FOR_LOG2N(X)
+#undef X
+    }
+    AE_TRY(rc);
+  }
+  ctx->launches += 2;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// C2R of the zero-EMBEDDED spectrum: spec is the small half spectrum [batch][Nxs][Nys/2+1]; the result is the inverse
+// transform of its embedding into Nx x Ny (spectral up-sampling, no amplitude rescale), scaled by `scale`.
+// tmp: batch*Nx*(Nys/2+1) complex.
+int launch_fft_c2r_embedded(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, int Nxs, int Nys, const float2* spec, float2* tmp,
+                            float* out, float scale) {
+  AE_ARG(batch > 0 && batch <= 65535 && is_pow2(Nx) && is_pow2(Ny) && is_pow2(Nxs) && is_pow2(Nys));
+  if (getenv("AEFFT_FFT_V1") || getenv("AEFFT_NO_FFT_POOL") || Nxs >= Nx || Nys >= Ny || Nxs < 4 || Nys < 4) return AEFFT_ERR_UNSUPPORTED;
+  const int ly = ilog2(Ny), lx = ilog2(Nx), keep = Nys / 2 + 1;
+  if (ly < 3 || ly > 12 || lx < 3 || lx > 12) return AEFFT_ERR_UNSUPPORTED;
+  const float2 *twx, *twy;
+  AE_TRY(get_twiddles(ctx, Nx, &twx));
+  AE_TRY(get_twiddles(ctx, Ny, &twy));
+  const double px = (double)batch * Nx * Ny, mid = (double)batch * Nx * keep, sp = (double)batch * Nxs * keep;
+  {
+    ProfScope prof(ctx, "fft_cols", 5.0 * mid * log2((double)Nx), 8.0 * (mid + sp));
+    int rc = AEFFT_ERR_UNSUPPORTED;
+    switch (lx) {
+#define X(L) case L: rc = cols_mode<+1, 2, L>(ctx, batch, keep, spec, tmp, twx, Nxs); break;
+      AEFFT_FOR_LOG2N(X)
+#undef X
+    }
+    AE_TRY(rc);
+  }
+  {
+    ProfScope prof(ctx, "fft_rows_c2r", 2.5 * px * log2((double)Ny), 4.0 * px + 8.0 * mid);
+    int rc = AEFFT_ERR_UNSUPPORTED;
+    switch (ly) {
+#define X(L) case L: rc = rows_c2r_embed<L>(ctx, batch, Nx, tmp, out, twy, scale, keep); break;
+      AEFFT_FOR_LOG2N(X)
+#undef X
+    }
+    AE_TRY(rc);
   }
   ctx->launches += 2;
   AE_CUDA(cudaGetLastError());

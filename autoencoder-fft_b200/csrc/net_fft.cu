@@ -160,21 +160,62 @@ int forward(aefft_net* net, int loc, const float* frames, int fft_l) {
                             loc == AEFFT_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream));
     if (loc == AEFFT_HOST) AE_CUDA(cudaStreamSynchronize(ctx->stream));
   }
-  AE_TRY(launch_fft_r2c(ctx, net->B * L0.D, L0.Nx, L0.Ny, L0.p, (float2*)net->spec[0].p));  // fft() :764-801
+  // fft() :764-801 + the first pool_fft :1346.  When the first level pools (crop), the transform writes the pooled spectrum
+  // directly: the full-resolution spectrum of the frames is read by nothing else (fft_kernels.cu: launch_fft_r2c_pooled).
+  bool pooled0 = false;
+  {
+    const LayerL& L1 = net->layers[1];
+    if (L1.Nx < L0.Nx && L1.Ny < L0.Ny) {
+      const size_t R = (size_t)net->B * L0.D, S1 = (size_t)L1.Nx * (L1.Ny / 2 + 1);
+      float2 *tmp, *dst = (float2*)net->spec[1].p;
+      AE_TRY(ctx->getT("nf_fft_tmp", R * L0.Nx * (L1.Ny / 2 + 1), &tmp));
+      if (net->spec[1].bin_major) AE_TRY(ctx->getT("nf_ff", R * S1, &dst));
+      const int rc = launch_fft_r2c_pooled(ctx, (int64_t)R, L0.Nx, L0.Ny, L1.Nx, L1.Ny, L0.p, tmp, dst);
+      if (rc == AEFFT_OK) {
+        pooled0 = true;
+        if (net->spec[1].bin_major) AE_TRY(launch_to_binmajor(ctx, (long long)R, (long long)S1, dst, nullptr, (float2*)net->spec[1].p));
+      } else if (rc != AEFFT_ERR_UNSUPPORTED) {
+        return rc;
+      }
+    }
+  }
+  if (!pooled0) AE_TRY(launch_fft_r2c(ctx, net->B * L0.D, L0.Nx, L0.Ny, L0.p, (float2*)net->spec[0].p));
   for (int n = 0; n < N; n++) {
     if (n < N / 2) {
-      AE_TRY(move_spec(net, 2 * n, 2 * n + 1));        // pool_fft :1346
+      if (!(n == 0 && pooled0)) AE_TRY(move_spec(net, 2 * n, 2 * n + 1));        // pool_fft :1346
       if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 1));
       AE_TRY(conv_spec(net, n, 2 * n + 1, 2 * n + 2));  // conv_fft :1356
       if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 2));
     } else {
       AE_TRY(conv_spec(net, n, 2 * n, 2 * n + 1));
       if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 1));
+      if (n == N - 1) {
+        // last up-sampling (pool_fft :1360) + fft_inv (:1373): the reconstruction is the only reader of the embedded
+        // full-resolution spectrum, so the inverse transform takes the small spectrum and embeds on the fly; with
+        // fft_l < 0 nobody wants the reconstruction and neither is done
+        if (fft_l < 0) break;
+        const LayerL &A = net->layers[2 * n + 1], &Z = net->layers[2 * n + 2];
+        if (A.Nx < Z.Nx && A.Ny < Z.Ny) {
+          const size_t R = (size_t)net->B * A.D, Sa = (size_t)A.Nx * (A.Ny / 2 + 1);
+          float2 *tmp, *src = (float2*)net->spec[2 * n + 1].p;
+          AE_TRY(ctx->getT("nf_fft_tmp", R * Z.Nx * (A.Ny / 2 + 1), &tmp));
+          if (net->spec[2 * n + 1].bin_major) {
+            AE_TRY(ctx->getT("nf_ff", R * Sa, &src));
+            AE_TRY(launch_to_binmajor(ctx, (long long)Sa, (long long)R, (const float2*)net->spec[2 * n + 1].p, nullptr, src));
+          }
+          const int rc = launch_fft_c2r_embedded(ctx, (int64_t)R, Z.Nx, Z.Ny, A.Nx, A.Ny, src, tmp, Z.p,
+                                                 1.f / ((float)Z.Nx * (float)Z.Ny));
+          if (rc == AEFFT_OK) break;
+          if (rc != AEFFT_ERR_UNSUPPORTED) return rc;
+        }
+        AE_TRY(move_spec(net, 2 * n + 1, 2 * n + 2));
+        AE_TRY(materialise(net, 2 * n + 2));
+        break;
+      }
       AE_TRY(move_spec(net, 2 * n + 1, 2 * n + 2));     // pool_fft :1360
       if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 2));
     }
   }
-  if (fft_l == 0) AE_TRY(materialise(net, 2 * N));       // fft_inv of the last layer only (:1373)
   return AEFFT_OK;
 }
 

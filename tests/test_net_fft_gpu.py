@@ -120,3 +120,28 @@ def test_net_fft_step_uses_tensor_cores_and_no_layer_transforms(ctx):
         assert rec.get("fft_rows_r2c", 0) == 1 and rec.get("fft_rows_c2r", 0) == 1, rec
     finally:
         net.close()
+
+
+@pytest.mark.parametrize("size,pool", [((1024, 512), 2), ((256, 2048), 4), ((512, 512), 2)])
+def test_net_fft_forward_fused_pooling_at_full_resolution(ctx, size, pool):
+    """The frame transform writes the pooled spectrum directly and the reconstruction's inverse transform embeds on the fly
+    (fft_kernels.cu: launch_fft_r2c_pooled / launch_fft_c2r_embedded) -- at the BASELINE resolutions (long multi-pass
+    transforms), against the reference-shaped path, which transforms at full resolution and pools with the resize kernel."""
+    Nx, Ny = size
+    net, net_c, net_b, scale, shapes = make_net(ctx, 3, Nx, Ny, [4], [pool], 2)
+    try:
+        x = O.synth_frames(21, 2, 3, Nx, Ny)
+        ctx.profile_enable(True)
+        net.fft_forward(x, fft_l=1)
+        ctx.sync()
+        rec = {r["name"]: r["launches"] for r in ctx.profile_records()}
+        ctx.profile_enable(False)
+        assert "spec_resize" not in rec, rec          # both poolings were fused into the transforms
+        got = [net.layer(l) for l in range(net.num_layers)]
+        capi, _ = ctx.autoenc_fft(x, net_c, net_b, scale, shapes, None, 1)
+        for l in range(len(shapes)):
+            assert O.rel_l2(got[l], capi[l]) < 2e-5, l
+        want, _ = O.autoenc_fft(x[0], net_c, net_b, scale, None, 0)
+        assert O.rel_l2(got[-1][0], want[-1]) < 2e-5
+    finally:
+        net.close()
