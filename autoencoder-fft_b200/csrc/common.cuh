@@ -328,9 +328,6 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
 int kernel_spectrum_dev(aefft_ctx* ctx, int64_t n_img, int Nk, int Nl, int Nx, int Ny, const float* taps, float* img, float2* spec,
                         int col0 = 0, int ncols = 0);
 
-// multiobjective term on the tensor cores (spec_tc.cu): xd rows [row0, row0+rows) of sum_b w_ab (x_a - x_b), x [n][T]
-int launch_gradient_diff_tc(aefft_ctx* ctx, const float* x, float* xd, int n, int n2, int T, int row0, int rows);
-
 // ---- collectives inside the engine (comm.cu): NCCL on the ctx stream; op 0 = sum, 1 = average over the ranks
 int comm_allreduce(aefft_ctx* ctx, float* dev, int64_t n_floats, int op);
 // slab exchange of a bin-sharded transform: rank r sends send + r'*chunk floats to every r' and receives into

@@ -47,7 +47,7 @@ using namespace umma;
 
 constexpr int TC_THREADS = 320;
 constexpr int TC_MAX_STAGES = 5;
-enum { EPI_STORE = 0, EPI_OUTER = 1, EPI_GDIFF = 2 };
+enum { EPI_STORE = 0, EPI_OUTER = 1 };
 
 struct TcParams {
   CUtensorMap amap, bmap;
@@ -67,12 +67,6 @@ struct TcParams {
   int conj_out;          // EPI_OUTER: negate the imaginary parts
   double* sq_part;       // EPI_STORE: per-warp sums of hw(bin) * out^2 ([grid][4]) or nullptr
   int ncols, col0, Ny;   // Hermitian weight of bin w: column col0 + w % ncols in {0, Ny/2} -> 1, else 2
-  // EPI_GDIFF (multiobjective term, gradient_diff fft_backproplib.cu:709-753): D = X X^T is the Gram matrix of the kernels;
-  // out[a][b] = w_ab = [a1 != b1 && a2 != b2] / |x_a - x_b|^2 with |x_a - x_b|^2 = na + nb - 2 D (recomputed directly from the
-  // taps when the subtraction would cancel), gd_swpart[nt][a] = sum over the N tile of w_ab
-  const float *gd_norm, *gd_x;  // |x|^2 per kernel [n], padded taps [n][32]
-  float* gd_swpart;
-  int gd_n2, gd_row0, gd_T;
   int knock;             // development knock-outs (AEFFT_TC_KNOCK bit mask): 1 no global stores, 2 no hi/lo split, 4 no MMAs
 };
 
@@ -233,39 +227,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_tc_kernel(const __grid_con
           for (int e = 0; e < 4; e++) o4[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
         }
         sq += (double)(part * hw);
-      } else if (p.epi == EPI_GDIFF) {
-        const int a = p.gd_row0 + row;
-        const bool row_ok = row < p.Mtot;
-        const int a1 = a / p.gd_n2, a2 = a - a1 * p.gd_n2;
-        const float na = row_ok ? __ldg(p.gd_norm + a) : 0.f;
-        float rowsum = 0.f;
-        for (int c0 = 0; c0 < p.NT; c0 += 16) {
-          float v[16];
-          tmem_ld16(taddr + c0, v);
-          const int n0 = nt * p.NT + c0;
-          if (!row_ok || n0 >= p.Ntot) continue;
-#pragma unroll
-          for (int e = 0; e < 16; e++) {
-            const int b = n0 + e;
-            const int b1 = b / p.gd_n2, b2 = b - b1 * p.gd_n2;
-            const float nb = __ldg(p.gd_norm + b);
-            float d2 = na + nb - 2.f * v[e];
-            if (d2 < 0.02f * (na + nb)) {  // near-duplicate kernels: the Gram form cancels, take the differences directly
-              d2 = 0.f;
-              for (int t = 0; t < p.gd_T; t++) {
-                const float df = __ldg(p.gd_x + (size_t)a * 32 + t) - __ldg(p.gd_x + (size_t)b * 32 + t);
-                d2 = fmaf(df, df, d2);
-              }
-            }
-            const float wv = (b1 != a1 && b2 != a2) ? 1.f / d2 : 0.f;
-            v[e] = wv;
-            rowsum += wv;
-          }
-          float4* o4 = reinterpret_cast<float4*>(p.out + (size_t)row * p.Ntot + n0);
-#pragma unroll
-          for (int e = 0; e < 4; e++) o4[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
-        }
-        if (row_ok) p.gd_swpart[(size_t)nt * p.Mtot + row] = rowsum;
       } else {
         // frame-reduced outer product of two interleaved complex operands: lane pair (2m, 2m+1) holds the four real sums
         // of row m; re = D[mr][dr] + D[mi][di], im = D[mi][dr] - D[mr][di]  (conj_out flips im)
@@ -651,13 +612,15 @@ struct TcOperand {
   int mn;          // 0: rows = M/N index, cols = K (K-major); 1: rows = K, cols = M/N index (MN-major)
 };
 
-// `p` carries the epilogue fields (scale, bias, sub, conj_out, ncols / col0 / Ny, gd_*); the geometry is filled here
-int launch_bgemm_ex(aefft_ctx* ctx, const char* name, long long S, const TcOperand& A, const TcOperand& B, int Mtot, int Ntot, int Ktot,
-                    int epi, float* out, TcParams p, double alg_bytes, float* sq_out = nullptr, double sq_scale = 0.0) {
+int launch_bgemm(aefft_ctx* ctx, const char* name, long long S, const TcOperand& A, const TcOperand& B, int Mtot, int Ntot,
+                 int Ktot, int epi, float scale, const float* bias, float bias_scale, const float* sub, float* out, int conj_out,
+                 float* sq_out, double sq_scale, int ncols, int col0, int Ny, double alg_bytes) {
   AE_ARG(S > 0 && S < (1LL << 31) && Mtot > 0 && Ntot > 0 && Ktot > 0 && Ntot % 16 == 0 && (epi != EPI_OUTER || Mtot % 2 == 0));
   AE_ARG((A.mn ? A.cols : A.rows) == Mtot && (A.mn ? A.rows : A.cols) == Ktot);
   AE_ARG((B.mn ? B.cols : B.rows) == Ntot && (B.mn ? B.rows : B.cols) == Ktot);
   AE_ARG(A.cols % 4 == 0 && B.cols % 4 == 0);
+  TcParams p;
+  memset(&p, 0, sizeof(p));
   p.a_mn = A.mn; p.b_mn = B.mn; p.Mtot = Mtot; p.Ntot = Ntot;
   int NT = Ntot <= 256 ? Ntot : 256;
   if (B.mn) NT = (NT + 31) / 32 * 32;
@@ -673,8 +636,8 @@ int launch_bgemm_ex(aefft_ctx* ctx, const char* name, long long S, const TcOpera
   }
   if (const char* e = getenv("AEFFT_TC_KNOCK")) p.knock = atoi(e);
   AE_ARG(p.stages >= 2);
-  p.epi = epi; p.out = out;
-  if (p.ncols <= 0) p.ncols = 1;
+  p.epi = epi; p.scale = scale; p.bias = bias; p.bias_scale = bias_scale; p.sub = sub; p.out = out; p.conj_out = conj_out;
+  p.ncols = ncols > 0 ? ncols : 1; p.col0 = col0; p.Ny = Ny;
   int rc = A.mn ? tma::make_tmap_3d_f32(&p.amap, A.base, A.cols, A.rows, S, 32, 32, 1, 2)
                 : tma::make_tmap_3d_f32(&p.amap, A.base, A.cols, A.rows, S, 32, 128, 1, 1);
   if (rc == 0)
@@ -703,72 +666,7 @@ int launch_bgemm_ex(aefft_ctx* ctx, const char* name, long long S, const TcOpera
   return AEFFT_OK;
 }
 
-int launch_bgemm(aefft_ctx* ctx, const char* name, long long S, const TcOperand& A, const TcOperand& B, int Mtot, int Ntot,
-                 int Ktot, int epi, float scale, const float* bias, float bias_scale, const float* sub, float* out, int conj_out,
-                 float* sq_out, double sq_scale, int ncols, int col0, int Ny, double alg_bytes) {
-  TcParams p;
-  memset(&p, 0, sizeof(p));
-  p.scale = scale; p.bias = bias; p.bias_scale = bias_scale; p.sub = sub; p.conj_out = conj_out;
-  p.ncols = ncols; p.col0 = col0; p.Ny = Ny;
-  return launch_bgemm_ex(ctx, name, S, A, B, Mtot, Ntot, Ktot, epi, out, p, alg_bytes, sq_out, sq_scale);
-}
-
-// ---- multiobjective term on the tensor cores -----------------------------------------------------------------------------
-__global__ void gd_prep_kernel(const float* __restrict__ x, float* __restrict__ xp, float* __restrict__ norm, int n, int T) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= n) return;
-  float s = 0.f;
-  for (int t = 0; t < 32; t++) {
-    const float v = t < T ? x[(size_t)a * T + t] : 0.f;
-    xp[(size_t)a * 32 + t] = v;
-    s = fmaf(v, v, s);
-  }
-  norm[a] = s;
-}
-// xd[a][t] = x[a][t] * (sum of w_ab over b) - (W X)[a][t]
-__global__ void gd_finish_kernel(const float* __restrict__ x, const float* __restrict__ swpart, const float* __restrict__ swx,
-                                 float* __restrict__ xd, int row0, int rows, int n_nt, int T) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * T) return;
-  const int r = idx / T, t = idx - r * T;
-  float sw = 0.f;
-  for (int z = 0; z < n_nt; z++) sw += swpart[(size_t)z * rows + r];
-  xd[(size_t)(row0 + r) * T + t] = x[(size_t)(row0 + r) * T + t] * sw - swx[(size_t)r * 32 + t];
-}
-
 }  // namespace
-
-// xd[a] = sum_b w_ab (x[a] - x[b]) for the rows [row0, row0 + rows) of the n kernels x [n][T] (a = a1 * n2 + a2), as two
-// tensor-core GEMMs: W = f(X X^T) [rows][n] (4 bytes per kernel PAIR in HBM), then W X.  Needs n % 256 == 0, T <= 32.
-int launch_gradient_diff_tc(aefft_ctx* ctx, const float* x, float* xd, int n, int n2, int T, int row0, int rows) {
-  AE_ARG(n % 256 == 0 && T <= 32 && rows > 0 && rows % 2 == 0 && row0 >= 0 && row0 + rows <= n);
-  float *xp, *norm, *W, *swpart, *swx;
-  AE_TRY(ctx->getT("gd_xp", (size_t)n * 32, &xp));
-  AE_TRY(ctx->getT("gd_norm", (size_t)n, &norm));
-  AE_TRY(ctx->getT("gd_W", (size_t)rows * n, &W));
-  AE_TRY(ctx->getT("gd_swpart", (size_t)(n / 256) * rows, &swpart));
-  AE_TRY(ctx->getT("gd_swx", (size_t)rows * 32, &swx));
-  gd_prep_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(x, xp, norm, n, T);
-  ctx->launches++;
-  {
-    TcParams p;
-    memset(&p, 0, sizeof(p));
-    p.gd_norm = norm; p.gd_x = xp; p.gd_swpart = swpart; p.gd_n2 = n2; p.gd_row0 = row0; p.gd_T = T;
-    TcOperand A{xp + (size_t)row0 * 32, rows, 32, 0}, B{xp, n, 32, 0};
-    AE_TRY(launch_bgemm_ex(ctx, "gradient_diff_tc", 1, A, B, rows, n, 32, EPI_GDIFF, W, p, 4.0 * rows * (double)n));
-  }
-  {
-    TcParams p;
-    memset(&p, 0, sizeof(p));
-    p.scale = 1.f;
-    TcOperand A{W, rows, n, 0}, B{xp, n, 32, 1};
-    AE_TRY(launch_bgemm_ex(ctx, "gradient_diff_tc", 1, A, B, rows, 32, n, EPI_STORE, swx, p, 4.0 * rows * (double)n));
-  }
-  gd_finish_kernel<<<(rows * T + 255) / 256, 256, 0, ctx->stream>>>(x, swpart, swx, xd, row0, rows, n / 256, T);
-  ctx->launches++;
-  AE_CUDA(cudaGetLastError());
-  return AEFFT_OK;
-}
 
 // ------------------------------------------------------------------------------------------------ public (engine-internal)
 

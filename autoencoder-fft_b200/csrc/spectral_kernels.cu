@@ -1023,20 +1023,7 @@ int launch_gradient_diff(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, const f
   AE_ARG(T <= 64 && world >= 1);
   ProfScope prof(ctx, "gradient_diff", 2.0 * 75.0 * (double)n * n / world, 8.0 * nC);
   if (world > 1) AE_CUDA(cudaMemsetAsync(div, 0, (size_t)(2 * nC + dM + dD) * sizeof(float), ctx->stream));
-  int tc_min = 2048;  // kernels from which the two-GEMM tensor-core form pays (its W matrix is 4 n^2 bytes of HBM traffic twice)
-  if (const char* e = getenv("AEFFT_GDIFF_TC_MIN")) tc_min = atoi(e);
-  if (n >= tc_min && n % 256 == 0 && T <= 32 && !getenv("AEFFT_NO_GDIFF_TC")) {
-    const int tiles = n / 64;
-    const int t0 = (int)((long long)tiles * rank / world), t1 = (int)((long long)tiles * (rank + 1) / world);
-    if (t1 > t0) {
-      AE_TRY(launch_gradient_diff_tc(ctx, c, cd, n, dD, T, t0 * 64, (t1 - t0) * 64));
-      AE_TRY(launch_gradient_diff_tc(ctx, f, fd, n, dM, T, t0 * 64, (t1 - t0) * 64));
-    }
-    if (rank == 0) {
-      gradient_diff_bias_kernel<<<(dM + dD + 127) / 128, 128, 0, ctx->stream>>>(b, p, bd, pd, dM, dD);
-      ctx->launches++;
-    }
-  } else if (n >= 256 && (T == 25 || T == 9)) {
+  if (n >= 256 && (T == 25 || T == 9)) {
     const int tiles = (n + 63) / 64;
     const int t0 = (int)((long long)tiles * rank / world), t1 = (int)((long long)tiles * (rank + 1) / world);
     if (t1 > t0) {

@@ -290,7 +290,7 @@ def test_bin_sharding_two_device_emulation(ctx, dims, maxdiff):
     assert np.isclose(post[0][0] + post[1][0], want_trace[1], rtol=1e-5), (post, want_trace)
 
 
-@pytest.mark.parametrize("chunks", [None, "3", "tc"])
+@pytest.mark.parametrize("chunks", [None, "3"])
 def test_multiobjective_tiled_kernel_vs_oracle(ctx, chunks):
     """maxdiff=1 with dM*dD >= 256 kernels takes the tiled gradient_diff kernel (fft_backproplib.cu:709-753 semantics);
     chunks: the form that splits the streamed kernels over several CTAs per row tile (what a bin-sharded device with few
@@ -299,18 +299,15 @@ def test_multiobjective_tiled_kernel_vs_oracle(ctx, chunks):
     cs = fft_case(11, *dims)
     w = {k: cs[k].copy() for k in "cfbp"}
     ctx.profile_enable(True)
-    if chunks == "tc":  # the two-GEMM tensor-core form (Gram matrix -> weights -> W X), forced on this small shape
-        os.environ["AEFFT_GDIFF_TC_MIN"] = "256"
-    elif chunks:
+    if chunks:
         os.environ["AEFFT_GDIFF_CHUNKS"] = chunks
     try:
         trace = ctx.backprop_fft(cs["inp"], cs["inp"], cs["out"], w["c"], w["f"], w["b"], w["p"], 0.2, 1, 2)
     finally:
         os.environ.pop("AEFFT_GDIFF_CHUNKS", None)
-        os.environ.pop("AEFFT_GDIFF_TC_MIN", None)
     names = [r["name"] for r in ctx.profile_records()]
     ctx.profile_enable(False)
-    assert ("gradient_diff_tc" if chunks == "tc" else "gradient_diff") in names
+    assert "gradient_diff" in names
     want = O.backprop_fft(cs["inp"], cs["inp"], cs["out"], cs["c"], cs["f"], cs["b"], cs["p"], 0.2, 1, 2)
     assert np.allclose(trace, want["mse"], rtol=2e-4), (trace, want["mse"])
     for k in "cfbp":
@@ -440,33 +437,3 @@ def test_backprop_fft_fused_small_channel_path(ctx, dims, B, maxdiff):
         assert O.rel_l2(runs["fused"][0][k], want[k]) < 1e-4, k
         assert O.rel_l2(runs["fused"][0][k], runs["generic"][0][k]) < 2e-5, k
         assert O.rel_l2(runs["fused"][0][k].astype(np.float64) - cs[k], want[k] - cs[k]) < 2e-3, k
-
-
-@pytest.mark.parametrize("near_duplicate", [False, True])
-def test_multiobjective_tensor_core_form_vs_cuda_cores(ctx, near_duplicate):
-    """2048 kernels (64 x 32): the multiobjective term runs as two tcgen05 GEMMs (W = f(X X^T), then W X).  Against the
-    all-pairs CUDA-core kernel on the same inputs; with two nearly identical kernels the Gram form would cancel
-    (|x_a - x_b|^2 = na + nb - 2 x_a.x_b) and the epilogue falls back to direct differences for that pair."""
-    dims = (64, 32, 5, 5, 16, 16)
-    cs = fft_case(71, *dims, B=2, wscale=0.1)
-    if near_duplicate:
-        cs["c"][5, 7] = cs["c"][2, 3] * (1 + 1e-3)
-        cs["f"][7, 5] = cs["f"][3, 2] * (1 - 2e-3)
-    runs = {}
-    for tag in ("tc", "cc"):
-        if tag == "cc":
-            os.environ["AEFFT_NO_GDIFF_TC"] = "1"
-        try:
-            w = {k: cs[k].copy() for k in "cfbp"}
-            ctx.profile_enable(True)
-            trace = ctx.backprop_fft(cs["inp"], cs["inp"], cs["out"], w["c"], w["f"], w["b"], w["p"], 0.2, 1, 2)
-            names = _names(ctx)
-            ctx.profile_enable(False)
-        finally:
-            os.environ.pop("AEFFT_NO_GDIFF_TC", None)
-        runs[tag] = (w, trace, names)
-    assert "gradient_diff_tc" in runs["tc"][2] and "gradient_diff_tc" not in runs["cc"][2]
-    for k in "cfbp":
-        assert O.rel_l2(runs["tc"][0][k], runs["cc"][0][k]) < 2e-5, k
-        assert O.rel_l2(runs["tc"][0][k].astype(np.float64) - cs[k], runs["cc"][0][k].astype(np.float64) - cs[k]) < 2e-3, k
-    assert np.allclose(runs["tc"][1], runs["cc"][1], rtol=1e-4)
