@@ -879,10 +879,9 @@ __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* _
   const int a = (tile0 + blockIdx.x) * 64 + la;
   const bool a_ok = a < n;
   const int a1 = a_ok ? a / n2 : -1, a2 = a_ok ? a - a1 * n2 : -1;
-  static_assert(TP > T, "the padded slot T of a shared-memory row carries |x_b|^2");
-  float xa[TP], swx[TP], sw = 0.f, na = 0.f;
+  float xa[TP], swx[TP], sw = 0.f;
 #pragma unroll
-  for (int t = 0; t < TP; t++) { xa[t] = (a_ok && t < T) ? x[(size_t)a * T + t] : 0.f; swx[t] = 0.f; na = fmaf(xa[t], xa[t], na); }
+  for (int t = 0; t < TP; t++) { xa[t] = (a_ok && t < T) ? x[(size_t)a * T + t] : 0.f; swx[t] = 0.f; }
   const int nbt = (n + 63) / 64;  // 64-kernel tiles of b
   const int bt_lo = (int)((long long)nbt * blockIdx.z / gridDim.z), bt_hi = (int)((long long)nbt * (blockIdx.z + 1) / gridDim.z);
   for (int b0 = bt_lo * 64; b0 < bt_hi * 64; b0 += 64) {
@@ -890,14 +889,6 @@ __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* _
     for (int i = threadIdx.x; i < 64 * TP; i += 256) {
       const int r = i / TP, t = i - r * TP;
       reinterpret_cast<float*>(&tb[r][0])[t] = (b0 + r < n && t < T) ? x[(size_t)(b0 + r) * T + t] : 0.f;
-    }
-    __syncthreads();
-    if (threadIdx.x < 64) {  // |x_b|^2 into the padded slot of the row
-      float* row = reinterpret_cast<float*>(&tb[threadIdx.x][0]);
-      float nb = 0.f;
-#pragma unroll
-      for (int t = 0; t < T; t++) nb = fmaf(row[t], row[t], nb);
-      row[T] = nb;
     }
     __syncthreads();
 #pragma unroll 2
@@ -910,18 +901,9 @@ __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* _
         const float4 v = tb[j][q];
         xb[4 * q] = v.x; xb[4 * q + 1] = v.y; xb[4 * q + 2] = v.z; xb[4 * q + 3] = v.w;
       }
-      // |x_a - x_b|^2 = |x_a|^2 + |x_b|^2 - 2 x_a.x_b: T multiply-adds instead of T subtractions + T multiply-adds; for
-      // near-duplicate kernels the three terms cancel, there the differences are taken directly
-      float dot = 0.f;
+      float d2 = 0.f;
 #pragma unroll
-      for (int t = 0; t < T; t++) dot = fmaf(xa[t], xb[t], dot);
-      const float nab = na + xb[T];
-      float d2 = fmaf(-2.f, dot, nab);
-      if (d2 < 0.02f * nab) {
-        d2 = 0.f;
-#pragma unroll
-        for (int t = 0; t < T; t++) { const float e = xa[t] - xb[t]; d2 = fmaf(e, e, d2); }
-      }
+      for (int t = 0; t < T; t++) { const float e = xa[t] - xb[t]; d2 = fmaf(e, e, d2); }
       const float w = (b < n && b1 != a1 && b2 != a2) ? 1.f / d2 : 0.f;
       sw += w;
 #pragma unroll

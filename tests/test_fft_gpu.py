@@ -297,8 +297,8 @@ def test_multiobjective_tiled_kernel_vs_oracle(ctx, chunks):
     row tiles runs), forced here on a small shape."""
     dims = (32, 8, 5, 5, 16, 16)
     cs = fft_case(11, *dims)
-    # two nearly identical kernels: the |x_a|^2 + |x_b|^2 - 2 x_a.x_b form of the distance cancels there and the kernel
-    # must fall back to direct differences (the reference sums (c - c')/|c - c'|^2 directly, :722-741)
+    # two nearly identical kernels stress the x_a * sum(w) - sum(w x_b) form of the tiled kernel (the reference sums
+    # (c - c')/|c - c'|^2 directly, :722-741); a norms-and-dot-product form of the distance was measured slower and dropped
     cs["c"][5, 7] = cs["c"][2, 3] * (1 + 1e-2)
     cs["f"][7, 5] = cs["f"][3, 2] * (1 - 2e-2)
     w = {k: cs[k].copy() for k in "cfbp"}
