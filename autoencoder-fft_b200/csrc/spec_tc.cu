@@ -23,7 +23,7 @@
 // rewrite the TMA-landed tile in place (hi) and into a twin buffer (lo) without caring about the swizzle.
 //
 // Kernel: persistent, one CTA per SM, warp specialised: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue
-// (TMEM -> registers -> global), warps 6-9 splitters.  Unit of the smem ring = one bin x one 32-wide K block
+// (TMEM -> registers -> global), warps 6-13 splitters.  Unit of the smem ring = one bin x one 32-wide K block
 // (A 16 KB + B NT*128 B, twice for hi/lo); TMEM holds two accumulators so the epilogue of bin i overlaps the MMAs of i+1.
 // Bound: HBM (per bin a 128 x 128 x 64 product is ~0.8 us of tensor time but 128+ KB of traffic).
 // Measured (tools/tc_sweep.py, c3 shapes): 3.9-4.3 TB/s of algorithmic bytes for the forward / adjoint forms and the
@@ -45,7 +45,8 @@ namespace {
 
 using namespace umma;
 
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;  // warp 0 TMA, 1 MMA, 2-5 epilogue, 6-13 splitters
+constexpr int TC_SPLIT_WARPS = 8;
 constexpr int TC_MAX_STAGES = 5;
 enum { EPI_STORE = 0, EPI_OUTER = 1 };
 
@@ -90,7 +91,9 @@ __device__ __forceinline__ void mma_tf32(uint32_t d, uint64_t a, uint64_t b, uin
 
 __global__ void __launch_bounds__(TC_THREADS, 1) spec_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by OFFSET from the shared array (a round trip through an integer makes the pointer generic and the
+  // splitters' loads / stores become LD.E / ST.E: ncu showed a third of all stall samples on those loads)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full[TC_MAX_STAGES], ready[TC_MAX_STAGES], empty[TC_MAX_STAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_tc_kernel(const __grid_con
   while ((int)tcols < 2 * p.NT) tcols <<= 1;
   if (warp == 0) tmem_alloc(&tmem_slot, tcols);
   if (tid == 32) {
-    for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], TC_SPLIT_WARPS); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
     fence_mbar_init();
   }
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_tc_kernel(const __grid_con
     }
   } else {
     // ------------------------------------------------------------------------------------------ splitters
-    const int t = tid - 6 * 32;  // 0..127
+    const int t = tid - 6 * 32;  // 0..255
     Ring r(p.stages);
     const int nb4 = p.NT * 8;    // float4 per B panel
     for (long long item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -286,9 +289,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_tc_kernel(const __grid_con
         };
         if (!(p.knock & 2)) {
 #pragma unroll 4
-          for (int i = t; i < na4; i += 128) split(ah, al, i);
+          for (int i = t; i < na4; i += 32 * TC_SPLIT_WARPS) split(ah, al, i);
 #pragma unroll 4
-          for (int i = t; i < nb4; i += 128) split(bh, bl, i);
+          for (int i = t; i < nb4; i += 32 * TC_SPLIT_WARPS) split(bh, bl, i);
         }
         fence_proxy_async();
         __syncwarp();
