@@ -868,12 +868,15 @@ __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* _
   // with scalar loads the inner loop issued 25 LDS per 77 arithmetic instructions and was bound by the shared-memory
   // pipe (one wavefront per clock) rather than by the FMA pipes.
   constexpr int T4 = (T + 3) / 4, TP = 4 * T4;
+  static_assert(TP - T == 3, "the padding of a staged kernel carries its (b1, b2) indices and the valid flag");
   const bool isf = blockIdx.y == 1;
   const float* x = isf ? f : c;
   float* xd = isf ? fd : cd;
   const int n2 = isf ? dM : dD;
   const int n = dM * dD;
-  __shared__ float4 tb[64][T4];
+  // Two tile buffers: tile k+1 is fetched with cp.async while tile k is consumed (one barrier per tile).  Slots T, T+1, T+2
+  // of a staged kernel hold b1, b2 (so the inner loop has no integer division) and 1.0 / 0.0 for rows inside / beyond n.
+  __shared__ float4 tb[2][64][T4];
   __shared__ float red[3][64][T + 1];
   const int la = threadIdx.x & 63, grp = threadIdx.x >> 6;
   const int a = (tile0 + blockIdx.x) * 64 + la;
@@ -884,27 +887,55 @@ __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* _
   for (int t = 0; t < TP; t++) { xa[t] = (a_ok && t < T) ? x[(size_t)a * T + t] : 0.f; swx[t] = 0.f; }
   const int nbt = (n + 63) / 64;  // 64-kernel tiles of b
   const int bt_lo = (int)((long long)nbt * blockIdx.z / gridDim.z), bt_hi = (int)((long long)nbt * (blockIdx.z + 1) / gridDim.z);
-  for (int b0 = bt_lo * 64; b0 < bt_hi * 64; b0 += 64) {
-    __syncthreads();
+  auto stage = [&](int bt, int buf) {
+    const int b0 = bt * 64;
+    float* dst = reinterpret_cast<float*>(&tb[buf][0][0]);
     for (int i = threadIdx.x; i < 64 * TP; i += 256) {
-      const int r = i / TP, t = i - r * TP;
-      reinterpret_cast<float*>(&tb[r][0])[t] = (b0 + r < n && t < T) ? x[(size_t)(b0 + r) * T + t] : 0.f;
+      const int r = i / TP, t = i - r * TP, b = b0 + r;
+      if (t < T) {
+        if (b < n) {
+          const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + i);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(x + (size_t)b * T + t) : "memory");
+        } else {
+          dst[i] = 0.f;
+        }
+      }
     }
-    __syncthreads();
+    if (threadIdx.x < 64) {  // one division per staged kernel, by two warps, instead of one per pair in the inner loop
+      const int b = b0 + threadIdx.x, b1 = b / n2;
+      float* row = dst + threadIdx.x * TP;
+      row[T] = __int_as_float(b1);
+      row[T + 1] = __int_as_float(b - b1 * n2);
+      row[T + 2] = b < n ? 1.f : 0.f;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (bt_lo < bt_hi) stage(bt_lo, 0);
+  for (int bt = bt_lo; bt < bt_hi; bt++) {
+    const int buf = (bt - bt_lo) & 1;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // tile bt has landed for every thread, and every thread is done with the other buffer
+    if (bt + 1 < bt_hi) stage(bt + 1, buf ^ 1);
 #pragma unroll 2
     for (int j = grp; j < 64; j += 4) {
-      const int b = b0 + j;
-      const int b1 = b / n2, b2 = b - b1 * n2;
       float xb[TP];
 #pragma unroll
       for (int q = 0; q < T4; q++) {
-        const float4 v = tb[j][q];
+        const float4 v = tb[buf][j][q];
         xb[4 * q] = v.x; xb[4 * q + 1] = v.y; xb[4 * q + 2] = v.z; xb[4 * q + 3] = v.w;
       }
-      float d2 = 0.f;
+      float d2a = 0.f, d2b = 0.f;  // two chains: the 25 dependent FMAs of one were latency, not issue
 #pragma unroll
-      for (int t = 0; t < T; t++) { const float e = xa[t] - xb[t]; d2 = fmaf(e, e, d2); }
-      const float w = (b < n && b1 != a1 && b2 != a2) ? 1.f / d2 : 0.f;
+      for (int t = 0; t < T; t++) {
+        const float e = xa[t] - xb[t];
+        if (t & 1) d2b = fmaf(e, e, d2b);
+        else d2a = fmaf(e, e, d2a);
+      }
+      const float d2 = d2a + d2b;
+      float r;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2));
+      const bool on = (__float_as_int(xb[T]) != a1) & (__float_as_int(xb[T + 1]) != a2) & (xb[T + 2] != 0.f);
+      const float w = on ? r : 0.f;
       sw += w;
 #pragma unroll
       for (int t = 0; t < T; t++) swx[t] = fmaf(w, xb[t], swx[t]);
