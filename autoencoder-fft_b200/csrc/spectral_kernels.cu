@@ -849,16 +849,52 @@ __global__ void gradient_diff_kernel(const float* __restrict__ c, const float* _
 }
 
 
+// Staging copy of c and f for the tiled kernel below: [tensor][npad][TP] with a kernel's T taps followed by its indices
+// (b1, b2) and |x|^2 -- TP = T + 3 floats = whole 16-byte units, so a 64-kernel tile is one contiguous block that
+// cp.async moves 16 bytes at a time.  Rows beyond n: zero taps, |x|^2 = +inf (distance inf, weight 0).
+template <int T>
+__global__ void gradient_diff_pack_kernel(const float* __restrict__ c, const float* __restrict__ f, float* __restrict__ xp,
+                                          int dM, int dD, int npad) {
+  constexpr int TP = T + 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * npad) return;
+  const int isf = i >= npad, b = isf ? i - npad : i, n = dM * dD, n2 = isf ? dM : dD;
+  float* o = xp + (size_t)i * TP;
+  if (b < n) {
+    const float* x = (isf ? f : c) + (size_t)b * T;
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < T; t++) { const float v = x[t]; o[t] = v; s = fmaf(v, v, s); }
+    const int b1 = b / n2;
+    o[T] = __int_as_float(b1);
+    o[T + 1] = __int_as_float(b - b1 * n2);
+    o[T + 2] = s;
+  } else {
+#pragma unroll
+    for (int t = 0; t < T + 2; t++) o[t] = 0.f;
+    o[T + 2] = __int_as_float(0x7f800000);
+  }
+}
+
 // Tiled form of the same sums (the one-CTA-per-kernel version above is O((dM dD)^2) with 25 active threads: 400 ms per call
 // at 128 -> 256 channels).  X is [n1][n2][T]; kernel a = (a1, a2) interacts with b = (b1, b2) iff a1 != b1 and a2 != b2:
 //   xd[a][t] = sum_b w_ab (x[a][t] - x[b][t]) = x[a][t] * sum_b w_ab - sum_b w_ab x[b][t],  w_ab = 1 / |x[a] - x[b]|^2
 // A CTA owns 64 kernels a (one per thread, its taps in registers) and streams all b through shared memory in tiles of
-// 64; the 4 thread groups of a CTA take every fourth b of a tile and are combined at the end.  Distances are computed
-// directly (no Gram-matrix cancellation).  grid.y selects the tensor (c or f).
+// 64 (cp.async, double buffered, from the packed staging copy); the 4 thread groups of a CTA take every fourth b of a
+// tile and are combined at the end.  grid.y selects the tensor (c or f).
+// Measured at 128 -> 256 channels (32 768 kernels per tensor, tools/gdiff_probe.py), per launch: 14.5 ms with an integer
+// division and a full-precision 1/x per pair in the loop; 8.3 ms with the indices staged next to the taps, prefetched
+// tiles and rcp.approx; 7.7 ms with packed FADD2 / FFMA2 (the packed forms halve the issue slots, not the FMA-pipe time:
+// tools/probe_ffma2.cu measures 128 fp32 lanes per clock per SM either way); 7.3 ms with dot-product distances; 6.1 ms with
+// 16-byte tile copies and four accumulators for the dot product.  Interleaving two pairs by hand, a branch-free loop
+// and three CTAs per SM (80 registers, spills: 9.8 ms) gave nothing more: the loop runs ~52 instructions per pair at 0.54
+// issues per scheduler-clock with 4 warps per scheduler.
 template <int T>
 __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* __restrict__ c, const float* __restrict__ f,
                                                                    float* __restrict__ cd, float* __restrict__ fd, int dM, int dD,
-                                                                   int tile0, float* __restrict__ part) {
+                                                                   int tile0, float* __restrict__ part,
+                                                                   const float* __restrict__ xp) {
+  // xp: the staging copy [tensor][npad][TP] (gradient_diff_pack_kernel)
   // gridDim.z > 1: the streamed kernels b are split into gridDim.z chunks (a bin-sharded device owns few row tiles -- 64 of
   // 512 at 8 devices -- and one CTA per tile would leave most SMs idle while each CTA walks ALL b); every (tile, chunk) CTA
   // then writes its partial (sw, swx[T]) to `part` [tensor][chunk][local a][T+1] and gradient_diff_finish_kernel combines
@@ -882,31 +918,31 @@ __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* _
   const int a = (tile0 + blockIdx.x) * 64 + la;
   const bool a_ok = a < n;
   const int a1 = a_ok ? a / n2 : -1, a2 = a_ok ? a - a1 * n2 : -1;
-  float xa[TP], swx[TP], sw = 0.f;
+  // Taps live in registers as packed pairs (FADD2 / FFMA2, sm_100).  T is odd: TH pairs + the last tap as a scalar (its
+  // pair partner in the staged tile is the b1 index).
+  // Distances: |a - b|^2 = |a|^2 + |b|^2 - 2 a.b costs one packed FMA per tap pair instead of an add and an FMA (the loop is
+  // bound by the FMA pipe); where that form cancels (kernels closer than 10 % of their norm: relative error of d^2 above
+  // 6e-8 / 0.01) the differences are summed directly, which is what the reference does (:722-741).
+  constexpr int TH = T / 2;
+  static_assert(T % 2 == 1 && TH >= 4, "odd tap count, at least four tap pairs");
+  float2 xa2[TH], swx2[TH];
+  float xa_l, swx_l = 0.f, sw = 0.f, na = 0.f;
 #pragma unroll
-  for (int t = 0; t < TP; t++) { xa[t] = (a_ok && t < T) ? x[(size_t)a * T + t] : 0.f; swx[t] = 0.f; }
+  for (int t = 0; t < TH; t++) {
+    xa2[t] = a_ok ? make_float2(x[(size_t)a * T + 2 * t], x[(size_t)a * T + 2 * t + 1]) : make_float2(0.f, 0.f);
+    swx2[t] = make_float2(0.f, 0.f);
+    na = fmaf(xa2[t].x, xa2[t].x, fmaf(xa2[t].y, xa2[t].y, na));
+  }
+  xa_l = a_ok ? x[(size_t)a * T + T - 1] : 0.f;
+  na = fmaf(xa_l, xa_l, na);
   const int nbt = (n + 63) / 64;  // 64-kernel tiles of b
   const int bt_lo = (int)((long long)nbt * blockIdx.z / gridDim.z), bt_hi = (int)((long long)nbt * (blockIdx.z + 1) / gridDim.z);
+  const float4* xp4 = reinterpret_cast<const float4*>(xp) + (size_t)blockIdx.y * nbt * 64 * T4;
   auto stage = [&](int bt, int buf) {
-    const int b0 = bt * 64;
-    float* dst = reinterpret_cast<float*>(&tb[buf][0][0]);
-    for (int i = threadIdx.x; i < 64 * TP; i += 256) {
-      const int r = i / TP, t = i - r * TP, b = b0 + r;
-      if (t < T) {
-        if (b < n) {
-          const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst + i);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(x + (size_t)b * T + t) : "memory");
-        } else {
-          dst[i] = 0.f;
-        }
-      }
-    }
-    if (threadIdx.x < 64) {  // one division per staged kernel, by two warps, instead of one per pair in the inner loop
-      const int b = b0 + threadIdx.x, b1 = b / n2;
-      float* row = dst + threadIdx.x * TP;
-      row[T] = __int_as_float(b1);
-      row[T + 1] = __int_as_float(b - b1 * n2);
-      row[T + 2] = b < n ? 1.f : 0.f;
+    const float4* src = xp4 + (size_t)bt * 64 * T4;
+    for (int i = threadIdx.x; i < 64 * T4; i += 256) {
+      const uint32_t d = (uint32_t)__cvta_generic_to_shared(&tb[buf][0][0] + i);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + i) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -916,31 +952,87 @@ __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* _
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();  // tile bt has landed for every thread, and every thread is done with the other buffer
     if (bt + 1 < bt_hi) stage(bt + 1, buf ^ 1);
-#pragma unroll 2
-    for (int j = grp; j < 64; j += 4) {
-      float xb[TP];
+    // Two streamed kernels per iteration, written stage by stage so that the two dependency chains (loads -> dot product ->
+    // reciprocal -> accumulation) interleave in program order: a warp issues in order and with 16 warps per SM one chain
+    // per warp left the schedulers without an eligible warp half of the time.  No branch in the loop: a pair whose
+    // dot-product distance cancels (d^2 < 1 % of |a|^2 + |b|^2) gets weight 0 here and is noted in `near`; those (rare)
+    // pairs are added after the loop with directly summed differences, which is what the reference does (:722-741).
+    unsigned near = 0;
+#pragma unroll 1
+    for (int j = grp; j < 64; j += 8) {
+      float2 xb[2][2 * T4];  // xb[u][TH] = (last tap, b1), xb[u][TH + 1] = (b2, |b|^2)
+#pragma unroll
+      for (int u = 0; u < 2; u++)
+#pragma unroll
+        for (int q = 0; q < T4; q++) {
+          const float4 v = tb[buf][j + 4 * u][q];
+          xb[u][2 * q] = make_float2(v.x, v.y);
+          xb[u][2 * q + 1] = make_float2(v.z, v.w);
+        }
+      float2 dq[2][4];
+#pragma unroll
+      for (int t = 0; t < TH; t++)
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+          dq[u][t & 3] = t < 4 ? __fmul2_rn(xa2[t], xb[u][t]) : __ffma2_rn(xa2[t], xb[u][t], dq[u][t & 3]);
+      float w[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const float2 dp = __fadd2_rn(__fadd2_rn(dq[u][0], dq[u][1]), __fadd2_rn(dq[u][2], dq[u][3]));
+        const float dot = fmaf(xa_l, xb[u][TH].x, dp.x) + dp.y;
+        const float nn = na + xb[u][TH + 1].y;
+        const float d2 = fmaf(-2.f, dot, nn);
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2));
+        const bool on = (__float_as_int(xb[u][TH].y) != a1) & (__float_as_int(xb[u][TH + 1].x) != a2);
+        const bool cancels = d2 < 0.01f * nn;  // false for rows beyond n (nn = inf)
+        if (on && cancels) near |= 1u << ((j >> 2) + u);
+        w[u] = (on && !cancels) ? r : 0.f;
+        sw += w[u];
+      }
+#pragma unroll
+      for (int t = 0; t < TH; t++)
+#pragma unroll
+        for (int u = 0; u < 2; u++) swx2[t] = __ffma2_rn(make_float2(w[u], w[u]), xb[u][t], swx2[t]);
+#pragma unroll
+      for (int u = 0; u < 2; u++) swx_l = fmaf(w[u], xb[u][TH].x, swx_l);
+    }
+    while (near) {  // near-duplicate kernels: distances from directly summed differences
+      const int jj = __ffs(near) - 1;
+      near &= near - 1;
+      const int j = 4 * jj + grp;
+      float2 xb[2 * T4];
 #pragma unroll
       for (int q = 0; q < T4; q++) {
         const float4 v = tb[buf][j][q];
-        xb[4 * q] = v.x; xb[4 * q + 1] = v.y; xb[4 * q + 2] = v.z; xb[4 * q + 3] = v.w;
+        xb[2 * q] = make_float2(v.x, v.y);
+        xb[2 * q + 1] = make_float2(v.z, v.w);
       }
-      float d2a = 0.f, d2b = 0.f;  // two chains: the 25 dependent FMAs of one were latency, not issue
+      float2 d2p = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int t = 0; t < T; t++) {
-        const float e = xa[t] - xb[t];
-        if (t & 1) d2b = fmaf(e, e, d2b);
-        else d2a = fmaf(e, e, d2a);
+      for (int t = 0; t < TH; t++) {
+        const float2 e = __fadd2_rn(xb[t], make_float2(-xa2[t].x, -xa2[t].y));
+        d2p = __ffma2_rn(e, e, d2p);
       }
-      const float d2 = d2a + d2b;
-      float r;
-      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2));
-      const bool on = (__float_as_int(xb[T]) != a1) & (__float_as_int(xb[T + 1]) != a2) & (xb[T + 2] != 0.f);
-      const float w = on ? r : 0.f;
+      const float el = xb[TH].x - xa_l;
+      const float d2 = fmaf(el, el, d2p.x) + d2p.y;
+      float w;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(d2));
       sw += w;
 #pragma unroll
-      for (int t = 0; t < T; t++) swx[t] = fmaf(w, xb[t], swx[t]);
+      for (int t = 0; t < TH; t++) swx2[t] = __ffma2_rn(make_float2(w, w), xb[t], swx2[t]);
+      swx_l = fmaf(w, xb[TH].x, swx_l);
     }
   }
+  // back to per-tap scalars for the reduction and the store
+  float xa[T], swx[T];
+#pragma unroll
+  for (int t = 0; t < TH; t++) {
+    xa[2 * t] = xa2[t].x; xa[2 * t + 1] = xa2[t].y;
+    swx[2 * t] = swx2[t].x; swx[2 * t + 1] = swx2[t].y;
+  }
+  xa[T - 1] = xa_l;
+  swx[T - 1] = swx_l;
   // combine the 4 groups (fixed order)
   if (grp > 0) {
 #pragma unroll
@@ -1071,8 +1163,17 @@ int launch_gradient_diff(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, const f
       float* part = nullptr;
       if (nchunks > 1) AE_TRY(ctx->getT("gdiff_part", (size_t)2 * nchunks * nt * 64 * (T + 1), &part));
       dim3 grid(nt, 2, nchunks);
-      if (T == 25) gradient_diff_tiled_kernel<25><<<grid, 256, 0, ctx->stream>>>(c, f, cd, fd, dM, dD, t0, part);
-      else gradient_diff_tiled_kernel<9><<<grid, 256, 0, ctx->stream>>>(c, f, cd, fd, dM, dD, t0, part);
+      float* xp = nullptr;
+      const int npad = tiles * 64;
+      AE_TRY(ctx->getT("gdiff_pack", (size_t)2 * npad * (T + 3), &xp));
+      if (T == 25) {
+        gradient_diff_pack_kernel<25><<<(2 * npad + 127) / 128, 128, 0, ctx->stream>>>(c, f, xp, dM, dD, npad);
+        gradient_diff_tiled_kernel<25><<<grid, 256, 0, ctx->stream>>>(c, f, cd, fd, dM, dD, t0, part, xp);
+      } else {
+        gradient_diff_pack_kernel<9><<<(2 * npad + 127) / 128, 128, 0, ctx->stream>>>(c, f, xp, dM, dD, npad);
+        gradient_diff_tiled_kernel<9><<<grid, 256, 0, ctx->stream>>>(c, f, cd, fd, dM, dD, t0, part, xp);
+      }
+      ctx->launches++;
       ctx->launches++;
       if (nchunks > 1) {
         const int total = 2 * nt * 64;
