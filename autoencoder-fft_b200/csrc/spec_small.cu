@@ -258,38 +258,75 @@ int run_mse(aefft_ctx* ctx, const SmallParams& p) {
 
 }  // namespace
 
-// ---- forward contraction (conv_k, :162-189) when CI*CO is small: one thread per bin keeps the whole CO x CI weight block of its
-// bin in registers and walks over a chunk of frames -- every load and store of a warp is one contiguous 256-byte run, the
-// weights are read once per frame chunk.  out[b][o][w] = in_scale * sum_c W[o][c][w] in[b][c][w]  (+ bias[o]*bias_scale at bin 0)
+// ---- forward contraction (conv_k, :162-189) when CI*CO is small: the CO x CI weight block of a bin lives in registers, split
+// over PARTS = 4 lanes of a warp (lane = part * 8 + bin): the lanes of a bin share the LARGER channel count -- each takes a
+// quarter of the inputs (partial sums combined by two shuffles) when CI >= CO, a quarter of the outputs otherwise.  A thread
+// walks over a chunk of frames, two frames per iteration with all loads issued before the arithmetic.
+//   out[b][o][w] = in_scale * sum_c W[o][c][w] in[b][c][w]  (+ bias[o]*bias_scale at bin 0)
+// One thread per bin with the whole block in registers (round 2's first form: 96 + 32 registers of operands at 16 x 3) ran
+// 11-15 warps per SM and waited on its own loads: 2.7 TB/s at 16 -> 3 channels (ncu: issue slots 14 % busy, 27 cycles of
+// long-scoreboard stall per issued instruction).
 namespace {
 template <int CI, int CO>
 __global__ void __launch_bounds__(128) conv_reg_kernel(const float2* __restrict__ in, const float2* __restrict__ W,
                                                        const float* __restrict__ bias, float2* __restrict__ out, long long S, int B,
                                                        int frames_per_block, float in_scale, float bias_scale) {
-  const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= S) return;
-  float2 Wr[CO][CI];
-  float bo[CO];
+  constexpr int PARTS = 4, BPW = 32 / PARTS;       // bins per warp
+  constexpr bool SPLIT_IN = CI >= CO;
+  constexpr int CIP = SPLIT_IN ? (CI + PARTS - 1) / PARTS : CI;  // inputs of this lane
+  constexpr int COP = SPLIT_IN ? CO : (CO + PARTS - 1) / PARTS;  // outputs of this lane
+  const int lane = threadIdx.x & 31, part = lane / BPW;
+  const long long w = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * BPW + (lane % BPW);
+  const bool live = w < S;
+  const long long wl = live ? w : 0;
+  const int c0 = SPLIT_IN ? part * CIP : 0, o0 = SPLIT_IN ? 0 : part * COP;
+  float2 Wr[COP][CIP];
+  float bo[COP];
 #pragma unroll
-  for (int o = 0; o < CO; o++) {
+  for (int o = 0; o < COP; o++) {
 #pragma unroll
-    for (int c = 0; c < CI; c++) {
-      const float2 v = __ldg(W + ((long long)o * CI + c) * S + w);
+    for (int c = 0; c < CIP; c++) {
+      const bool ok = o0 + o < CO && c0 + c < CI;
+      const float2 v = ok ? __ldg(W + ((long long)(o0 + o) * CI + (c0 + c)) * S + wl) : make_float2(0.f, 0.f);
       Wr[o][c] = make_float2(v.x * in_scale, v.y * in_scale);
     }
-    bo[o] = (w == 0 && bias) ? bias[o] * bias_scale : 0.f;
+    bo[o] = (w == 0 && bias && o0 + o < CO && (!SPLIT_IN || part == 0)) ? bias[o0 + o] * bias_scale : 0.f;
   }
   const int b0 = blockIdx.y * frames_per_block, b1 = min(B, b0 + frames_per_block);
-  for (int b = b0; b < b1; b++) {
-    float2 x[CI];
+  for (int b = b0; b < b1; b += 2) {
+    const bool two = b + 1 < b1;
+    float2 x[2][CIP];
 #pragma unroll
-    for (int c = 0; c < CI; c++) x[c] = __ldg(in + ((long long)b * CI + c) * S + w);
+    for (int u = 0; u < 2; u++)
 #pragma unroll
-    for (int o = 0; o < CO; o++) {
-      float2 acc = make_float2(bo[o], 0.f);
+      for (int c = 0; c < CIP; c++)
+        x[u][c] = (c0 + c < CI && (u == 0 || two)) ? __ldg(in + ((long long)(b + u) * CI + (c0 + c)) * S + wl) : make_float2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < CI; c++) cmac(acc, Wr[o][c], x[c]);
-      out[((long long)b * CO + o) * S + w] = acc;
+    for (int u = 0; u < 2; u++) {
+      float2 acc[COP];
+#pragma unroll
+      for (int o = 0; o < COP; o++) {
+        acc[o] = make_float2(bo[o], 0.f);
+#pragma unroll
+        for (int c = 0; c < CIP; c++) cmac(acc[o], Wr[o][c], x[u][c]);
+      }
+      if (SPLIT_IN) {
+        // sum over the four parts (fixed order: the xor tree), then part p stores the outputs o = p, p + 4, ...
+#pragma unroll
+        for (int o = 0; o < COP; o++) {
+          acc[o].x += __shfl_xor_sync(0xffffffffu, acc[o].x, BPW);
+          acc[o].y += __shfl_xor_sync(0xffffffffu, acc[o].y, BPW);
+          acc[o].x += __shfl_xor_sync(0xffffffffu, acc[o].x, 2 * BPW);
+          acc[o].y += __shfl_xor_sync(0xffffffffu, acc[o].y, 2 * BPW);
+        }
+#pragma unroll
+        for (int o = 0; o < COP; o++)
+          if (live && (o % PARTS) == part && (u == 0 || two)) out[((long long)(b + u) * CO + o) * S + w] = acc[o];
+      } else {
+#pragma unroll
+        for (int o = 0; o < COP; o++)
+          if (live && o0 + o < CO && (u == 0 || two)) out[((long long)(b + u) * CO + (o0 + o)) * S + w] = acc[o];
+      }
     }
   }
 }
@@ -299,7 +336,7 @@ int launch_spec_conv_reg(aefft_ctx* ctx, int64_t B, int CI, int CO, int64_t S, c
                          float bias_scale, float in_scale, float2* out) {
   if (getenv("AEFFT_NO_SPEC_SMALL")) return AEFFT_ERR_UNSUPPORTED;
   const int fpb = 16;
-  dim3 grid((unsigned)((S + 127) / 128), (unsigned)((B + fpb - 1) / fpb));
+  dim3 grid((unsigned)((S + 31) / 32), (unsigned)((B + fpb - 1) / fpb));  // 128 threads = 4 warps x 8 bins
   if (grid.y > 65535) return AEFFT_ERR_UNSUPPORTED;
 #define AEFFT_CONV_REG(ci, co)                                                                                              \
   if (CI == ci && CO == co) {                                                                                               \
