@@ -70,8 +70,20 @@ __global__ void __launch_bounds__(128) small_grad_kernel(SmallParams p) {
 #pragma unroll
   for (int d = 0; d < DD; d++) esum[d] = 0.f;
   const long long fs = (long long)DD * p.S;
+  // Operands of the frame PF steps ahead are pulled into L2 (no registers held): with 161 registers per thread 12 warps fit on
+  // an SM and more than half of them waited on DRAM at any time; a register double buffer of the next frame was slower
+  // (1.19 vs 1.06 ms at 3 -> 16 channels, 512 x 257 bins, 128 frames), the L2 prefetch gives 0.91 ms.
+  constexpr int PF = 3;
   for (int b = 0; b < p.B; b++) {
     float2 x[DD], e[DD], hh[4];
+    if (mq == 0 && b + PF < p.B) {
+#pragma unroll
+      for (int d = 0; d < DD; d++) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.X + (b + PF) * fs + d * p.S + wc));
+        if (HAS_O) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.O + (b + PF) * fs + d * p.S + wc));
+        if (p.Xt != p.X) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.Xt + (b + PF) * fs + d * p.S + wc));
+      }
+    }
 #pragma unroll
     for (int d = 0; d < DD; d++) x[d] = __ldg(p.X + b * fs + d * p.S + wc);
     // H-hat[m] = sum_d C[m][d] X[d] + b[m] Nx Ny at DC  (no /dM: quirk F1);  H = (H-hat - bias)/dM + bias
