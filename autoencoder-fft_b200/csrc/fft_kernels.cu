@@ -94,6 +94,34 @@ __device__ __forceinline__ void dft8(float2* a) {
   a[3] = cadd(e[3], w3);   a[7] = csub(e[3], w3);
 }
 
+// a * (wr + i wi) with (wr, wi) the FORWARD twiddle; the inverse transform takes the conjugate
+template <int DIR>
+__device__ __forceinline__ float2 mul_w(float2 a, float wr, float wi) {
+  const float y = DIR < 0 ? wi : -wi;
+  return make_float2(a.x * wr - a.y * y, a.x * y + a.y * wr);
+}
+// 16-point DFT in registers as 4 x 4 (n = 4 n1 + n2, k = k1 + 4 k2), natural order in and out
+template <int DIR>
+__device__ __forceinline__ void dft16(float2* a) {
+  const float c = 0.92387953251128674f, s = 0.38268343236508977f, h = 0.70710678118654752440f;
+  float2 t[4][4];
+#pragma unroll
+  for (int n2 = 0; n2 < 4; n2++) {
+    t[n2][0] = a[n2]; t[n2][1] = a[4 + n2]; t[n2][2] = a[8 + n2]; t[n2][3] = a[12 + n2];
+    dft4<DIR>(t[n2]);
+  }
+  // W16^(n2 k1), forward values (cos, -sin)
+  t[1][1] = mul_w<DIR>(t[1][1], c, -s);  t[1][2] = mul_w<DIR>(t[1][2], h, -h);  t[1][3] = mul_w<DIR>(t[1][3], s, -c);
+  t[2][1] = mul_w<DIR>(t[2][1], h, -h);  t[2][2] = mul_mi<DIR>(t[2][2]);        t[2][3] = mul_w<DIR>(t[2][3], -h, -h);
+  t[3][1] = mul_w<DIR>(t[3][1], s, -c);  t[3][2] = mul_w<DIR>(t[3][2], -h, -h); t[3][3] = mul_w<DIR>(t[3][3], -c, s);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; k1++) {
+    float2 y[4] = {t[0][k1], t[1][k1], t[2][k1], t[3][k1]};
+    dft4<DIR>(y);
+    a[k1] = y[0]; a[k1 + 4] = y[1]; a[k1 + 8] = y[2]; a[k1 + 12] = y[3];
+  }
+}
+
 // One radix-R pass over `nseq` sequences held in shared memory: element n of sequence c lives at s[n*sn + c*sc].
 // seq_fast: consecutive threads take consecutive sequences (column tiles) or consecutive butterflies (row tiles).
 template <int DIR, int R>
@@ -429,12 +457,28 @@ __global__ void __launch_bounds__(256) fft_cols_t(const float2* __restrict__ in,
 // from global memory and -- for the column and the C2R row kernels -- the LAST pass stores straight to global memory:
 // a 512-point transform makes 2 shared-memory exchanges instead of 4 staging/pass/readout round trips.
 // Buffer index padding pad(i) = i + (i >> 3) makes the stride-R stores of the first passes conflict free.
-__device__ __forceinline__ int padi(int i) { return i + (i >> 3); }
+// (8-byte elements: 16 lanes fill the 32 banks.  One pad element per 16 keeps a half-warp's run of consecutive elements
+// inside one wavefront -- a pad per 8 elements, the first choice, split every such run over two -- and still spreads the
+// stride-8 and stride-16 stores of the first pass: element 8 j sits at word 16 j + 2 (j >> 1), element 16 j at word 34 j.)
+#ifndef AEFFT_FFT_PADSHIFT
+#define AEFFT_FFT_PADSHIFT 4
+#endif
+__device__ __forceinline__ int padi(int i) { return i + (i >> AEFFT_FFT_PADSHIFT); }
+// Radix schedule of the Stockham kernels: radix 8 passes after a first pass of radix 2 / 4 / 8 -- or 16 for N = 1024:
+// three shared-memory-free register DFTs of 16 * 8 * 8 instead of four passes 2 * 8 * 8 * 8 (the extra pass cost
+// a full shared-memory round trip and two barriers: the 1024-point row kernels ran at 0.6 of the 512-point ones per byte).
+template <int LOG2N>
+struct SSched {
+  static constexpr int first = (LOG2N % 3 == 1) ? (LOG2N == 10 ? 4 : 1) : ((LOG2N % 3 == 2) ? 2 : 3);
+  static constexpr int npass = 1 + (LOG2N - first) / 3;
+  __host__ __device__ static constexpr int lr(int i) { return i == 0 ? first : 3; }
+};
+
 
 // one butterfly of pass I: loads + twiddles + DFT into a[], returns the output base index j0 (outputs go to j0 + q*NS)
 template <int DIR, int LOG2N, int I, int LOG2NS, class Load>
 __device__ __forceinline__ int stockham_load(int j, Load ld, const float2* __restrict__ tw, float2* a) {
-  constexpr int LR = Sched<LOG2N>::lr(I), R = 1 << LR, NS = 1 << LOG2NS;
+  constexpr int LR = SSched<LOG2N>::lr(I), R = 1 << LR, NS = 1 << LOG2NS;
   const int k = j & (NS - 1);
 #pragma unroll
   for (int q = 0; q < R; q++) a[q] = ld(j + (q << (LOG2N - LR)));
@@ -448,12 +492,13 @@ __device__ __forceinline__ int stockham_load(int j, Load ld, const float2* __res
   }
   if (R == 2) dft2<DIR>(a);
   else if (R == 4) dft4<DIR>(a);
-  else dft8<DIR>(a);
+  else if (R == 8) dft8<DIR>(a);
+  else dft16<DIR>(a);
   return ((j - k) << LR) + k;
 }
 template <int DIR, int LOG2N, int I, int LOG2NS, class Load, class Store>
 __device__ __forceinline__ void stockham_item(int j, Load ld, Store st, const float2* __restrict__ tw) {
-  constexpr int LR = Sched<LOG2N>::lr(I), R = 1 << LR;
+  constexpr int LR = SSched<LOG2N>::lr(I), R = 1 << LR;
   float2 a[R];
   const int j0 = stockham_load<DIR, LOG2N, I, LOG2NS>(j, ld, tw, a);
 #pragma unroll
@@ -463,11 +508,13 @@ __device__ __forceinline__ void stockham_item(int j, Load ld, Store st, const fl
 template <int LOG2N>
 struct SRowCfg {
   static constexpr int N = 1 << LOG2N;
-  static constexpr int LOG2RP = LOG2N >= 11 ? 0 : (11 - LOG2N > 5 ? 5 : 11 - LOG2N);  // ~18 KB
+  static constexpr int LOG2RP0 = LOG2N >= 11 ? 0 : (11 - LOG2N > 5 ? 5 : 11 - LOG2N);  // ~18 KB
+  static constexpr int LOG2RPMIN = 8 + SSched<LOG2N>::first - LOG2N;  // >= 256 first-pass butterflies per CTA
+  static constexpr int LOG2RP = LOG2RP0 >= LOG2RPMIN ? LOG2RP0 : (LOG2RPMIN > 5 ? 5 : LOG2RPMIN);
   static constexpr int RP = 1 << LOG2RP;
   static constexpr int SP = N + (N >> 3) + 2;
   static constexpr size_t smem = (size_t)RP * SP * sizeof(float2);
-  static constexpr int npass = Sched<LOG2N>::npass;
+  static constexpr int npass = SSched<LOG2N>::npass;
 };
 
 // middle passes I = 1 .. npass-1 (shared -> shared) IN PLACE: every thread first loads and transforms all its butterflies
@@ -475,9 +522,9 @@ struct SRowCfg {
 // doubles the CTAs per SM.  256 threads per CTA.
 template <int DIR, int LOG2N, int LOG2SEQ, int I, int LOG2NS, bool LAST_TO_CALLER, class Seq>
 __device__ __forceinline__ void stockham_middle(float2* buf, const float2* __restrict__ tw, Seq sq) {
-  constexpr int npass = Sched<LOG2N>::npass;
+  constexpr int npass = SSched<LOG2N>::npass;
   if constexpr (I < npass - (LAST_TO_CALLER ? 1 : 0)) {
-    constexpr int LR = Sched<LOG2N>::lr(I), R = 1 << LR;
+    constexpr int LR = SSched<LOG2N>::lr(I), R = 1 << LR;
     constexpr int TOTAL = 1 << (LOG2N - LR + LOG2SEQ);
     constexpr int ITEMS = TOTAL >= 256 ? TOTAL / 256 : 1;
     float2 a[ITEMS][R];
@@ -525,7 +572,7 @@ template <int LOG2N, bool PRUNE = false>
 __global__ void __launch_bounds__(256) fft_rows_r2c_s(const float* __restrict__ in, float2* __restrict__ out, int Nx,
                                                       const float2* __restrict__ tw, int ch, long long fstride, int keep = 0) {
   using C = SRowCfg<LOG2N>;
-  constexpr int Ny = C::N, Nyr = Ny / 2 + 1, SP = C::SP, RP = C::RP, LR0 = Sched<LOG2N>::lr(0);
+  constexpr int Ny = C::N, Nyr = Ny / 2 + 1, SP = C::SP, RP = C::RP, LR0 = SSched<LOG2N>::lr(0);
   extern __shared__ __align__(16) float2 sm[];
   float2* src = sm;
   const long long img = blockIdx.y;
@@ -581,8 +628,8 @@ __global__ void __launch_bounds__(256) fft_rows_c2r_s(const float2* __restrict__
                                                       const float2* __restrict__ tw, float scale, int ch, long long fstride,
                                                       int keep = 0) {
   using C = SRowCfg<LOG2N>;
-  constexpr int Ny = C::N, Nyr = Ny / 2 + 1, SP = C::SP, RP = C::RP, LR0 = Sched<LOG2N>::lr(0), NP = C::npass;
-  constexpr int LRL = Sched<LOG2N>::lr(NP - 1);
+  constexpr int Ny = C::N, Nyr = Ny / 2 + 1, SP = C::SP, RP = C::RP, LR0 = SSched<LOG2N>::lr(0), NP = C::npass;
+  constexpr int LRL = SSched<LOG2N>::lr(NP - 1);
   extern __shared__ __align__(16) float2 sm[];
   float2* src = sm;
   const long long img = blockIdx.y;
@@ -656,8 +703,8 @@ template <int DIR, int LOG2N, int MODE = 0>
 __global__ void __launch_bounds__(256) fft_cols_s(const float2* __restrict__ in, float2* __restrict__ out, int W,
                                                   const float2* __restrict__ tw, int Nxo = 0) {
   using C = SColCfg<LOG2N>;
-  constexpr int Nx = C::N, CT = C::CT, LOG2CT = C::LOG2CT, LR0 = Sched<LOG2N>::lr(0), NP = Sched<LOG2N>::npass;
-  constexpr int LRL = Sched<LOG2N>::lr(NP - 1);
+  constexpr int Nx = C::N, CT = C::CT, LOG2CT = C::LOG2CT, LR0 = SSched<LOG2N>::lr(0), NP = SSched<LOG2N>::npass;
+  constexpr int LRL = SSched<LOG2N>::lr(NP - 1);
   extern __shared__ __align__(16) float2 sm[];
   float2* src = sm;
   const long long img = blockIdx.y;
