@@ -593,32 +593,31 @@ __global__ void __launch_bounds__(256) fft_rows_r2c_s(const float* __restrict__ 
   }
   stockham_middle<-1, LOG2N, C::LOG2RP, 1, LR0, false>(src, tw, rs);
   __syncthreads();
-  if constexpr (PRUNE) {
-    float2* o = out + img * (long long)Nx * keep;
-    for (int idx = threadIdx.x; idx < RP * keep; idx += blockDim.x) {
-      const int r = idx / keep, kk = idx - r * keep;
-      const int k = kk < keep - 1 ? kk : Ny / 2;
+  // split Z = A + i B into the half spectra of the two rows.  The RP row pairs of the CTA are ONE index space over the
+  // power-of-two part of the half spectrum (columns 0 .. ncol-1: shifts, no division -- the flat index over 2^k + 1 columns
+  // cost ~25 integer instructions per element, more than the loads, the arithmetic and the stores together); the Nyquist
+  // column Ny/2, which would be an extra one-thread trip per row, is left to the first RP threads.
+  const int pitch = PRUNE ? keep : Nyr;
+  const int ncol = PRUNE ? keep - 1 : Ny / 2;  // columns 0 .. ncol-1, then the Nyquist column at output column ncol
+  float2* o = out + img * (long long)Nx * pitch;
+  auto split = [&](const float2* sr, float2* o0, int k, int kk) {
+    const float2 z1 = sr[padi(k)];
+    const float2 z2 = sr[padi((Ny - k) & (Ny - 1))];
+    o0[kk] = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+    o0[pitch + kk] = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+  };
+  {
+    const bool p2 = (ncol & (ncol - 1)) == 0;
+    const int sh = PRUNE ? 31 - __clz(ncol) : LOG2N - 1;
+    for (int idx = threadIdx.x; idx < RP * ncol; idx += blockDim.x) {
+      const int r = (!PRUNE || p2) ? idx >> sh : idx / ncol, k = idx - r * ncol;
       const int row = 2 * (rp0 + r);
       if (row >= Nx) break;
-      const float2 z1 = src[rs.addr(r, k)];
-      const float2 z2 = src[rs.addr(r, (Ny - k) & (Ny - 1))];
-      o[(long long)row * keep + kk] = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
-      o[(long long)(row + 1) * keep + kk] = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+      split(src + r * SP, o + (long long)row * pitch, k, k);
     }
-    return;
   }
-  float2* o = out + img * (long long)Nx * Nyr;
-  // the RP row pairs of the CTA as ONE index space: a half spectrum has 2^k + 1 columns, so a per-row loop would spend a
-  // whole extra pass on the Nyquist column of every row
-  for (int idx = threadIdx.x; idx < RP * Nyr; idx += blockDim.x) {
-    const int r = idx / Nyr, k = idx - r * Nyr;  // Nyr is a compile-time constant
-    const int row = 2 * (rp0 + r);
-    if (row >= Nx) break;
-    const float2 z1 = src[rs.addr(r, k)];
-    const float2 z2 = src[rs.addr(r, (Ny - k) & (Ny - 1))];
-    o[(long long)row * Nyr + k] = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
-    o[(long long)(row + 1) * Nyr + k] = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
-  }
+  if (threadIdx.x < RP && 2 * (rp0 + (int)threadIdx.x) < Nx)
+    split(src + threadIdx.x * SP, o + (long long)(2 * (rp0 + threadIdx.x)) * pitch, Ny / 2, ncol);
 }
 
 // EMBED: the input is a spectrum that was zero-embedded from a smaller one (spectral up-sampling): only `keep` columns
