@@ -131,6 +131,63 @@ int conv_spec(aefft_net* net, int n, int li, int lo) {
                               1.f / (float)c.dM, c.b, norm, (float2*)net->spec[lo].p);
 }
 
+// Level 0-style convs (few channels on the image side, bins-fastest spectra) next to a level change, when nobody looks at the
+// full-resolution spectrum in between (fft_l <= 0):
+//   encoder: conv n (layer li -> li+1) + spectral pooling (li+1 -> li+2): only the bins the crop keeps are computed and the
+//            pooled spectrum is written directly -- layer li+1's spectrum is NOT produced;
+//   decoder: spectral up-sampling (ls -> ls+1) + conv n (ls+1 -> ls+2): the conv reads the small spectrum and writes the kept
+//            bins of its output (the rest is the conv of zeros = zero) -- layer ls+1's spectrum is NOT produced.
+// Training never reads the skipped spectra: a pair trains on layers 2n+1 and 2N-1-2n, and only tensor-core pairs reuse the
+// forward's hidden spectrum (train_pair_spectra).
+bool fusable_conv(const aefft_net* net, int n, int l_conv_in) {
+  const ConvL& c = net->convs[n];
+  return !net->spec[l_conv_in].bin_major && spec_conv_reg_supported(c.dD, c.dM) && !getenv("AEFFT_NO_FWD_FUSE");
+}
+int conv_kspec(aefft_net* net, int n, int Nx, int Ny, float2** kspec) {
+  aefft_ctx* ctx = net->ctx;
+  const ConvL& c = net->convs[n];
+  const long long S = (long long)Nx * (Ny / 2 + 1);
+  float* kimg;
+  AE_TRY(ctx->getT("nf_kspec", (size_t)c.dM * c.dD * S, kspec));
+  AE_TRY(ctx->getT("nf_kimg", (size_t)c.dM * c.dD * Nx * Ny, &kimg));
+  return kernel_spectrum_dev(ctx, (int64_t)c.dM * c.dD, c.Nk, c.Nl, Nx, Ny, c.c, kimg, *kspec);
+}
+// encoder: spec[li] --conv n--> (pooled) spec[li + 2]
+int conv_then_pool(aefft_net* net, int n, int li) {
+  aefft_ctx* ctx = net->ctx;
+  const ConvL& c = net->convs[n];
+  const LayerL &A = net->layers[li], &Z = net->layers[li + 2];
+  AE_ARG(A.D == c.dD && Z.D == c.dM && Z.Nx < A.Nx && Z.Ny < A.Ny);
+  float2* kspec;
+  AE_TRY(conv_kspec(net, n, A.Nx, A.Ny, &kspec));
+  const long long Sz = (long long)Z.Nx * (Z.Ny / 2 + 1), R = net->B * Z.D;
+  float2* dst = (float2*)net->spec[li + 2].p;
+  if (net->spec[li + 2].bin_major) AE_TRY(ctx->getT("nf_tmp", (size_t)R * Sz * 2, (float**)&dst));
+  AE_TRY(launch_spec_conv_reg_resized(ctx, net->B, c.dD, c.dM, A.Nx, A.Ny, Z.Nx, Z.Ny, true, (const float2*)net->spec[li].p, kspec,
+                                      c.b, (float)A.Nx * (float)A.Ny, 1.f / (float)c.dM, dst));
+  if (net->spec[li + 2].bin_major) AE_TRY(launch_to_binmajor(ctx, R, Sz, dst, nullptr, (float2*)net->spec[li + 2].p));
+  return AEFFT_OK;
+}
+// decoder: (small) spec[ls] --up-sampling, conv n--> spec[ls + 2]
+int unpool_then_conv(aefft_net* net, int n, int ls) {
+  aefft_ctx* ctx = net->ctx;
+  const ConvL& c = net->convs[n];
+  const LayerL &A = net->layers[ls], &Z = net->layers[ls + 2];
+  AE_ARG(A.D == c.dD && Z.D == c.dM && A.Nx < Z.Nx && A.Ny < Z.Ny && !net->spec[ls + 2].bin_major);
+  float2* kspec;
+  AE_TRY(conv_kspec(net, n, Z.Nx, Z.Ny, &kspec));
+  const long long Sa = (long long)A.Nx * (A.Ny / 2 + 1), R = net->B * A.D;
+  const float2* src = (const float2*)net->spec[ls].p;
+  if (net->spec[ls].bin_major) {
+    float2* ff;
+    AE_TRY(ctx->getT("nf_tmp", (size_t)R * Sa * 2, (float**)&ff));
+    AE_TRY(launch_to_binmajor(ctx, Sa, R, src, nullptr, ff));
+    src = ff;
+  }
+  return launch_spec_conv_reg_resized(ctx, net->B, c.dD, c.dM, Z.Nx, Z.Ny, A.Nx, A.Ny, false, src, kspec, c.b,
+                                      (float)Z.Nx * (float)Z.Ny, 1.f / (float)c.dM, (float2*)net->spec[ls + 2].p);
+}
+
 // fft_inv (:806-864): spectrum of layer l -> real layer l, scaled by 1/(Nx Ny)
 int materialise(aefft_net* net, int l) {
   aefft_ctx* ctx = net->ctx;
@@ -180,14 +237,24 @@ int forward(aefft_net* net, int loc, const float* frames, int fft_l) {
     }
   }
   if (!pooled0) AE_TRY(launch_fft_r2c(ctx, net->B * L0.D, L0.Nx, L0.Ny, L0.p, (float2*)net->spec[0].p));
+  bool next_in_done = false;  // the previous iteration already produced this conv's input (encoder) / output (decoder)
   for (int n = 0; n < N; n++) {
     if (n < N / 2) {
-      if (!(n == 0 && pooled0)) AE_TRY(move_spec(net, 2 * n, 2 * n + 1));        // pool_fft :1346
+      if (!(n == 0 && pooled0) && !next_in_done) AE_TRY(move_spec(net, 2 * n, 2 * n + 1));        // pool_fft :1346
+      next_in_done = false;
       if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 1));
+      const LayerL &Lc = net->layers[2 * n + 2], &Ln = net->layers[2 * n + 3];
+      if (fft_l <= 0 && n + 1 < N / 2 && Ln.Nx < Lc.Nx && Ln.Ny < Lc.Ny && Ln.Nx >= 2 && Ln.Ny >= 2 &&
+          fusable_conv(net, n, 2 * n + 1)) {
+        AE_TRY(conv_then_pool(net, n, 2 * n + 1));  // conv_fft :1356 + the next pool_fft :1346, on the kept bins only
+        next_in_done = true;
+        continue;
+      }
       AE_TRY(conv_spec(net, n, 2 * n + 1, 2 * n + 2));  // conv_fft :1356
       if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 2));
     } else {
-      AE_TRY(conv_spec(net, n, 2 * n, 2 * n + 1));
+      if (!next_in_done) AE_TRY(conv_spec(net, n, 2 * n, 2 * n + 1));
+      next_in_done = false;
       if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 1));
       if (n == N - 1) {
         // last up-sampling (pool_fft :1360) + fft_inv (:1373): the reconstruction is the only reader of the embedded
@@ -211,6 +278,15 @@ int forward(aefft_net* net, int loc, const float* frames, int fft_l) {
         AE_TRY(move_spec(net, 2 * n + 1, 2 * n + 2));
         AE_TRY(materialise(net, 2 * n + 2));
         break;
+      }
+      {
+        const LayerL &As = net->layers[2 * n + 1], &Zb = net->layers[2 * n + 2];
+        if (fft_l <= 0 && As.Nx < Zb.Nx && As.Ny < Zb.Ny && As.Nx >= 2 && As.Ny >= 2 && !net->spec[2 * n + 3].bin_major &&
+            fusable_conv(net, n + 1, 2 * n + 2)) {
+          AE_TRY(unpool_then_conv(net, n + 1, 2 * n + 1));  // pool_fft :1360 + the next conv_fft on the embedded bins only
+          next_in_done = true;
+          continue;
+        }
       }
       AE_TRY(move_spec(net, 2 * n + 1, 2 * n + 2));     // pool_fft :1360
       if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 2));

@@ -278,10 +278,21 @@ int run_mse(aefft_ctx* ctx, const SmallParams& p) {
 // One thread per bin with the whole block in registers (round 2's first form: 96 + 32 registers of operands at 16 x 3) ran
 // 11-15 warps per SM and waited on its own loads: 2.7 TB/s at 16 -> 3 channels (ncu: issue slots 14 % busy, 27 cycles of
 // long-scoreboard stall per issued instruction).
+// Fused with the spectral pooling next to it (resize :87-157), MODE != 0: the threads walk over the bins of the SMALL grid
+// (Nxm x Nyrm); wb is the same frequency on the BIG grid (rows i < Nxm/2 -> i, Nxm/2 -> Nxb/2, above -> i + Nxb - Nxm; columns
+// j < Nyrm-1 -> j, Nyrm-1 -> Nyrb-1).  The kernel spectrum W always lives on the big grid (the conv runs at that resolution).
+//   MODE 1 (conv, then pooling by cropping): in at wb, out at the small bin -- the 3/4 of the conv output that the crop
+//           discards is never computed;
+//   MODE 2 (up-sampling by zero embedding, then conv): in at the small bin, out at wb -- the caller zeroes the output first;
+//           the conv of the zero band is zero (the bias lives on the DC bin, which is always kept).
+struct ConvRegMap {
+  int mode, Nxm, Nyrm, Nxb, Nyrb;
+};
 namespace {
 template <int CI, int CO>
 __global__ void __launch_bounds__(128) conv_reg_kernel(const float2* __restrict__ in, const float2* __restrict__ W,
-                                                       const float* __restrict__ bias, float2* __restrict__ out, long long S, int B,
+                                                       const float* __restrict__ bias, float2* __restrict__ out, long long S,
+                                                       long long S_in, long long S_w, long long S_out, ConvRegMap map, int B,
                                                        int frames_per_block, float in_scale, float bias_scale) {
   constexpr int PARTS = 4, BPW = 32 / PARTS;       // bins per warp
   constexpr bool SPLIT_IN = CI >= CO;
@@ -291,6 +302,15 @@ __global__ void __launch_bounds__(128) conv_reg_kernel(const float2* __restrict_
   const long long w = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * BPW + (lane % BPW);
   const bool live = w < S;
   const long long wl = live ? w : 0;
+  long long w_in = wl, w_w = wl, w_out = wl;
+  if (map.mode != 0) {
+    const int i = (int)(wl / map.Nyrm), j = (int)(wl - (long long)i * map.Nyrm);
+    const int ib = i < map.Nxm / 2 ? i : (i == map.Nxm / 2 ? map.Nxb / 2 : i + map.Nxb - map.Nxm);
+    const int jb = j < map.Nyrm - 1 ? j : map.Nyrb - 1;
+    const long long wb = (long long)ib * map.Nyrb + jb;
+    w_w = wb;
+    if (map.mode == 1) w_in = wb; else w_out = wb;
+  }
   const int c0 = SPLIT_IN ? part * CIP : 0, o0 = SPLIT_IN ? 0 : part * COP;
   float2 Wr[COP][CIP];
   float bo[COP];
@@ -299,7 +319,7 @@ __global__ void __launch_bounds__(128) conv_reg_kernel(const float2* __restrict_
 #pragma unroll
     for (int c = 0; c < CIP; c++) {
       const bool ok = o0 + o < CO && c0 + c < CI;
-      const float2 v = ok ? __ldg(W + ((long long)(o0 + o) * CI + (c0 + c)) * S + wl) : make_float2(0.f, 0.f);
+      const float2 v = ok ? __ldg(W + ((long long)(o0 + o) * CI + (c0 + c)) * S_w + w_w) : make_float2(0.f, 0.f);
       Wr[o][c] = make_float2(v.x * in_scale, v.y * in_scale);
     }
     bo[o] = (w == 0 && bias && o0 + o < CO && (!SPLIT_IN || part == 0)) ? bias[o0 + o] * bias_scale : 0.f;
@@ -312,7 +332,7 @@ __global__ void __launch_bounds__(128) conv_reg_kernel(const float2* __restrict_
     for (int u = 0; u < 2; u++)
 #pragma unroll
       for (int c = 0; c < CIP; c++)
-        x[u][c] = (c0 + c < CI && (u == 0 || two)) ? __ldg(in + ((long long)(b + u) * CI + (c0 + c)) * S + wl) : make_float2(0.f, 0.f);
+        x[u][c] = (c0 + c < CI && (u == 0 || two)) ? __ldg(in + ((long long)(b + u) * CI + (c0 + c)) * S_in + w_in) : make_float2(0.f, 0.f);
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       float2 acc[COP];
@@ -333,35 +353,64 @@ __global__ void __launch_bounds__(128) conv_reg_kernel(const float2* __restrict_
         }
 #pragma unroll
         for (int o = 0; o < COP; o++)
-          if (live && (o % PARTS) == part && (u == 0 || two)) out[((long long)(b + u) * CO + o) * S + w] = acc[o];
+          if (live && (o % PARTS) == part && (u == 0 || two)) out[((long long)(b + u) * CO + o) * S_out + w_out] = acc[o];
       } else {
 #pragma unroll
         for (int o = 0; o < COP; o++)
-          if (live && o0 + o < CO && (u == 0 || two)) out[((long long)(b + u) * CO + (o0 + o)) * S + w] = acc[o];
+          if (live && o0 + o < CO && (u == 0 || two)) out[((long long)(b + u) * CO + (o0 + o)) * S_out + w_out] = acc[o];
       }
     }
   }
 }
-}  // namespace
 
-int launch_spec_conv_reg(aefft_ctx* ctx, int64_t B, int CI, int CO, int64_t S, const float2* in, const float2* W, const float* bias,
-                         float bias_scale, float in_scale, float2* out) {
-  if (getenv("AEFFT_NO_SPEC_SMALL")) return AEFFT_ERR_UNSUPPORTED;
+int conv_reg_launch(aefft_ctx* ctx, int64_t B, int CI, int CO, int64_t S, int64_t S_in, int64_t S_w, int64_t S_out,
+                    const ConvRegMap& map, const float2* in, const float2* W, const float* bias, float bias_scale, float in_scale,
+                    float2* out, const char* name) {
   const int fpb = 16;
   dim3 grid((unsigned)((S + 31) / 32), (unsigned)((B + fpb - 1) / fpb));  // 128 threads = 4 warps x 8 bins
   if (grid.y > 65535) return AEFFT_ERR_UNSUPPORTED;
-#define AEFFT_CONV_REG(ci, co)                                                                                              \
-  if (CI == ci && CO == co) {                                                                                               \
-    ProfScope prof(ctx, "spec_contract_reg", 8.0 * B * CI * CO * S, 8.0 * S * ((double)B * (CI + CO) + (double)CI * CO));   \
-    conv_reg_kernel<ci, co><<<grid, 128, 0, ctx->stream>>>(in, W, bias, out, S, (int)B, fpb, in_scale, bias_scale);         \
-    ctx->launches++;                                                                                                        \
-    AE_CUDA(cudaGetLastError());                                                                                            \
-    return AEFFT_OK;                                                                                                        \
+#define AEFFT_CONV_REG(ci, co)                                                                                               \
+  if (CI == ci && CO == co) {                                                                                                \
+    ProfScope prof(ctx, name, 8.0 * B * CI * CO * S, 8.0 * S * ((double)B * (CI + CO) + (double)CI * CO));                   \
+    conv_reg_kernel<ci, co><<<grid, 128, 0, ctx->stream>>>(in, W, bias, out, S, S_in, S_w, S_out, map, (int)B, fpb, in_scale, \
+                                                           bias_scale);                                                      \
+    ctx->launches++;                                                                                                         \
+    AE_CUDA(cudaGetLastError());                                                                                             \
+    return AEFFT_OK;                                                                                                         \
   }
   AEFFT_CONV_REG(3, 16) AEFFT_CONV_REG(16, 3) AEFFT_CONV_REG(3, 8) AEFFT_CONV_REG(8, 3) AEFFT_CONV_REG(1, 8) AEFFT_CONV_REG(8, 1)
   AEFFT_CONV_REG(3, 4) AEFFT_CONV_REG(4, 3) AEFFT_CONV_REG(1, 16) AEFFT_CONV_REG(16, 1)
 #undef AEFFT_CONV_REG
   return AEFFT_ERR_UNSUPPORTED;
+}
+}  // namespace
+
+bool spec_conv_reg_supported(int CI, int CO) {
+  if (getenv("AEFFT_NO_SPEC_SMALL")) return false;
+  const int lo = CI < CO ? CI : CO, hi = CI < CO ? CO : CI;
+  return (lo == 3 && (hi == 16 || hi == 8 || hi == 4)) || (lo == 1 && (hi == 16 || hi == 8));
+}
+
+int launch_spec_conv_reg(aefft_ctx* ctx, int64_t B, int CI, int CO, int64_t S, const float2* in, const float2* W, const float* bias,
+                         float bias_scale, float in_scale, float2* out) {
+  if (!spec_conv_reg_supported(CI, CO)) return AEFFT_ERR_UNSUPPORTED;
+  return conv_reg_launch(ctx, B, CI, CO, S, S, S, S, ConvRegMap{0, 0, 0, 0, 0}, in, W, bias, bias_scale, in_scale, out,
+                         "spec_contract_reg");
+}
+
+// conv_k at resolution (Nxb, Nyb) followed by the spectral pooling to (Nxm, Nym) [pooled_out], or preceded by the spectral
+// up-sampling from (Nxm, Nym) [!pooled_out]; spectra bins-fastest, W = kernel spectrum at (Nxb, Nyb).  The up-sampling form
+// zeroes `out` itself.
+int launch_spec_conv_reg_resized(aefft_ctx* ctx, int64_t B, int CI, int CO, int Nxb, int Nyb, int Nxm, int Nym, bool pooled_out,
+                                 const float2* in, const float2* W, const float* bias, float bias_scale, float in_scale,
+                                 float2* out) {
+  if (!spec_conv_reg_supported(CI, CO)) return AEFFT_ERR_UNSUPPORTED;
+  AE_ARG(Nxm < Nxb && Nym < Nyb && Nxm >= 2 && Nym >= 2);
+  const int64_t Sb = (int64_t)Nxb * (Nyb / 2 + 1), Sm = (int64_t)Nxm * (Nym / 2 + 1);
+  const ConvRegMap map{pooled_out ? 1 : 2, Nxm, Nym / 2 + 1, Nxb, Nyb / 2 + 1};
+  if (!pooled_out) AE_CUDA(cudaMemsetAsync(out, 0, (size_t)B * CO * Sb * sizeof(float2), ctx->stream));
+  return conv_reg_launch(ctx, B, CI, CO, Sm, pooled_out ? Sb : Sm, Sb, pooled_out ? Sm : Sb, map, in, W, bias, bias_scale,
+                         in_scale, out, pooled_out ? "spec_contract_reg_pool" : "spec_contract_reg_embed");
 }
 
 bool spec_small_eligible(int dD, int dM) {

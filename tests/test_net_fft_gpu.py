@@ -145,3 +145,34 @@ def test_net_fft_forward_fused_pooling_at_full_resolution(ctx, size, pool):
         assert O.rel_l2(got[-1][0], want[-1]) < 2e-5
     finally:
         net.close()
+
+
+@pytest.mark.parametrize("cfg", [(3, 64, 32, [4, 5], [2, 2], 3), (3, 64, 64, [16, 32], [2, 2], 16), (1, 32, 64, [8, 16], [1, 2], 16)])
+def test_net_fft_forward_fused_with_level_changes_equals_unfused(ctx, cfg, monkeypatch):
+    """fft_l <= 0: the image-side convs run fused with the spectral pooling after / the up-sampling before them and compute
+    only the kept bins (net_fft.cu: conv_then_pool / unpool_then_conv).  Same arithmetic per kept bin, so the reconstruction
+    and the trained kernels equal those of the unfused path (AEFFT_NO_FWD_FUSE) bit for bit."""
+    D, Nx, Ny, widths, pools, B = cfg
+    out = []
+    for nofuse in (False, True):
+        if nofuse:
+            monkeypatch.setenv("AEFFT_NO_FWD_FUSE", "1")
+        else:
+            monkeypatch.delenv("AEFFT_NO_FWD_FUSE", raising=False)
+        net, *_ = make_net(ctx, D, Nx, Ny, widths, pools, B)
+        try:
+            x = O.synth_frames(5, B, D, Nx, Ny)
+            ctx.profile_enable(True)
+            traces = net.fft_step(x, del0=0.2, maxdiff=0, n_iter=2, fft_l=0)
+            names = {r["name"] for r in ctx.profile_records()}
+            ctx.profile_enable(False)
+            assert ("spec_contract_reg_pool" in names) == (not nofuse), names
+            assert ("spec_contract_reg_embed" in names) == (not nofuse), names
+            out.append((np.array(traces), net.layer(net.num_layers - 1).copy(),
+                        [net.get_conv(n)[0].copy() for n in range(2 * net.num_pairs)]))
+        finally:
+            net.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    for a, b in zip(out[0][2], out[1][2]):
+        assert np.array_equal(a, b)
