@@ -298,9 +298,10 @@ int launch_spec_conv_reg(aefft_ctx* ctx, int64_t B, int CI, int CO, int64_t S, c
 bool spec_conv_reg_supported(int CI, int CO);
 // the same contraction at resolution (Nxb, Nyb) fused with the spectral pooling after it (pooled_out: out is the cropped
 // (Nxm, Nym) spectrum) or with the spectral up-sampling before it (!pooled_out: in is the small spectrum, out the big one)
+// small_bin_major: the small spectrum is bin-major [bin][frame][channel]
 int launch_spec_conv_reg_resized(aefft_ctx* ctx, int64_t B, int CI, int CO, int Nxb, int Nyb, int Nxm, int Nym, bool pooled_out,
-                                 const float2* in, const float2* W, const float* bias, float bias_scale, float in_scale,
-                                 float2* out);
+                                 bool small_bin_major, const float2* in, const float2* W, const float* bias, float bias_scale,
+                                 float in_scale, float2* out);
 int launch_small_grad(aefft_ctx* ctx, int64_t B, int dD, int dM, int64_t S, const float2* X, const float2* Xt, const float2* O,
                       const float2* C, const float2* F, const float* bias_b, const float* bias_p, float norm, float gscale,
                       float dbscale, float2* dC, float2* dF, float* db, float* dp);

@@ -160,13 +160,10 @@ int conv_then_pool(aefft_net* net, int n, int li) {
   AE_ARG(A.D == c.dD && Z.D == c.dM && Z.Nx < A.Nx && Z.Ny < A.Ny);
   float2* kspec;
   AE_TRY(conv_kspec(net, n, A.Nx, A.Ny, &kspec));
-  const long long Sz = (long long)Z.Nx * (Z.Ny / 2 + 1), R = net->B * Z.D;
-  float2* dst = (float2*)net->spec[li + 2].p;
-  if (net->spec[li + 2].bin_major) AE_TRY(ctx->getT("nf_tmp", (size_t)R * Sz * 2, (float**)&dst));
-  AE_TRY(launch_spec_conv_reg_resized(ctx, net->B, c.dD, c.dM, A.Nx, A.Ny, Z.Nx, Z.Ny, true, (const float2*)net->spec[li].p, kspec,
-                                      c.b, (float)A.Nx * (float)A.Ny, 1.f / (float)c.dM, dst));
-  if (net->spec[li + 2].bin_major) AE_TRY(launch_to_binmajor(ctx, R, Sz, dst, nullptr, (float2*)net->spec[li + 2].p));
-  return AEFFT_OK;
+  // the pooled spectrum is written in the layout of the next level (bin-major when that level runs on the tensor cores)
+  return launch_spec_conv_reg_resized(ctx, net->B, c.dD, c.dM, A.Nx, A.Ny, Z.Nx, Z.Ny, true, net->spec[li + 2].bin_major,
+                                      (const float2*)net->spec[li].p, kspec, c.b, (float)A.Nx * (float)A.Ny, 1.f / (float)c.dM,
+                                      (float2*)net->spec[li + 2].p);
 }
 // decoder: (small) spec[ls] --up-sampling, conv n--> spec[ls + 2]
 int unpool_then_conv(aefft_net* net, int n, int ls) {
@@ -176,16 +173,9 @@ int unpool_then_conv(aefft_net* net, int n, int ls) {
   AE_ARG(A.D == c.dD && Z.D == c.dM && A.Nx < Z.Nx && A.Ny < Z.Ny && !net->spec[ls + 2].bin_major);
   float2* kspec;
   AE_TRY(conv_kspec(net, n, Z.Nx, Z.Ny, &kspec));
-  const long long Sa = (long long)A.Nx * (A.Ny / 2 + 1), R = net->B * A.D;
-  const float2* src = (const float2*)net->spec[ls].p;
-  if (net->spec[ls].bin_major) {
-    float2* ff;
-    AE_TRY(ctx->getT("nf_tmp", (size_t)R * Sa * 2, (float**)&ff));
-    AE_TRY(launch_to_binmajor(ctx, Sa, R, src, nullptr, ff));
-    src = ff;
-  }
-  return launch_spec_conv_reg_resized(ctx, net->B, c.dD, c.dM, Z.Nx, Z.Ny, A.Nx, A.Ny, false, src, kspec, c.b,
-                                      (float)Z.Nx * (float)Z.Ny, 1.f / (float)c.dM, (float2*)net->spec[ls + 2].p);
+  return launch_spec_conv_reg_resized(ctx, net->B, c.dD, c.dM, Z.Nx, Z.Ny, A.Nx, A.Ny, false, net->spec[ls].bin_major,
+                                      (const float2*)net->spec[ls].p, kspec, c.b, (float)Z.Nx * (float)Z.Ny, 1.f / (float)c.dM,
+                                      (float2*)net->spec[ls + 2].p);
 }
 
 // fft_inv (:806-864): spectrum of layer l -> real layer l, scaled by 1/(Nx Ny)

@@ -288,12 +288,17 @@ int run_mse(aefft_ctx* ctx, const SmallParams& p) {
 struct ConvRegMap {
   int mode, Nxm, Nyrm, Nxb, Nyrb;
 };
+// element (frame b, channel c, bin w) of a spectrum at b * sb + c * sc + w * sw (in float2):
+// bins-fastest [b][c][w]: (C S, S, 1); bin-major [w][b][c]: (C, 1, B C) -- what a tensor-core level next door keeps
+struct ConvRegLayout {
+  long long sb, sc, sw;
+};
 namespace {
 template <int CI, int CO>
 __global__ void __launch_bounds__(128) conv_reg_kernel(const float2* __restrict__ in, const float2* __restrict__ W,
                                                        const float* __restrict__ bias, float2* __restrict__ out, long long S,
-                                                       long long S_in, long long S_w, long long S_out, ConvRegMap map, int B,
-                                                       int frames_per_block, float in_scale, float bias_scale) {
+                                                       ConvRegLayout in_l, long long S_w, ConvRegLayout out_l, ConvRegMap map,
+                                                       int B, int frames_per_block, float in_scale, float bias_scale) {
   constexpr int PARTS = 4, BPW = 32 / PARTS;       // bins per warp
   constexpr bool SPLIT_IN = CI >= CO;
   constexpr int CIP = SPLIT_IN ? (CI + PARTS - 1) / PARTS : CI;  // inputs of this lane
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(128) conv_reg_kernel(const float2* __restrict_
     for (int u = 0; u < 2; u++)
 #pragma unroll
       for (int c = 0; c < CIP; c++)
-        x[u][c] = (c0 + c < CI && (u == 0 || two)) ? __ldg(in + ((long long)(b + u) * CI + (c0 + c)) * S_in + w_in) : make_float2(0.f, 0.f);
+        x[u][c] = (c0 + c < CI && (u == 0 || two)) ? __ldg(in + (b + u) * in_l.sb + (c0 + c) * in_l.sc + w_in * in_l.sw) : make_float2(0.f, 0.f);
 #pragma unroll
     for (int u = 0; u < 2; u++) {
       float2 acc[COP];
@@ -353,17 +358,17 @@ __global__ void __launch_bounds__(128) conv_reg_kernel(const float2* __restrict_
         }
 #pragma unroll
         for (int o = 0; o < COP; o++)
-          if (live && (o % PARTS) == part && (u == 0 || two)) out[((long long)(b + u) * CO + o) * S_out + w_out] = acc[o];
+          if (live && (o % PARTS) == part && (u == 0 || two)) out[(b + u) * out_l.sb + o * out_l.sc + w_out * out_l.sw] = acc[o];
       } else {
 #pragma unroll
         for (int o = 0; o < COP; o++)
-          if (live && o0 + o < CO && (u == 0 || two)) out[((long long)(b + u) * CO + (o0 + o)) * S_out + w_out] = acc[o];
+          if (live && o0 + o < CO && (u == 0 || two)) out[(b + u) * out_l.sb + (o0 + o) * out_l.sc + w_out * out_l.sw] = acc[o];
       }
     }
   }
 }
 
-int conv_reg_launch(aefft_ctx* ctx, int64_t B, int CI, int CO, int64_t S, int64_t S_in, int64_t S_w, int64_t S_out,
+int conv_reg_launch(aefft_ctx* ctx, int64_t B, int CI, int CO, int64_t S, ConvRegLayout in_l, int64_t S_w, ConvRegLayout out_l,
                     const ConvRegMap& map, const float2* in, const float2* W, const float* bias, float bias_scale, float in_scale,
                     float2* out, const char* name) {
   const int fpb = 16;
@@ -372,7 +377,7 @@ int conv_reg_launch(aefft_ctx* ctx, int64_t B, int CI, int CO, int64_t S, int64_
 #define AEFFT_CONV_REG(ci, co)                                                                                               \
   if (CI == ci && CO == co) {                                                                                                \
     ProfScope prof(ctx, name, 8.0 * B * CI * CO * S, 8.0 * S * ((double)B * (CI + CO) + (double)CI * CO));                   \
-    conv_reg_kernel<ci, co><<<grid, 128, 0, ctx->stream>>>(in, W, bias, out, S, S_in, S_w, S_out, map, (int)B, fpb, in_scale, \
+    conv_reg_kernel<ci, co><<<grid, 128, 0, ctx->stream>>>(in, W, bias, out, S, in_l, S_w, out_l, map, (int)B, fpb, in_scale,      \
                                                            bias_scale);                                                      \
     ctx->launches++;                                                                                                         \
     AE_CUDA(cudaGetLastError());                                                                                             \
@@ -394,22 +399,26 @@ bool spec_conv_reg_supported(int CI, int CO) {
 int launch_spec_conv_reg(aefft_ctx* ctx, int64_t B, int CI, int CO, int64_t S, const float2* in, const float2* W, const float* bias,
                          float bias_scale, float in_scale, float2* out) {
   if (!spec_conv_reg_supported(CI, CO)) return AEFFT_ERR_UNSUPPORTED;
-  return conv_reg_launch(ctx, B, CI, CO, S, S, S, S, ConvRegMap{0, 0, 0, 0, 0}, in, W, bias, bias_scale, in_scale, out,
-                         "spec_contract_reg");
+  return conv_reg_launch(ctx, B, CI, CO, S, ConvRegLayout{CI * S, S, 1}, S, ConvRegLayout{CO * S, S, 1}, ConvRegMap{0, 0, 0, 0, 0},
+                         in, W, bias, bias_scale, in_scale, out, "spec_contract_reg");
 }
 
 // conv_k at resolution (Nxb, Nyb) followed by the spectral pooling to (Nxm, Nym) [pooled_out], or preceded by the spectral
-// up-sampling from (Nxm, Nym) [!pooled_out]; spectra bins-fastest, W = kernel spectrum at (Nxb, Nyb).  The up-sampling form
-// zeroes `out` itself.
+// up-sampling from (Nxm, Nym) [!pooled_out]; W = kernel spectrum at (Nxb, Nyb).  The big-resolution spectrum is bins-fastest;
+// small_bin_major: the small one is bin-major [bin][frame][channel] (the level next door runs on the tensor cores).  The
+// up-sampling form zeroes `out` itself.
 int launch_spec_conv_reg_resized(aefft_ctx* ctx, int64_t B, int CI, int CO, int Nxb, int Nyb, int Nxm, int Nym, bool pooled_out,
-                                 const float2* in, const float2* W, const float* bias, float bias_scale, float in_scale,
-                                 float2* out) {
+                                 bool small_bin_major, const float2* in, const float2* W, const float* bias, float bias_scale,
+                                 float in_scale, float2* out) {
   if (!spec_conv_reg_supported(CI, CO)) return AEFFT_ERR_UNSUPPORTED;
   AE_ARG(Nxm < Nxb && Nym < Nyb && Nxm >= 2 && Nym >= 2);
   const int64_t Sb = (int64_t)Nxb * (Nyb / 2 + 1), Sm = (int64_t)Nxm * (Nym / 2 + 1);
   const ConvRegMap map{pooled_out ? 1 : 2, Nxm, Nym / 2 + 1, Nxb, Nyb / 2 + 1};
+  const int Csmall = pooled_out ? CO : CI;
+  const ConvRegLayout small = small_bin_major ? ConvRegLayout{Csmall, 1, B * Csmall} : ConvRegLayout{Csmall * Sm, Sm, 1};
+  const ConvRegLayout big{(pooled_out ? CI : CO) * Sb, Sb, 1};
   if (!pooled_out) AE_CUDA(cudaMemsetAsync(out, 0, (size_t)B * CO * Sb * sizeof(float2), ctx->stream));
-  return conv_reg_launch(ctx, B, CI, CO, Sm, pooled_out ? Sb : Sm, Sb, pooled_out ? Sm : Sb, map, in, W, bias, bias_scale,
+  return conv_reg_launch(ctx, B, CI, CO, Sm, pooled_out ? big : small, Sb, pooled_out ? small : big, map, in, W, bias, bias_scale,
                          in_scale, out, pooled_out ? "spec_contract_reg_pool" : "spec_contract_reg_embed");
 }
 
