@@ -491,8 +491,9 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
       AE_TRY(launch_kernel_spectrum_emb(ctx, dD, dM, Nk, Nl, Nx, Ny, col0, ncols, df_w, Femb));
       AE_TRY(launch_tc_forward(ctx, S, (int)B, dD, dM, Xb, Cemb, 1.f / (float)dM, bias_b, norm, nullptr, Hb, nullptr, 0.0, 0, 0, 0));
       // re-forward O = conv(H; F, p), kept as E = O - Xt, and its mse (:1460-1463)
-      AE_TRY(launch_tc_forward(ctx, S, (int)B, dM, dD, Hb, Femb, 1.f / (float)dD, bias_p, norm, Xtb, Eb, q.mse + n + 1, mse_scale,
-                               ncols, col0, Ny));
+      // (after the last iteration nothing reads E any more: only its mse is formed)
+      AE_TRY(launch_tc_forward(ctx, S, (int)B, dM, dD, Hb, Femb, 1.f / (float)dD, bias_p, norm, Xtb, n + 1 < n_iter ? Eb : nullptr,
+                               q.mse + n + 1, mse_scale, ncols, col0, Ny));
       if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse + n + 1, 1));
     }
     if (!sharded && !inp.resident) {  // the bins-fastest spectra of the trained kernels, for the export below

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) spec_tc_kernel(const __grid_con
 #pragma unroll
             for (int e = 0; e < 16; e++) part = fmaf(v[e], v[e], part);
           }
-          if (p.knock & 1) continue;
+          if ((p.knock & 1) || !p.out) continue;  // out == nullptr: the caller wants the sum of squares only
           float4* o4 = reinterpret_cast<float4*>(p.out + base + c0);
 #pragma unroll
           for (int e = 0; e < 4; e++) o4[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
@@ -759,12 +759,13 @@ int launch_binmajor_to_taps(aefft_ctx* ctx, int R, int C, int transpose, int Nk,
 }
 
 // forward contraction (conv_k): out~[S][B][2 O] = scale * in~[S][B][2 C] . Wemb[S][2 O][2 C]^T  (+ bias[o] * bias_scale at bin 0)
-//   minus `sub` when given (E = O - Xt), and then *mse_out = mse_scale * sum_bins hw * |out|^2 (Hermitian weights)
+//   minus `sub` when given (E = O - Xt), and then *mse_out = mse_scale * sum_bins hw * |out|^2 (Hermitian weights);
+//   out == nullptr (with mse_out): only the sum is wanted, nothing is stored
 int launch_tc_forward(aefft_ctx* ctx, long long S, int B, int C, int O, const float* in, const float* Wemb, float scale,
                       const float* bias, float bias_scale, const float* sub, float* out, float* mse_out, double mse_scale, int ncols,
                       int col0, int Ny) {
   TcOperand A{in, B, 2 * C, 0}, W{Wemb, 2 * O, 2 * C, 0};
-  const double bytes = 4.0 * S * (2.0 * B * C * (sub ? 1 : 1) + 2.0 * B * O * (sub ? 2 : 1) + 4.0 * O * C);
+  const double bytes = 4.0 * S * (2.0 * B * C + 2.0 * B * O * ((sub ? 1 : 0) + (out ? 1 : 0)) + 4.0 * O * C);
   return launch_bgemm(ctx, "spec_contract_tc", S, A, W, B, 2 * O, 2 * C, EPI_STORE, scale, bias, bias_scale, sub, out, 0, mse_out,
                       mse_scale, ncols, col0, Ny, bytes);
 }
