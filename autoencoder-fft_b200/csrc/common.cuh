@@ -286,6 +286,12 @@ int launch_tc_forward(aefft_ctx* ctx, long long S, int B, int C, int O, const fl
 int launch_tc_adjoint(aefft_ctx* ctx, long long S, int B, int dD, int dM, const float* E, const float* Femb, float* G);
 int launch_tc_outer(aefft_ctx* ctx, long long S, int B, int nP, int nQ, const float* P, const float* Q, float scale, int conj_out,
                     float* out);
+// Gram form of the gradients (spec_tc.cu): both gradient spectra of a bin from Mg = sum_b E conj(X), E / X bin-major
+bool spec_tc_gram_pays(int B, int dD, int dM);
+int launch_tc_gram_grad(aefft_ctx* ctx, long long S, int B, int dM, int dD, const float* E, const float* X, const float* Cemb,
+                        const float* Femb, float gs, float* dCt, float* dFt);
+int launch_tc_dc_terms_gram(aefft_ctx* ctx, int B, int dM, int dD, const float* E, const float* Femb, const float* bias_b, float* dFt,
+                            float* db, float* dp, float gs, float fs, float norm);
 int launch_tc_dc_terms(aefft_ctx* ctx, int B, int dM, int dD, const float* G, const float* E, const float* bias_b, float* dFt,
                        float* db, float* dp, float gs, float fs, float corr_scale);
 

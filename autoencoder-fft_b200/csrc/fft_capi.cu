@@ -436,11 +436,14 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
   // the bin-major gradient spectra.  Callers that pass spectra caches (cfreq / ffreq) keep the bins-fastest path, whose
   // first iteration consumes those caches as they are.
   if (use_tc) {
-    float *Xb = nullptr, *Xtb, *Eb, *Hb, *Gb, *Cemb, *Femb, *dCt, *dFt;
+    float *Xb = nullptr, *Xtb, *Eb, *Hb, *Gb = nullptr, *Cemb, *Femb, *dCt, *dFt;
+    // Gram form (spec_tc.cu: gram_grad_kernel): both gradient spectra from Mg = sum_b E conj(X); no G, and the hidden
+    // spectrum is needed by the re-forward only
+    const bool gram = spec_tc_gram_pays((int)B, dD, dM);
     if (!have_bm) AE_TRY(ctx->getT("tc_Xb", 2 * nXs, &Xb));
     AE_TRY(ctx->getT("tc_Eb", 2 * nXs, &Eb));
     AE_TRY(ctx->getT("tc_Hb", 2 * nHs, &Hb));
-    AE_TRY(ctx->getT("tc_Gb", 2 * nHs, &Gb));
+    if (!gram) AE_TRY(ctx->getT("tc_Gb", 2 * nHs, &Gb));
     AE_TRY(ctx->getT("tc_Cemb", 4 * nKS, &Cemb));
     AE_TRY(ctx->getT("tc_Femb", 4 * nKS, &Femb));
     AE_TRY(ctx->getT("tc_dCt", 2 * nKS, &dCt));
@@ -463,12 +466,21 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
     // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1);
     // the resident net hands over the hidden layer its forward just computed with these very kernels
     const float* Hcur = inp.Hbm;
-    if (!Hcur) {
+    if (gram) {
+      AE_TRY(launch_kernel_spectrum_emb(ctx, dM, dD, Nk, Nl, Nx, Ny, col0, ncols, dc_w, Cemb));
+    } else if (!Hcur) {
       AE_TRY(launch_kernel_spectrum_emb(ctx, dM, dD, Nk, Nl, Nx, Ny, col0, ncols, dc_w, Cemb));
       AE_TRY(launch_tc_forward(ctx, S, (int)B, dD, dM, Xb, Cemb, 1.f / (float)dM, bias_b, norm, nullptr, Hb, nullptr, 0.0, 0, 0, 0));
       Hcur = Hb;
     }
     for (int n = 0; n < n_iter; n++) {
+      if (gram) {
+        AE_TRY(launch_tc_gram_grad(ctx, S, (int)B, dM, dD, Eb, Xb, Cemb, Femb, gscale, dCt, dFt));
+        if (own_dc)
+          AE_TRY(launch_tc_dc_terms_gram(ctx, (int)B, dM, dD, Eb, Femb, bias_b, dFt, q.db, q.dp,
+                                         (float)((double)norm / (Norm * (double)B)), gscale, norm));
+        else AE_CUDA(cudaMemsetAsync(q.db, 0, (size_t)(dM + dD) * sizeof(float), st));
+      } else {
       AE_TRY(launch_tc_adjoint(ctx, S, (int)B, dD, dM, Eb, Femb, Gb));                               // G = E conj(F)
       AE_TRY(launch_tc_outer(ctx, S, (int)B, dM, dD, Gb, Xb, gscale, 0, dCt));                       // dC[m][d] = G conj(X)
       AE_TRY(launch_tc_outer(ctx, S, (int)B, dM, dD, Hcur, Eb, gscale * (float)dM, 1, dFt));         // dF[d][m] = E conj(dM H) at [m][d]
@@ -477,6 +489,7 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
         AE_TRY(launch_tc_dc_terms(ctx, (int)B, dM, dD, Gb, Eb, bias_b, dFt, q.db, q.dp, (float)((double)norm / (Norm * (double)B)),
                                   gscale, -(float)(dM - 1) * norm));
       else AE_CUDA(cudaMemsetAsync(q.db, 0, (size_t)(dM + dD) * sizeof(float), st));
+      }
       AE_TRY(launch_binmajor_to_taps(ctx, dM, dD, 0, Nk, Nl, Nx, Ny, col0, ncols, (const float2*)dCt, q.taps, 1.f));
       AE_TRY(launch_binmajor_to_taps(ctx, dM, dD, 1, Nk, Nl, Nx, Ny, col0, ncols, (const float2*)dFt, q.taps + nC, 1.f));
       const bool fold_div = sharded && maxdiff;

@@ -609,6 +609,161 @@ __global__ void dc_terms_kernel(const float* __restrict__ G, const float* __rest
   }
 }
 
+// ---- Both gradient spectra of an iteration from ONE frame-reduced outer product (associativity):
+//   Mg[d][d'] = sum_b E[b][d] conj(X[b][d'])                                   (dD x dD per bin)
+//   dC[m][d]  = gs * sum_k conj(F[k][m]) Mg[k][d]             = gs * sum_b G[b][m] conj(X[b][d]),  G = E conj(F)  (:437-445)
+//   dF[d][m]  = gs * sum_k conj(C[m][k]) Mg[d][k]             = gs * sum_b E[b][d] conj(H-hat[b][m]) away from DC  (:447-459)
+// so neither G nor the hidden spectrum is read (or written) for the gradients: the per-iteration traffic of a pair drops from
+// adjoint + two outer products over [frames][dM] operands to ONE pass over the [frames][dD] operands E and X plus
+// kernel-spectrum-sized data.  One CTA per bin, CUDA cores: phase 1 stages E and X of the bin in shared memory and forms Mg
+// with TR x TR register tiles; phase 2 re-uses that shared memory for C and F (even rows of the embedded blocks: row 2r =
+// (Re, -Im) of W[r][:], stored [k][m]) and gives every thread NO adjacent m of one d.  Outputs [bin][m][d] like the
+// outer-product epilogue writes them.  (A first version ran Mg on the tensor cores -- 128-row MMA tiles with 32 or 64 live
+// rows and one pipeline round trip per bin: 1.97 TB/s -- and phase 2 without register tiles: 0.9 + 0.7 ms at config 3.)
+template <int DD, int NO>
+__global__ void __launch_bounds__(256) gram_grad_kernel(const float* __restrict__ E, const float* __restrict__ X,
+                                                        const float* __restrict__ Cemb, const float* __restrict__ Femb,
+                                                        float2* __restrict__ dCt, float2* __restrict__ dFt, int B, int dM, float gs) {
+  // phase 1 tiling: (DD / TR)^2 register tiles of TR x TR outputs; with fewer than 256 tiles the frames are split over
+  // NG = 256 / tiles thread groups whose partial sums are added in group order (deterministic)
+  constexpr int TR = DD >= 32 ? 4 : (DD >= 16 ? 2 : 1), TG = DD / TR, NT = TG * TG, NG = 256 / NT, MP = DD + 1;
+  static_assert(NT * NG == 256, "256 threads");
+  extern __shared__ __align__(16) float2 gg_sm[];
+  float2* Ms = gg_sm;                // [DD][DD + 1]
+  float2* Es = Ms + DD * MP;         // [B][DD]   (DD is even: DD * MP float2 keep the 16-byte alignment)
+  float2* Xs = Es + (size_t)B * DD;  // [B][DD]
+  float2* Fs = Es;                   // phase 2: [DD][dM]
+  float2* Cs = Es + (size_t)DD * dM; // phase 2: [DD][dM]  (C transposed: Cs[k][m] = C[m][k])
+  const long long w = blockIdx.x;
+  const int tid = threadIdx.x;
+  {
+    const float4* e4 = reinterpret_cast<const float4*>(E + w * (long long)B * 2 * DD);
+    const float4* x4 = reinterpret_cast<const float4*>(X + w * (long long)B * 2 * DD);
+    float4* es4 = reinterpret_cast<float4*>(Es);
+    float4* xs4 = reinterpret_cast<float4*>(Xs);
+    for (int i = tid; i < B * DD / 2; i += 256) { es4[i] = __ldg(e4 + i); xs4[i] = __ldg(x4 + i); }
+  }
+  __syncthreads();
+  {
+    const int tile = tid % NT, grp = tid / NT;
+    const int dr = (tile / TG) * TR, dc = (tile % TG) * TR;
+    float2 acc[TR][TR];
+#pragma unroll
+    for (int a = 0; a < TR; a++)
+#pragma unroll
+      for (int c = 0; c < TR; c++) acc[a][c] = make_float2(0.f, 0.f);
+#pragma unroll 2
+    for (int b = grp; b < B; b += NG) {
+      float2 e[TR], x[TR];
+#pragma unroll
+      for (int a = 0; a < TR; a++) { e[a] = Es[b * DD + dr + a]; x[a] = Xs[b * DD + dc + a]; }
+#pragma unroll
+      for (int a = 0; a < TR; a++)
+#pragma unroll
+        for (int c = 0; c < TR; c++) {  // e * conj(x)
+          acc[a][c].x = fmaf(e[a].x, x[c].x, acc[a][c].x); acc[a][c].x = fmaf(e[a].y, x[c].y, acc[a][c].x);
+          acc[a][c].y = fmaf(e[a].y, x[c].x, acc[a][c].y); acc[a][c].y = fmaf(-e[a].x, x[c].y, acc[a][c].y);
+        }
+    }
+    if constexpr (NG == 1) {
+#pragma unroll
+      for (int a = 0; a < TR; a++)
+#pragma unroll
+        for (int c = 0; c < TR; c++) Ms[(dr + a) * MP + dc + c] = acc[a][c];
+    } else {
+      __syncthreads();  // every group is done with E and X: their space takes the partial sums [group][DD][MP]
+      float2* Pp = Es + (size_t)grp * DD * MP;
+#pragma unroll
+      for (int a = 0; a < TR; a++)
+#pragma unroll
+        for (int c = 0; c < TR; c++) Pp[(dr + a) * MP + dc + c] = acc[a][c];
+      __syncthreads();
+      for (int i = tid; i < DD * MP; i += 256) {
+        float2 sum = Es[i];
+#pragma unroll
+        for (int g = 1; g < NG; g++) { const float2 v = Es[(size_t)g * DD * MP + i]; sum.x += v.x; sum.y += v.y; }
+        Ms[i] = sum;
+      }
+    }
+  }
+  __syncthreads();  // Mg complete; E and X are dead: their space takes F and C
+  for (int i = tid; i < dM * DD; i += 256) {
+    const int k = i / dM, m = i - k * dM;   // F[k][m]: embedded row 2k, columns 2m, 2m+1
+    const float2 u = __ldg(reinterpret_cast<const float2*>(Femb + ((w * 2 * DD + 2 * k) * 2 * (long long)dM + 2 * m)));
+    Fs[i] = make_float2(u.x, -u.y);
+    const int mc = i / DD, kc = i - mc * DD;  // C[mc][kc]: embedded row 2 mc, columns 2 kc, 2 kc + 1
+    const float2 v = __ldg(reinterpret_cast<const float2*>(Cemb + ((w * 2 * dM + 2 * mc) * 2 * (long long)DD + 2 * kc)));
+    Cs[kc * dM + mc] = make_float2(v.x, -v.y);
+  }
+  __syncthreads();
+  const int d = tid % DD, m0 = (tid / DD) * NO;
+  if (m0 < dM) {
+    float2 aC[NO], aF[NO];
+#pragma unroll
+    for (int j = 0; j < NO; j++) { aC[j] = make_float2(0.f, 0.f); aF[j] = make_float2(0.f, 0.f); }
+#pragma unroll 2
+    for (int k = 0; k < DD; k++) {
+      const float2 m1 = Ms[k * MP + d], m2 = Ms[d * MP + k];
+      float2 f[NO], c[NO];
+      if constexpr (NO % 2 == 0) {
+#pragma unroll
+        for (int j = 0; j < NO; j += 2) {
+          const float4 fv = *reinterpret_cast<const float4*>(Fs + k * dM + m0 + j);
+          const float4 cv = *reinterpret_cast<const float4*>(Cs + k * dM + m0 + j);
+          f[j] = make_float2(fv.x, fv.y); f[j + 1] = make_float2(fv.z, fv.w);
+          c[j] = make_float2(cv.x, cv.y); c[j + 1] = make_float2(cv.z, cv.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NO; j++) { f[j] = Fs[k * dM + m0 + j]; c[j] = Cs[k * dM + m0 + j]; }
+      }
+#pragma unroll
+      for (int j = 0; j < NO; j++) {  // conj(F[k][m]) * Mg[k][d]  and  conj(C[m][k]) * Mg[d][k]
+        aC[j].x = fmaf(f[j].x, m1.x, aC[j].x); aC[j].x = fmaf(f[j].y, m1.y, aC[j].x);
+        aC[j].y = fmaf(f[j].x, m1.y, aC[j].y); aC[j].y = fmaf(-f[j].y, m1.x, aC[j].y);
+        aF[j].x = fmaf(c[j].x, m2.x, aF[j].x); aF[j].x = fmaf(c[j].y, m2.y, aF[j].x);
+        aF[j].y = fmaf(c[j].x, m2.y, aF[j].y); aF[j].y = fmaf(-c[j].y, m2.x, aF[j].y);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NO; j++) {
+      const long long o = (w * dM + m0 + j) * DD + d;
+      dCt[o] = make_float2(aC[j].x * gs, aC[j].y * gs);
+      dFt[o] = make_float2(aF[j].x * gs, aF[j].y * gs);
+    }
+  }
+}
+
+// DC-bin terms of gradient_k_io (:447-473) for the Gram form (bin 0 = the first block of the bin-major arrays), from
+// Esum[d] = sum_b E[b][d](0):   dp[d] = gs Re Esum[d];   db[m] = gs Re sum_d conj(F[d][m](0)) Esum[d]  (= gs sum_b Re G[b][m](0));
+//   dF^T[0][m][d] += fs * bias_b[m] * norm * Esum[d]   (the bias part of H-hat = sum_d' C X + b Nx Ny at DC, quirk F1)
+__global__ void dc_terms_gram_kernel(const float* __restrict__ E, const float* __restrict__ Femb, const float* __restrict__ bias_b,
+                                     float* __restrict__ dFt, float* __restrict__ db, float* __restrict__ dp, int B, int dM, int dD,
+                                     float gs, float fs, float norm) {
+  extern __shared__ double dcg_sm[];  // Esum re / im [dD]
+  for (int d = threadIdx.x; d < dD; d += blockDim.x) {
+    double sr = 0.0, si = 0.0;
+    for (int b = 0; b < B; b++) { sr += (double)E[(size_t)b * 2 * dD + 2 * d]; si += (double)E[(size_t)b * 2 * dD + 2 * d + 1]; }
+    dcg_sm[2 * d] = sr; dcg_sm[2 * d + 1] = si;
+    dp[d] = (float)(sr * (double)gs);
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < dM; m += blockDim.x) {
+    double s = 0.0;
+    for (int d = 0; d < dD; d++) {
+      // F[d][m](0) = (emb[2d][2m], -emb[2d][2m+1]);  Re(conj(F) Esum) = Fr Er + Fi Ei
+      const double fr = (double)Femb[((size_t)2 * d) * 2 * dM + 2 * m], fi = -(double)Femb[((size_t)2 * d) * 2 * dM + 2 * m + 1];
+      s += fr * dcg_sm[2 * d] + fi * dcg_sm[2 * d + 1];
+      if (bias_b) {
+        const double corr = (double)bias_b[m] * (double)norm * (double)fs;
+        dFt[((size_t)m * dD + d) * 2] += (float)(corr * dcg_sm[2 * d]);
+        dFt[((size_t)m * dD + d) * 2 + 1] += (float)(corr * dcg_sm[2 * d + 1]);
+      }
+    }
+    db[m] = (float)(s * (double)gs);
+  }
+}
+
 struct TcOperand {
   const float* base;
   int rows, cols;  // memory [S][rows][cols]
@@ -872,6 +1027,58 @@ int launch_bm_resize(aefft_ctx* ctx, long long rowlen, int Nx, int Ny, int Nxs, 
 int launch_tc_dc_terms(aefft_ctx* ctx, int B, int dM, int dD, const float* G, const float* E, const float* bias_b, float* dFt,
                        float* db, float* dp, float gs, float fs, float corr_scale) {
   dc_terms_kernel<<<(dM + dD + 127) / 128, 128, 0, ctx->stream>>>(G, E, bias_b, dFt, db, dp, B, dM, dD, gs, fs, corr_scale);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
+// Whether the Gram form of the gradients pays: gram_grad_kernel runs on the CUDA cores (4 B dD^2 + 8 dM dD^2 FMA per bin), the
+// form it replaces streams 6 B (dD + dM) + 8 dD dM floats per bin through HBM instead of 4 B dD + 8 dD dM.
+static size_t gram_smem(int B, int dD, int dM) {
+  const int tr = dD >= 32 ? 4 : (dD >= 16 ? 2 : 1), ng = 256 / ((dD / tr) * (dD / tr));
+  const size_t ex = 2 * (size_t)B * dD, cf = 2 * (size_t)dD * dM, pp = ng > 1 ? (size_t)ng * dD * (dD + 1) : 0;
+  size_t m = ex > cf ? ex : cf;
+  if (pp > m) m = pp;
+  return ((size_t)dD * (dD + 1) + m) * sizeof(float2);
+}
+bool spec_tc_gram_pays(int B, int dD, int dM) {
+  if (getenv("AEFFT_NO_GRAM")) return false;
+  if (dD != 8 && dD != 16 && dD != 32 && dD != 64) return false;
+  const int no = dM * dD / 256;
+  if (dM * dD >= 256 ? (dM * dD % 256 != 0 || (no != 1 && no != 2 && no != 4 && no != 8 && no != 16)) : false) return false;
+  if (gram_smem(B, dD, dM) > 200 * 1024) return false;
+  if (getenv("AEFFT_FORCE_GRAM")) return true;
+  const double clk_new = (4.0 * B * dD * dD + 8.0 * dM * dD * dD) / 128.0;  // 128 FMA lanes per clock (measured at config 3:
+                                                                             // 0.53 vs 1.2 ms at 16 -> 32, 0.51 vs 0.68 ms at 32 -> 64)
+  const double clk_old = (6.0 * B * (dD + dM) - 4.0 * B * dD) * 4.0 / 15.6;  // 4.4 TB/s over 148 SMs at 1.9 GHz
+  return clk_new < clk_old;
+}
+
+int launch_tc_gram_grad(aefft_ctx* ctx, long long S, int B, int dM, int dD, const float* E, const float* X, const float* Cemb,
+                        const float* Femb, float gs, float* dCt, float* dFt) {
+  const size_t smem = gram_smem(B, dD, dM);
+  const int no = dM * dD >= 256 ? dM * dD / 256 : 1;
+  ProfScope prof(ctx, "spec_gram_grad", 8.0 * S * ((double)B * dD * dD + 2.0 * dM * dD * dD),
+                 4.0 * S * (4.0 * B * dD + 8.0 * dM * dD));
+#define AEFFT_GRAM(dd, n)                                                                                                    \
+  if (dD == dd && no == n) {                                                                                                 \
+    AE_TRY(ctx->ensure_dyn_smem((const void*)gram_grad_kernel<dd, n>, smem));                                                \
+    gram_grad_kernel<dd, n><<<(unsigned)S, 256, smem, ctx->stream>>>(E, X, Cemb, Femb, (float2*)dCt, (float2*)dFt, B, dM, gs); \
+    ctx->launches++;                                                                                                         \
+    AE_CUDA(cudaGetLastError());                                                                                             \
+    return AEFFT_OK;                                                                                                         \
+  }
+  AEFFT_GRAM(8, 1) AEFFT_GRAM(8, 2) AEFFT_GRAM(8, 4) AEFFT_GRAM(8, 8)
+  AEFFT_GRAM(16, 1) AEFFT_GRAM(16, 2) AEFFT_GRAM(16, 4) AEFFT_GRAM(16, 8) AEFFT_GRAM(16, 16)
+  AEFFT_GRAM(32, 1) AEFFT_GRAM(32, 2) AEFFT_GRAM(32, 4) AEFFT_GRAM(32, 8) AEFFT_GRAM(32, 16)
+  AEFFT_GRAM(64, 2) AEFFT_GRAM(64, 4) AEFFT_GRAM(64, 8) AEFFT_GRAM(64, 16)
+#undef AEFFT_GRAM
+  return AEFFT_ERR_UNSUPPORTED;
+}
+
+int launch_tc_dc_terms_gram(aefft_ctx* ctx, int B, int dM, int dD, const float* E, const float* Femb, const float* bias_b, float* dFt,
+                            float* db, float* dp, float gs, float fs, float norm) {
+  dc_terms_gram_kernel<<<1, 128, 2 * dD * sizeof(double), ctx->stream>>>(E, Femb, bias_b, dFt, db, dp, B, dM, dD, gs, fs, norm);
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
   return AEFFT_OK;

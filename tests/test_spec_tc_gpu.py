@@ -82,9 +82,10 @@ def test_backprop_fft_tc_vs_cuda_core_and_oracle(ctx, dims, B):
     """The tensor path against the CUDA-core path it replaces (AEFFT_NO_SPEC_TC=1) and against the fp64 oracle."""
     cs = _fft_case(51, *dims, B=B)
     runs = {}
-    for tag, env in (("tc", None), ("cc", "1")):
-        if env:
-            os.environ["AEFFT_NO_SPEC_TC"] = env
+    # tc: adjoint + two outer products (AEFFT_NO_GRAM); gram: both gradient spectra from Mg = sum_b E conj(X)
+    # (gram_grad_kernel, forced: by default the engine picks it where it is cheaper); cc: the CUDA-core path
+    for tag, env in (("tc", "AEFFT_NO_GRAM"), ("gram", "AEFFT_FORCE_GRAM"), ("cc", "AEFFT_NO_SPEC_TC")):
+        os.environ[env] = "1"
         try:
             w = {k: cs[k].copy() for k in "cfbp"}
             ctx.profile_enable(True)
@@ -92,16 +93,19 @@ def test_backprop_fft_tc_vs_cuda_core_and_oracle(ctx, dims, B):
             names = {r["name"] for r in ctx.profile_records()}
             ctx.profile_enable(False)
         finally:
-            os.environ.pop("AEFFT_NO_SPEC_TC", None)
+            os.environ.pop(env, None)
         runs[tag] = (w, trace, names)
     assert {"spec_contract_tc", "spec_outer_tc"} <= runs["tc"][2], runs["tc"][2]
+    assert "spec_gram_grad" not in runs["tc"][2] and "spec_gram_grad" in runs["gram"][2], runs["gram"][2]
     assert not any(n.endswith("_tc") for n in runs["cc"][2]), runs["cc"][2]
-    for k in "cfbp":
-        assert O.rel_l2(runs["tc"][0][k], runs["cc"][0][k]) < 2e-5, k
-    assert np.allclose(runs["tc"][1], runs["cc"][1], rtol=1e-4)
+    for tag in ("tc", "gram"):
+        for k in "cfbp":
+            assert O.rel_l2(runs[tag][0][k], runs["cc"][0][k]) < 2e-5, (tag, k)
+        assert np.allclose(runs[tag][1], runs["cc"][1], rtol=1e-4), tag
     if B <= 17:
         want = O.backprop_fft(cs["inp"], cs["inp"], cs["out"], cs["c"], cs["f"], cs["b"], cs["p"], 0.2, 0, 3)
-        assert np.allclose(runs["tc"][1], want["mse"], rtol=2e-4)
-        for k in "cfbp":
-            assert O.rel_l2(runs["tc"][0][k], want[k]) < 1e-4, k
-            assert O.rel_l2(runs["tc"][0][k].astype(np.float64) - cs[k], want[k] - cs[k]) < 2e-3, k
+        for tag in ("tc", "gram"):
+            assert np.allclose(runs[tag][1], want["mse"], rtol=2e-4), tag
+            for k in "cfbp":
+                assert O.rel_l2(runs[tag][0][k], want[k]) < 1e-4, (tag, k)
+                assert O.rel_l2(runs[tag][0][k].astype(np.float64) - cs[k], want[k] - cs[k]) < 2e-3, (tag, k)
