@@ -286,6 +286,20 @@ int launch_tc_forward(aefft_ctx* ctx, long long S, int B, int C, int O, const fl
 int launch_tc_adjoint(aefft_ctx* ctx, long long S, int B, int dD, int dM, const float* E, const float* Femb, float* G);
 int launch_tc_outer(aefft_ctx* ctx, long long S, int B, int nP, int nQ, const float* P, const float* Q, float scale, int conj_out,
                     float* out);
+// backprop_fft's iteration loop on per-bin Gram matrices (spec_gram.cu; expout == in): ONE pass over the frames per call
+bool spec_gram_loop_pays(int B, int dD, int dM, bool bin_major);
+int launch_gram_stats_bm(aefft_ctx* ctx, long long S, int B, int dD, const float* X, const float* O, int sub, float* Gx, float* M0,
+                         float* mse_out, double mse_scale, float* dcsum, int ncols, int col0, int Ny);
+int launch_gram_iter_bm(aefft_ctx* ctx, long long S, int B, int dD, int dM, const float* Gx, const float* M0, const float* Cemb,
+                        const float* Femb, int first, float gs, float gb, float norm, const float* dcsum, const float* bias_b,
+                        const float* bias_p, float* dCt, float* dFt, float* db, float* dp, float* mse_out, double mse_scale, int ncols,
+                        int col0, int Ny);
+int launch_gram_stats_ff(aefft_ctx* ctx, long long S, int B, int dD, const float2* X, const float2* O, float2* Gx, float2* M0,
+                         float* mse_out, double mse_scale, float* dcsum, int ncols, int col0, int Ny);
+int launch_gram_iter_ff(aefft_ctx* ctx, long long S, int B, int dD, int dM, const float2* Gx, const float2* M0, const float2* C,
+                        const float2* F, int first, float gs, float gb, float norm, const float* dcsum, const float* bias_b,
+                        const float* bias_p, float2* dC, float2* dF, float* db, float* dp, float* mse_out, double mse_scale, int ncols,
+                        int col0, int Ny);
 // Gram form of the gradients (spec_tc.cu): both gradient spectra of a bin from Mg = sum_b E conj(X), E / X bin-major
 bool spec_tc_gram_pays(int B, int dD, int dM);
 int launch_tc_gram_grad(aefft_ctx* ctx, long long S, int B, int dM, int dD, const float* E, const float* X, const float* Cemb,

@@ -339,6 +339,11 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
   }
   // <= 4 input channels (the image side): one fused kernel per iteration, H / G / E never touch HBM (spec_small.cu)
   const bool use_small = !use_tc && spec_small_eligible(dD, dM) && n_iter > 0;
+  // The autoencoder case expout == in: the whole iteration loop runs on per-bin Gram matrices of the frames, formed in ONE
+  // pass (spec_gram.cu); an iteration then touches kernel-spectrum-sized data only.
+  const bool same_target = !have_real || expout == in;
+  const bool gram_tc = use_tc && same_target && spec_gram_loop_pays((int)B, dD, dM, true);
+  const bool gram_ff = use_small && same_target && spec_gram_loop_pays((int)B, dD, dM, false);
   if (!use_tc) {  // the bins-fastest CUDA-core path keeps the gradient spectra, and H, G unless fused
     if (!use_small) {
       AE_TRY(ctx->getT("bpf_H", nHs, &q.H));
@@ -423,7 +428,7 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
   const float* bias_b = own_dc ? db_w : nullptr;
   const float* bias_p = own_dc ? dp_w : nullptr;
   const double mse_scale = 1.0 / ((double)dD * Nx * Ny) / (2.0 * dM * Nx * Ny) / (double)B;
-  if (!have_bm) {
+  if (!have_bm && !gram_ff) {
     AE_TRY(launch_spec_mse(ctx, B, dD, dM, Nx, Ny, Xt, q.O, q.mse, col0, ncols));  // "mse fft:" (:1440)
     if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse, 1));
   }
@@ -436,14 +441,14 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
   // the bin-major gradient spectra.  Callers that pass spectra caches (cfreq / ffreq) keep the bins-fastest path, whose
   // first iteration consumes those caches as they are.
   if (use_tc) {
-    float *Xb = nullptr, *Xtb, *Eb, *Hb, *Gb = nullptr, *Cemb, *Femb, *dCt, *dFt;
+    float *Xb = nullptr, *Xtb, *Eb = nullptr, *Hb = nullptr, *Gb = nullptr, *Cemb, *Femb, *dCt, *dFt;
     // Gram form (spec_tc.cu: gram_grad_kernel): both gradient spectra from Mg = sum_b E conj(X); no G, and the hidden
     // spectrum is needed by the re-forward only
     const bool gram = spec_tc_gram_pays((int)B, dD, dM);
     if (!have_bm) AE_TRY(ctx->getT("tc_Xb", 2 * nXs, &Xb));
-    AE_TRY(ctx->getT("tc_Eb", 2 * nXs, &Eb));
-    AE_TRY(ctx->getT("tc_Hb", 2 * nHs, &Hb));
-    if (!gram) AE_TRY(ctx->getT("tc_Gb", 2 * nHs, &Gb));
+    if (!gram_tc || !have_bm) AE_TRY(ctx->getT("tc_Eb", 2 * nXs, &Eb));
+    if (!gram_tc) AE_TRY(ctx->getT("tc_Hb", 2 * nHs, &Hb));
+    if (!gram && !gram_tc) AE_TRY(ctx->getT("tc_Gb", 2 * nHs, &Gb));
     AE_TRY(ctx->getT("tc_Cemb", 4 * nKS, &Cemb));
     AE_TRY(ctx->getT("tc_Femb", 4 * nKS, &Femb));
     AE_TRY(ctx->getT("tc_dCt", 2 * nKS, &dCt));
@@ -452,7 +457,7 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
       // the layer spectra are bin-major already: E = O - X and the "mse fft:" value in one pass
       Xb = const_cast<float*>(inp.Xbm);
       Xtb = Xb;
-      AE_TRY(launch_bm_sub_mse(ctx, S, (long long)B * 2 * dD, inp.Obm, inp.Xbm, Eb, q.mse, mse_scale, ncols, col0, Ny));
+      if (!gram_tc) AE_TRY(launch_bm_sub_mse(ctx, S, (long long)B * 2 * dD, inp.Obm, inp.Xbm, Eb, q.mse, mse_scale, ncols, col0, Ny));
     } else {
       AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, q.X, nullptr, (float2*)Xb));
       Xtb = Xb;
@@ -463,6 +468,42 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
       AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, q.O, Xt, (float2*)Eb));  // E = O - Xt of the caller's `out`
     }
     AE_TRY(launch_kernel_spectrum_emb(ctx, dD, dM, Nk, Nl, Nx, Ny, col0, ncols, df_w, Femb));
+    if (gram_tc) {
+      float *Gx, *M0, *dcs;
+      AE_TRY(ctx->getT("gr_Gx", (size_t)2 * S * dD * dD, &Gx));
+      AE_TRY(ctx->getT("gr_M0", (size_t)2 * S * dD * dD, &M0));
+      AE_TRY(ctx->getT("gr_dc", (size_t)4 * dD, &dcs));
+      // the one pass over the frames: Gx, M0 (and "mse fft:" when the caller's spectra are bin-major)
+      if (have_bm)
+        AE_TRY(launch_gram_stats_bm(ctx, S, (int)B, dD, inp.Xbm, inp.Obm, 1, Gx, M0, q.mse, mse_scale, own_dc ? dcs : nullptr, ncols,
+                                    col0, Ny));
+      else
+        AE_TRY(launch_gram_stats_bm(ctx, S, (int)B, dD, Xb, Eb, 0, Gx, M0, nullptr, 0.0, own_dc ? dcs : nullptr, ncols, col0, Ny));
+      AE_TRY(launch_kernel_spectrum_emb(ctx, dM, dD, Nk, Nl, Nx, Ny, col0, ncols, dc_w, Cemb));
+      const float gb = (float)((double)norm / (Norm * (double)B));
+      for (int n = 0; n <= n_iter; n++) {
+        // iteration n: mse of the current kernels (n >= 1: what the reference prints after update n, :1463) and the gradients
+        const bool last = n == n_iter;
+        AE_TRY(launch_gram_iter_bm(ctx, S, (int)B, dD, dM, Gx, M0, Cemb, Femb, n == 0, gscale, gb, norm, own_dc ? dcs : nullptr, bias_b,
+                                   bias_p, last ? nullptr : dCt, last ? nullptr : dFt, q.db, q.dp, n ? q.mse + n : nullptr, mse_scale,
+                                   ncols, col0, Ny));
+        if (n && sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse + n, 1));
+        if (last) break;
+        if (!own_dc) AE_CUDA(cudaMemsetAsync(q.db, 0, (size_t)(dM + dD) * sizeof(float), st));
+        AE_TRY(launch_binmajor_to_taps(ctx, dM, dD, 0, Nk, Nl, Nx, Ny, col0, ncols, (const float2*)dCt, q.taps, 1.f));
+        AE_TRY(launch_binmajor_to_taps(ctx, dM, dD, 1, Nk, Nl, Nx, Ny, col0, ncols, (const float2*)dFt, q.taps + nC, 1.f));
+        const bool fold_div = sharded && maxdiff;
+        if (fold_div) {
+          AE_TRY(launch_gradient_diff(ctx, dM, dD, Nk, Nl, dc_w, df_w, db_w, dp_w, q.div, srank, world));
+          AE_TRY(launch_axpby(ctx, q.taps, q.div, 1.f, -10.f, (long long)(2 * nC + dM + dD)));
+        }
+        AE_TRY(reduce_over_devices(q.taps, (int64_t)(2 * nC + dM + dD)));
+        AE_TRY(launch_fft_update(ctx, dM, dD, Nk, Nl, dc_w, df_w, db_w, dp_w, q.taps, q.taps + nC, q.db, q.dp, q.Dc, q.Df, q.Db,
+                                 q.Dp, del, fold_div ? 0 : maxdiff, q.div));
+        AE_TRY(launch_kernel_spectrum_emb(ctx, dM, dD, Nk, Nl, Nx, Ny, col0, ncols, dc_w, Cemb));
+        AE_TRY(launch_kernel_spectrum_emb(ctx, dD, dM, Nk, Nl, Nx, Ny, col0, ncols, df_w, Femb));
+      }
+    } else {
     // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1);
     // the resident net hands over the hidden layer its forward just computed with these very kernels
     const float* Hcur = inp.Hbm;
@@ -509,7 +550,38 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
                                q.mse + n + 1, mse_scale, ncols, col0, Ny));
       if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse + n + 1, 1));
     }
+    }  // !gram_tc
     if (!sharded && !inp.resident) {  // the bins-fastest spectra of the trained kernels, for the export below
+      AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C, col0, ncols));
+      AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F, col0, ncols));
+    }
+  } else if (gram_ff) {
+    float2 *Gx, *M0;
+    float* dcs;
+    AE_TRY(ctx->getT("gr_Gx", (size_t)S * dD * dD, &Gx));
+    AE_TRY(ctx->getT("gr_M0", (size_t)S * dD * dD, &M0));
+    AE_TRY(ctx->getT("gr_dc", (size_t)4 * dD, &dcs));
+    // the one pass over the frames: Gx, M0 and "mse fft:" (:1440)
+    AE_TRY(launch_gram_stats_ff(ctx, S, (int)B, dD, q.X, q.O, Gx, M0, q.mse, mse_scale, own_dc ? dcs : nullptr, ncols, col0, Ny));
+    if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse, 1));
+    const float gb = (float)((double)norm / (Norm * (double)B));
+    for (int n = 0; n <= n_iter; n++) {
+      const bool last = n == n_iter;
+      AE_TRY(launch_gram_iter_ff(ctx, S, (int)B, dD, dM, Gx, M0, q.C, q.F, n == 0, gscale, gb, norm, own_dc ? dcs : nullptr, bias_b,
+                                 bias_p, last ? nullptr : q.dCF, last ? nullptr : q.dCF + nKS, q.db, q.dp, n ? q.mse + n : nullptr,
+                                 mse_scale, ncols, col0, Ny));
+      if (n && sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse + n, 1));
+      if (last) break;
+      if (!own_dc) AE_CUDA(cudaMemsetAsync(q.db, 0, (size_t)(dM + dD) * sizeof(float), st));
+      AE_TRY(spectrum_taps_dev(ctx, 2 * (int64_t)dM * dD, Nk, Nl, Nx, Ny, q.dCF, q.work, q.img, q.taps, 1.f, col0, ncols));
+      const bool fold_div = sharded && maxdiff;
+      if (fold_div) {
+        AE_TRY(launch_gradient_diff(ctx, dM, dD, Nk, Nl, dc_w, df_w, db_w, dp_w, q.div, srank, world));
+        AE_TRY(launch_axpby(ctx, q.taps, q.div, 1.f, -10.f, (long long)(2 * nC + dM + dD)));
+      }
+      AE_TRY(reduce_over_devices(q.taps, (int64_t)(2 * nC + dM + dD)));
+      AE_TRY(launch_fft_update(ctx, dM, dD, Nk, Nl, dc_w, df_w, db_w, dp_w, q.taps, q.taps + nC, q.db, q.dp, q.Dc, q.Df, q.Db,
+                               q.Dp, del, fold_div ? 0 : maxdiff, q.div));
       AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, dc_w, q.img, q.C, col0, ncols));
       AE_TRY(kernel_spectrum_dev(ctx, (int64_t)dM * dD, Nk, Nl, Nx, Ny, df_w, q.img, q.F, col0, ncols));
     }

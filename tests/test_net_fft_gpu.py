@@ -105,9 +105,16 @@ def test_net_fft_step_vs_oracle_and_capi(ctx, cfg, maxdiff):
         net.close()
 
 
-def test_net_fft_step_uses_tensor_cores_and_no_layer_transforms(ctx):
-    """At the c3 channel widths the step runs the tcgen05 contraction for pairs 1 and 2 and transforms only the frames
-    (one R2C) and the reconstruction (one C2R): no per-layer C2R/R2C round trips."""
+@pytest.mark.parametrize("gram_loop", [True, False])
+def test_net_fft_step_uses_tensor_cores_and_no_layer_transforms(ctx, gram_loop, monkeypatch):
+    """At the c3 channel widths the forward runs the tcgen05 contraction for pairs 1 and 2 and transforms only the frames
+    (one R2C) and the reconstruction (one C2R): no per-layer C2R/R2C round trips.  Training: by default every pair's iteration
+    loop runs on the per-bin Gram matrices (spec_gram.cu: one statistics pass over the frames per pair, then n_iter + 1
+    kernel-spectrum-sized evaluations); with AEFFT_NO_GRAM_LOOP / AEFFT_NO_GRAM the per-frame forms (tensor-core pairs:
+    adjoint + 2 outer products + 2 re-forward contractions per iteration)."""
+    if not gram_loop:
+        monkeypatch.setenv("AEFFT_NO_GRAM_LOOP", "1")
+        monkeypatch.setenv("AEFFT_NO_GRAM", "1")
     net, *_ = make_net(ctx, 3, 64, 64, [16, 32, 64], [2, 2, 2], 16)
     try:
         x = O.synth_frames(3, 16, 3, 64, 64)
@@ -116,9 +123,12 @@ def test_net_fft_step_uses_tensor_cores_and_no_layer_transforms(ctx):
         net.fft_step(x, n_iter=1, fft_l=0, want_mse=False)
         rec = {r["name"]: r["launches"] for r in ctx.profile_records()}
         ctx.profile_enable(False)
-        # per tensor-core pair: 2 forward + 2 re-forward contractions, and either adjoint + 2 outer products or the Gram kernel
-        gram = rec.get("spec_gram_grad", 0)
-        assert rec.get("spec_contract_tc", 0) == 10 - gram and rec.get("spec_outer_tc", 0) == 4 - 2 * gram, rec
+        if gram_loop:
+            assert rec.get("spec_contract_tc", 0) == 4 and rec.get("spec_outer_tc", 0) == 0, rec
+            assert rec.get("spec_gram_stats", 0) == 3 and rec.get("spec_gram_iter", 0) == 6, rec
+        else:
+            assert rec.get("spec_contract_tc", 0) == 10 and rec.get("spec_outer_tc", 0) == 4, rec
+            assert "spec_gram_stats" not in rec, rec
         assert rec.get("fft_rows_r2c", 0) == 1 and rec.get("fft_rows_c2r", 0) == 1, rec
     finally:
         net.close()

@@ -84,8 +84,11 @@ def test_backprop_fft_tc_vs_cuda_core_and_oracle(ctx, dims, B):
     runs = {}
     # tc: adjoint + two outer products (AEFFT_NO_GRAM); gram: both gradient spectra from Mg = sum_b E conj(X)
     # (gram_grad_kernel, forced: by default the engine picks it where it is cheaper); cc: the CUDA-core path
-    for tag, env in (("tc", "AEFFT_NO_GRAM"), ("gram", "AEFFT_FORCE_GRAM"), ("cc", "AEFFT_NO_SPEC_TC")):
-        os.environ[env] = "1"
+    # loop: the whole iteration loop on per-bin Gram matrices (spec_gram.cu), forced where the cost model would not pick it
+    for tag, envs in (("tc", ("AEFFT_NO_GRAM", "AEFFT_NO_GRAM_LOOP")), ("gram", ("AEFFT_FORCE_GRAM", "AEFFT_NO_GRAM_LOOP")),
+                      ("loop", ("AEFFT_FORCE_GRAM_LOOP",)), ("cc", ("AEFFT_NO_SPEC_TC", "AEFFT_NO_GRAM_LOOP"))):
+        for env in envs:
+            os.environ[env] = "1"
         try:
             w = {k: cs[k].copy() for k in "cfbp"}
             ctx.profile_enable(True)
@@ -93,18 +96,20 @@ def test_backprop_fft_tc_vs_cuda_core_and_oracle(ctx, dims, B):
             names = {r["name"] for r in ctx.profile_records()}
             ctx.profile_enable(False)
         finally:
-            os.environ.pop(env, None)
+            for env in envs:
+                os.environ.pop(env, None)
         runs[tag] = (w, trace, names)
     assert {"spec_contract_tc", "spec_outer_tc"} <= runs["tc"][2], runs["tc"][2]
     assert "spec_gram_grad" not in runs["tc"][2] and "spec_gram_grad" in runs["gram"][2], runs["gram"][2]
+    assert {"spec_gram_stats", "spec_gram_iter"} <= runs["loop"][2] and "spec_outer_tc" not in runs["loop"][2], runs["loop"][2]
     assert not any(n.endswith("_tc") for n in runs["cc"][2]), runs["cc"][2]
-    for tag in ("tc", "gram"):
+    for tag in ("tc", "gram", "loop"):
         for k in "cfbp":
             assert O.rel_l2(runs[tag][0][k], runs["cc"][0][k]) < 2e-5, (tag, k)
         assert np.allclose(runs[tag][1], runs["cc"][1], rtol=1e-4), tag
     if B <= 17:
         want = O.backprop_fft(cs["inp"], cs["inp"], cs["out"], cs["c"], cs["f"], cs["b"], cs["p"], 0.2, 0, 3)
-        for tag in ("tc", "gram"):
+        for tag in ("tc", "gram", "loop"):
             assert np.allclose(runs[tag][1], want["mse"], rtol=2e-4), tag
             for k in "cfbp":
                 assert O.rel_l2(runs[tag][0][k], want[k]) < 1e-4, (tag, k)
