@@ -276,6 +276,8 @@ bool spec_tc_eligible(int dD, int dM, int Nk, int Nl);
 // [R][S] complex (bins fastest) -> [S][R] complex, optionally in0 - in1
 int launch_to_binmajor(aefft_ctx* ctx, long long R, long long S, const float2* in0, const float2* in1, float2* out);
 // emb[w][2r+a][2c+b] for the R x C kernels `taps` [R][C][Nk][Nl] on the slab [col0, col0+ncols) (ncols <= 0: whole half spectrum)
+int launch_kernel_spectrum_emb_pooled(aefft_ctx* ctx, int R, int C, int Nk, int Nl, int Nx, int Ny, int Nxm, int Nym,
+                                      const float* taps, float* emb);
 int launch_kernel_spectrum_emb(aefft_ctx* ctx, int R, int C, int Nk, int Nl, int Nx, int Ny, int col0, int ncols, const float* taps,
                                float* emb);
 int launch_binmajor_to_taps(aefft_ctx* ctx, int R, int C, int transpose, int Nk, int Nl, int Nx, int Ny, int col0, int ncols,
@@ -344,6 +346,8 @@ struct FftTrainInputs {
   const float *Xbm = nullptr, *Obm = nullptr;  // device spectra, bin-major [bin][B][2 dD]         (expout = in)
   const float* Hbm = nullptr;                  // optional with Xbm: conv_k(X; c, b) of the CURRENT kernels, bin-major
                                                // [bin][B][2 dM] (the forward's hidden layer): saves its recomputation
+  const float *Cemb = nullptr, *Femb = nullptr; // optional with Xbm: embedded bin-major spectra of the CURRENT c / f (what the
+                                               // forward generated for its two convs of this pair): not generated again
   bool resident = false;      // c,f,b,p are the device-resident masters: no export through the spectra, and no stream
                               // synchronisation unless a host trace is requested
   float* trace_dev = nullptr; // device destination of the mse trace (n_iter + 1 floats), optional

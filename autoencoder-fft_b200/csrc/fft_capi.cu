@@ -467,7 +467,12 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
       }
       AE_TRY(launch_to_binmajor(ctx, (long long)B * dD, S, q.O, Xt, (float2*)Eb));  // E = O - Xt of the caller's `out`
     }
-    AE_TRY(launch_kernel_spectrum_emb(ctx, dD, dM, Nk, Nl, Nx, Ny, col0, ncols, df_w, Femb));
+    // spectra of the current kernels: generated here unless the caller (the resident net's forward) just did
+    const float *Cemb0 = inp.Cemb, *Femb0 = inp.Femb;
+    if (!Femb0) {
+      AE_TRY(launch_kernel_spectrum_emb(ctx, dD, dM, Nk, Nl, Nx, Ny, col0, ncols, df_w, Femb));
+      Femb0 = Femb;
+    }
     if (gram_tc) {
       float *Gx, *M0, *dcs;
       AE_TRY(ctx->getT("gr_Gx", (size_t)2 * S * dD * dD, &Gx));
@@ -479,12 +484,16 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
                                     col0, Ny));
       else
         AE_TRY(launch_gram_stats_bm(ctx, S, (int)B, dD, Xb, Eb, 0, Gx, M0, nullptr, 0.0, own_dc ? dcs : nullptr, ncols, col0, Ny));
-      AE_TRY(launch_kernel_spectrum_emb(ctx, dM, dD, Nk, Nl, Nx, Ny, col0, ncols, dc_w, Cemb));
+      if (!Cemb0) {
+        AE_TRY(launch_kernel_spectrum_emb(ctx, dM, dD, Nk, Nl, Nx, Ny, col0, ncols, dc_w, Cemb));
+        Cemb0 = Cemb;
+      }
       const float gb = (float)((double)norm / (Norm * (double)B));
       for (int n = 0; n <= n_iter; n++) {
         // iteration n: mse of the current kernels (n >= 1: what the reference prints after update n, :1463) and the gradients
         const bool last = n == n_iter;
-        AE_TRY(launch_gram_iter_bm(ctx, S, (int)B, dD, dM, Gx, M0, Cemb, Femb, n == 0, gscale, gb, norm, own_dc ? dcs : nullptr, bias_b,
+        AE_TRY(launch_gram_iter_bm(ctx, S, (int)B, dD, dM, Gx, M0, n ? Cemb : Cemb0, n ? Femb : Femb0, n == 0, gscale, gb, norm,
+                                   own_dc ? dcs : nullptr, bias_b,
                                    bias_p, last ? nullptr : dCt, last ? nullptr : dFt, q.db, q.dp, n ? q.mse + n : nullptr, mse_scale,
                                    ncols, col0, Ny));
         if (n && sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse + n, 1));
@@ -504,6 +513,7 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
         AE_TRY(launch_kernel_spectrum_emb(ctx, dD, dM, Nk, Nl, Nx, Ny, col0, ncols, df_w, Femb));
       }
     } else {
+    if (inp.Femb) AE_TRY(launch_kernel_spectrum_emb(ctx, dD, dM, Nk, Nl, Nx, Ny, col0, ncols, df_w, Femb));  // this loop rewrites its own
     // H of the current kernels (the reference recomputes it inside gradient_k_io as H-hat, without the /dM: quirk F1);
     // the resident net hands over the hidden layer its forward just computed with these very kernels
     const float* Hcur = inp.Hbm;

@@ -30,6 +30,7 @@ struct PairState {
 struct SpecL {
   float* p = nullptr;
   int bin_major = 0;
+  bool skipped = false;  // the last forward (fft_l <= 0) fused this layer away: its spectrum was not produced
 };
 
 }  // namespace aefft

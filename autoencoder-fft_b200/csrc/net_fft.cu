@@ -116,8 +116,12 @@ int conv_spec(aefft_net* net, int n, int li, int lo) {
   const long long S = (long long)A.Nx * (A.Ny / 2 + 1);
   const float norm = (float)A.Nx * (float)A.Ny;
   if (net->spec[li].bin_major) {
+    // one embedded-spectrum buffer per conv: the training of the pair right after the forward (aefft_net_fft_step) takes
+    // them over instead of generating the same spectra again
     float* emb;
-    AE_TRY(ctx->getT("nf_emb", (size_t)4 * c.dM * c.dD * S, &emb));
+    char name[32];
+    snprintf(name, sizeof(name), "nf_emb_%d", n);
+    AE_TRY(ctx->getT(name, (size_t)4 * c.dM * c.dD * S, &emb));
     AE_TRY(launch_kernel_spectrum_emb(ctx, c.dM, c.dD, c.Nk, c.Nl, A.Nx, A.Ny, 0, 0, c.c, emb));
     return launch_tc_forward(ctx, S, (int)net->B, c.dD, c.dM, net->spec[li].p, emb, 1.f / (float)c.dM, c.b, norm, nullptr,
                              net->spec[lo].p, nullptr, 0.0, 0, 0, 0);
@@ -164,6 +168,24 @@ int conv_then_pool(aefft_net* net, int n, int li) {
   return launch_spec_conv_reg_resized(ctx, net->B, c.dD, c.dM, A.Nx, A.Ny, Z.Nx, Z.Ny, true, net->spec[li + 2].bin_major,
                                       (const float2*)net->spec[li].p, kspec, c.b, (float)A.Nx * (float)A.Ny, 1.f / (float)c.dM,
                                       (float2*)net->spec[li + 2].p);
+}
+// the same on a tensor-core level: the input spectrum is cropped first (bin-major rows), the kernel spectra are evaluated on
+// the kept bins, and the contraction runs on a quarter of the bins.  Only when the pair's training does not want the hidden
+// spectrum at full resolution (the Gram loop, spec_gram.cu, reads the pair's in / out spectra only).
+int conv_then_pool_tc(aefft_net* net, int n, int li) {
+  aefft_ctx* ctx = net->ctx;
+  const ConvL& c = net->convs[n];
+  const LayerL &A = net->layers[li], &Z = net->layers[li + 2];
+  AE_ARG(A.D == c.dD && Z.D == c.dM && Z.Nx < A.Nx && Z.Ny < A.Ny && net->spec[li].bin_major && net->spec[li + 2].bin_major);
+  const long long Sz = (long long)Z.Nx * (Z.Ny / 2 + 1);
+  float *xs, *emb;
+  AE_TRY(ctx->getT("nf_tmp", (size_t)net->B * 2 * c.dD * Sz, &xs));
+  AE_TRY(ctx->getT("nf_emb_pool", (size_t)4 * c.dM * c.dD * Sz, &emb));
+  const int rc = launch_kernel_spectrum_emb_pooled(ctx, c.dM, c.dD, c.Nk, c.Nl, A.Nx, A.Ny, Z.Nx, Z.Ny, c.c, emb);
+  if (rc != AEFFT_OK) return rc;
+  AE_TRY(launch_bm_resize(ctx, 2 * net->B * c.dD, A.Nx, A.Ny, Z.Nx, Z.Ny, net->spec[li].p, xs));
+  return launch_tc_forward(ctx, Sz, (int)net->B, c.dD, c.dM, xs, emb, 1.f / (float)c.dM, c.b, (float)A.Nx * (float)A.Ny, nullptr,
+                           net->spec[li + 2].p, nullptr, 0.0, 0, 0, 0);
 }
 // decoder: (small) spec[ls] --up-sampling, conv n--> spec[ls + 2]
 int unpool_then_conv(aefft_net* net, int n, int ls) {
@@ -234,11 +256,25 @@ int forward(aefft_net* net, int loc, const float* frames, int fft_l) {
       next_in_done = false;
       if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 1));
       const LayerL &Lc = net->layers[2 * n + 2], &Ln = net->layers[2 * n + 3];
-      if (fft_l <= 0 && n + 1 < N / 2 && Ln.Nx < Lc.Nx && Ln.Ny < Lc.Ny && Ln.Nx >= 2 && Ln.Ny >= 2 &&
-          fusable_conv(net, n, 2 * n + 1)) {
-        AE_TRY(conv_then_pool(net, n, 2 * n + 1));  // conv_fft :1356 + the next pool_fft :1346, on the kept bins only
-        next_in_done = true;
-        continue;
+      net->spec[2 * n + 2].skipped = false;
+      if (fft_l <= 0 && n + 1 < N / 2 && Ln.Nx < Lc.Nx && Ln.Ny < Lc.Ny && Ln.Nx >= 2 && Ln.Ny >= 2) {
+        if (fusable_conv(net, n, 2 * n + 1)) {
+          AE_TRY(conv_then_pool(net, n, 2 * n + 1));  // conv_fft :1356 + the next pool_fft :1346, on the kept bins only
+          net->spec[2 * n + 2].skipped = true;
+          next_in_done = true;
+          continue;
+        }
+        const ConvL& cc = net->convs[n];
+        if (net->spec[2 * n + 1].bin_major && net->spec[2 * n + 3].bin_major && !getenv("AEFFT_NO_FWD_FUSE") &&
+            spec_gram_loop_pays((int)net->B, cc.dD, cc.dM, true)) {
+          const int rc = conv_then_pool_tc(net, n, 2 * n + 1);
+          if (rc == AEFFT_OK) {
+            net->spec[2 * n + 2].skipped = true;
+            next_in_done = true;
+            continue;
+          }
+          if (rc != AEFFT_ERR_UNSUPPORTED) return rc;
+        }
       }
       AE_TRY(conv_spec(net, n, 2 * n + 1, 2 * n + 2));  // conv_fft :1356
       if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 2));
@@ -351,7 +387,22 @@ static int train_pair_spectra(aefft_net* net, int n, float del0, int maxdiff, in
   }
   if (net->spec[li].bin_major) {
     inp.Xbm = net->spec[li].p; inp.Obm = net->spec[lo].p;
-    if (fresh_forward) inp.Hbm = net->spec[li + 1].p;  // hin = conv_k(in; c, b) with the kernels as they are now
+    if (fresh_forward) {
+      // what the forward just computed with the kernels as they are now: the hidden spectrum hin = conv_k(in; c, b) and the
+      // embedded spectra of c and f (the encoder side only when that conv ran at full resolution)
+      char name[32];
+      const size_t ne = (size_t)4 * e.dM * e.dD * L.Nx * (L.Ny / 2 + 1);
+      float* buf = nullptr;
+      if (!net->spec[li + 1].skipped) {
+        inp.Hbm = net->spec[li + 1].p;
+        snprintf(name, sizeof(name), "nf_emb_%d", n);
+        AE_TRY(ctx->getT(name, ne, &buf));
+        inp.Cemb = buf;
+      }
+      snprintf(name, sizeof(name), "nf_emb_%d", N - 1 - n);
+      AE_TRY(ctx->getT(name, ne, &buf));
+      inp.Femb = buf;
+    }
   } else { inp.Xs = (const float2*)net->spec[li].p; inp.Os = (const float2*)net->spec[lo].p; }
   return backprop_fft_run(ctx, AEFFT_DEVICE, net->B, e.dD, e.dM, L.Nx, L.Ny, e.Nk, e.Nl, inp, nullptr, e.c, nullptr, d.c, e.b, d.b,
                           del0, maxdiff, n_iter, trace_host);

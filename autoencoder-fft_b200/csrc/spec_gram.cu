@@ -53,17 +53,21 @@ __device__ __forceinline__ double block_sum_256(double v, double* red) {
   return s;
 }
 
-__global__ void gram_final_kernel(const double* __restrict__ part, long long n, double scale, float* __restrict__ out) {
-  __shared__ double red[256];
+__global__ void __launch_bounds__(1024) gram_final_kernel(const double* __restrict__ part, long long n, double scale,
+                                                          float* __restrict__ out) {
+  __shared__ double red[32];
   double s = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
-  red[threadIdx.x] = s;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += part[i];  // fixed assignment and order: deterministic
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  for (int h = 128; h > 0; h >>= 1) {
-    if (threadIdx.x < h) red[threadIdx.x] += red[threadIdx.x + h];
-    __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *out = (float)(s * scale);
   }
-  if (threadIdx.x == 0) *out = (float)(red[0] * scale);
 }
 
 // ------------------------------------------------------------------------------------------------ family A: bin-major
@@ -555,7 +559,7 @@ bool spec_gram_loop_pays(int B, int dD, int dM, bool bin_major) {
 }
 
 int launch_gram_final(aefft_ctx* ctx, const double* part, long long n, double scale, float* out) {
-  gram_final_kernel<<<1, 256, 0, ctx->stream>>>(part, n, scale, out);
+  gram_final_kernel<<<1, 1024, 0, ctx->stream>>>(part, n, scale, out);
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
   return AEFFT_OK;

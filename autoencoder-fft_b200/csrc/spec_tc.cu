@@ -425,19 +425,24 @@ __global__ void __launch_bounds__(256) kernel_spectrum_emb_kernel_t(const float*
 // 5 taps instead of 50); a CTA covers KS_COLS columns x KS_ROWS rows.
 constexpr int KS_COLS = 4, KS_ROWS = 32;
 template <int NK, int NL>
+// Nxm > 0: the spectrum is evaluated on the bins that a spectral pooling to Nxm rows x ncols columns keeps (resize :87-157:
+// rows i < Nxm/2 -> i, Nxm/2 -> Nx/2, above -> i + Nx - Nxm; columns j < ncols-1 -> j, ncols-1 -> Ny/2), written on that grid.
 __global__ void __launch_bounds__(256) kernel_spectrum_emb_sep_kernel(const float* __restrict__ taps, float* __restrict__ emb, int R,
                                                                       int C, int Nx, int Ny, int ncols, int col0,
                                                                       const float2* __restrict__ twx,
-                                                                      const float2* __restrict__ twy) {
+                                                                      const float2* __restrict__ twy, int Nxm) {
   __shared__ float2 ex[KS_ROWS][NK], ey[KS_COLS][NL];
   const int wl0 = blockIdx.x * KS_COLS, wx0 = blockIdx.z * KS_ROWS;
+  const int rows = Nxm > 0 ? Nxm : Nx;
   for (int i = threadIdx.x; i < KS_ROWS * NK; i += blockDim.x) {
     const int rr = i / NK, k = i - rr * NK, wx = wx0 + rr;
-    ex[rr][k] = wx < Nx ? twx[(wx * ((k - NK / 2) & (Nx - 1))) & (Nx - 1)] : make_float2(0.f, 0.f);
+    const int wxb = Nxm > 0 ? (wx < Nxm / 2 ? wx : (wx == Nxm / 2 ? Nx / 2 : wx + Nx - Nxm)) : wx;
+    ex[rr][k] = wx < rows ? twx[(wxb * ((k - NK / 2) & (Nx - 1))) & (Nx - 1)] : make_float2(0.f, 0.f);
   }
   for (int i = threadIdx.x; i < KS_COLS * NL; i += blockDim.x) {
     const int cc = i / NL, l = i - cc * NL, wy = col0 + wl0 + cc;
-    ey[cc][l] = wl0 + cc < ncols ? twy[(wy * ((l - NL / 2) & (Ny - 1))) & (Ny - 1)] : make_float2(0.f, 0.f);
+    const int wyb = Nxm > 0 ? (wy < ncols - 1 ? wy : Ny / 2) : wy;
+    ey[cc][l] = wl0 + cc < ncols ? twy[(wyb * ((l - NL / 2) & (Ny - 1))) & (Ny - 1)] : make_float2(0.f, 0.f);
   }
   __syncthreads();
   const int e = blockIdx.y * blockDim.x + threadIdx.x;
@@ -446,7 +451,7 @@ __global__ void __launch_bounds__(256) kernel_spectrum_emb_sep_kernel(const floa
   float tp[NK * NL];
 #pragma unroll
   for (int t = 0; t < NK * NL; t++) tp[t] = __ldg(taps + (size_t)e * (NK * NL) + t);
-  const int nrows = min(KS_ROWS, Nx - wx0);
+  const int nrows = min(KS_ROWS, rows - wx0);
   for (int cc = 0; cc < KS_COLS && wl0 + cc < ncols; cc++) {
     float2 u[NK];
 #pragma unroll
@@ -842,6 +847,25 @@ int launch_to_binmajor(aefft_ctx* ctx, long long R, long long S, const float2* i
   return AEFFT_OK;
 }
 
+// the embedded spectra at resolution (Nx, Ny) on the bins a spectral pooling to (Nxm, Nym) keeps: [Nxm * (Nym/2+1)][2R][2C]
+int launch_kernel_spectrum_emb_pooled(aefft_ctx* ctx, int R, int C, int Nk, int Nl, int Nx, int Ny, int Nxm, int Nym,
+                                      const float* taps, float* emb) {
+  const float2 *twx, *twy;
+  AE_TRY(get_twiddles(ctx, Nx, &twx));
+  AE_TRY(get_twiddles(ctx, Ny, &twy));
+  if (!(Nk == Nl && (Nk == 5 || Nk == 3 || Nk == 7)) || Nxm >= Nx || Nym >= Ny || Nxm < 2 || Nym < 2) return AEFFT_ERR_UNSUPPORTED;
+  const int ncols = Nym / 2 + 1;
+  const long long S = (long long)Nxm * ncols;
+  ProfScope prof(ctx, "kernel_spectrum_emb", 4.0 * S * R * C * 2.0 * Nk, 16.0 * S * R * C);
+  dim3 g2((unsigned)((ncols + KS_COLS - 1) / KS_COLS), (unsigned)((R * C + 255) / 256), (unsigned)((Nxm + KS_ROWS - 1) / KS_ROWS));
+  if (Nk == 5) kernel_spectrum_emb_sep_kernel<5, 5><<<g2, 256, 0, ctx->stream>>>(taps, emb, R, C, Nx, Ny, ncols, 0, twx, twy, Nxm);
+  else if (Nk == 3) kernel_spectrum_emb_sep_kernel<3, 3><<<g2, 256, 0, ctx->stream>>>(taps, emb, R, C, Nx, Ny, ncols, 0, twx, twy, Nxm);
+  else kernel_spectrum_emb_sep_kernel<7, 7><<<g2, 256, 0, ctx->stream>>>(taps, emb, R, C, Nx, Ny, ncols, 0, twx, twy, Nxm);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  return AEFFT_OK;
+}
+
 int launch_kernel_spectrum_emb(aefft_ctx* ctx, int R, int C, int Nk, int Nl, int Nx, int Ny, int col0, int ncols, const float* taps,
                                float* emb) {
   const float2 *twx, *twy;
@@ -856,9 +880,9 @@ int launch_kernel_spectrum_emb(aefft_ctx* ctx, int R, int C, int Nk, int Nl, int
   ProfScope prof(ctx, "kernel_spectrum_emb", 4.0 * S * R * C * (sep ? 2.0 * Nk : (double)T), 16.0 * S * R * C);
   if (sep) {
     dim3 g2((unsigned)((ncols + KS_COLS - 1) / KS_COLS), (unsigned)((R * C + 255) / 256), (unsigned)((Nx + KS_ROWS - 1) / KS_ROWS));
-    if (Nk == 5) kernel_spectrum_emb_sep_kernel<5, 5><<<g2, 256, 0, ctx->stream>>>(taps, emb, R, C, Nx, Ny, ncols, col0, twx, twy);
-    else if (Nk == 3) kernel_spectrum_emb_sep_kernel<3, 3><<<g2, 256, 0, ctx->stream>>>(taps, emb, R, C, Nx, Ny, ncols, col0, twx, twy);
-    else kernel_spectrum_emb_sep_kernel<7, 7><<<g2, 256, 0, ctx->stream>>>(taps, emb, R, C, Nx, Ny, ncols, col0, twx, twy);
+    if (Nk == 5) kernel_spectrum_emb_sep_kernel<5, 5><<<g2, 256, 0, ctx->stream>>>(taps, emb, R, C, Nx, Ny, ncols, col0, twx, twy, 0);
+    else if (Nk == 3) kernel_spectrum_emb_sep_kernel<3, 3><<<g2, 256, 0, ctx->stream>>>(taps, emb, R, C, Nx, Ny, ncols, col0, twx, twy, 0);
+    else kernel_spectrum_emb_sep_kernel<7, 7><<<g2, 256, 0, ctx->stream>>>(taps, emb, R, C, Nx, Ny, ncols, col0, twx, twy, 0);
   } else if (T == 25) kernel_spectrum_emb_kernel_t<25><<<grid, 256, 0, ctx->stream>>>(taps, emb, R, C, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
   else if (T == 9) kernel_spectrum_emb_kernel_t<9><<<grid, 256, 0, ctx->stream>>>(taps, emb, R, C, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);
   else if (T == 49) kernel_spectrum_emb_kernel_t<49><<<grid, 256, 0, ctx->stream>>>(taps, emb, R, C, Nk, Nl, Nx, Ny, ncols, col0, S, twx, twy);

@@ -159,11 +159,13 @@ def test_net_fft_forward_fused_pooling_at_full_resolution(ctx, size, pool):
         net.close()
 
 
-@pytest.mark.parametrize("cfg", [(3, 64, 32, [4, 5], [2, 2], 3), (3, 64, 64, [16, 32], [2, 2], 16), (1, 32, 64, [8, 16], [1, 2], 16)])
+@pytest.mark.parametrize("cfg", [(3, 64, 32, [4, 5], [2, 2], 3), (3, 64, 64, [16, 32], [2, 2], 16), (1, 32, 64, [8, 16], [1, 2], 16),
+                                 (3, 64, 128, [8, 16, 32], [2, 2, 2], 16)])
 def test_net_fft_forward_fused_with_level_changes_equals_unfused(ctx, cfg, monkeypatch):
     """fft_l <= 0: the image-side convs run fused with the spectral pooling after / the up-sampling before them and compute
-    only the kept bins (net_fft.cu: conv_then_pool / unpool_then_conv).  Same arithmetic per kept bin, so the reconstruction
-    and the trained kernels equal those of the unfused path (AEFFT_NO_FWD_FUSE) bit for bit."""
+    only the kept bins (net_fft.cu: conv_then_pool / unpool_then_conv); a tensor-core level followed by a pooling does the
+    same when its training runs on the Gram matrices (conv_then_pool_tc; the last configuration).  Same arithmetic per kept
+    bin, so the reconstruction and the trained kernels equal those of the unfused path (AEFFT_NO_FWD_FUSE) bit for bit."""
     D, Nx, Ny, widths, pools, B = cfg
     out = []
     for nofuse in (False, True):
