@@ -290,14 +290,17 @@ int launch_tc_outer(aefft_ctx* ctx, long long S, int B, int nP, int nQ, const fl
                     float* out);
 // backprop_fft's iteration loop on per-bin Gram matrices (spec_gram.cu; expout == in): ONE pass over the frames per call
 bool spec_gram_loop_pays(int B, int dD, int dM, bool bin_major);
+// (Nx, sNx, sNy: O is compact on the support grid (sNx, sNy) of an up-sampling, zero on the other bins; sNx = 0: dense)
 int launch_gram_stats_bm(aefft_ctx* ctx, long long S, int B, int dD, const float* X, const float* O, int sub, float* Gx, float* M0,
-                         float* mse_out, double mse_scale, float* dcsum, int ncols, int col0, int Ny);
+                         float* mse_out, double mse_scale, float* dcsum, int ncols, int col0, int Ny, int Nx = 0, int sNx = 0,
+                         int sNy = 0);
 int launch_gram_iter_bm(aefft_ctx* ctx, long long S, int B, int dD, int dM, const float* Gx, const float* M0, const float* Cemb,
                         const float* Femb, int first, float gs, float gb, float norm, const float* dcsum, const float* bias_b,
                         const float* bias_p, float* dCt, float* dFt, float* db, float* dp, float* mse_out, double mse_scale, int ncols,
                         int col0, int Ny);
 int launch_gram_stats_ff(aefft_ctx* ctx, long long S, int B, int dD, const float2* X, const float2* O, float2* Gx, float2* M0,
-                         float* mse_out, double mse_scale, float* dcsum, int ncols, int col0, int Ny);
+                         float* mse_out, double mse_scale, float* dcsum, int ncols, int col0, int Ny, int Nx = 0, int sNx = 0,
+                         int sNy = 0);
 int launch_gram_iter_ff(aefft_ctx* ctx, long long S, int B, int dD, int dM, const float2* Gx, const float2* M0, const float2* C,
                         const float2* F, int first, float gs, float gb, float norm, const float* dcsum, const float* bias_b,
                         const float* bias_p, float2* dC, float2* dF, float* db, float* dp, float* mse_out, double mse_scale, int ncols,
@@ -324,6 +327,9 @@ bool spec_conv_reg_supported(int CI, int CO);
 int launch_spec_conv_reg_resized(aefft_ctx* ctx, int64_t B, int CI, int CO, int Nxb, int Nyb, int Nxm, int Nym, bool pooled_out,
                                  bool small_bin_major, const float2* in, const float2* W, const float* bias, float bias_scale,
                                  float in_scale, float2* out);
+int launch_spec_conv_reg_support(aefft_ctx* ctx, int64_t B, int CI, int CO, int Nxb, int Nyb, int Nxm, int Nym, bool in_bin_major,
+                                 bool out_bin_major, const float2* in, const float2* W, const float* bias, float bias_scale,
+                                 float in_scale, float2* out);
 int launch_small_grad(aefft_ctx* ctx, int64_t B, int dD, int dM, int64_t S, const float2* X, const float2* Xt, const float2* O,
                       const float2* C, const float2* F, const float* bias_b, const float* bias_p, float norm, float gscale,
                       float dbscale, float2* dC, float2* dF, float* db, float* dp);
@@ -348,6 +354,8 @@ struct FftTrainInputs {
                                                // [bin][B][2 dM] (the forward's hidden layer): saves its recomputation
   const float *Cemb = nullptr, *Femb = nullptr; // optional with Xbm: embedded bin-major spectra of the CURRENT c / f (what the
                                                // forward generated for its two convs of this pair): not generated again
+  int o_sNx = 0, o_sNy = 0;   // > 0: Os / Obm is COMPACT on the (o_sNx, o_sNy) grid an up-sampling fills (zero elsewhere);
+                              // only the Gram-matrix loop takes it (spec_gram.cu)
   bool resident = false;      // c,f,b,p are the device-resident masters: no export through the spectra, and no stream
                               // synchronisation unless a host trace is requested
   float* trace_dev = nullptr; // device destination of the mse trace (n_iter + 1 floats), optional

@@ -344,6 +344,8 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
   const bool same_target = !have_real || expout == in;
   const bool gram_tc = use_tc && same_target && spec_gram_loop_pays((int)B, dD, dM, true);
   const bool gram_ff = use_small && same_target && spec_gram_loop_pays((int)B, dD, dM, false);
+  // a compact `out` spectrum (support of an up-sampling) is understood by the statistics pass of the Gram loop only
+  AE_ARG(inp.o_sNx == 0 || ((have_bm && gram_tc) || (have_ff && gram_ff)));
   if (!use_tc) {  // the bins-fastest CUDA-core path keeps the gradient spectra, and H, G unless fused
     if (!use_small) {
       AE_TRY(ctx->getT("bpf_H", nHs, &q.H));
@@ -481,7 +483,7 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
       // the one pass over the frames: Gx, M0 (and "mse fft:" when the caller's spectra are bin-major)
       if (have_bm)
         AE_TRY(launch_gram_stats_bm(ctx, S, (int)B, dD, inp.Xbm, inp.Obm, 1, Gx, M0, q.mse, mse_scale, own_dc ? dcs : nullptr, ncols,
-                                    col0, Ny));
+                                    col0, Ny, Nx, inp.o_sNx, inp.o_sNy));
       else
         AE_TRY(launch_gram_stats_bm(ctx, S, (int)B, dD, Xb, Eb, 0, Gx, M0, nullptr, 0.0, own_dc ? dcs : nullptr, ncols, col0, Ny));
       if (!Cemb0) {
@@ -572,7 +574,8 @@ int backprop_fft_run(aefft_ctx* ctx, int loc, int64_t B, int dD, int dM, int Nx,
     AE_TRY(ctx->getT("gr_M0", (size_t)S * dD * dD, &M0));
     AE_TRY(ctx->getT("gr_dc", (size_t)4 * dD, &dcs));
     // the one pass over the frames: Gx, M0 and "mse fft:" (:1440)
-    AE_TRY(launch_gram_stats_ff(ctx, S, (int)B, dD, q.X, q.O, Gx, M0, q.mse, mse_scale, own_dc ? dcs : nullptr, ncols, col0, Ny));
+    AE_TRY(launch_gram_stats_ff(ctx, S, (int)B, dD, q.X, q.O, Gx, M0, q.mse, mse_scale, own_dc ? dcs : nullptr, ncols, col0, Ny, Nx,
+                                inp.o_sNx, inp.o_sNy));
     if (sharded && !use_comm) AE_TRY(reduce_over_devices(q.mse, 1));
     const float gb = (float)((double)norm / (Norm * (double)B));
     for (int n = 0; n <= n_iter; n++) {

@@ -31,6 +31,8 @@ struct SpecL {
   float* p = nullptr;
   int bin_major = 0;
   bool skipped = false;  // the last forward (fft_l <= 0) fused this layer away: its spectrum was not produced
+  int sNx = 0, sNy = 0;  // > 0: the spectrum is stored COMPACT on the (sNx, sNy) grid of the innermost level (decoder layers of
+                         // a forward with fft_l <= 0: everything an up-sampling adds is zero); 0: dense
 };
 
 }  // namespace aefft
@@ -49,6 +51,7 @@ struct aefft_net {
   int gall_mode = -1;
   // momentum space (net_fft.cu): per-layer spectra, planned lazily for the current topology
   std::vector<aefft::SpecL> spec;
+  std::vector<char> emb_valid;  // per conv: the last forward left the full-resolution embedded kernel spectra in "nf_emb_<n>"
   float* fft_trace = nullptr;  // device [pairs][n_iter+1] mse values of the last fft step
   int64_t fft_trace_cap = 0;
 };

@@ -123,6 +123,7 @@ int conv_spec(aefft_net* net, int n, int li, int lo) {
     snprintf(name, sizeof(name), "nf_emb_%d", n);
     AE_TRY(ctx->getT(name, (size_t)4 * c.dM * c.dD * S, &emb));
     AE_TRY(launch_kernel_spectrum_emb(ctx, c.dM, c.dD, c.Nk, c.Nl, A.Nx, A.Ny, 0, 0, c.c, emb));
+    net->emb_valid[n] = 1;
     return launch_tc_forward(ctx, S, (int)net->B, c.dD, c.dM, net->spec[li].p, emb, 1.f / (float)c.dM, c.b, norm, nullptr,
                              net->spec[lo].p, nullptr, 0.0, 0, 0, 0);
   }
@@ -200,6 +201,86 @@ int unpool_then_conv(aefft_net* net, int n, int ls) {
                                       (float2*)net->spec[ls + 2].p);
 }
 
+// ---- The decoder on the support of the innermost level (fft_l <= 0).  A spectral up-sampling only adds zeros, and conv_k is
+// per bin, so every decoder spectrum is non-zero only on the bins that came up from the innermost resolution (sNx x sNy): the
+// decoder convs run on that grid alone (kernel spectra evaluated at the level's frequencies of those bins), their outputs are
+// stored COMPACT (SpecL::sNx / sNy), the up-sampled layers are never produced, the reconstruction's inverse transform embeds
+// from the support grid, and the statistics pass of the Gram loop reads the compact `out` spectrum through the same map.
+static int ilog2i(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
+bool decoder_support_capable(const aefft_net* net, int fft_l) {
+  if (fft_l > 0 || getenv("AEFFT_NO_FWD_FUSE") || getenv("AEFFT_NO_SPARSE_DECODER") || net->ctx->shard_world != 1) return false;
+  const int N = (int)net->convs.size(), P = N / 2;
+  if (N - 1 == P) return false;
+  const LayerL& S0 = net->layers[2 * P + 1];
+  if (S0.Nx < 4 || S0.Ny < 4) return false;
+  for (int n = P + 1; n < N; n++) {
+    const LayerL &A = net->layers[2 * n - 1], &Z = net->layers[2 * n + 1];
+    const ConvL& c = net->convs[n];
+    if (!(A.Nx < Z.Nx && A.Ny < Z.Ny)) return false;
+    if (net->spec[2 * n + 1].bin_major) {
+      if (!net->spec[2 * n - 1].bin_major || c.Nk != c.Nl || !(c.Nk == 3 || c.Nk == 5 || c.Nk == 7)) return false;
+    } else if (!spec_conv_reg_supported(c.dD, c.dM)) {
+      return false;
+    }
+  }
+  if (fft_l == 0) {
+    const LayerL& Zf = net->layers[2 * N];
+    if (!(S0.Nx < Zf.Nx && S0.Ny < Zf.Ny) || getenv("AEFFT_FFT_V1") || getenv("AEFFT_NO_FFT_POOL")) return false;
+    const int lx = ilog2i(Zf.Nx), ly = ilog2i(Zf.Ny);
+    if (lx < 3 || lx > 12 || ly < 3 || ly > 12 || net->B * Zf.D > 65535) return false;
+  }
+  return true;
+}
+int decoder_on_support(aefft_net* net, int fft_l) {
+  aefft_ctx* ctx = net->ctx;
+  const int N = (int)net->convs.size(), P = N / 2;
+  AE_TRY(conv_spec(net, P, 2 * P, 2 * P + 1));  // the innermost decoder conv: dense at its own resolution
+  const int sNx = net->layers[2 * P + 1].Nx, sNy = net->layers[2 * P + 1].Ny;
+  const long long Ss = (long long)sNx * (sNy / 2 + 1);
+  for (int n = P + 1; n < N; n++) {
+    const ConvL& c = net->convs[n];
+    const LayerL& Z = net->layers[2 * n + 1];
+    const float norm = (float)Z.Nx * (float)Z.Ny;
+    if (net->spec[2 * n + 1].bin_major) {
+      float* emb;
+      AE_TRY(ctx->getT("nf_emb_pool", (size_t)4 * c.dM * c.dD * Ss, &emb));
+      AE_TRY(launch_kernel_spectrum_emb_pooled(ctx, c.dM, c.dD, c.Nk, c.Nl, Z.Nx, Z.Ny, sNx, sNy, c.c, emb));
+      AE_TRY(launch_tc_forward(ctx, Ss, (int)net->B, c.dD, c.dM, net->spec[2 * n - 1].p, emb, 1.f / (float)c.dM, c.b, norm, nullptr,
+                               net->spec[2 * n + 1].p, nullptr, 0.0, 0, 0, 0));
+    } else {
+      float2* kspec;
+      AE_TRY(conv_kspec(net, n, Z.Nx, Z.Ny, &kspec));
+      AE_TRY(launch_spec_conv_reg_support(ctx, net->B, c.dD, c.dM, Z.Nx, Z.Ny, sNx, sNy, net->spec[2 * n - 1].bin_major, false,
+                                          (const float2*)net->spec[2 * n - 1].p, kspec, c.b, norm, 1.f / (float)c.dM,
+                                          (float2*)net->spec[2 * n + 1].p));
+    }
+    net->spec[2 * n].skipped = true;
+    net->spec[2 * n + 1].sNx = sNx;
+    net->spec[2 * n + 1].sNy = sNy;
+  }
+  if (fft_l < 0) return AEFFT_OK;
+  // reconstruction: fft_inv (:1373) of the last layer's spectrum, embedded from the support grid on the fly
+  const LayerL &A = net->layers[2 * N - 1], &Zf = net->layers[2 * N];
+  const size_t R = (size_t)net->B * A.D;
+  float2 *tmp, *src = (float2*)net->spec[2 * N - 1].p;
+  AE_TRY(ctx->getT("nf_fft_tmp", R * Zf.Nx * (sNy / 2 + 1), &tmp));
+  if (net->spec[2 * N - 1].bin_major) {
+    AE_TRY(ctx->getT("nf_ff", R * Ss, &src));
+    AE_TRY(launch_to_binmajor(ctx, Ss, (long long)R, (const float2*)net->spec[2 * N - 1].p, nullptr, src));
+  }
+  return launch_fft_c2r_embedded(ctx, (int64_t)R, Zf.Nx, Zf.Ny, sNx, sNy, src, tmp, Zf.p, 1.f / ((float)Zf.Nx * (float)Zf.Ny));
+}
+// dense copy of a compact decoder spectrum (the consumers that do not understand the support map)
+int densify(aefft_net* net, int l, float** dense) {
+  aefft_ctx* ctx = net->ctx;
+  const LayerL& L = net->layers[l];
+  const SpecL& sp = net->spec[l];
+  const long long R = net->B * L.D;
+  AE_TRY(ctx->getT("nf_dense", spec_floats(net, l), dense));
+  if (sp.bin_major) return launch_bm_resize(ctx, 2 * R, sp.sNx, sp.sNy, L.Nx, L.Ny, sp.p, *dense);
+  return launch_spec_resize(ctx, R, sp.sNx, sp.sNy, L.Nx, L.Ny, (const float2*)sp.p, (float2*)*dense);
+}
+
 // fft_inv (:806-864): spectrum of layer l -> real layer l, scaled by 1/(Nx Ny)
 int materialise(aefft_net* net, int l) {
   aefft_ctx* ctx = net->ctx;
@@ -249,14 +330,17 @@ int forward(aefft_net* net, int loc, const float* frames, int fft_l) {
     }
   }
   if (!pooled0) AE_TRY(launch_fft_r2c(ctx, net->B * L0.D, L0.Nx, L0.Ny, L0.p, (float2*)net->spec[0].p));
+  for (auto& sp : net->spec) { sp.skipped = false; sp.sNx = sp.sNy = 0; }
+  net->emb_valid.assign(net->convs.size(), 0);
+  const bool sparse_decoder = decoder_support_capable(net, fft_l);
   bool next_in_done = false;  // the previous iteration already produced this conv's input (encoder) / output (decoder)
   for (int n = 0; n < N; n++) {
+    if (n == N / 2 && sparse_decoder) return decoder_on_support(net, fft_l);
     if (n < N / 2) {
       if (!(n == 0 && pooled0) && !next_in_done) AE_TRY(move_spec(net, 2 * n, 2 * n + 1));        // pool_fft :1346
       next_in_done = false;
       if (fft_l > 0) AE_TRY(materialise(net, 2 * n + 1));
       const LayerL &Lc = net->layers[2 * n + 2], &Ln = net->layers[2 * n + 3];
-      net->spec[2 * n + 2].skipped = false;
       if (fft_l <= 0 && n + 1 < N / 2 && Ln.Nx < Lc.Nx && Ln.Ny < Lc.Ny && Ln.Nx >= 2 && Ln.Ny >= 2) {
         if (fusable_conv(net, n, 2 * n + 1)) {
           AE_TRY(conv_then_pool(net, n, 2 * n + 1));  // conv_fft :1356 + the next pool_fft :1346, on the kept bins only
@@ -385,25 +469,38 @@ static int train_pair_spectra(aefft_net* net, int n, float del0, int maxdiff, in
     return backprop_fft_run(ctx, AEFFT_DEVICE, net->B * W, e.dD, e.dM, L.Nx, L.Ny, e.Nk, e.Nl, inp, nullptr, e.c, nullptr, d.c, e.b,
                             d.b, del0, maxdiff, n_iter, trace_host);
   }
+  // the pair's `out` spectrum may be compact on the decoder's support grid: the Gram loop reads it through the map, every
+  // other path gets a dense copy
+  const float* Op = net->spec[lo].p;
+  if (net->spec[lo].sNx > 0) {
+    const bool bm = net->spec[li].bin_major;
+    const bool gram = bm ? spec_gram_loop_pays((int)net->B, e.dD, e.dM, true)
+                         : (!(spec_tc_eligible(e.dD, e.dM, e.Nk, e.Nl) && net->B >= 16) && spec_small_eligible(e.dD, e.dM) &&
+                            spec_gram_loop_pays((int)net->B, e.dD, e.dM, false));
+    if (gram) { inp.o_sNx = net->spec[lo].sNx; inp.o_sNy = net->spec[lo].sNy; }
+    else { float* dense; AE_TRY(densify(net, lo, &dense)); Op = dense; }
+  }
   if (net->spec[li].bin_major) {
-    inp.Xbm = net->spec[li].p; inp.Obm = net->spec[lo].p;
+    inp.Xbm = net->spec[li].p; inp.Obm = Op;
     if (fresh_forward) {
       // what the forward just computed with the kernels as they are now: the hidden spectrum hin = conv_k(in; c, b) and the
       // embedded spectra of c and f (the encoder side only when that conv ran at full resolution)
       char name[32];
       const size_t ne = (size_t)4 * e.dM * e.dD * L.Nx * (L.Ny / 2 + 1);
       float* buf = nullptr;
-      if (!net->spec[li + 1].skipped) {
-        inp.Hbm = net->spec[li + 1].p;
+      if (!net->spec[li + 1].skipped) inp.Hbm = net->spec[li + 1].p;
+      if ((int)net->emb_valid.size() == N && net->emb_valid[n]) {
         snprintf(name, sizeof(name), "nf_emb_%d", n);
         AE_TRY(ctx->getT(name, ne, &buf));
         inp.Cemb = buf;
       }
-      snprintf(name, sizeof(name), "nf_emb_%d", N - 1 - n);
-      AE_TRY(ctx->getT(name, ne, &buf));
-      inp.Femb = buf;
+      if ((int)net->emb_valid.size() == N && net->emb_valid[N - 1 - n]) {
+        snprintf(name, sizeof(name), "nf_emb_%d", N - 1 - n);
+        AE_TRY(ctx->getT(name, ne, &buf));
+        inp.Femb = buf;
+      }
     }
-  } else { inp.Xs = (const float2*)net->spec[li].p; inp.Os = (const float2*)net->spec[lo].p; }
+  } else { inp.Xs = (const float2*)net->spec[li].p; inp.Os = (const float2*)Op; }
   return backprop_fft_run(ctx, AEFFT_DEVICE, net->B, e.dD, e.dM, L.Nx, L.Ny, e.Nk, e.Nl, inp, nullptr, e.c, nullptr, d.c, e.b, d.b,
                           del0, maxdiff, n_iter, trace_host);
 }

@@ -70,6 +70,23 @@ __global__ void __launch_bounds__(1024) gram_final_kernel(const double* __restri
   }
 }
 
+// O given COMPACT on the support grid (sNx x sNyr) of a spectral up-sampling (resize :87-157, embedding): index of dense bin
+// (i, j) of the (Nx x Nyr) grid on that grid, or -1 where the up-sampled spectrum is zero
+struct Support {
+  int Nx, Nyr, sNx, sNyr;  // sNx == 0: dense
+};
+__device__ __forceinline__ long long support_index(const Support& sp, long long w) {
+  if (sp.sNx == 0) return w;
+  const int i = (int)(w / sp.Nyr), j = (int)(w - (long long)i * sp.Nyr);
+  int si = -1, sj = -1;
+  if (i < sp.sNx / 2) si = i;
+  else if (i > sp.Nx - sp.sNx / 2) si = i - sp.Nx + sp.sNx;
+  else if (i == sp.Nx / 2) si = sp.sNx / 2;
+  if (j < sp.sNyr - 1) sj = j;
+  else if (j == sp.Nyr - 1) sj = sp.sNyr - 1;
+  return (si < 0 || sj < 0) ? -1 : (long long)si * sp.sNyr + sj;
+}
+
 // ------------------------------------------------------------------------------------------------ family A: bin-major
 // Statistics of one bin: E0 = O - X (sub) or O itself (the caller hands E0), Gx, M0, hw * sum |E0|^2, and at the DC bin
 // Sx = sum_b X, Se = sum_b E0.  TR x TR register tiles; with fewer than 256 tiles the frames are split over NG thread
@@ -78,7 +95,7 @@ template <int DD>
 __global__ void __launch_bounds__(256) gram_stats_bm_kernel(const float* __restrict__ X, const float* __restrict__ O, int sub,
                                                             float2* __restrict__ Gx, float2* __restrict__ M0,
                                                             double* __restrict__ sq_part, float2* __restrict__ dcsum, int B,
-                                                            int ncols, int col0, int Ny) {
+                                                            int ncols, int col0, int Ny, Support sup) {
   constexpr int TR = DD >= 32 ? 4 : (DD >= 16 ? 2 : 1), TG = DD / TR, NT = TG * TG, NG = 256 / NT;
   static_assert(NT * NG == 256, "256 threads");
   extern __shared__ __align__(16) float2 gs_sm[];
@@ -89,13 +106,14 @@ __global__ void __launch_bounds__(256) gram_stats_bm_kernel(const float* __restr
   const int tid = threadIdx.x;
   float sq = 0.f;
   {
+    const long long wo = support_index(sup, w);  // -1: O is zero on this bin
     const float4* x4 = reinterpret_cast<const float4*>(X + w * (long long)B * 2 * DD);
-    const float4* o4 = reinterpret_cast<const float4*>(O + w * (long long)B * 2 * DD);
+    const float4* o4 = reinterpret_cast<const float4*>(O + (wo < 0 ? 0 : wo) * (long long)B * 2 * DD);
     float4* xs4 = reinterpret_cast<float4*>(Xs);
     float4* es4 = reinterpret_cast<float4*>(Es);
     for (int i = tid; i < B * DD / 2; i += 256) {
       const float4 x = __ldg(x4 + i);
-      float4 e = __ldg(o4 + i);
+      float4 e = wo < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(o4 + i);
       if (sub) { e.x -= x.x; e.y -= x.y; e.z -= x.z; e.w -= x.w; }
       xs4[i] = x; es4[i] = e;
       sq = fmaf(e.x, e.x, fmaf(e.y, e.y, fmaf(e.z, e.z, fmaf(e.w, e.w, sq))));
@@ -305,10 +323,12 @@ template <int DD>
 __global__ void __launch_bounds__(128) gram_stats_ff_kernel(const float2* __restrict__ X, const float2* __restrict__ O,
                                                             float2* __restrict__ Gx, float2* __restrict__ M0,
                                                             double* __restrict__ sq_part, float2* __restrict__ dcsum, long long S,
-                                                            int B, int ncols, int col0, int Ny) {
+                                                            int B, int ncols, int col0, int Ny, Support sup) {
   const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = w < S;
   const long long wc = live ? w : 0;
+  const long long wo = support_index(sup, wc);  // -1: O is zero on this bin
+  const long long So = sup.sNx ? (long long)sup.sNx * sup.sNyr : S, fso = (long long)DD * So;
   float2 g[DD][DD], m[DD][DD];
   float2 sx[DD], se[DD];
 #pragma unroll
@@ -327,14 +347,14 @@ __global__ void __launch_bounds__(128) gram_stats_ff_kernel(const float2* __rest
 #pragma unroll
       for (int d = 0; d < DD; d++) {
         asm volatile("prefetch.global.L2 [%0];" ::"l"(X + (b + PF) * fs + d * S + wc));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(O + (b + PF) * fs + d * S + wc));
+        if (wo >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(O + (b + PF) * fso + d * So + wo));
       }
     }
     float2 x[DD], e[DD];
 #pragma unroll
     for (int d = 0; d < DD; d++) {
       x[d] = __ldg(X + b * fs + d * S + wc);
-      const float2 o = __ldg(O + b * fs + d * S + wc);
+      const float2 o = wo >= 0 ? __ldg(O + b * fso + d * So + wo) : make_float2(0.f, 0.f);
       e[d] = make_float2(o.x - x[d].x, o.y - x[d].y);
       sq = fmaf(e[d].x, e[d].x, fmaf(e[d].y, e[d].y, sq));
     }
@@ -568,8 +588,10 @@ int launch_gram_final(aefft_ctx* ctx, const double* part, long long n, double sc
 // statistics of a bin-major pair: X, O [S][B][2 dD] (sub: E0 = O - X, else O is E0 already) -> Gx, M0 [S][dD][dD][2],
 // *mse_out = mse_scale * sum_bins hw |E0|^2 (when mse_out), dcsum = Sx | Se of bin 0 (when the device owns the DC column)
 int launch_gram_stats_bm(aefft_ctx* ctx, long long S, int B, int dD, const float* X, const float* O, int sub, float* Gx, float* M0,
-                         float* mse_out, double mse_scale, float* dcsum, int ncols, int col0, int Ny) {
+                         float* mse_out, double mse_scale, float* dcsum, int ncols, int col0, int Ny, int Nx, int sNx, int sNy) {
   if (ncols <= 0) { ncols = Ny / 2 + 1; col0 = 0; }
+  AE_ARG(sNx == 0 || (ncols == Ny / 2 + 1 && Nx > 0 && S == (long long)Nx * ncols && sNy > 0));
+  const Support sup{Nx, Ny / 2 + 1, sNx, sNx ? sNy / 2 + 1 : 0};
   const size_t smem = gram_stats_bm_smem(B, dD);
   double* part;
   AE_TRY(ctx->getT("gram_sq_part", (size_t)S, &part));
@@ -579,7 +601,7 @@ int launch_gram_stats_bm(aefft_ctx* ctx, long long S, int B, int dD, const float
   if (dD == dd) {                                                                                                          \
     AE_TRY(ctx->ensure_dyn_smem((const void*)gram_stats_bm_kernel<dd>, smem));                                             \
     gram_stats_bm_kernel<dd><<<(unsigned)S, 256, smem, ctx->stream>>>(X, O, sub, (float2*)Gx, (float2*)M0, part,           \
-                                                                     (float2*)dcsum, B, ncols, col0, Ny);                  \
+                                                                     (float2*)dcsum, B, ncols, col0, Ny, sup);             \
   }
     AEFFT_GS(8) AEFFT_GS(16) AEFFT_GS(32) AEFFT_GS(64)
 #undef AEFFT_GS
@@ -629,18 +651,20 @@ int launch_gram_iter_bm(aefft_ctx* ctx, long long S, int B, int dD, int dM, cons
 
 // ---- bins-fastest, dD <= 4
 int launch_gram_stats_ff(aefft_ctx* ctx, long long S, int B, int dD, const float2* X, const float2* O, float2* Gx, float2* M0,
-                         float* mse_out, double mse_scale, float* dcsum, int ncols, int col0, int Ny) {
+                         float* mse_out, double mse_scale, float* dcsum, int ncols, int col0, int Ny, int Nx, int sNx, int sNy) {
   if (ncols <= 0) { ncols = Ny / 2 + 1; col0 = 0; }
+  AE_ARG(sNx == 0 || (ncols == Ny / 2 + 1 && Nx > 0 && S == (long long)Nx * ncols && sNy > 0));
+  const Support sup{Nx, Ny / 2 + 1, sNx, sNx ? sNy / 2 + 1 : 0};
   const long long blocks = (S + 127) / 128;
   double* part;
   AE_TRY(ctx->getT("gram_sq_part", (size_t)(S > blocks ? S : blocks), &part));
   {
     ProfScope prof(ctx, "spec_gram_stats", 16.0 * S * B * dD * dD, 16.0 * S * B * dD);
     switch (dD) {
-      case 1: gram_stats_ff_kernel<1><<<(unsigned)blocks, 128, 0, ctx->stream>>>(X, O, Gx, M0, part, (float2*)dcsum, S, B, ncols, col0, Ny); break;
-      case 2: gram_stats_ff_kernel<2><<<(unsigned)blocks, 128, 0, ctx->stream>>>(X, O, Gx, M0, part, (float2*)dcsum, S, B, ncols, col0, Ny); break;
-      case 3: gram_stats_ff_kernel<3><<<(unsigned)blocks, 128, 0, ctx->stream>>>(X, O, Gx, M0, part, (float2*)dcsum, S, B, ncols, col0, Ny); break;
-      case 4: gram_stats_ff_kernel<4><<<(unsigned)blocks, 128, 0, ctx->stream>>>(X, O, Gx, M0, part, (float2*)dcsum, S, B, ncols, col0, Ny); break;
+      case 1: gram_stats_ff_kernel<1><<<(unsigned)blocks, 128, 0, ctx->stream>>>(X, O, Gx, M0, part, (float2*)dcsum, S, B, ncols, col0, Ny, sup); break;
+      case 2: gram_stats_ff_kernel<2><<<(unsigned)blocks, 128, 0, ctx->stream>>>(X, O, Gx, M0, part, (float2*)dcsum, S, B, ncols, col0, Ny, sup); break;
+      case 3: gram_stats_ff_kernel<3><<<(unsigned)blocks, 128, 0, ctx->stream>>>(X, O, Gx, M0, part, (float2*)dcsum, S, B, ncols, col0, Ny, sup); break;
+      case 4: gram_stats_ff_kernel<4><<<(unsigned)blocks, 128, 0, ctx->stream>>>(X, O, Gx, M0, part, (float2*)dcsum, S, B, ncols, col0, Ny, sup); break;
       default: return AEFFT_ERR_UNSUPPORTED;
     }
     ctx->launches++;

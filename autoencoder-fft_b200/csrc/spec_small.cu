@@ -284,7 +284,8 @@ int run_mse(aefft_ctx* ctx, const SmallParams& p) {
 //   MODE 1 (conv, then pooling by cropping): in at wb, out at the small bin -- the 3/4 of the conv output that the crop
 //           discards is never computed;
 //   MODE 2 (up-sampling by zero embedding, then conv): in at the small bin, out at wb -- the caller zeroes the output first;
-//           the conv of the zero band is zero (the bias lives on the DC bin, which is always kept).
+//           the conv of the zero band is zero (the bias lives on the DC bin, which is always kept);
+//   MODE 3 (the same, output kept COMPACT on the small grid: the decoder's spectra stay on the support of the innermost level).
 struct ConvRegMap {
   int mode, Nxm, Nyrm, Nxb, Nyrb;
 };
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(128) conv_reg_kernel(const float2* __restrict_
     const int jb = j < map.Nyrm - 1 ? j : map.Nyrb - 1;
     const long long wb = (long long)ib * map.Nyrb + jb;
     w_w = wb;
-    if (map.mode == 1) w_in = wb; else w_out = wb;
+    if (map.mode == 1) w_in = wb; else if (map.mode == 2) w_out = wb;  // mode 3: in and out both on the small grid
   }
   const int c0 = SPLIT_IN ? part * CIP : 0, o0 = SPLIT_IN ? 0 : part * COP;
   float2 Wr[COP][CIP];
@@ -420,6 +421,20 @@ int launch_spec_conv_reg_resized(aefft_ctx* ctx, int64_t B, int CI, int CO, int 
   if (!pooled_out) AE_CUDA(cudaMemsetAsync(out, 0, (size_t)B * CO * Sb * sizeof(float2), ctx->stream));
   return conv_reg_launch(ctx, B, CI, CO, Sm, pooled_out ? big : small, Sb, pooled_out ? small : big, map, in, W, bias, bias_scale,
                          in_scale, out, pooled_out ? "spec_contract_reg_pool" : "spec_contract_reg_embed");
+}
+
+// conv_k at resolution (Nxb, Nyb) of a spectrum that is non-zero only on the bins an up-sampling from (Nxm, Nym) fills: in and
+// out are COMPACT on that (Nxm, Nym) grid (bin-major [bin][frame][ch] or bins-fastest [frame][ch][bins] each)
+int launch_spec_conv_reg_support(aefft_ctx* ctx, int64_t B, int CI, int CO, int Nxb, int Nyb, int Nxm, int Nym, bool in_bin_major,
+                                 bool out_bin_major, const float2* in, const float2* W, const float* bias, float bias_scale,
+                                 float in_scale, float2* out) {
+  if (!spec_conv_reg_supported(CI, CO)) return AEFFT_ERR_UNSUPPORTED;
+  AE_ARG(Nxm < Nxb && Nym < Nyb && Nxm >= 2 && Nym >= 2);
+  const int64_t Sb = (int64_t)Nxb * (Nyb / 2 + 1), Sm = (int64_t)Nxm * (Nym / 2 + 1);
+  const ConvRegMap map{3, Nxm, Nym / 2 + 1, Nxb, Nyb / 2 + 1};
+  const ConvRegLayout li = in_bin_major ? ConvRegLayout{CI, 1, B * CI} : ConvRegLayout{CI * Sm, Sm, 1};
+  const ConvRegLayout lo = out_bin_major ? ConvRegLayout{CO, 1, B * CO} : ConvRegLayout{CO * Sm, Sm, 1};
+  return conv_reg_launch(ctx, B, CI, CO, Sm, li, Sb, lo, map, in, W, bias, bias_scale, in_scale, out, "spec_contract_reg_support");
 }
 
 bool spec_small_eligible(int dD, int dM) {

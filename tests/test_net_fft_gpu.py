@@ -168,11 +168,15 @@ def test_net_fft_forward_fused_with_level_changes_equals_unfused(ctx, cfg, monke
     bin, so the reconstruction and the trained kernels equal those of the unfused path (AEFFT_NO_FWD_FUSE) bit for bit."""
     D, Nx, Ny, widths, pools, B = cfg
     out = []
-    for nofuse in (False, True):
-        if nofuse:
+    # fused + decoder on the support grid (default) | fused, dense decoder | nothing fused
+    for mode in ("default", "dense_decoder", "unfused"):
+        nofuse = mode == "unfused"
+        monkeypatch.delenv("AEFFT_NO_FWD_FUSE", raising=False)
+        monkeypatch.delenv("AEFFT_NO_SPARSE_DECODER", raising=False)
+        if mode == "unfused":
             monkeypatch.setenv("AEFFT_NO_FWD_FUSE", "1")
-        else:
-            monkeypatch.delenv("AEFFT_NO_FWD_FUSE", raising=False)
+        if mode == "dense_decoder":
+            monkeypatch.setenv("AEFFT_NO_SPARSE_DECODER", "1")
         net, *_ = make_net(ctx, D, Nx, Ny, widths, pools, B)
         try:
             x = O.synth_frames(5, B, D, Nx, Ny)
@@ -181,12 +185,14 @@ def test_net_fft_forward_fused_with_level_changes_equals_unfused(ctx, cfg, monke
             names = {r["name"] for r in ctx.profile_records()}
             ctx.profile_enable(False)
             assert ("spec_contract_reg_pool" in names) == (not nofuse), names
-            assert ("spec_contract_reg_embed" in names) == (not nofuse), names
+            assert ("spec_contract_reg_embed" in names) == (mode == "dense_decoder"), names
+            assert ("spec_contract_reg_support" in names) == (mode == "default"), names
             out.append((np.array(traces), net.layer(net.num_layers - 1).copy(),
                         [net.get_conv(n)[0].copy() for n in range(2 * net.num_pairs)]))
         finally:
             net.close()
-    assert np.array_equal(out[0][0], out[1][0])
-    assert np.array_equal(out[0][1], out[1][1])
-    for a, b in zip(out[0][2], out[1][2]):
-        assert np.array_equal(a, b)
+    for other in out[1:]:
+        assert np.array_equal(out[0][0], other[0])
+        assert np.array_equal(out[0][1], other[1])
+        for a, b in zip(out[0][2], other[2]):
+            assert np.array_equal(a, b)
