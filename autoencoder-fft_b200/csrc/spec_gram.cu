@@ -198,9 +198,10 @@ __global__ void __launch_bounds__(256) gram_iter_bm_kernel(GramIterBm p) {
   __shared__ double red[8];
   __shared__ float2 dcv[3 * DD];  // DC bin: Sx, Esum, (beta, 0)
   const int dM = p.dM;
+  const int CP = dM + 2;              // pitch of Cs: the transposing stores below hit 2 banks per lane instead of one for all
   float2* Fs = gi_sm;                 // [DD][dM]
-  float2* Cs = Fs + DD * dM;          // [DD][dM]
-  float2* Cm = Cs + DD * dM;          // [dM][DD]
+  float2* Cs = Fs + DD * dM;          // [DD][CP]
+  float2* Cm = Cs + DD * CP;          // [dM][DD]
   float2* Ms = Cm + DD * dM;          // [DD][MP]
   float2* Gs = Ms + DD * MP;
   float2* Ds = Gs + DD * MP;
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(256) gram_iter_bm_kernel(GramIterBm p) {
     Fs[i] = make_float2(u.x, -u.y);
     const int mc = i / DD, kc = i - mc * DD;  // C[mc][kc]: embedded row 2 mc, columns 2 kc, 2 kc + 1
     const float2 v = __ldg(reinterpret_cast<const float2*>(p.Cemb + ((w * 2 * dM + 2 * mc) * 2 * (long long)DD + 2 * kc)));
-    Cs[kc * dM + mc] = make_float2(v.x, -v.y);
+    Cs[kc * CP + mc] = make_float2(v.x, -v.y);
     Cm[i] = make_float2(v.x, -v.y);
   }
   const float2* src = p.first ? p.M0 : p.Gx;
@@ -227,13 +228,23 @@ __global__ void __launch_bounds__(256) gram_iter_bm_kernel(GramIterBm p) {
   }
   __syncthreads();
   if (!p.first) {
-    // D = F C / (dM dD) - I
-    for (int i = tid; i < DD * DD; i += 256) {
-      const int d = i / DD, e = i - d * DD;
-      float2 t = make_float2(0.f, 0.f);
+    // D = F C / (dM dD) - I, 2 x 2 register tiles (3 shared-memory loads per 4 complex MACs instead of 8: the kernel is bound
+    // by shared-memory wavefronts)
+    constexpr int HT = DD / 2;
+    for (int t = tid; t < HT * HT; t += 256) {
+      const int d = (t / HT) * 2, e = (t % HT) * 2;
+      float2 a00 = make_float2(0.f, 0.f), a01 = a00, a10 = a00, a11 = a00;
 #pragma unroll 4
-      for (int m = 0; m < dM; m++) cmac(t, Fs[d * dM + m], Cm[m * DD + e]);
-      Ds[d * MP + e] = make_float2(t.x * p.tscale - (d == e ? 1.f : 0.f), t.y * p.tscale);
+      for (int m = 0; m < dM; m++) {
+        const float2 f0 = Fs[d * dM + m], f1 = Fs[(d + 1) * dM + m];
+        const float4 cv = *reinterpret_cast<const float4*>(Cm + m * DD + e);
+        const float2 c0 = make_float2(cv.x, cv.y), c1 = make_float2(cv.z, cv.w);
+        cmac(a00, f0, c0); cmac(a01, f0, c1); cmac(a10, f1, c0); cmac(a11, f1, c1);
+      }
+      Ds[d * MP + e] = make_float2(a00.x * p.tscale - (d == e ? 1.f : 0.f), a00.y * p.tscale);
+      Ds[d * MP + e + 1] = make_float2(a01.x * p.tscale, a01.y * p.tscale);
+      Ds[(d + 1) * MP + e] = make_float2(a10.x * p.tscale, a10.y * p.tscale);
+      Ds[(d + 1) * MP + e + 1] = make_float2(a11.x * p.tscale - (d == e ? 1.f : 0.f), a11.y * p.tscale);
     }
     if (dc_bin && tid < DD) {  // beta[d] = Nx Ny (sum_m Re F[d][m](0) b[m] / dD + p[d])
       float s = 0.f;
@@ -243,19 +254,28 @@ __global__ void __launch_bounds__(256) gram_iter_bm_kernel(GramIterBm p) {
     __syncthreads();
     // M = D Gx (+ beta Sx^H at DC);  sum_b |E|^2 = Re sum M o conj(D)  (+ 2 beta . Re(D Sx) + B |beta|^2 at DC)
     float sq = 0.f;
-    for (int i = tid; i < DD * DD; i += 256) {
-      const int d = i / DD, l = i - d * DD;
-      float2 y = make_float2(0.f, 0.f);
+    for (int t = tid; t < HT * HT; t += 256) {
+      const int d = (t / HT) * 2, l = (t % HT) * 2;
+      float2 y[2][2];
+      y[0][0] = y[0][1] = y[1][0] = y[1][1] = make_float2(0.f, 0.f);
 #pragma unroll 4
-      for (int k = 0; k < DD; k++) cmac(y, Ds[d * MP + k], Gs[k * MP + l]);
-      const float2 dd = Ds[d * MP + l];
-      sq = fmaf(y.x, dd.x, fmaf(y.y, dd.y, sq));
-      if (dc_bin) {
-        const float beta = dcv[2 * DD + d].x;
-        y.x = fmaf(beta, dcv[l].x, y.x);
-        y.y = fmaf(-beta, dcv[l].y, y.y);
+      for (int k = 0; k < DD; k++) {
+        const float2 d0 = Ds[d * MP + k], d1 = Ds[(d + 1) * MP + k], g0 = Gs[k * MP + l], g1 = Gs[k * MP + l + 1];
+        cmac(y[0][0], d0, g0); cmac(y[0][1], d0, g1); cmac(y[1][0], d1, g0); cmac(y[1][1], d1, g1);
       }
-      Ms[d * MP + l] = y;
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+          const float2 dd = Ds[(d + a) * MP + l + c];
+          sq = fmaf(y[a][c].x, dd.x, fmaf(y[a][c].y, dd.y, sq));
+          if (dc_bin) {
+            const float beta = dcv[2 * DD + d + a].x;
+            y[a][c].x = fmaf(beta, dcv[l + c].x, y[a][c].x);
+            y[a][c].y = fmaf(-beta, dcv[l + c].y, y[a][c].y);
+          }
+          Ms[(d + a) * MP + l + c] = y[a][c];
+        }
     }
     if (dc_bin && tid < DD) {
       float2 ds = make_float2(0.f, 0.f);
@@ -292,13 +312,13 @@ __global__ void __launch_bounds__(256) gram_iter_bm_kernel(GramIterBm p) {
 #pragma unroll
         for (int j = 0; j < NO; j += 2) {
           const float4 fv = *reinterpret_cast<const float4*>(Fs + k * dM + m0 + j);
-          const float4 cv = *reinterpret_cast<const float4*>(Cs + k * dM + m0 + j);
+          const float4 cv = *reinterpret_cast<const float4*>(Cs + k * CP + m0 + j);
           f[j] = make_float2(fv.x, fv.y); f[j + 1] = make_float2(fv.z, fv.w);
           c[j] = make_float2(cv.x, cv.y); c[j + 1] = make_float2(cv.z, cv.w);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < NO; j++) { f[j] = Fs[k * dM + m0 + j]; c[j] = Cs[k * dM + m0 + j]; }
+        for (int j = 0; j < NO; j++) { f[j] = Fs[k * dM + m0 + j]; c[j] = Cs[k * CP + m0 + j]; }
       }
 #pragma unroll
       for (int j = 0; j < NO; j++) { cmac_conja(aC[j], f[j], m1); cmac_conja(aF[j], c[j], m2); }
@@ -541,7 +561,7 @@ __global__ void __launch_bounds__(128) gram_iter_ff_kernel(GramIterFf p) {
   }
 }
 
-size_t gram_iter_bm_smem(int dD, int dM) { return ((size_t)3 * dD * dM + (size_t)3 * dD * (dD + 1)) * sizeof(float2); }
+size_t gram_iter_bm_smem(int dD, int dM) { return ((size_t)3 * dD * dM + 2 * dD + (size_t)3 * dD * (dD + 1)) * sizeof(float2); }
 size_t gram_stats_bm_smem(int B, int dD) {
   const int tr = dD >= 32 ? 4 : (dD >= 16 ? 2 : 1), ng = 256 / ((dD / tr) * (dD / tr));
   const size_t ex = 2 * (size_t)B * dD, pp = ng > 1 ? (size_t)ng * 2 * dD * dD : 0;

@@ -10,7 +10,7 @@ for WL in c2 c3; do
   $CMD > $OUT/${TAG}_${WL}_plain.json 2> $OUT/${TAG}_${WL}_plain.err || { echo "plain run of $WL failed"; continue; }
   ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/${TAG}_launches_${WL}.csv $CMD \
       > $OUT/${TAG}_${WL}_ncu1.log 2>&1
-  if [ $WL = c2 ]; then PAT='regex:wgrad_ts_kernel|conv_rs_kernel'; SKIP=36; CNT=12; else PAT='regex:spec_tc_kernel|small_grad|small_mse|fft_rows|fft_cols|conv_reg'; SKIP=60; CNT=24; fi
+  if [ $WL = c2 ]; then PAT='regex:wgrad_ts_kernel|conv_rs_kernel'; SKIP=36; CNT=12; else PAT='regex:spec_tc_kernel|gram_iter|gram_stats|fft_rows|fft_cols|conv_reg|kernel_spectrum_emb|binmajor_to_taps'; SKIP=99; CNT=33; fi
   ncu --set full --clock-control none -k "$PAT" -s $SKIP -c $CNT -o $OUT/${TAG}_${WL}_full $CMD \
       > $OUT/${TAG}_${WL}_ncu2.log 2>&1
   tail -2 $OUT/${TAG}_${WL}_ncu2.log
@@ -19,4 +19,5 @@ for WL in c2 c3; do
   python tools/ncu_summary.py $OUT/${TAG}_${WL}_full.ncu-rep "$WL: ncu --set full, one step after 3 warm-up steps ($CMD)" > $OUT/${TAG}_${WL}_ncu_summary.txt
   ls -la $OUT/${TAG}_${WL}_full.ncu-rep; rm -f $OUT/${TAG}_${WL}_full.ncu-rep
 done
+python tools/traffic_from_raw.py c2=$OUT/${TAG}_c2_full_raw.csv c3=$OUT/${TAG}_c3_full_raw.csv > $OUT/${TAG}_traffic.json
 du -sh $OUT
