@@ -248,6 +248,15 @@ int launch_spec_outer(aefft_ctx* ctx, int64_t B, int nA, int nC, int64_t S, cons
 int launch_spec_dc_sums(aefft_ctx* ctx, int64_t B, int dM, int dD, int64_t S, const float2* G, const float2* O,
                         const float2* Xt, float* db, float* dp, float gscale);
 // W_N^t = exp(-2 pi i t / N), t = 0..N-1, computed in double on the host once per length (device table, L1 resident)
+// transform lengths the FFT kernels take: even, 2^a 3^b 5^c, <= 8192 (fft_kernels.cu)
+bool fft_len_supported(int N);
+// (x mod N) for the twiddle tables: a mask for powers of two, else the remainder (x >= 0)
+__host__ __device__ __forceinline__ int tw_mod(int x, int N) { return (N & (N - 1)) == 0 ? (x & (N - 1)) : (x % N); }
+// index of W_N^(w * (k - half)) in the N-entry twiddle table (k - half may be negative)
+__host__ __device__ __forceinline__ int tw_index(int w, int k_minus_half, int N) {
+  const int s = k_minus_half < 0 ? k_minus_half + N : k_minus_half;
+  return tw_mod(w * s, N);
+}
 int get_twiddles(aefft_ctx* ctx, int N, const float2** out);
 // Pruned DFTs of the Nk x Nl-tap kernels (replace pad_k + full-size R2C and full-size C2R + shrink_k, which move
 // >= 20 bytes per bin to obtain / consume 25 numbers per image):

@@ -10,7 +10,8 @@ using namespace aefft;
 
 namespace aefft {
 
-static bool pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+// transform lengths: even 2^a 3^b 5^c (fft_kernels.cu); the name is historical
+static bool pow2(int n) { return aefft::fft_len_supported(n); }
 
 // C = R2C(pad(c)) for n_img kernels (StoreLoad_cfreq first-time branch, fft_backproplib.cu:1148-1157; backprop :1274-1282)
 // Evaluated directly from the Nk x Nl taps (pruned DFT): mathematically the same spectrum, no padded image, one write.

@@ -1,4 +1,6 @@
-// Hand-written batched 2-D real-to-complex / complex-to-real FFT (power-of-two Nx, Ny), fp32, unnormalised both ways.
+// Hand-written batched 2-D real-to-complex / complex-to-real FFT, fp32, unnormalised both ways.  Lengths: even numbers of the
+// form 2^a 3^b 5^c up to 8192 (the camera's 640 x 480 and its pooled levels in momentum space); powers of two take
+// the compile-time kernels further down, every other length the run-time mixed-radix kernels (radix 8 / 5 / 4 / 3 / 2).
 // Replaces the cufftPlanMany + cufftExecR2C / cufftExecC2R call sites of the reference
 // (fft_backproplib.cu:779/796, 821/829, 885/910, 937/946, 1208-1209/1219-1220/1281-1282), which also re-create and
 // destroy their plans on every call.
@@ -20,23 +22,35 @@
 namespace aefft {
 
 struct FftPlan {
-  int N, log2N;
+  int N;
   int npass;
-  int radix[6];
+  int radix[12];
 };
 
+// N = 2^a 3^b 5^c: the odd radices first, then the power-of-two part as one small radix and radix 8 for the rest (the small
+// radices run with the smallest strides, where bank conflicts are worst)
 static FftPlan make_plan(int N) {
   FftPlan p;
   p.N = N;
-  p.log2N = 0;
-  while ((1 << p.log2N) < N) p.log2N++;
   p.npass = 0;
-  int rem = p.log2N;
-  // small radix first (it runs with the smallest stride, where bank conflicts are worst), radix 8 for the rest
-  if (rem % 3 == 1) { p.radix[p.npass++] = 2; rem -= 1; }
-  else if (rem % 3 == 2) { p.radix[p.npass++] = 4; rem -= 2; }
-  while (rem > 0) { p.radix[p.npass++] = 8; rem -= 3; }
+  int rem = N;
+  while (rem % 5 == 0) { p.radix[p.npass++] = 5; rem /= 5; }
+  while (rem % 3 == 0) { p.radix[p.npass++] = 3; rem /= 3; }
+  int l2 = 0;
+  while (rem > 1 && rem % 2 == 0) { l2++; rem /= 2; }
+  if (l2 % 3 == 1) { p.radix[p.npass++] = 2; l2 -= 1; }
+  else if (l2 % 3 == 2) { p.radix[p.npass++] = 4; l2 -= 2; }
+  while (l2 > 0) { p.radix[p.npass++] = 8; l2 -= 3; }
   return p;
+}
+// even, only factors 2, 3, 5, at most 8192
+static bool fft_len_ok(int N) {
+  if (N < 2 || N > 8192 || (N & 1)) return false;
+  int r = N;
+  while (r % 2 == 0) r /= 2;
+  while (r % 3 == 0) r /= 3;
+  while (r % 5 == 0) r /= 5;
+  return r == 1;
 }
 
 // position of input sample n in the staged (digit-reversed) order: the LAST pass splits n by its radix first
@@ -46,7 +60,7 @@ __device__ __forceinline__ int digit_reverse(const FftPlan& p, int n) {
   for (int i = p.npass - 1; i >= 0; i--) {
     const int r = p.radix[i];
     M /= r;
-    pos += (n & (r - 1)) * M;
+    pos += (n % r) * M;
     n /= r;
   }
   return pos;
@@ -64,6 +78,34 @@ __device__ __forceinline__ void dft2(float2* a) {
   float2 t = a[0];
   a[0] = cadd(t, a[1]);
   a[1] = csub(t, a[1]);
+}
+// W3 = exp(-+ 2 pi i / 3) = (-1/2, -+ sqrt(3)/2)
+template <int DIR>
+__device__ __forceinline__ void dft3(float2* a) {
+  const float s3 = 0.86602540378443864676f;
+  const float2 t = cadd(a[1], a[2]), d = mul_mi<DIR>(csub(a[1], a[2]));  // d = -+ i (a1 - a2)
+  const float2 m = make_float2(a[0].x - 0.5f * t.x, a[0].y - 0.5f * t.y);
+  a[0] = cadd(a[0], t);
+  a[1] = make_float2(m.x + s3 * d.x, m.y + s3 * d.y);
+  a[2] = make_float2(m.x - s3 * d.x, m.y - s3 * d.y);
+}
+// 5-point DFT (Rader / Winograd-style pairing): X[k] = a0 + sum_j a_j W5^(jk)
+template <int DIR>
+__device__ __forceinline__ void dft5(float2* a) {
+  const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;  // cos(2 pi / 5), cos(4 pi / 5)
+  const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;   // sin(2 pi / 5), sin(4 pi / 5)
+  const float2 p1 = cadd(a[1], a[4]), p2 = cadd(a[2], a[3]);
+  const float2 q1 = mul_mi<DIR>(csub(a[1], a[4])), q2 = mul_mi<DIR>(csub(a[2], a[3]));  // -+ i (a1 - a4), -+ i (a2 - a3)
+  const float2 a0 = a[0];
+  const float2 u1 = make_float2(a0.x + c1 * p1.x + c2 * p2.x, a0.y + c1 * p1.y + c2 * p2.y);
+  const float2 u2 = make_float2(a0.x + c2 * p1.x + c1 * p2.x, a0.y + c2 * p1.y + c1 * p2.y);
+  const float2 v1 = make_float2(s1 * q1.x + s2 * q2.x, s1 * q1.y + s2 * q2.y);
+  const float2 v2 = make_float2(s2 * q1.x - s1 * q2.x, s2 * q1.y - s1 * q2.y);
+  a[0] = make_float2(a0.x + p1.x + p2.x, a0.y + p1.y + p2.y);
+  a[1] = cadd(u1, v1);
+  a[4] = csub(u1, v1);
+  a[2] = cadd(u2, v2);
+  a[3] = csub(u2, v2);
 }
 template <int DIR>
 __device__ __forceinline__ void dft4(float2* a) {
@@ -148,7 +190,9 @@ __device__ __forceinline__ void fft_pass(float2* s, int N, int M, int nseq, int 
       }
     }
     if (R == 2) dft2<DIR>(a);
+    else if (R == 3) dft3<DIR>(a);
     else if (R == 4) dft4<DIR>(a);
+    else if (R == 5) dft5<DIR>(a);
     else dft8<DIR>(a);
 #pragma unroll
     for (int j = 0; j < R; j++) base[(size_t)j * M * sn] = a[j];
@@ -164,7 +208,9 @@ __device__ __forceinline__ void fft_smem(float2* s, const FftPlan& p, int nseq, 
     __syncthreads();
     const int r = p.radix[i];
     if (r == 2) fft_pass<DIR, 2>(s, p.N, M, nseq, sn, sc, seq_fast, tw);
+    else if (r == 3) fft_pass<DIR, 3>(s, p.N, M, nseq, sn, sc, seq_fast, tw);
     else if (r == 4) fft_pass<DIR, 4>(s, p.N, M, nseq, sn, sc, seq_fast, tw);
+    else if (r == 5) fft_pass<DIR, 5>(s, p.N, M, nseq, sn, sc, seq_fast, tw);
     else fft_pass<DIR, 8>(s, p.N, M, nseq, sn, sc, seq_fast, tw);
     M *= r;
   }
@@ -174,13 +220,14 @@ __device__ __forceinline__ void fft_smem(float2* s, const FftPlan& p, int nseq, 
 // ------------------------------------------------------------------------------------------------ row passes
 // R2C rows: real [img][Nx][Ny] -> complex [img][Nx][Nyr]
 __global__ void __launch_bounds__(256) fft_rows_r2c_kernel(const float* __restrict__ in, float2* __restrict__ out, int Nx,
-                                                           int Ny, int RP, FftPlan plan, const float2* __restrict__ tw) {
+                                                           int Ny, int RP, FftPlan plan, const float2* __restrict__ tw, int ch,
+                                                           long long fstride) {
   extern __shared__ __align__(16) float2 sm[];
   const int Nyr = Ny / 2 + 1;
   const int SP = Ny + 1;  // row pitch in complex elements (odd -> rows start in different banks)
   const long long img = blockIdx.y;
   const int rp0 = blockIdx.x * RP;
-  const float* src = in + img * (long long)Nx * Ny;
+  const float* src = in + (img / ch) * fstride + (img % ch) * (long long)Nx * Ny;
   for (int idx = threadIdx.x; idx < RP * Ny; idx += blockDim.x) {
     const int r = idx / Ny, n = idx % Ny;
     const int row = 2 * (rp0 + r);
@@ -198,7 +245,7 @@ __global__ void __launch_bounds__(256) fft_rows_r2c_kernel(const float* __restri
     const int row = 2 * (rp0 + r);
     if (row >= Nx) continue;
     const float2 z1 = sm[r * SP + k];
-    const float2 z2 = sm[r * SP + ((Ny - k) & (Ny - 1))];
+    const float2 z2 = sm[r * SP + (k == 0 ? 0 : Ny - k)];
     // Xa = (Z[k] + conj Z[N-k]) / 2 ;  Xb = (Z[k] - conj Z[N-k]) / (2i)
     dst[(long long)row * Nyr + k] = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
     dst[(long long)(row + 1) * Nyr + k] = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
@@ -209,7 +256,7 @@ __global__ void __launch_bounds__(256) fft_rows_r2c_kernel(const float* __restri
 // of each row are ignored, as a Hermitian C2R does.
 __global__ void __launch_bounds__(256) fft_rows_c2r_kernel(const float2* __restrict__ in, float* __restrict__ out, int Nx,
                                                            int Ny, int RP, FftPlan plan, const float2* __restrict__ tw,
-                                                           float scale) {
+                                                           float scale, int ch, long long fstride) {
   extern __shared__ __align__(16) float2 sm[];
   const int Nyr = Ny / 2 + 1;
   const int SP = Ny + 1;
@@ -230,7 +277,7 @@ __global__ void __launch_bounds__(256) fft_rows_c2r_kernel(const float2* __restr
     if (k > 0 && k < Ny / 2) sm[r * SP + digit_reverse(plan, Ny - k)] = make_float2(a.x + b.y, b.x - a.y);
   }
   fft_smem<+1>(sm, plan, RP, 1, SP, false, tw);
-  float* dst = out + img * (long long)Nx * Ny;
+  float* dst = out + (img / ch) * fstride + (img % ch) * (long long)Nx * Ny;
   for (int idx = threadIdx.x; idx < RP * Ny; idx += blockDim.x) {
     const int r = idx / Ny, n = idx % Ny;
     const int row = 2 * (rp0 + r);
@@ -838,6 +885,7 @@ static int ilog2(int n) { int l = 0; while ((1 << l) < n) l++; return l; }
 
 // ------------------------------------------------------------------------------------------------ host side
 static bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+bool fft_len_supported(int N) { return fft_len_ok(N); }
 
 int get_twiddles(aefft_ctx* ctx, int N, const float2** out) {
   char name[32];
@@ -887,7 +935,7 @@ int launch_fft_r2c(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float* i
 // AEFFT_ERR_UNSUPPORTED when the layout is not contiguous and the length has no strided-capable kernel.
 int launch_fft_r2c_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float* in, int ch, long long fstride,
                            float2* spec) {
-  AE_ARG(batch > 0 && is_pow2(Nx) && is_pow2(Ny) && Nx >= 2 && Ny >= 2 && Nx <= 8192 && Ny <= 8192);
+  AE_ARG(batch > 0 && fft_len_ok(Nx) && fft_len_ok(Ny));
   AE_ARG(batch <= 65535);
   const int Nyr = Ny / 2 + 1;
   const float2 *twx, *twy;
@@ -900,10 +948,9 @@ int launch_fft_r2c_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const 
     AE_TRY(set_smem(fft_rows_r2c_kernel, smem));
     dim3 grid((Nx / 2 + RP - 1) / RP, (unsigned)batch);
     ProfScope prof(ctx, "fft_rows_r2c", 2.5 * px * log2((double)Ny), 4.0 * px + 8.0 * sp);
-    const bool contiguous = fstride == (long long)ch * Nx * Ny;
-    const int rc = rows_r2c_fast(ctx, ilog2(Ny), batch, Nx, in, spec, twy, ch, fstride);
-    if (rc == AEFFT_ERR_UNSUPPORTED && !contiguous) return rc;
-    if (rc == AEFFT_ERR_UNSUPPORTED) fft_rows_r2c_kernel<<<grid, 256, smem, ctx->stream>>>(in, spec, Nx, Ny, RP, make_plan(Ny), twy);
+    const int rc = is_pow2(Ny) ? rows_r2c_fast(ctx, ilog2(Ny), batch, Nx, in, spec, twy, ch, fstride) : AEFFT_ERR_UNSUPPORTED;
+    if (rc == AEFFT_ERR_UNSUPPORTED)
+      fft_rows_r2c_kernel<<<grid, 256, smem, ctx->stream>>>(in, spec, Nx, Ny, RP, make_plan(Ny), twy, ch, fstride);
     else if (rc != AEFFT_OK) return rc;
   }
   {
@@ -912,7 +959,7 @@ int launch_fft_r2c_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const 
     AE_TRY(set_smem(fft_cols_kernel<-1>, smem));
     dim3 grid((Nyr + CT - 1) / CT, (unsigned)batch);
     ProfScope prof(ctx, "fft_cols", 5.0 * sp * log2((double)Nx), 16.0 * sp);
-    const int rc = cols_fast<-1>(ctx, ilog2(Nx), batch, Nyr, spec, spec, twx);
+    const int rc = is_pow2(Nx) ? cols_fast<-1>(ctx, ilog2(Nx), batch, Nyr, spec, spec, twx) : AEFFT_ERR_UNSUPPORTED;
     if (rc == AEFFT_ERR_UNSUPPORTED) fft_cols_kernel<-1><<<grid, 256, smem, ctx->stream>>>(spec, spec, Nx, Nyr, CT, make_plan(Nx), twx);
     else if (rc != AEFFT_OK) return rc;
   }
@@ -954,7 +1001,8 @@ static int rows_c2r_embed(aefft_ctx* ctx, int64_t batch, int Nx, const float2* t
 
 int launch_fft_r2c_pooled(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, int Nxs, int Nys, const float* in, float2* tmp,
                           float2* out) {
-  AE_ARG(batch > 0 && batch <= 65535 && is_pow2(Nx) && is_pow2(Ny) && is_pow2(Nxs) && is_pow2(Nys));
+  AE_ARG(batch > 0 && batch <= 65535);
+  if (!(is_pow2(Nx) && is_pow2(Ny) && is_pow2(Nxs) && is_pow2(Nys))) return AEFFT_ERR_UNSUPPORTED;
   if (getenv("AEFFT_FFT_V1") || getenv("AEFFT_NO_FFT_POOL") || Nxs >= Nx || Nys >= Ny || Nxs < 4 || Nys < 4) return AEFFT_ERR_UNSUPPORTED;
   const int ly = ilog2(Ny), lx = ilog2(Nx), keep = Nys / 2 + 1;
   if (ly < 3 || ly > 12 || lx < 3 || lx > 12) return AEFFT_ERR_UNSUPPORTED;
@@ -992,7 +1040,8 @@ int launch_fft_r2c_pooled(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, int Nxs
 // tmp: batch*Nx*(Nys/2+1) complex.
 int launch_fft_c2r_embedded(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, int Nxs, int Nys, const float2* spec, float2* tmp,
                             float* out, float scale) {
-  AE_ARG(batch > 0 && batch <= 65535 && is_pow2(Nx) && is_pow2(Ny) && is_pow2(Nxs) && is_pow2(Nys));
+  AE_ARG(batch > 0 && batch <= 65535);
+  if (!(is_pow2(Nx) && is_pow2(Ny) && is_pow2(Nxs) && is_pow2(Nys))) return AEFFT_ERR_UNSUPPORTED;
   if (getenv("AEFFT_FFT_V1") || getenv("AEFFT_NO_FFT_POOL") || Nxs >= Nx || Nys >= Ny || Nxs < 4 || Nys < 4) return AEFFT_ERR_UNSUPPORTED;
   const int ly = ilog2(Ny), lx = ilog2(Nx), keep = Nys / 2 + 1;
   if (ly < 3 || ly > 12 || lx < 3 || lx > 12) return AEFFT_ERR_UNSUPPORTED;
@@ -1033,7 +1082,7 @@ int launch_fft_c2r(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float2* 
 
 int launch_fft_c2r_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const float2* spec, float2* work, float* out, int ch,
                            long long fstride, float scale) {
-  AE_ARG(batch > 0 && is_pow2(Nx) && is_pow2(Ny) && Nx >= 2 && Ny >= 2 && Nx <= 8192 && Ny <= 8192);
+  AE_ARG(batch > 0 && fft_len_ok(Nx) && fft_len_ok(Ny));
   AE_ARG(batch <= 65535);
   const int Nyr = Ny / 2 + 1;
   const float2 *twx, *twy;
@@ -1046,7 +1095,7 @@ int launch_fft_c2r_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const 
     AE_TRY(set_smem(fft_cols_kernel<+1>, smem));
     dim3 grid((Nyr + CT - 1) / CT, (unsigned)batch);
     ProfScope prof(ctx, "fft_cols", 5.0 * sp * log2((double)Nx), 16.0 * sp);
-    const int rc = cols_fast<+1>(ctx, ilog2(Nx), batch, Nyr, spec, work, twx);
+    const int rc = is_pow2(Nx) ? cols_fast<+1>(ctx, ilog2(Nx), batch, Nyr, spec, work, twx) : AEFFT_ERR_UNSUPPORTED;
     if (rc == AEFFT_ERR_UNSUPPORTED) fft_cols_kernel<+1><<<grid, 256, smem, ctx->stream>>>(spec, work, Nx, Nyr, CT, make_plan(Nx), twx);
     else if (rc != AEFFT_OK) return rc;
   }
@@ -1056,10 +1105,9 @@ int launch_fft_c2r_strided(aefft_ctx* ctx, int64_t batch, int Nx, int Ny, const 
     AE_TRY(set_smem(fft_rows_c2r_kernel, smem));
     dim3 grid((Nx / 2 + RP - 1) / RP, (unsigned)batch);
     ProfScope prof(ctx, "fft_rows_c2r", 2.5 * px * log2((double)Ny), 4.0 * px + 8.0 * sp);
-    const bool contiguous = fstride == (long long)ch * Nx * Ny;
-    const int rc = rows_c2r_fast(ctx, ilog2(Ny), batch, Nx, work, out, twy, scale, ch, fstride);
-    if (rc == AEFFT_ERR_UNSUPPORTED && !contiguous) return rc;
-    if (rc == AEFFT_ERR_UNSUPPORTED) fft_rows_c2r_kernel<<<grid, 256, smem, ctx->stream>>>(work, out, Nx, Ny, RP, make_plan(Ny), twy, scale);
+    const int rc = is_pow2(Ny) ? rows_c2r_fast(ctx, ilog2(Ny), batch, Nx, work, out, twy, scale, ch, fstride) : AEFFT_ERR_UNSUPPORTED;
+    if (rc == AEFFT_ERR_UNSUPPORTED)
+      fft_rows_c2r_kernel<<<grid, 256, smem, ctx->stream>>>(work, out, Nx, Ny, RP, make_plan(Ny), twy, scale, ch, fstride);
     else if (rc != AEFFT_OK) return rc;
   }
   ctx->launches += 2;

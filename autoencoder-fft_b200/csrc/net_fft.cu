@@ -40,7 +40,7 @@ void net_fft_release(aefft_net* net) {
 
 namespace {
 
-bool pow2i(int n) { return n > 0 && (n & (n - 1)) == 0; }
+bool pow2i(int n) { return fft_len_supported(n); }  // even 2^a 3^b 5^c (the name is historical)
 
 // resolution level of layer l (-1: frame resolution): level n holds layers 2n+1, 2n+2, 2N-2-2n, 2N-1-2n
 int level_of(int l, int N) {
@@ -226,6 +226,8 @@ bool decoder_support_capable(const aefft_net* net, int fft_l) {
   if (fft_l == 0) {
     const LayerL& Zf = net->layers[2 * N];
     if (!(S0.Nx < Zf.Nx && S0.Ny < Zf.Ny) || getenv("AEFFT_FFT_V1") || getenv("AEFFT_NO_FFT_POOL")) return false;
+    auto p2 = [](int n) { return n > 0 && (n & (n - 1)) == 0; };  // the embedding inverse transform has power-of-two kernels only
+    if (!p2(Zf.Nx) || !p2(Zf.Ny) || !p2(S0.Nx) || !p2(S0.Ny)) return false;
     const int lx = ilog2i(Zf.Nx), ly = ilog2i(Zf.Ny);
     if (lx < 3 || lx > 12 || ly < 3 || ly > 12 || net->B * Zf.D > 65535) return false;
   }

@@ -357,8 +357,8 @@ __global__ void __launch_bounds__(256) kernel_spectrum_emb_kernel(const float* _
     float2 v = make_float2(0.f, 0.f);
     if (w < S) {
       const int wx = (int)(w / ncols), wy = col0 + (int)(w - (long long)wx * ncols);
-      const float2 ex = twx[(wx * ((k - Nk / 2) & (Nx - 1))) & (Nx - 1)];
-      const float2 ey = twy[(wy * ((l - Nl / 2) & (Ny - 1))) & (Ny - 1)];
+      const float2 ex = twx[tw_index(wx, k - Nk / 2, Nx)];
+      const float2 ey = twy[tw_index(wy, l - Nl / 2, Ny)];
       v = make_float2(ex.x * ey.x - ex.y * ey.y, ex.x * ey.y + ex.y * ey.x);
     }
     ph[bi][t] = v;
@@ -394,8 +394,8 @@ __global__ void __launch_bounds__(256) kernel_spectrum_emb_kernel_t(const float*
     float2 v = make_float2(0.f, 0.f);
     if (w < S) {
       const int wx = (int)(w / ncols), wy = col0 + (int)(w - (long long)wx * ncols);
-      const float2 ex = twx[(wx * ((k - Nk / 2) & (Nx - 1))) & (Nx - 1)];
-      const float2 ey = twy[(wy * ((l - Nl / 2) & (Ny - 1))) & (Ny - 1)];
+      const float2 ex = twx[tw_index(wx, k - Nk / 2, Nx)];
+      const float2 ey = twy[tw_index(wy, l - Nl / 2, Ny)];
       v = make_float2(ex.x * ey.x - ex.y * ey.y, ex.x * ey.y + ex.y * ey.x);
     }
     ph[bi][t] = v;
@@ -437,12 +437,12 @@ __global__ void __launch_bounds__(256) kernel_spectrum_emb_sep_kernel(const floa
   for (int i = threadIdx.x; i < KS_ROWS * NK; i += blockDim.x) {
     const int rr = i / NK, k = i - rr * NK, wx = wx0 + rr;
     const int wxb = Nxm > 0 ? (wx < Nxm / 2 ? wx : (wx == Nxm / 2 ? Nx / 2 : wx + Nx - Nxm)) : wx;
-    ex[rr][k] = wx < rows ? twx[(wxb * ((k - NK / 2) & (Nx - 1))) & (Nx - 1)] : make_float2(0.f, 0.f);
+    ex[rr][k] = wx < rows ? twx[tw_index(wxb, k - NK / 2, Nx)] : make_float2(0.f, 0.f);
   }
   for (int i = threadIdx.x; i < KS_COLS * NL; i += blockDim.x) {
     const int cc = i / NL, l = i - cc * NL, wy = col0 + wl0 + cc;
     const int wyb = Nxm > 0 ? (wy < ncols - 1 ? wy : Ny / 2) : wy;
-    ey[cc][l] = wl0 + cc < ncols ? twy[(wyb * ((l - NL / 2) & (Ny - 1))) & (Ny - 1)] : make_float2(0.f, 0.f);
+    ey[cc][l] = wl0 + cc < ncols ? twy[tw_index(wyb, l - NL / 2, Ny)] : make_float2(0.f, 0.f);
   }
   __syncthreads();
   const int e = blockIdx.y * blockDim.x + threadIdx.x;
@@ -501,8 +501,8 @@ __global__ void __launch_bounds__(128) binmajor_to_taps_kernel(const float2* __r
       if (w < w_hi) {
         const int wx = (int)(w / ncols), wy = col0 + (int)(w - (long long)wx * ncols);
         const float h = (wy == 0 || wy == Ny / 2) ? 1.f : 2.f;
-        const float2 ex = twx[(wx * ((k - Nk / 2) & (Nx - 1))) & (Nx - 1)];
-        const float2 ey = twy[(wy * ((l - Nl / 2) & (Ny - 1))) & (Ny - 1)];
+        const float2 ex = twx[tw_index(wx, k - Nk / 2, Nx)];
+        const float2 ey = twy[tw_index(wy, l - Nl / 2, Ny)];
         v = make_float2(h * (ex.x * ey.x - ex.y * ey.y), h * (ex.x * ey.y + ex.y * ey.x));
       }
       ph[bi][t] = v;
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(128) binmajor_to_taps_sep_kernel(const float2*
   for (int i = threadIdx.x; i < ncols * NL; i += blockDim.x) {
     const int wl = i / NL, l = i - wl * NL, wy = col0 + wl;
     const float h = (wy == 0 || wy == Ny / 2) ? 1.f : 2.f;
-    const float2 ey = twy[(wy * ((l - NL / 2) & (Ny - 1))) & (Ny - 1)];
+    const float2 ey = twy[tw_index(wy, l - NL / 2, Ny)];
     phy[i] = make_float2(h * ey.x, h * ey.y);
   }
   __syncthreads();
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(128) binmajor_to_taps_sep_kernel(const float2*
     }
 #pragma unroll
     for (int k = 0; k < NK; k++) {
-      const float2 ex = __ldg(twx + ((wx * ((k - NK / 2) & (Nx - 1))) & (Nx - 1)));
+      const float2 ex = __ldg(twx + (tw_index(wx, k - NK / 2, Nx)));
 #pragma unroll
       for (int l = 0; l < NL; l++) g[k * NL + l] = fmaf(t[l].x, ex.x, fmaf(t[l].y, ex.y, g[k * NL + l]));  // Re(t conj(ex))
     }

@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(128) kernel_spectrum_direct_kernel(const float
 #pragma unroll
   for (int l = 0; l < (NL ? NL : PD_MAXT); l++) {
     if (l < nl) {
-      const float2 ey = __ldg(twy + ((wy * ((l - nl / 2) & (Ny - 1))) & (Ny - 1)));
+      const float2 ey = __ldg(twy + (tw_index(wy, l - nl / 2, Ny)));
 #pragma unroll
       for (int k = 0; k < (NK ? NK : PD_MAXT); k++) {
         if (k < nk) {
@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(128) kernel_spectrum_direct_kernel(const float
 #pragma unroll
     for (int k = 0; k < (NK ? NK : PD_MAXT); k++) {
       if (k < nk) {
-        const float2 ex = __ldg(twx + ((wx * ((k - nk / 2) & (Nx - 1))) & (Nx - 1)));  // warp-uniform address
+        const float2 ex = __ldg(twx + (tw_index(wx, k - nk / 2, Nx)));  // warp-uniform address
         cfma(acc, ex, t[k]);
       }
     }
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(768) spectrum_to_taps_kernel(const float2* __r
 #pragma unroll
       for (int k = 0; k < TK; k++) {
         if (k < nk) {
-          const float2 e = __ldg(twx + ((wx * ((k - nk / 2) & (Nx - 1))) & (Nx - 1)));  // warp-uniform address
+          const float2 e = __ldg(twx + (tw_index(wx, k - nk / 2, Nx)));  // warp-uniform address
           b[k].x = fmaf(v.x, e.x, fmaf(v.y, e.y, b[k].x));   // v * conj(e)
           b[k].y = fmaf(v.y, e.x, fmaf(-v.x, e.y, b[k].y));
         }
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(768) spectrum_to_taps_kernel(const float2* __r
 #pragma unroll
     for (int l = 0; l < TL; l++) {
       if (l < nl) {
-        const float2 ey = __ldg(twy + ((wy * ((l - nl / 2) & (Ny - 1))) & (Ny - 1)));
+        const float2 ey = __ldg(twy + (tw_index(wy, l - nl / 2, Ny)));
 #pragma unroll
         for (int k = 0; k < TK; k++)
           if (k < nk) g[k * TL + l] = fmaf(h, b[k].x * ey.x + b[k].y * ey.y, g[k * TL + l]);  // h * Re(b * conj(ey))

@@ -20,7 +20,10 @@ def cplx(w):
 
 
 @pytest.mark.parametrize("shape", [(1, 8, 8), (3, 16, 16), (2, 32, 16), (2, 16, 64), (5, 128, 128), (2, 256, 512),
-                                   (1, 1024, 1024), (1, 2048, 256), (1, 4, 2048), (1, 4096, 8), (3, 2, 2)])
+                                   (1, 1024, 1024), (1, 2048, 256), (1, 4, 2048), (1, 4096, 8), (3, 2, 2),
+                                   # mixed radix (2^a 3^b 5^c): the camera format and its pooled levels
+                                   (2, 6, 10), (3, 40, 30), (2, 80, 60), (1, 160, 120), (1, 640, 480), (1, 12, 1000),
+                                   (1, 486, 250), (1, 16, 30), (1, 30, 16)])
 def test_r2c_c2r_vs_numpy(ctx, shape):
     rng = np.random.default_rng(sum(shape))
     x = (rng.random(shape) * 255).astype(np.float32)
@@ -115,7 +118,9 @@ def fft_case(seed, dM, dD, Nk, Nl, Nx, Ny, B=None, wscale=0.5):
 
 @pytest.mark.parametrize("dims,maxdiff,B", [((4, 3, 5, 5, 16, 16), 0, None), ((3, 2, 3, 3, 32, 16), 0, None),
                                            ((4, 3, 5, 5, 16, 16), 1, None), ((6, 3, 5, 5, 32, 32), 0, 3),
-                                           ((5, 4, 3, 3, 16, 32), 1, 2)])
+                                           ((5, 4, 3, 3, 16, 32), 1, 2),
+                                           # lengths with factors 3 and 5 (640 x 480 pooled four / five times)
+                                           ((4, 3, 5, 5, 40, 30), 0, 2), ((8, 3, 3, 3, 20, 30), 1, None)])
 def test_backprop_fft_vs_oracle(ctx, dims, maxdiff, B):
     cs = fft_case(3, *dims, B=B)
     n_iter = 6

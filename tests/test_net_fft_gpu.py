@@ -33,6 +33,8 @@ CASES = [
     (3, 64, 64, [8, 16], [2, 2], 16),        # pair 0 CUDA cores, pair 1 tensor cores (layout change at the pooling)
     (8, 32, 64, [16, 8], [2, 1], 17),        # both pairs tensor cores, pool 1 between them, rectangular
     (3, 64, 128, [8, 16, 32], [2, 2, 2], 16), # the c3 stack at reduced size
+    (3, 160, 120, [4, 8], [2, 2], 3),         # the camera's aspect (factors 3 and 5): 80 x 60 and 40 x 30 levels
+    (3, 80, 120, [8, 16], [2, 2], 16),        # the same with a tensor-core pair (40 x 60, 20 x 30)
 ]
 
 
@@ -160,7 +162,7 @@ def test_net_fft_forward_fused_pooling_at_full_resolution(ctx, size, pool):
 
 
 @pytest.mark.parametrize("cfg", [(3, 64, 32, [4, 5], [2, 2], 3), (3, 64, 64, [16, 32], [2, 2], 16), (1, 32, 64, [8, 16], [1, 2], 16),
-                                 (3, 64, 128, [8, 16, 32], [2, 2, 2], 16)])
+                                 (3, 64, 128, [8, 16, 32], [2, 2, 2], 16), (3, 80, 120, [8, 16], [2, 2], 16)])
 def test_net_fft_forward_fused_with_level_changes_equals_unfused(ctx, cfg, monkeypatch):
     """fft_l <= 0: the image-side convs run fused with the spectral pooling after / the up-sampling before them and compute
     only the kept bins (net_fft.cu: conv_then_pool / unpool_then_conv); a tensor-core level followed by a pooling does the
@@ -185,8 +187,11 @@ def test_net_fft_forward_fused_with_level_changes_equals_unfused(ctx, cfg, monke
             names = {r["name"] for r in ctx.profile_records()}
             ctx.profile_enable(False)
             assert ("spec_contract_reg_pool" in names) == (not nofuse), names
-            assert ("spec_contract_reg_embed" in names) == (mode == "dense_decoder"), names
-            assert ("spec_contract_reg_support" in names) == (mode == "default"), names
+            # (the decoder runs on the support grid only when the reconstruction's embedding inverse transform exists:
+            # power-of-two frames)
+            sparse = mode == "default" and all(v & (v - 1) == 0 for v in (Nx, Ny))
+            assert ("spec_contract_reg_embed" in names) == (not nofuse and not sparse), names
+            assert ("spec_contract_reg_support" in names) == sparse, names
             out.append((np.array(traces), net.layer(net.num_layers - 1).copy(),
                         [net.get_conv(n)[0].copy() for n in range(2 * net.num_pairs)]))
         finally:
@@ -196,3 +201,27 @@ def test_net_fft_forward_fused_with_level_changes_equals_unfused(ctx, cfg, monke
         assert np.array_equal(out[0][1], other[1])
         for a, b in zip(out[0][2], other[2]):
             assert np.array_equal(a, b)
+
+
+def test_net_fft_step_at_the_camera_format(ctx):
+    """640 x 480 frames in momentum space (lengths 640 = 2^7 5 and 480 = 2^5 3 5 and their pooled levels run on
+    the mixed-radix transforms): one step of the c3 stack against the reference-shaped C-ABI path of this engine (per-layer
+    transforms), which the small mixed-radix cases above pin against the fp64 oracle."""
+    net, net_c, net_b, scale, shapes = make_net(ctx, 3, 640, 480, [16, 32, 64], [2, 2, 2], 16)
+    try:
+        P, N = 3, 6
+        x = O.synth_frames(13, 16, 3, 640, 480)
+        traces = net.fft_step(x, del0=0.2, maxdiff=0, n_iter=1, fft_l=0)
+        trained = [net.get_conv(n) for n in range(N)]
+        layers, _ = ctx.autoenc_fft(x, net_c, net_b, scale, shapes, None, 1)
+        layers = [np.ascontiguousarray(t) for t in layers]
+        assert O.rel_l2(net.layer(len(shapes) - 1), layers[-1]) < 2e-5
+        for n in range(P):
+            c, f, b, p = (net_c[n].copy(), net_c[N - 1 - n].copy(), net_b[n].copy(), net_b[N - 1 - n].copy())
+            li, lo = 2 * n + 1, 2 * N - 1 - 2 * n
+            tr = ctx.backprop_fft(layers[li], layers[li], layers[lo], c, f, b, p, 0.2, 0, 1)
+            assert np.allclose(traces[n], tr, rtol=1e-4), (n, traces[n], tr)
+            for got, want in ((trained[n][0], c), (trained[N - 1 - n][0], f), (trained[n][1], b), (trained[N - 1 - n][1], p)):
+                assert O.rel_l2(got, want) < 2e-5, n
+    finally:
+        net.close()
