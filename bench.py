@@ -51,6 +51,9 @@ WORKLOADS = {
     # backprop_fft call amortise the frame transforms (the reference runs 100 per call)
     "c4": dict(D=3, Nx=2048, Ny=2048, widths=[16, 32, 64, 128, 256], Lk=1, Ll=1, pool=2, rmax=3.0, batch=32, space="fft",
                shard="bins", n_iter=10, maxdiff=1),
+    # the c2 stack in momentum space on the camera's 640x480 frames: lengths with factors 3 and 5 run on the
+    # mixed-radix transforms (--workload c3cam --only; not part of the default line)
+    "c3cam": dict(D=3, Nx=640, Ny=480, widths=[16, 32, 64], Lk=1, Ll=1, pool=2, rmax=3.0, batch=64, space="fft"),
 }
 DELMAX, ALPHA = 0.2, 0.9  # autoencoder.cpp:87-89
 METRIC = "training frames/sec (fwd+backprop)"

@@ -157,7 +157,9 @@ int aefft_coord_update(aefft_ctx* ctx, int mode, int64_t B_global, int dD, int d
 
 /* Batched 2-D real-to-complex / complex-to-real transforms, unnormalised both ways, n={Nx,Ny}; replaces the
  * cufftPlanMany+cufftExecR2C/C2R call sites fft_backproplib.cu:779/796, 821/829, 885/910, 937/946, 1208-1282.
- * spec is interleaved (re,im) [batch][Nx][Ny/2+1][2].  Nx, Ny powers of two (8..8192). */
+ * spec is interleaved (re,im) [batch][Nx][Ny/2+1][2].  Nx, Ny: even numbers of the form 2^a 3^b 5^c up to 8192 (the same
+ * holds for every momentum-space entry point below); powers of two take the fast compile-time kernels, other lengths (the
+ * camera's 640 x 480 and its pooled levels) the run-time mixed-radix kernels. */
 int aefft_fft_r2c(aefft_ctx* ctx, int loc, int64_t batch, int Nx, int Ny, const float* in, float* spec);
 int aefft_fft_c2r(aefft_ctx* ctx, int loc, int64_t batch, int Nx, int Ny, const float* spec, float* out);
 
