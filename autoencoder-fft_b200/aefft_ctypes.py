@@ -507,6 +507,13 @@ class Net:
         ptr = images.ctypes.data if isinstance(images, np.ndarray) else int(images)
         _chk(lib().aefft_net_set_frames_u8(self.h, loc, C.c_void_p(ptr)))
 
+    def get_layer_u8(self, layer, mode=0):
+        """SpinToImage_C (mode 0) / SpinToImage_V (mode 1) of a layer with <= 4 channels: uint8 [B][Ny][Nx][D]."""
+        D, Nx, Ny = self.layer_info(layer)[:3]
+        out = np.empty((self.B, Ny, Nx, D), np.uint8)
+        _chk(lib().aefft_net_get_layer_u8(self.h, int(layer), int(mode), HOST, C.c_void_p(out.ctypes.data)))
+        return out
+
     def step(self, frames, mode, delmax=0.2, alpha=0.9, quirks=QUIRKS_ALL, loc=HOST, mse=None):
         _chk(lib().aefft_net_step(self.h, loc, _ptr(frames), mode, quirks, C.c_float(delmax), C.c_float(alpha),
                                   _ptr(mse)))

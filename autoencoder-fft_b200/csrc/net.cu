@@ -304,7 +304,65 @@ __global__ void image_to_spin_kernel(const unsigned char* __restrict__ img, floa
   }
 }
 
+// SpinToImage_C (netlib.cpp:52-76): clamp(round(v), 0, 255) per channel, interleaved [rows = Ny][cols = Nx][D];
+// mode 1 = SpinToImage_V (:79-92): (int)v truncated, stored as uchar (wraps modulo 256)
+__global__ void spin_to_image_kernel(const float* __restrict__ spin, unsigned char* __restrict__ img, int D, int Nx, int Ny,
+                                     int mode) {
+  __shared__ unsigned char tile[32][32 * 4 + 4];  // [j][i*D + d], D <= 4
+  const long long b = blockIdx.z;
+  const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  const float* src = spin + b * (long long)D * Nx * Ny;
+  for (int idx = threadIdx.x; idx < D * 32 * 32; idx += blockDim.x) {
+    const int j = idx & 31, i = (idx >> 5) & 31, d = idx >> 10;
+    unsigned char o = 0;
+    if (i0 + i < Nx && j0 + j < Ny) {
+      const float v = src[((long long)d * Nx + i0 + i) * Ny + j0 + j];
+      if (mode == 0) {
+        int val = (int)roundf(v);
+        val = val <= 255 ? val : 255;
+        val = val >= 0 ? val : 0;
+        o = (unsigned char)val;
+      } else {
+        o = (unsigned char)(int)v;
+      }
+    }
+    tile[j][i * D + d] = o;
+  }
+  __syncthreads();
+  unsigned char* dst = img + b * (long long)Ny * Nx * D;
+  const int wbytes = 32 * D;
+  for (int idx = threadIdx.x; idx < 32 * wbytes; idx += blockDim.x) {
+    const int j = idx / wbytes, x = idx - j * wbytes;
+    const long long col = (long long)i0 * D + x;
+    if (j0 + j < Ny && col < (long long)Nx * D) dst[(long long)(j0 + j) * Nx * D + col] = tile[j][x];
+  }
+}
+
 extern "C" {
+
+int aefft_net_get_layer_u8(aefft_net* net, int layer, int mode, int loc, unsigned char* images) {
+  AE_ARG(net && images && layer >= 0 && layer < (int)net->layers.size() && (mode == 0 || mode == 1));
+  aefft_ctx* ctx = net->ctx;
+  AE_CUDA(cudaSetDevice(ctx->device));
+  const LayerL& L = net->layers[layer];
+  AE_ARG(L.D <= 4 && net->B <= 65535);
+  const size_t nbytes = (size_t)net->B * L.D * L.Nx * L.Ny;
+  unsigned char* dev = images;
+  if (loc == AEFFT_HOST) {
+    void* stage;
+    AE_TRY(ctx->get("net_layer_u8", nbytes, &stage));
+    dev = (unsigned char*)stage;
+  }
+  dim3 grid((L.Nx + 31) / 32, (L.Ny + 31) / 32, (unsigned)net->B);
+  spin_to_image_kernel<<<grid, 256, 0, ctx->stream>>>(L.p, dev, L.D, L.Nx, L.Ny, mode);
+  ctx->launches++;
+  AE_CUDA(cudaGetLastError());
+  if (loc == AEFFT_HOST) {
+    AE_CUDA(cudaMemcpyAsync(images, dev, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    AE_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return AEFFT_OK;
+}
 
 int aefft_net_set_frames_u8(aefft_net* net, int loc, const unsigned char* images) {
   AE_ARG(net && images);

@@ -5,6 +5,11 @@
 //                [--precision fp32|bf16x3|bf16] [--del 0.2] [--alpha 0.9] [--quirks 7] [--fft-iters 100]
 //                [--device K --rank R --world W --id-file PATH] [--sidecar]
 //                --script "n n t5 z t3 p t2 s d l t1 i f g t1"
+// --video FILE: training frames come from a raw 8-bit video instead of the synthetic generator -- consecutive interleaved images
+//   [frame][rows = Ny][cols = Nx][D] (what `ffmpeg -i in.mp4 -f rawvideo -pix_fmt bgr24 FILE` writes; the reference's webcam
+//   loop feeds cv::Mat frames of exactly this layout through ImageToSpin_C), converted on the device; the file wraps around.
+// --dump FILE: after the script, one more forward of the last batch and its reconstruction written as raw 8-bit frames of the
+//   same layout (SpinToImage_C: clamp(round(v), 0, 255)).
 // --rank/--world/--id-file: data-parallel frames over W processes, one GPU each, WITHOUT any Python: rank 0 writes the
 // NCCL unique id (aefft_comm_unique_id) to PATH, the others read it, every rank calls aefft_comm_init; rank r then
 // trains on frames [it*W*B + r*B, +B) and the engine all-reduces the raw gradient block before every update, so all
@@ -47,7 +52,7 @@ int main(int argc, char** argv) {
   int D = 3, Nx = 640, Ny = 480, precision = AEFFT_PRECISION_BF16X3, quirks = -1;
   unsigned seed = 1234;
   float del = 0.2f, alpha = 0.9f;
-  std::string param = "New_Layer_Param.txt", weights = "./weights", script, id_file;
+  std::string param = "New_Layer_Param.txt", weights = "./weights", script, id_file, video, dump;
   int device = 0, rank = 0, world = 1, fft_iters = 100, sidecar = 0;
   for (int a = 1; a < argc; a++) {
     const std::string k = argv[a];
@@ -66,6 +71,8 @@ int main(int argc, char** argv) {
     else if (k == "--rank") { rank = std::atoi(v); a++; }
     else if (k == "--world") { world = std::atoi(v); a++; }
     else if (k == "--id-file") { id_file = v; a++; }
+    else if (k == "--video") { video = v; a++; }
+    else if (k == "--dump") { dump = v; a++; }
     else if (k == "--fft-iters") { fft_iters = std::atoi(v); a++; }
     else if (k == "--sidecar") { sidecar = 1; }
     else if (k == "--precision") {
@@ -98,6 +105,18 @@ int main(int argc, char** argv) {
     CHECK(aefft_comm_init(ctx, id, rank, world));
   }
   CHECK(aefft_net_create(ctx, &net, D, Nx, Ny, B));
+  FILE* vfh = nullptr;
+  const size_t fbytes = (size_t)Nx * Ny * D;
+  int64_t vframes = 0;
+  std::vector<unsigned char> vbuf;
+  if (!video.empty()) {
+    vfh = std::fopen(video.c_str(), "rb");
+    if (!vfh) { std::fprintf(stderr, "aefft_replay: cannot open %s\n", video.c_str()); return 1; }
+    std::fseek(vfh, 0, SEEK_END);
+    vframes = (int64_t)(std::ftell(vfh) / (long)fbytes);
+    if (vframes < 1 || D > 4) { std::fprintf(stderr, "aefft_replay: %s holds no %dx%dx%d frame\n", video.c_str(), Nx, Ny, D); return 1; }
+    vbuf.resize((size_t)B * fbytes);
+  }
   std::srand(seed);  // the reference seeds once and draws every Init_conv from the same stream (autoencoder.cpp:100)
   int n_l = 0, sym = 0, fft = 0, fft_l = 0, maxdiff = 0;
   int64_t frame0 = 0;
@@ -190,7 +209,20 @@ int main(int argc, char** argv) {
       CHECK(aefft_net_layer(net, 0, &D0, &X0, &Y0, &layer0));
       std::vector<float> trace((size_t)fft_iters + 1);
       for (int it = 0; it < K; it++) {
-        CHECK(aefft_synth_frames(ctx, AEFFT_DEVICE, 1234, frame0 + (int64_t)rank * B, B, D0, X0, Y0, layer0));
+        if (vfh) {
+          // this rank's B frames of the batch, wrapping around at the end of the file
+          for (int64_t b = 0; b < B; b++) {
+            const int64_t fidx = (frame0 + (int64_t)rank * B + b) % vframes;
+            if (std::fseek(vfh, (long)(fidx * (int64_t)fbytes), SEEK_SET) != 0 ||
+                std::fread(vbuf.data() + (size_t)b * fbytes, 1, fbytes, vfh) != fbytes) {
+              std::fprintf(stderr, "aefft_replay: cannot read frame %lld of %s\n", (long long)fidx, video.c_str());
+              return 1;
+            }
+          }
+          CHECK(aefft_net_set_frames_u8(net, AEFFT_HOST, vbuf.data()));
+        } else {
+          CHECK(aefft_synth_frames(ctx, AEFFT_DEVICE, 1234, frame0 + (int64_t)rank * B, B, D0, X0, Y0, layer0));
+        }
         frame0 += B * world;
         if (fft) {
           CHECK(aefft_net_fft_forward(net, AEFFT_DEVICE, nullptr, fft_l));
@@ -209,6 +241,19 @@ int main(int argc, char** argv) {
       return 1;
     }
   }
+  if (!dump.empty()) {
+    if (aefft_net_num_pairs(net) < 1) { std::fprintf(stderr, "aefft_replay: --dump needs a layer\n"); return 1; }
+    const int nl = aefft_net_num_layers(net);
+    if (fft) CHECK(aefft_net_fft_forward(net, AEFFT_DEVICE, nullptr, 0));
+    else CHECK(aefft_net_forward(net, AEFFT_DEVICE, nullptr));
+    std::vector<unsigned char> img((size_t)B * fbytes);
+    CHECK(aefft_net_get_layer_u8(net, nl - 1, 0, AEFFT_HOST, img.data()));
+    FILE* fh = std::fopen(dump.c_str(), "wb");
+    if (!fh || std::fwrite(img.data(), 1, img.size(), fh) != img.size()) { std::fprintf(stderr, "aefft_replay: cannot write %s\n", dump.c_str()); return 1; }
+    std::fclose(fh);
+    std::printf("reconstruction of %lld frames -> %s\n", (long long)B, dump.c_str());
+  }
+  if (vfh) std::fclose(vfh);
   CHECK(aefft_sync(ctx));
   CHECK(aefft_net_destroy(net));
   CHECK(aefft_destroy(ctx));

@@ -281,6 +281,11 @@ int aefft_net_forward(aefft_net* net, int loc, const float* frames);
  * normalised.  Uploading bytes moves 4x less data over PCIe than float frames; follow with aefft_net_forward /
  * aefft_net_step with frames == NULL (layer 0 already set). */
 int aefft_net_set_frames_u8(aefft_net* net, int loc, const unsigned char* images);
+/* SpinToImage_C (netlib.cpp:52-76; mode 0: clamp(round(v), 0, 255)) / SpinToImage_V (:79-92; mode 1: (uchar)(int)v) of a
+ * real-space layer with <= 4 channels on the device: B interleaved 8-bit images [B][rows = Ny][cols = Nx][D] -- the display
+ * side of the reference's webcam loop, and together with aefft_net_set_frames_u8 the raw-video front end of aefft_replay
+ * (--video / --dump).  The layer must be current (coordinate forward, or a momentum-space forward that materialises it). */
+int aefft_net_get_layer_u8(aefft_net* net, int layer, int mode, int loc, unsigned char* images);
 /* train pair n_l on the activations of the last forward (autoencoder.cpp:158-201, q=1).  *mse host or NULL.
  * With a communicator (world > 1) the pair's raw gradient block is all-reduced before the update (B_global = B * world). */
 int aefft_net_train_pair(aefft_net* net, int n_l, int mode, int quirks, float delmax, float alpha, float* mse);

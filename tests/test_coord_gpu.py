@@ -370,6 +370,28 @@ def test_image_to_spin_u8_bit_exact(ctx):
     assert np.array_equal(got, want)
 
 
+def test_spin_to_image_u8_bit_exact(ctx):
+    """aefft_net_get_layer_u8 = SpinToImage_C (netlib.cpp:52-76: clamp(round(v), 0, 255), round half away from zero) and
+    SpinToImage_V (:79-92: (uchar)(int)v): the display side of the reference's webcam loop."""
+    B, D, Nx, Ny = 2, 3, 38, 52
+    rng = np.random.default_rng(9)
+    net = A.Net(ctx, D, Nx, Ny, B)
+    try:
+        net.add_layer(4, 1, 1, 2, 1.0)
+        v = (rng.random((B, D, Nx, Ny)) * 300 - 20).astype(np.float32)
+        v[0, 0, :4, 0] = [0.5, 1.5, 2.5, -0.5]  # halves: C round() goes away from zero
+        _, _, _, ptr = net.layer_info(0)
+        ctx.memcpy(ptr, v.ctypes.data, v.nbytes, 0)
+        got_c, got_v = net.get_layer_u8(0, 0), net.get_layer_u8(0, 1)
+    finally:
+        net.close()
+    r = np.where(v >= 0, np.floor(v.astype(np.float64) + 0.5), np.ceil(v.astype(np.float64) - 0.5))
+    want_c = np.clip(r, 0, 255).astype(np.uint8).transpose(0, 3, 2, 1)
+    want_v = (np.trunc(v).astype(np.int64) & 255).astype(np.uint8).transpose(0, 3, 2, 1)
+    assert np.array_equal(got_c, want_c)
+    assert np.array_equal(got_v, want_v)
+
+
 def test_net_step_cuda_ref_quirks_two_pairs(ctx):
     """aefft_net_step in CUDA_REF mode with all quirks on, two square pairs of DIFFERENT resolution trained back to back
     without a host sync in between (the stale-border kernel of pair 0 must not see pair 1's border geometry), against

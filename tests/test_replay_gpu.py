@@ -281,3 +281,43 @@ def test_momentum_sidecar_makes_a_reload_bit_identical(ctx, tmp_path):
     assert all(np.array_equal(g[0], w[0]) and np.array_equal(g[1], w[1]) for g, w in zip(got, want))
     cold = reload(False)
     assert not np.array_equal(cold[0][0], want[0][0])
+
+
+def test_replay_raw_video_front_end(ctx, tmp_path):
+    """--video / --dump: frames from a raw 8-bit video file (interleaved [frame][Ny][Nx][3], the layout of the
+    reference's webcam frames) through ImageToSpin_C on the device, the reconstruction back through SpinToImage_C -- against
+    the same calls through ctypes on the same bytes."""
+    exe = driver_exe()
+    (tmp_path / "New_Layer_Param.txt").write_text(PARAM)
+    (tmp_path / "weights").mkdir()
+    Bv, nx, ny = 2, 48, 32
+    rng = np.random.default_rng(3)
+    video = rng.integers(0, 256, size=(5, ny, nx, 3), dtype=np.uint8)  # 5 frames: the second batch wraps around
+    (tmp_path / "in.raw").write_bytes(video.tobytes())
+    run = subprocess.run([exe, "--frames", str(Bv), "--size", f"{nx}x{ny}", "--seed", "77", "--param",
+                          str(tmp_path / "New_Layer_Param.txt"), "--weights", str(tmp_path / "weights"), "--video",
+                          str(tmp_path / "in.raw"), "--dump", str(tmp_path / "out.raw"), "--script", "n t3"],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    got_mse = [float(l.split()[1]) for l in run.stdout.splitlines() if l.startswith("mse ")]
+    got_img = np.frombuffer((tmp_path / "out.raw").read_bytes(), np.uint8).reshape(Bv, ny, nx, 3)
+    # the same through ctypes
+    ctypes.CDLL("libc.so.6").srand(77)
+    ctx.set_precision(A.PRECISION_BF16X3)
+    dM, Lk, Ll, scal, rmax = A.load_param(tmp_path / "New_Layer_Param.txt")
+    net = A.Net(ctx, 3, nx, ny, Bv)
+    try:
+        net.add_layer(dM, Lk, Ll, scal, rmax)
+        want_mse = []
+        for it in range(3):
+            idx = [(it * Bv + b) % len(video) for b in range(Bv)]
+            net.set_frames_u8(np.ascontiguousarray(video[idx]))
+            net.forward(None, loc=A.DEVICE)
+            want_mse.append(net.train_pair(0, A.MODE_CUDA_REF, quirks=0))
+        net.forward(None, loc=A.DEVICE)
+        ctx.sync()
+        want_img = net.get_layer_u8(net.num_layers - 1, 0)
+    finally:
+        net.close()
+    assert np.allclose(got_mse, want_mse, rtol=1e-6), (got_mse, want_mse)
+    assert np.array_equal(got_img, want_img)
