@@ -888,7 +888,9 @@ __global__ void gradient_diff_pack_kernel(const float* __restrict__ c, const flo
 // tools/probe_ffma2.cu measures 128 fp32 lanes per clock per SM either way); 7.3 ms with dot-product distances; 6.1 ms with
 // 16-byte tile copies and four accumulators for the dot product.  Interleaving two pairs by hand, a branch-free loop
 // and three CTAs per SM (80 registers, spills: 9.8 ms) gave nothing more: the loop runs ~52 instructions per pair at 0.54
-// issues per scheduler-clock with 4 warps per scheduler.
+// issues per scheduler-clock with 4 warps per scheduler.  Splitting the 25 taps of a kernel over two lanes (80 registers, three
+// CTAs per SM, partial dot products joined by a shuffle) was slower as well: 8.6 ms -- both lanes repeat the reciprocal and
+// index work and the loop is bound by issued instructions, not by latency.
 template <int T>
 __global__ void __launch_bounds__(256) gradient_diff_tiled_kernel(const float* __restrict__ c, const float* __restrict__ f,
                                                                    float* __restrict__ cd, float* __restrict__ fd, int dM, int dD,
