@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(256) gram_stats_bm_kernel(const float* __restr
                                                             float2* __restrict__ Gx, float2* __restrict__ M0,
                                                             double* __restrict__ sq_part, float2* __restrict__ dcsum, int B,
                                                             int ncols, int col0, int Ny, Support sup) {
-  constexpr int TR = DD >= 32 ? 4 : (DD >= 16 ? 2 : 1), TG = DD / TR, NT = TG * TG, NG = 256 / NT;
+  constexpr int TR = DD >= 32 ? 4 : (DD >= 16 ? 2 : 1), TG = DD / TR, NT = TG * TG, NG = 256 / NT;  // (4 x 4 tiles at 16
+  // channels: 16 tiles x 16 frame groups and a 64 KB reduction buffer measured 0.23 ms slower)
   static_assert(NT * NG == 256, "256 threads");
   extern __shared__ __align__(16) float2 gs_sm[];
   __shared__ double red[8];

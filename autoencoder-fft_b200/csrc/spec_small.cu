@@ -360,6 +360,13 @@ __global__ void __launch_bounds__(128) conv_reg_kernel(const float2* __restrict_
 #pragma unroll
         for (int o = 0; o < COP; o++)
           if (live && (o % PARTS) == part && (u == 0 || two)) out[(b + u) * out_l.sb + o * out_l.sc + w_out * out_l.sw] = acc[o];
+      } else if (COP % 2 == 0 && CO % COP == 0 && out_l.sc == 1) {
+        // channel-contiguous output (bin-major): this lane's COP outputs are one 8 * COP byte run: 16-byte stores
+        if (live && (u == 0 || two)) {
+          float4* o4 = reinterpret_cast<float4*>(out + (b + u) * out_l.sb + o0 + w_out * out_l.sw);
+#pragma unroll
+          for (int o = 0; o < COP; o += 2) o4[o / 2] = make_float4(acc[o].x, acc[o].y, acc[o + 1].x, acc[o + 1].y);
+        }
       } else {
 #pragma unroll
         for (int o = 0; o < COP; o++)
