@@ -53,15 +53,21 @@ static bool fft_len_ok(int N) {
   return r == 1;
 }
 
+// x / d for 0 <= x < 2^20 through the float reciprocal inv = 1 / d: (x + 0.5) * inv stays at least 0.5 / d away from an integer
+// while its rounding error is below x / d * 2^-22, so the truncation is exact.  The run-time (mixed-radix) kernels index
+// through these instead of ~20-instruction integer divisions.
+__device__ __forceinline__ int idiv_f(int x, float inv) { return (int)(((float)x + 0.5f) * inv); }
 // position of input sample n in the staged (digit-reversed) order: the LAST pass splits n by its radix first
 __device__ __forceinline__ int digit_reverse(const FftPlan& p, int n) {
   int pos = 0, M = p.N;
 #pragma unroll 1
   for (int i = p.npass - 1; i >= 0; i--) {
     const int r = p.radix[i];
-    M /= r;
-    pos += (n % r) * M;
-    n /= r;
+    const float ir = 1.f / (float)r;
+    M = idiv_f(M, ir);
+    const int q = idiv_f(n, ir);
+    pos += (n - q * r) * M;
+    n = q;
   }
   return pos;
 }
@@ -172,11 +178,12 @@ __device__ __forceinline__ void fft_pass(float2* s, int N, int M, int nseq, int 
   const int L = M * R;
   const int nbf = N / R;
   const int tstep = N / L;  // twiddle W_L^x = W_N^(x * N/L)
+  const float inv_seq = 1.f / (float)nseq, inv_nbf = 1.f / (float)nbf, inv_M = 1.f / (float)M;
   for (int item = threadIdx.x; item < nbf * nseq; item += blockDim.x) {
     int c, t;
-    if (seq_fast) { c = item % nseq; t = item / nseq; }
-    else { t = item % nbf; c = item / nbf; }
-    const int k = t % M, blk = t / M;
+    if (seq_fast) { t = idiv_f(item, inv_seq); c = item - t * nseq; }
+    else { c = idiv_f(item, inv_nbf); t = item - c * nbf; }
+    const int blk = idiv_f(t, inv_M), k = t - blk * M;
     float2* base = s + (size_t)(blk * L + k) * sn + (size_t)c * sc;
     float2 a[R];
 #pragma unroll
@@ -228,8 +235,9 @@ __global__ void __launch_bounds__(256) fft_rows_r2c_kernel(const float* __restri
   const long long img = blockIdx.y;
   const int rp0 = blockIdx.x * RP;
   const float* src = in + (img / ch) * fstride + (img % ch) * (long long)Nx * Ny;
+  const float inv_Ny = 1.f / (float)Ny, inv_Nyr = 1.f / (float)Nyr;
   for (int idx = threadIdx.x; idx < RP * Ny; idx += blockDim.x) {
-    const int r = idx / Ny, n = idx % Ny;
+    const int r = idiv_f(idx, inv_Ny), n = idx - r * Ny;
     const int row = 2 * (rp0 + r);
     float2 v = make_float2(0.f, 0.f);
     if (row < Nx) {
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(256) fft_rows_r2c_kernel(const float* __restri
   fft_smem<-1>(sm, plan, RP, 1, SP, false, tw);
   float2* dst = out + img * (long long)Nx * Nyr;
   for (int idx = threadIdx.x; idx < RP * Nyr; idx += blockDim.x) {
-    const int r = idx / Nyr, k = idx % Nyr;
+    const int r = idiv_f(idx, inv_Nyr), k = idx - r * Nyr;
     const int row = 2 * (rp0 + r);
     if (row >= Nx) continue;
     const float2 z1 = sm[r * SP + k];
@@ -263,8 +271,9 @@ __global__ void __launch_bounds__(256) fft_rows_c2r_kernel(const float2* __restr
   const long long img = blockIdx.y;
   const int rp0 = blockIdx.x * RP;
   const float2* src = in + img * (long long)Nx * Nyr;
+  const float inv_Ny = 1.f / (float)Ny, inv_Nyr = 1.f / (float)Nyr;
   for (int idx = threadIdx.x; idx < RP * Nyr; idx += blockDim.x) {
-    const int r = idx / Nyr, k = idx % Nyr;
+    const int r = idiv_f(idx, inv_Nyr), k = idx - r * Nyr;
     const int row = 2 * (rp0 + r);
     float2 a = make_float2(0.f, 0.f), b = a;
     if (row < Nx) {
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(256) fft_rows_c2r_kernel(const float2* __restr
   fft_smem<+1>(sm, plan, RP, 1, SP, false, tw);
   float* dst = out + (img / ch) * fstride + (img % ch) * (long long)Nx * Ny;
   for (int idx = threadIdx.x; idx < RP * Ny; idx += blockDim.x) {
-    const int r = idx / Ny, n = idx % Ny;
+    const int r = idiv_f(idx, inv_Ny), n = idx - r * Ny;
     const int row = 2 * (rp0 + r);
     if (row >= Nx) continue;
     const float2 z = sm[r * SP + n];
@@ -298,8 +307,9 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const float2* __restrict_
   const int c0 = blockIdx.x * CT;
   const float2* src = in + img * (long long)Nx * W;
   const int SC = CT | 1;  // odd pitch between samples: consecutive n land in different banks
+  const float inv_CT = 1.f / (float)CT;
   for (int idx = threadIdx.x; idx < Nx * CT; idx += blockDim.x) {
-    const int n = idx / CT, c = idx % CT;
+    const int n = idiv_f(idx, inv_CT), c = idx - n * CT;
     float2 v = make_float2(0.f, 0.f);
     if (c0 + c < W) v = src[(long long)n * W + c0 + c];
     sm[digit_reverse(plan, n) * SC + c] = v;
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(256) fft_cols_kernel(const float2* __restrict_
   fft_smem<DIR>(sm, plan, CT, SC, 1, true, tw);
   float2* dst = out + img * (long long)Nx * W;
   for (int idx = threadIdx.x; idx < Nx * CT; idx += blockDim.x) {
-    const int n = idx / CT, c = idx % CT;
+    const int n = idiv_f(idx, inv_CT), c = idx - n * CT;
     if (c0 + c < W) dst[(long long)n * W + c0 + c] = sm[n * SC + c];
   }
 }
