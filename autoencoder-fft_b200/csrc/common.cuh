@@ -273,6 +273,9 @@ int launch_shrink(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl,
 int launch_fft_update(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, float* c, float* f, float* b, float* p,
                       const float* dck, const float* dfk, const float* db, const float* dp, float* Dc, float* Df, float* Db,
                       float* Dp, float del, int maxdiff, float* div_scratch);
+// tcgen05 form for 5 x 5 kernels (gdiff_tc.cu); AEFFT_ERR_UNSUPPORTED: the caller runs the CUDA-core kernel
+int launch_gradient_diff_tc(aefft_ctx* ctx, int dM, int dD, const float* c, const float* f, float* cd, float* fd, int t0, int nt,
+                            int nchunks, float* part);
 int launch_gradient_diff(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, const float* c, const float* f, const float* b,
                          const float* p, float* div, int rank, int world);
 int launch_axpby(aefft_ctx* ctx, float* y, const float* x, float a, float b, long long n);

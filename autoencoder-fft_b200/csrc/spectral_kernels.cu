@@ -1165,18 +1165,24 @@ int launch_gradient_diff(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, const f
       float* part = nullptr;
       if (nchunks > 1) AE_TRY(ctx->getT("gdiff_part", (size_t)2 * nchunks * nt * 64 * (T + 1), &part));
       dim3 grid(nt, 2, nchunks);
+      // 5 x 5 kernels, many of them: both halves of the all-pairs sum as tcgen05 GEMMs (gdiff_tc.cu)
+      int rc_tc = AEFFT_ERR_UNSUPPORTED;
+      if (T == 25) rc_tc = launch_gradient_diff_tc(ctx, dM, dD, c, f, cd, fd, t0, nt, nchunks, part);
+      if (rc_tc != AEFFT_OK && rc_tc != AEFFT_ERR_UNSUPPORTED) return rc_tc;
       float* xp = nullptr;
       const int npad = tiles * 64;
-      AE_TRY(ctx->getT("gdiff_pack", (size_t)2 * npad * (T + 3), &xp));
-      if (T == 25) {
+      if (rc_tc != AEFFT_OK) AE_TRY(ctx->getT("gdiff_pack", (size_t)2 * npad * (T + 3), &xp));
+      if (rc_tc == AEFFT_OK) {
+        // (launched and counted there)
+      } else if (T == 25) {
         gradient_diff_pack_kernel<25><<<(2 * npad + 127) / 128, 128, 0, ctx->stream>>>(c, f, xp, dM, dD, npad);
         gradient_diff_tiled_kernel<25><<<grid, 256, 0, ctx->stream>>>(c, f, cd, fd, dM, dD, t0, part, xp);
+        ctx->launches += 2;
       } else {
         gradient_diff_pack_kernel<9><<<(2 * npad + 127) / 128, 128, 0, ctx->stream>>>(c, f, xp, dM, dD, npad);
         gradient_diff_tiled_kernel<9><<<grid, 256, 0, ctx->stream>>>(c, f, cd, fd, dM, dD, t0, part, xp);
+        ctx->launches += 2;
       }
-      ctx->launches++;
-      ctx->launches++;
       if (nchunks > 1) {
         const int total = 2 * nt * 64;
         if (T == 25) gradient_diff_finish_kernel<25><<<(total + 127) / 128, 128, 0, ctx->stream>>>(c, f, cd, fd, part, n, t0, nt, nchunks);

@@ -295,8 +295,8 @@ def test_bin_sharding_two_device_emulation(ctx, dims, maxdiff):
     assert np.isclose(post[0][0] + post[1][0], want_trace[1], rtol=1e-5), (post, want_trace)
 
 
-@pytest.mark.parametrize("chunks", [None, "3"])
-def test_multiobjective_tiled_kernel_vs_oracle(ctx, chunks):
+@pytest.mark.parametrize("chunks", [None, "3", "tc", "tc3"])
+def test_multiobjective_tiled_kernel_vs_oracle(ctx, chunks, monkeypatch):
     """maxdiff=1 with dM*dD >= 256 kernels takes the tiled gradient_diff kernel (fft_backproplib.cu:709-753 semantics);
     chunks: the form that splits the streamed kernels over several CTAs per row tile (what a bin-sharded device with few
     row tiles runs), forced here on a small shape."""
@@ -308,6 +308,11 @@ def test_multiobjective_tiled_kernel_vs_oracle(ctx, chunks):
     cs["f"][7, 5] = cs["f"][3, 2] * (1 - 2e-2)
     w = {k: cs[k].copy() for k in "cfbp"}
     ctx.profile_enable(True)
+    if chunks in ("tc", "tc3"):  # the tcgen05 form (gdiff_tc.cu), which large kernel counts take by default
+        monkeypatch.setenv("AEFFT_GDIFF_TC_MIN", "128")
+        chunks = "3" if chunks == "tc3" else None
+    else:
+        monkeypatch.setenv("AEFFT_NO_GDIFF_TC", "1")
     if chunks:
         os.environ["AEFFT_GDIFF_CHUNKS"] = chunks
     try:
