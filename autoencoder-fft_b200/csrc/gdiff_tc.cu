@@ -11,8 +11,9 @@
 // kind::tf32 with the 3xTF32 split (hi = x & 0xffffe000, lo = x - hi; hi hi + hi lo + lo hi) on both products: fp32-grade dot
 // products and sums.  Pairs whose dot-product distance cancels (d^2 < 1 % of |a|^2 + |b|^2: near-duplicate kernels) get their
 // distance from directly summed differences in the epilogue, as the reference computes it (:722-741).
-// Roles (448 threads, one CTA per SM): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue (two warps per TMEM lane
-// quarter, 32 columns of S each), warps 10-13 split the landed tiles into hi / lo.
+// Roles (704 threads, one CTA per SM): warp 0 TMA producer, warp 1 MMA issuer, warps 2-17 epilogue (four warps per TMEM lane
+// quarter, 16 columns of S each: the epilogue of tile k and the second MMA of tile k are serial through the single W buffer, so
+// its latency is what the kernel runs at), warps 18-21 split the landed tiles into hi / lo.
 #include <cstdlib>
 #include <cstring>
 
@@ -27,7 +28,7 @@ namespace {
 
 using namespace umma;
 
-constexpr int GT_THREADS = 448, GT_NST = 3, GT_T = 25;
+constexpr int GT_EPI_WARPS = 16, GT_THREADS = 32 * (2 + GT_EPI_WARPS + 4), GT_NST = 3, GT_T = 25;
 constexpr uint32_t GT_A_LO = 16384, GT_W_HI = 32768, GT_W_LO = 65536, GT_ST0 = 98304, GT_STAGE = 34816;
 constexpr uint32_t GT_BK_LO = 8192, GT_BM_HI = 16384, GT_BM_LO = 24576, GT_AUX = 32768;
 constexpr size_t GT_SMEM = GT_ST0 + GT_NST * GT_STAGE + 1024;
@@ -101,8 +102,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gdiff_tc_kernel(const __grid_co
   if (tid == 32) {
     mbar_init(&a_full, 1); mbar_init(&a_ready, 4);
     for (int s = 0; s < GT_NST; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_ready[s], 4); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8); }
-    mbar_init(&w_full, 8); mbar_init(&w_empty, 1); mbar_init(&v_full, 1);
+    for (int s = 0; s < 2; s++) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], GT_EPI_WARPS); }
+    mbar_init(&w_full, GT_EPI_WARPS); mbar_init(&w_empty, 1); mbar_init(&v_full, 1);
     fence_mbar_init();
   }
   if (tid == 0) {
@@ -176,60 +177,55 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gdiff_tc_kernel(const __grid_co
       mma2(ntile - 1);
       commit(&v_full);
     }
-  } else if (warp < 10) {
+  } else if (warp < 2 + GT_EPI_WARPS) {
     // ------------------------------------------------------------------------------------------ epilogue (weights)
-    const int q = warp & 3, hcol = (warp - 2) >> 2;
+    const int q = warp & 3, cg = (warp - 2) >> 2;  // TMEM lane quarter, 16-column group of the S tile
     const int r = 32 * q + lane;
     const long long a = a_row0 + r;
     const bool a_ok = a < p.n && a < ((long long)p.tile0 + p.nt64) * 64;
     const float* x = isf ? p.f : p.c;
-    float xa[GT_T];
-#pragma unroll
-    for (int t = 0; t < GT_T; t++) xa[t] = a_ok ? __ldg(x + a * GT_T + t) : 0.f;
     const float4 au_a = a < p.npad ? __ldg(p.aux + (long long)isf * p.npad + a) : make_float4(0.f, 0.f, 0.f, 0.f);
     const float na = a_ok ? au_a.x : 0.f;
     const int a1 = a_ok ? __float_as_int(au_a.y) : -1, a2 = a_ok ? __float_as_int(au_a.z) : -1;
     const uint32_t lane_base = tb + ((uint32_t)(32 * q) << 16);
-    uint8_t* w_hi = smem + GT_W_HI + (size_t)hcol * 16384 + (size_t)r * 128;
+    uint8_t* w_hi = smem + GT_W_HI + (size_t)(cg >> 1) * 16384 + (size_t)r * 128;
+    const int ch0 = 4 * (cg & 1);  // first 16-byte chunk of this warp's columns inside the 32-column atom
     for (int k = 0; k < ntile; k++) {
       const uint8_t* st = smem + GT_ST0 + (size_t)(k % GT_NST) * GT_STAGE;
       mbar_wait_role<false>(&s_full[k & 1], (uint32_t)((k >> 1) & 1));
       mbar_wait_role<false>(&w_empty, (uint32_t)((k & 1) ^ 1));
       fence_after_sync();
-      const float4* aux_s = reinterpret_cast<const float4*>(st + GT_AUX) + hcol * 32;
+      const float4* aux_s = reinterpret_cast<const float4*>(st + GT_AUX) + cg * 16;
       unsigned near = 0;  // columns whose dot-product distance cancels: patched below (a branch per element cost the loop its ILP)
+      float v[16];
+      tmem_ld16(lane_base + (uint32_t)(k & 1) * 64u + (uint32_t)(cg * 16), v);
 #pragma unroll
-      for (int c0 = 0; c0 < 32; c0 += 16) {
-        float v[16];
-        tmem_ld16(lane_base + (uint32_t)(k & 1) * 64u + (uint32_t)(hcol * 32 + c0), v);
+      for (int e = 0; e < 16; e++) {
+        const float4 au = aux_s[e];
+        const float nn = na + au.x;
+        const float d2 = fmaf(-2.f, v[e], nn);
+        const bool on = (__float_as_int(au.y) != a1) & (__float_as_int(au.z) != a2);
+        const bool cancels = d2 < 0.01f * nn;
+        if (on && cancels) near |= 1u << e;
+        float w;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(d2));
+        v[e] = (on && !cancels) ? w : 0.f;
+      }
+      // hi / lo split, 16-byte chunks of the K-major SWIZZLE_128B tile (chunk c of row r at c ^ (r & 7))
 #pragma unroll
-        for (int e = 0; e < 16; e++) {
-          const float4 au = aux_s[c0 + e];
-          const float nn = na + au.x;
-          const float d2 = fmaf(-2.f, v[e], nn);
-          const bool on = (__float_as_int(au.y) != a1) & (__float_as_int(au.z) != a2);
-          const bool cancels = d2 < 0.01f * nn;
-          if (on && cancels) near |= 1u << (c0 + e);
-          float w;
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(d2));
-          v[e] = (on && !cancels) ? w : 0.f;
-        }
-        // hi / lo split, 16-byte chunks of the K-major SWIZZLE_128B tile (chunk c of row r at c ^ (r & 7))
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          uint4 h = make_uint4(__float_as_uint(v[4 * i]) & 0xffffe000u, __float_as_uint(v[4 * i + 1]) & 0xffffe000u,
-                               __float_as_uint(v[4 * i + 2]) & 0xffffe000u, __float_as_uint(v[4 * i + 3]) & 0xffffe000u);
-          const float4 l = make_float4(v[4 * i] - __uint_as_float(h.x), v[4 * i + 1] - __uint_as_float(h.y),
-                                       v[4 * i + 2] - __uint_as_float(h.z), v[4 * i + 3] - __uint_as_float(h.w));
-          const uint32_t off = (uint32_t)((((c0 >> 2) + i) ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(w_hi + off) = h;
-          *reinterpret_cast<float4*>(w_hi + (GT_W_LO - GT_W_HI) + off) = l;
-        }
+      for (int i = 0; i < 4; i++) {
+        uint4 h = make_uint4(__float_as_uint(v[4 * i]) & 0xffffe000u, __float_as_uint(v[4 * i + 1]) & 0xffffe000u,
+                             __float_as_uint(v[4 * i + 2]) & 0xffffe000u, __float_as_uint(v[4 * i + 3]) & 0xffffe000u);
+        const float4 l = make_float4(v[4 * i] - __uint_as_float(h.x), v[4 * i + 1] - __uint_as_float(h.y),
+                                     v[4 * i + 2] - __uint_as_float(h.z), v[4 * i + 3] - __uint_as_float(h.w));
+        const uint32_t off = (uint32_t)(((ch0 + i) ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(w_hi + off) = h;
+        *reinterpret_cast<float4*>(w_hi + (GT_W_LO - GT_W_HI) + off) = l;
       }
       while (near) {  // near-duplicate kernels (rare): directly summed differences, x[b] = hi + lo from the K-major tile
         const int cc = __ffs(near) - 1;
         near &= near - 1;
-        const int j = hcol * 32 + cc;
+        const int j = cg * 16 + cc;
         const uint8_t* row = st + (size_t)j * 128;
         float s2 = 0.f;
 #pragma unroll
@@ -239,12 +235,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gdiff_tc_kernel(const __grid_co
           const float xb[4] = {h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w};
 #pragma unroll
           for (int u = 0; u < 4; u++)
-            if (4 * t4 + u < GT_T) { const float dlt = xa[4 * t4 + u] - xb[u]; s2 = fmaf(dlt, dlt, s2); }
+            if (4 * t4 + u < GT_T) { const float dlt = (a_ok ? __ldg(x + a * GT_T + 4 * t4 + u) : 0.f) - xb[u]; s2 = fmaf(dlt, dlt, s2); }
         }
         float w;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(s2));
         const uint32_t hb = __float_as_uint(w) & 0xffffe000u;
-        const uint32_t off = (uint32_t)(((cc >> 2) ^ (r & 7)) << 4) + (uint32_t)(cc & 3) * 4u;
+        const uint32_t off = (uint32_t)(((ch0 + (cc >> 2)) ^ (r & 7)) << 4) + (uint32_t)(cc & 3) * 4u;
         *reinterpret_cast<uint32_t*>(w_hi + off) = hb;
         *reinterpret_cast<float*>(w_hi + (GT_W_LO - GT_W_HI) + off) = w - __uint_as_float(hb);
       }
@@ -256,7 +252,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gdiff_tc_kernel(const __grid_co
     if (ntile > 0) {
       mbar_wait_role<false>(&v_full, 0);
       fence_after_sync();
-      if (hcol == 0) {
+      if (cg == 0) {
         float v[32];
         tmem_ld16(lane_base + 128u, v);
         tmem_ld16(lane_base + 128u + 16u, v + 16);
@@ -265,7 +261,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gdiff_tc_kernel(const __grid_co
           if (gridDim.z == 1) {
             float* xd = (isf ? p.fd : p.cd) + a * GT_T;
 #pragma unroll
-            for (int t = 0; t < GT_T; t++) xd[t] = xa[t] * sw - v[t];
+            for (int t = 0; t < GT_T; t++) xd[t] = __ldg(x + a * GT_T + t) * sw - v[t];
           } else {
             const long long local = a - (long long)p.tile0 * 64;
             float* o = p.part + ((((long long)isf * gridDim.z + blockIdx.z) * p.nt64) * 64 + local) * (GT_T + 1);
@@ -278,7 +274,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gdiff_tc_kernel(const __grid_co
     }
   } else {
     // ------------------------------------------------------------------------------------------ splitters
-    const int t = tid - 320;  // 0..127
+    const int t = tid - 32 * (2 + GT_EPI_WARPS);  // 0..127
     {
       mbar_wait_role<false>(&a_full, 0);
       uint4* ah = reinterpret_cast<uint4*>(smem);

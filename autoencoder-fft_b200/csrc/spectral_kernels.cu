@@ -1162,6 +1162,16 @@ int launch_gradient_diff(aefft_ctx* ctx, int dM, int dD, int Nk, int Nl, const f
         if (nchunks > tiles) nchunks = tiles;
         if (nchunks < 1) nchunks = 1;
       }
+      if (T == 25 && n >= 2048 && !getenv("AEFFT_GDIFF_CHUNKS") && !getenv("AEFFT_NO_GDIFF_TC")) {
+        // the tensor-core form runs one CTA of 128 rows per SM: pick the chunk count whose last wave is the fullest
+        const int atiles = 2 * ((nt + 1) / 2);
+        long long best = -1;
+        for (int z = 1; z <= 8 && z <= tiles / 8; z++) {
+          const long long waves = ((long long)atiles * z + ctx->sm_count - 1) / ctx->sm_count;
+          const long long cost = waves * ((tiles + z - 1) / z + 4);  // + the per-CTA prologue / epilogue
+          if (best < 0 || cost < best) { best = cost; nchunks = z; }
+        }
+      }
       float* part = nullptr;
       if (nchunks > 1) AE_TRY(ctx->getT("gdiff_part", (size_t)2 * nchunks * nt * 64 * (T + 1), &part));
       dim3 grid(nt, 2, nchunks);
