@@ -294,9 +294,11 @@ int aefft_net_train_pair(aefft_net* net, int n_l, int mode, int quirks, float de
 int aefft_net_pair_gradients(aefft_net* net, int n_l, int mode, int quirks, float** gbuf_dev, int64_t* gbuf_len);
 int aefft_net_pair_update(aefft_net* net, int n_l, int mode, int64_t B_global, float delmax, float alpha, float* mse);
 /* ---- momentum (FFT) space on the resident net (autoencoder.cpp:131-133 forward with fft == 1, :190-196 training).
- * The forward keeps EVERY layer's spectrum in HBM; real-space layers (aefft_net_layer) are written per fft_l:
- * 1 = every layer (the reference's display mode, fft_backproplib.cu:1347-1361), 0 = the last layer only (:1373),
- * -1 = none.  aefft_net_fft_step = that forward + n_iter iterations of backprop_fft (:1381-1511; the reference runs 100,
+ * The forward keeps the layer spectra in HBM; real-space layers (aefft_net_layer) are written per fft_l:
+ * 1 = every layer (the reference's display mode, fft_backproplib.cu:1347-1361; every spectrum is produced), 0 = the last
+ * layer only (:1373), -1 = none.  With fft_l <= 0 only the spectra the training reads are produced (every pair's in / out
+ * layers; a conv followed by a spectral pooling computes the kept bins only, the decoder runs on the bins that came up
+ * from the innermost level), so real-space layers other than the last are NOT current after such a forward.  aefft_net_fft_step = that forward + n_iter iterations of backprop_fft (:1381-1511; the reference runs 100,
  * lr 0.1*del0, alpha 0.9, momentum zeroed per call) for EVERY pair, consuming the pair's in / out spectra directly -- the
  * reference inverse-transforms the layers and backprop_fft transforms them again, a round trip that is the identity up to
  * fp32 rounding.  mse: host [pairs][n_iter+1] (the "mse fft:" / "n: .. mse:" values) or NULL (then nothing synchronises).
