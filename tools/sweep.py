@@ -1,6 +1,6 @@
 """BASELINE configs[4]: batch / resolution sweep, coordinate vs FFT space, on the GPUs of this box.  Runs bench.py once per
 point (resident frames; --no-cpu-baseline) and prints a markdown table (kept under profiles/).
-usage: python tools/sweep.py [--gpus N] > profiles/r1_sweep.md"""
+usage: python tools/sweep.py [--gpus N] > profiles/r2_sweep.md"""
 import argparse, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,8 +8,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--gpus", type=int, default=1)
 ap.add_argument("--quick", action="store_true")
 a = ap.parse_args()
-points = [("c2", 256, 64), ("c2", 512, 64), ("c2", 1024, 16), ("c2", 2048, 4),
-          ("c3", 256, 128), ("c3", 512, 128), ("c3", 1024, 64), ("c3", 2048, 16)]
+points = [("c2", 256, 64), ("c2", 512, 64), ("c2", 1024, 16), ("c2", 2048, 4), ("c2", 4096, 1),
+          ("c3", 256, 128), ("c3", 512, 128), ("c3", 1024, 64), ("c3", 2048, 16), ("c3", 4096, 4)]
 if a.quick:
     points = [p for p in points if p[1] <= 512]
 print("| workload | frame | frames per GPU | GPUs | frames/s (resident) | ms/step | frames/s (end to end, fp32 frames) | top kernel (share) |")
