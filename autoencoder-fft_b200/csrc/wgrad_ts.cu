@@ -941,6 +941,16 @@ int launch_wgrad_ts(aefft_ctx* ctx, const Window& win, int64_t B, int dD, int dM
     for (int r = 0; r < 4; r++)
       fprintf(stderr, "[wgrad_ts]   %-30s waitA %9.0f  waitB %9.0f  total %9.0f  work %9.0f + %9.0f cycles\n", role[r],
               acc[r][0] / cnt[r], acc[r][1] / cnt[r], acc[r][2] / cnt[r], acc[r][3] / cnt[r], acc[r][4] / cnt[r]);
+    // per job (GC jobs first, then GF): mean / max of the CTAs' total cycles (first issuer warp) -- an imbalance between the
+    // two gradients shows up here
+    for (int j = 0; j < p.n_jobs; j++) {
+      double sum = 0, mx = 0;
+      for (int c = 0; c < cpj; c++) {
+        const double t = (double)h[(((size_t)j * cpj + c) * 16 + 12) * 8 + 2];
+        sum += t; if (t > mx) mx = t;
+      }
+      fprintf(stderr, "[wgrad_ts]   job %d (%s): CTA total mean %9.0f  max %9.0f cycles\n", j, p.job[j].is_gf ? "GF" : "GC", sum / cpj, mx);
+    }
   }
   return AEFFT_OK;
 }

@@ -587,6 +587,33 @@ def gradient_diff(c, f, b, p):
     return cd, fd, bd, pd
 
 
+def gradient_diff_blocked(c, f, b, p, rows=1024):
+    """Same sums as gradient_diff for the kernel counts of BASELINE config 4 (2 048 .. 32 768 kernels per tensor), where the
+    literal loop above would take hours: sum_b w_ab (x_a - x_b) = x_a sum_b w_ab - sum_b w_ab x_b with
+    w_ab = [m_a != m_b and d_a != d_b] / |x_a - x_b|^2 and |x_a - x_b|^2 = |x_a|^2 + |x_b|^2 - 2 x_a.x_b, `rows` kernels at
+    a time (fp64: the cancellation costs ~1e-11 relative even for kernels 1e-2 apart).  The loop is the restatement;
+    tests/test_oracle_cpu.py pins this form against it."""
+    c, f, b, p = (np.asarray(t, F64) for t in (c, f, b, p))
+    dM, dD = c.shape[:2]
+    T = c.shape[2] * c.shape[3]
+    xc = c.reshape(dM * dD, T)                              # row a = m * dD + d
+    xf = np.swapaxes(f, 0, 1).reshape(dM * dD, T)           # f[d][m] put on the same row index a
+    am, ad = np.divmod(np.arange(dM * dD), dD)
+    oc, of = np.zeros_like(xc), np.zeros_like(xf)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for x, o in ((xc, oc), (xf, of)):
+            n2 = (x * x).sum(1)
+            for a0 in range(0, dM * dD, rows):
+                sl = slice(a0, min(a0 + rows, dM * dD))
+                ok = (am[sl, None] != am[None, :]) & (ad[sl, None] != ad[None, :])
+                d2 = n2[sl, None] + n2[None, :] - 2.0 * (x[sl] @ x.T)
+                w = np.where(ok, 1.0 / d2, 0.0)
+                o[sl] = x[sl] * w.sum(1)[:, None] - w @ x
+        bd = np.array([sum(1.0 / (b[m] - b[m1]) for m1 in range(dM) if m1 != m) for m in range(dM)], F64)
+        pd = np.array([sum(1.0 / (p[d] - p[d1]) for d1 in range(dD) if d1 != d) for d in range(dD)], F64)
+    return oc.reshape(c.shape), np.swapaxes(of.reshape(dM, dD, *f.shape[2:]), 0, 1).copy(), bd, pd
+
+
 def backprop_fft(inp, expout, out, c, f, b, p, del0, maxdiff=0, n_iter=100, cfreq=None, ffreq=None,
                  return_trace=False):
     """backprop_fft (fft_backproplib.cu:1381-1511).  Batched [B,...]: raw kernel-space gradients averaged over
@@ -616,7 +643,7 @@ def backprop_fft(inp, expout, out, c, f, b, p, del0, maxdiff=0, n_iter=100, cfre
                 acc[i] = acc[i] + t / B
         dck, dfk, db, dp = acc
         if maxdiff:
-            cd, fd, bd, pd = gradient_diff(c, f, b, p)  # (:1237) w0=1, w1=10 (:1252)
+            cd, fd, bd, pd = (gradient_diff if dM * dD <= 512 else gradient_diff_blocked)(c, f, b, p)  # (:1237) w0=1, w1=10 (:1252)
             dck, dfk, db, dp = dck - 10 * cd, dfk - 10 * fd, db - 10 * bd, dp - 10 * pd
         c, Dc = momentum_update(c, Dc, dck, delta, alpha)  # backprop_d / backprop_double (:605-704)
         f, Df = momentum_update(f, Df, dfk, delta, alpha)

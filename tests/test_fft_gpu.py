@@ -328,6 +328,30 @@ def test_multiobjective_tiled_kernel_vs_oracle(ctx, chunks, monkeypatch):
         assert O.rel_l2(w[k], want[k]) < 1e-4, k
 
 
+@pytest.mark.parametrize("dM,dD,n_iter", [(64, 32, 2), (128, 64, 2), (256, 128, 1)])
+def test_multiobjective_at_config4_widths_default_dispatch(ctx, dM, dD, n_iter):
+    """The inner pairs of BASELINE config 4 (32 -> 64, 64 -> 128, 128 -> 256 channels: 2 048 .. 32 768 kernels per tensor) with
+    the multiobjective term, NO forcing switch: the dispatch takes the tcgen05 kernel (gdiff_tc.cu) there.  Small frames
+    (the term acts in kernel space only); oracle = backprop_fft with gradient_diff in its blocked form, which
+    test_oracle_cpu.py pins against the literal loop of fft_backproplib.cu:709-753.  Two near-duplicate kernels per
+    tensor exercise the direct-difference patch of the dot-product distances."""
+    cs = fft_case(17, dM, dD, 5, 5, 8, 8, wscale=0.1)
+    cs["c"][5, 7] = cs["c"][2, 3] * (1 + 1e-2)
+    cs["f"][7, 5] = cs["f"][3, 2] * (1 - 2e-2)
+    w = {k: cs[k].copy() for k in "cfbp"}
+    ctx.profile_enable(True)
+    trace = ctx.backprop_fft(cs["inp"], cs["inp"], cs["out"], w["c"], w["f"], w["b"], w["p"], 0.2, 1, n_iter)
+    names = [r["name"] for r in ctx.profile_records()]
+    ctx.profile_enable(False)
+    assert "gradient_diff" in names
+    want = O.backprop_fft(cs["inp"], cs["inp"], cs["out"], cs["c"], cs["f"], cs["b"], cs["p"], 0.2, 1, n_iter)
+    assert np.allclose(trace, want["mse"], rtol=2e-4), (trace, want["mse"])
+    for k in "cfbp":
+        assert O.rel_l2(w[k], want[k]) < 1e-4, k
+        # the update itself (what the term moved), not only the weights it is a small part of
+        assert O.rel_l2(w[k].astype(np.float64) - cs[k], want[k] - cs[k]) < 2e-3, k
+
+
 # ---- the kernels the c3 / c4 benchmarks actually run: B >= 8 and >= 8 channels take the shared-memory tiled contraction
 # (forward conv_k, G, dC, dF forms).  Channel shapes are those of the c3 pairs 1 and 2 (16->32, 32->64) and a c4-like
 # wide pair; resolutions are what the fp64 numpy oracle finishes in seconds.

@@ -263,3 +263,20 @@ def test_oracle_vs_reference_cuda_golden_fft():
                 assert O.rel_l2(res[x], Gg[f"bpf_{tag}_new_{x}"]) < 1e-5, (tag, x)
             assert O.rel_l2(O.cfreq_to_wire(res["cfreq"]), Gg[f"bpf_{tag}_new_cfreq"]) < 1e-5
             assert O.rel_l2(O.cfreq_to_wire(res["ffreq"]), Gg[f"bpf_{tag}_new_ffreq"]) < 1e-5
+
+
+def test_gradient_diff_blocked_form_equals_the_literal_loop():
+    """oracle_np.gradient_diff_blocked (what backprop_fft uses above 512 kernels per tensor, i.e. for the widths of BASELINE
+    config 4) against the literal restatement of fft_backproplib.cu:709-753, incl. near-duplicate kernels."""
+    rng = np.random.default_rng(0)
+    for dM, dD, rows in ((6, 4, 5), (16, 8, 1024), (12, 9, 7)):
+        c = rng.standard_normal((dM, dD, 5, 5)) * 0.1
+        f = rng.standard_normal((dD, dM, 5, 5)) * 0.1
+        b, p = rng.standard_normal(dM), rng.standard_normal(dD)
+        c[3, 2] = c[1, 1] * (1 + 1e-2)
+        f[2, 3] = f[1, 1] * (1 - 2e-2)
+        lit = O.gradient_diff(c, f, b, p)
+        blk = O.gradient_diff_blocked(c, f, b, p, rows=rows)
+        for x, y in zip(lit, blk):
+            assert x.shape == y.shape
+            assert O.rel_l2(y, x) < 1e-10
