@@ -41,6 +41,8 @@ for _p in (os.path.join(ROOT, "autoencoder-fft_b200"), os.path.join(ROOT, "oracl
 
 import numpy as np  # noqa: E402
 
+import dp  # noqa: E402  (who owns which frames / bins: the sharding plan the gloo tests check on CPU)
+
 SEED = 1234
 WORKLOADS = {
     "c1": dict(D=1, Nx=640, Ny=480, widths=[8], Lk=1, Ll=1, pool=1, rmax=3.0, batch=1, space="coordinate", mode="cpu_ref"),
@@ -443,7 +445,7 @@ class CoordWorkload:
                 net.set_symmetric(n)  # 'p' key: decoder = transposed encoder before symmetric training
         _, _, _, self.l0 = net.layer_info(0)
         self.n0 = B * w["D"] * w["Nx"] * w["Ny"]
-        ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=rank * B, out=self.l0, loc=A.DEVICE)
+        ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=dp.frame_range(rank, world, B)[0], out=self.l0, loc=A.DEVICE)
         self.h2d_bytes, self.d2h_bytes = self.n0 * 4, 4 * self.P
         host = torch.empty(self.n0, dtype=torch.float32).pin_memory()
         A.lib().aefft_memcpy(ctx.h, ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(self.l0), ctypes.c_int64(self.n0 * 4), 1)
@@ -511,7 +513,7 @@ class FftNetWorkload:
         self.n_iter, self.maxdiff = int(w.get("n_iter", 1)), int(w.get("maxdiff", 0))
         _, _, _, self.l0 = net.layer_info(0)
         self.n0 = B * w["D"] * w["Nx"] * w["Ny"]
-        ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=rank * B, out=self.l0, loc=A.DEVICE)
+        ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=dp.frame_range(rank, world, B)[0], out=self.l0, loc=A.DEVICE)
         host = torch.empty(self.n0, dtype=torch.float32).pin_memory()
         ctx.memcpy(host.data_ptr(), self.l0, self.n0 * 4, 1)
         self.f32 = Staging(torch, dev, host)
@@ -594,7 +596,7 @@ class FftWorkload:
         self.shard = w.get("shard") == "bins"
         self.n_iter, self.maxdiff = int(w.get("n_iter", 1)), int(w.get("maxdiff", 0))
         # data parallel: every rank owns its own frames; bin sharded: every rank holds the SAME frames
-        ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=0 if self.shard else rank * B, out=frames.ptr, loc=A.DEVICE)
+        ctx.synth_frames(SEED, B, w["D"], w["Nx"], w["Ny"], b0=0 if self.shard else dp.frame_range(rank, world, B)[0], out=frames.ptr, loc=A.DEVICE)
         self.frames = frames
         host = torch.empty(B * self.n0, dtype=torch.float32).pin_memory()
         ctx.memcpy(host.data_ptr(), frames.ptr, B * self.n0 * 4, 1)
