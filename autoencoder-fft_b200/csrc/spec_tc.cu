@@ -530,12 +530,22 @@ __global__ void __launch_bounds__(128) binmajor_to_taps_kernel(const float2* __r
 // NL complex partial sums t[l] = sum_wy h(wy) z conj(Ey_l(wy)) (NL complex multiply-adds per bin instead of NK*NL real
 // pairs) and applies the NK row factors conj(Ex_k(wx)) once per row.  The h-weighted column factors of the slab sit in
 // shared memory.  Splits are over rows.
+constexpr int BT_ST = 16;  // bins per staging slot of the separable form (two slots per thread)
+__device__ __forceinline__ void bt_cp_async8(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// The spectrum values of a thread's kernel e are 8 bytes every E * 8 bytes: plain loads left the kernel bound by the memory
+// latency (the compiler sinks them next to their uses: one or two in flight per thread, 1.5-2.1 TB/s).  Every thread therefore
+// copies ITS next BT_ST bins into its own column of a shared-memory slot with cp.async while it works on the previous slot --
+// 16 to 32 loads in flight per thread, no barrier (a thread only reads what it copied itself).  The sums keep their order.
 template <int NK, int NL>
 __global__ void __launch_bounds__(128) binmajor_to_taps_sep_kernel(const float2* __restrict__ z, float* __restrict__ part, int E,
                                                                    int R, int C, int transpose, int Nx, int Ny, int ncols, int col0,
                                                                    const float2* __restrict__ twx,
                                                                    const float2* __restrict__ twy) {
-  extern __shared__ float2 phy[];  // [ncols][NL]
+  extern __shared__ __align__(16) float2 phy[];  // [ncols][NL], then the staging slots [2][BT_ST][128]
+  float2* ring = phy + (((size_t)ncols * NL + 1) & ~(size_t)1);
   for (int i = threadIdx.x; i < ncols * NL; i += blockDim.x) {
     const int wl = i / NL, l = i - wl * NL, wy = col0 + wl;
     const float h = (wy == 0 || wy == Ny / 2) ? 1.f : 2.f;
@@ -550,32 +560,51 @@ __global__ void __launch_bounds__(128) binmajor_to_taps_sep_kernel(const float2*
   float g[NK * NL];
 #pragma unroll
   for (int t = 0; t < NK * NL; t++) g[t] = 0.f;
-  for (int wx = r_lo; wx < r_hi; wx++) {
-    float2 t[NL];
+  const long long nq = (long long)(r_hi - r_lo) * ncols;      // bins of this CTA, row after row
+  const float2* zb = z + (long long)r_lo * ncols * E + e;
+  float2* mine = ring + threadIdx.x;
+  auto issue = [&](int slot, long long q0) {
 #pragma unroll
-    for (int l = 0; l < NL; l++) t[l] = make_float2(0.f, 0.f);
-    const float2* zr = z + (long long)wx * ncols * E + e;
+    for (int u = 0; u < BT_ST; u++)
+      if (q0 + u < nq) bt_cp_async8(mine + (slot * BT_ST + u) * 128, zb + (q0 + u) * E);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float2 t[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) t[l] = make_float2(0.f, 0.f);
+  int wl = 0, wx = r_lo, slot = 0;
+  if (nq > 0) issue(0, 0);
+  for (long long q0 = 0; q0 < nq; q0 += BT_ST, slot ^= 1) {
+    issue(slot ^ 1, q0 + BT_ST);  // (an empty group past the end keeps the group count uniform)
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
 #pragma unroll 4
-    for (int wl = 0; wl < ncols; wl++) {
-      const float2 v = __ldg(zr + (long long)wl * E);
+    for (int u = 0; u < BT_ST; u++) {
+      if (q0 + u >= nq) break;
+      const float2 v = mine[(slot * BT_ST + u) * 128];
 #pragma unroll
       for (int l = 0; l < NL; l++) {  // t[l] += v * conj(phy)
         const float2 ph = phy[wl * NL + l];
         t[l].x = fmaf(v.x, ph.x, fmaf(v.y, ph.y, t[l].x));
         t[l].y = fmaf(v.y, ph.x, fmaf(-v.x, ph.y, t[l].y));
       }
-    }
+      if (++wl == ncols) {  // end of a spectrum row: the NK row factors conj(Ex_k(wx)), once per row
 #pragma unroll
-    for (int k = 0; k < NK; k++) {
-      const float2 ex = __ldg(twx + (tw_index(wx, k - NK / 2, Nx)));
+        for (int k = 0; k < NK; k++) {
+          const float2 ex = __ldg(twx + (tw_index(wx, k - NK / 2, Nx)));
 #pragma unroll
-      for (int l = 0; l < NL; l++) g[k * NL + l] = fmaf(t[l].x, ex.x, fmaf(t[l].y, ex.y, g[k * NL + l]));  // Re(t conj(ex))
+          for (int l = 0; l < NL; l++) g[k * NL + l] = fmaf(t[l].x, ex.x, fmaf(t[l].y, ex.y, g[k * NL + l]));  // Re(t conj(ex))
+        }
+#pragma unroll
+        for (int l = 0; l < NL; l++) t[l] = make_float2(0.f, 0.f);
+        wl = 0; wx++;
+      }
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   int n = e;
   if (transpose) { const int r = e / C, c = e - r * C; n = c * R + r; }
 #pragma unroll
-  for (int t = 0; t < NK * NL; t++) part[((size_t)n * nsplit + sp) * (NK * NL) + t] = g[t];
+  for (int t2 = 0; t2 < NK * NL; t2++) part[((size_t)n * nsplit + sp) * (NK * NL) + t2] = g[t2];
 }
 
 __global__ void taps_final_kernel(const float* __restrict__ part, float* __restrict__ taps, long long total, int nsplit, int T,
@@ -592,25 +621,33 @@ __global__ void taps_final_kernel(const float* __restrict__ part, float* __restr
 // ---- DC-bin terms of gradient_k_io (:447-473) on bin-major data (bin 0 = the first block):
 //   db[m] = gs * sum_b Re G[b][m](0);  dp[d] = gs * sum_b Re E[b][d](0);
 //   dF^T[0][m][d] += fs * corr[m] * sum_b E[b][d](0)   (H-hat's bias correction, quirk F1; corr real)
-__global__ void dc_terms_kernel(const float* __restrict__ G, const float* __restrict__ E, const float* __restrict__ bias_b,
-                                float* __restrict__ dFt, float* __restrict__ db, float* __restrict__ dp, int B, int dM, int dD,
-                                float gs, float fs, float corr_scale) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < dM) {
-    double s = 0.0;
-    for (int b = 0; b < B; b++) s += (double)G[(size_t)b * 2 * dM + 2 * n];
-    db[n] = (float)(s * (double)gs);
-  } else if (n < dM + dD) {
-    const int d = n - dM;
-    double sr = 0.0, si = 0.0;
-    for (int b = 0; b < B; b++) { sr += (double)E[(size_t)b * 2 * dD + 2 * d]; si += (double)E[(size_t)b * 2 * dD + 2 * d + 1]; }
-    dp[d] = (float)(sr * (double)gs);
-    if (bias_b)
-      for (int m = 0; m < dM; m++) {
-        const double corr = (double)bias_b[m] * (double)corr_scale * (double)fs;
-        dFt[((size_t)m * dD + d) * 2] += (float)(corr * sr);
-        dFt[((size_t)m * dD + d) * 2 + 1] += (float)(corr * si);
-      }
+__global__ void __launch_bounds__(512) dc_terms_kernel(const float* __restrict__ G, const float* __restrict__ E,
+                                                       const float* __restrict__ bias_b, float* __restrict__ dFt, float* __restrict__ db,
+                                                       float* __restrict__ dp, int B, int dM, int dD, float gs, float fs,
+                                                       float corr_scale) {
+  // ONE CTA, two phases: the frame sums (a thread per channel), then the dM x dD corrections of dF^T spread over all threads
+  // (a thread per d walking the dM read-modify-writes one after the other took 90 us at 128 -> 256 channels)
+  extern __shared__ double dct_es[];  // [dD][2]: sum_b E[b][d](0)
+  for (int n = threadIdx.x; n < dM + dD; n += blockDim.x) {
+    if (n < dM) {
+      double s = 0.0;
+      for (int b = 0; b < B; b++) s += (double)G[(size_t)b * 2 * dM + 2 * n];
+      db[n] = (float)(s * (double)gs);
+    } else {
+      const int d = n - dM;
+      double sr = 0.0, si = 0.0;
+      for (int b = 0; b < B; b++) { sr += (double)E[(size_t)b * 2 * dD + 2 * d]; si += (double)E[(size_t)b * 2 * dD + 2 * d + 1]; }
+      dp[d] = (float)(sr * (double)gs);
+      dct_es[2 * d] = sr; dct_es[2 * d + 1] = si;
+    }
+  }
+  if (!bias_b) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < dM * dD; i += blockDim.x) {
+    const int m = i / dD, d = i - m * dD;
+    const double corr = (double)bias_b[m] * (double)corr_scale * (double)fs;
+    dFt[(size_t)i * 2] += (float)(corr * dct_es[2 * d]);
+    dFt[(size_t)i * 2 + 1] += (float)(corr * dct_es[2 * d + 1]);
   }
 }
 
@@ -903,7 +940,9 @@ int launch_binmajor_to_taps(aefft_ctx* ctx, int R, int C, int transpose, int Nk,
   const int T = Nk * Nl, E = R * C;
   AE_ARG(T == 25 || T == 9 || T == 49);
   const int etiles = (E + 127) / 128;
-  long long nsplit = (4LL * ctx->sm_count + etiles - 1) / etiles;
+  // CTAs per SM of the reduction grid (AEFFT_TAPS_SPLIT: development knob)
+  const int per_sm = getenv("AEFFT_TAPS_SPLIT") ? atoi(getenv("AEFFT_TAPS_SPLIT")) : 4;
+  long long nsplit = ((long long)(per_sm > 0 ? per_sm : 4) * ctx->sm_count + etiles - 1) / etiles;
   const bool sep = (Nk == Nl) && (Nk == 5 || Nk == 3 || Nk == 7) && !getenv("AEFFT_TAPS_NOSEP");
   const long long max_split = sep ? Nx : S / BT_BINS;
   if (nsplit > max_split) nsplit = max_split;
@@ -915,7 +954,7 @@ int launch_binmajor_to_taps(aefft_ctx* ctx, int R, int C, int transpose, int Nk,
   {
     ProfScope prof(ctx, "binmajor_to_taps", 4.0 * S * E * (sep ? 2.0 * Nl : (double)T), 8.0 * S * E);
     if (sep) {
-      const size_t smem = (size_t)ncols * Nl * sizeof(float2);
+      const size_t smem = ((((size_t)ncols * Nl + 1) & ~(size_t)1) + (size_t)2 * BT_ST * 128) * sizeof(float2);
       if (Nk == 5) {
         AE_TRY(ctx->ensure_dyn_smem((const void*)binmajor_to_taps_sep_kernel<5, 5>, smem));
         binmajor_to_taps_sep_kernel<5, 5><<<grid, 128, smem, ctx->stream>>>(z, part, E, R, C, transpose, Nx, Ny, ncols, col0, twx, twy);
@@ -1050,7 +1089,7 @@ int launch_bm_resize(aefft_ctx* ctx, long long rowlen, int Nx, int Ny, int Nxs, 
 
 int launch_tc_dc_terms(aefft_ctx* ctx, int B, int dM, int dD, const float* G, const float* E, const float* bias_b, float* dFt,
                        float* db, float* dp, float gs, float fs, float corr_scale) {
-  dc_terms_kernel<<<(dM + dD + 127) / 128, 128, 0, ctx->stream>>>(G, E, bias_b, dFt, db, dp, B, dM, dD, gs, fs, corr_scale);
+  dc_terms_kernel<<<1, 512, 2 * dD * sizeof(double), ctx->stream>>>(G, E, bias_b, dFt, db, dp, B, dM, dD, gs, fs, corr_scale);
   ctx->launches++;
   AE_CUDA(cudaGetLastError());
   return AEFFT_OK;

@@ -602,6 +602,7 @@ int launch_shrink(aefft_ctx* ctx, int64_t n_img, int Nx, int Ny, int Nk, int Nl,
 
 // ------------------------------------------------------------------------------------------------ pruned kernel DFTs
 constexpr int PD_MAXT = 8;  // taps per axis
+constexpr int ST_UB = 4;    // spectrum rows in flight per thread (spectrum_to_taps)
 
 // Both kernels are instantiated for the tap counts the reference's parameter file can produce (3, 5, 7 per axis) plus a
 // generic 8 x 8 variant; index arithmetic is 32-bit (bins per image < 2^31).
@@ -701,13 +702,32 @@ __global__ void __launch_bounds__(768) spectrum_to_taps_kernel(const float2* __r
     float2 b[TK];
 #pragma unroll
     for (int k = 0; k < TK; k++) b[k] = make_float2(0.f, 0.f);
-    for (int wx = r_lo; wx < r_hi; wx++) {
-      const float2 v = z[(size_t)wx * Nyr + wl];
+    // ST_UB rows in flight per thread before the first use (one dependent 8-byte load per row left the kernel latency
+    // bound at 0.8 TB/s); the sums keep their order
+    int wx = r_lo;
+    for (; wx + ST_UB <= r_hi; wx += ST_UB) {
+      float2 v[ST_UB];
+#pragma unroll
+      for (int u = 0; u < ST_UB; u++) v[u] = __ldg(z + (size_t)(wx + u) * Nyr + wl);
+#pragma unroll
+      for (int u = 0; u < ST_UB; u++) {
+#pragma unroll
+        for (int k = 0; k < TK; k++) {
+          if (k < nk) {
+            const float2 e = __ldg(twx + (tw_index(wx + u, k - nk / 2, Nx)));  // warp-uniform address
+            b[k].x = fmaf(v[u].x, e.x, fmaf(v[u].y, e.y, b[k].x));   // v * conj(e)
+            b[k].y = fmaf(v[u].y, e.x, fmaf(-v[u].x, e.y, b[k].y));
+          }
+        }
+      }
+    }
+    for (; wx < r_hi; wx++) {
+      const float2 v = __ldg(z + (size_t)wx * Nyr + wl);
 #pragma unroll
       for (int k = 0; k < TK; k++) {
         if (k < nk) {
-          const float2 e = __ldg(twx + (tw_index(wx, k - nk / 2, Nx)));  // warp-uniform address
-          b[k].x = fmaf(v.x, e.x, fmaf(v.y, e.y, b[k].x));   // v * conj(e)
+          const float2 e = __ldg(twx + (tw_index(wx, k - nk / 2, Nx)));
+          b[k].x = fmaf(v.x, e.x, fmaf(v.y, e.y, b[k].x));
           b[k].y = fmaf(v.y, e.x, fmaf(-v.x, e.y, b[k].y));
         }
       }
