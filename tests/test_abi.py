@@ -32,3 +32,40 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(A.AefftError) as e:
         A.Ctx(0)
     assert e.value.code == A.ERR_CUDA
+
+
+REF_SRC = "/root/reference/source"
+SHIM_FUNCS = ["Pool", "Init_conv", "SaveLoad_conv", "LoadParam", "Portion", "Conv", "backprop", "Conv_gpu", "backprop_gpu",
+              "backprop_gpu_cc", "act", "act1", "autoenc_fft", "kernel_pad", "backprop_fft"]
+
+
+def _mangled(nm_args, path):
+    import subprocess
+
+    out = subprocess.run(["nm"] + nm_args + [path], check=True, capture_output=True, text=True).stdout
+    return {ln.split()[-1] for ln in out.splitlines() if ln.strip()}
+
+
+def test_shim_exports_the_references_own_signatures(tmp_path):
+    """Drop-in at link level: a translation unit that includes the REFERENCE's headers (netlib.h, backproplib.h,
+    fft_backproplib.h, where they lie) and takes the address of every hot-path function leaves undefined C++ symbols whose
+    mangled names encode the full parameter lists; libaefft_shim.so must define every one of them.  Needs the reference
+    tree (this container); the GPU box has no /root/reference and skips."""
+    import subprocess
+
+    if not os.path.isdir(REF_SRC):
+        pytest.skip("reference headers not present on this machine")
+    shim = os.path.join(ROOT, "autoencoder-fft_b200", "libaefft_shim.so")
+    assert os.path.exists(shim), "libaefft_shim.so was not built"
+    src = tmp_path / "uses_reference_api.cpp"
+    body = "\n".join(f"  (const void*)&{f}," for f in SHIM_FUNCS)
+    src.write_text('#include <vector>\n#include <opencv2/opencv.hpp>\n#include "netlib.h"\n#include "backproplib.h"\n'
+                   f'#include "fft_backproplib.h"\nconst void* aefft_test_table[] = {{\n{body}\n}};\n')
+    obj = tmp_path / "uses_reference_api.o"
+    subprocess.run(["g++", "-std=c++11", "-c", "-I", os.path.join(ROOT, "oracle", "stub"), "-I", REF_SRC, str(src), "-o", str(obj)],
+                   check=True, capture_output=True, text=True)
+    wanted = {s for s in _mangled(["-u"], str(obj)) if s.startswith("_Z")}
+    assert len(wanted) == len(SHIM_FUNCS), wanted
+    defined = _mangled(["-D", "--defined-only"], shim)
+    missing = sorted(wanted - defined)
+    assert not missing, f"reference signatures the shim does not define: {missing}"
