@@ -51,3 +51,21 @@ def row_slab(rank: int, world: int, Nx: int):
     """(first row, row count) of every frame that `rank` row-transforms in the slab-decomposed 2-D R2C."""
     r0 = rank * Nx // world
     return r0, (rank + 1) * Nx // world - r0
+
+
+def slab_exchange_plan(rank: int, world: int, images_per_rank: int, Nx: int, Ny: int):
+    """Counts / offsets (in floats; complex = 2 floats) of the all-to-all that turns frame-sharded FULL half spectra
+    [images_per_rank][Nx][Ny//2+1] into this rank's column slab of ALL ranks' images -- the same arithmetic as the engine
+    (csrc/net_fft.cu, bin-sharded training step): the block sent to rank r is the slab bin_slab(r) of every local image,
+    [images_per_rank][Nx][ncols_r]; the blocks received, ordered by source rank, form [world * images_per_rank][Nx][ncols_me].
+    Returns (send_counts, send_offsets, recv_counts, recv_offsets)."""
+    _, my_nc = bin_slab(rank, world, Ny)
+    scount, soff, rcount, roff, so = [], [], [], [], 0
+    for r in range(world):
+        _, nc = bin_slab(r, world, Ny)
+        scount.append(2 * images_per_rank * Nx * nc)
+        soff.append(so)
+        so += scount[-1]
+        rcount.append(2 * images_per_rank * Nx * my_nc)
+        roff.append(r * rcount[-1])
+    return scount, soff, rcount, roff

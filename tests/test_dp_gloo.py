@@ -201,3 +201,62 @@ def test_two_rank_bin_sharded_kernel_gradient_equals_full_transform():
     want = np.array([[full[(k - Nk // 2) % Nx, (l - Nl // 2) % Ny] for l in range(Nl)] for k in range(Nk)])
     assert np.allclose(ret[0], want, rtol=1e-10, atol=1e-9)
     assert np.array_equal(ret[0], ret[1])
+
+
+def _a2a_worker(rank, world, port, ret):
+    import dp
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    B, dD, Nx, Ny = 3, 2, 8, 12          # Ny//2+1 = 7 columns: slabs of 3 and 4
+    img = B * dD
+    rng = np.random.default_rng(11)
+    frames = rng.standard_normal((world * B, dD, Nx, Ny))
+    b0, nb = dp.frame_range(rank, world, B)
+    mine = np.fft.rfft2(frames[b0:b0 + nb])                      # the data-parallel forward: FULL spectra of my frames
+    scount, soff, rcount, roff = dp.slab_exchange_plan(rank, world, img, Nx, Ny)
+    send = np.zeros(soff[-1] + scount[-1])
+    for r in range(world):                                       # launch_spec_slab: slab r of every local image, packed
+        c0, nc = dp.bin_slab(r, world, Ny)
+        blk = np.ascontiguousarray(mine[..., c0:c0 + nc]).reshape(img, Nx, nc)
+        send[soff[r]:soff[r] + scount[r]] = blk.view(np.float64).ravel()
+    # (gloo has no all_to_all on every build: the exchange goes through an all_gather of the send buffers and of their
+    # count / offset tables, and every rank then picks the block each source addressed to it -- what ncclSend/Recv delivers)
+    outs = [None] * world
+    pad = max(world * max(scount), 1)
+    buf = torch.zeros(pad, dtype=torch.float64)
+    buf[:send.size] = torch.from_numpy(send)
+    meta = torch.tensor(scount + soff, dtype=torch.int64)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    dist.all_gather(metas, meta)
+    for src in range(world):
+        cnt, off = int(metas[src][rank]), int(metas[src][world + rank])
+        assert cnt == rcount[src]
+        outs[src] = bufs[src][off:off + cnt]
+    recv = np.zeros(roff[-1] + rcount[-1])
+    for src in range(world):
+        recv[roff[src]:roff[src] + rcount[src]] = outs[src].numpy()
+    ret[rank] = recv
+    dist.destroy_process_group()
+
+
+def test_two_rank_slab_exchange_yields_the_frame_major_slab():
+    """The all-to-all of the bin-sharded step (csrc/net_fft.cu; plan restated in dp.slab_exchange_plan): after it every rank
+    holds [world * B][dD][Nx][its columns] of the GLOBAL batch, frames in global order -- exactly the slab of the global
+    spectrum, with nothing but the exchange's own counts and offsets."""
+    import dp
+
+    world, port = 2, 33500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_a2a_worker, args=(world, port, ret), nprocs=world, join=True)
+    B, dD, Nx, Ny = 3, 2, 8, 12
+    rng = np.random.default_rng(11)
+    full = np.fft.rfft2(rng.standard_normal((world * B, dD, Nx, Ny)))
+    for rank in range(world):
+        c0, nc = dp.bin_slab(rank, world, Ny)
+        got = ret[rank].view(np.complex128).reshape(world * B, dD, Nx, nc)
+        assert np.array_equal(got, full[..., c0:c0 + nc]), rank
